@@ -1,0 +1,181 @@
+/*
+ * sake_b200.h — C ABI of libsake_b200.so: the B200 (sm_100a) implementation of SAKE's dense
+ * spatial-attention message-passing layer (forward + backward).
+ *
+ * The reference (ArnNag/sake) is pure Python/JAX/flax and has NO plugin / FFI layer of its own;
+ * the only interface the hot path sits behind is the flax module API
+ *     sake/layers.py:42-52,188-235   DenseSAKELayer.__call__(h, x, v=None, mask=None, he=None)
+ *     sake/models.py:11-61           DenseSAKEModel.__call__
+ * so this header is the boundary a JAX custom call (XLA FFI) or any other host binds.  Each entry
+ * point cites the reference code it replaces.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all tensors are dense row-major fp32 DEVICE buffers.
+ *   - The callee never allocates, frees or retains caller memory; outputs, `saved` and `scratch`
+ *     are caller-allocated (sizes from the *_bytes queries).  Weights are read every call.
+ *   - Enqueue-only on the caller's stream: no host synchronisation, CUDA-graph capturable.
+ *   - Return 0 on success, a negative SAKE_E* code on error; sake_last_error() gives the message
+ *     (thread-local).  Unsupported configurations are errors — there is no CPU fallback.
+ *   - Parameter gradients are ACCUMULATED (+=) into the SakeLayerGrads buffers.
+ */
+#ifndef SAKE_B200_H_
+#define SAKE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sake_stream_t; /* cudaStream_t */
+
+enum {
+  SAKE_OK = 0,
+  SAKE_EINVAL = -1,       /* bad dims / null pointer / too-small buffer */
+  SAKE_EUNSUPPORTED = -2, /* configuration outside what the kernels implement */
+  SAKE_ECUDA = -3         /* a CUDA runtime call failed (message has the CUDA error string) */
+};
+
+/* flags (SakeDims.flags) — mirror the module fields / call arguments of DenseSAKELayer */
+enum {
+  SAKE_UPDATE = 1,       /* DenseSAKELayer.update (sake/layers.py:46,217)                      */
+  SAKE_HAS_V = 2,        /* v argument is not None (sake/layers.py:226-229)                    */
+  SAKE_HAS_MASK = 4,     /* mask argument is not None, float [B,N,N]                           */
+  SAKE_NO_SPATIAL = 8    /* use_spatial_attention=False (sake/layers.py:210-212)              */
+};
+
+/* precision / engine (SakeDims.engine) */
+enum {
+  SAKE_ENGINE_AUTO = 0,   /* tcgen05 3xTF32 when the shape allows, else the generic fp32 path   */
+  SAKE_ENGINE_FP32 = 1,   /* generic CUDA-core fp32 kernels, any H / A / K                      */
+  SAKE_ENGINE_TF32X3 = 2, /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs) — fp32-parity mode     */
+  SAKE_ENGINE_BF16 = 3    /* tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate) — fast mode  */
+};
+
+typedef struct SakeDims {
+  int32_t B;      /* number of molecules (all leading batch dims flattened)                      */
+  int32_t N;      /* atoms per molecule (padded width)                                           */
+  int32_t H;      /* hidden_features == in_features == out_features (residual, layers.py:150)   */
+  int32_t A;      /* n_heads (layers.py:45)                                                      */
+  int32_t K;      /* number of RBFs, kernel_features (layers.py:14) — 50 in every script        */
+  int32_t flags;  /* SAKE_UPDATE | SAKE_HAS_V | SAKE_HAS_MASK | SAKE_NO_SPATIAL                  */
+  int32_t engine; /* SAKE_ENGINE_*                                                               */
+  int32_t reserved;
+} SakeDims;
+
+/* Parameters of one DenseSAKELayer, flax layouts (kernel = [in, out]); SURVEY Appendix C.
+ * C = A*H.  Pointers that a configuration does not use may be NULL. */
+typedef struct SakeLayerParams {
+  const float* rbf_means;       /* edge_model/kernel/means            [K]            utils.py:37 */
+  const float* rbf_betas;       /* edge_model/kernel/betas            [K]            utils.py:43 */
+  const float* mlp_in_kernel;   /* edge_model/mlp_in/kernel           [2H, K]       layers.py:19 */
+  const float* mlp_in_bias;     /*                                    [K]                       */
+  const float* mlp_out0_kernel; /* edge_model/mlp_out/layers_0/kernel [2H+K+1, H]   layers.py:22 */
+  const float* mlp_out0_bias;   /*                                    [H]                       */
+  const float* mlp_out2_kernel; /* edge_model/mlp_out/layers_2/kernel [H, H]        layers.py:24 */
+  const float* mlp_out2_bias;   /*                                    [H]                       */
+  const float* sem_kernel;      /* semantic_attention_mlp/layers_0    [H, A]        layers.py:80 */
+  const float* sem_bias;        /*                                    [A]                       */
+  const float* x_mixing_kernel; /* x_mixing/layers_0/kernel           [C, C]        layers.py:95 */
+  const float* post0_kernel;    /* post_norm_mlp/layers_0             [C, H]        layers.py:87 */
+  const float* post0_bias;      /*                                    [H]                       */
+  const float* post2_kernel;    /* post_norm_mlp/layers_2             [H, H]        layers.py:89 */
+  const float* post2_bias;      /*                                    [H]                       */
+  const float* node0_kernel;    /* node_mlp/layers_0                  [H+C+H, H]    layers.py:61 */
+  const float* node0_bias;      /*                                    [H]                       */
+  const float* node2_kernel;    /* node_mlp/layers_2                  [H, H]        layers.py:63 */
+  const float* node2_bias;      /*                                    [H]                       */
+  const float* v_mixing_kernel; /* v_mixing/kernel                    [C, 1]        layers.py:94 */
+  const float* vel0_kernel;     /* velocity_mlp/layers_0              [H, H]        layers.py:71 */
+  const float* vel0_bias;       /*                                    [H]                       */
+  const float* vel2_kernel;     /* velocity_mlp/layers_2/kernel       [H, 1]        layers.py:73 */
+} SakeLayerParams;
+
+/* Same field order as SakeLayerParams; gradient buffers (accumulated).  log_gamma has no
+ * gradient in the dense layer (it is never read: layers.py:97-105 vs :107-235). */
+typedef struct SakeLayerGrads {
+  float* rbf_means;
+  float* rbf_betas;
+  float* mlp_in_kernel;
+  float* mlp_in_bias;
+  float* mlp_out0_kernel;
+  float* mlp_out0_bias;
+  float* mlp_out2_kernel;
+  float* mlp_out2_bias;
+  float* sem_kernel;
+  float* sem_bias;
+  float* x_mixing_kernel;
+  float* post0_kernel;
+  float* post0_bias;
+  float* post2_kernel;
+  float* post2_bias;
+  float* node0_kernel;
+  float* node0_bias;
+  float* node2_kernel;
+  float* node2_bias;
+  float* v_mixing_kernel;
+  float* vel0_kernel;
+  float* vel0_bias;
+  float* vel2_kernel;
+} SakeLayerGrads;
+
+/* Library / build information. */
+const char* sake_version(void);
+const char* sake_last_error(void);
+
+/* Which engine SAKE_ENGINE_AUTO resolves to for these dims (one of SAKE_ENGINE_*; <0 on error). */
+int sake_resolve_engine(const SakeDims* dims);
+
+/* Bytes of the `saved` buffer: what sake_layer_fwd leaves for sake_layer_bwd (edge features
+ * e[B,N,N,H], attention att[B,N,N,A], per-node projections and reductions).  Nothing O(N^2*C). */
+size_t sake_layer_saved_bytes(const SakeDims* dims);
+/* Bytes of the `scratch` buffer (temporaries; may be shared by all layers on one stream).
+ * for_backward != 0 sizes it for sake_layer_bwd (with_param_grads selects the training variant). */
+size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with_param_grads);
+
+/* DenseSAKELayer.__call__ (sake/layers.py:188-235) with he=None, cutoff=None.
+ *   h [B,N,H], x [B,N,3], v [B,N,3] or NULL, mask [B,N,N] float or NULL
+ *   -> h_out [B,N,H], x_out [B,N,3], v_out [B,N,3]
+ * Coordinates are always 3 wide; 2-D systems (scripts/dw4) pad z = 0 on the host side.
+ * With SAKE_UPDATE clear, x_out / v_out are plain copies of x / v (v_out untouched if v NULL).
+ * Guarded masking: a row whose attention normaliser is 0 gets att = 0 (the reference yields
+ * 0/0 = NaN there, layers.py:178-180); every other value follows the reference formulas. */
+int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
+                   const float* h, const float* x, const float* v, const float* mask,
+                   float* h_out, float* x_out, float* v_out,
+                   void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
+                   sake_stream_t stream);
+
+/* Vector-Jacobian product of sake_layer_fwd (what jax.grad / jax.vjp of the layer computes:
+ * scripts/md17/run.py:58 forces, scripts/qm9/run.py:84-89 parameter gradients).
+ *   cotangents dh_out [B,N,H], dx_out [B,N,3] (NULL = 0), dv_out [B,N,3] (NULL = 0)
+ *   -> dh [B,N,H], dx [B,N,3], dv [B,N,3] (dv may be NULL when v is NULL)
+ *   grads: NULL for the forces-only (inference) variant, else accumulated parameter gradients.
+ * `saved` must be the buffer written by sake_layer_fwd for the same inputs. */
+int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params,
+                   const float* h, const float* x, const float* v, const float* mask,
+                   const void* saved, size_t saved_bytes,
+                   const float* dh_out, const float* dx_out, const float* dv_out,
+                   float* dh, float* dx, float* dv, const SakeLayerGrads* grads,
+                   void* scratch, size_t scratch_bytes, sake_stream_t stream);
+
+/* nn.Dense (+ optional silu) over the last axis — embedding_in / embedding_out of
+ * DenseSAKEModel (sake/models.py:24-31,57,60).  y[rows,out] = act(x[rows,in] @ kernel + bias).
+ * act: 0 = identity, 1 = silu.  bias may be NULL. */
+int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act,
+                   const float* x, const float* kernel, const float* bias, float* y,
+                   sake_stream_t stream);
+/* VJP of sake_dense_fwd: dx (may be NULL), and accumulated dkernel / dbias (may be NULL). */
+int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act,
+                   const float* x, const float* kernel, const float* bias, const float* dy,
+                   float* dx, float* dkernel, float* dbias, sake_stream_t stream);
+
+/* Self-test of the tcgen05 building blocks (descriptor encodings, swizzled operand images,
+ * TMEM load layout) on the current device; returns 0 when every check passes. max_abs_err out. */
+int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAKE_B200_H_ */

@@ -1,0 +1,81 @@
+"""ctypes binding of libsake_b200.so (the C ABI declared in include/sake_b200.h)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsake_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C sake_b200/csrc`). sake_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+# enums (include/sake_b200.h)
+SAKE_UPDATE, SAKE_HAS_V, SAKE_HAS_MASK, SAKE_NO_SPATIAL = 1, 2, 4, 8
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32X3, ENGINE_BF16 = 0, 1, 2, 3
+ENGINES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32x3": ENGINE_TF32X3, "bf16": ENGINE_BF16}
+ENGINE_NAMES = {v: k for k, v in ENGINES.items()}
+
+
+class SakeDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "N", "H", "A", "K", "flags", "engine", "reserved")]
+
+
+PARAM_FIELDS = (
+    "rbf_means", "rbf_betas", "mlp_in_kernel", "mlp_in_bias", "mlp_out0_kernel", "mlp_out0_bias",
+    "mlp_out2_kernel", "mlp_out2_bias", "sem_kernel", "sem_bias", "x_mixing_kernel", "post0_kernel",
+    "post0_bias", "post2_kernel", "post2_bias", "node0_kernel", "node0_bias", "node2_kernel",
+    "node2_bias", "v_mixing_kernel", "vel0_kernel", "vel0_bias", "vel2_kernel",
+)
+
+
+class SakeLayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class SakeLayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+_vp, _sz, _i32, _i64 = C.c_void_p, C.c_size_t, C.c_int32, C.c_int64
+_DP = C.POINTER(SakeDims)
+
+lib.sake_version.restype = C.c_char_p
+lib.sake_last_error.restype = C.c_char_p
+lib.sake_resolve_engine.argtypes = [_DP]
+lib.sake_resolve_engine.restype = C.c_int
+lib.sake_layer_saved_bytes.argtypes = [_DP]
+lib.sake_layer_saved_bytes.restype = _sz
+lib.sake_layer_scratch_bytes.argtypes = [_DP, C.c_int, C.c_int]
+lib.sake_layer_scratch_bytes.restype = _sz
+lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _sz, _vp, _sz, _vp]
+lib.sake_layer_fwd.restype = C.c_int
+lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _sz,
+                               _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SakeLayerGrads), _vp, _sz, _vp]
+lib.sake_layer_bwd.restype = C.c_int
+lib.sake_dense_fwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
+lib.sake_dense_fwd.restype = C.c_int
+lib.sake_dense_bwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.sake_dense_bwd.restype = C.c_int
+lib.sake_selftest_tcgen05.argtypes = [C.POINTER(C.c_float), _vp]
+lib.sake_selftest_tcgen05.restype = C.c_int
+
+EXPORTS = ("sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
+           "sake_layer_scratch_bytes", "sake_layer_fwd", "sake_layer_bwd", "sake_dense_fwd",
+           "sake_dense_bwd", "sake_selftest_tcgen05")
+
+
+class SakeError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise SakeError(f"{what} failed (code {rc}): {lib.sake_last_error().decode()}")
+
+
+def version():
+    return lib.sake_version().decode()

@@ -1,0 +1,211 @@
+// C ABI of libsake_b200.so (see include/sake_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace sake {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int dense_fwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b, float* y,
+              cudaStream_t st);
+int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
+              const float* dy, float* dx, float* dw, float* db, cudaStream_t st);
+int tc_selftest(float* max_abs_err, cudaStream_t st);
+
+static int make_dims(const SakeDims* s, Dims* d) {
+  if (!s) { set_error("dims is NULL"); return SAKE_EINVAL; }
+  if (s->B < 0 || s->N <= 0 || s->H <= 0 || s->A <= 0 || s->K <= 0) {
+    set_error("bad dims B=%d N=%d H=%d A=%d K=%d", s->B, s->N, s->H, s->A, s->K);
+    return SAKE_EINVAL;
+  }
+  if ((long long)s->B * s->N > 0x7fffffffLL / 4) { set_error("B*N too large"); return SAKE_EUNSUPPORTED; }
+  d->B = s->B; d->N = s->N; d->H = s->H; d->A = s->A; d->K = s->K;
+  d->C = s->A * s->H;
+  d->R = s->B * s->N;
+  d->P = (long long)d->R * s->N;
+  d->NP = 2 * s->K + 2 * s->H;
+  d->update = (s->flags & SAKE_UPDATE) != 0;
+  d->has_v = (s->flags & SAKE_HAS_V) != 0;
+  d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
+  d->spatial = (s->flags & SAKE_NO_SPATIAL) == 0;
+  return 0;
+}
+
+static int resolve_engine(const SakeDims* s, const Dims& d) {
+  int e = s->engine;
+  if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_TF32X3 : SAKE_ENGINE_FP32;
+  if (e == SAKE_ENGINE_FP32) return e;
+  if (e == SAKE_ENGINE_TF32X3 || e == SAKE_ENGINE_BF16) {
+    if (!tc_supported(d)) {
+      set_error("tcgen05 engine needs H=64, A=4 (C=256); got H=%d A=%d", d.H, d.A);
+      return SAKE_EUNSUPPORTED;
+    }
+    return e;
+  }
+  set_error("unknown engine %d", e);
+  return SAKE_EINVAL;
+}
+
+struct SavedLayout { size_t e, att, ssum, he, nodeproj, total; };
+static SavedLayout saved_layout(const Dims& d) {
+  SavedLayout L;
+  size_t o = 0;
+  L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
+  L.att = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
+  L.ssum = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
+  L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
+  L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
+  L.total = o;
+  return L;
+}
+static Saved carve_saved(const Dims& d, void* base) {
+  SavedLayout L = saved_layout(d);
+  char* b = (char*)base;
+  Saved s;
+  s.e = (float*)(b + L.e); s.att = (float*)(b + L.att); s.ssum = (float*)(b + L.ssum);
+  s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj);
+  return s;
+}
+
+struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, total; };
+static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
+  ScratchLayout L;
+  memset(&L, 0, sizeof(L));
+  size_t o = 0;
+  if (for_backward) {
+    L.T = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
+    L.ghe = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
+    L.ge = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
+    L.gatt = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
+    L.gdir = o; o += align_up(sizeof(float) * (size_t)d.P * 3);
+    L.gproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
+    L.wxT = o; o += align_up(sizeof(float) * (size_t)d.C * d.C);
+    L.gZ = o;
+    if (with_grads && engine == SAKE_ENGINE_FP32) o += align_up(sizeof(float) * (size_t)d.P * d.C);
+  }
+  L.tc = o;
+  if (engine != SAKE_ENGINE_FP32) o += align_up(tc_scratch_bytes(d, engine, for_backward, with_grads));
+  L.total = o + 256;
+  return L;
+}
+
+}  // namespace sake
+
+using namespace sake;
+
+extern "C" {
+
+const char* sake_version(void) { return "sake_b200 0.1 (sm_100a)"; }
+const char* sake_last_error(void) { return g_err; }
+
+int sake_resolve_engine(const SakeDims* dims) {
+  Dims d;
+  int rc = make_dims(dims, &d);
+  if (rc) return rc;
+  return resolve_engine(dims, d);
+}
+
+size_t sake_layer_saved_bytes(const SakeDims* dims) {
+  Dims d;
+  if (make_dims(dims, &d)) return 0;
+  return saved_layout(d).total;
+}
+
+size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with_param_grads) {
+  Dims d;
+  if (make_dims(dims, &d)) return 0;
+  int e = resolve_engine(dims, d);
+  if (e < 0) return 0;
+  return scratch_layout(d, e, for_backward, with_param_grads).total;
+}
+
+int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
+                   const float* v, const float* mask, float* h_out, float* x_out, float* v_out, void* saved,
+                   size_t saved_bytes, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
+  Dims d;
+  int rc = make_dims(dims, &d);
+  if (rc) return rc;
+  if (!params || !h || !x || !h_out || !x_out || !saved) { set_error("sake_layer_fwd: NULL argument"); return SAKE_EINVAL; }
+  if (d.has_v != (v != nullptr)) { set_error("SAKE_HAS_V flag does not match v pointer"); return SAKE_EINVAL; }
+  if (d.has_mask != (mask != nullptr)) { set_error("SAKE_HAS_MASK flag does not match mask pointer"); return SAKE_EINVAL; }
+  if (d.update && !v_out) { set_error("update=True needs v_out"); return SAKE_EINVAL; }
+  int engine = resolve_engine(dims, d);
+  if (engine < 0) return engine;
+  if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small: %zu < %zu", saved_bytes, saved_layout(d).total); return SAKE_EINVAL; }
+  ScratchLayout SL = scratch_layout(d, engine, 0, 0);
+  if (SL.total > 256 && (!scratch || scratch_bytes < SL.total)) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
+  if (d.R == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(d, saved);
+  if ((rc = gen_fwd_pre(d, *params, h, x, mask, sv, st))) return rc;
+  if (!d.spatial) {
+    SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
+  } else if (engine == SAKE_ENGINE_FP32) {
+    if ((rc = gen_mix_fwd(d, *params, x, mask, sv, st))) return rc;
+  } else {
+    if ((rc = tc_mix_fwd(d, *params, x, mask, sv, (char*)scratch + SL.tc, engine, st))) return rc;
+  }
+  return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
+}
+
+int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
+                   const float* v, const float* mask, const void* saved, size_t saved_bytes, const float* dh_out,
+                   const float* dx_out, const float* dv_out, float* dh, float* dx, float* dv,
+                   const SakeLayerGrads* grads, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
+  Dims d;
+  int rc = make_dims(dims, &d);
+  if (rc) return rc;
+  if (!params || !h || !x || !saved || !dh_out || !dh || !dx || !scratch) { set_error("sake_layer_bwd: NULL argument"); return SAKE_EINVAL; }
+  if (d.has_v != (v != nullptr)) { set_error("SAKE_HAS_V flag does not match v pointer"); return SAKE_EINVAL; }
+  if (d.has_mask != (mask != nullptr)) { set_error("SAKE_HAS_MASK flag does not match mask pointer"); return SAKE_EINVAL; }
+  if (d.has_v && !dv) { set_error("v given but dv is NULL"); return SAKE_EINVAL; }
+  int engine = resolve_engine(dims, d);
+  if (engine < 0) return engine;
+  if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
+  ScratchLayout SL = scratch_layout(d, engine, 1, grads != nullptr);
+  if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
+  if (d.R == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(d, const_cast<void*>(saved));
+  char* b = (char*)scratch;
+  BwdScratch sc;
+  sc.T = (float*)(b + SL.T); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
+  sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
+  sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ);
+  if ((rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st)))
+    return rc;
+  float* gWx = grads ? grads->x_mixing_kernel : nullptr;
+  if (engine == SAKE_ENGINE_FP32 || !d.spatial) {
+    if ((rc = gen_mix_bwd(d, *params, x, mask, sv, sc, gWx, st))) return rc;
+  } else {
+    if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, st))) return rc;
+  }
+  return gen_bwd_post(d, *params, h, x, mask, sv, dh, dx, grads, sc, st);
+}
+
+int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,
+                   const float* kernel, const float* bias, float* y, sake_stream_t stream) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !y) { set_error("sake_dense_fwd: bad argument"); return SAKE_EINVAL; }
+  return dense_fwd(rows, in_features, out_features, act, x, kernel, bias, y, (cudaStream_t)stream);
+}
+
+int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,
+                   const float* kernel, const float* bias, const float* dy, float* dx, float* dkernel,
+                   float* dbias, sake_stream_t stream) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !dy) { set_error("sake_dense_bwd: bad argument"); return SAKE_EINVAL; }
+  return dense_bwd(rows, in_features, out_features, act, x, kernel, bias, dy, dx, dkernel, dbias, (cudaStream_t)stream);
+}
+
+int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream) {
+  return tc_selftest(max_abs_err, (cudaStream_t)stream);
+}
+
+}  // extern "C"

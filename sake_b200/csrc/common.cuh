@@ -1,0 +1,101 @@
+// Shared definitions for libsake_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/sake_b200.h"
+
+namespace sake {
+
+// Resolved problem description handed to every kernel by value.
+struct Dims {
+  int B, N, H, A, K, C;   // C = A*H
+  int R;                  // rows = B*N (one row per receiving atom i)
+  long long P;            // pairs = R*N
+  int NP;                 // per-node projection width = 2K + 2H
+  int update, has_v, has_mask, spatial;
+};
+
+// Layout of the per-node projection buffer nodeproj[R][NP]:
+//   [0,K)        uj = h @ W_in[0:H]            (sender part of mlp_in,   layers.py:30)
+//   [K,2K)       ui = h @ W_in[H:2H] + b_in    (receiver part)
+//   [2K,2K+H)    pj = h @ W_1[0:H]             (sender part of mlp_out[0], layers.py:33-38)
+//   [2K+H,2K+2H) pi = h @ W_1[H:2H] + b_1      (receiver part)
+// (get_h_cat_ht, functional.py:33-44, is never materialised: Dense on [h_j | h_i] is separable.)
+
+// `saved` buffer (fwd -> bwd), all fp32:
+struct Saved {
+  float* e;         // [P,H]   edge features h_e_mtx (layers.py:204)
+  float* att;       // [P,A]   combined attention (layers.py:205); holds logits between kernels
+  float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
+  float* he;        // [R,C]   aggregate (layers.py:135-140)
+  float* nodeproj;  // [R,NP]
+};
+
+// `scratch` buffer for the backward pass
+struct BwdScratch {
+  float* T;         // [R,C,3] cotangent of ssum
+  float* ghe;       // [R,C]   cotangent of he
+  float* ge;        // [P,H]   cotangent of e
+  float* gatt;      // [P,A]   cotangent of att, then of the pre-celu logits q
+  float* gdir;      // [P,3]   cotangent of the unit direction
+  float* gproj;     // [R,NP]  cotangent of nodeproj
+  float* wxT;       // [C,C]   x_mixing kernel transposed
+  float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (generic dW path only)
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// d silu / dx
+__device__ __forceinline__ float dsiluf_(float x) {
+  float s = sigmoidf_(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+// nn.celu(alpha=2): max(x,0) + 2*expm1(min(x,0)/2)   (layers.py:81)
+__device__ __forceinline__ float celu2f_(float x) { return x > 0.f ? x : 2.0f * expm1f(0.5f * x); }
+__device__ __forceinline__ float dcelu2f_(float x) { return x > 0.f ? 1.0f : expf(0.5f * x); }
+
+void set_error(const char* fmt, ...);
+
+#define SAKE_CUDA_CHECK(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      sake::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SAKE_ECUDA;                                                             \
+    }                                                                                \
+  } while (0)
+
+// ---- generic fp32 engine ------------------------------------------------------------------
+int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
+                const Saved& sv, cudaStream_t st);
+int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                cudaStream_t st);
+int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv,
+                  cudaStream_t st);
+// backward, in execution order
+int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                      const float* mask, const Saved& sv, const float* dh_out, const float* dx_out,
+                      const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
+                      const BwdScratch& sc, cudaStream_t st);
+int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                const BwdScratch& sc, float* gWx, cudaStream_t st);
+int gen_bwd_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
+                 const Saved& sv, float* dh, float* dx, const SakeLayerGrads* g, const BwdScratch& sc,
+                 cudaStream_t st);
+
+// ---- tcgen05 engine (x_mixing GEMM family) -------------------------------------------------
+// mix forward: ssum[R,C,3] from e, att, x (replaces the generic k_mix_fwd)
+int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
+               const Saved& sv, void* tc_scratch, int engine, cudaStream_t st);
+// mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
+int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
+               const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine,
+               cudaStream_t st);
+size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads);
+bool tc_supported(const Dims& d);
+
+}  // namespace sake

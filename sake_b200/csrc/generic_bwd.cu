@@ -1,0 +1,898 @@
+// Generic fp32 CUDA-core backward (VJP) of DenseSAKELayer.  Mirrors generic_fwd.cu in reverse:
+//   node_post_bwd -> mix_bwd -> attn_bwd -> edge_bwd -> node_pre_bwd   (+ x_mixing dW GEMM)
+// Derivation: SURVEY Appendix B; every forward formula cites sake/layers.py in generic_fwd.cu.
+#include "common.cuh"
+
+namespace sake {
+
+static constexpr int NODES = 8;
+static constexpr int PJ = 16;
+static constexpr int MJ = 8;
+
+// gW[r][f] += sum_n X[n][r] * G[n][f]   (X: smem [NODES][ldx], G: smem [NODES][out])
+__device__ __forceinline__ void accum_outer(float* gW, const float* X, int ldx, int in, const float* G, int out,
+                                            int nn) {
+  for (int t = threadIdx.x; t < in * out; t += blockDim.x) {
+    const int r = t / out, f = t % out;
+    float s = 0.f;
+    for (int n = 0; n < nn; ++n) s = fmaf(X[n * ldx + r], G[n * out + f], s);
+    atomicAdd(gW + t, s);
+  }
+}
+__device__ __forceinline__ void accum_bias(float* gb, const float* G, int out, int nn) {
+  for (int f = threadIdx.x; f < out; f += blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < nn; ++n) s += G[n * out + f];
+    atomicAdd(gb + f, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// node_post_bwd
+// ------------------------------------------------------------------------------------------
+size_t node_post_bwd_smem_bytes(const Dims& d) {
+  return sizeof(float) * (NODES * (2 * d.C + 13 * d.H) + 8 * NODES + 64);
+}
+
+__global__ void __launch_bounds__(256) k_node_post_bwd(
+    Dims d, const SakeLayerParams p, const float* __restrict__ h, const float* __restrict__ v,
+    const float* __restrict__ mask, const float* __restrict__ ssum, const float* __restrict__ he_in,
+    const float* __restrict__ dh_out, const float* __restrict__ dx_out, const float* __restrict__ dv_out,
+    float* __restrict__ dh, float* __restrict__ dx, float* __restrict__ dv, float* __restrict__ T,
+    float* __restrict__ ghe, SakeLayerGrads g, int want_grads) {
+  extern __shared__ float sm[];
+  const int H = d.H, C = d.C, N = d.N;
+  float* nrm = sm;                   // [NODES][C]  (later: g_nrm)
+  float* hes = nrm + NODES * C;      // [NODES][C]
+  float* hin = hes + NODES * C;      // [NODES][H] each below
+  float* tp1 = hin + NODES * H;
+  float* tp2 = tp1 + NODES * H;
+  float* t1 = tp2 + NODES * H;
+  float* t2 = t1 + NODES * H;
+  float* hout = t2 + NODES * H;
+  float* tv = hout + NODES * H;
+  float* ghout = tv + NODES * H;
+  float* gt2 = ghout + NODES * H;
+  float* gt1 = gt2 + NODES * H;
+  float* gtp2 = gt1 + NODES * H;
+  float* gtp1 = gtp2 + NODES * H;
+  float* gtv = gtp1 + NODES * H;
+  float* den = gtv + NODES * H;      // [NODES]
+  float* den2 = den + NODES;         // [NODES]
+  float* gy = den2 + NODES;          // [NODES]
+  float* gate = gy + NODES;          // [NODES]
+  float* gdv = gate + NODES;         // [NODES][3] (+pad)
+  const int r0 = blockIdx.x * NODES;
+  const int nn = min(NODES, d.R - r0);
+
+  // ---------------- recompute forward ----------------
+  if (threadIdx.x < NODES) {
+    float dn = (float)N, dn2 = (float)N;
+    if (mask && threadIdx.x < nn) {
+      float ms = 0.f;
+      for (int j = 0; j < N; ++j) ms += mask[(size_t)(r0 + threadIdx.x) * N + j];
+      dn = ms + 1e-8f;
+      dn2 = ms + 1e-10f;
+    }
+    den[threadIdx.x] = dn;
+    den2[threadIdx.x] = dn2;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
+    const int n = t / C, c = t % C;
+    float nr = 0.f, hv = 0.f;
+    if (n < nn) {
+      const float* sp = ssum + ((size_t)(r0 + n) * C + c) * 3;
+      float inv = 1.0f / den[n];
+      float a0 = sp[0] * inv, a1 = sp[1] * inv, a2 = sp[2] * inv;
+      nr = a0 * a0 + a1 * a1 + a2 * a2;
+      hv = he_in[(size_t)(r0 + n) * C + c];
+    }
+    nrm[t] = nr;
+    hes[t] = hv;
+  }
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H;
+    hin[t] = n < nn ? h[(size_t)r0 * H + t] : 0.f;
+    ghout[t] = n < nn ? dh_out[(size_t)r0 * H + t] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.post0_bias[f];
+    for (int c = 0; c < C; ++c) acc = fmaf(nrm[n * C + c], p.post0_kernel[(size_t)c * H + f], acc);
+    tp1[t] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.post2_bias[f];
+    for (int q = 0; q < H; ++q) acc = fmaf(siluf_(tp1[n * H + q]), p.post2_kernel[(size_t)q * H + f], acc);
+    tp2[t] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.node0_bias[f];
+    const float* w = p.node0_kernel + f;
+    for (int q = 0; q < H; ++q) acc = fmaf(hin[n * H + q], w[(size_t)q * H], acc);
+    w += (size_t)H * H;
+    for (int c = 0; c < C; ++c) acc = fmaf(hes[n * C + c], w[(size_t)c * H], acc);
+    w += (size_t)C * H;
+    if (d.spatial)
+      for (int q = 0; q < H; ++q) acc = fmaf(siluf_(tp2[n * H + q]), w[(size_t)q * H], acc);
+    t1[t] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.node2_bias[f];
+    for (int q = 0; q < H; ++q) acc = fmaf(siluf_(t1[n * H + q]), p.node2_kernel[(size_t)q * H + f], acc);
+    t2[t] = acc;
+    hout[t] = hin[t] + siluf_(acc);
+  }
+  __syncthreads();
+
+  // ---------------- velocity / position update backward ----------------
+  const bool upd = d.update != 0, hv = d.has_v != 0;
+  if (upd && hv) {
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+      const int n = t / H, f = t % H;
+      float acc = p.vel0_bias[f];
+      for (int q = 0; q < H; ++q) acc = fmaf(hout[n * H + q], p.vel0_kernel[(size_t)q * H + f], acc);
+      tv[t] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NODES) {
+    const int n = threadIdx.x;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gyv = 0.f, gt = 0.f;
+    if (n < nn) {
+      const size_t row = (size_t)(r0 + n);
+      float dxo0 = dx_out ? dx_out[row * 3 + 0] : 0.f, dxo1 = dx_out ? dx_out[row * 3 + 1] : 0.f,
+            dxo2 = dx_out ? dx_out[row * 3 + 2] : 0.f;
+      float dvo0 = dv_out ? dv_out[row * 3 + 0] : 0.f, dvo1 = dv_out ? dv_out[row * 3 + 1] : 0.f,
+            dvo2 = dv_out ? dv_out[row * 3 + 2] : 0.f;
+      dx[row * 3 + 0] = dxo0; dx[row * 3 + 1] = dxo1; dx[row * 3 + 2] = dxo2;   // x' = x + v'
+      if (upd) {
+        g0 = dvo0 + dxo0; g1 = dvo1 + dxo1; g2 = dvo2 + dxo2;                   // cotangent of v'
+        if (hv) {
+          float y = 0.f;
+          for (int f = 0; f < H; ++f) y = fmaf(siluf_(tv[n * H + f]), p.vel2_kernel[f], y);
+          gt = 2.0f * sigmoidf_(y);
+          const float* vv = v + row * 3;
+          float ggate = g0 * vv[0] + g1 * vv[1] + g2 * vv[2];
+          gyv = ggate * gt * (1.0f - 0.5f * gt);
+          if (dv) { dv[row * 3 + 0] = gt * g0; dv[row * 3 + 1] = gt * g1; dv[row * 3 + 2] = gt * g2; }
+        }
+      } else if (dv && hv) {
+        dv[row * 3 + 0] = dvo0; dv[row * 3 + 1] = dvo1; dv[row * 3 + 2] = dvo2;   // v passes through
+      }
+    }
+    gdv[n * 3 + 0] = g0; gdv[n * 3 + 1] = g1; gdv[n * 3 + 2] = g2;
+    gy[n] = gyv;
+    gate[n] = gt;
+  }
+  __syncthreads();
+  if (upd && hv) {
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+      const int n = t / H, f = t % H;
+      gtv[t] = p.vel2_kernel[f] * gy[n] * dsiluf_(tv[t]);
+    }
+    __syncthreads();
+    if (want_grads) {
+      for (int f = threadIdx.x; f < H; f += blockDim.x) {
+        float s = 0.f;
+        for (int n = 0; n < nn; ++n) s = fmaf(siluf_(tv[n * H + f]), gy[n], s);
+        atomicAdd(g.vel2_kernel + f, s);
+      }
+      accum_outer(g.vel0_kernel, hout, H, H, gtv, H, nn);
+      accum_bias(g.vel0_bias, gtv, H, nn);
+    }
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+      const int n = t / H, q = t % H;
+      float acc = 0.f;
+      for (int f = 0; f < H; ++f) acc = fmaf(p.vel0_kernel[(size_t)q * H + f], gtv[n * H + f], acc);
+      ghout[t] += acc;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- node_mlp backward ----------------
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) gt2[t] = ghout[t] * dsiluf_(t2[t]);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, q = t % H;
+    float acc = 0.f;
+    for (int f = 0; f < H; ++f) acc = fmaf(p.node2_kernel[(size_t)q * H + f], gt2[n * H + f], acc);
+    gt1[t] = acc * dsiluf_(t1[t]);
+  }
+  __syncthreads();
+  if (want_grads) {
+    // n1 = silu(t1) recomputed into tv (free now)
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(t1[t]);
+    __syncthreads();
+    accum_outer(g.node2_kernel, tv, H, H, gt2, H, nn);
+    accum_bias(g.node2_bias, gt2, H, nn);
+    accum_outer(g.node0_kernel, hin, H, H, gt1, H, nn);
+    accum_outer(g.node0_kernel + (size_t)H * H, hes, C, C, gt1, H, nn);
+    if (d.spatial) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(tp2[t]);
+      __syncthreads();
+      accum_outer(g.node0_kernel + (size_t)(H + C) * H, tv, H, H, gt1, H, nn);
+    }
+    accum_bias(g.node0_bias, gt1, H, nn);
+    __syncthreads();
+  }
+  // g_cat = Wn1 @ gt1 : dh, ghe, g_hcomb
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, q = t % H;
+    float acc = 0.f, acc2 = 0.f;
+    const float* w0 = p.node0_kernel + (size_t)q * H;
+    const float* w2 = p.node0_kernel + (size_t)(H + C + q) * H;
+    for (int f = 0; f < H; ++f) {
+      float gv = gt1[n * H + f];
+      acc = fmaf(w0[f], gv, acc);
+      acc2 = fmaf(w2[f], gv, acc2);
+    }
+    if (n < nn) dh[(size_t)r0 * H + t] = ghout[t] + acc;
+    gtp2[t] = d.spatial ? acc2 * dsiluf_(tp2[t]) : 0.f;
+  }
+  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
+    const int n = t / C, c = t % C;
+    float acc = 0.f;
+    const float* w1 = p.node0_kernel + (size_t)(H + c) * H;
+    for (int f = 0; f < H; ++f) acc = fmaf(w1[f], gt1[n * H + f], acc);
+    if (n < nn) ghe[(size_t)(r0 + n) * C + c] = acc;
+  }
+  __syncthreads();
+  // ---------------- post_norm_mlp backward ----------------
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, q = t % H;
+    float acc = 0.f;
+    for (int f = 0; f < H; ++f) acc = fmaf(p.post2_kernel[(size_t)q * H + f], gtp2[n * H + f], acc);
+    gtp1[t] = acc * dsiluf_(tp1[t]);
+  }
+  __syncthreads();
+  if (want_grads && d.spatial) {
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(tp1[t]);
+    __syncthreads();
+    accum_outer(g.post2_kernel, tv, H, H, gtp2, H, nn);
+    accum_bias(g.post2_bias, gtp2, H, nn);
+    accum_outer(g.post0_kernel, nrm, C, C, gtp1, H, nn);
+    accum_bias(g.post0_bias, gtp1, H, nn);
+    __syncthreads();
+  }
+  // T[c][d] = 2*ssum[c][d]*g_nrm[c]/den^2 + Wv[c]*g_dv[d]/den2 ;  gWv[c] += sum_d ssum[c][d]*g_dv[d]/den2
+  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
+    const int n = t / C, c = t % C;
+    if (n >= nn) continue;
+    const size_t row = (size_t)(r0 + n);
+    float t0 = 0.f, t1v = 0.f, t2v = 0.f;
+    if (d.spatial) {
+      float gn = 0.f;
+      const float* w = p.post0_kernel + (size_t)c * H;
+      for (int f = 0; f < H; ++f) gn = fmaf(w[f], gtp1[n * H + f], gn);
+      const float* sp = ssum + (row * C + c) * 3;
+      float k2 = 2.0f * gn / (den[n] * den[n]);
+      t0 = k2 * sp[0]; t1v = k2 * sp[1]; t2v = k2 * sp[2];
+      if (upd) {
+        float wv = p.v_mixing_kernel[c] / den2[n];
+        t0 = fmaf(wv, gdv[n * 3 + 0], t0); t1v = fmaf(wv, gdv[n * 3 + 1], t1v); t2v = fmaf(wv, gdv[n * 3 + 2], t2v);
+        if (want_grads) {
+          float s = (sp[0] * gdv[n * 3 + 0] + sp[1] * gdv[n * 3 + 1] + sp[2] * gdv[n * 3 + 2]) / den2[n];
+          atomicAdd(g.v_mixing_kernel + c, s);
+        }
+      }
+    }
+    float* tp = T + (row * C + c) * 3;
+    tp[0] = t0; tp[1] = t1v; tp[2] = t2v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mix_bwd (generic): recompute coef, then g_e, g_att, g_dir (and gZ for the dW GEMM)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix_bwd(Dims d, const float* __restrict__ x, const float* __restrict__ mask,
+                                                 const float* __restrict__ Wx, const float* __restrict__ WxT,
+                                                 const float* __restrict__ e, const float* __restrict__ att,
+                                                 const float* __restrict__ T, const float* __restrict__ ghe,
+                                                 float* __restrict__ ge, float* __restrict__ gatt,
+                                                 float* __restrict__ gdir, float* __restrict__ gZ_out) {
+  extern __shared__ float sm[];
+  const int N = d.N, A = d.A, H = d.H, C = d.C;
+  float* ET = sm;                  // [C][MJ]
+  float* coefT = ET + C * MJ;      // [C][MJ]
+  float* gZT = coefT + C * MJ;     // [C][MJ]  (later reused as gE[C][MJ])
+  float* Ts = gZT + C * MJ;        // [C][3]
+  float* ghes = Ts + C * 3;        // [C]
+  float* dirm = ghes + C;          // [MJ][4]
+  const int row = blockIdx.x;
+  const int b = row / N;
+  const float xi0 = x[(size_t)row * 3 + 0], xi1 = x[(size_t)row * 3 + 1], xi2 = x[(size_t)row * 3 + 2];
+  for (int t = threadIdx.x; t < C * 3; t += blockDim.x) Ts[t] = T[(size_t)row * C * 3 + t];
+  for (int t = threadIdx.x; t < C; t += blockDim.x) ghes[t] = ghe[(size_t)row * C + t];
+  for (int j0 = 0; j0 < N; j0 += MJ) {
+    const int np = min(MJ, N - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < C * MJ; t += blockDim.x) {
+      const int c = t / MJ, pj = t % MJ;
+      float val = 0.f;
+      if (pj < np) {
+        size_t pr = (size_t)row * N + j0 + pj;
+        val = e[pr * H + c / A] * att[pr * A + c % A];
+      }
+      ET[t] = val;
+    }
+    if (threadIdx.x < MJ) {
+      const int pj = threadIdx.x;
+      float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pj < np) {
+        const int j = j0 + pj;
+        const float* xj = x + (size_t)(b * N + j) * 3;
+        float r0 = xj[0] - xi0, r1 = xj[1] - xi1, r2 = xj[2] - xi2;
+        float n = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
+        float inv = 1.0f / (n + 1e-5f);
+        float m = mask ? mask[(size_t)row * N + j] : 1.0f;
+        dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, m);
+      }
+      reinterpret_cast<float4*>(dirm)[pj] = dm;
+    }
+    __syncthreads();
+    for (int cp = threadIdx.x; cp < C; cp += blockDim.x) {
+      float acc[MJ];
+#pragma unroll
+      for (int q = 0; q < MJ; ++q) acc[q] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        float w = Wx[(size_t)c * C + cp];
+        const float4 ea = reinterpret_cast<const float4*>(ET + c * MJ)[0];
+        const float4 eb = reinterpret_cast<const float4*>(ET + c * MJ)[1];
+        acc[0] = fmaf(ea.x, w, acc[0]); acc[1] = fmaf(ea.y, w, acc[1]);
+        acc[2] = fmaf(ea.z, w, acc[2]); acc[3] = fmaf(ea.w, w, acc[3]);
+        acc[4] = fmaf(eb.x, w, acc[4]); acc[5] = fmaf(eb.y, w, acc[5]);
+        acc[6] = fmaf(eb.z, w, acc[6]); acc[7] = fmaf(eb.w, w, acc[7]);
+      }
+      const float tt0 = Ts[cp * 3 + 0], tt1 = Ts[cp * 3 + 1], tt2 = Ts[cp * 3 + 2];
+#pragma unroll
+      for (int q = 0; q < MJ; ++q) {
+        float co = tanhf(acc[q]);
+        const float4 dm = reinterpret_cast<const float4*>(dirm)[q];
+        float gco = dm.x * tt0 + dm.y * tt1 + dm.z * tt2;     // includes the mask
+        float gz = gco * (1.0f - co * co);
+        coefT[cp * MJ + q] = co;
+        gZT[cp * MJ + q] = gz;
+        if (gZ_out && q < np) gZ_out[((size_t)row * N + j0 + q) * C + cp] = gz;
+      }
+    }
+    __syncthreads();
+    // g_dir[pj][dd] = m * sum_c coef[c] * T[c][dd]
+    if (threadIdx.x < np * 3) {
+      const int pj = threadIdx.x / 3, dd = threadIdx.x % 3;
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) acc = fmaf(coefT[c * MJ + pj], Ts[c * 3 + dd], acc);
+      gdir[((size_t)row * N + j0 + pj) * 3 + dd] = acc * dirm[pj * 4 + 3];
+    }
+    // g_E[c] = sum_c' gZ[c'] * Wx[c][c'] + m * ghe[c]   -> stored over ET (ET no longer needed)
+    float gEv[MJ];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+      for (int q = 0; q < MJ; ++q) gEv[q] = 0.f;
+      for (int cp = 0; cp < C; ++cp) {
+        float w = WxT[(size_t)cp * C + c];
+        const float4 ga = reinterpret_cast<const float4*>(gZT + cp * MJ)[0];
+        const float4 gb = reinterpret_cast<const float4*>(gZT + cp * MJ)[1];
+        gEv[0] = fmaf(ga.x, w, gEv[0]); gEv[1] = fmaf(ga.y, w, gEv[1]);
+        gEv[2] = fmaf(ga.z, w, gEv[2]); gEv[3] = fmaf(ga.w, w, gEv[3]);
+        gEv[4] = fmaf(gb.x, w, gEv[4]); gEv[5] = fmaf(gb.y, w, gEv[5]);
+        gEv[6] = fmaf(gb.z, w, gEv[6]); gEv[7] = fmaf(gb.w, w, gEv[7]);
+      }
+      const float gh = ghes[c];
+#pragma unroll
+      for (int q = 0; q < MJ; ++q) ET[c * MJ + q] = fmaf(dirm[q * 4 + 3], gh, gEv[q]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
+      const int pj = t / H, f = t % H;
+      const size_t pr = (size_t)row * N + j0 + pj;
+      float acc = 0.f;
+      for (int a = 0; a < A; ++a) acc = fmaf(ET[(f * A + a) * MJ + pj], att[pr * A + a], acc);
+      ge[pr * H + f] = acc;
+    }
+    for (int t = threadIdx.x; t < np * A; t += blockDim.x) {
+      const int pj = t / A, a = t % A;
+      const size_t pr = (size_t)row * N + j0 + pj;
+      float acc = 0.f;
+      for (int f = 0; f < H; ++f) acc = fmaf(ET[(f * A + a) * MJ + pj], e[pr * H + f], acc);
+      gatt[pr * A + a] = acc;
+    }
+  }
+}
+
+// no spatial attention: only the aggregate path feeds e / att
+__global__ void __launch_bounds__(256) k_mix_bwd_nospatial(Dims d, const float* __restrict__ mask,
+                                                           const float* __restrict__ e, const float* __restrict__ att,
+                                                           const float* __restrict__ ghe, float* __restrict__ ge,
+                                                           float* __restrict__ gatt, float* __restrict__ gdir) {
+  const int N = d.N, A = d.A, H = d.H, C = d.C;
+  const size_t pr = blockIdx.x;
+  const size_t row = pr / N;
+  const float m = mask ? mask[pr] : 1.0f;
+  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+    float acc = 0.f;
+    for (int a = 0; a < A; ++a) acc = fmaf(m * ghe[row * C + f * A + a], att[pr * A + a], acc);
+    ge[pr * H + f] = acc;
+  }
+  for (int a = threadIdx.x; a < A; a += blockDim.x) {
+    float acc = 0.f;
+    for (int f = 0; f < H; ++f) acc = fmaf(m * ghe[row * C + f * A + a], e[pr * H + f], acc);
+    gatt[pr * A + a] = acc;
+  }
+  if (threadIdx.x < 3) gdir[pr * 3 + threadIdx.x] = 0.f;
+}
+
+// dWx[c][c'] += sum_p E[p][c] * gZ[p][c']
+__global__ void __launch_bounds__(256) k_mix_dw(Dims d, const float* __restrict__ e, const float* __restrict__ att,
+                                                const float* __restrict__ gZ, float* __restrict__ gWx,
+                                                long long pairs_per_split) {
+  __shared__ float Es[16][64 + 1];
+  __shared__ float Gs[16][64 + 1];
+  const int C = d.C, A = d.A, H = d.H;
+  const int c0 = blockIdx.x * 64, cp0 = blockIdx.y * 64;
+  const long long pbeg = (long long)blockIdx.z * pairs_per_split;
+  const long long pend = min(d.P, pbeg + pairs_per_split);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (long long p0 = pbeg; p0 < pend; p0 += 16) {
+    for (int t = threadIdx.x; t < 16 * 64; t += blockDim.x) {
+      const int pp = t / 64, cc = t % 64;
+      const long long pr = p0 + pp;
+      float ev = 0.f, gv = 0.f;
+      if (pr < pend) {
+        if (c0 + cc < C) ev = e[pr * H + (c0 + cc) / A] * att[pr * A + (c0 + cc) % A];
+        if (cp0 + cc < C) gv = gZ[pr * C + cp0 + cc];
+      }
+      Es[pp][cc] = ev;
+      Gs[pp][cc] = gv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < 16; ++pp) {
+      float ev[4], gv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ev[q] = Es[pp][ty * 4 + q]; gv[q] = Gs[pp][tx * 4 + q]; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = fmaf(ev[a], gv[b2], acc[a][b2]);
+    }
+    __syncthreads();
+  }
+  for (int a = 0; a < 4; ++a)
+    for (int b2 = 0; b2 < 4; ++b2) {
+      const int c = c0 + ty * 4 + a, cp = cp0 + tx * 4 + b2;
+      if (c < C && cp < C) atomicAdd(gWx + (size_t)c * C + cp, acc[a][b2]);
+    }
+}
+
+__global__ void k_transpose(int n, const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    int xx = threadIdx.x;
+    if (x0 + xx < n && y0 + yy < n) tile[yy][xx] = in[(size_t)(y0 + yy) * n + x0 + xx];
+  }
+  __syncthreads();
+  for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+    int xx = threadIdx.x;
+    if (y0 + xx < n && x0 + yy < n) out[(size_t)(x0 + yy) * n + y0 + xx] = tile[xx][yy];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attn_bwd: att (softmax over unmasked senders) backward, celu', and the W_s transpose
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_attn_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ e,
+                                                  const float* __restrict__ att, float* __restrict__ gatt,
+                                                  float* __restrict__ ge) {
+  extern __shared__ float sm[];
+  const int N = d.N, A = d.A, H = d.H;
+  float* as = sm;           // [N][A]
+  float* gs = as + N * A;   // [N][A]
+  float* G = gs + N * A;    // [A]
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * N;
+  for (int t = threadIdx.x; t < N * A; t += blockDim.x) {
+    as[t] = att[base * A + t];
+    gs[t] = gatt[base * A + t];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int a = warp; a < A; a += nw) {
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) s = fmaf(gs[j * A + a], as[j * A + a], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) G[a] = s;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N * A; t += blockDim.x) {
+    const int j = t / A, a = t % A;
+    float gsv = as[t] * (gs[t] - G[a]);
+    float q = p.sem_bias[a];
+    const float* er = e + (base + j) * H;
+    for (int f = 0; f < H; ++f) q = fmaf(er[f], p.sem_kernel[(size_t)f * A + a], q);
+    float gq = gsv * dcelu2f_(q);
+    gs[t] = gq;
+    gatt[base * A + t] = gq;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N * H; t += blockDim.x) {
+    const int j = t / H, f = t % H;
+    float acc = 0.f;
+    for (int a = 0; a < A; ++a) acc = fmaf(p.sem_kernel[(size_t)f * A + a], gs[j * A + a], acc);
+    ge[(base + j) * H + f] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// edge_bwd: persistent over receiving atoms; recomputes the edge MLP, back-propagates to the
+// per-node projections, coordinates and the pair-level parameters.
+// ------------------------------------------------------------------------------------------
+struct EdgeBwdSmem {
+  float *aW2, *aW1g, *aw1n, *ab2, *aWs, *abs_, *amu, *abeta;   // CTA-lifetime accumulators
+  float *pri, *gui, *gpi, *dxi;                                // per receiving atom
+  float *g, *rho, *u, *z1, *a1, *ges, *gz1, *gg, *rs, *ns, *ts; // per chunk
+};
+__host__ __device__ inline size_t edge_bwd_floats(const Dims& d) {
+  return (size_t)d.H * d.H + (size_t)d.K * d.H + 2 * d.H + (size_t)d.H * d.A + d.A + 2 * d.K  // accumulators
+         + d.NP + d.K + d.H + 4                                                                  // per row
+         + (size_t)PJ * (4 * d.K + 4 * d.H + 3 + 2) + 16;
+}
+__device__ inline EdgeBwdSmem edge_bwd_carve(float* sm, const Dims& d) {
+  EdgeBwdSmem s;
+  const int H = d.H, K = d.K, A = d.A;
+  s.aW2 = sm; s.aW1g = s.aW2 + H * H; s.aw1n = s.aW1g + K * H; s.ab2 = s.aw1n + H; s.aWs = s.ab2 + H;
+  s.abs_ = s.aWs + H * A; s.amu = s.abs_ + A; s.abeta = s.amu + K;
+  s.pri = s.abeta + K; s.gui = s.pri + d.NP; s.gpi = s.gui + K; s.dxi = s.gpi + H;
+  s.g = s.dxi + 4; s.rho = s.g + PJ * K; s.u = s.rho + PJ * K; s.gg = s.u + PJ * K;
+  s.z1 = s.gg + PJ * K; s.a1 = s.z1 + PJ * H; s.ges = s.a1 + PJ * H; s.gz1 = s.ges + PJ * H;
+  s.rs = s.gz1 + PJ * H; s.ns = s.rs + PJ * 3; s.ts = s.ns + PJ;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restrict__ x, const SakeLayerParams p,
+                                                  const float* __restrict__ proj, const float* __restrict__ e,
+                                                  const float* __restrict__ ge, const float* __restrict__ gq,
+                                                  const float* __restrict__ gdir, float* __restrict__ gproj,
+                                                  float* __restrict__ dx, SakeLayerGrads g, int want_grads) {
+  extern __shared__ float sm[];
+  EdgeBwdSmem s = edge_bwd_carve(sm, d);
+  const int H = d.H, K = d.K, A = d.A, N = d.N;
+  const float* W1g = p.mlp_out0_kernel + (size_t)2 * H * H;
+  const float* w1n = W1g + (size_t)K * H;
+  const int nacc = H * H + K * H + 2 * H + H * A + A + 2 * K;
+  for (int t = threadIdx.x; t < nacc; t += blockDim.x) s.aW2[t] = 0.f;
+  __syncthreads();
+  for (int row = blockIdx.x; row < d.R; row += gridDim.x) {
+    const int b = row / N;
+    for (int t = threadIdx.x; t < d.NP; t += blockDim.x) s.pri[t] = proj[(size_t)row * d.NP + t];
+    for (int t = threadIdx.x; t < K + H + 4; t += blockDim.x) s.gui[t] = 0.f;   // gui, gpi, dxi contiguous
+    const float xi0 = x[(size_t)row * 3 + 0], xi1 = x[(size_t)row * 3 + 1], xi2 = x[(size_t)row * 3 + 2];
+    __syncthreads();
+    for (int j0 = 0; j0 < N; j0 += PJ) {
+      const int np = min(PJ, N - j0);
+      if (threadIdx.x < np) {
+        const int j = j0 + threadIdx.x;
+        const float* xj = x + (size_t)(b * N + j) * 3;
+        float r0 = xj[0] - xi0, r1 = xj[1] - xi1, r2 = xj[2] - xi2;
+        s.rs[threadIdx.x * 3 + 0] = r0; s.rs[threadIdx.x * 3 + 1] = r1; s.rs[threadIdx.x * 3 + 2] = r2;
+        float n = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
+        s.ns[threadIdx.x] = n;
+        s.ts[threadIdx.x] = expf(-n);
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < np * K; t += blockDim.x) {
+        const int pj = t / K, k = t % K;
+        const int j = j0 + pj;
+        float dm = s.ts[pj] - p.rbf_means[k];
+        float rho = expf(-p.rbf_betas[k] * dm * dm);
+        float u = proj[(size_t)(b * N + j) * d.NP + k] + s.pri[K + k];
+        s.rho[pj * K + k] = rho;
+        s.u[pj * K + k] = u;
+        s.g[pj * K + k] = rho * u;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
+        const int pj = t / H, f = t % H;
+        const int j = j0 + pj;
+        float z = proj[(size_t)(b * N + j) * d.NP + 2 * K + f] + s.pri[2 * K + H + f];
+        z = fmaf(s.ns[pj], w1n[f], z);
+        for (int k = 0; k < K; ++k) z = fmaf(s.g[pj * K + k], W1g[(size_t)k * H + f], z);
+        s.z1[pj * H + f] = z;
+        s.a1[pj * H + f] = siluf_(z);
+        s.ges[pj * H + f] = ge[((size_t)row * N + j) * H + f];
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
+        const int pj = t / H, q = t % H;
+        float acc = 0.f;
+        const float* w = p.mlp_out2_kernel + (size_t)q * H;
+        for (int f = 0; f < H; ++f) acc = fmaf(w[f], s.ges[pj * H + f], acc);
+        s.gz1[pj * H + q] = acc * dsiluf_(s.z1[pj * H + q]);
+      }
+      __syncthreads();
+      if (want_grads) {
+        for (int t = threadIdx.x; t < H * H; t += blockDim.x) {
+          const int q = t / H, f = t % H;
+          float acc = 0.f;
+          for (int pj = 0; pj < np; ++pj) acc = fmaf(s.a1[pj * H + q], s.ges[pj * H + f], acc);
+          s.aW2[t] += acc;
+        }
+        for (int t = threadIdx.x; t < K * H; t += blockDim.x) {
+          const int k = t / H, f = t % H;
+          float acc = 0.f;
+          for (int pj = 0; pj < np; ++pj) acc = fmaf(s.g[pj * K + k], s.gz1[pj * H + f], acc);
+          s.aW1g[t] += acc;
+        }
+        for (int f = threadIdx.x; f < H; f += blockDim.x) {
+          float acc = 0.f, accb = 0.f;
+          for (int pj = 0; pj < np; ++pj) {
+            acc = fmaf(s.ns[pj], s.gz1[pj * H + f], acc);
+            accb += s.ges[pj * H + f];
+          }
+          s.aw1n[f] += acc;
+          s.ab2[f] += accb;
+        }
+        for (int t = threadIdx.x; t < H * A; t += blockDim.x) {
+          const int f = t / A, a = t % A;
+          float acc = 0.f;
+          for (int pj = 0; pj < np; ++pj) {
+            const size_t pr = (size_t)row * N + j0 + pj;
+            acc = fmaf(e[pr * H + f], gq[pr * A + a], acc);
+          }
+          s.aWs[t] += acc;
+        }
+        for (int a = threadIdx.x; a < A; a += blockDim.x) {
+          float acc = 0.f;
+          for (int pj = 0; pj < np; ++pj) acc += gq[((size_t)row * N + j0 + pj) * A + a];
+          s.abs_[a] += acc;
+        }
+      }
+      // g_g = W1g @ g_z1
+      for (int t = threadIdx.x; t < np * K; t += blockDim.x) {
+        const int pj = t / K, k = t % K;
+        float acc = 0.f;
+        const float* w = W1g + (size_t)k * H;
+        for (int f = 0; f < H; ++f) acc = fmaf(w[f], s.gz1[pj * H + f], acc);
+        s.gg[pj * K + k] = acc;
+      }
+      __syncthreads();
+      // per-k and per-f reductions / scatters
+      for (int k = threadIdx.x; k < K + H; k += blockDim.x) {
+        if (k < K) {
+          const float mu = p.rbf_means[k], beta = p.rbf_betas[k];
+          float gui = 0.f, gmu = 0.f, gbeta = 0.f;
+          for (int pj = 0; pj < np; ++pj) {
+            const int j = j0 + pj;
+            const float ggv = s.gg[pj * K + k], rho = s.rho[pj * K + k];
+            const float gu = ggv * rho;
+            const float grho = ggv * s.u[pj * K + k];
+            const float dm = s.ts[pj] - mu;
+            atomicAdd(gproj + (size_t)(b * N + j) * d.NP + k, gu);
+            gui += gu;
+            const float w = dm * rho * grho;
+            gmu = fmaf(2.0f * beta, w, gmu);
+            gbeta = fmaf(-dm, w, gbeta);
+            s.gg[pj * K + k] = -2.0f * beta * w;        // d/dt contribution
+          }
+          s.gui[k] += gui;
+          if (want_grads) { s.amu[k] += gmu; s.abeta[k] += gbeta; }
+        } else {
+          const int f = k - K;
+          float gpi = 0.f;
+          for (int pj = 0; pj < np; ++pj) {
+            const int j = j0 + pj;
+            const float gz = s.gz1[pj * H + f];
+            atomicAdd(gproj + (size_t)(b * N + j) * d.NP + 2 * K + f, gz);
+            gpi += gz;
+          }
+          s.gpi[f] += gpi;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < np) {
+        const int pj = threadIdx.x, j = j0 + pj;
+        float gt = 0.f;
+        for (int k = 0; k < K; ++k) gt += s.gg[pj * K + k];
+        float gn = -s.ts[pj] * gt;
+        for (int f = 0; f < H; ++f) gn = fmaf(w1n[f], s.gz1[pj * H + f], gn);
+        const float n = s.ns[pj];
+        const float r0 = s.rs[pj * 3 + 0], r1 = s.rs[pj * 3 + 1], r2 = s.rs[pj * 3 + 2];
+        const float* gd = gdir + ((size_t)row * N + j) * 3;
+        const float inv = 1.0f / (n + 1e-5f);
+        float gr0 = gd[0] * inv, gr1 = gd[1] * inv, gr2 = gd[2] * inv;
+        gn -= (gd[0] * r0 + gd[1] * r1 + gd[2] * r2) * inv * inv;
+        const float n2 = r0 * r0 + r1 * r1 + r2 * r2;
+        const float gn2 = n2 > 0.f ? gn / (2.0f * n) : 0.f;     // relu'(0) = 0 (functional.py:15)
+        gr0 = fmaf(2.0f * r0, gn2, gr0); gr1 = fmaf(2.0f * r1, gn2, gr1); gr2 = fmaf(2.0f * r2, gn2, gr2);
+        if (j == row % N) { gr0 = 0.f; gr1 = 0.f; gr2 = 0.f; }   // r_ii = x_i - x_i: +g and -g cancel exactly
+        float* dxj = dx + (size_t)(b * N + j) * 3;
+        atomicAdd(dxj + 0, gr0); atomicAdd(dxj + 1, gr1); atomicAdd(dxj + 2, gr2);
+        atomicAdd(s.dxi + 0, -gr0); atomicAdd(s.dxi + 1, -gr1); atomicAdd(s.dxi + 2, -gr2);
+      }
+      __syncthreads();
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) gproj[(size_t)row * d.NP + K + k] = s.gui[k];
+    for (int f = threadIdx.x; f < H; f += blockDim.x) gproj[(size_t)row * d.NP + 2 * K + H + f] = s.gpi[f];
+    if (threadIdx.x < 3) atomicAdd(dx + (size_t)row * 3 + threadIdx.x, s.dxi[threadIdx.x]);
+    __syncthreads();
+  }
+  if (want_grads) {
+    for (int t = threadIdx.x; t < H * H; t += blockDim.x) atomicAdd(g.mlp_out2_kernel + t, s.aW2[t]);
+    for (int t = threadIdx.x; t < K * H; t += blockDim.x)
+      atomicAdd(g.mlp_out0_kernel + (size_t)2 * H * H + t, s.aW1g[t]);
+    for (int f = threadIdx.x; f < H; f += blockDim.x) {
+      atomicAdd(g.mlp_out0_kernel + (size_t)(2 * H + K) * H + f, s.aw1n[f]);
+      atomicAdd(g.mlp_out2_bias + f, s.ab2[f]);
+    }
+    for (int t = threadIdx.x; t < H * A; t += blockDim.x) atomicAdd(g.sem_kernel + t, s.aWs[t]);
+    for (int a = threadIdx.x; a < A; a += blockDim.x) atomicAdd(g.sem_bias + a, s.abs_[a]);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      atomicAdd(g.rbf_means + k, s.amu[k]);
+      atomicAdd(g.rbf_betas + k, s.abeta[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// node_pre_bwd: cotangent of the per-node projections -> dh and W_in / W_1[0:2H] / biases
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ h,
+                                                      const float* __restrict__ gproj, float* __restrict__ dh,
+                                                      SakeLayerGrads g, int want_grads) {
+  extern __shared__ float sm[];
+  const int H = d.H, K = d.K, NP = d.NP;
+  float* gp = sm;               // [NODES][NP]
+  float* hs = gp + NODES * NP;  // [NODES][H]
+  const int r0 = blockIdx.x * NODES;
+  const int nn = min(NODES, d.R - r0);
+  for (int t = threadIdx.x; t < NODES * NP; t += blockDim.x) gp[t] = (t / NP) < nn ? gproj[(size_t)r0 * NP + t] : 0.f;
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) hs[t] = (t / H) < nn ? h[(size_t)r0 * H + t] : 0.f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < nn * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    const float* gr = gp + n * NP;
+    float acc = 0.f;
+    const float* wj = p.mlp_in_kernel + (size_t)f * K;
+    const float* wi = p.mlp_in_kernel + (size_t)(H + f) * K;
+    for (int k = 0; k < K; ++k) acc = fmaf(wj[k], gr[k], fmaf(wi[k], gr[K + k], acc));
+    const float* vj = p.mlp_out0_kernel + (size_t)f * H;
+    const float* vi = p.mlp_out0_kernel + (size_t)(H + f) * H;
+    for (int q = 0; q < H; ++q) acc = fmaf(vj[q], gr[2 * K + q], fmaf(vi[q], gr[2 * K + H + q], acc));
+    dh[(size_t)r0 * H + t] += acc;
+  }
+  if (want_grads) {
+    for (int t = threadIdx.x; t < H * K; t += blockDim.x) {
+      const int f = t / K, k = t % K;
+      float sj = 0.f, si = 0.f;
+      for (int n = 0; n < nn; ++n) {
+        sj = fmaf(hs[n * H + f], gp[n * NP + k], sj);
+        si = fmaf(hs[n * H + f], gp[n * NP + K + k], si);
+      }
+      atomicAdd(g.mlp_in_kernel + t, sj);
+      atomicAdd(g.mlp_in_kernel + (size_t)H * K + t, si);
+    }
+    for (int t = threadIdx.x; t < H * H; t += blockDim.x) {
+      const int f = t / H, q = t % H;
+      float sj = 0.f, si = 0.f;
+      for (int n = 0; n < nn; ++n) {
+        sj = fmaf(hs[n * H + f], gp[n * NP + 2 * K + q], sj);
+        si = fmaf(hs[n * H + f], gp[n * NP + 2 * K + H + q], si);
+      }
+      atomicAdd(g.mlp_out0_kernel + t, sj);
+      atomicAdd(g.mlp_out0_kernel + (size_t)H * H + t, si);
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float sb = 0.f;
+      for (int n = 0; n < nn; ++n) sb += gp[n * NP + K + k];
+      atomicAdd(g.mlp_in_bias + k, sb);
+    }
+    for (int q = threadIdx.x; q < H; q += blockDim.x) {
+      float sb = 0.f;
+      for (int n = 0; n < nn; ++n) sb += gp[n * NP + 2 * K + H + q];
+      atomicAdd(g.mlp_out0_bias + q, sb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+template <typename Kern>
+static int ensure_smem(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    if (smem > 227 * 1024) {
+      set_error("generic engine: %zu bytes of shared memory needed (H/A too large)", smem);
+      return SAKE_EUNSUPPORTED;
+    }
+    SAKE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  return 0;
+}
+
+static SakeLayerGrads null_grads() {
+  SakeLayerGrads g;
+  memset(&g, 0, sizeof(g));
+  return g;
+}
+
+int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                      const float* mask, const Saved& sv, const float* dh_out, const float* dx_out,
+                      const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
+                      const BwdScratch& sc, cudaStream_t st) {
+  (void)x;
+  size_t smem = node_post_bwd_smem_bytes(d);
+  int rc;
+  if ((rc = ensure_smem(k_node_post_bwd, smem))) return rc;
+  k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, v, mask, sv.ssum, sv.he, dh_out, dx_out,
+                                                                dv_out, dh, dx, dv, sc.T, sc.ghe,
+                                                                g ? *g : null_grads(), g != nullptr);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                const BwdScratch& sc, float* gWx, cudaStream_t st) {
+  int rc;
+  if (!d.spatial) {
+    k_mix_bwd_nospatial<<<(unsigned)d.P, 64, 0, st>>>(d, mask, sv.e, sv.att, sc.ghe, sc.ge, sc.gatt, sc.gdir);
+    SAKE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  dim3 tb(32, 8), tg((d.C + 31) / 32, (d.C + 31) / 32);
+  k_transpose<<<tg, tb, 0, st>>>(d.C, p.x_mixing_kernel, sc.wxT);
+  size_t smem = sizeof(float) * (3 * d.C * MJ + 4 * d.C + MJ * 4);
+  if ((rc = ensure_smem(k_mix_bwd, smem))) return rc;
+  k_mix_bwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sc.wxT, sv.e, sv.att, sc.T, sc.ghe, sc.ge,
+                                    sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+  if (gWx) {
+    int splits = (int)min((long long)64, (d.P + 255) / 256);
+    if (splits < 1) splits = 1;
+    long long pps = (d.P + splits - 1) / splits;
+    pps = (pps + 15) / 16 * 16;
+    dim3 grid((d.C + 63) / 64, (d.C + 63) / 64, splits);
+    k_mix_dw<<<grid, 256, 0, st>>>(d, sv.e, sv.att, sc.gZ, gWx, pps);
+  }
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_bwd_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
+                 const Saved& sv, float* dh, float* dx, const SakeLayerGrads* g, const BwdScratch& sc,
+                 cudaStream_t st) {
+  (void)mask;
+  int rc;
+  {
+    size_t smem = sizeof(float) * (2 * d.N * d.A + d.A);
+    if ((rc = ensure_smem(k_attn_bwd, smem))) return rc;
+    k_attn_bwd<<<d.R, 128, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
+  }
+  SAKE_CUDA_CHECK(cudaMemsetAsync(sc.gproj, 0, sizeof(float) * (size_t)d.R * d.NP, st));
+  {
+    size_t smem = sizeof(float) * edge_bwd_floats(d);
+    if ((rc = ensure_smem(k_edge_bwd, smem))) return rc;
+    int grid = d.R < 148 * 2 ? d.R : 148 * 2;
+    k_edge_bwd<<<grid, 256, smem, st>>>(d, x, p, sv.nodeproj, sv.e, sc.ge, sc.gatt, sc.gdir, sc.gproj, dx,
+                                        g ? *g : null_grads(), g != nullptr);
+  }
+  {
+    size_t smem = sizeof(float) * NODES * (d.NP + d.H);
+    if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
+    k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, sc.gproj, dh, g ? *g : null_grads(),
+                                                                 g != nullptr);
+  }
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sake

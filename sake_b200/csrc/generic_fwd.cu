@@ -1,0 +1,450 @@
+// Generic fp32 CUDA-core forward of DenseSAKELayer (any H / A / K).
+// Correctness-first engine and the permanent path for shapes the tcgen05 engine does not take
+// (H = 4, 7, 16, 32 of the reference's tests and scripts).  Reference: sake/layers.py:188-235.
+#include "common.cuh"
+
+namespace sake {
+
+static constexpr int NODES = 8;    // nodes per CTA in the per-node kernels
+static constexpr int PJ = 16;      // pairs per chunk in the edge kernel
+static constexpr int MJ = 8;       // pairs per chunk in the mix kernel
+
+// ------------------------------------------------------------------------------------------
+// node_pre: separable halves of mlp_in and mlp_out[0] applied per node (layers.py:30,33-38)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restrict__ h,
+                                                  const float* __restrict__ Win, const float* __restrict__ bin,
+                                                  const float* __restrict__ W1, const float* __restrict__ b1,
+                                                  float* __restrict__ proj) {
+  extern __shared__ float sm[];
+  float* hs = sm;  // [NODES][H]
+  const int r0 = blockIdx.x * NODES;
+  const int nn = min(NODES, d.R - r0);
+  for (int t = threadIdx.x; t < nn * d.H; t += blockDim.x) hs[t] = h[(size_t)r0 * d.H + t];
+  __syncthreads();
+  const int H = d.H, K = d.K;
+  for (int o = threadIdx.x; o < d.NP; o += blockDim.x) {
+    const float* w;
+    int ld;
+    float bias = 0.f;
+    if (o < K) { w = Win + o; ld = K; }
+    else if (o < 2 * K) { w = Win + (size_t)H * K + (o - K); ld = K; bias = bin[o - K]; }
+    else if (o < 2 * K + H) { w = W1 + (o - 2 * K); ld = H; }
+    else { w = W1 + (size_t)H * H + (o - 2 * K - H); ld = H; bias = b1[o - 2 * K - H]; }
+    float acc[NODES];
+#pragma unroll
+    for (int n = 0; n < NODES; ++n) acc[n] = bias;
+    for (int f = 0; f < H; ++f) {
+      float wv = w[(size_t)f * ld];
+#pragma unroll
+      for (int n = 0; n < NODES; ++n) acc[n] = fmaf(hs[n * H + f], wv, acc[n]);
+    }
+    for (int n = 0; n < nn; ++n) proj[(size_t)(r0 + n) * d.NP + o] = acc[n];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// edge_fwd: one CTA per receiving atom i; pair geometry, RBF, edge MLP, attention logits
+// (functional.py:7-19, utils.py:61-65, layers.py:28-40,155-165)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restrict__ x,
+                                                  const float* __restrict__ mask, const SakeLayerParams p,
+                                                  const float* __restrict__ proj, float* __restrict__ e_out,
+                                                  float* __restrict__ logit_out) {
+  extern __shared__ float sm[];
+  const int H = d.H, K = d.K, A = d.A, N = d.N;
+  float* pri = sm;                 // [NP] projections of node i
+  float* gs = pri + d.NP;          // [PJ][K]
+  float* a1 = gs + PJ * K;         // [PJ][H]
+  float* es = a1 + PJ * H;         // [PJ][H]
+  float* ns = es + PJ * H;         // [PJ]
+  const int row = blockIdx.x;
+  const int b = row / N, i = row % N;
+  for (int t = threadIdx.x; t < d.NP; t += blockDim.x) pri[t] = proj[(size_t)row * d.NP + t];
+  const float xi0 = x[(size_t)row * 3 + 0], xi1 = x[(size_t)row * 3 + 1], xi2 = x[(size_t)row * 3 + 2];
+  const float* W1g = p.mlp_out0_kernel + (size_t)2 * H * H;   // rows [2H, 2H+K)
+  const float* w1n = W1g + (size_t)K * H;                      // row 2H+K
+  __syncthreads();
+  for (int j0 = 0; j0 < N; j0 += PJ) {
+    const int np = min(PJ, N - j0);
+    if (threadIdx.x < np) {
+      const int j = j0 + threadIdx.x;
+      const float* xj = x + (size_t)(b * N + j) * 3;
+      float r0 = xj[0] - xi0, r1 = xj[1] - xi1, r2 = xj[2] - xi2;
+      float n2 = r0 * r0 + r1 * r1 + r2 * r2;
+      ns[threadIdx.x] = sqrtf(fmaxf(n2, 0.f) + 1e-5f);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * K; t += blockDim.x) {
+      const int pj = t / K, k = t % K;
+      const int j = j0 + pj;
+      float tt = expf(-ns[pj]);
+      float dm = tt - p.rbf_means[k];
+      float rho = expf(-p.rbf_betas[k] * dm * dm);
+      float u = proj[(size_t)(b * N + j) * d.NP + k] + pri[K + k];
+      gs[pj * K + k] = rho * u;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
+      const int pj = t / H, f = t % H;
+      const int j = j0 + pj;
+      float z = proj[(size_t)(b * N + j) * d.NP + 2 * K + f] + pri[2 * K + H + f];
+      z = fmaf(ns[pj], w1n[f], z);
+      for (int k = 0; k < K; ++k) z = fmaf(gs[pj * K + k], W1g[(size_t)k * H + f], z);
+      a1[pj * H + f] = siluf_(z);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
+      const int pj = t / H, f = t % H;
+      float acc = p.mlp_out2_bias[f];
+      for (int g = 0; g < H; ++g) acc = fmaf(a1[pj * H + g], p.mlp_out2_kernel[(size_t)g * H + f], acc);
+      es[pj * H + f] = acc;
+      e_out[((size_t)row * N + j0 + pj) * H + f] = acc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * A; t += blockDim.x) {
+      const int pj = t / A, a = t % A;
+      const int j = j0 + pj;
+      float q = p.sem_bias[a];
+      for (int f = 0; f < H; ++f) q = fmaf(es[pj * H + f], p.sem_kernel[(size_t)f * A + a], q);
+      float s = celu2f_(q);
+      if (j == i) s -= 1e5f;
+      if (mask) s -= 1e5f * (1.0f - mask[(size_t)row * N + j]);
+      logit_out[((size_t)row * N + j) * A + a] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attn_fwd: softmax over senders j, mask, renormalise (layers.py:167,172-180) + aggregate
+// (layers.py:135-140).  One CTA per receiving atom.  att is normalised in place.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_attn_fwd(Dims d, const float* __restrict__ mask,
+                                                  const float* __restrict__ e, float* __restrict__ att,
+                                                  float* __restrict__ he) {
+  extern __shared__ float sm[];
+  const int N = d.N, A = d.A, H = d.H;
+  float* as = sm;  // [N][A]
+  const int row = blockIdx.x;
+  float* arow = att + (size_t)row * N * A;
+  const float* mrow = mask ? mask + (size_t)row * N : nullptr;
+  for (int t = threadIdx.x; t < N * A; t += blockDim.x) as[t] = arow[t];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int a = warp; a < A; a += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, as[j * A + a]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float ex = expf(as[j * A + a] - mx);
+      as[j * A + a] = ex;
+      sum += ex;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float inv = 1.0f / sum;
+    float csum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float c = as[j * A + a] * inv;          // semantic attention (softmax)
+      if (mrow) c *= mrow[j];                 // combined = euclidean(1.0) * semantic * mask
+      as[j * A + a] = c;
+      csum += c;
+    }
+    for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    float rinv = csum > 0.f ? 1.0f / csum : 0.f;   // guarded: fully masked row -> att = 0
+    for (int j = lane; j < N; j += 32) as[j * A + a] = as[j * A + a] * rinv;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N * A; t += blockDim.x) arow[t] = as[t];
+  // aggregate: he[c = f*A+a] = sum_j e[j,f] * att[j,a] * m_j
+  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+    const int f = c / A, a = c % A;
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float w = as[j * A + a];
+      if (mrow) w *= mrow[j];
+      acc = fmaf(e[((size_t)row * N + j) * H + f], w, acc);
+    }
+    he[(size_t)row * d.C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mix_fwd (generic): coef = tanh(E @ Wx), ssum[c,d] = sum_j dir_d * coef_c * m  (layers.py:111-123)
+// One CTA per receiving atom, one thread per output coefficient c'.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix_fwd(Dims d, const float* __restrict__ x,
+                                                 const float* __restrict__ mask, const float* __restrict__ Wx,
+                                                 const float* __restrict__ e, const float* __restrict__ att,
+                                                 float* __restrict__ ssum) {
+  extern __shared__ float sm[];
+  const int N = d.N, A = d.A, H = d.H, C = d.C;
+  float* ET = sm;               // [C][MJ]
+  float* dirm = ET + C * MJ;    // [MJ][4]
+  const int row = blockIdx.x;
+  const int b = row / N;
+  const float xi0 = x[(size_t)row * 3 + 0], xi1 = x[(size_t)row * 3 + 1], xi2 = x[(size_t)row * 3 + 2];
+  for (int cp0 = 0; cp0 < C; cp0 += blockDim.x) {
+    const int cp = cp0 + threadIdx.x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j0 = 0; j0 < N; j0 += MJ) {
+      const int np = min(MJ, N - j0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < C * MJ; t += blockDim.x) {
+        const int c = t / MJ, pj = t % MJ;
+        float val = 0.f;
+        if (pj < np) {
+          size_t pr = (size_t)row * N + j0 + pj;
+          val = e[pr * H + c / A] * att[pr * A + c % A];
+        }
+        ET[t] = val;
+      }
+      if (threadIdx.x < MJ) {
+        const int pj = threadIdx.x;
+        float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pj < np) {
+          const int j = j0 + pj;
+          const float* xj = x + (size_t)(b * N + j) * 3;
+          float r0 = xj[0] - xi0, r1 = xj[1] - xi1, r2 = xj[2] - xi2;
+          float n = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
+          float inv = 1.0f / (n + 1e-5f);
+          float m = mask ? mask[(size_t)row * N + j] : 1.0f;
+          dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, m);
+        }
+        reinterpret_cast<float4*>(dirm)[pj] = dm;
+      }
+      __syncthreads();
+      if (cp < C) {
+        float acc[MJ];
+#pragma unroll
+        for (int q = 0; q < MJ; ++q) acc[q] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          float w = Wx[(size_t)c * C + cp];
+          const float4 ea = reinterpret_cast<const float4*>(ET + c * MJ)[0];
+          const float4 eb = reinterpret_cast<const float4*>(ET + c * MJ)[1];
+          acc[0] = fmaf(ea.x, w, acc[0]); acc[1] = fmaf(ea.y, w, acc[1]);
+          acc[2] = fmaf(ea.z, w, acc[2]); acc[3] = fmaf(ea.w, w, acc[3]);
+          acc[4] = fmaf(eb.x, w, acc[4]); acc[5] = fmaf(eb.y, w, acc[5]);
+          acc[6] = fmaf(eb.z, w, acc[6]); acc[7] = fmaf(eb.w, w, acc[7]);
+        }
+#pragma unroll
+        for (int q = 0; q < MJ; ++q) {
+          float co = tanhf(acc[q]);
+          const float4 dm = reinterpret_cast<const float4*>(dirm)[q];
+          s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
+        }
+      }
+    }
+    if (cp < C) {
+      float* o = ssum + ((size_t)row * C + cp) * 3;
+      o[0] = s0; o[1] = s1; o[2] = s2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// node_post: norms, post_norm_mlp, node_mlp + residual, velocity / position update
+// (layers.py:123-131,142-151,218-232).  NODES nodes per CTA.
+// ------------------------------------------------------------------------------------------
+struct NodePostSmem {
+  float *nrm, *he, *hin, *hp1, *hcomb, *n1, *hout, *den, *den2;
+};
+__device__ inline NodePostSmem node_post_carve(float* sm, const Dims& d) {
+  NodePostSmem s;
+  s.nrm = sm;                       // [NODES][C]
+  s.he = s.nrm + NODES * d.C;       // [NODES][C]
+  s.hin = s.he + NODES * d.C;       // [NODES][H]
+  s.hp1 = s.hin + NODES * d.H;
+  s.hcomb = s.hp1 + NODES * d.H;
+  s.n1 = s.hcomb + NODES * d.H;
+  s.hout = s.n1 + NODES * d.H;
+  s.den = s.hout + NODES * d.H;     // [NODES]
+  s.den2 = s.den + NODES;           // [NODES]
+  return s;
+}
+size_t node_post_smem_bytes(const Dims& d) { return sizeof(float) * (NODES * (2 * d.C + 5 * d.H) + 2 * NODES + 64); }
+
+__global__ void __launch_bounds__(256) k_node_post(Dims d, const SakeLayerParams p, const float* __restrict__ h,
+                                                   const float* __restrict__ x, const float* __restrict__ v,
+                                                   const float* __restrict__ mask, const float* __restrict__ ssum,
+                                                   const float* __restrict__ he_in, float* __restrict__ h_out,
+                                                   float* __restrict__ x_out, float* __restrict__ v_out) {
+  extern __shared__ float sm[];
+  NodePostSmem s = node_post_carve(sm, d);
+  const int H = d.H, C = d.C, N = d.N;
+  const int r0 = blockIdx.x * NODES;
+  const int nn = min(NODES, d.R - r0);
+  if (threadIdx.x < NODES) {
+    float dn = (float)N, dn2 = (float)N;
+    if (mask && threadIdx.x < nn) {
+      float ms = 0.f;
+      for (int j = 0; j < N; ++j) ms += mask[(size_t)(r0 + threadIdx.x) * N + j];
+      dn = ms + 1e-8f;     // layers.py:123
+      dn2 = ms + 1e-10f;   // layers.py:221
+    }
+    s.den[threadIdx.x] = dn;
+    s.den2[threadIdx.x] = dn2;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
+    const int n = t / C, c = t % C;
+    float nr = 0.f, hv = 0.f;
+    if (n < nn) {
+      const float* sp = ssum + ((size_t)(r0 + n) * C + c) * 3;
+      float inv = 1.0f / s.den[n];
+      float a0 = sp[0] * inv, a1 = sp[1] * inv, a2 = sp[2] * inv;
+      nr = a0 * a0 + a1 * a1 + a2 * a2;
+      hv = he_in[(size_t)(r0 + n) * C + c];
+    }
+    s.nrm[t] = nr;
+    s.he[t] = hv;
+  }
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H;
+    s.hin[t] = n < nn ? h[(size_t)r0 * H + t] : 0.f;
+  }
+  __syncthreads();
+  // post_norm_mlp layer 0
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.post0_bias[f];
+    for (int c = 0; c < C; ++c) acc = fmaf(s.nrm[n * C + c], p.post0_kernel[(size_t)c * H + f], acc);
+    s.hp1[t] = siluf_(acc);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.post2_bias[f];
+    for (int g = 0; g < H; ++g) acc = fmaf(s.hp1[n * H + g], p.post2_kernel[(size_t)g * H + f], acc);
+    s.hcomb[t] = d.spatial ? siluf_(acc) : 0.f;
+  }
+  __syncthreads();
+  // node_mlp layer 0 over [h | he | hcomb]
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.node0_bias[f];
+    const float* w = p.node0_kernel + f;
+    for (int g = 0; g < H; ++g) acc = fmaf(s.hin[n * H + g], w[(size_t)g * H], acc);
+    w += (size_t)H * H;
+    for (int c = 0; c < C; ++c) acc = fmaf(s.he[n * C + c], w[(size_t)c * H], acc);
+    w += (size_t)C * H;
+    for (int g = 0; g < H; ++g) acc = fmaf(s.hcomb[n * H + g], w[(size_t)g * H], acc);
+    s.n1[t] = siluf_(acc);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+    const int n = t / H, f = t % H;
+    float acc = p.node2_bias[f];
+    for (int g = 0; g < H; ++g) acc = fmaf(s.n1[n * H + g], p.node2_kernel[(size_t)g * H + f], acc);
+    float ho = s.hin[t] + siluf_(acc);
+    s.hout[t] = ho;
+    if (n < nn) h_out[(size_t)r0 * H + t] = ho;
+  }
+  __syncthreads();
+  // velocity / position update: one warp per node
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < nn; n += (blockDim.x >> 5)) {
+    const size_t row = (size_t)(r0 + n);
+    if (!d.update) {
+      if (lane < 3) {
+        x_out[row * 3 + lane] = x[row * 3 + lane];
+        if (v && v_out) v_out[row * 3 + lane] = v[row * 3 + lane];
+      }
+      continue;
+    }
+    float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+    if (d.spatial) {
+      for (int c = lane; c < C; c += 32) {
+        float wv = p.v_mixing_kernel[c];
+        const float* sp = ssum + (row * C + c) * 3;
+        dv0 = fmaf(wv, sp[0], dv0); dv1 = fmaf(wv, sp[1], dv1); dv2 = fmaf(wv, sp[2], dv2);
+      }
+    }
+    float y = 0.f;
+    if (d.has_v) {
+      for (int f = lane; f < H; f += 32) {
+        float acc = p.vel0_bias[f];
+        for (int g = 0; g < H; ++g) acc = fmaf(s.hout[n * H + g], p.vel0_kernel[(size_t)g * H + f], acc);
+        y = fmaf(siluf_(acc), p.vel2_kernel[f], y);
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      dv0 += __shfl_xor_sync(0xffffffffu, dv0, o);
+      dv1 += __shfl_xor_sync(0xffffffffu, dv1, o);
+      dv2 += __shfl_xor_sync(0xffffffffu, dv2, o);
+      y += __shfl_xor_sync(0xffffffffu, y, o);
+    }
+    if (lane < 3) {
+      float dvv = (lane == 0 ? dv0 : lane == 1 ? dv1 : dv2) / s.den2[n];
+      float vn = dvv;
+      if (d.has_v) vn += 2.0f * sigmoidf_(y) * v[row * 3 + lane];
+      v_out[row * 3 + lane] = vn;
+      x_out[row * 3 + lane] = x[row * 3 + lane] + vn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+template <typename Kern>
+static int ensure_smem(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    if (smem > 227 * 1024) {
+      set_error("generic engine: %zu bytes of shared memory needed (H/A too large)", smem);
+      return SAKE_EUNSUPPORTED;
+    }
+    SAKE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  return 0;
+}
+
+// node_pre + edge + attention: fills sv.nodeproj, sv.e, sv.att, sv.he
+int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
+                const Saved& sv, cudaStream_t st) {
+  int rc;
+  {
+    size_t smem = sizeof(float) * NODES * d.H;
+    if ((rc = ensure_smem(k_node_pre, smem))) return rc;
+    k_node_pre<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, h, p.mlp_in_kernel, p.mlp_in_bias,
+                                                              p.mlp_out0_kernel, p.mlp_out0_bias, sv.nodeproj);
+  }
+  {
+    size_t smem = sizeof(float) * (d.NP + PJ * d.K + 2 * PJ * d.H + PJ);
+    if ((rc = ensure_smem(k_edge_fwd, smem))) return rc;
+    k_edge_fwd<<<d.R, 256, smem, st>>>(d, x, mask, p, sv.nodeproj, sv.e, sv.att);
+  }
+  {
+    size_t smem = sizeof(float) * d.N * d.A;
+    if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
+    k_attn_fwd<<<d.R, 128, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
+  }
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// x_mixing + tanh + sum over senders on CUDA cores: fills sv.ssum
+int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                cudaStream_t st) {
+  size_t smem = sizeof(float) * (d.C * MJ + MJ * 4);
+  int rc;
+  if ((rc = ensure_smem(k_mix_fwd, smem))) return rc;
+  k_mix_fwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sv.e, sv.att, sv.ssum);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv,
+                  cudaStream_t st) {
+  size_t smem = node_post_smem_bytes(d);
+  int rc;
+  if ((rc = ensure_smem(k_node_post, smem))) return rc;
+  k_node_post<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, x, v, mask, sv.ssum, sv.he, h_out, x_out,
+                                                            v_out);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sake

@@ -1,0 +1,118 @@
+"""GPU parity of the CUDA path against the CPU oracle on seeded synthetic molecules: energies,
+forces and every parameter gradient; padded batches against the per-molecule unpadded oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sake_oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_params(p, dt=torch.float64):
+    return O.tree_map(lambda t: t.detach().cpu().to(dt), p)
+
+
+def _setup(H, depth, B, N, S, seed, engine, padded=False, n_min=2, update=True):
+    import sake_b200
+    h, x, mask, am = synth.molecules(seed, B, N, S, padded, n_min)
+    model = sake_b200.DenseSAKEModel(hidden_features=H, out_features=1, depth=depth, update=update, engine=engine)
+    dev = "cuda"
+    ht, xt = torch.tensor(h, device=dev), torch.tensor(x, device=dev)
+    variables = model.init(seed, ht, xt)
+    # non-zero biases so that every bias path is exercised
+    import sake_b200.layers as L
+    flat = L.flatten_tree(variables["params"])
+    g = torch.Generator().manual_seed(seed + 1)
+    for k, t in flat.items():
+        if k.endswith("bias"):
+            t.add_(0.1 * torch.randn(t.shape, generator=g).to(dev))
+    return model, variables["params"], ht, xt, (None if mask is None else torch.tensor(mask, device=dev)), \
+        (None if am is None else torch.tensor(am, device=dev))
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("H,depth,B,N", [(64, 2, 4, 21), (16, 3, 3, 9), (64, 1, 2, 70)])
+def test_energy_forces_vs_oracle(engine, H, depth, B, N):
+    model, p, h, x, _, _ = _setup(H, depth, B, N, 8, 2666 + N, engine)
+    e, f = model.energy_and_forces(p, h, x)
+    po = _oracle_params(p)
+    e0, f0 = O.energy_and_forces(po, h.cpu().double(), x.cpu().double())
+    rel = ((e.cpu().double() - e0).abs() / e0.abs().clamp_min(1e-12)).max().item()
+    ferr = (f.cpu().double() - f0).abs().max().item()
+    assert rel < 1e-5, f"energy rel err {rel:.3e}"
+    assert ferr < 1e-4, f"force abs err {ferr:.3e} (max |F| {f0.abs().max().item():.3e})"
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_param_grads_vs_oracle(engine):
+    import sake_b200.layers as L
+    H, depth, B, N = 64, 2, 3, 12
+    model, p, h, x, _, _ = _setup(H, depth, B, N, 6, 77, engine)
+    flat = L.flatten_tree(p)
+    for t in flat.values():
+        t.requires_grad_(True)
+    y = torch.tensor(np.random.default_rng(5).standard_normal(B).astype(np.float32), device="cuda")
+    e = model.energy(p, h, x)
+    loss = (e - y).abs().mean()                      # scripts/qm9/run.py:79-82
+    grads = torch.autograd.grad(loss, list(flat.values()), allow_unused=True)
+    po = _oracle_params(p)
+    fo = O.tree_flatten(po)
+    for t in fo.values():
+        t.requires_grad_(True)
+    e0 = O.energy(po, h.cpu().double(), x.cpu().double())
+    loss0 = (e0 - y.cpu().double()).abs().mean()
+    g0 = torch.autograd.grad(loss0, list(fo.values()), allow_unused=True)
+    assert abs(loss.item() - loss0.item()) < 1e-5 * max(1.0, abs(loss0.item()))
+    for (k, _), ga, gb in zip(flat.items(), grads, g0):
+        if gb is None:
+            assert ga is None or float(ga.abs().max()) == 0.0, k
+            continue
+        assert ga is not None, k
+        scale = max(float(gb.abs().max()), 1e-6)
+        err = float((ga.cpu().double() - gb).abs().max())
+        assert err < 2e-3 * scale + 1e-6, f"{k}: err {err:.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_padded_batch_matches_unpadded_oracle(engine):
+    """QM9-style padding (scripts/qm9/run.py:23-24,35): real atoms of every padded molecule match the
+    oracle run on that molecule alone, unpadded and unmasked (sake/tests/test_mask.py:202-240)."""
+    H, depth, B, N = 64, 2, 5, 13
+    model, p, h, x, mask, am = _setup(H, depth, B, N, 5, 4242, engine, padded=True, n_min=3)
+    e, f = model.energy_and_forces(p, h, x, mask=mask, atom_mask=am)
+    assert torch.isfinite(e).all() and torch.isfinite(f).all()
+    po = _oracle_params(p)
+    for b in range(B):
+        n = int(am[b].sum().item())
+        e0, f0 = O.energy_and_forces(po, h[b, :n].cpu().double(), x[b, :n].cpu().double())
+        assert abs(e[b].item() - e0.item()) < 1e-5 * max(1.0, abs(e0.item())), (b, e[b].item(), e0.item())
+        assert (f[b, :n].cpu().double() - f0).abs().max().item() < 1e-4
+        assert float(f[b, n:].abs().max()) == 0.0 if n < N else True
+
+
+def test_equivariance():
+    """E(3): h invariant, x equivariant (sake/tests/test_equivariance.py:3-45), on the CUDA path."""
+    model, p, h, x, _, _ = _setup(64, 2, 2, 10, 4, 31, "auto")
+    rng = np.random.default_rng(0)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    Rm = torch.tensor(q.astype(np.float32), device="cuda")
+    t = torch.tensor(rng.standard_normal((1, 3)).astype(np.float32), device="cuda")
+    h0, x0, _ = model(p, h, x)
+    h1, x1, _ = model(p, h, x @ Rm + t)
+    assert torch.allclose(h0, h1, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(x0 @ Rm + t, x1, rtol=1e-4, atol=1e-4)
+
+
+def test_error_paths():
+    import sake_b200
+    from sake_b200._lib import SakeError
+    with pytest.raises(SakeError):
+        sake_b200.DenseSAKELayer(16, 16, cutoff=lambda d: d)
+    layer = sake_b200.DenseSAKELayer(16, 16)
+    h = torch.zeros(3, 16)
+    x = torch.zeros(3, 3)
+    with pytest.raises(SakeError):               # CPU tensors: no CPU fallback
+        p = layer.init(0, h, x)
+        layer.apply(p, h, x)

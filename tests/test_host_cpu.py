@@ -1,0 +1,67 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/sake_b200.h declares,
+argument validation works without a GPU, and the host parameter trees match the flax naming."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from sake_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sake_b200.h")).read()
+    declared = set(re.findall(r"\b(sake_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("sake_stream_t")
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert "sm_100a" in _lib.version()
+
+
+def test_argument_validation_without_gpu():
+    from sake_b200 import _lib
+    d = _lib.SakeDims(1, 0, 64, 4, 50, 0, 0, 0)       # N = 0 is invalid
+    assert _lib.lib.sake_layer_saved_bytes(C.byref(d)) == 0
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == -1
+    assert b"bad dims" in _lib.lib.sake_last_error()
+    d = _lib.SakeDims(2, 5, 16, 4, 50, _lib.SAKE_UPDATE, _lib.ENGINE_TF32X3, 0)   # tcgen05 needs H=64
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == -2
+    d = _lib.SakeDims(2, 5, 16, 4, 50, _lib.SAKE_UPDATE, _lib.ENGINE_AUTO, 0)
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == _lib.ENGINE_FP32
+    assert _lib.lib.sake_layer_saved_bytes(C.byref(d)) > 0
+    rc = _lib.lib.sake_layer_fwd(C.byref(d), None, None, None, None, None, None, None, None, None, 0, None, 0, None)
+    assert rc == -1
+
+
+def test_param_tree_matches_flax_names():
+    """Same leaves / shapes as the reference's init under the shim."""
+    from tests import golden_util as G
+    import sake_b200
+    import sake_b200.layers as L
+    g = G.load("model_h32_d3_n7_v_updlist")
+    model = sake_b200.DenseSAKEModel(hidden_features=32, out_features=1, depth=3, update=[False, True, True])
+    h = torch.zeros(3, 7, 5)
+    x = torch.zeros(3, 7, 3)
+    ours = L.flatten_tree(model.init(0, h, x, v=torch.zeros(3, 7, 3))["params"])
+    ref = g["params"]
+    assert set(ours) == set(ref), (set(ours) ^ set(ref))
+    for k in ref:
+        assert tuple(ours[k].shape) == tuple(ref[k].shape), k
+    g = G.load("layer_h16_n5")
+    layer = sake_b200.DenseSAKELayer(16, 16)
+    ours = L.flatten_tree(layer.init(0, torch.zeros(5, 16), torch.zeros(5, 3))["params"])
+    assert set(ours) == set(g["params"])
+
+
+def test_functional_shapes():
+    # sake/tests/test_functional.py:3-29
+    import sake_b200
+    x = torch.randn(5, 3)
+    r = sake_b200.functional.get_x_minus_xt(x)
+    assert r.shape == (5, 5, 3)
+    assert sake_b200.functional.get_x_minus_xt_norm(r).shape == (5, 5, 1)
+    assert sake_b200.functional.get_h_cat_ht(x).shape == (5, 5, 6)
