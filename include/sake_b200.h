@@ -171,6 +171,36 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
                    const float* x, const float* kernel, const float* bias, const float* dy,
                    float* dx, float* dkernel, float* dbias, sake_stream_t stream);
 
+/* Energy head of the drivers: E[b] = sum_i sum_o y[b,i,o] * atom_mask[b,i]
+ * (scripts/md17/run.py:46-52; masked sum of scripts/qm9/run.py:58-60), plus the cotangent dy that
+ * starts the backward pass:
+ *   mode 0 (forces, scripts/md17/run.py:54-58): dy = atom_mask  (d sum_b E / dy)
+ *   mode 1 (L1 loss, scripts/qm9/run.py:79-82, coloring utils.py:7-8):
+ *           loss += mean_b |std*E[b] + mean - target[b]| ;  dy = sign(.)*std/B * atom_mask
+ * atom_mask [B,N] may be NULL (all ones); target NULL in mode 0; loss is a device scalar that is
+ * accumulated (zero it first). */
+int sake_energy_head(int32_t B, int32_t N, int32_t out_features, int32_t mode, const float* y,
+                     const float* atom_mask, const float* target, float mean, float std,
+                     float* energy, float* loss, float* dy, sake_stream_t stream);
+
+/* One optimiser step over a flat fp32 parameter vector, the chain every training driver uses
+ * (scripts/qm9/run.py:134-138): additive_weight_decay(wd) -> clip(max_delta, element-wise)
+ * -> adam(lr, b1, b2, eps) with bias correction for `step` (1-based).  grad_scale multiplies the
+ * gradients first (1/world_size after an all-reduce sum = lax.pmean, scripts/ani/run_gpu.py:130). */
+int sake_adam_step(int64_t n, float* params, const float* grads, float* m, float* v, int32_t step,
+                   float lr, float b1, float b2, float eps, float weight_decay, float max_delta,
+                   float grad_scale, sake_stream_t stream);
+
+/* Per-launch device timing of the dominant (x_mixing GEMM) kernels with CUDA events recorded on
+ * the launch stream.  begin(capacity) arms it, collect() synchronises the recorded events and
+ * returns how many records were written: ms[i] = duration, kind[i] = 1 mix-forward,
+ * 2 mix-backward (dX), 3 mix-dW, pairs[i] = atom pairs processed by that launch. */
+int sake_profile_begin(int32_t capacity);
+int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capacity);
+
+/* Number of CUDA kernels this library has launched in this process (diagnostic). */
+unsigned long long sake_launch_count(void);
+
 /* Self-test of the tcgen05 building blocks (descriptor encodings, swizzled operand images,
  * TMEM load layout) on the current device; returns 0 when every check passes. max_abs_err out. */
 int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream);

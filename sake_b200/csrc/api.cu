@@ -6,6 +6,8 @@
 namespace sake {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;   // kernels launched by this library (diagnostic counter)
+void note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -194,6 +196,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
 int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,
                    const float* kernel, const float* bias, float* y, sake_stream_t stream) {
   if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !y) { set_error("sake_dense_fwd: bad argument"); return SAKE_EINVAL; }
+  note_launches(1);
   return dense_fwd(rows, in_features, out_features, act, x, kernel, bias, y, (cudaStream_t)stream);
 }
 
@@ -201,8 +204,11 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
                    const float* kernel, const float* bias, const float* dy, float* dx, float* dkernel,
                    float* dbias, sake_stream_t stream) {
   if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !dy) { set_error("sake_dense_bwd: bad argument"); return SAKE_EINVAL; }
+  note_launches(1);
   return dense_bwd(rows, in_features, out_features, act, x, kernel, bias, dy, dx, dkernel, dbias, (cudaStream_t)stream);
 }
+
+unsigned long long sake_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream) {
   return tc_selftest(max_abs_err, (cudaStream_t)stream);

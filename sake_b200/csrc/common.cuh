@@ -58,6 +58,7 @@ __device__ __forceinline__ float celu2f_(float x) { return x > 0.f ? x : 2.0f * 
 __device__ __forceinline__ float dcelu2f_(float x) { return x > 0.f ? 1.0f : expf(0.5f * x); }
 
 void set_error(const char* fmt, ...);
+void note_launches(int n);
 
 #define SAKE_CUDA_CHECK(expr)                                                        \
   do {                                                                               \
@@ -67,6 +68,15 @@ void set_error(const char* fmt, ...);
       return SAKE_ECUDA;                                                             \
     }                                                                                \
   } while (0)
+
+// event profiler hooks around the dominant kernels (optim.cu)
+bool prof_begin_launch(int kind, long long pairs, cudaStream_t st);
+void prof_end_launch(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(int kind, long long pairs, cudaStream_t s) : st(s), on(prof_begin_launch(kind, pairs, s)) {}
+  ~ProfScope() { if (on) prof_end_launch(st); }
+};
 
 // ---- generic fp32 engine ------------------------------------------------------------------
 int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,

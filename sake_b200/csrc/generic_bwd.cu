@@ -837,6 +837,7 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
   k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, v, mask, sv.ssum, sv.he, dh_out, dx_out,
                                                                 dv_out, dh, dx, dv, sc.T, sc.ghe,
                                                                 g ? *g : null_grads(), g != nullptr);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -846,6 +847,7 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   int rc;
   if (!d.spatial) {
     k_mix_bwd_nospatial<<<(unsigned)d.P, 64, 0, st>>>(d, mask, sv.e, sv.att, sc.ghe, sc.ge, sc.gatt, sc.gdir);
+    note_launches(1);
     SAKE_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
@@ -853,16 +855,22 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   k_transpose<<<tg, tb, 0, st>>>(d.C, p.x_mixing_kernel, sc.wxT);
   size_t smem = sizeof(float) * (3 * d.C * MJ + 4 * d.C + MJ * 4);
   if ((rc = ensure_smem(k_mix_bwd, smem))) return rc;
-  k_mix_bwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sc.wxT, sv.e, sv.att, sc.T, sc.ghe, sc.ge,
-                                    sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+  {
+    ProfScope prof(2, d.P, st);
+    k_mix_bwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sc.wxT, sv.e, sv.att, sc.T, sc.ghe, sc.ge,
+                                      sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+  }
   if (gWx) {
+    ProfScope prof(3, d.P, st);
     int splits = (int)min((long long)64, (d.P + 255) / 256);
     if (splits < 1) splits = 1;
     long long pps = (d.P + splits - 1) / splits;
     pps = (pps + 15) / 16 * 16;
     dim3 grid((d.C + 63) / 64, (d.C + 63) / 64, splits);
     k_mix_dw<<<grid, 256, 0, st>>>(d, sv.e, sv.att, sc.gZ, gWx, pps);
+    note_launches(1);
   }
+  note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -891,6 +899,7 @@ int gen_bwd_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
     k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, sc.gproj, dh, g ? *g : null_grads(),
                                                                  g != nullptr);
   }
+  note_launches(3);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -420,6 +420,7 @@ int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const f
     if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
     k_attn_fwd<<<d.R, 128, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
   }
+  note_launches(3);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -430,7 +431,9 @@ int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   size_t smem = sizeof(float) * (d.C * MJ + MJ * 4);
   int rc;
   if ((rc = ensure_smem(k_mix_fwd, smem))) return rc;
+  ProfScope prof(1, d.P, st);
   k_mix_fwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sv.e, sv.att, sv.ssum);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -443,6 +446,7 @@ int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const
   if ((rc = ensure_smem(k_node_post, smem))) return rc;
   k_node_post<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, x, v, mask, sv.ssum, sv.he, h_out, x_out,
                                                             v_out);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,198 @@
+"""Preallocated, stream-ordered execution of a DenseSAKEModel through the C ABI: the energy+forces
+closure (scripts/md17/run.py:46-58) and the energy-L1 training step (scripts/qm9/run.py:74-96,
+134-138) without autograd or per-step allocation.  Every buffer lives in HBM for the lifetime of
+the runner; a step is a fixed sequence of library calls on the current stream, so it can be
+captured in a CUDA graph."""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import lib, check
+from .layers import flatten_tree
+
+
+class ModelRunner:
+    def __init__(self, model, params, B, N, in_features, *, masked=False, train=False, device="cuda",
+                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0):
+        self.model, self.B, self.N, self.F = model, int(B), int(N), int(in_features)
+        self.H, self.L, self.A = model.hidden_features, model.depth, model.n_heads
+        self.out = model.out_features
+        self.masked, self.train, self.dev = masked, train, torch.device(device)
+        self.lr, self.wd, self.max_delta, self.mean, self.std = lr, weight_decay, max_delta, mean, std
+        self.step_count = 0
+        dev, f32 = self.dev, torch.float32
+        # ---- one flat fp32 parameter vector (+ grads, Adam moments): one all-reduce bucket --------
+        flat = flatten_tree(params)
+        self.paths = list(flat.keys())
+        sizes = [flat[k].numel() for k in self.paths]
+        self.n_params = sum(sizes)
+        self.flat_params = torch.empty(self.n_params, device=dev, dtype=f32)
+        self.p, off = {}, 0
+        for k, n in zip(self.paths, sizes):
+            self.p[k] = self.flat_params[off:off + n].view(flat[k].shape)
+            self.p[k].copy_(flat[k])
+            off += n
+        self.g = {}
+        if train:
+            self.flat_grads = torch.zeros(self.n_params, device=dev, dtype=f32)
+            self.adam_m = torch.zeros_like(self.flat_grads)
+            self.adam_v = torch.zeros_like(self.flat_grads)
+            off = 0
+            for k, n in zip(self.paths, sizes):
+                self.g[k] = self.flat_grads[off:off + n].view(flat[k].shape)
+                off += n
+        # ---- per-layer dims / param structs ---------------------------------------------------
+        K = flat["d0/edge_model/kernel/means"].shape[0]
+        self.dims, self.ps, self.gs, self._keep = [], [], [], []
+        has_v = False
+        self.has_v = []
+        for l in range(self.L):
+            upd = model.update_list[l]
+            d = ops.make_dims(B, N, self.H, self.A, K, upd, has_v, masked, model.use_spatial_attention,
+                              model.engine)
+            self.dims.append(d)
+            self.has_v.append(has_v)
+            sub = {k[len("d%d/" % l):]: t for k, t in self.p.items() if k.startswith("d%d/" % l)}
+            ps, keep = ops.params_struct(sub)
+            self.ps.append(ps)
+            self._keep.append(keep)
+            if train:
+                gsub = {k[len("d%d/" % l):]: t for k, t in self.g.items() if k.startswith("d%d/" % l)}
+                gs, keep = ops.params_struct(gsub, _lib.SakeLayerGrads)
+                self.gs.append(gs)
+                self._keep.append(keep)
+            has_v = has_v or upd
+        self.engine = ops.resolve_engine(self.dims[0])
+        # ---- activations -----------------------------------------------------------------------
+        R = B * N
+        self.h_in = torch.zeros(B, N, self.F, device=dev, dtype=f32)
+        self.x_in = torch.zeros(B, N, 3, device=dev, dtype=f32)
+        self.mask = torch.ones(B, N, N, device=dev, dtype=f32) if masked else None
+        self.atom_mask = torch.ones(B, N, device=dev, dtype=f32) if masked else None
+        self.target = torch.zeros(B, device=dev, dtype=f32)
+        self.hs = [torch.empty(B, N, self.H, device=dev, dtype=f32) for _ in range(self.L + 1)]
+        self.xs = [self.x_in] + [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(self.L)]
+        self.vs = [None] + [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(self.L)]
+        self.saved = [ops._buf(ops.saved_bytes(d), dev) for d in self.dims]
+        nscr = max(max(ops.scratch_bytes(d, 0, 0), ops.scratch_bytes(d, 1, int(train))) for d in self.dims)
+        self.scratch = ops._buf(nscr, dev)
+        self.y0 = torch.empty(B, N, self.H, device=dev, dtype=f32)
+        self.y = torch.empty(B, N, self.out, device=dev, dtype=f32)
+        self.energy = torch.empty(B, device=dev, dtype=f32)
+        self.loss = torch.zeros(1, device=dev, dtype=f32)
+        self.dy = torch.empty_like(self.y)
+        self.dy0 = torch.empty_like(self.y0)
+        self.dh = [torch.empty(B, N, self.H, device=dev, dtype=f32) for _ in range(2)]
+        self.dx = [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(2)]
+        self.dv = [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(2)]
+        self.forces = torch.empty(B, N, 3, device=dev, dtype=f32)
+        self.hbm_bytes = sum(t.numel() * t.element_size() for t in
+                             [self.flat_params, self.scratch, *self.saved, *self.hs, *self.xs[1:], *self.vs[1:]])
+
+    # -- inputs ------------------------------------------------------------------------------------
+    def load_inputs(self, h, x, mask=None, atom_mask=None, target=None):
+        """Copy one batch into the resident input buffers (host pinned or device tensors)."""
+        self.h_in.copy_(h, non_blocking=True)
+        self.x_in.copy_(x, non_blocking=True)
+        if self.masked:
+            self.mask.copy_(mask, non_blocking=True)
+            self.atom_mask.copy_(atom_mask, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+
+    def input_bytes(self):
+        n = self.h_in.numel() + self.x_in.numel() + (self.target.numel() if self.train else 0)
+        if self.masked:
+            n += self.mask.numel() + self.atom_mask.numel()
+        return 4 * n
+
+    # -- forward (sake/models.py:56-61) -------------------------------------------------------------
+    def forward(self):
+        p = self.p
+        ops.dense_fwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.hs[0], 0)
+        for l in range(self.L):
+            v_in = self.vs[l] if self.has_v[l] else None
+            upd = self.model.update_list[l]
+            v_out = self.vs[l + 1] if (upd or v_in is not None) else None
+            ops.layer_fwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
+                              self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch)
+        ops.dense_fwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
+                          p.get("embedding_out/layers_0/bias"), self.y0, 1)
+        ops.dense_fwd_raw(self.y0, p["embedding_out/layers_2/kernel"], p.get("embedding_out/layers_2/bias"),
+                          self.y, 0)
+
+    def _head(self, mode):
+        check(lib.sake_energy_head(self.B, self.N, self.out, mode, ops._ptr(self.y), ops._ptr(self.atom_mask),
+                                   ops._ptr(self.target) if mode == 1 else None, self.mean, self.std,
+                                   ops._ptr(self.energy), ops._ptr(self.loss) if mode == 1 else None,
+                                   ops._ptr(self.dy), ops._stream()), "sake_energy_head")
+
+    # -- backward ------------------------------------------------------------------------------------
+    def backward(self, with_grads):
+        p, g = self.p, self.g
+        gk = (lambda k: g[k]) if with_grads else (lambda k: None)
+        ops.dense_bwd_raw(self.y0, p["embedding_out/layers_2/kernel"], p.get("embedding_out/layers_2/bias"),
+                          self.dy, self.dy0, gk("embedding_out/layers_2/kernel"),
+                          gk("embedding_out/layers_2/bias") if "embedding_out/layers_2/bias" in p else None, 0)
+        cur = 0
+        ops.dense_bwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
+                          p.get("embedding_out/layers_0/bias"), self.dy0, self.dh[cur],
+                          gk("embedding_out/layers_0/kernel"), gk("embedding_out/layers_0/bias"), 1)
+        dx_out = dv_out = None
+        for l in reversed(range(self.L)):
+            nxt = 1 - cur
+            v_in = self.vs[l] if self.has_v[l] else None
+            ops.layer_bwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask, self.saved[l],
+                              self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
+                              self.dv[nxt] if v_in is not None else None,
+                              self.gs[l] if with_grads else None, self.scratch)
+            dx_out = self.dx[nxt]
+            dv_out = self.dv[nxt] if v_in is not None else None
+            cur = nxt
+        if with_grads:
+            ops.dense_bwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.dh[cur], None,
+                              g["embedding_in/kernel"], g.get("embedding_in/bias"), 0)
+        self._dx_final = dx_out
+
+    # -- the two driver closures ---------------------------------------------------------------------
+    def energy_forces_step(self):
+        """E[b] and F = -dE/dx for the resident batch (scripts/md17/run.py:46-58)."""
+        self.forward()
+        self._head(0)
+        self.backward(False)
+        torch.neg(self._dx_final, out=self.forces)
+        return self.energy, self.forces
+
+    def train_step(self, allreduce=None):
+        """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
+        optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
+        self.flat_grads.zero_()
+        self.loss.zero_()
+        self.forward()
+        self._head(1)
+        self.backward(True)
+        scale = 1.0
+        if allreduce is not None:
+            scale = allreduce(self.flat_grads)
+        self.step_count += 1
+        check(lib.sake_adam_step(self.n_params, ops._ptr(self.flat_params), ops._ptr(self.flat_grads),
+                                 ops._ptr(self.adam_m), ops._ptr(self.adam_v), self.step_count, self.lr, 0.9,
+                                 0.999, 1e-8, self.wd, self.max_delta, scale, ops._stream()), "sake_adam_step")
+        return self.loss
+
+    def params_tree(self):
+        from .layers import unflatten_tree
+        return unflatten_tree({k: v for k, v in self.p.items()})
+
+
+def profile_begin(capacity=4096):
+    check(lib.sake_profile_begin(int(capacity)), "sake_profile_begin")
+
+
+def profile_collect(capacity=4096):
+    ms = (C.c_float * capacity)()
+    kind = (C.c_int32 * capacity)()
+    pairs = (C.c_int64 * capacity)()
+    n = lib.sake_profile_collect(ms, kind, pairs, capacity)
+    return [(float(ms[i]), int(kind[i]), int(pairs[i])) for i in range(n)]

@@ -116,3 +116,40 @@ def test_error_paths():
     with pytest.raises(SakeError):               # CPU tensors: no CPU fallback
         p = layer.init(0, h, x)
         layer.apply(p, h, x)
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_runner_matches_autograd_path(engine):
+    """The preallocated ModelRunner (bench / production path) equals the autograd-Function path:
+    energies, forces, the L1 training loss and every parameter gradient."""
+    import sake_b200
+    import sake_b200.layers as L
+    from sake_b200.runner import ModelRunner
+    H, depth, B, N, S = 64, 2, 4, 11, 6
+    model, p, h, x, mask, am = _setup(H, depth, B, N, S, 909, engine, padded=True, n_min=4)
+    run = ModelRunner(model, p, B, N, S, masked=True, train=True)
+    y = torch.tensor(np.random.default_rng(1).standard_normal(B).astype(np.float32), device="cuda")
+    run.load_inputs(h, x, mask, am, y)
+    e, f = run.energy_forces_step()
+    e1, f1 = model.energy_and_forces(p, h, x, mask=mask, atom_mask=am)
+    assert torch.allclose(e, e1, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(f, f1, rtol=1e-4, atol=1e-5)
+    # training step: gradients before the Adam update are left in run.g
+    flat = L.flatten_tree(p)
+    for t in flat.values():
+        t.requires_grad_(True)
+    loss1 = (model.energy(p, h, x, mask=mask, atom_mask=am) - y).abs().mean()
+    grads = torch.autograd.grad(loss1, list(flat.values()), allow_unused=True)
+    before = run.flat_params.clone()
+    loss = run.train_step()
+    assert abs(loss.item() - loss1.item()) < 1e-5 * max(1.0, abs(loss1.item()))
+    for (k, _), ga in zip(flat.items(), grads):
+        gb = run.g[k]
+        if ga is None:
+            assert float(gb.abs().max()) == 0.0, k
+            continue
+        scale = max(float(ga.abs().max()), 1e-6)
+        assert float((ga - gb).abs().max()) < 2e-3 * scale + 1e-7, k
+    # Adam moved the parameters (first step: |delta| ~ lr for every non-zero gradient)
+    delta = (run.flat_params - before).abs()
+    assert float(delta.max()) <= 1.1e-3 and float(delta.max()) > 1e-4
