@@ -202,7 +202,8 @@ int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capac
 unsigned long long sake_launch_count(void);
 
 /* Self-test of the tcgen05 building blocks (descriptor encodings, swizzled operand images,
- * TMEM load layout) on the current device; returns 0 when every check passes. max_abs_err out. */
+ * TMEM load layout) on the current device; returns 0 when every check passes.
+ * max_abs_err[0] = 3xTF32 GEMM error, max_abs_err[1] = bf16 GEMM error (two floats, host memory). */
 int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream);
 
 #ifdef __cplusplus

@@ -83,7 +83,7 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
   memset(&L, 0, sizeof(L));
   size_t o = 0;
   if (for_backward) {
-    L.T = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
+    L.T = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 4);
     L.ghe = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
     L.ge = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
     L.gatt = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
@@ -91,7 +91,7 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.gproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
     L.wxT = o; o += align_up(sizeof(float) * (size_t)d.C * d.C);
     L.gZ = o;
-    if (with_grads && engine == SAKE_ENGINE_FP32) o += align_up(sizeof(float) * (size_t)d.P * d.C);
+    if (with_grads) o += align_up(sizeof(float) * (size_t)d.P * d.C);
   }
   L.tc = o;
   if (engine != SAKE_ENGINE_FP32) o += align_up(tc_scratch_bytes(d, engine, for_backward, with_grads));

@@ -34,14 +34,14 @@ struct Saved {
 
 // `scratch` buffer for the backward pass
 struct BwdScratch {
-  float* T;         // [R,C,3] cotangent of ssum
+  float* T;         // [R,C,4] cotangent of ssum (float4 per coefficient, w unused)
   float* ghe;       // [R,C]   cotangent of he
   float* ge;        // [P,H]   cotangent of e
   float* gatt;      // [P,A]   cotangent of att, then of the pre-celu logits q
   float* gdir;      // [P,3]   cotangent of the unit direction
   float* gproj;     // [R,NP]  cotangent of nodeproj
   float* wxT;       // [C,C]   x_mixing kernel transposed
-  float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (generic dW path only)
+  float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (training only, feeds the dW GEMM)
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

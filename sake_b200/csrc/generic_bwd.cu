@@ -286,8 +286,7 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
         }
       }
     }
-    float* tp = T + (row * C + c) * 3;
-    tp[0] = t0; tp[1] = t1v; tp[2] = t2v;
+    *reinterpret_cast<float4*>(T + (row * C + c) * 4) = make_float4(t0, t1v, t2v, 0.f);   // [R][C] float4
   }
 }
 
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__(256) k_mix_bwd(Dims d, const float* __restrict
   const int row = blockIdx.x;
   const int b = row / N;
   const float xi0 = x[(size_t)row * 3 + 0], xi1 = x[(size_t)row * 3 + 1], xi2 = x[(size_t)row * 3 + 2];
-  for (int t = threadIdx.x; t < C * 3; t += blockDim.x) Ts[t] = T[(size_t)row * C * 3 + t];
+  for (int t = threadIdx.x; t < C * 3; t += blockDim.x) Ts[t] = T[((size_t)row * C + t / 3) * 4 + t % 3];
   for (int t = threadIdx.x; t < C; t += blockDim.x) ghes[t] = ghe[(size_t)row * C + t];
   for (int j0 = 0; j0 < N; j0 += MJ) {
     const int np = min(MJ, N - j0);
@@ -842,6 +841,20 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
   return 0;
 }
 
+// dWx += E^T gZ on CUDA cores, gZ [P,C] row-major fp32
+int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st) {
+  ProfScope prof(3, d.P, st);
+  int splits = (int)min((long long)64, (d.P + 255) / 256);
+  if (splits < 1) splits = 1;
+  long long pps = (d.P + splits - 1) / splits;
+  pps = (pps + 15) / 16 * 16;
+  dim3 grid((d.C + 63) / 64, (d.C + 63) / 64, splits);
+  k_mix_dw<<<grid, 256, 0, st>>>(d, sv.e, sv.att, gZ, gWx, pps);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st) {
   int rc;
@@ -860,17 +873,9 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     k_mix_bwd<<<d.R, 256, smem, st>>>(d, x, mask, p.x_mixing_kernel, sc.wxT, sv.e, sv.att, sc.T, sc.ghe, sc.ge,
                                       sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
   }
-  if (gWx) {
-    ProfScope prof(3, d.P, st);
-    int splits = (int)min((long long)64, (d.P + 255) / 256);
-    if (splits < 1) splits = 1;
-    long long pps = (d.P + splits - 1) / splits;
-    pps = (pps + 15) / 16 * 16;
-    dim3 grid((d.C + 63) / 64, (d.C + 63) / 64, splits);
-    k_mix_dw<<<grid, 256, 0, st>>>(d, sv.e, sv.att, sc.gZ, gWx, pps);
-    note_launches(1);
-  }
   note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  if (gWx) return gen_mix_dw_from_gz(d, sv, sc.gZ, gWx, st);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

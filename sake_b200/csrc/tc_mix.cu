@@ -1,9 +1,780 @@
-// placeholder — replaced by the tcgen05 engine
+// tcgen05 engine for the x_mixing GEMM family of DenseSAKELayer (sake/layers.py:95,111) — 89 % of
+// the layer's MACs — with everything that hangs off it fused around the tensor-core tiles:
+//   forward : E = e (x) att built on the fly -> coef = tanh(E Wx) -> ssum[c,d] = sum_j dir_d*m*coef_c
+//   backward: recompute coef, dZ = (m dir.T)(1-coef^2), dE = dZ Wx^T + m*ghe -> g_e, g_att, g_dir
+// Tiles are 128 atom pairs.  Operands are 128-byte-swizzled K-major images in shared memory:
+// the pair-side image is written by builder / epilogue warps, the weight-side image is streamed
+// with bulk async copies (TMA) from a pre-swizzled copy of Wx.  Accumulators live in TMEM.
+// Precision: SAKE_ENGINE_TF32X3 = kind::tf32 with an exact hi/lo split of both operands (3 MMAs:
+// hi*hi + lo*hi + hi*lo) -> fp32-class accuracy; SAKE_ENGINE_BF16 = kind::f16, bf16 operands.
+#include <cuda_bf16.h>
+#include <vector>
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace sake {
-bool tc_supported(const Dims& d) { (void)d; return false; }
-size_t tc_scratch_bytes(const Dims&, int, int, int) { return 0; }
-int tc_mix_fwd(const Dims&, const SakeLayerParams&, const float*, const float*, const Saved&, void*, int, cudaStream_t) { set_error("tcgen05 engine not built"); return SAKE_EUNSUPPORTED; }
-int tc_mix_bwd(const Dims&, const SakeLayerParams&, const float*, const float*, const Saved&, const BwdScratch&, float*, void*, int, cudaStream_t) { set_error("tcgen05 engine not built"); return SAKE_EUNSUPPORTED; }
-int tc_selftest(float* e, cudaStream_t) { if (e) *e = -1.f; set_error("tcgen05 engine not built"); return SAKE_EUNSUPPORTED; }
+using namespace tc;
+
+constexpr int TILE = 128;            // atom pairs per tile
+constexpr int CC = 256;              // C = A*H (the engine is specialised to H=64, A=4)
+constexpr int P_IMG = TILE * 128;    // bytes of one pair-side chunk image   (128 rows x 128 B)
+constexpr int W_IMG = CC * 128;      // bytes of one weight-side chunk image (256 rows x 128 B)
+constexpr int NTHREADS = 448;        // 14 warps: 0 TMA producer, 1 MMA issuer, 2-5 builders, 6-13 epilogue
+
+template <int ENGINE> struct Cfg;
+template <> struct Cfg<SAKE_ENGINE_TF32X3> {
+  static constexpr bool TF32 = true;
+  static constexpr int KCH = 32, NSPLIT = 2, NPROD = 3, NCHUNK = 8, FMT = 2, NSTAGE = 2, EPU = 4;
+};
+template <> struct Cfg<SAKE_ENGINE_BF16> {
+  static constexpr bool TF32 = false;
+  static constexpr int KCH = 64, NSPLIT = 1, NPROD = 1, NCHUNK = 4, FMT = 1, NSTAGE = 4, EPU = 8;
+};
+template <class CF> __host__ __device__ constexpr int stage_bytes() { return CF::NSPLIT * (P_IMG + W_IMG); }
+template <class CF> __host__ __device__ constexpr size_t smem_bytes() {
+  return (size_t)CF::NSTAGE * stage_bytes<CF>() + 2 * TILE * 16 /*dirm*/ + 2 * TILE * 16 /*gdS*/ + 2 * TILE * 16 /*gaS*/ +
+         256 /*barriers*/ + 1024 /*alignment slack*/;
 }
+// products (pair-side split, weight-side split), small terms last
+__device__ __constant__ int c_prod_p[3] = {0, 1, 0};
+__device__ __constant__ int c_prod_w[3] = {0, 0, 1};
+
+struct TileGeom {
+  int N, R, rpt, nseg, js, num_tiles;
+};
+static TileGeom make_geom(const Dims& d) {
+  TileGeom g;
+  g.N = d.N; g.R = d.R;
+  if (d.N <= TILE) { g.rpt = TILE / d.N; g.nseg = 1; g.js = d.N; g.num_tiles = (d.R + g.rpt - 1) / g.rpt; }
+  else { g.rpt = 1; g.nseg = (d.N + TILE - 1) / TILE; g.js = (d.N + g.nseg - 1) / g.nseg; g.num_tiles = d.R * g.nseg; }
+  return g;
+}
+// pair handled by column/row p of a tile
+__device__ __forceinline__ void tile_pair(const TileGeom& g, int tile, int p, bool& valid, int& row, int& j,
+                                          bool& seg_end) {
+  if (g.nseg == 1) {
+    const int lr = p / g.N;
+    j = p - lr * g.N;
+    row = tile * g.rpt + lr;
+    valid = lr < g.rpt && row < g.R;
+    seg_end = valid && (j == g.N - 1);
+  } else {
+    row = tile / g.nseg;
+    const int seg = tile - row * g.nseg;
+    j = seg * g.js + p;
+    const int nj = min(g.js, g.N - seg * g.js);
+    valid = p < nj;
+    seg_end = valid && (p == nj - 1);
+  }
+}
+
+// ---- operand image writers -------------------------------------------------------------------
+template <class CF>
+__device__ __forceinline__ void store_unit(uint8_t* img, int row, int u, const float* vals) {
+  // img: base of the NSPLIT pair-side images of one stage; vals: EPU consecutive K elements
+  const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)u);
+  if constexpr (CF::TF32) {
+    float4 hi, lo;
+    split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+    split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+    *reinterpret_cast<float4*>(img + off) = hi;
+    *reinterpret_cast<float4*>(img + P_IMG + off) = lo;
+  } else {
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(vals[0], vals[1]);
+    __nv_bfloat162 b1 = __floats2bfloat162_rn(vals[2], vals[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(vals[4], vals[5]);
+    __nv_bfloat162 b3 = __floats2bfloat162_rn(vals[6], vals[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+    pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(img + off) = pk;
+  }
+}
+
+// E chunk kc of one pair row: E[c = f*4+a] = e[f]*att[a]
+template <class CF>
+__device__ __forceinline__ void build_E_chunk(uint8_t* img, int row, int kc, const float* e, const float4& at) {
+  if constexpr (CF::TF32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float ef = e[kc * 8 + u];
+      float vals[4] = {ef * at.x, ef * at.y, ef * at.z, ef * at.w};
+      store_unit<CF>(img, row, u, vals);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float e0 = e[kc * 16 + 2 * u], e1 = e[kc * 16 + 2 * u + 1];
+      float vals[8] = {e0 * at.x, e0 * at.y, e0 * at.z, e0 * at.w, e1 * at.x, e1 * at.y, e1 * at.z, e1 * at.w};
+      store_unit<CF>(img, row, u, vals);
+    }
+  }
+}
+
+// ---- weight image preparation ------------------------------------------------------------------
+// w1img[kc][split][row=c'][128B]: K index = c      (GEMM1: Z = E Wx)
+// w2img[q ][split][row=c ][128B]: K index = c', ring order q -> chunk (q%2)*(NCHUNK/2) + q/2 (GEMM2: dE = dZ Wx^T)
+template <int ENGINE>
+__global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1img, uint8_t* __restrict__ w2img) {
+  using CF = Cfg<ENGINE>;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_img = CF::NCHUNK * CC * 8;
+  if (t >= 2 * per_img) return;
+  const int which = t / per_img;
+  int r = t % per_img;
+  const int chunk = r / (CC * 8);
+  r %= CC * 8;
+  const int row = r / 8, u = r % 8;
+  float vals[CF::EPU];
+#pragma unroll
+  for (int i = 0; i < CF::EPU; ++i) {
+    const int k = u * CF::EPU + i;
+    if (which == 0) {
+      vals[i] = Wx[(size_t)(chunk * CF::KCH + k) * CC + row];
+    } else {
+      const int kc2 = (chunk % 2) * (CF::NCHUNK / 2) + chunk / 2;
+      vals[i] = Wx[(size_t)row * CC + kc2 * CF::KCH + k];
+    }
+  }
+  uint8_t* base = (which == 0 ? w1img : w2img) + (size_t)chunk * CF::NSPLIT * W_IMG;
+  const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)u);
+  if constexpr (CF::TF32) {
+    float4 hi, lo;
+    split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+    split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + W_IMG + off) = lo;
+  } else {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(vals[2 * i], vals[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---- shared-memory carve-up -----------------------------------------------------------------
+template <class CF>
+struct Smem {
+  uint8_t* stages;
+  float4* dirm;   // [2][TILE]  (dir*m xyz, segment-end flag)            forward
+  float4* gdS;    // [2][TILE]  partial g_dir of the two column halves     backward
+  float4* gaS;    // [2][TILE]  partial g_att of the two column halves     backward
+  uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty;
+  uint32_t* tmem_ptr;
+  __device__ Smem(uint8_t* raw) {
+    uint8_t* b = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    stages = b;
+    dirm = reinterpret_cast<float4*>(b + (size_t)CF::NSTAGE * stage_bytes<CF>());
+    gdS = dirm + 2 * TILE;
+    gaS = gdS + 2 * TILE;
+    full_w = reinterpret_cast<uint64_t*>(gaS + 2 * TILE);
+    full_e = full_w + CF::NSTAGE;
+    empty = full_e + CF::NSTAGE;
+    acc_full = empty + CF::NSTAGE;      // [2]
+    acc_empty = acc_full + 2;           // [2]
+    tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  }
+  __device__ uint8_t* p_img(int s) const { return stages + (size_t)s * stage_bytes<CF>(); }
+  __device__ uint8_t* w_img(int s) const { return stages + (size_t)s * stage_bytes<CF>() + CF::NSPLIT * P_IMG; }
+};
+
+// =================================================================================================
+// forward:  D^T[c' (lane), pair (column)] = sum_c Wx[c][c'] * E[pair][c]
+//   A = weight image (M = 128 of the 256 c' per MMA, two halves), B = E image (N = 128 pairs)
+//   -> every thread of the epilogue owns one coefficient c' and walks the 128 pairs of the tile, so
+//      the sum over senders j (layers.py:123,127) is a thread-local accumulation.
+// =================================================================================================
+template <int ENGINE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
+             const float* __restrict__ att, const uint8_t* __restrict__ w1img, float* __restrict__ ssum) {
+  using CF = Cfg<ENGINE>;
+  extern __shared__ uint8_t smem_raw[];
+  Smem<CF> sm(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 128); mbar_init(sm.empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(sm.acc_full + b, 1); mbar_init(sm.acc_empty + b, 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(sm.tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+  const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer (TMA)
+    if (lane == 0) {
+      int pos = 0;
+      for (int it = 0; it < ntl; ++it)
+        for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
+          const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          mbar_wait(sm.empty + s, (n & 1) ^ 1);
+          mbar_arrive_expect_tx(sm.full_w + s, CF::NSPLIT * W_IMG);
+          for (int sp = 0; sp < CF::NSPLIT; ++sp)
+            bulk_g2s(sm.w_img(s) + sp * W_IMG, w1img + ((size_t)kc * CF::NSPLIT + sp) * W_IMG, W_IMG, sm.full_w + s);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(CF::FMT, 128, TILE);
+      int pos = 0;
+      for (int it = 0; it < ntl; ++it) {
+        const int buf = it & 1, use = it >> 1;
+        mbar_wait(sm.acc_empty + buf, (use & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
+          const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          mbar_wait(sm.full_w + s, n & 1);
+          mbar_wait(sm.full_e + s, n & 1);
+          tc_fence_after();
+          const uint32_t wbase = smem_u32(sm.w_img(s)), pbase = smem_u32(sm.p_img(s));
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const uint32_t d = tmem_base + buf * 256 + mh * 128;
+#pragma unroll
+            for (int pr = 0; pr < CF::NPROD; ++pr) {
+              const uint32_t a0 = wbase + c_prod_w[pr] * W_IMG + mh * (128 * 128);
+              const uint32_t b0 = pbase + c_prod_p[pr] * P_IMG;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma<CF::TF32>(d, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc,
+                               (kc | pr | ks) != 0);
+            }
+          }
+          umma_commit(sm.empty + s);
+        }
+        umma_commit(sm.acc_full + buf);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ builders: E image + pair geometry
+    const int p = (warp - 2) * 32 + lane;
+    int pos = 0;
+    for (int it = 0; it < ntl; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int buf = it & 1, use = it >> 1;
+      bool valid, seg_end;
+      int row, j;
+      tile_pair(g, tile, p, valid, row, j, seg_end);
+      float ev[64];
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const size_t prx = (size_t)row * g.N + j;
+        at = *reinterpret_cast<const float4*>(att + prx * 4);
+        const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float4 t4 = __ldg(ep + q);
+          ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
+        }
+        const int b = row / g.N;
+        const float* xi = x + (size_t)row * 3;
+        const float* xj = x + (size_t)(b * g.N + j) * 3;
+        const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
+        const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);   // functional.py:14-17
+        const float inv = 1.0f / (nrm + 1e-5f);                                      // layers.py:115
+        const float m = mask ? mask[prx] : 1.0f;
+        dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, __int_as_float(seg_end ? row + 1 : 0));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q) ev[q] = 0.f;
+      }
+      mbar_wait(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
+      sm.dirm[buf * TILE + p] = dm;
+#pragma unroll
+      for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
+        const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+        mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        build_E_chunk<CF>(sm.p_img(s), p, kc, ev, at);
+        fence_proxy_async();
+        mbar_arrive(sm.full_e + s);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: tanh + sum over senders
+    const int q = warp & 3, mh = (warp - 6) >> 2;
+    const int cp = mh * 128 + q * 32 + lane;
+    const bool accumulate = g.nseg > 1;
+    for (int it = 0; it < ntl; ++it) {
+      const int buf = it & 1, use = it >> 1;
+      mbar_wait(sm.acc_full + buf, use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + mh * 128;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tmem_ld32(taddr + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float4 dm = sm.dirm[buf * TILE + cc * 32 + k];
+          const float co = tanhf(v[k]);
+          s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
+          const int flag = __float_as_int(dm.w);
+          if (flag != 0) {
+            float* o = ssum + ((size_t)(flag - 1) * CC + cp) * 3;
+            if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
+            else { o[0] = s0; o[1] = s1; o[2] = s2; }
+            s0 = 0.f; s1 = 0.f; s2 = 0.f;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(sm.acc_empty + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================
+// backward (dX): per tile  GEMM1  Z[pair (lane), c'] = E Wx          (recompute)
+//                          epi-1  coef = tanh Z; dZ = (m dir.T[c'])(1-coef^2); g_dir += coef*T
+//                          GEMM2  dE[pair, c] = dZ Wx^T
+//                          epi-2  dE += m*ghe;  g_e[f] = sum_a dE*att;  g_att[a] = sum_f dE*e
+//   every epilogue thread owns one pair (TMEM lane), so all reductions over c / c' are thread-local.
+// =================================================================================================
+template <int ENGINE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
+             const float* __restrict__ att, const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
+             const float4* __restrict__ T4, const float* __restrict__ ghe, float* __restrict__ ge,
+             float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out) {
+  using CF = Cfg<ENGINE>;
+  constexpr int NCH = CF::NCHUNK;
+  extern __shared__ uint8_t smem_raw[];
+  Smem<CF> sm(smem_raw);
+  uint64_t* d1_full = sm.acc_full;        // GEMM1 accumulator ready
+  uint64_t* d2_full = sm.acc_full + 1;    // GEMM2 accumulator ready
+  uint64_t* d2_empty = sm.acc_empty;      // GEMM2 accumulator drained
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 128); mbar_init(sm.empty + s, 1); }
+    mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d2_empty, 256); mbar_init(sm.acc_empty + 1, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(sm.tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+  const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int pos = 0;
+      for (int it = 0; it < ntl; ++it)
+        for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
+          const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          const uint8_t* src = (c2 < NCH ? w1img + (size_t)c2 * CF::NSPLIT * W_IMG
+                                         : w2img + (size_t)(c2 - NCH) * CF::NSPLIT * W_IMG);
+          mbar_wait(sm.empty + s, (n & 1) ^ 1);
+          mbar_arrive_expect_tx(sm.full_w + s, CF::NSPLIT * W_IMG);
+          for (int sp = 0; sp < CF::NSPLIT; ++sp)
+            bulk_g2s(sm.w_img(s) + sp * W_IMG, src + (size_t)sp * W_IMG, W_IMG, sm.full_w + s);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(CF::FMT, TILE, CC);
+      int pos = 0;
+      for (int it = 0; it < ntl; ++it) {
+        for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
+          const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          if (c2 == NCH) {                              // before GEMM2 overwrites D2: previous tile drained
+            mbar_wait(d2_empty, (it & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(sm.full_w + s, n & 1);
+          mbar_wait(sm.full_e + s, n & 1);
+          tc_fence_after();
+          const uint32_t wbase = smem_u32(sm.w_img(s)), pbase = smem_u32(sm.p_img(s));
+          const uint32_t d = tmem_base + (c2 < NCH ? 0 : 256);
+          const int kc = c2 < NCH ? c2 : c2 - NCH;
+#pragma unroll
+          for (int pr = 0; pr < CF::NPROD; ++pr) {
+            const uint32_t a0 = pbase + c_prod_p[pr] * P_IMG;
+            const uint32_t b0 = wbase + c_prod_w[pr] * W_IMG;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma<CF::TF32>(d, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc,
+                             (kc | pr | ks) != 0);
+          }
+          umma_commit(sm.empty + s);
+          if (c2 == NCH - 1) umma_commit(d1_full);
+          if (c2 == 2 * NCH - 1) umma_commit(d2_full);
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ builders: E image for GEMM1
+    const int p = (warp - 2) * 32 + lane;
+    for (int it = 0; it < ntl; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      bool valid, seg_end;
+      int row, j;
+      tile_pair(g, tile, p, valid, row, j, seg_end);
+      float ev[64];
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const size_t prx = (size_t)row * g.N + j;
+        at = *reinterpret_cast<const float4*>(att + prx * 4);
+        const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float4 t4 = __ldg(ep + q);
+          ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q) ev[q] = 0.f;
+      }
+      int pos = it * 2 * NCH;
+#pragma unroll
+      for (int kc = 0; kc < NCH; ++kc, ++pos) {
+        const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+        mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        build_E_chunk<CF>(sm.p_img(s), p, kc, ev, at);
+        fence_proxy_async();
+        mbar_arrive(sm.full_e + s);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (thread = pair)
+    const int q = warp & 3, hh = (warp - 6) >> 2;
+    const int p = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int it = 0; it < ntl; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      bool valid, seg_end;
+      int row, j;
+      tile_pair(g, tile, p, valid, row, j, seg_end);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, m = 0.f;
+      size_t prx = 0;
+      const float4* Trow = T4;
+      if (valid) {
+        prx = (size_t)row * g.N + j;
+        const int b = row / g.N;
+        const float* xi = x + (size_t)row * 3;
+        const float* xj = x + (size_t)(b * g.N + j) * 3;
+        const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
+        const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
+        const float inv = 1.0f / (nrm + 1e-5f);
+        m = mask ? mask[prx] : 1.0f;
+        d0 = r0 * inv * m; d1 = r1 * inv * m; d2 = r2 * inv * m;
+        Trow = T4 + (size_t)row * CC;
+      }
+      // ---------------- epilogue 1: dZ chunks for GEMM2 (this half owns ring slots of parity hh)
+      mbar_wait(d1_full, it & 1);
+      tc_fence_after();
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 1
+      for (int qq = 0; qq < NCH / 2; ++qq) {
+        const int kc2 = hh * (NCH / 2) + qq;
+        const int pos = it * 2 * NCH + NCH + 2 * qq + hh;
+        const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+        float dz[CF::KCH];
+#pragma unroll
+        for (int part = 0; part < CF::KCH / 32; ++part) {
+          float v[32];
+          tmem_ld32(lane_addr + kc2 * CF::KCH + part * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int cpi = kc2 * CF::KCH + part * 32 + k;
+            const float co = tanhf(v[k]);
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) t4 = __ldg(Trow + cpi);
+            const float gco = d0 * t4.x + d1 * t4.y + d2 * t4.z;
+            g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
+            dz[part * 32 + k] = gco * (1.0f - co * co);
+          }
+        }
+        if (gZ_out != nullptr && valid) {
+          float4* o = reinterpret_cast<float4*>(gZ_out + prx * CC + kc2 * CF::KCH);
+#pragma unroll
+          for (int k = 0; k < CF::KCH / 4; ++k) o[k] = make_float4(dz[4 * k], dz[4 * k + 1], dz[4 * k + 2], dz[4 * k + 3]);
+        }
+        mbar_wait(sm.empty + s, (n & 1) ^ 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) store_unit<CF>(sm.p_img(s), p, u, dz + u * CF::EPU);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(sm.full_e + s);
+      }
+      sm.gdS[hh * TILE + p] = make_float4(g0, g1, g2, 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hh == 0 && valid) {
+        const float4 a = sm.gdS[p], bq = sm.gdS[TILE + p];
+        float* o = gdir + prx * 3;
+        o[0] = (a.x + bq.x) * m; o[1] = (a.y + bq.y) * m; o[2] = (a.z + bq.z) * m;
+      }
+      // ---------------- epilogue 2: dE -> g_e, g_att   (this half owns f in [32 hh, 32 hh + 32))
+      mbar_wait(d2_full, it & 1);
+      tc_fence_after();
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) at = *reinterpret_cast<const float4*>(att + prx * 4);
+      float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, ga3 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tmem_ld32(lane_addr + 256 + hh * 128 + cc * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int f0 = hh * 32 + cc * 8;
+          const float4* gh4 = reinterpret_cast<const float4*>(ghe + (size_t)row * CC) + f0;
+          const float4* e4 = reinterpret_cast<const float4*>(e + prx * 64 + f0);
+          const float4 ea = __ldg(e4), eb = __ldg(e4 + 1);
+          const float ef[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+          float gev[8];
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const float4 gh = __ldg(gh4 + k8);
+            const float x0 = fmaf(m, gh.x, v[4 * k8]), x1 = fmaf(m, gh.y, v[4 * k8 + 1]),
+                        x2 = fmaf(m, gh.z, v[4 * k8 + 2]), x3 = fmaf(m, gh.w, v[4 * k8 + 3]);
+            gev[k8] = x0 * at.x + x1 * at.y + x2 * at.z + x3 * at.w;
+            ga0 = fmaf(x0, ef[k8], ga0); ga1 = fmaf(x1, ef[k8], ga1);
+            ga2 = fmaf(x2, ef[k8], ga2); ga3 = fmaf(x3, ef[k8], ga3);
+          }
+          float4* o = reinterpret_cast<float4*>(ge + prx * 64 + f0);
+          o[0] = make_float4(gev[0], gev[1], gev[2], gev[3]);
+          o[1] = make_float4(gev[4], gev[5], gev[6], gev[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(d2_empty);
+      sm.gaS[hh * TILE + p] = make_float4(ga0, ga1, ga2, ga3);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hh == 0 && valid) {
+        const float4 a = sm.gaS[p], bq = sm.gaS[TILE + p];
+        *reinterpret_cast<float4*>(gatt + prx * 4) = make_float4(a.x + bq.x, a.y + bq.y, a.z + bq.z, a.w + bq.w);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================
+// self-test: D[128 x 256] = A[128 x K] * B[256 x K]^T through the same descriptors / images / TMEM loads
+// =================================================================================================
+template <int ENGINE>
+__global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B,
+                                                        float* __restrict__ D, int nchunk) {
+  using CF = Cfg<ENGINE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* pimg = base;                                  // [nchunk][NSPLIT][P_IMG]
+  uint8_t* wimg = base + (size_t)nchunk * CF::NSPLIT * P_IMG;    // [nchunk][NSPLIT][W_IMG]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wimg + (size_t)nchunk * CF::NSPLIT * W_IMG);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int Kt = nchunk * CF::KCH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<256>(tptr);
+  for (int kc = 0; kc < nchunk; ++kc)
+    for (int u = 0; u < 8; ++u) {
+      float vals[CF::EPU];
+      const int r = threadIdx.x;
+      for (int i = 0; i < CF::EPU; ++i) vals[i] = A[(size_t)r * Kt + kc * CF::KCH + u * CF::EPU + i];
+      store_unit<CF>(pimg + (size_t)kc * CF::NSPLIT * P_IMG, r, u, vals);
+      for (int rr = r; rr < CC; rr += 128) {
+        for (int i = 0; i < CF::EPU; ++i) vals[i] = B[(size_t)rr * Kt + kc * CF::KCH + u * CF::EPU + i];
+        uint8_t* wb = wimg + (size_t)kc * CF::NSPLIT * W_IMG;
+        const uint32_t off = sw128_offset((uint32_t)rr, (uint32_t)u);
+        if constexpr (CF::TF32) {
+          float4 hi, lo;
+          split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+          split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+          *reinterpret_cast<float4*>(wb + off) = hi;
+          *reinterpret_cast<float4*>(wb + W_IMG + off) = lo;
+        } else {
+          uint32_t pk[4];
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(vals[2 * i], vals[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(wb + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = umma_idesc(CF::FMT, TILE, CC);
+    for (int kc = 0; kc < nchunk; ++kc)
+      for (int pr = 0; pr < CF::NPROD; ++pr)
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a0 = smem_u32(pimg + (size_t)kc * CF::NSPLIT * P_IMG + c_prod_p[pr] * P_IMG) + ks * 32;
+          const uint32_t b0 = smem_u32(wimg + (size_t)kc * CF::NSPLIT * W_IMG + c_prod_w[pr] * W_IMG) + ks * 32;
+          umma<CF::TF32>(tmem_base, umma_desc_k_sw128(a0), umma_desc_k_sw128(b0), idesc, (kc | pr | ks) != 0);
+        }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int cc = 0; cc < 8; ++cc) {
+    float v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+    tmem_ld_wait();
+    for (int k = 0; k < 32; ++k) D[(size_t)(warp * 32 + lane) * CC + cc * 32 + k] = v[k];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
+
+template <class CF> static size_t wimg_bytes() { return (size_t)CF::NCHUNK * CF::NSPLIT * W_IMG; }
+
+size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads) {
+  (void)d; (void)for_backward; (void)with_param_grads;
+  size_t w = engine == SAKE_ENGINE_BF16 ? wimg_bytes<Cfg<SAKE_ENGINE_BF16>>() : wimg_bytes<Cfg<SAKE_ENGINE_TF32X3>>();
+  return 2 * w + 1024;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int ENGINE>
+static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                       void* scratch, cudaStream_t st) {
+  using CF = Cfg<ENGINE>;
+  uint8_t* w1 = (uint8_t*)scratch;
+  uint8_t* w2 = w1 + wimg_bytes<CF>();
+  TileGeom g = make_geom(d);
+  const int prep_threads = 2 * CF::NCHUNK * CC * 8;
+  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2);
+  if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mix_fwd<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes<CF>()));
+    attr_set = true;
+  }
+  const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+  {
+    ProfScope prof(1, d.P, st);
+    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, sv.ssum);
+  }
+  note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st);
+
+template <int ENGINE>
+static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                       const BwdScratch& sc, float* gWx, void* scratch, cudaStream_t st) {
+  using CF = Cfg<ENGINE>;
+  uint8_t* w1 = (uint8_t*)scratch;
+  uint8_t* w2 = w1 + wimg_bytes<CF>();
+  TileGeom g = make_geom(d);
+  const int prep_threads = 2 * CF::NCHUNK * CC * 8;
+  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mix_bwd<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes<CF>()));
+    attr_set = true;
+  }
+  const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
+  {
+    ProfScope prof(2, d.P, st);
+    k_tc_mix_bwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
+                                                                  reinterpret_cast<const float4*>(sc.T), sc.ghe, sc.ge,
+                                                                  sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+  }
+  note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  if (gWx) return gen_mix_dw_from_gz(d, sv, sc.gZ, gWx, st);
+  return 0;
+}
+
+int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+               void* tc_scratch, int engine, cudaStream_t st) {
+  if (engine == SAKE_ENGINE_BF16) return tc_fwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, tc_scratch, st);
+  return tc_fwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, tc_scratch, st);
+}
+
+int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+               const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, cudaStream_t st) {
+  if (engine == SAKE_ENGINE_BF16) return tc_bwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, sc, gWx, tc_scratch, st);
+  return tc_bwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, sc, gWx, tc_scratch, st);
+}
+
+// ---- self-test ------------------------------------------------------------------------------------
+template <int ENGINE>
+static int selftest_one(float* max_err, cudaStream_t st) {
+  using CF = Cfg<ENGINE>;
+  const int nchunk = 2, Kt = nchunk * CF::KCH;
+  std::vector<float> A((size_t)TILE * Kt), B((size_t)CC * Kt), D((size_t)TILE * CC);
+  uint32_t seed = 12345u;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : A) v = rnd();
+  for (auto& v : B) v = rnd();
+  float *dA, *dB, *dD;
+  SAKE_CUDA_CHECK(cudaMalloc(&dA, A.size() * 4));
+  SAKE_CUDA_CHECK(cudaMalloc(&dB, B.size() * 4));
+  SAKE_CUDA_CHECK(cudaMalloc(&dD, D.size() * 4));
+  SAKE_CUDA_CHECK(cudaMemcpyAsync(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice, st));
+  SAKE_CUDA_CHECK(cudaMemcpyAsync(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice, st));
+  const size_t smem = (size_t)nchunk * CF::NSPLIT * (P_IMG + W_IMG) + 1024 + 64;
+  SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_selftest<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_selftest<ENGINE><<<1, 128, smem, st>>>(dA, dB, dD, nchunk);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  SAKE_CUDA_CHECK(cudaMemcpyAsync(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost, st));
+  SAKE_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  double worst = 0.0;
+  for (int r = 0; r < TILE; ++r)
+    for (int c = 0; c < CC; ++c) {
+      double ref = 0.0;
+      for (int k = 0; k < Kt; ++k) ref += (double)A[(size_t)r * Kt + k] * (double)B[(size_t)c * Kt + k];
+      double err = fabs(ref - (double)D[(size_t)r * CC + c]);
+      if (err > worst) worst = err;
+    }
+  *max_err = (float)worst;
+  return 0;
+}
+
+int tc_selftest(float* max_abs_err, cudaStream_t st) {
+  float e1 = 0.f, e2 = 0.f;
+  int rc = selftest_one<SAKE_ENGINE_TF32X3>(&e1, st);
+  if (rc) return rc;
+  rc = selftest_one<SAKE_ENGINE_BF16>(&e2, st);
+  if (rc) return rc;
+  if (max_abs_err) { max_abs_err[0] = e1; max_abs_err[1] = e2; }
+  if (!(e1 < 1e-5f)) { set_error("tcgen05 selftest: tf32x3 max abs err %g", e1); return SAKE_ECUDA; }
+  if (!(e2 < 5e-2f)) { set_error("tcgen05 selftest: bf16 max abs err %g", e2); return SAKE_ECUDA; }
+  return 0;
+}
+
+}  // namespace sake

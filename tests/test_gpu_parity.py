@@ -153,3 +153,14 @@ def test_runner_matches_autograd_path(engine):
     # Adam moved the parameters (first step: |delta| ~ lr for every non-zero gradient)
     delta = (run.flat_params - before).abs()
     assert float(delta.max()) <= 1.1e-3 and float(delta.max()) > 1e-4
+
+
+def test_tcgen05_selftest():
+    """Descriptor encodings, swizzled operand images and the TMEM load layout on the real device."""
+    import ctypes as C
+    from sake_b200 import _lib
+    err = (C.c_float * 2)()
+    rc = _lib.lib.sake_selftest_tcgen05(err, None)
+    torch.cuda.synchronize()
+    assert rc == 0, (_lib.lib.sake_last_error().decode(), err[0], err[1])
+    assert err[0] < 1e-5 and err[1] < 5e-2
