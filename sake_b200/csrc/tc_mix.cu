@@ -448,6 +448,13 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         fence_proxy_async();
         mbar_arrive(sm.full_e + s);
       }
+      // The GEMM2 ring slots of this tile are filled by the epilogue warps.  A parity wait can only tell
+      // adjacent phases apart, so walk through those slots too (no work) to stay phase-synchronised with
+      // the `empty` barriers before building the next tile's chunks.
+      for (int kc = 0; kc < NCH; ++kc, ++pos) {
+        const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+        mbar_wait(sm.empty + s, (n & 1) ^ 1);
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (thread = pair)

@@ -164,3 +164,38 @@ def test_tcgen05_selftest():
     torch.cuda.synchronize()
     assert rc == 0, (_lib.lib.sake_last_error().decode(), err[0], err[1])
     assert err[0] < 1e-5 and err[1] < 5e-2
+
+
+@pytest.mark.parametrize("engine", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("B,N,padded", [(64, 29, True), (40, 21, False), (3, 200, False)])
+def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
+    """More 128-pair tiles than SMs (persistent multi-tile pipeline, every ring/phase wrap) and rows
+    split over several tiles (N > 128): tcgen05 engines against the generic fp32 CUDA engine."""
+    import sake_b200
+    import sake_b200.layers as L
+    from sake_b200.runner import ModelRunner
+    S, depth = 6, 2
+    h, x, mask, am = synth.molecules(7 + N, B, N, S, padded, 5)
+    y = np.random.default_rng(3).standard_normal(B).astype(np.float32)
+    dev = "cuda"
+    T = lambda a: None if a is None else torch.tensor(a, device=dev)
+    outs = {}
+    for eng in ("fp32", engine):
+        model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=depth, engine=eng)
+        params = model.init(5, T(h), T(x))["params"]
+        run = ModelRunner(model, params, B, N, S, masked=padded, train=True)
+        run.load_inputs(T(h), T(x), T(mask), T(am), T(y))
+        e, f = run.energy_forces_step()
+        e, f = e.clone(), f.clone()
+        loss = run.train_step().clone()
+        torch.cuda.synchronize()
+        outs[eng] = (e, f, loss, run.flat_grads.clone(), {k: v.clone() for k, v in run.g.items()})
+    e0, f0, l0, g0, gd0 = outs["fp32"]
+    e1, f1, l1, g1, gd1 = outs[engine]
+    etol, ftol, gtol = (1e-5, 1e-4, 2e-3) if engine == "tf32x3" else (2e-2, 5e-2, 1e-1)
+    assert torch.isfinite(e1).all() and torch.isfinite(f1).all() and torch.isfinite(g1).all()
+    assert ((e1 - e0).abs() / e0.abs().clamp_min(1e-3)).max().item() < etol
+    assert (f1 - f0).abs().max().item() < ftol * max(1.0, f0.abs().max().item() if engine == "bf16" else 1.0)
+    for k in gd0:
+        scale = max(float(gd0[k].abs().max()), 1e-6)
+        assert float((gd1[k] - gd0[k]).abs().max()) < gtol * scale + 1e-7, k
