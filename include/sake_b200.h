@@ -198,6 +198,11 @@ int sake_adam_step(int64_t n, float* params, const float* grads, float* m, float
 int sake_profile_begin(int32_t capacity);
 int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capacity);
 
+/* Diagnostic entry for the weight-gradient contraction kernel: out[xw, gw] += X[P, xw]^T G[P, gw]
+ * (device pointers, fp32 row-major) on the tcgen05 engine `engine` (SAKE_ENGINE_TF32X3 / _BF16). */
+int sake_selftest_xtg(int32_t engine, int64_t P, int32_t xw, int32_t gw, const float* X, const float* G,
+                      float* out, sake_stream_t stream);
+
 /* Number of CUDA kernels this library has launched in this process (diagnostic). */
 unsigned long long sake_launch_count(void);
 

@@ -210,6 +210,17 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
 
 unsigned long long sake_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+int sake_selftest_xtg(int32_t engine, int64_t P, int32_t xw, int32_t gw, const float* X, const float* G, float* out,
+                      sake_stream_t stream) {
+  XtgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = X; a.ldx = xw; a.xw = xw; a.ones_col = -1;
+  a.G = G; a.ldg = gw; a.gw = gw;
+  a.MXpad = (xw + 127) / 128 * 128; a.NG = (gw + 15) / 16 * 16; a.P = P;
+  a.out = out; a.ldo = gw; a.out_rows = xw; a.out_cols = gw;
+  return tc_xtg(a, engine, 0, (cudaStream_t)stream);
+}
+
 int sake_selftest_tcgen05(float* max_abs_err, sake_stream_t stream) {
   return tc_selftest(max_abs_err, (cudaStream_t)stream);
 }

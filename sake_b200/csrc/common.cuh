@@ -74,7 +74,7 @@ bool prof_begin_launch(int kind, long long pairs, cudaStream_t st);
 void prof_end_launch(cudaStream_t st);
 struct ProfScope {
   cudaStream_t st; bool on;
-  ProfScope(int kind, long long pairs, cudaStream_t s) : st(s), on(prof_begin_launch(kind, pairs, s)) {}
+  ProfScope(int kind, long long pairs, cudaStream_t s) : st(s), on(kind > 0 && prof_begin_launch(kind, pairs, s)) {}
   ~ProfScope() { if (on) prof_end_launch(st); }
 };
 
@@ -106,6 +106,19 @@ int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const fl
                const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine,
                cudaStream_t st);
 size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads);
+
+// D[MX x NG] += sum_p X[p][:]^T G[p][:]  (tc_xtg.cu) — every weight-gradient contraction (K = pairs or nodes)
+struct XtgArgs {
+  const float* X; int ldx; int xw;     // X source [P, xw] row-major fp32 (ignored when e != nullptr)
+  const float* e; const float* att;    // X = e (x) att  (xw = 256, feature c = f*4 + head) when e != nullptr
+  int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
+  const float* G; int ldg; int gw;     // G source [P, gw]
+  int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
+  long long P, pairs_per_cta;
+  float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
+  float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
+};
+int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
 bool tc_supported(const Dims& d);
 
 }  // namespace sake

@@ -8,6 +8,7 @@
 // Precision: SAKE_ENGINE_TF32X3 = kind::tf32 with an exact hi/lo split of both operands (3 MMAs:
 // hi*hi + lo*hi + hi*lo) -> fp32-class accuracy; SAKE_ENGINE_BF16 = kind::f16, bf16 operands.
 #include <cuda_bf16.h>
+#include <string.h>
 #include <vector>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -721,7 +722,16 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
-  if (gWx) return gen_mix_dw_from_gz(d, sv, sc.gZ, gWx, st);
+  if (gWx) {
+    // dWx[c][c'] += sum_pairs E[pair][c] * dZ[pair][c']  (layers.py:95) on the tensor cores
+    XtgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.e = sv.e; a.att = sv.att; a.xw = CC; a.ones_col = -1;
+    a.G = sc.gZ; a.ldg = CC; a.gw = CC;
+    a.MXpad = CC; a.NG = CC; a.P = d.P;
+    a.out = gWx; a.ldo = CC; a.out_rows = CC; a.out_cols = CC;
+    return tc_xtg(a, ENGINE, 3, st);
+  }
   return 0;
 }
 
