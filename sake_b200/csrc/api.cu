@@ -33,7 +33,8 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->C = s->A * s->H;
   d->R = s->B * s->N;
   d->P = (long long)d->R * s->N;
-  d->NP = 2 * s->K + 2 * s->H;
+  d->Kp = (s->K + 3) / 4 * 4;
+  d->NP = 2 * d->Kp + 2 * s->H;
   d->update = (s->flags & SAKE_UPDATE) != 0;
   d->has_v = (s->flags & SAKE_HAS_V) != 0;
   d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
@@ -77,7 +78,7 @@ static Saved carve_saved(const Dims& d, void* base) {
   return s;
 }
 
-struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, total; };
+struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, edgew, edgeb, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -95,6 +96,13 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
   }
   L.tc = o;
   if (engine != SAKE_ENGINE_FP32) o += align_up(tc_scratch_bytes(d, engine, for_backward, with_grads));
+  L.edgew = o;
+  L.edgeb = o;
+  if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d)) {
+    o += align_up(edge_w_bytes());
+    L.edgeb = o;
+    if (for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
+  }
   L.total = o + 256;
   return L;
 }
@@ -147,7 +155,12 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (d.R == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   Saved sv = carve_saved(d, saved);
-  if ((rc = gen_fwd_pre(d, *params, h, x, mask, sv, st))) return rc;
+  const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
+  if ((rc = gen_node_pre(d, *params, h, sv, st))) return rc;
+  if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, (char*)scratch + SL.edgew, st);
+  else rc = gen_edge_fwd(d, *params, x, mask, sv, st);
+  if (rc) return rc;
+  if ((rc = gen_attn_fwd(d, mask, sv, st))) return rc;
   if (!d.spatial) {
     SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
   } else if (engine == SAKE_ENGINE_FP32) {
@@ -190,7 +203,13 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, st))) return rc;
   }
-  return gen_bwd_post(d, *params, h, x, mask, sv, dh, dx, grads, sc, st);
+  if ((rc = gen_attn_bwd(d, *params, sv, sc, st))) return rc;
+  if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d))
+    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, b + SL.edgew, b + SL.edgeb, engine, st);
+  else
+    rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);
+  if (rc) return rc;
+  return gen_node_pre_bwd(d, *params, h, dh, grads, sc, st);
 }
 
 int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,

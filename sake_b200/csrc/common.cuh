@@ -12,15 +12,17 @@ struct Dims {
   int B, N, H, A, K, C;   // C = A*H
   int R;                  // rows = B*N (one row per receiving atom i)
   long long P;            // pairs = R*N
-  int NP;                 // per-node projection width = 2K + 2H
+  int Kp;                 // K rounded up to a multiple of 4 (16-byte aligned projection blocks)
+  int NP;                 // per-node projection width = 2Kp + 2H
   int update, has_v, has_mask, spatial;
 };
 
 // Layout of the per-node projection buffer nodeproj[R][NP]:
-//   [0,K)        uj = h @ W_in[0:H]            (sender part of mlp_in,   layers.py:30)
-//   [K,2K)       ui = h @ W_in[H:2H] + b_in    (receiver part)
-//   [2K,2K+H)    pj = h @ W_1[0:H]             (sender part of mlp_out[0], layers.py:33-38)
-//   [2K+H,2K+2H) pi = h @ W_1[H:2H] + b_1      (receiver part)
+//   [0,K)            uj = h @ W_in[0:H]            (sender part of mlp_in,   layers.py:30)
+//   [Kp,Kp+K)        ui = h @ W_in[H:2H] + b_in    (receiver part)
+//   [2Kp,2Kp+H)      pj = h @ W_1[0:H]             (sender part of mlp_out[0], layers.py:33-38)
+//   [2Kp+H,2Kp+2H)   pi = h @ W_1[H:2H] + b_1      (receiver part)
+// (Kp = K rounded up to 4; the padding slots are zero)
 // (get_h_cat_ht, functional.py:33-44, is never materialised: Dense on [h_j | h_i] is separable.)
 
 // `saved` buffer (fwd -> bwd), all fp32:
@@ -79,8 +81,10 @@ struct ProfScope {
 };
 
 // ---- generic fp32 engine ------------------------------------------------------------------
-int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
-                const Saved& sv, cudaStream_t st);
+int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st);
+int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                 cudaStream_t st);
+int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
 int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 cudaStream_t st);
 int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
@@ -93,9 +97,11 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const BwdScratch& sc, cudaStream_t st);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
-int gen_bwd_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
-                 const Saved& sv, float* dh, float* dx, const SakeLayerGrads* g, const BwdScratch& sc,
-                 cudaStream_t st);
+int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
+int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, float* dx,
+                 const SakeLayerGrads* g, const BwdScratch& sc, cudaStream_t st);
+int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,
+                     const BwdScratch& sc, cudaStream_t st);
 
 // ---- tcgen05 engine (x_mixing GEMM family) -------------------------------------------------
 // mix forward: ssum[R,C,3] from e, att, x (replaces the generic k_mix_fwd)
@@ -120,5 +126,15 @@ struct XtgArgs {
 };
 int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
 bool tc_supported(const Dims& d);
+
+// ---- tcgen05 engine (edge model), tc_edge.cu ---------------------------------------------------
+bool tc_edge_supported(const Dims& d);
+size_t edge_w_bytes();
+size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads);
+int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                void* wscratch, cudaStream_t st);
+int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, int engine,
+                cudaStream_t st);
 
 }  // namespace sake

@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
         const int j = j0 + pj;
         float dm = s.ts[pj] - p.rbf_means[k];
         float rho = expf(-p.rbf_betas[k] * dm * dm);
-        float u = proj[(size_t)(b * N + j) * d.NP + k] + s.pri[K + k];
+        float u = proj[(size_t)(b * N + j) * d.NP + k] + s.pri[d.Kp + k];
         s.rho[pj * K + k] = rho;
         s.u[pj * K + k] = u;
         s.g[pj * K + k] = rho * u;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
       for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
         const int pj = t / H, f = t % H;
         const int j = j0 + pj;
-        float z = proj[(size_t)(b * N + j) * d.NP + 2 * K + f] + s.pri[2 * K + H + f];
+        float z = proj[(size_t)(b * N + j) * d.NP + 2 * d.Kp + f] + s.pri[2 * d.Kp + H + f];
         z = fmaf(s.ns[pj], w1n[f], z);
         for (int k = 0; k < K; ++k) z = fmaf(s.g[pj * K + k], W1g[(size_t)k * H + f], z);
         s.z1[pj * H + f] = z;
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
           for (int pj = 0; pj < np; ++pj) {
             const int j = j0 + pj;
             const float gz = s.gz1[pj * H + f];
-            atomicAdd(gproj + (size_t)(b * N + j) * d.NP + 2 * K + f, gz);
+            atomicAdd(gproj + (size_t)(b * N + j) * d.NP + 2 * d.Kp + f, gz);
             gpi += gz;
           }
           s.gpi[f] += gpi;
@@ -721,8 +721,8 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
       }
       __syncthreads();
     }
-    for (int k = threadIdx.x; k < K; k += blockDim.x) gproj[(size_t)row * d.NP + K + k] = s.gui[k];
-    for (int f = threadIdx.x; f < H; f += blockDim.x) gproj[(size_t)row * d.NP + 2 * K + H + f] = s.gpi[f];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) gproj[(size_t)row * d.NP + d.Kp + k] = s.gui[k];
+    for (int f = threadIdx.x; f < H; f += blockDim.x) gproj[(size_t)row * d.NP + 2 * d.Kp + H + f] = s.gpi[f];
     if (threadIdx.x < 3) atomicAdd(dx + (size_t)row * 3 + threadIdx.x, s.dxi[threadIdx.x]);
     __syncthreads();
   }
@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
                                                       const float* __restrict__ gproj, float* __restrict__ dh,
                                                       SakeLayerGrads g, int want_grads) {
   extern __shared__ float sm[];
-  const int H = d.H, K = d.K, NP = d.NP;
+  const int H = d.H, K = d.K, NP = d.NP, Kp = d.Kp;
   float* gp = sm;               // [NODES][NP]
   float* hs = gp + NODES * NP;  // [NODES][H]
   const int r0 = blockIdx.x * NODES;
@@ -764,10 +764,10 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
     float acc = 0.f;
     const float* wj = p.mlp_in_kernel + (size_t)f * K;
     const float* wi = p.mlp_in_kernel + (size_t)(H + f) * K;
-    for (int k = 0; k < K; ++k) acc = fmaf(wj[k], gr[k], fmaf(wi[k], gr[K + k], acc));
+    for (int k = 0; k < K; ++k) acc = fmaf(wj[k], gr[k], fmaf(wi[k], gr[Kp + k], acc));
     const float* vj = p.mlp_out0_kernel + (size_t)f * H;
     const float* vi = p.mlp_out0_kernel + (size_t)(H + f) * H;
-    for (int q = 0; q < H; ++q) acc = fmaf(vj[q], gr[2 * K + q], fmaf(vi[q], gr[2 * K + H + q], acc));
+    for (int q = 0; q < H; ++q) acc = fmaf(vj[q], gr[2 * Kp + q], fmaf(vi[q], gr[2 * Kp + H + q], acc));
     dh[(size_t)r0 * H + t] += acc;
   }
   if (want_grads) {
@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
       float sj = 0.f, si = 0.f;
       for (int n = 0; n < nn; ++n) {
         sj = fmaf(hs[n * H + f], gp[n * NP + k], sj);
-        si = fmaf(hs[n * H + f], gp[n * NP + K + k], si);
+        si = fmaf(hs[n * H + f], gp[n * NP + Kp + k], si);
       }
       atomicAdd(g.mlp_in_kernel + t, sj);
       atomicAdd(g.mlp_in_kernel + (size_t)H * K + t, si);
@@ -785,20 +785,20 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
       const int f = t / H, q = t % H;
       float sj = 0.f, si = 0.f;
       for (int n = 0; n < nn; ++n) {
-        sj = fmaf(hs[n * H + f], gp[n * NP + 2 * K + q], sj);
-        si = fmaf(hs[n * H + f], gp[n * NP + 2 * K + H + q], si);
+        sj = fmaf(hs[n * H + f], gp[n * NP + 2 * Kp + q], sj);
+        si = fmaf(hs[n * H + f], gp[n * NP + 2 * Kp + H + q], si);
       }
       atomicAdd(g.mlp_out0_kernel + t, sj);
       atomicAdd(g.mlp_out0_kernel + (size_t)H * H + t, si);
     }
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float sb = 0.f;
-      for (int n = 0; n < nn; ++n) sb += gp[n * NP + K + k];
+      for (int n = 0; n < nn; ++n) sb += gp[n * NP + Kp + k];
       atomicAdd(g.mlp_in_bias + k, sb);
     }
     for (int q = threadIdx.x; q < H; q += blockDim.x) {
       float sb = 0.f;
-      for (int n = 0; n < nn; ++n) sb += gp[n * NP + 2 * K + H + q];
+      for (int n = 0; n < nn; ++n) sb += gp[n * NP + 2 * Kp + H + q];
       atomicAdd(g.mlp_out0_bias + q, sb);
     }
   }
@@ -880,31 +880,38 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   return 0;
 }
 
-int gen_bwd_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
-                 const Saved& sv, float* dh, float* dx, const SakeLayerGrads* g, const BwdScratch& sc,
-                 cudaStream_t st) {
-  (void)mask;
+int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
   int rc;
-  {
-    size_t smem = sizeof(float) * (2 * d.N * d.A + d.A);
-    if ((rc = ensure_smem(k_attn_bwd, smem))) return rc;
-    k_attn_bwd<<<d.R, 128, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
-  }
+  size_t smem = sizeof(float) * (2 * d.N * d.A + d.A);
+  if ((rc = ensure_smem(k_attn_bwd, smem))) return rc;
+  k_attn_bwd<<<d.R, 128, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, float* dx,
+                 const SakeLayerGrads* g, const BwdScratch& sc, cudaStream_t st) {
+  int rc;
   SAKE_CUDA_CHECK(cudaMemsetAsync(sc.gproj, 0, sizeof(float) * (size_t)d.R * d.NP, st));
-  {
-    size_t smem = sizeof(float) * edge_bwd_floats(d);
-    if ((rc = ensure_smem(k_edge_bwd, smem))) return rc;
-    int grid = d.R < 148 * 2 ? d.R : 148 * 2;
-    k_edge_bwd<<<grid, 256, smem, st>>>(d, x, p, sv.nodeproj, sv.e, sc.ge, sc.gatt, sc.gdir, sc.gproj, dx,
-                                        g ? *g : null_grads(), g != nullptr);
-  }
-  {
-    size_t smem = sizeof(float) * NODES * (d.NP + d.H);
-    if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
-    k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, sc.gproj, dh, g ? *g : null_grads(),
-                                                                 g != nullptr);
-  }
-  note_launches(3);
+  size_t smem = sizeof(float) * edge_bwd_floats(d);
+  if ((rc = ensure_smem(k_edge_bwd, smem))) return rc;
+  int grid = d.R < 148 * 2 ? d.R : 148 * 2;
+  k_edge_bwd<<<grid, 256, smem, st>>>(d, x, p, sv.nodeproj, sv.e, sc.ge, sc.gatt, sc.gdir, sc.gproj, dx,
+                                      g ? *g : null_grads(), g != nullptr);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,
+                     const BwdScratch& sc, cudaStream_t st) {
+  int rc;
+  size_t smem = sizeof(float) * NODES * (d.NP + d.H);
+  if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
+  k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, sc.gproj, dh, g ? *g : null_grads(),
+                                                               g != nullptr);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

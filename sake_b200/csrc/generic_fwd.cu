@@ -23,14 +23,19 @@ __global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restric
   for (int t = threadIdx.x; t < nn * d.H; t += blockDim.x) hs[t] = h[(size_t)r0 * d.H + t];
   __syncthreads();
   const int H = d.H, K = d.K;
+  const int Kp = d.Kp;
   for (int o = threadIdx.x; o < d.NP; o += blockDim.x) {
-    const float* w;
-    int ld;
+    const float* w = nullptr;
+    int ld = 0;
     float bias = 0.f;
-    if (o < K) { w = Win + o; ld = K; }
-    else if (o < 2 * K) { w = Win + (size_t)H * K + (o - K); ld = K; bias = bin[o - K]; }
-    else if (o < 2 * K + H) { w = W1 + (o - 2 * K); ld = H; }
-    else { w = W1 + (size_t)H * H + (o - 2 * K - H); ld = H; bias = b1[o - 2 * K - H]; }
+    if (o < Kp) { if (o < K) { w = Win + o; ld = K; } }
+    else if (o < 2 * Kp) { const int k = o - Kp; if (k < K) { w = Win + (size_t)H * K + k; ld = K; bias = bin[k]; } }
+    else if (o < 2 * Kp + H) { w = W1 + (o - 2 * Kp); ld = H; }
+    else { w = W1 + (size_t)H * H + (o - 2 * Kp - H); ld = H; bias = b1[o - 2 * Kp - H]; }
+    if (w == nullptr) {      // padding slot
+      for (int n = 0; n < nn; ++n) proj[(size_t)(r0 + n) * d.NP + o] = 0.f;
+      continue;
+    }
     float acc[NODES];
 #pragma unroll
     for (int n = 0; n < NODES; ++n) acc[n] = bias;
@@ -81,14 +86,14 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
       float tt = expf(-ns[pj]);
       float dm = tt - p.rbf_means[k];
       float rho = expf(-p.rbf_betas[k] * dm * dm);
-      float u = proj[(size_t)(b * N + j) * d.NP + k] + pri[K + k];
+      float u = proj[(size_t)(b * N + j) * d.NP + k] + pri[d.Kp + k];
       gs[pj * K + k] = rho * u;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < np * H; t += blockDim.x) {
       const int pj = t / H, f = t % H;
       const int j = j0 + pj;
-      float z = proj[(size_t)(b * N + j) * d.NP + 2 * K + f] + pri[2 * K + H + f];
+      float z = proj[(size_t)(b * N + j) * d.NP + 2 * d.Kp + f] + pri[2 * d.Kp + H + f];
       z = fmaf(ns[pj], w1n[f], z);
       for (int k = 0; k < K; ++k) z = fmaf(gs[pj * K + k], W1g[(size_t)k * H + f], z);
       a1[pj * H + f] = siluf_(z);
@@ -400,27 +405,37 @@ static int ensure_smem(Kern kern, size_t smem) {
   return 0;
 }
 
-// node_pre + edge + attention: fills sv.nodeproj, sv.e, sv.att, sv.he
-int gen_fwd_pre(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* mask,
-                const Saved& sv, cudaStream_t st) {
+// per-node projections: fills sv.nodeproj
+int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st) {
   int rc;
-  {
-    size_t smem = sizeof(float) * NODES * d.H;
-    if ((rc = ensure_smem(k_node_pre, smem))) return rc;
-    k_node_pre<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, h, p.mlp_in_kernel, p.mlp_in_bias,
-                                                              p.mlp_out0_kernel, p.mlp_out0_bias, sv.nodeproj);
-  }
-  {
-    size_t smem = sizeof(float) * (d.NP + PJ * d.K + 2 * PJ * d.H + PJ);
-    if ((rc = ensure_smem(k_edge_fwd, smem))) return rc;
-    k_edge_fwd<<<d.R, 256, smem, st>>>(d, x, mask, p, sv.nodeproj, sv.e, sv.att);
-  }
-  {
-    size_t smem = sizeof(float) * d.N * d.A;
-    if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
-    k_attn_fwd<<<d.R, 128, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
-  }
-  note_launches(3);
+  size_t smem = sizeof(float) * NODES * d.H;
+  if ((rc = ensure_smem(k_node_pre, smem))) return rc;
+  k_node_pre<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, h, p.mlp_in_kernel, p.mlp_in_bias, p.mlp_out0_kernel,
+                                                            p.mlp_out0_bias, sv.nodeproj);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// edge model + attention logits on CUDA cores: fills sv.e and the logits in sv.att
+int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                 cudaStream_t st) {
+  int rc;
+  size_t smem = sizeof(float) * (d.NP + PJ * d.K + 2 * PJ * d.H + PJ);
+  if ((rc = ensure_smem(k_edge_fwd, smem))) return rc;
+  k_edge_fwd<<<d.R, 256, smem, st>>>(d, x, mask, p, sv.nodeproj, sv.e, sv.att);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// softmax over senders + aggregate: normalises sv.att in place, fills sv.he
+int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st) {
+  int rc;
+  size_t smem = sizeof(float) * d.N * d.A;
+  if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
+  k_attn_fwd<<<d.R, 128, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,563 @@
+// tcgen05 engine for the edge model of DenseSAKELayer (sake/layers.py:12-40,153-165): pair geometry,
+// ExpNormalSmearing RBFs (sake/utils.py:61-65), the two edge-MLP GEMMs and the attention logits,
+// forward and backward, on 128-pair tiles.  One thread owns one pair (= one TMEM lane), so every
+// per-pair chain (RBF, silu, celu, the scalar geometry backward) is thread-local; the GEMMs
+//   Z1 = [rho*u | n] W1[2H:]          (K = 64: 50 RBF channels + distance, zero padded)
+//   E' = silu(z1) [W2 | W2 Ws]        (edge features and pre-activation attention logits in one MMA)
+//   GA1 = g_e W2^T ,  GG = g_z1 W1[2H:]^T          (backward)
+// run on the tensor cores in 3xTF32 (fp32-class accuracy) with the small weight images resident in
+// shared memory.  Two 128-thread groups per CTA work on alternate tiles so that one group's MMA /
+// TMEM traffic overlaps the other group's transcendental work.  h_cat_ht (functional.py:33-44) is
+// never formed: Dense on [h_j | h_i] is separable and arrives as per-node projections.
+#include <string.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_tile.cuh"
+
+namespace sake {
+using namespace tc;
+
+constexpr int EP_IMG = TILE * 128;          // one chunk image, one split (16 KB)
+constexpr int EG_IMG = 4 * EP_IMG;          // pair-side image of one group: 2 K-chunks x {hi, lo}
+constexpr int WA_BYTES = 2 * 2 * 64 * 128;  // rows f  (64), K = k
+constexpr int WB_BYTES = 2 * 2 * 80 * 128;  // rows [e(64) | q(4) | 0(12)], K = f'
+constexpr int WC_BYTES = 2 * 2 * 64 * 128;  // rows f' (64), K = f
+constexpr int WD_BYTES = 2 * 2 * 64 * 128;  // rows k  (64), K = f
+constexpr int EVEC = 256;                   // floats: mu[64] beta[64] b2[64] bq[4] ...
+constexpr int PB_LD = 192;                  // per-pair backward record: gz1[64] | gu[<=60] | g_r[124..126] | w[128..]
+constexpr int EDGE_THREADS = 256;
+
+struct EdgeW {
+  uint8_t *WA, *WB, *WC, *WD;
+  float* vec;
+};
+size_t edge_w_bytes() { return WA_BYTES + WB_BYTES + WC_BYTES + WD_BYTES + EVEC * sizeof(float) + 1024; }
+static EdgeW carve_edge_w(void* p) {
+  EdgeW w;
+  uint8_t* b = (uint8_t*)p;
+  w.WA = b; w.WB = w.WA + WA_BYTES; w.WC = w.WB + WB_BYTES; w.WD = w.WC + WC_BYTES;
+  w.vec = (float*)(w.WD + WD_BYTES);
+  return w;
+}
+
+// ---- weight images --------------------------------------------------------------------------
+__global__ void k_edge_prep(int H, int K, int A, const float* __restrict__ W1, const float* __restrict__ W2,
+                            const float* __restrict__ b2, const float* __restrict__ Ws, const float* __restrict__ bs,
+                            const float* __restrict__ mu, const float* __restrict__ beta, EdgeW w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // units: WA 2*64*8, WB 2*80*8, WC 2*64*8, WD 2*64*8
+  const int nA = 2 * 64 * 8, nB = 2 * 80 * 8, nC = nA, nD = nA;
+  if (t < nA + nB + nC + nD) {
+    int which, r = t, rows;
+    if (r < nA) { which = 0; rows = 64; }
+    else if ((r -= nA) < nB) { which = 1; rows = 80; }
+    else if ((r -= nB) < nC) { which = 2; rows = 64; }
+    else { r -= nC; which = 3; rows = 64; }
+    const int chunk = r / (rows * 8);
+    r %= rows * 8;
+    const int row = r / 8, u = r % 8;
+    float vals[4];
+    for (int i = 0; i < 4; ++i) {
+      const int kk = chunk * 32 + u * 4 + i;
+      float v = 0.f;
+      if (which == 0) { if (kk <= K) v = W1[(size_t)(2 * H + kk) * H + row]; }
+      else if (which == 1) {
+        if (row < 64) v = W2[(size_t)kk * H + row];
+        else if (row < 64 + A) {
+          float s = 0.f;
+          for (int f = 0; f < H; ++f) s = fmaf(W2[(size_t)kk * H + f], Ws[(size_t)f * A + (row - 64)], s);
+          v = s;
+        }
+      }
+      else if (which == 2) v = W2[(size_t)row * H + kk];
+      else { if (row <= K) v = W1[(size_t)(2 * H + row) * H + kk]; }
+      vals[i] = v;
+    }
+    uint8_t* base = (which == 0 ? w.WA : which == 1 ? w.WB : which == 2 ? w.WC : w.WD) + (size_t)chunk * 2 * rows * 128;
+    const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)u);
+    float4 hi, lo;
+    split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+    split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + (size_t)rows * 128 + off) = lo;
+  }
+  if (t < EVEC) {
+    float v = 0.f;
+    if (t < 64) v = t < K ? mu[t] : 0.f;
+    else if (t < 128) v = (t - 64) < K ? beta[t - 64] : 0.f;
+    else if (t < 192) v = b2[t - 128];
+    else if (t < 192 + A) {
+      const int a = t - 192;
+      float s = bs[a];
+      for (int f = 0; f < H; ++f) s = fmaf(b2[f], Ws[(size_t)f * A + a], s);
+      v = s;
+    }
+    w.vec[t] = v;
+  }
+}
+
+struct EdgeArgs {
+  TileGeom g;
+  int K, Kp, NP;
+  const float *x, *mask, *proj;
+  EdgeW w;
+  float *e_out, *logit_out;            // forward outputs  [P,64], [P,4]
+  const float *ge, *gdir;              // backward inputs  [P,64], [P,3]
+  float *PB, *a1buf, *gbuf;            // backward outputs [P,192], [P,64], [P,64] (a1buf/gbuf: training only)
+  int train;
+};
+
+__device__ __forceinline__ void store_unit_tf32(uint8_t* chunk_img, int row, int u, const float* vals) {
+  const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)u);
+  float4 hi, lo;
+  split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+  split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+  *reinterpret_cast<float4*>(chunk_img + off) = hi;
+  *reinterpret_cast<float4*>(chunk_img + EP_IMG + off) = lo;
+}
+
+// one 3xTF32 GEMM: D[128 x N] = A[128 x 64] * B[N x 64]^T, K = 64 = 2 chunks of 32
+__device__ __forceinline__ void edge_gemm(uint32_t d_tmem, uint32_t a_img, uint32_t b_img, int b_rows, uint32_t idesc) {
+  const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a0 = a_img + (c * 2 + pp[pr]) * EP_IMG + ks * 32;
+        const uint32_t b0 = b_img + (c * 2 + pw[pr]) * (b_rows * 128) + ks * 32;
+        umma<true>(d_tmem, umma_desc_k_sw128(a0), umma_desc_k_sw128(b0), idesc, (c | pr | ks) != 0);
+      }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int W_BYTES = BWD ? (WA_BYTES + WC_BYTES + WD_BYTES) : (WA_BYTES + WB_BYTES);
+  uint8_t* sWA = base;
+  uint8_t* sW2 = base + WA_BYTES;                          // fwd: WB ; bwd: WC
+  uint8_t* sWD = base + WA_BYTES + WC_BYTES;               // bwd only
+  uint8_t* imgs = base + W_BYTES;                          // [2 groups][EG_IMG]
+  float* svec = reinterpret_cast<float*>(imgs + 2 * EG_IMG);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(svec + EVEC);
+  uint64_t* mbar = wbar + 1;                               // [2]
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(mbar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = threadIdx.x >> 7, pl = threadIdx.x & 127;
+  if (threadIdx.x == 0) {
+    mbar_init(wbar, 1); mbar_init(mbar, 1); mbar_init(mbar + 1, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(wbar, W_BYTES);
+    bulk_g2s(sWA, a.w.WA, WA_BYTES, wbar);
+    if (BWD) { bulk_g2s(sW2, a.w.WC, WC_BYTES, wbar); bulk_g2s(sWD, a.w.WD, WD_BYTES, wbar); }
+    else bulk_g2s(sW2, a.w.WB, WB_BYTES, wbar);
+  }
+  if (warp == 0) tmem_alloc<512>(tptr);
+  for (int t = threadIdx.x; t < EVEC; t += EDGE_THREADS) svec[t] = a.w.vec[t];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  mbar_wait(wbar, 0);
+  const uint32_t tmem_base = *tptr;
+  const uint32_t tcol = tmem_base + grp * 256;                         // this group's TMEM columns
+  const uint32_t lane_addr = tcol + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* img = imgs + grp * EG_IMG;
+  const uint32_t img_u32 = smem_u32(img);
+  const float* s_mu = svec;
+  const float* s_beta = svec + 64;
+  const float* s_b2 = svec + 128;
+  const float* s_bq = svec + 192;
+  const int K = a.K, Kp = a.Kp, NP = a.NP;
+  const int ntl = (a.g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  uint32_t ph = 0;
+  constexpr uint32_t idesc64 = umma_idesc(2, 128, 64);
+  constexpr uint32_t idesc80 = umma_idesc(2, 128, 80);
+  const int bar_id = 1 + grp;
+
+  for (int it = grp; it < ntl; it += 2) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    bool valid, seg_end;
+    int row, j;
+    tile_pair(a.g, tile, pl, valid, row, j, seg_end);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, nrm = 0.f, tt = 0.f, m = 1.0f;
+    size_t prx = 0;
+    const float* nj = a.proj;
+    const float* ni = a.proj;
+    bool diag = false;
+    if (valid) {
+      prx = (size_t)row * a.g.N + j;
+      const int b = row / a.g.N;
+      diag = (row - b * a.g.N) == j;
+      nj = a.proj + (size_t)(b * a.g.N + j) * NP;
+      ni = a.proj + (size_t)row * NP;
+      const float* xi = a.x + (size_t)row * 3;
+      const float* xj = a.x + (size_t)(b * a.g.N + j) * 3;
+      r0 = xj[0] - xi[0]; r1 = xj[1] - xi[1]; r2 = xj[2] - xi[2];
+      nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);     // functional.py:14-17
+      tt = expf(-nrm);                                                    // utils.py:62-64 (alpha = 1, lower = 0)
+      if (a.mask) m = a.mask[prx];
+    }
+    // ---------------- (a) G = [rho*u | n | 1 | t | 0...]  ->  A operand of GEMM A
+#pragma unroll 4
+    for (int u = 0; u < 16; ++u) {
+      float vals[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        float uj[4] = {0.f, 0.f, 0.f, 0.f}, ui[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * u < Kp) {
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
+          uj[0] = t1.x; uj[1] = t1.y; uj[2] = t1.z; uj[3] = t1.w;
+          ui[0] = t2.x; ui[1] = t2.y; ui[2] = t2.z; ui[3] = t2.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = 4 * u + i;
+          if (k < K) {
+            const float dm = tt - s_mu[k];
+            vals[i] = expf(-s_beta[k] * dm * dm) * (uj[i] + ui[i]);
+          } else if (k == K) vals[i] = nrm;
+          else if (k == K + 1) vals[i] = 1.0f;        // column sums for free in the dW contraction
+          else if (k == K + 2) vals[i] = tt;
+        }
+        if (BWD && a.train) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      }
+      store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    if (pl == 0) {
+      tc_fence_after();
+      edge_gemm(tcol + 0, img_u32, smem_u32(sWA), 64, idesc64);          // Z1 -> cols [0,64)
+      umma_commit(mbar + grp);
+    }
+    mbar_wait(mbar + grp, ph); ph ^= 1;
+    tc_fence_after();
+
+    if (!BWD) {
+      // ---------------- (c) a1 = silu(Z1 + pj[j] + pi[i])  (layers.py:33-38, 23)
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(lane_addr + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float vals[4] = {0.f, 0.f, 0.f, 0.f};
+          if (valid) {
+            const int f0 = half * 32 + 4 * u;
+            const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
+            const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+            vals[0] = siluf_(v[4 * u] + pj.x + pi.x); vals[1] = siluf_(v[4 * u + 1] + pj.y + pi.y);
+            vals[2] = siluf_(v[4 * u + 2] + pj.z + pi.z); vals[3] = siluf_(v[4 * u + 3] + pj.w + pi.w);
+          }
+          store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (pl == 0) {
+        tc_fence_after();
+        edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 80, idesc80);       // E' -> cols [64,144)
+        umma_commit(mbar + grp);
+      }
+      mbar_wait(mbar + grp, ph); ph ^= 1;
+      tc_fence_after();
+      // ---------------- (e) e = E' + b2 ; logits = celu(q) - 1e5*diag - 1e5*(1-m)  (layers.py:24,155-165)
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(lane_addr + 64 + half * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(a.e_out + prx * 64 + half * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int f0 = half * 32 + 4 * u;
+            o[u] = make_float4(v[4 * u] + s_b2[f0], v[4 * u + 1] + s_b2[f0 + 1], v[4 * u + 2] + s_b2[f0 + 2],
+                               v[4 * u + 3] + s_b2[f0 + 3]);
+          }
+        }
+      }
+      {
+        float v[32];
+        tmem_ld32(lane_addr + 128, v);
+        tmem_ld_wait();
+        if (valid) {
+          float s[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            s[q] = celu2f_(v[q] + s_bq[q]);
+            if (diag) s[q] -= 1e5f;
+            if (a.mask) s[q] -= 1e5f * (1.0f - m);
+          }
+          *reinterpret_cast<float4*>(a.logit_out + prx * 4) = make_float4(s[0], s[1], s[2], s[3]);
+        }
+      }
+      tc_fence_before();
+    } else {
+      // ---------------- (c') a1 for the dW2 contraction (training), then GE -> A operand of GEMM C
+      if (a.train) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(lane_addr + half * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(a.a1buf + prx * 64 + half * 32);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int f0 = half * 32 + 4 * u;
+              const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
+              const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+              o[u] = make_float4(siluf_(v[4 * u] + pj.x + pi.x), siluf_(v[4 * u + 1] + pj.y + pi.y),
+                                 siluf_(v[4 * u + 2] + pj.z + pi.z), siluf_(v[4 * u + 3] + pj.w + pi.w));
+            }
+          }
+        }
+      }
+#pragma unroll 4
+      for (int u = 0; u < 16; ++u) {
+        float vals[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u));
+          vals[0] = t4.x; vals[1] = t4.y; vals[2] = t4.z; vals[3] = t4.w;
+        }
+        store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (pl == 0) {
+        tc_fence_after();
+        edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 64, idesc64);       // GA1 = GE W2^T -> cols [64,128)
+        umma_commit(mbar + grp);
+      }
+      mbar_wait(mbar + grp, ph); ph ^= 1;
+      tc_fence_after();
+      // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float z[32], ga[32];
+        tmem_ld32(lane_addr + half * 32, z);
+        tmem_ld32(lane_addr + 64 + half * 32, ga);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float vals[4] = {0.f, 0.f, 0.f, 0.f};
+          if (valid) {
+            const int f0 = half * 32 + 4 * u;
+            const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
+            const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+            vals[0] = ga[4 * u] * dsiluf_(z[4 * u] + pj.x + pi.x);
+            vals[1] = ga[4 * u + 1] * dsiluf_(z[4 * u + 1] + pj.y + pi.y);
+            vals[2] = ga[4 * u + 2] * dsiluf_(z[4 * u + 2] + pj.z + pi.z);
+            vals[3] = ga[4 * u + 3] * dsiluf_(z[4 * u + 3] + pj.w + pi.w);
+            *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+          }
+          store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (pl == 0) {
+        tc_fence_after();
+        edge_gemm(tcol + 128, img_u32, smem_u32(sWD), 64, idesc64);      // GG = GZ1 W1[2H:]^T -> cols [128,192)
+        umma_commit(mbar + grp);
+      }
+      mbar_wait(mbar + grp, ph); ph ^= 1;
+      tc_fence_after();
+      // ---------------- (g) RBF / geometry backward (utils.py:61-65, functional.py:7-19, layers.py:115)
+      float gt = 0.f, gn = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float gg[32];
+        tmem_ld32(lane_addr + 128 + half * 32, gg);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k0 = half * 32 + 4 * u;
+            float gu[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
+            float uj[4] = {0.f, 0.f, 0.f, 0.f}, ui[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k0 < Kp) {
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(nj + k0));
+              const float4 t2 = __ldg(reinterpret_cast<const float4*>(ni + Kp + k0));
+              uj[0] = t1.x; uj[1] = t1.y; uj[2] = t1.z; uj[3] = t1.w;
+              ui[0] = t2.x; ui[1] = t2.y; ui[2] = t2.z; ui[3] = t2.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = k0 + i;
+              if (k < K) {
+                const float dm = tt - s_mu[k];
+                const float rho = expf(-s_beta[k] * dm * dm);
+                gu[i] = gg[4 * u + i] * rho;                                   // d/du
+                const float w = dm * rho * gg[4 * u + i] * (uj[i] + ui[i]);   // dm * rho * d/drho
+                wv[i] = w;
+                gt = fmaf(-2.0f * s_beta[k], w, gt);
+              } else if (k == K) {
+                gn = gg[4 * u + i];                                            // through the distance input of mlp_out[0]
+              }
+            }
+            if (k0 < 60) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 64 + k0) = make_float4(gu[0], gu[1], gu[2], gu[3]);
+            if (a.train) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 128 + k0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        }
+      }
+      if (valid) {
+        gn = fmaf(-tt, gt, gn);                                  // t = exp(-n)
+        const float* gd = a.gdir + prx * 3;
+        const float inv = 1.0f / (nrm + 1e-5f);
+        float g0 = gd[0] * inv, g1 = gd[1] * inv, g2 = gd[2] * inv;
+        gn -= (gd[0] * r0 + gd[1] * r1 + gd[2] * r2) * inv * inv;
+        const float n2 = r0 * r0 + r1 * r1 + r2 * r2;
+        const float gn2 = n2 > 0.f ? gn / (2.0f * nrm) : 0.f;   // relu'(0) = 0 (functional.py:15)
+        g0 = fmaf(2.0f * r0, gn2, g0); g1 = fmaf(2.0f * r1, gn2, g1); g2 = fmaf(2.0f * r2, gn2, g2);
+        if (diag) { g0 = 0.f; g1 = 0.f; g2 = 0.f; }
+        *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 124) = make_float4(g0, g1, g2, 0.f);
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- reductions of the per-pair record over senders / receivers -----------------------------------
+// gproj[n] = [ sum_i gu[(i,n)] | sum_j gu[(n,j)] | sum_i gz1[(i,n)] | sum_j gz1[(n,j)] ],  dx[n] += sum_i g_r[(i,n)] - sum_j g_r[(n,j)]
+__global__ void __launch_bounds__(128) k_pair_reduce(int N, int K, int Kp, int NP, const float* __restrict__ PB,
+                                                     float* __restrict__ gproj, float* __restrict__ dx) {
+  const int n = blockIdx.x;
+  const int b = n / N, a = n - b * N;
+  const int c = threadIdx.x;                               // column of the record [0,128)
+  const float* rowp = PB + ((size_t)n * N) * PB_LD + c;                    // (n, j) j = 0..N-1
+  const float* colp = PB + ((size_t)b * N * N + a) * PB_LD + c;            // (i, n) i = 0..N-1, stride N records
+  float si = 0.f, sj = 0.f;
+  for (int q = 0; q < N; ++q) {
+    si += rowp[(size_t)q * PB_LD];
+    sj += colp[(size_t)q * N * PB_LD];
+  }
+  float* gp = gproj + (size_t)n * NP;
+  if (c < 64) { gp[2 * Kp + c] = sj; gp[2 * Kp + 64 + c] = si; }
+  else if (c < 64 + Kp) {
+    const int k = c - 64;
+    gp[k] = k < K ? sj : 0.f;
+    gp[Kp + k] = k < K ? si : 0.f;
+  } else if (c >= 124 && c < 127) {
+    dx[(size_t)n * 3 + (c - 124)] += sj - si;
+  }
+}
+
+// dmu_k += 2 beta_k S1_k ;  dbeta_k += -(S2_k - mu_k S1_k)   with S1 = sum_p w_pk, S2 = sum_p t_p w_pk
+__global__ void k_mubeta_finish(int K, const float* __restrict__ mu, const float* __restrict__ beta,
+                                const float* __restrict__ extra, float* __restrict__ gmu, float* __restrict__ gbeta) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  const float s1 = extra[128 + k], s2 = extra[PB_LD + 128 + k];
+  gmu[k] += 2.0f * beta[k] * s1;
+  gbeta[k] += -(s2 - mu[k] * s1);
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+bool tc_edge_supported(const Dims& d) { return d.H == 64 && d.A == 4 && d.K <= 58; }
+
+static int edge_prep(const Dims& d, const SakeLayerParams& p, const EdgeW& w, cudaStream_t st) {
+  const int units = 2 * 64 * 8 * 3 + 2 * 80 * 8;
+  k_edge_prep<<<(units + 255) / 256, 256, 0, st>>>(d.H, d.K, d.A, p.mlp_out0_kernel, p.mlp_out2_kernel, p.mlp_out2_bias,
+                                                   p.sem_kernel, p.sem_bias, p.rbf_means, p.rbf_betas, w);
+  note_launches(1);
+  return 0;
+}
+
+static int edge_grid(const TileGeom& g) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int want = (g.num_tiles + 1) / 2;             // two groups per CTA
+  return want < sms ? (want < 1 ? 1 : want) : sms;
+}
+
+int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                void* wscratch, cudaStream_t st) {
+  EdgeW w = carve_edge_w(wscratch);
+  edge_prep(d, p, w, st);
+  EdgeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = make_geom(d);
+  a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
+  a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
+  a.e_out = sv.e; a.logit_out = sv.att;
+  const size_t smem = WA_BYTES + WB_BYTES + 2 * EG_IMG + EVEC * 4 + 64 + 1024;
+  static bool attr = false;
+  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// PB [P,192] | a1buf [P,64] | gbuf [P,64] | extra [2,192]   (a1buf / gbuf only when training)
+size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads) {
+  size_t n = align_up(sizeof(float) * (size_t)d.P * PB_LD) + align_up(sizeof(float) * 2 * PB_LD);
+  if (with_grads) n += 2 * align_up(sizeof(float) * (size_t)d.P * 64);
+  return n;
+}
+
+int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
+                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, int engine,
+                cudaStream_t st) {
+  EdgeW w = carve_edge_w(wscratch);
+  edge_prep(d, p, w, st);
+  char* eb = (char*)escratch;
+  float* PB = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * PB_LD);
+  float* extra = (float*)eb; eb += align_up(sizeof(float) * 2 * PB_LD);
+  float* a1buf = nullptr; float* gbuf = nullptr;
+  if (g) { a1buf = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * 64); gbuf = (float*)eb; }
+  EdgeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = make_geom(d);
+  a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
+  a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
+  a.ge = sc.ge; a.gdir = sc.gdir; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
+  const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + 2 * EG_IMG + EVEC * 4 + 64 + 1024;
+  static bool attr = false;
+  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  k_pair_reduce<<<d.R, 128, 0, st>>>(d.N, d.K, d.Kp, d.NP, PB, sc.gproj, dx);
+  note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  if (g) {
+    int rc;
+    XtgArgs q;
+    // dW2, db2 (layers.py:24):  a1^T g_e
+    memset(&q, 0, sizeof(q));
+    q.X = a1buf; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.ge; q.ldg = 64; q.gw = 64; q.MXpad = 128; q.NG = 64;
+    q.P = d.P; q.out = g->mlp_out2_kernel; q.ldo = 64; q.out_rows = 64; q.out_cols = 64;
+    q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64;
+    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
+    // dW1[2H : 2H+K+1] (RBF channels + distance row, layers.py:22) and the RBF mean / width sums
+    SAKE_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(float) * 2 * PB_LD, st));
+    memset(&q, 0, sizeof(q));
+    q.X = gbuf; q.ldx = 64; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
+    q.P = d.P; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
+    q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD;
+    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
+    k_mubeta_finish<<<1, 64, 0, st>>>(d.K, p.rbf_means, p.rbf_betas, extra, g->rbf_means, g->rbf_betas);
+    // dWs, dbs (layers.py:80):  e^T g_q
+    memset(&q, 0, sizeof(q));
+    q.X = sv.e; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.gw = 4; q.MXpad = 128; q.NG = 16;
+    q.P = d.P; q.out = g->sem_kernel; q.ldo = 4; q.out_rows = 64; q.out_cols = 4;
+    q.extra = g->sem_bias; q.extra_rows = 1; q.extra_ld = 4;
+    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
+    note_launches(1);
+    SAKE_CUDA_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace sake

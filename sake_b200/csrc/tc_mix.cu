@@ -12,11 +12,11 @@
 #include <vector>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_tile.cuh"
 
 namespace sake {
 using namespace tc;
 
-constexpr int TILE = 128;            // atom pairs per tile
 constexpr int CC = 256;              // C = A*H (the engine is specialised to H=64, A=4)
 constexpr int P_IMG = TILE * 128;    // bytes of one pair-side chunk image   (128 rows x 128 B)
 constexpr int W_IMG = CC * 128;      // bytes of one weight-side chunk image (256 rows x 128 B)
@@ -39,35 +39,6 @@ template <class CF> __host__ __device__ constexpr size_t smem_bytes() {
 // products (pair-side split, weight-side split), small terms last
 __device__ __constant__ int c_prod_p[3] = {0, 1, 0};
 __device__ __constant__ int c_prod_w[3] = {0, 0, 1};
-
-struct TileGeom {
-  int N, R, rpt, nseg, js, num_tiles;
-};
-static TileGeom make_geom(const Dims& d) {
-  TileGeom g;
-  g.N = d.N; g.R = d.R;
-  if (d.N <= TILE) { g.rpt = TILE / d.N; g.nseg = 1; g.js = d.N; g.num_tiles = (d.R + g.rpt - 1) / g.rpt; }
-  else { g.rpt = 1; g.nseg = (d.N + TILE - 1) / TILE; g.js = (d.N + g.nseg - 1) / g.nseg; g.num_tiles = d.R * g.nseg; }
-  return g;
-}
-// pair handled by column/row p of a tile
-__device__ __forceinline__ void tile_pair(const TileGeom& g, int tile, int p, bool& valid, int& row, int& j,
-                                          bool& seg_end) {
-  if (g.nseg == 1) {
-    const int lr = p / g.N;
-    j = p - lr * g.N;
-    row = tile * g.rpt + lr;
-    valid = lr < g.rpt && row < g.R;
-    seg_end = valid && (j == g.N - 1);
-  } else {
-    row = tile / g.nseg;
-    const int seg = tile - row * g.nseg;
-    j = seg * g.js + p;
-    const int nj = min(g.js, g.N - seg * g.js);
-    valid = p < nj;
-    seg_end = valid && (p == nj - 1);
-  }
-}
 
 // ---- operand image writers -------------------------------------------------------------------
 template <class CF>
