@@ -78,7 +78,7 @@ static Saved carve_saved(const Dims& d, void* base) {
   return s;
 }
 
-struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, edgew, edgeb, total; };
+struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -103,6 +103,10 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.edgeb = o;
     if (for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
   }
+  L.xtgp = o;
+  if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_xtg_partial_bytes());
+  L.nbuf = o;
+  if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_node_dw_scratch_bytes(d));
   L.total = o + 256;
   return L;
 }
@@ -195,8 +199,11 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.T = (float*)(b + SL.T); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ);
+  sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
+  sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
   if ((rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st)))
     return rc;
+  if (sc.nbuf && (rc = tc_node_dw(d, *grads, sc, engine, st))) return rc;
   float* gWx = grads ? grads->x_mixing_kernel : nullptr;
   if (engine == SAKE_ENGINE_FP32 || !d.spatial) {
     if ((rc = gen_mix_bwd(d, *params, x, mask, sv, sc, gWx, st))) return rc;

@@ -44,6 +44,8 @@ struct BwdScratch {
   float* gproj;     // [R,NP]  cotangent of nodeproj
   float* wxT;       // [C,C]   x_mixing kernel transposed
   float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (training only, feeds the dW GEMM)
+  float* nbuf;         // per-node record for the node-level weight-gradient contractions (tcgen05 engines, training)
+  float* xtg_partial;  // per-CTA partial sums of the weight-gradient contractions (tcgen05 engines, training)
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -95,6 +97,8 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const float* mask, const Saved& sv, const float* dh_out, const float* dx_out,
                       const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
                       const BwdScratch& sc, cudaStream_t st);
+size_t tc_node_dw_scratch_bytes(const Dims& d);
+int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, int engine, cudaStream_t st);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
 int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
@@ -123,8 +127,10 @@ struct XtgArgs {
   long long P, pairs_per_cta;
   float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
   float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
+  float* partial;                            // scratch for per-CTA partial sums (tc_xtg_partial_bytes()); NULL = atomics
 };
 int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
+size_t tc_xtg_partial_bytes();
 bool tc_supported(const Dims& d);
 
 // ---- tcgen05 engine (edge model), tc_edge.cu ---------------------------------------------------

@@ -30,6 +30,16 @@ __device__ __forceinline__ void accum_bias(float* gb, const float* G, int out, i
 // ------------------------------------------------------------------------------------------
 // node_post_bwd
 // ------------------------------------------------------------------------------------------
+// column offsets of the per-node record (NB_LD floats) consumed by tc_node_dw
+enum { NB_N1 = 0, NB_GT2 = 64, NB_CAT = 128, NB_GT1 = 512, NB_HP1 = 576, NB_GTP2 = 640, NB_GTP1 = 704, NB_NRM = 768,
+       NB_HOUT = 1024, NB_GTV = 1088, NB_AV = 1152, NB_GY = 1216, NB_LD = 1232 };
+__device__ __forceinline__ void nb_store(float* nbuf, int r0, int nn, int col, const float* src, int w, bool silu) {
+  for (int t = threadIdx.x; t < nn * w; t += blockDim.x) {
+    const int n = t / w, f = t % w;
+    const float v = src[n * w + f];
+    nbuf[(size_t)(r0 + n) * NB_LD + col + f] = silu ? siluf_(v) : v;
+  }
+}
 size_t node_post_bwd_smem_bytes(const Dims& d) {
   return sizeof(float) * (NODES * (2 * d.C + 13 * d.H) + 8 * NODES + 64);
 }
@@ -39,9 +49,13 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     const float* __restrict__ mask, const float* __restrict__ ssum, const float* __restrict__ he_in,
     const float* __restrict__ dh_out, const float* __restrict__ dx_out, const float* __restrict__ dv_out,
     float* __restrict__ dh, float* __restrict__ dx, float* __restrict__ dv, float* __restrict__ T,
-    float* __restrict__ ghe, SakeLayerGrads g, int want_grads) {
+    float* __restrict__ ghe, SakeLayerGrads g, int want_grads, float* __restrict__ nbuf) {
   extern __shared__ float sm[];
   const int H = d.H, C = d.C, N = d.N;
+  // nbuf != NULL (tcgen05 engines, H = 64): the per-node operands of the weight-gradient contractions are
+  // written out (NB_LD floats per node) and the contractions run on the tensor cores (tc_node_dw).
+  const bool to_buf = want_grads && nbuf != nullptr;
+  const bool atom = want_grads && nbuf == nullptr;
   float* nrm = sm;                   // [NODES][C]  (later: g_nrm)
   float* hes = nrm + NODES * C;      // [NODES][C]
   float* hin = hes + NODES * C;      // [NODES][H] each below
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
       gtv[t] = p.vel2_kernel[f] * gy[n] * dsiluf_(tv[t]);
     }
     __syncthreads();
-    if (want_grads) {
+    if (atom) {
       for (int f = threadIdx.x; f < H; f += blockDim.x) {
         float s = 0.f;
         for (int n = 0; n < nn; ++n) s = fmaf(siluf_(tv[n * H + f]), gy[n], s);
@@ -188,6 +202,12 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
       }
       accum_outer(g.vel0_kernel, hout, H, H, gtv, H, nn);
       accum_bias(g.vel0_bias, gtv, H, nn);
+    }
+    if (to_buf) {
+      nb_store(nbuf, r0, nn, NB_HOUT, hout, H, false);
+      nb_store(nbuf, r0, nn, NB_GTV, gtv, H, false);
+      nb_store(nbuf, r0, nn, NB_AV, tv, H, true);
+      if (threadIdx.x < nn) nbuf[(size_t)(r0 + threadIdx.x) * NB_LD + NB_GY] = gy[threadIdx.x];
     }
     for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
       const int n = t / H, q = t % H;
@@ -208,7 +228,16 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     gt1[t] = acc * dsiluf_(t1[t]);
   }
   __syncthreads();
-  if (want_grads) {
+  if (to_buf) {
+    nb_store(nbuf, r0, nn, NB_N1, t1, H, true);
+    nb_store(nbuf, r0, nn, NB_GT2, gt2, H, false);
+    nb_store(nbuf, r0, nn, NB_GT1, gt1, H, false);
+    nb_store(nbuf, r0, nn, NB_CAT, hin, H, false);
+    nb_store(nbuf, r0, nn, NB_CAT + H, hes, C, false);
+    for (int t = threadIdx.x; t < nn * H; t += blockDim.x)
+      nbuf[(size_t)(r0 + t / H) * NB_LD + NB_CAT + H + C + t % H] = d.spatial ? siluf_(tp2[t]) : 0.f;
+  }
+  if (atom) {
     // n1 = silu(t1) recomputed into tv (free now)
     for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(t1[t]);
     __syncthreads();
@@ -255,7 +284,13 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     gtp1[t] = acc * dsiluf_(tp1[t]);
   }
   __syncthreads();
-  if (want_grads && d.spatial) {
+  if (to_buf && d.spatial) {
+    nb_store(nbuf, r0, nn, NB_HP1, tp1, H, true);
+    nb_store(nbuf, r0, nn, NB_GTP2, gtp2, H, false);
+    nb_store(nbuf, r0, nn, NB_GTP1, gtp1, H, false);
+    nb_store(nbuf, r0, nn, NB_NRM, nrm, C, false);
+  }
+  if (atom && d.spatial) {
     for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(tp1[t]);
     __syncthreads();
     accum_outer(g.post2_kernel, tv, H, H, gtp2, H, nn);
@@ -835,13 +870,56 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
   if ((rc = ensure_smem(k_node_post_bwd, smem))) return rc;
   k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, v, mask, sv.ssum, sv.he, dh_out, dx_out,
                                                                 dv_out, dh, dx, dv, sc.T, sc.ghe,
-                                                                g ? *g : null_grads(), g != nullptr);
+                                                                g ? *g : null_grads(), g != nullptr, sc.nbuf);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 // dWx += E^T gZ on CUDA cores, gZ [P,C] row-major fp32
+// weight gradients of node_mlp / post_norm_mlp / velocity_mlp from the per-node record (K = nodes)
+__global__ void k_post_bias_finish(const float* __restrict__ tmp, float* __restrict__ gbp2, float* __restrict__ gbp1) {
+  const int t = threadIdx.x;
+  if (t < 64) gbp2[t] += tmp[t];
+  else if (t < 128) gbp1[t - 64] += tmp[t];
+}
+size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) * (size_t)d.R * NB_LD) + 1024; }
+
+int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, int engine, cudaStream_t st) {
+  const float* nb = sc.nbuf;
+  float* tmp = sc.nbuf + (size_t)d.R * NB_LD;          // [128] bias scratch
+  int rc;
+  auto call = [&](const float* X, int xw, int ones, int mxpad, const float* G, int gw, int ng, float* out, int ldo,
+                  int out_rows, int out_cols, float* extra, int extra_ld) {
+    XtgArgs q;
+    memset(&q, 0, sizeof(q));
+    q.X = X; q.ldx = NB_LD; q.xw = xw; q.ones_col = ones; q.G = G; q.ldg = NB_LD; q.gw = gw; q.MXpad = mxpad; q.NG = ng;
+    q.P = d.R; q.out = out; q.ldo = ldo; q.out_rows = out_rows; q.out_cols = out_cols;
+    q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld; q.partial = sc.xtg_partial;
+    return tc_xtg(q, engine, 0, st);
+  };
+  // node_mlp (layers.py:58-66)
+  if ((rc = call(nb + NB_N1, 64, 64, 128, nb + NB_GT2, 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64))) return rc;
+  if ((rc = call(nb + NB_CAT, 256, -1, 256, nb + NB_GT1, 64, 64, g.node0_kernel, 64, 256, 64, nullptr, 64))) return rc;
+  if ((rc = call(nb + NB_CAT + 256, 128, 128, 256, nb + NB_GT1, 64, 64, g.node0_kernel + 256 * 64, 64, 128, 64,
+                 g.node0_bias, 64))) return rc;
+  if (d.spatial) {
+    // post_norm_mlp (layers.py:85-92); the ones-row of the first call carries both bias gradients
+    SAKE_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 128, st));
+    if ((rc = call(nb + NB_HP1, 64, 64, 128, nb + NB_GTP2, 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128))) return rc;
+    k_post_bias_finish<<<1, 128, 0, st>>>(tmp, g.post2_bias, g.post0_bias);
+    if ((rc = call(nb + NB_NRM, 256, -1, 256, nb + NB_GTP1, 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64))) return rc;
+  }
+  if (d.update && d.has_v) {
+    // velocity_mlp (layers.py:69-76)
+    if ((rc = call(nb + NB_HOUT, 64, 64, 128, nb + NB_GTV, 64, 64, g.vel0_kernel, 64, 64, 64, g.vel0_bias, 64))) return rc;
+    if ((rc = call(nb + NB_AV, 64, -1, 128, nb + NB_GY, 1, 16, g.vel2_kernel, 1, 64, 1, nullptr, 16))) return rc;
+  }
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st) {
   ProfScope prof(3, d.P, st);
   int splits = (int)min((long long)64, (d.P + 255) / 256);

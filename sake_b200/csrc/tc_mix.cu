@@ -701,6 +701,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     a.G = sc.gZ; a.ldg = CC; a.gw = CC;
     a.MXpad = CC; a.NG = CC; a.P = d.P;
     a.out = gWx; a.ldo = CC; a.out_rows = CC; a.out_cols = CC;
+    a.partial = sc.xtg_partial;
     return tc_xtg(a, ENGINE, 3, st);
   }
   return 0;

@@ -3,8 +3,8 @@
 //   dWx = E^T dZ (sake/layers.py:95), dW2 = a1^T g_e, dW1[2H:] = g^T g_z1 (layers.py:20-26), dWs = e^T g_q, ...
 // Operands are MN-major 128B-swizzled images: rows = pairs (the K dimension), 128 contiguous bytes of
 // features per row and MN block — exactly what a thread-per-pair builder writes with 16-byte stores.
-// fp32 inputs are converted on the fly (tf32 hi/lo split, 3 MMAs; or bf16).  The accumulator lives in
-// TMEM for the whole CTA and is flushed once with atomics.
+// fp32 inputs are converted on the fly (exact 3-way bf16 split, 6 MMAs; or plain bf16).  The accumulator
+// lives in TMEM for the whole CTA and is flushed once with atomics.
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -12,40 +12,59 @@
 namespace sake {
 using namespace tc;
 
+// Operand precision.  kind::tf32 has no MN-major (transposing) operand path on sm_100a (measured: the
+// MMA is a silent no-op), and K-major images with K = pairs need a transposing builder that is L1-bound.
+// kind::f16 does support MN-major, so the fp32-parity engine uses an exact 3-way bf16 split
+// (x = hi + mid + lo, 24 mantissa bits) and 6 MMAs (hh, hm, mh, mm, hl, lh) — the same tensor time as
+// 3xTF32 — while the bf16 engine uses one bf16 image and one MMA.
 template <int ENGINE> struct XCfg;
-template <> struct XCfg<SAKE_ENGINE_TF32X3> {
-  static constexpr bool TF32 = true;
-  // kind::tf32 has no MN-major (transposing) operand path on sm_100a — measured: the MMA is a silent
-  // no-op — so the tf32 images are K-major: rows = features, 128 contiguous bytes = 32 pairs.
-  static constexpr int NSPLIT = 2, NPROD = 3, FMT = 2, EPU = 4, BLK = 32, KP = 32, KSTEP = 8;
-};
-template <> struct XCfg<SAKE_ENGINE_BF16> {
-  static constexpr bool TF32 = false;
-  // kind::f16 supports MN-major operands: rows = pairs (K), 128 contiguous bytes = 64 features per block.
-  static constexpr int NSPLIT = 1, NPROD = 1, FMT = 1, EPU = 8, BLK = 64 /*features per MN block*/, KP = 32, KSTEP = 16;
-};
-__device__ __constant__ int x_prod_x[3] = {0, 1, 0};
-__device__ __constant__ int x_prod_g[3] = {0, 0, 1};
+template <> struct XCfg<SAKE_ENGINE_TF32X3> { static constexpr int NSPLIT = 3, NPROD = 6; };
+template <> struct XCfg<SAKE_ENGINE_BF16> { static constexpr int NSPLIT = 1, NPROD = 1; };
+constexpr int XEPU = 8;      // features per 16-byte unit (bf16)
+constexpr int XBLK = 64;     // features per 128-byte MN block
+constexpr int XKP = 32;      // pairs per stage
+constexpr int XKSTEP = 16;   // pairs per MMA (K of kind::f16)
+__device__ __constant__ int x_prod_x[6] = {0, 0, 1, 1, 0, 2};
+__device__ __constant__ int x_prod_g[6] = {0, 1, 0, 1, 2, 0};
 
 constexpr int XTG_THREADS = 288;   // warp 0: MMA issuer / TMEM owner; warps 1-8: builders + epilogue
 constexpr int XTG_NSTAGE = 2;
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 8 consecutive features of one pair -> one 16-byte unit in each split image
 template <class CF>
-__device__ __forceinline__ void xtg_store_unit(uint8_t* img, size_t split_stride, uint32_t off, const float* vals) {
-  if constexpr (CF::TF32) {
-    float4 hi, lo;
-    split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
-    split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
-    *reinterpret_cast<float4*>(img + off) = hi;
-    *reinterpret_cast<float4*>(img + split_stride + off) = lo;
-  } else {
-    uint32_t pk[4];
+__device__ __forceinline__ void xtg_store_unit(uint8_t* img, size_t split_stride, uint32_t off, const float* v) {
+  uint32_t pk[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 b = __floats2bfloat162_rn(vals[2 * i], vals[2 * i + 1]);
-      pk[i] = *reinterpret_cast<uint32_t*>(&b);
-    }
-    *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  if constexpr (CF::NSPLIT == 3) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+    *reinterpret_cast<uint4*>(img + split_stride + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = r[i] - __bfloat162float(__float2bfloat16_rn(r[i]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+    *reinterpret_cast<uint4*>(img + 2 * split_stride + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// load 8 consecutive floats of a row-major fp32 source (zero beyond `width`)
+__device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int width, bool vec_ok, float* v) {
+  if (vec_ok && c0 + 8 <= width) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (c0 + i < width) ? __ldg(src + c0 + i) : 0.f;
   }
 }
 
@@ -54,12 +73,10 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
   using CF = XCfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int ncol0 = blockIdx.y * a.NG;                        // first G column of this CTA
-  const int xblocks = a.MXpad / CF::BLK;
-  const int gblocks = (a.NG + CF::BLK - 1) / CF::BLK;
-  const uint32_t LBO = CF::KP * 128;                          // bf16: bytes between MN blocks
-  const size_t ximg = CF::TF32 ? (size_t)a.MXpad * 128 : (size_t)xblocks * LBO;
-  const size_t gimg = CF::TF32 ? (size_t)((a.NG + 7) / 8 * 8) * 128 : (size_t)gblocks * LBO;
+  const int xblocks = a.MXpad / XBLK;
+  const int gblocks = (a.NG + XBLK - 1) / XBLK;
+  constexpr uint32_t LBO = XKP * 128;                         // bytes between 64-feature MN blocks
+  const size_t ximg = (size_t)xblocks * LBO, gimg = (size_t)gblocks * LBO;
   const size_t stage = CF::NSPLIT * (ximg + gimg);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + XTG_NSTAGE * stage);
   uint64_t* empty = full + XTG_NSTAGE;
@@ -78,126 +95,81 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
   const uint32_t tmem_base = *tptr;
   const long long p_beg = (long long)blockIdx.x * a.pairs_per_cta;
   const long long p_end = min(a.P, p_beg + a.pairs_per_cta);
-  const int nst = p_end > p_beg ? (int)((p_end - p_beg + CF::KP - 1) / CF::KP) : 0;
+  const int nst = p_end > p_beg ? (int)((p_end - p_beg + XKP - 1) / XKP) : 0;
   const int MH = a.MXpad / 128;
 
   if (warp == 0) {
     if (lane == 0 && nst > 0) {
-      const uint32_t idesc = CF::TF32 ? umma_idesc(CF::FMT, 128, a.NG, 0, 0) : umma_idesc(CF::FMT, 128, a.NG, 1, 1);
+      const uint32_t idesc = umma_idesc(1 /*bf16*/, 128, a.NG, 1, 1);      // both operands MN-major
       for (int it = 0; it < nst; ++it) {
         const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
         mbar_wait(full + s, n & 1);
         tc_fence_after();
         const uint32_t xb = smem_u32(base + s * stage), gb = xb + (uint32_t)(CF::NSPLIT * ximg);
         for (int mh = 0; mh < MH; ++mh)
+#pragma unroll
           for (int pr = 0; pr < CF::NPROD; ++pr)
 #pragma unroll
-            for (int ks = 0; ks < CF::KP / CF::KSTEP; ++ks) {
-              if constexpr (CF::TF32) {
-                const uint32_t aaddr = xb + x_prod_x[pr] * (uint32_t)ximg + mh * (128 * 128) + ks * 32;
-                const uint32_t baddr = gb + x_prod_g[pr] * (uint32_t)gimg + ks * 32;
-                umma<true>(tmem_base + mh * a.NG, umma_desc_k_sw128(aaddr), umma_desc_k_sw128(baddr), idesc,
-                           (it | pr | ks) != 0);
-              } else {
-                const uint32_t aaddr = xb + x_prod_x[pr] * (uint32_t)ximg + mh * (128 / CF::BLK) * LBO + ks * (CF::KSTEP * 128);
-                const uint32_t baddr = gb + x_prod_g[pr] * (uint32_t)gimg + ks * (CF::KSTEP * 128);
-                umma<false>(tmem_base + mh * a.NG, umma_desc_mn_sw128(aaddr, LBO, 1024),
-                            umma_desc_mn_sw128(baddr, LBO, 1024), idesc, (it | pr | ks) != 0);
-              }
+            for (int ks = 0; ks < XKP / XKSTEP; ++ks) {
+              const uint32_t aaddr = xb + x_prod_x[pr] * (uint32_t)ximg + mh * (128 / XBLK) * LBO + ks * (XKSTEP * 128);
+              const uint32_t baddr = gb + x_prod_g[pr] * (uint32_t)gimg + ks * (XKSTEP * 128);
+              umma<false>(tmem_base + mh * a.NG, umma_desc_mn_sw128(aaddr, LBO, 1024), umma_desc_mn_sw128(baddr, LBO, 1024),
+                          idesc, (it | pr | ks) != 0);
             }
         umma_commit(empty + s);
       }
       umma_commit(done);
     }
   } else {
-    // ------------------------------------------------------------ builders
+    // ------------------------------------------------------------ builders (thread = pair x 8-feature unit)
     const int bt = threadIdx.x - 32;                 // 0..255
-    const int xu = a.MXpad / CF::EPU;                // 16-byte units per pair row, X side
-    const int gu = gblocks * (CF::BLK / CF::EPU);    // G side
+    const int xu = a.MXpad / XEPU;                   // 16-byte units per pair row, X side
+    const int gu = gblocks * (XBLK / XEPU);          // G side
+    const bool xvec = a.X != nullptr && (a.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0);
+    const bool gvec = (a.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
     for (int it = 0; it < nst; ++it) {
       const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
       mbar_wait(empty + s, (n & 1) ^ 1);
       uint8_t* ximgp = base + s * stage;
       uint8_t* gimgp = ximgp + CF::NSPLIT * ximg;
-      const long long p0 = p_beg + (long long)it * CF::KP;
-      if constexpr (CF::TF32) {
-        // K-major: lane = pair of the 32-pair chunk, each warp walks features; 4-byte conflict-free stores
-        const int bw = bt >> 5, r = bt & 31;
-        const long long p = p0 + r;
-        const bool ok = p < p_end;
-        const uint32_t kof = (uint32_t)(r & 3) * 4;
-        float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && a.e != nullptr) at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
-        for (int c = bw; c < a.MXpad; c += 8) {
-          float val = 0.f;
-          if (ok) {
-            if (a.e != nullptr) {
-              if (c < 256) {
-                const float ef = __ldg(a.e + p * 64 + (c >> 2));
-                const int hd = c & 3;
-                val = ef * (hd == 0 ? at.x : hd == 1 ? at.y : hd == 2 ? at.z : at.w);
-              }
-            } else if (c < a.xw) {
-              val = __ldg(a.X + p * a.ldx + c);
-            }
-            if (c == a.ones_col) val = 1.0f;
-          }
-          float hi, lo;
-          split_tf32(val, hi, lo);
-          const uint32_t off = sw128_offset((uint32_t)c, (uint32_t)(r >> 2)) + kof;
-          *reinterpret_cast<float*>(ximgp + off) = hi;
-          *reinterpret_cast<float*>(ximgp + ximg + off) = lo;
-        }
-        const int grows = (a.NG + 7) / 8 * 8;
-        for (int c = bw; c < grows; c += 8) {
-          float val = 0.f;
-          if (ok && c < a.NG && ncol0 + c < a.gw) val = __ldg(a.G + p * a.ldg + ncol0 + c);
-          float hi, lo;
-          split_tf32(val, hi, lo);
-          const uint32_t off = sw128_offset((uint32_t)c, (uint32_t)(r >> 2)) + kof;
-          *reinterpret_cast<float*>(gimgp + off) = hi;
-          *reinterpret_cast<float*>(gimgp + gimg + off) = lo;
-        }
-      } else {
-      for (int idx = bt; idx < CF::KP * xu; idx += 256) {
+      const long long p0 = p_beg + (long long)it * XKP;
+      for (int idx = bt; idx < XKP * xu; idx += 256) {
         const int r = idx / xu, ug = idx - r * xu;
         const long long p = p0 + r;
-        const int c0 = ug * CF::EPU;
-        float vals[CF::EPU];
+        const int c0 = ug * XEPU;
+        float vals[8];
 #pragma unroll
-        for (int i = 0; i < CF::EPU; ++i) vals[i] = 0.f;
+        for (int i = 0; i < 8; ++i) vals[i] = 0.f;
         if (p < p_end) {
-          if (a.e != nullptr) {             // X = e (x) att, feature c = f*4 + head
+          if (a.e != nullptr) {             // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
             if (c0 < 256) {
               const float4 at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
-#pragma unroll
-              for (int q = 0; q < CF::EPU / 4; ++q) {
-                const float ef = __ldg(a.e + p * 64 + c0 / 4 + q);
-                vals[4 * q] = ef * at.x; vals[4 * q + 1] = ef * at.y; vals[4 * q + 2] = ef * at.z; vals[4 * q + 3] = ef * at.w;
-              }
+              const float2 ef = __ldg(reinterpret_cast<const float2*>(a.e + p * 64 + c0 / 4));
+              vals[0] = ef.x * at.x; vals[1] = ef.x * at.y; vals[2] = ef.x * at.z; vals[3] = ef.x * at.w;
+              vals[4] = ef.y * at.x; vals[5] = ef.y * at.y; vals[6] = ef.y * at.z; vals[7] = ef.y * at.w;
             }
           } else {
-#pragma unroll
-            for (int i = 0; i < CF::EPU; ++i)
-              if (c0 + i < a.xw) vals[i] = __ldg(a.X + p * a.ldx + c0 + i);
+            load8(a.X + p * a.ldx, c0, a.xw, xvec, vals);
           }
 #pragma unroll
-          for (int i = 0; i < CF::EPU; ++i)
+          for (int i = 0; i < 8; ++i)
             if (c0 + i == a.ones_col) vals[i] = 1.0f;
         }
-        const int mb = c0 / CF::BLK, u = (c0 % CF::BLK) / CF::EPU;
+        const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
         xtg_store_unit<CF>(ximgp, ximg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
       }
-      for (int idx = bt; idx < CF::KP * gu; idx += 256) {
+      for (int idx = bt; idx < XKP * gu; idx += 256) {
         const int r = idx / gu, ug = idx - r * gu;
         const long long p = p0 + r;
-        const int c0 = ug * CF::EPU;
-        float vals[CF::EPU];
+        const int c0 = ug * XEPU;
+        float vals[8];
+        if (p < p_end) load8(a.G + p * a.ldg, c0, a.gw, gvec, vals);
+        else {
 #pragma unroll
-        for (int i = 0; i < CF::EPU; ++i) vals[i] = (p < p_end && ncol0 + c0 + i < a.gw) ? __ldg(a.G + p * a.ldg + ncol0 + c0 + i) : 0.f;
-        const int mb = c0 / CF::BLK, u = (c0 % CF::BLK) / CF::EPU;
+          for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+        }
+        const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
         xtg_store_unit<CF>(gimgp, gimg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
-      }
       }
       fence_proxy_async();
       mbar_arrive(full + s);
@@ -214,14 +186,24 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * a.NG + cc * 32, v);
           tmem_ld_wait();
+          if (a.partial != nullptr) {
+            // per-CTA partial, stored transposed [col][row] so that a warp writes 128 contiguous bytes
+            float* pp = a.partial + (size_t)blockIdx.x * a.MXpad * a.NG + row;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const int col = cc * 32 + k;
-            if (col >= a.NG) continue;
-            if (row < a.out_rows) {
-              if (ncol0 + col < a.out_cols) atomicAdd(a.out + (size_t)row * a.ldo + ncol0 + col, v[k]);
-            } else if (row < a.out_rows + a.extra_rows) {
-              if (ncol0 + col < a.extra_ld) atomicAdd(a.extra + (size_t)(row - a.out_rows) * a.extra_ld + ncol0 + col, v[k]);
+            for (int k = 0; k < 32; ++k) {
+              const int col = cc * 32 + k;
+              if (col < a.NG) pp[(size_t)col * a.MXpad] = v[k];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int col = cc * 32 + k;
+              if (col >= a.NG) continue;
+              if (row < a.out_rows) {
+                if (col < a.out_cols) atomicAdd(a.out + (size_t)row * a.ldo + col, v[k]);
+              } else if (row < a.out_rows + a.extra_rows) {
+                if (col < a.extra_ld) atomicAdd(a.extra + (size_t)(row - a.out_rows) * a.extra_ld + col, v[k]);
+              }
             }
           }
         }
@@ -233,30 +215,45 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// out[row][col] += sum_cta partial[cta][col][row]   (deterministic second stage of the flush)
+__global__ void __launch_bounds__(128) k_xtg_reduce(XtgArgs a, int ncta) {
+  const int col = blockIdx.x;
+  for (int row = threadIdx.x; row < a.out_rows + a.extra_rows; row += blockDim.x) {
+    const float* pp = a.partial + (size_t)col * a.MXpad + row;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += pp[(size_t)c * a.MXpad * a.NG];
+    if (row < a.out_rows) {
+      if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += s;
+    } else if (col < a.extra_ld) {
+      a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += s;
+    }
+  }
+}
+
+size_t tc_xtg_partial_bytes() { return (size_t)160 * 256 * 256 * sizeof(float); }
+
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
   XtgArgs a = a0;
   if (a.P <= 0) return 0;
   const bool bf = engine == SAKE_ENGINE_BF16;
-  const int kp = 32;
-  int ny = 1;
-  if (!bf && a.NG > 128) { ny = (a.NG + 127) / 128; a.NG = 128; }      // tf32: <= 128 G columns per CTA (smem)
-  if (a.extra_ld == 0) a.extra_ld = a0.NG;
+  const int nsplit = bf ? 1 : 3;
+  if (a.extra_ld == 0) a.extra_ld = a.NG;
   if (a.MXpad % 128 != 0 || a.MXpad > 256 || a.NG % 16 != 0 || a.NG > 256 || (a.MXpad / 128) * a.NG > 512) {
     set_error("tc_xtg: unsupported shape MXpad=%d NG=%d", a.MXpad, a.NG);
     return SAKE_EUNSUPPORTED;
   }
-  size_t stage;
-  if (bf) stage = (size_t)(a.MXpad / 64) * kp * 128 + (size_t)((a.NG + 63) / 64) * kp * 128;
-  else stage = 2 * ((size_t)a.MXpad * 128 + (size_t)((a.NG + 7) / 8 * 8) * 128);
+  const size_t lbo = (size_t)XKP * 128;
+  const size_t stage = nsplit * ((size_t)(a.MXpad / XBLK) * lbo + (size_t)((a.NG + XBLK - 1) / XBLK) * lbo);
   const size_t smem = XTG_NSTAGE * stage + 256 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long stages_total = (a.P + kp - 1) / kp;
-  long long per = (stages_total * ny + sms - 1) / sms;
+  long long stages_total = (a.P + XKP - 1) / XKP;
+  long long per = (stages_total + sms - 1) / sms;
   if (per < 4) per = 4;                                  // keep the atomic flush amortised
-  a.pairs_per_cta = per * kp;
+  a.pairs_per_cta = per * XKP;
   const int gx = (int)((a.P + a.pairs_per_cta - 1) / a.pairs_per_cta);
+  if (gx > 160) a.partial = nullptr;                   // partial buffer is sized for <= 160 CTAs
   static bool attr_tf = false, attr_bf = false;
   if (bf) {
     if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
@@ -266,9 +263,12 @@ int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
   if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
   {
     ProfScope prof(prof_kind, a.P, st);
-    dim3 grid(gx, ny);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16><<<grid, XTG_THREADS, smem, st>>>(a);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3><<<grid, XTG_THREADS, smem, st>>>(a);
+    if (bf) k_tc_xtg<SAKE_ENGINE_BF16><<<gx, XTG_THREADS, smem, st>>>(a);
+    else k_tc_xtg<SAKE_ENGINE_TF32X3><<<gx, XTG_THREADS, smem, st>>>(a);
+    if (a.partial != nullptr) {
+      k_xtg_reduce<<<a.NG, 128, 0, st>>>(a, gx);
+      note_launches(1);
+    }
   }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
