@@ -78,7 +78,7 @@ static Saved carve_saved(const Dims& d, void* base) {
   return s;
 }
 
-struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
+struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -91,6 +91,8 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.gdir = o; o += align_up(sizeof(float) * (size_t)d.P * 3);
     L.gproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
     L.wxT = o; o += align_up(sizeof(float) * (size_t)d.C * d.C);
+    L.nodeWT = o; o += align_up(sizeof(float) * ((size_t)d.H * (2 * d.H + d.C) + 3 * (size_t)d.H * d.H + (size_t)d.H * d.C +
+                                                  (size_t)d.K * 2 * d.H + (size_t)d.H * 2 * d.H));
     L.gZ = o;
     if (with_grads) o += align_up(sizeof(float) * (size_t)d.P * d.C);
   }
@@ -198,7 +200,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   BwdScratch sc;
   sc.T = (float*)(b + SL.T); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
-  sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ);
+  sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
   if ((rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st)))

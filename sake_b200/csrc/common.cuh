@@ -44,6 +44,7 @@ struct BwdScratch {
   float* gproj;     // [R,NP]  cotangent of nodeproj
   float* wxT;       // [C,C]   x_mixing kernel transposed
   float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (training only, feeds the dW GEMM)
+  float* nodeWT;       // transposed copies of the node-level weight matrices (k_node_wt)
   float* nbuf;         // per-node record for the node-level weight-gradient contractions (tcgen05 engines, training)
   float* xtg_partial;  // per-CTA partial sums of the weight-gradient contractions (tcgen05 engines, training)
 };
@@ -60,6 +61,29 @@ __device__ __forceinline__ float dsiluf_(float x) {
 // nn.celu(alpha=2): max(x,0) + 2*expm1(min(x,0)/2)   (layers.py:81)
 __device__ __forceinline__ float celu2f_(float x) { return x > 0.f ? x : 2.0f * expm1f(0.5f * x); }
 __device__ __forceinline__ float dcelu2f_(float x) { return x > 0.f ? 1.0f : expf(0.5f * x); }
+
+constexpr int SAKE_NODES = 8;   // nodes per CTA in the per-node kernels
+
+// y[n][o] = bias[o] + sum_i x[n][i] * W[i][o]      (W row-major [in][out]; coalesced over o)
+// work item = (output o, pair of nodes): every thread of the CTA is busy for out = H = 64
+__device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, int in, const float* __restrict__ W,
+                                           const float* __restrict__ bias, int out, bool accumulate) {
+  for (int idx = threadIdx.x; idx < out * (SAKE_NODES / 2); idx += blockDim.x) {
+    const int o = idx % out, n0 = (idx / out) * 2;
+    float a0 = accumulate ? y[n0 * out + o] : (bias ? bias[o] : 0.f);
+    float a1 = accumulate ? y[(n0 + 1) * out + o] : (bias ? bias[o] : 0.f);
+    const float* x0 = x + n0 * ldx;
+    const float* x1 = x0 + ldx;
+#pragma unroll 4
+    for (int i = 0; i < in; ++i) {
+      const float w = W[(size_t)i * out + o];
+      a0 = fmaf(x0[i], w, a0);
+      a1 = fmaf(x1[i], w, a1);
+    }
+    y[n0 * out + o] = a0;
+    y[(n0 + 1) * out + o] = a1;
+  }
+}
 
 void set_error(const char* fmt, ...);
 void note_launches(int n);

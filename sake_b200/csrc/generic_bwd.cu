@@ -40,122 +40,154 @@ __device__ __forceinline__ void nb_store(float* nbuf, int r0, int nn, int col, c
     nbuf[(size_t)(r0 + n) * NB_LD + col + f] = silu ? siluf_(v) : v;
   }
 }
+// transposed copies of the node-level weight matrices, so that the W^T g products of the backward pass
+// read memory coalesced (thread index = input feature)
+struct NodeWT {
+  const float *node0T;   // [H][H+C+H]
+  const float *node2T;   // [H][H]
+  const float *post0T;   // [H][C]
+  const float *post2T;   // [H][H]
+  const float *vel0T;    // [H][H]
+  const float *mlp_inT;  // [K][2H]
+  const float *w1hT;     // [H][2H]   rows [0,2H) of mlp_out[0]
+};
+__host__ __device__ inline size_t node_wt_floats(const Dims& d) {
+  return (size_t)d.H * (2 * d.H + d.C) + 3 * (size_t)d.H * d.H + (size_t)d.H * d.C + (size_t)d.K * 2 * d.H + (size_t)d.H * 2 * d.H;
+}
+static NodeWT carve_node_wt(const Dims& d, float* base) {
+  NodeWT w;
+  float* q = base;
+  w.node0T = q; q += (size_t)d.H * (2 * d.H + d.C);
+  w.node2T = q; q += (size_t)d.H * d.H;
+  w.post0T = q; q += (size_t)d.H * d.C;
+  w.post2T = q; q += (size_t)d.H * d.H;
+  w.vel0T = q; q += (size_t)d.H * d.H;
+  w.mlp_inT = q; q += (size_t)d.K * 2 * d.H;
+  w.w1hT = q;
+  return w;
+}
+__global__ void k_node_wt(Dims d, const SakeLayerParams p, float* __restrict__ base) {
+  const int H = d.H, C = d.C, K = d.K;
+  const size_t n0 = (size_t)H * (2 * H + C), n1 = (size_t)H * H, n2 = (size_t)H * C, n5 = (size_t)K * 2 * H, n6 = (size_t)H * 2 * H;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // out[f][r] = in[r][f]
+  if (t < n0) { const int NC = 2 * H + C; const int f = t / NC, r = t % NC; base[t] = p.node0_kernel[(size_t)r * H + f]; return; }
+  t -= n0; base += n0;
+  if (t < n1) { const int f = t / H, r = t % H; base[t] = p.node2_kernel[(size_t)r * H + f]; return; }
+  t -= n1; base += n1;
+  if (t < n2) { const int f = t / C, r = t % C; base[t] = p.post0_kernel[(size_t)r * H + f]; return; }
+  t -= n2; base += n2;
+  if (t < n1) { const int f = t / H, r = t % H; base[t] = p.post2_kernel[(size_t)r * H + f]; return; }
+  t -= n1; base += n1;
+  if (t < n1) { const int f = t / H, r = t % H; base[t] = p.vel0_kernel ? p.vel0_kernel[(size_t)r * H + f] : 0.f; return; }
+  t -= n1; base += n1;
+  if (t < n5) { const int k = t / (2 * H), r = t % (2 * H); base[t] = p.mlp_in_kernel[(size_t)r * K + k]; return; }
+  t -= n5; base += n5;
+  if (t < n6) { const int q = t / (2 * H), r = t % (2 * H); base[t] = p.mlp_out0_kernel[(size_t)r * H + q]; return; }
+}
+
 size_t node_post_bwd_smem_bytes(const Dims& d) {
-  return sizeof(float) * (NODES * (2 * d.C + 13 * d.H) + 8 * NODES + 64);
+  return sizeof(float) * (NODES * (2 * d.C + 17 * d.H) + 8 * NODES + 64);
 }
 
 __global__ void __launch_bounds__(256) k_node_post_bwd(
-    Dims d, const SakeLayerParams p, const float* __restrict__ h, const float* __restrict__ v,
+    Dims d, const SakeLayerParams p, NodeWT wt, const float* __restrict__ h, const float* __restrict__ v,
     const float* __restrict__ mask, const float* __restrict__ ssum, const float* __restrict__ he_in,
     const float* __restrict__ dh_out, const float* __restrict__ dx_out, const float* __restrict__ dv_out,
     float* __restrict__ dh, float* __restrict__ dx, float* __restrict__ dv, float* __restrict__ T,
     float* __restrict__ ghe, SakeLayerGrads g, int want_grads, float* __restrict__ nbuf) {
   extern __shared__ float sm[];
-  const int H = d.H, C = d.C, N = d.N;
+  const int H = d.H, C = d.C, N = d.N, NH = NODES * d.H;
   // nbuf != NULL (tcgen05 engines, H = 64): the per-node operands of the weight-gradient contractions are
   // written out (NB_LD floats per node) and the contractions run on the tensor cores (tc_node_dw).
   const bool to_buf = want_grads && nbuf != nullptr;
   const bool atom = want_grads && nbuf == nullptr;
-  float* nrm = sm;                   // [NODES][C]  (later: g_nrm)
+  float* nrm = sm;                   // [NODES][C]
   float* hes = nrm + NODES * C;      // [NODES][C]
   float* hin = hes + NODES * C;      // [NODES][H] each below
-  float* tp1 = hin + NODES * H;
-  float* tp2 = tp1 + NODES * H;
-  float* t1 = tp2 + NODES * H;
-  float* t2 = t1 + NODES * H;
-  float* hout = t2 + NODES * H;
-  float* tv = hout + NODES * H;
-  float* ghout = tv + NODES * H;
-  float* gt2 = ghout + NODES * H;
-  float* gt1 = gt2 + NODES * H;
-  float* gtp2 = gt1 + NODES * H;
-  float* gtp1 = gtp2 + NODES * H;
-  float* gtv = gtp1 + NODES * H;
-  float* den = gtv + NODES * H;      // [NODES]
-  float* den2 = den + NODES;         // [NODES]
-  float* gy = den2 + NODES;          // [NODES]
-  float* gate = gy + NODES;          // [NODES]
+  float* hp1 = hin + NH;  float* dhp1 = hp1 + NH;      // silu(tp1), silu'(tp1)
+  float* hcb = dhp1 + NH; float* dhcb = hcb + NH;      // silu(tp2) (h_combinations), silu'(tp2)
+  float* n1 = dhcb + NH;  float* dn1 = n1 + NH;        // silu(t1), silu'(t1)
+  float* dn2 = dn1 + NH;                               // silu'(t2)
+  float* hout = dn2 + NH;
+  float* av = hout + NH;  float* dav = av + NH;        // silu(tv), silu'(tv)
+  float* ghout = dav + NH;
+  float* gt2 = ghout + NH;
+  float* gt1 = gt2 + NH;
+  float* gtp2 = gt1 + NH;
+  float* gtp1 = gtp2 + NH;
+  float* gtv = gtp1 + NH;
+  float* den = gtv + NH;             // [NODES]
+  float* den2 = den + NODES;
+  float* gy = den2 + NODES;
+  float* gate = gy + NODES;
   float* gdv = gate + NODES;         // [NODES][3] (+pad)
   const int r0 = blockIdx.x * NODES;
   const int nn = min(NODES, d.R - r0);
+  const bool upd = d.update != 0, hv = d.has_v != 0, spatial = d.spatial != 0;
 
-  // ---------------- recompute forward ----------------
+  // ---------------- recompute forward (layers.py:123-131,142-151,226-229) ----------------
   if (threadIdx.x < NODES) {
-    float dn = (float)N, dn2 = (float)N;
+    float dn = (float)N, dnb = (float)N;
     if (mask && threadIdx.x < nn) {
       float ms = 0.f;
       for (int j = 0; j < N; ++j) ms += mask[(size_t)(r0 + threadIdx.x) * N + j];
       dn = ms + 1e-8f;
-      dn2 = ms + 1e-10f;
+      dnb = ms + 1e-10f;
     }
     den[threadIdx.x] = dn;
-    den2[threadIdx.x] = dn2;
+    den2[threadIdx.x] = dnb;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
     const int n = t / C, c = t % C;
-    float nr = 0.f, hv = 0.f;
+    float nr = 0.f, hvv = 0.f;
     if (n < nn) {
       const float* sp = ssum + ((size_t)(r0 + n) * C + c) * 3;
-      float inv = 1.0f / den[n];
-      float a0 = sp[0] * inv, a1 = sp[1] * inv, a2 = sp[2] * inv;
+      const float inv = 1.0f / den[n];
+      const float a0 = sp[0] * inv, a1 = sp[1] * inv, a2 = sp[2] * inv;
       nr = a0 * a0 + a1 * a1 + a2 * a2;
-      hv = he_in[(size_t)(r0 + n) * C + c];
+      hvv = he_in[(size_t)(r0 + n) * C + c];
     }
     nrm[t] = nr;
-    hes[t] = hv;
+    hes[t] = hvv;
   }
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) {
     const int n = t / H;
     hin[t] = n < nn ? h[(size_t)r0 * H + t] : 0.f;
     ghout[t] = n < nn ? dh_out[(size_t)r0 * H + t] : 0.f;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.post0_bias[f];
-    for (int c = 0; c < C; ++c) acc = fmaf(nrm[n * C + c], p.post0_kernel[(size_t)c * H + f], acc);
-    tp1[t] = acc;
+  node_dense(hp1, nrm, C, C, p.post0_kernel, p.post0_bias, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = hp1[t]; hp1[t] = siluf_(z); dhp1[t] = dsiluf_(z); }
+  __syncthreads();
+  node_dense(hcb, hp1, H, H, p.post2_kernel, p.post2_bias, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) {
+    const float z = hcb[t];
+    hcb[t] = spatial ? siluf_(z) : 0.f;
+    dhcb[t] = spatial ? dsiluf_(z) : 0.f;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.post2_bias[f];
-    for (int q = 0; q < H; ++q) acc = fmaf(siluf_(tp1[n * H + q]), p.post2_kernel[(size_t)q * H + f], acc);
-    tp2[t] = acc;
-  }
+  node_dense(n1, hin, H, H, p.node0_kernel, p.node0_bias, H, false);
   __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.node0_bias[f];
-    const float* w = p.node0_kernel + f;
-    for (int q = 0; q < H; ++q) acc = fmaf(hin[n * H + q], w[(size_t)q * H], acc);
-    w += (size_t)H * H;
-    for (int c = 0; c < C; ++c) acc = fmaf(hes[n * C + c], w[(size_t)c * H], acc);
-    w += (size_t)C * H;
-    if (d.spatial)
-      for (int q = 0; q < H; ++q) acc = fmaf(siluf_(tp2[n * H + q]), w[(size_t)q * H], acc);
-    t1[t] = acc;
-  }
+  node_dense(n1, hes, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true);
   __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.node2_bias[f];
-    for (int q = 0; q < H; ++q) acc = fmaf(siluf_(t1[n * H + q]), p.node2_kernel[(size_t)q * H + f], acc);
-    t2[t] = acc;
-    hout[t] = hin[t] + siluf_(acc);
-  }
+  node_dense(n1, hcb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = n1[t]; n1[t] = siluf_(z); dn1[t] = dsiluf_(z); }
+  __syncthreads();
+  node_dense(hout, n1, H, H, p.node2_kernel, p.node2_bias, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = hout[t]; dn2[t] = dsiluf_(z); hout[t] = hin[t] + siluf_(z); }
   __syncthreads();
 
-  // ---------------- velocity / position update backward ----------------
-  const bool upd = d.update != 0, hv = d.has_v != 0;
+  // ---------------- velocity / position update backward (layers.py:226-232) ----------------
   if (upd && hv) {
-    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-      const int n = t / H, f = t % H;
-      float acc = p.vel0_bias[f];
-      for (int q = 0; q < H; ++q) acc = fmaf(hout[n * H + q], p.vel0_kernel[(size_t)q * H + f], acc);
-      tv[t] = acc;
-    }
+    node_dense(av, hout, H, H, p.vel0_kernel, p.vel0_bias, H, false);
+    __syncthreads();
+    for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = av[t]; av[t] = siluf_(z); dav[t] = dsiluf_(z); }
   }
   __syncthreads();
   if (threadIdx.x < NODES) {
@@ -163,19 +195,19 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     float g0 = 0.f, g1 = 0.f, g2 = 0.f, gyv = 0.f, gt = 0.f;
     if (n < nn) {
       const size_t row = (size_t)(r0 + n);
-      float dxo0 = dx_out ? dx_out[row * 3 + 0] : 0.f, dxo1 = dx_out ? dx_out[row * 3 + 1] : 0.f,
-            dxo2 = dx_out ? dx_out[row * 3 + 2] : 0.f;
-      float dvo0 = dv_out ? dv_out[row * 3 + 0] : 0.f, dvo1 = dv_out ? dv_out[row * 3 + 1] : 0.f,
-            dvo2 = dv_out ? dv_out[row * 3 + 2] : 0.f;
+      const float dxo0 = dx_out ? dx_out[row * 3 + 0] : 0.f, dxo1 = dx_out ? dx_out[row * 3 + 1] : 0.f,
+                  dxo2 = dx_out ? dx_out[row * 3 + 2] : 0.f;
+      const float dvo0 = dv_out ? dv_out[row * 3 + 0] : 0.f, dvo1 = dv_out ? dv_out[row * 3 + 1] : 0.f,
+                  dvo2 = dv_out ? dv_out[row * 3 + 2] : 0.f;
       dx[row * 3 + 0] = dxo0; dx[row * 3 + 1] = dxo1; dx[row * 3 + 2] = dxo2;   // x' = x + v'
       if (upd) {
         g0 = dvo0 + dxo0; g1 = dvo1 + dxo1; g2 = dvo2 + dxo2;                   // cotangent of v'
         if (hv) {
           float y = 0.f;
-          for (int f = 0; f < H; ++f) y = fmaf(siluf_(tv[n * H + f]), p.vel2_kernel[f], y);
+          for (int f = 0; f < H; ++f) y = fmaf(av[n * H + f], p.vel2_kernel[f], y);
           gt = 2.0f * sigmoidf_(y);
           const float* vv = v + row * 3;
-          float ggate = g0 * vv[0] + g1 * vv[1] + g2 * vv[2];
+          const float ggate = g0 * vv[0] + g1 * vv[1] + g2 * vv[2];
           gyv = ggate * gt * (1.0f - 0.5f * gt);
           if (dv) { dv[row * 3 + 0] = gt * g0; dv[row * 3 + 1] = gt * g1; dv[row * 3 + 2] = gt * g2; }
         }
@@ -189,15 +221,12 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
   }
   __syncthreads();
   if (upd && hv) {
-    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-      const int n = t / H, f = t % H;
-      gtv[t] = p.vel2_kernel[f] * gy[n] * dsiluf_(tv[t]);
-    }
+    for (int t = threadIdx.x; t < NH; t += blockDim.x) gtv[t] = p.vel2_kernel[t % H] * gy[t / H] * dav[t];
     __syncthreads();
     if (atom) {
       for (int f = threadIdx.x; f < H; f += blockDim.x) {
         float s = 0.f;
-        for (int n = 0; n < nn; ++n) s = fmaf(siluf_(tv[n * H + f]), gy[n], s);
+        for (int n = 0; n < nn; ++n) s = fmaf(av[n * H + f], gy[n], s);
         atomicAdd(g.vel2_kernel + f, s);
       }
       accum_outer(g.vel0_kernel, hout, H, H, gtv, H, nn);
@@ -206,122 +235,105 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     if (to_buf) {
       nb_store(nbuf, r0, nn, NB_HOUT, hout, H, false);
       nb_store(nbuf, r0, nn, NB_GTV, gtv, H, false);
-      nb_store(nbuf, r0, nn, NB_AV, tv, H, true);
+      nb_store(nbuf, r0, nn, NB_AV, av, H, false);
       if (threadIdx.x < nn) nbuf[(size_t)(r0 + threadIdx.x) * NB_LD + NB_GY] = gy[threadIdx.x];
     }
-    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-      const int n = t / H, q = t % H;
-      float acc = 0.f;
-      for (int f = 0; f < H; ++f) acc = fmaf(p.vel0_kernel[(size_t)q * H + f], gtv[n * H + f], acc);
-      ghout[t] += acc;
-    }
+    node_dense(ghout, gtv, H, H, wt.vel0T, nullptr, H, true);      // g_h' += Wv1 g_tv
     __syncthreads();
   }
 
-  // ---------------- node_mlp backward ----------------
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) gt2[t] = ghout[t] * dsiluf_(t2[t]);
+  // ---------------- node_mlp backward (layers.py:142-151) ----------------
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) gt2[t] = ghout[t] * dn2[t];
   __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, q = t % H;
-    float acc = 0.f;
-    for (int f = 0; f < H; ++f) acc = fmaf(p.node2_kernel[(size_t)q * H + f], gt2[n * H + f], acc);
-    gt1[t] = acc * dsiluf_(t1[t]);
-  }
+  node_dense(gt1, gt2, H, H, wt.node2T, nullptr, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) gt1[t] *= dn1[t];
   __syncthreads();
   if (to_buf) {
-    nb_store(nbuf, r0, nn, NB_N1, t1, H, true);
+    nb_store(nbuf, r0, nn, NB_N1, n1, H, false);
     nb_store(nbuf, r0, nn, NB_GT2, gt2, H, false);
     nb_store(nbuf, r0, nn, NB_GT1, gt1, H, false);
     nb_store(nbuf, r0, nn, NB_CAT, hin, H, false);
     nb_store(nbuf, r0, nn, NB_CAT + H, hes, C, false);
-    for (int t = threadIdx.x; t < nn * H; t += blockDim.x)
-      nbuf[(size_t)(r0 + t / H) * NB_LD + NB_CAT + H + C + t % H] = d.spatial ? siluf_(tp2[t]) : 0.f;
+    nb_store(nbuf, r0, nn, NB_CAT + H + C, hcb, H, false);
   }
   if (atom) {
-    // n1 = silu(t1) recomputed into tv (free now)
-    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(t1[t]);
-    __syncthreads();
-    accum_outer(g.node2_kernel, tv, H, H, gt2, H, nn);
+    accum_outer(g.node2_kernel, n1, H, H, gt2, H, nn);
     accum_bias(g.node2_bias, gt2, H, nn);
     accum_outer(g.node0_kernel, hin, H, H, gt1, H, nn);
     accum_outer(g.node0_kernel + (size_t)H * H, hes, C, C, gt1, H, nn);
-    if (d.spatial) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(tp2[t]);
-      __syncthreads();
-      accum_outer(g.node0_kernel + (size_t)(H + C) * H, tv, H, H, gt1, H, nn);
-    }
+    if (spatial) accum_outer(g.node0_kernel + (size_t)(H + C) * H, hcb, H, H, gt1, H, nn);
     accum_bias(g.node0_bias, gt1, H, nn);
-    __syncthreads();
   }
-  // g_cat = Wn1 @ gt1 : dh, ghe, g_hcomb
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, q = t % H;
-    float acc = 0.f, acc2 = 0.f;
-    const float* w0 = p.node0_kernel + (size_t)q * H;
-    const float* w2 = p.node0_kernel + (size_t)(H + C + q) * H;
-    for (int f = 0; f < H; ++f) {
-      float gv = gt1[n * H + f];
-      acc = fmaf(w0[f], gv, acc);
-      acc2 = fmaf(w2[f], gv, acc2);
+  // g_cat = Wn1 g_t1 : [dh | ghe | g_hcomb]   (coalesced through the transposed copy)
+  {
+    const int NC = 2 * H + C;
+    for (int idx = threadIdx.x; idx < NC * (NODES / 2); idx += blockDim.x) {
+      const int o = idx % NC, n0 = (idx / NC) * 2;
+      float a0 = 0.f, a1 = 0.f;
+      const float* g0p = gt1 + n0 * H;
+      const float* g1p = g0p + H;
+#pragma unroll 4
+      for (int f = 0; f < H; ++f) {
+        const float w = wt.node0T[(size_t)f * NC + o];
+        a0 = fmaf(g0p[f], w, a0);
+        a1 = fmaf(g1p[f], w, a1);
+      }
+      if (o < H) {
+        if (n0 < nn) dh[(size_t)(r0 + n0) * H + o] = ghout[n0 * H + o] + a0;
+        if (n0 + 1 < nn) dh[(size_t)(r0 + n0 + 1) * H + o] = ghout[(n0 + 1) * H + o] + a1;
+      } else if (o < H + C) {
+        if (n0 < nn) ghe[(size_t)(r0 + n0) * C + (o - H)] = a0;
+        if (n0 + 1 < nn) ghe[(size_t)(r0 + n0 + 1) * C + (o - H)] = a1;
+      } else {
+        const int q = o - H - C;
+        gtp2[n0 * H + q] = a0 * dhcb[n0 * H + q];
+        gtp2[(n0 + 1) * H + q] = a1 * dhcb[(n0 + 1) * H + q];
+      }
     }
-    if (n < nn) dh[(size_t)r0 * H + t] = ghout[t] + acc;
-    gtp2[t] = d.spatial ? acc2 * dsiluf_(tp2[t]) : 0.f;
-  }
-  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
-    const int n = t / C, c = t % C;
-    float acc = 0.f;
-    const float* w1 = p.node0_kernel + (size_t)(H + c) * H;
-    for (int f = 0; f < H; ++f) acc = fmaf(w1[f], gt1[n * H + f], acc);
-    if (n < nn) ghe[(size_t)(r0 + n) * C + c] = acc;
   }
   __syncthreads();
-  // ---------------- post_norm_mlp backward ----------------
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, q = t % H;
-    float acc = 0.f;
-    for (int f = 0; f < H; ++f) acc = fmaf(p.post2_kernel[(size_t)q * H + f], gtp2[n * H + f], acc);
-    gtp1[t] = acc * dsiluf_(tp1[t]);
-  }
+  // ---------------- post_norm_mlp backward (layers.py:85-92,129-131) ----------------
+  node_dense(gtp1, gtp2, H, H, wt.post2T, nullptr, H, false);
   __syncthreads();
-  if (to_buf && d.spatial) {
-    nb_store(nbuf, r0, nn, NB_HP1, tp1, H, true);
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) gtp1[t] *= dhp1[t];
+  __syncthreads();
+  if (to_buf && spatial) {
+    nb_store(nbuf, r0, nn, NB_HP1, hp1, H, false);
     nb_store(nbuf, r0, nn, NB_GTP2, gtp2, H, false);
     nb_store(nbuf, r0, nn, NB_GTP1, gtp1, H, false);
     nb_store(nbuf, r0, nn, NB_NRM, nrm, C, false);
   }
-  if (atom && d.spatial) {
-    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) tv[t] = siluf_(tp1[t]);
-    __syncthreads();
-    accum_outer(g.post2_kernel, tv, H, H, gtp2, H, nn);
+  if (atom && spatial) {
+    accum_outer(g.post2_kernel, hp1, H, H, gtp2, H, nn);
     accum_bias(g.post2_bias, gtp2, H, nn);
     accum_outer(g.post0_kernel, nrm, C, C, gtp1, H, nn);
     accum_bias(g.post0_bias, gtp1, H, nn);
-    __syncthreads();
   }
+  __syncthreads();
+  // g_nrm = Wp1 g_tp1 (overwrites nrm), then
   // T[c][d] = 2*ssum[c][d]*g_nrm[c]/den^2 + Wv[c]*g_dv[d]/den2 ;  gWv[c] += sum_d ssum[c][d]*g_dv[d]/den2
-  for (int t = threadIdx.x; t < NODES * C; t += blockDim.x) {
-    const int n = t / C, c = t % C;
-    if (n >= nn) continue;
-    const size_t row = (size_t)(r0 + n);
-    float t0 = 0.f, t1v = 0.f, t2v = 0.f;
-    if (d.spatial) {
-      float gn = 0.f;
-      const float* w = p.post0_kernel + (size_t)c * H;
-      for (int f = 0; f < H; ++f) gn = fmaf(w[f], gtp1[n * H + f], gn);
-      const float* sp = ssum + (row * C + c) * 3;
-      float k2 = 2.0f * gn / (den[n] * den[n]);
-      t0 = k2 * sp[0]; t1v = k2 * sp[1]; t2v = k2 * sp[2];
-      if (upd) {
-        float wv = p.v_mixing_kernel[c] / den2[n];
-        t0 = fmaf(wv, gdv[n * 3 + 0], t0); t1v = fmaf(wv, gdv[n * 3 + 1], t1v); t2v = fmaf(wv, gdv[n * 3 + 2], t2v);
-        if (want_grads) {
-          float s = (sp[0] * gdv[n * 3 + 0] + sp[1] * gdv[n * 3 + 1] + sp[2] * gdv[n * 3 + 2]) / den2[n];
-          atomicAdd(g.v_mixing_kernel + c, s);
+  if (spatial) node_dense(nrm, gtp1, H, H, wt.post0T, nullptr, C, false);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float wv = (spatial && upd) ? p.v_mixing_kernel[c] : 0.f;
+    float gwv = 0.f;
+    for (int n = 0; n < nn; ++n) {
+      const size_t row = (size_t)(r0 + n);
+      float t0 = 0.f, t1v = 0.f, t2v = 0.f;
+      if (spatial) {
+        const float* sp = ssum + (row * C + c) * 3;
+        const float k2 = 2.0f * nrm[n * C + c] / (den[n] * den[n]);
+        t0 = k2 * sp[0]; t1v = k2 * sp[1]; t2v = k2 * sp[2];
+        if (upd) {
+          const float wq = wv / den2[n];
+          t0 = fmaf(wq, gdv[n * 3 + 0], t0); t1v = fmaf(wq, gdv[n * 3 + 1], t1v); t2v = fmaf(wq, gdv[n * 3 + 2], t2v);
+          gwv += (sp[0] * gdv[n * 3 + 0] + sp[1] * gdv[n * 3 + 1] + sp[2] * gdv[n * 3 + 2]) / den2[n];
         }
       }
+      *reinterpret_cast<float4*>(T + (row * C + c) * 4) = make_float4(t0, t1v, t2v, 0.f);   // [R][C] float4
     }
-    *reinterpret_cast<float4*>(T + (row * C + c) * 4) = make_float4(t0, t1v, t2v, 0.f);   // [R][C] float4
+    if (want_grads && spatial && upd) atomicAdd(g.v_mixing_kernel + c, gwv);
   }
 }
 
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
 // ------------------------------------------------------------------------------------------
 // node_pre_bwd: cotangent of the per-node projections -> dh and W_in / W_1[0:2H] / biases
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ h,
+__global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerParams p, NodeWT wt, const float* __restrict__ h,
                                                       const float* __restrict__ gproj, float* __restrict__ dh,
                                                       SakeLayerGrads g, int want_grads) {
   extern __shared__ float sm[];
@@ -793,17 +805,24 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
   for (int t = threadIdx.x; t < NODES * NP; t += blockDim.x) gp[t] = (t / NP) < nn ? gproj[(size_t)r0 * NP + t] : 0.f;
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) hs[t] = (t / H) < nn ? h[(size_t)r0 * H + t] : 0.f;
   __syncthreads();
-  for (int t = threadIdx.x; t < nn * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    const float* gr = gp + n * NP;
-    float acc = 0.f;
-    const float* wj = p.mlp_in_kernel + (size_t)f * K;
-    const float* wi = p.mlp_in_kernel + (size_t)(H + f) * K;
-    for (int k = 0; k < K; ++k) acc = fmaf(wj[k], gr[k], fmaf(wi[k], gr[Kp + k], acc));
-    const float* vj = p.mlp_out0_kernel + (size_t)f * H;
-    const float* vi = p.mlp_out0_kernel + (size_t)(H + f) * H;
-    for (int q = 0; q < H; ++q) acc = fmaf(vj[q], gr[2 * Kp + q], fmaf(vi[q], gr[2 * Kp + H + q], acc));
-    dh[(size_t)r0 * H + t] += acc;
+  // dh[n][f] += sum_k Win[f][k] g_uj[k] + Win[H+f][k] g_ui[k] + sum_q W1[f][q] g_pj[q] + W1[H+f][q] g_pi[q]
+  for (int idx = threadIdx.x; idx < H * (NODES / 2); idx += blockDim.x) {
+    const int f = idx % H, n0 = (idx / H) * 2;
+    const float* ga = gp + n0 * NP;
+    const float* gb = ga + NP;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float wj = wt.mlp_inT[(size_t)k * 2 * H + f], wi = wt.mlp_inT[(size_t)k * 2 * H + H + f];
+      a0 = fmaf(wj, ga[k], fmaf(wi, ga[Kp + k], a0));
+      a1 = fmaf(wj, gb[k], fmaf(wi, gb[Kp + k], a1));
+    }
+    for (int q = 0; q < H; ++q) {
+      const float vj = wt.w1hT[(size_t)q * 2 * H + f], vi = wt.w1hT[(size_t)q * 2 * H + H + f];
+      a0 = fmaf(vj, ga[2 * Kp + q], fmaf(vi, ga[2 * Kp + H + q], a0));
+      a1 = fmaf(vj, gb[2 * Kp + q], fmaf(vi, gb[2 * Kp + H + q], a1));
+    }
+    if (n0 < nn) dh[(size_t)(r0 + n0) * H + f] += a0;
+    if (n0 + 1 < nn) dh[(size_t)(r0 + n0 + 1) * H + f] += a1;
   }
   if (want_grads) {
     for (int t = threadIdx.x; t < H * K; t += blockDim.x) {
@@ -865,18 +884,19 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
                       const BwdScratch& sc, cudaStream_t st) {
   (void)x;
+  const size_t nwt = node_wt_floats(d);
+  k_node_wt<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(d, p, sc.nodeWT);
   size_t smem = node_post_bwd_smem_bytes(d);
   int rc;
   if ((rc = ensure_smem(k_node_post_bwd, smem))) return rc;
-  k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, v, mask, sv.ssum, sv.he, dh_out, dx_out,
-                                                                dv_out, dh, dx, dv, sc.T, sc.ghe,
+  k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, carve_node_wt(d, sc.nodeWT), h, v, mask, sv.ssum,
+                                                                sv.he, dh_out, dx_out, dv_out, dh, dx, dv, sc.T, sc.ghe,
                                                                 g ? *g : null_grads(), g != nullptr, sc.nbuf);
-  note_launches(1);
+  note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-// dWx += E^T gZ on CUDA cores, gZ [P,C] row-major fp32
 // weight gradients of node_mlp / post_norm_mlp / velocity_mlp from the per-node record (K = nodes)
 __global__ void k_post_bias_finish(const float* __restrict__ tmp, float* __restrict__ gbp2, float* __restrict__ gbp1) {
   const int t = threadIdx.x;
@@ -987,8 +1007,8 @@ int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, fl
   int rc;
   size_t smem = sizeof(float) * NODES * (d.NP + d.H);
   if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
-  k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, h, sc.gproj, dh, g ? *g : null_grads(),
-                                                               g != nullptr);
+  k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, carve_node_wt(d, sc.nodeWT), h, sc.gproj, dh,
+                                                               g ? *g : null_grads(), g != nullptr);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

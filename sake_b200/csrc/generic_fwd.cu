@@ -310,41 +310,30 @@ __global__ void __launch_bounds__(256) k_node_post(Dims d, const SakeLayerParams
     s.hin[t] = n < nn ? h[(size_t)r0 * H + t] : 0.f;
   }
   __syncthreads();
-  // post_norm_mlp layer 0
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.post0_bias[f];
-    for (int c = 0; c < C; ++c) acc = fmaf(s.nrm[n * C + c], p.post0_kernel[(size_t)c * H + f], acc);
-    s.hp1[t] = siluf_(acc);
-  }
+  // post_norm_mlp (layers.py:85-92)
+  node_dense(s.hp1, s.nrm, C, C, p.post0_kernel, p.post0_bias, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.hp1[t] = siluf_(s.hp1[t]);
+  __syncthreads();
+  node_dense(s.hcomb, s.hp1, H, H, p.post2_kernel, p.post2_bias, H, false);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.hcomb[t] = d.spatial ? siluf_(s.hcomb[t]) : 0.f;
+  __syncthreads();
+  // node_mlp over [h | he | hcomb] + residual (layers.py:142-151)
+  node_dense(s.n1, s.hin, H, H, p.node0_kernel, p.node0_bias, H, false);
+  __syncthreads();
+  node_dense(s.n1, s.he, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true);
+  __syncthreads();
+  node_dense(s.n1, s.hcomb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.n1[t] = siluf_(s.n1[t]);
+  __syncthreads();
+  node_dense(s.hout, s.n1, H, H, p.node2_kernel, p.node2_bias, H, false);
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.post2_bias[f];
-    for (int g = 0; g < H; ++g) acc = fmaf(s.hp1[n * H + g], p.post2_kernel[(size_t)g * H + f], acc);
-    s.hcomb[t] = d.spatial ? siluf_(acc) : 0.f;
-  }
-  __syncthreads();
-  // node_mlp layer 0 over [h | he | hcomb]
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.node0_bias[f];
-    const float* w = p.node0_kernel + f;
-    for (int g = 0; g < H; ++g) acc = fmaf(s.hin[n * H + g], w[(size_t)g * H], acc);
-    w += (size_t)H * H;
-    for (int c = 0; c < C; ++c) acc = fmaf(s.he[n * C + c], w[(size_t)c * H], acc);
-    w += (size_t)C * H;
-    for (int g = 0; g < H; ++g) acc = fmaf(s.hcomb[n * H + g], w[(size_t)g * H], acc);
-    s.n1[t] = siluf_(acc);
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
-    const int n = t / H, f = t % H;
-    float acc = p.node2_bias[f];
-    for (int g = 0; g < H; ++g) acc = fmaf(s.n1[n * H + g], p.node2_kernel[(size_t)g * H + f], acc);
-    float ho = s.hin[t] + siluf_(acc);
+    const float ho = s.hin[t] + siluf_(s.hout[t]);
     s.hout[t] = ho;
-    if (n < nn) h_out[(size_t)r0 * H + t] = ho;
+    if (t / H < nn) h_out[(size_t)r0 * H + t] = ho;
   }
   __syncthreads();
   // velocity / position update: one warp per node
