@@ -127,52 +127,78 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
     const int gu = gblocks * (XBLK / XEPU);          // G side
     const bool xvec = a.X != nullptr && (a.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0);
     const bool gvec = (a.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
+    // Software pipeline: the global loads of stage it+1 are issued right after the stores of stage it, so
+    // their latency overlaps the wait for the next free slot instead of sitting in front of every store.
+    float xv[4][8], gv[4][8];
+    auto load_stage = [&](int it) {
+      const long long p0 = p_beg + (long long)it * XKP;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = bt + 256 * k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xv[k][i] = 0.f; gv[k][i] = 0.f; }
+        if (idx < XKP * xu) {
+          const int r = idx / xu, ug = idx - r * xu;
+          const long long p = p0 + r;
+          const int c0 = ug * XEPU;
+          if (p < p_end) {
+            if (a.e != nullptr) {           // raw operands of E = e (x) att; the product is formed at store time
+              if (c0 < 256) {
+                const float4 at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
+                const float2 ef = __ldg(reinterpret_cast<const float2*>(a.e + p * 64 + c0 / 4));
+                xv[k][0] = at.x; xv[k][1] = at.y; xv[k][2] = at.z; xv[k][3] = at.w; xv[k][4] = ef.x; xv[k][5] = ef.y;
+              }
+            } else {
+              load8(a.X + p * a.ldx, c0, a.xw, xvec, xv[k]);
+            }
+          }
+        }
+        if (idx < XKP * gu) {
+          const int r = idx / gu, ug = idx - r * gu;
+          const long long p = p0 + r;
+          if (p < p_end) load8(a.G + p * a.ldg, ug * XEPU, a.gw, gvec, gv[k]);
+        }
+      }
+    };
+    if (nst > 0) load_stage(0);
     for (int it = 0; it < nst; ++it) {
       const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
       mbar_wait(empty + s, (n & 1) ^ 1);
       uint8_t* ximgp = base + s * stage;
       uint8_t* gimgp = ximgp + CF::NSPLIT * ximg;
       const long long p0 = p_beg + (long long)it * XKP;
-      for (int idx = bt; idx < XKP * xu; idx += 256) {
-        const int r = idx / xu, ug = idx - r * xu;
-        const long long p = p0 + r;
-        const int c0 = ug * XEPU;
-        float vals[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vals[i] = 0.f;
-        if (p < p_end) {
+      for (int k = 0; k < 4; ++k) {
+        const int idx = bt + 256 * k;
+        if (idx < XKP * xu) {
+          const int r = idx / xu, ug = idx - r * xu;
+          const int c0 = ug * XEPU;
+          float vals[8];
           if (a.e != nullptr) {             // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
-            if (c0 < 256) {
-              const float4 at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
-              const float2 ef = __ldg(reinterpret_cast<const float2*>(a.e + p * 64 + c0 / 4));
-              vals[0] = ef.x * at.x; vals[1] = ef.x * at.y; vals[2] = ef.x * at.z; vals[3] = ef.x * at.w;
-              vals[4] = ef.y * at.x; vals[5] = ef.y * at.y; vals[6] = ef.y * at.z; vals[7] = ef.y * at.w;
-            }
+            vals[0] = xv[k][4] * xv[k][0]; vals[1] = xv[k][4] * xv[k][1]; vals[2] = xv[k][4] * xv[k][2]; vals[3] = xv[k][4] * xv[k][3];
+            vals[4] = xv[k][5] * xv[k][0]; vals[5] = xv[k][5] * xv[k][1]; vals[6] = xv[k][5] * xv[k][2]; vals[7] = xv[k][5] * xv[k][3];
           } else {
-            load8(a.X + p * a.ldx, c0, a.xw, xvec, vals);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vals[i] = xv[k][i];
           }
+          if (p0 + r < p_end) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (c0 + i == a.ones_col) vals[i] = 1.0f;
+            for (int i = 0; i < 8; ++i)
+              if (c0 + i == a.ones_col) vals[i] = 1.0f;
+          }
+          const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
+          xtg_store_unit<CF>(ximgp, ximg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
         }
-        const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
-        xtg_store_unit<CF>(ximgp, ximg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
-      }
-      for (int idx = bt; idx < XKP * gu; idx += 256) {
-        const int r = idx / gu, ug = idx - r * gu;
-        const long long p = p0 + r;
-        const int c0 = ug * XEPU;
-        float vals[8];
-        if (p < p_end) load8(a.G + p * a.ldg, c0, a.gw, gvec, vals);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+        if (idx < XKP * gu) {
+          const int r = idx / gu, ug = idx - r * gu;
+          const int c0 = ug * XEPU;
+          const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
+          xtg_store_unit<CF>(gimgp, gimg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), gv[k]);
         }
-        const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
-        xtg_store_unit<CF>(gimgp, gimg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
       }
       fence_proxy_async();
       mbar_arrive(full + s);
+      if (it + 1 < nst) load_stage(it + 1);
     }
     // ------------------------------------------------------------ epilogue: flush the accumulator
     if (nst > 0) {
