@@ -536,48 +536,77 @@ __global__ void k_transpose(int n, const float* __restrict__ in, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// attn_bwd: att (softmax over unmasked senders) backward, celu', and the W_s transpose
+// attn_bwd: att (softmax over unmasked senders) backward, celu', and the W_s transpose.
+// One warp per receiving atom.  g_s = att*(g_att - sum_j g_att*att) (the renormalisation of
+// layers.py:180 is the identity on the gradient); g_q = g_s*celu'(q); g_e += Ws g_q.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_attn_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ e,
+__global__ void __launch_bounds__(256) k_attn_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ e,
                                                   const float* __restrict__ att, float* __restrict__ gatt,
                                                   float* __restrict__ ge) {
   extern __shared__ float sm[];
   const int N = d.N, A = d.A, H = d.H;
-  float* as = sm;           // [N][A]
-  float* gs = as + N * A;   // [N][A]
-  float* G = gs + N * A;    // [A]
-  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x * nw + warp;
+  if (row >= d.R) return;
+  float* as = sm + (size_t)warp * 2 * N * A;   // [N][A]
+  float* gs = as + N * A;                      // [N][A]
   const size_t base = (size_t)row * N;
-  for (int t = threadIdx.x; t < N * A; t += blockDim.x) {
+  for (int t = lane; t < N * A; t += 32) {
     as[t] = att[base * A + t];
     gs[t] = gatt[base * A + t];
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int a = warp; a < A; a += nw) {
+  __syncwarp();
+  for (int a = 0; a < A; ++a) {
     float s = 0.f;
     for (int j = lane; j < N; j += 32) s = fmaf(gs[j * A + a], as[j * A + a], s);
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) G[a] = s;
+    for (int j = lane; j < N; j += 32) gs[j * A + a] = as[j * A + a] * (gs[j * A + a] - s);    // g_s
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < N * A; t += blockDim.x) {
-    const int j = t / A, a = t % A;
-    float gsv = as[t] * (gs[t] - G[a]);
-    float q = p.sem_bias[a];
-    const float* er = e + (base + j) * H;
-    for (int f = 0; f < H; ++f) q = fmaf(er[f], p.sem_kernel[(size_t)f * A + a], q);
-    float gq = gsv * dcelu2f_(q);
-    gs[t] = gq;
-    gatt[base * A + t] = gq;
+  __syncwarp();
+  if (A == 4 && H == 64) {
+    // lane owns f = 2*lane, 2*lane+1: q via a warp reduction of the per-lane partial dot products
+    // (parameter pointers are only guaranteed 4-byte aligned: scalar loads)
+    const float* wp = p.sem_kernel + (size_t)(2 * lane) * 4;
+    const float4 w0 = make_float4(wp[0], wp[1], wp[2], wp[3]);
+    const float4 w1 = make_float4(wp[4], wp[5], wp[6], wp[7]);
+    const float b0 = p.sem_bias[0], b1 = p.sem_bias[1], b2 = p.sem_bias[2], b3 = p.sem_bias[3];
+    for (int j = 0; j < N; ++j) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gs + j * 4);
+      if (g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;   // masked / self pair: exact zero
+      float2* gep = reinterpret_cast<float2*>(ge + (base + j) * 64 + 2 * lane);
+      const float2 ev = *reinterpret_cast<const float2*>(e + (base + j) * 64 + 2 * lane);
+      float q0 = ev.x * w0.x + ev.y * w1.x, q1 = ev.x * w0.y + ev.y * w1.y, q2 = ev.x * w0.z + ev.y * w1.z,
+            q3 = ev.x * w0.w + ev.y * w1.w;
+      for (int o = 16; o; o >>= 1) {
+        q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        q2 += __shfl_xor_sync(0xffffffffu, q2, o); q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+      }
+      const float gq0 = g4.x * dcelu2f_(q0 + b0), gq1 = g4.y * dcelu2f_(q1 + b1), gq2 = g4.z * dcelu2f_(q2 + b2),
+                  gq3 = g4.w * dcelu2f_(q3 + b3);
+      if (lane == 0) *reinterpret_cast<float4*>(gs + j * 4) = make_float4(gq0, gq1, gq2, gq3);
+      float2 gv = *gep;
+      gv.x += w0.x * gq0 + w0.y * gq1 + w0.z * gq2 + w0.w * gq3;
+      gv.y += w1.x * gq0 + w1.y * gq1 + w1.z * gq2 + w1.w * gq3;
+      *gep = gv;
+    }
+    __syncwarp();
+  } else {
+    for (int t = lane; t < N * A; t += 32) {
+      const int j = t / A, a = t % A;
+      float q = p.sem_bias[a];
+      const float* er = e + (base + j) * H;
+      for (int f = 0; f < H; ++f) q = fmaf(er[f], p.sem_kernel[(size_t)f * A + a], q);
+      gs[t] *= dcelu2f_(q);
+    }
+    __syncwarp();
+    for (int t = lane; t < N * H; t += 32) {
+      const int j = t / H, f = t % H;
+      float acc = 0.f;
+      for (int a = 0; a < A; ++a) acc = fmaf(p.sem_kernel[(size_t)f * A + a], gs[j * A + a], acc);
+      ge[(base + j) * H + f] += acc;
+    }
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < N * H; t += blockDim.x) {
-    const int j = t / H, f = t % H;
-    float acc = 0.f;
-    for (int a = 0; a < A; ++a) acc = fmaf(p.sem_kernel[(size_t)f * A + a], gs[j * A + a], acc);
-    ge[(base + j) * H + f] += acc;
-  }
+  for (int t = lane; t < N * A; t += 32) gatt[base * A + t] = gs[t];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -980,9 +1009,11 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
 
 int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
   int rc;
-  size_t smem = sizeof(float) * (2 * d.N * d.A + d.A);
+  int nw = 8;
+  while (nw > 1 && sizeof(float) * 2 * d.N * d.A * nw > 160 * 1024) nw >>= 1;
+  size_t smem = sizeof(float) * 2 * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_bwd, smem))) return rc;
-  k_attn_bwd<<<d.R, 128, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
+  k_attn_bwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

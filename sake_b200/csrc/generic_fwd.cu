@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
                                                   const float* __restrict__ mask, const SakeLayerParams p,
                                                   const float* __restrict__ proj, float* __restrict__ e_out,
                                                   float* __restrict__ logit_out) {
+  // logit_out holds celu(q) + masks; the pre-activation q is recovered in the backward pass from e
   extern __shared__ float sm[];
   const int H = d.H, K = d.K, A = d.A, N = d.N;
   float* pri = sm;                 // [NP] projections of node i
@@ -123,21 +124,22 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
 
 // ------------------------------------------------------------------------------------------
 // attn_fwd: softmax over senders j, mask, renormalise (layers.py:167,172-180) + aggregate
-// (layers.py:135-140).  One CTA per receiving atom.  att is normalised in place.
+// (layers.py:135-140).  One warp per receiving atom, several rows per CTA; att is normalised in place.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_attn_fwd(Dims d, const float* __restrict__ mask,
+__global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restrict__ mask,
                                                   const float* __restrict__ e, float* __restrict__ att,
                                                   float* __restrict__ he) {
   extern __shared__ float sm[];
-  const int N = d.N, A = d.A, H = d.H;
-  float* as = sm;  // [N][A]
-  const int row = blockIdx.x;
+  const int N = d.N, A = d.A, H = d.H, C = d.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x * nw + warp;
+  if (row >= d.R) return;
+  float* as = sm + (size_t)warp * N * A;  // [N][A]
   float* arow = att + (size_t)row * N * A;
   const float* mrow = mask ? mask + (size_t)row * N : nullptr;
-  for (int t = threadIdx.x; t < N * A; t += blockDim.x) as[t] = arow[t];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int a = warp; a < A; a += nw) {
+  for (int t = lane; t < N * A; t += 32) as[t] = arow[t];
+  __syncwarp();
+  for (int a = 0; a < A; ++a) {
     float mx = -INFINITY;
     for (int j = lane; j < N; j += 32) mx = fmaxf(mx, as[j * A + a]);
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(128) k_attn_fwd(Dims d, const float* __restric
       sum += ex;
     }
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float inv = 1.0f / sum;
+    const float inv = 1.0f / sum;
     float csum = 0.f;
     for (int j = lane; j < N; j += 32) {
       float c = as[j * A + a] * inv;          // semantic attention (softmax)
@@ -157,21 +159,37 @@ __global__ void __launch_bounds__(128) k_attn_fwd(Dims d, const float* __restric
       csum += c;
     }
     for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-    float rinv = csum > 0.f ? 1.0f / csum : 0.f;   // guarded: fully masked row -> att = 0
-    for (int j = lane; j < N; j += 32) as[j * A + a] = as[j * A + a] * rinv;
+    const float rinv = csum > 0.f ? 1.0f / csum : 0.f;   // guarded: fully masked row -> att = 0
+    for (int j = lane; j < N; j += 32) as[j * A + a] *= rinv;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < N * A; t += blockDim.x) arow[t] = as[t];
+  __syncwarp();
+  for (int t = lane; t < N * A; t += 32) arow[t] = as[t];
   // aggregate: he[c = f*A+a] = sum_j e[j,f] * att[j,a] * m_j
-  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-    const int f = c / A, a = c % A;
-    float acc = 0.f;
+  if (A == 4 && H == 64) {
+    // lane owns f = 2*lane, 2*lane+1 (coalesced float2 loads of e) and all four heads
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* ep = e + (size_t)row * N * 64 + 2 * lane;
     for (int j = 0; j < N; ++j) {
-      float w = as[j * A + a];
-      if (mrow) w *= mrow[j];
-      acc = fmaf(e[((size_t)row * N + j) * H + f], w, acc);
+      const float2 ev = *reinterpret_cast<const float2*>(ep + (size_t)j * 64);
+      float4 w = *reinterpret_cast<const float4*>(as + j * 4);
+      if (mrow) { const float m = mrow[j]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+      acc[0] = fmaf(ev.x, w.x, acc[0]); acc[1] = fmaf(ev.x, w.y, acc[1]); acc[2] = fmaf(ev.x, w.z, acc[2]); acc[3] = fmaf(ev.x, w.w, acc[3]);
+      acc[4] = fmaf(ev.y, w.x, acc[4]); acc[5] = fmaf(ev.y, w.y, acc[5]); acc[6] = fmaf(ev.y, w.z, acc[6]); acc[7] = fmaf(ev.y, w.w, acc[7]);
     }
-    he[(size_t)row * d.C + c] = acc;
+    float4* o = reinterpret_cast<float4*>(he + (size_t)row * 256 + 8 * lane);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      const int f = c / A, a = c % A;
+      float acc = 0.f;
+      for (int j = 0; j < N; ++j) {
+        float w = as[j * A + a];
+        if (mrow) w *= mrow[j];
+        acc = fmaf(e[((size_t)row * N + j) * H + f], w, acc);
+      }
+      he[(size_t)row * C + c] = acc;
+    }
   }
 }
 
@@ -421,9 +439,11 @@ int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 // softmax over senders + aggregate: normalises sv.att in place, fills sv.he
 int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st) {
   int rc;
-  size_t smem = sizeof(float) * d.N * d.A;
+  int nw = 8;
+  while (nw > 1 && sizeof(float) * d.N * d.A * nw > 160 * 1024) nw >>= 1;
+  size_t smem = sizeof(float) * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
-  k_attn_fwd<<<d.R, 128, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
+  k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

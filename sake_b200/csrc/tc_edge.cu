@@ -200,30 +200,40 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       if (a.mask) m = a.mask[prx];
     }
     // ---------------- (a) G = [rho*u | n | 1 | t | 0...]  ->  A operand of GEMM A
-#pragma unroll 4
-    for (int u = 0; u < 16; ++u) {
-      float vals[4] = {0.f, 0.f, 0.f, 0.f};
-      if (valid) {
-        float uj[4] = {0.f, 0.f, 0.f, 0.f}, ui[4] = {0.f, 0.f, 0.f, 0.f};
-        if (4 * u < Kp) {
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
-          const float4 t2 = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
-          uj[0] = t1.x; uj[1] = t1.y; uj[2] = t1.z; uj[3] = t1.w;
-          ui[0] = t2.x; ui[1] = t2.y; ui[2] = t2.z; ui[3] = t2.w;
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = 4 * u + i;
-          if (k < K) {
-            const float dm = tt - s_mu[k];
-            vals[i] = expf(-s_beta[k] * dm * dm) * (uj[i] + ui[i]);
-          } else if (k == K) vals[i] = nrm;
-          else if (k == K + 1) vals[i] = 1.0f;        // column sums for free in the dW contraction
-          else if (k == K + 2) vals[i] = tt;
+    for (int hb = 0; hb < 2; ++hb) {
+      // issue the 16 projection loads of this half before any of the exp chains (latency overlap)
+      float4 uj4[8], ui4[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int u = hb * 8 + q;
+        uj4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ui4[q] = uj4[q];
+        if (valid && 4 * u < Kp) {
+          uj4[q] = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
+          ui4[q] = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
         }
-        if (BWD && a.train) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int u = hb * 8 + q;
+        float vals[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+          const float us[4] = {uj4[q].x + ui4[q].x, uj4[q].y + ui4[q].y, uj4[q].z + ui4[q].z, uj4[q].w + ui4[q].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * u + i;
+            if (k < K) {
+              const float dm = tt - s_mu[k];
+              vals[i] = expf(-s_beta[k] * dm * dm) * us[i];
+            } else if (k == K) vals[i] = nrm;
+            else if (k == K + 1) vals[i] = 1.0f;        // column sums for free in the dW contraction
+            else if (k == K + 2) vals[i] = tt;
+          }
+          if (BWD && a.train) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        }
+        store_unit_tf32(img + hb * 2 * EP_IMG, pl, q, vals);
+      }
     }
     fence_proxy_async();
     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -239,6 +249,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       // ---------------- (c) a1 = silu(Z1 + pj[j] + pi[i])  (layers.py:33-38, 23)
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        float4 pj4[8], pi4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pi4[u] = pj4[u];
+          if (valid) {
+            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
+            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
+          }
+        }
         float v[32];
         tmem_ld32(lane_addr + half * 32, v);
         tmem_ld_wait();
@@ -246,11 +266,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         for (int u = 0; u < 8; ++u) {
           float vals[4] = {0.f, 0.f, 0.f, 0.f};
           if (valid) {
-            const int f0 = half * 32 + 4 * u;
-            const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
-            const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
-            vals[0] = siluf_(v[4 * u] + pj.x + pi.x); vals[1] = siluf_(v[4 * u + 1] + pj.y + pi.y);
-            vals[2] = siluf_(v[4 * u + 2] + pj.z + pi.z); vals[3] = siluf_(v[4 * u + 3] + pj.w + pi.w);
+            vals[0] = siluf_(v[4 * u] + pj4[u].x + pi4[u].x); vals[1] = siluf_(v[4 * u + 1] + pj4[u].y + pi4[u].y);
+            vals[2] = siluf_(v[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = siluf_(v[4 * u + 3] + pj4[u].w + pi4[u].w);
           }
           store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
         }
@@ -318,14 +335,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           }
         }
       }
-#pragma unroll 4
-      for (int u = 0; u < 16; ++u) {
-        float vals[4] = {0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u));
-          vals[0] = t4.x; vals[1] = t4.y; vals[2] = t4.z; vals[3] = t4.w;
+      {
+        float4 g4[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          g4[u] = valid ? __ldg(reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+          store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
         }
-        store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -340,6 +359,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        float4 pj4[8], pi4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pi4[u] = pj4[u];
+          if (valid) {
+            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
+            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
+          }
+        }
         float z[32], ga[32];
         tmem_ld32(lane_addr + half * 32, z);
         tmem_ld32(lane_addr + 64 + half * 32, ga);
@@ -349,8 +378,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           float vals[4] = {0.f, 0.f, 0.f, 0.f};
           if (valid) {
             const int f0 = half * 32 + 4 * u;
-            const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
-            const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+            const float4 pj = pj4[u];
+            const float4 pi = pi4[u];
             vals[0] = ga[4 * u] * dsiluf_(z[4 * u] + pj.x + pi.x);
             vals[1] = ga[4 * u + 1] * dsiluf_(z[4 * u + 1] + pj.y + pi.y);
             vals[2] = ga[4 * u + 2] * dsiluf_(z[4 * u + 2] + pj.z + pi.z);
@@ -374,6 +403,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       float gt = 0.f, gn = 0.f;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        float4 uj4[8], ui4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ui4[u] = uj4[u];
+          if (valid && half * 32 + 4 * u < Kp) {
+            uj4[u] = __ldg(reinterpret_cast<const float4*>(nj + half * 32 + 4 * u));
+            ui4[u] = __ldg(reinterpret_cast<const float4*>(ni + Kp + half * 32 + 4 * u));
+          }
+        }
         float gg[32];
         tmem_ld32(lane_addr + 128 + half * 32, gg);
         tmem_ld_wait();
@@ -382,13 +421,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           for (int u = 0; u < 8; ++u) {
             const int k0 = half * 32 + 4 * u;
             float gu[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
-            float uj[4] = {0.f, 0.f, 0.f, 0.f}, ui[4] = {0.f, 0.f, 0.f, 0.f};
-            if (k0 < Kp) {
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(nj + k0));
-              const float4 t2 = __ldg(reinterpret_cast<const float4*>(ni + Kp + k0));
-              uj[0] = t1.x; uj[1] = t1.y; uj[2] = t1.z; uj[3] = t1.w;
-              ui[0] = t2.x; ui[1] = t2.y; ui[2] = t2.z; ui[3] = t2.w;
-            }
+            const float uj[4] = {uj4[u].x, uj4[u].y, uj4[u].z, uj4[u].w};
+            const float ui[4] = {ui4[u].x, ui4[u].y, ui4[u].z, ui4[u].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int k = k0 + i;
