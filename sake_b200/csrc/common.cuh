@@ -85,6 +85,25 @@ __device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, in
   }
 }
 
+// ---- fast fp32-class transcendentals for the tensor-core kernels --------------------------------
+// One MUFU each (ex2.approx / rcp.approx, <= 2 ulp) instead of the ~25-instruction libdevice paths.
+// Errors stay at the 1e-7 .. 1e-6 level (absolute for tanh/sigmoid, relative ~|x|*2^-24 for exp), well
+// inside the 1e-5 energy / 1e-4 force tolerance — and the epilogues are issue-bound, not MUFU-bound.
+__device__ __forceinline__ float fexp_(float x) { return __expf(x); }
+__device__ __forceinline__ float frcp_(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float fsigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fsilu_(float x) { return x * fsigmoid_(x); }
+__device__ __forceinline__ float fdsilu_(float x) {
+  const float s = fsigmoid_(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+// tanh(x) = sign(x) * (1 - 2/(exp(2|x|)+1)); exp overflow -> 2/inf = 0 -> +-1
+__device__ __forceinline__ float ftanh_(float x) {
+  const float ax = fabsf(x);
+  const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * ax) + 1.0f);
+  return copysignf(t, x);
+}
+
 void set_error(const char* fmt, ...);
 void note_launches(int n);
 

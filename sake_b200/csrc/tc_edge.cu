@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       const float* xj = a.x + (size_t)(b * a.g.N + j) * 3;
       r0 = xj[0] - xi[0]; r1 = xj[1] - xi[1]; r2 = xj[2] - xi[2];
       nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);     // functional.py:14-17
-      tt = expf(-nrm);                                                    // utils.py:62-64 (alpha = 1, lower = 0)
+      tt = fexp_(-nrm);                                                    // utils.py:62-64 (alpha = 1, lower = 0)
       if (a.mask) m = a.mask[prx];
     }
     // ---------------- (a) G = [rho*u | n | 1 | t | 0...]  ->  A operand of GEMM A
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             const int k = 4 * u + i;
             if (k < K) {
               const float dm = tt - s_mu[k];
-              vals[i] = expf(-s_beta[k] * dm * dm) * us[i];
+              vals[i] = fexp_(-s_beta[k] * dm * dm) * us[i];
             } else if (k == K) vals[i] = nrm;
             else if (k == K + 1) vals[i] = 1.0f;        // column sums for free in the dW contraction
             else if (k == K + 2) vals[i] = tt;
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         for (int u = 0; u < 8; ++u) {
           float vals[4] = {0.f, 0.f, 0.f, 0.f};
           if (valid) {
-            vals[0] = siluf_(v[4 * u] + pj4[u].x + pi4[u].x); vals[1] = siluf_(v[4 * u + 1] + pj4[u].y + pi4[u].y);
-            vals[2] = siluf_(v[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = siluf_(v[4 * u + 3] + pj4[u].w + pi4[u].w);
+            vals[0] = fsilu_(v[4 * u] + pj4[u].x + pi4[u].x); vals[1] = fsilu_(v[4 * u + 1] + pj4[u].y + pi4[u].y);
+            vals[2] = fsilu_(v[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = fsilu_(v[4 * u + 3] + pj4[u].w + pi4[u].w);
           }
           store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
         }
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
               const int f0 = half * 32 + 4 * u;
               const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
               const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
-              o[u] = make_float4(siluf_(v[4 * u] + pj.x + pi.x), siluf_(v[4 * u + 1] + pj.y + pi.y),
-                                 siluf_(v[4 * u + 2] + pj.z + pi.z), siluf_(v[4 * u + 3] + pj.w + pi.w));
+              o[u] = make_float4(fsilu_(v[4 * u] + pj.x + pi.x), fsilu_(v[4 * u + 1] + pj.y + pi.y),
+                                 fsilu_(v[4 * u + 2] + pj.z + pi.z), fsilu_(v[4 * u + 3] + pj.w + pi.w));
             }
           }
         }
@@ -380,10 +380,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             const int f0 = half * 32 + 4 * u;
             const float4 pj = pj4[u];
             const float4 pi = pi4[u];
-            vals[0] = ga[4 * u] * dsiluf_(z[4 * u] + pj.x + pi.x);
-            vals[1] = ga[4 * u + 1] * dsiluf_(z[4 * u + 1] + pj.y + pi.y);
-            vals[2] = ga[4 * u + 2] * dsiluf_(z[4 * u + 2] + pj.z + pi.z);
-            vals[3] = ga[4 * u + 3] * dsiluf_(z[4 * u + 3] + pj.w + pi.w);
+            vals[0] = ga[4 * u] * fdsilu_(z[4 * u] + pj.x + pi.x);
+            vals[1] = ga[4 * u + 1] * fdsilu_(z[4 * u + 1] + pj.y + pi.y);
+            vals[2] = ga[4 * u + 2] * fdsilu_(z[4 * u + 2] + pj.z + pi.z);
+            vals[3] = ga[4 * u + 3] * fdsilu_(z[4 * u + 3] + pj.w + pi.w);
             *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
           }
           store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
               const int k = k0 + i;
               if (k < K) {
                 const float dm = tt - s_mu[k];
-                const float rho = expf(-s_beta[k] * dm * dm);
+                const float rho = fexp_(-s_beta[k] * dm * dm);
                 gu[i] = gg[4 * u + i] * rho;                                   // d/du
                 const float w = dm * rho * gg[4 * u + i] * (uj[i] + ui[i]);   // dm * rho * d/drho
                 wv[i] = w;

@@ -8,6 +8,7 @@
 // Precision: SAKE_ENGINE_TF32X3 = kind::tf32 with an exact hi/lo split of both operands (3 MMAs:
 // hi*hi + lo*hi + hi*lo) -> fp32-class accuracy; SAKE_ENGINE_BF16 = kind::f16, bf16 operands.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -162,7 +163,7 @@ struct Smem {
 template <int ENGINE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
-             const float* __restrict__ att, const uint8_t* __restrict__ w1img, float* __restrict__ ssum) {
+             const float* __restrict__ att, const uint8_t* __restrict__ w1img, float* __restrict__ ssum, int dbg_wsplits) {
   using CF = Cfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
   Smem<CF> sm(smem_raw);
@@ -187,8 +188,9 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           mbar_wait(sm.empty + s, (n & 1) ^ 1);
-          mbar_arrive_expect_tx(sm.full_w + s, CF::NSPLIT * W_IMG);
-          for (int sp = 0; sp < CF::NSPLIT; ++sp)
+          const int nsp = dbg_wsplits > 0 ? dbg_wsplits : CF::NSPLIT;
+          mbar_arrive_expect_tx(sm.full_w + s, nsp * W_IMG);
+          for (int sp = 0; sp < nsp; ++sp)
             bulk_g2s(sm.w_img(s) + sp * W_IMG, w1img + ((size_t)kc * CF::NSPLIT + sp) * W_IMG, W_IMG, sm.full_w + s);
         }
     }
@@ -212,6 +214,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
             const uint32_t d = tmem_base + buf * 256 + mh * 128;
 #pragma unroll
             for (int pr = 0; pr < CF::NPROD; ++pr) {
+              if (dbg_wsplits < 0 && pr >= -dbg_wsplits) continue;     // timing experiment only
               const uint32_t a0 = wbase + c_prod_w[pr] * W_IMG + mh * (128 * 128);
               const uint32_t b0 = pbase + c_prod_p[pr] * P_IMG;
 #pragma unroll
@@ -289,7 +292,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const float4 dm = sm.dirm[buf * TILE + cc * 32 + k];
-          const float co = tanhf(v[k]);
+          const float co = ftanh_(v[k]);
           s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
           const int flag = __float_as_int(dm.w);
           if (flag != 0) {
@@ -471,7 +474,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int cpi = kc2 * CF::KCH + part * 32 + k;
-            const float co = tanhf(v[k]);
+            const float co = ftanh_(v[k]);
             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) t4 = __ldg(Trow + cpi);
             const float gco = d0 * t4.x + d1 * t4.y + d2 * t4.z;
@@ -660,7 +663,9 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
   {
     ProfScope prof(1, d.P, st);
-    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, sv.ssum);
+    static int dbg = -1;
+    if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
+    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, sv.ssum, dbg);
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
