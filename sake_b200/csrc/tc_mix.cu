@@ -32,10 +32,11 @@ template <> struct Cfg<SAKE_ENGINE_BF16> {
   static constexpr bool TF32 = false;
   static constexpr int KCH = 64, NSPLIT = 1, NPROD = 1, NCHUNK = 4, FMT = 1, NSTAGE = 4, EPU = 8;
 };
+constexpr int TSM_ROWS = 6;                       // receiver rows whose T = d(loss)/d(ssum) fits the staging buffer
+constexpr int AUX_BYTES = 2 * TILE * 16 /*gdS (fwd: dirm)*/ + 2 * TILE * 16 /*gaS*/ + TSM_ROWS * CC * 16 /*T rows*/;
 template <class CF> __host__ __device__ constexpr int stage_bytes() { return CF::NSPLIT * (P_IMG + W_IMG); }
 template <class CF> __host__ __device__ constexpr size_t smem_bytes() {
-  return (size_t)CF::NSTAGE * stage_bytes<CF>() + 2 * TILE * 16 /*dirm*/ + 2 * TILE * 16 /*gdS*/ + 2 * TILE * 16 /*gaS*/ +
-         256 /*barriers*/ + 1024 /*alignment slack*/;
+  return (size_t)CF::NSTAGE * stage_bytes<CF>() + AUX_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 }
 // products (pair-side split, weight-side split), small terms last
 __device__ __constant__ int c_prod_p[3] = {0, 1, 0};
@@ -132,23 +133,27 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
 template <class CF>
 struct Smem {
   uint8_t* stages;
-  float4* dirm;   // [2][TILE]  (dir*m xyz, segment-end flag)            forward
+  float4* dirm;   // [2][TILE]  (dir*m xyz, segment-end flag)            forward (aliases gdS)
   float4* gdS;    // [2][TILE]  partial g_dir of the two column halves     backward
   float4* gaS;    // [2][TILE]  partial g_att of the two column halves     backward
-  uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty;
+  float4* Tsm;    // [TSM_ROWS][CC] cotangent rows of the tile's receivers   backward (TMA-staged)
+  uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty, *t_full, *t_empty;
   uint32_t* tmem_ptr;
   __device__ Smem(uint8_t* raw) {
     uint8_t* b = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     stages = b;
     dirm = reinterpret_cast<float4*>(b + (size_t)CF::NSTAGE * stage_bytes<CF>());
-    gdS = dirm + 2 * TILE;
+    gdS = dirm;
     gaS = gdS + 2 * TILE;
-    full_w = reinterpret_cast<uint64_t*>(gaS + 2 * TILE);
+    Tsm = gaS + 2 * TILE;
+    full_w = reinterpret_cast<uint64_t*>(Tsm + TSM_ROWS * CC);
     full_e = full_w + CF::NSTAGE;
     empty = full_e + CF::NSTAGE;
     acc_full = empty + CF::NSTAGE;      // [2]
     acc_empty = acc_full + 2;           // [2]
-    tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    t_full = acc_empty + 2;
+    t_empty = t_full + 1;
+    tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 1);
   }
   __device__ uint8_t* p_img(int s) const { return stages + (size_t)s * stage_bytes<CF>(); }
   __device__ uint8_t* w_img(int s) const { return stages + (size_t)s * stage_bytes<CF>() + CF::NSPLIT * P_IMG; }
@@ -336,6 +341,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 128); mbar_init(sm.empty + s, 1); }
     mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d2_empty, 256); mbar_init(sm.acc_empty + 1, 1);
+    mbar_init(sm.t_full, 1); mbar_init(sm.t_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(sm.tmem_ptr);
@@ -345,10 +351,19 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   const uint32_t tmem_base = *sm.tmem_ptr;
   const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  const bool use_tsm = g.rpt <= TSM_ROWS;          // T rows of the tile are staged in smem by TMA
   if (warp == 0) {
     if (lane == 0) {
       int pos = 0;
-      for (int it = 0; it < ntl; ++it)
+      for (int it = 0; it < ntl; ++it) {
+        if (use_tsm) {
+          const int tile = blockIdx.x + it * gridDim.x;
+          const int row0 = g.nseg == 1 ? tile * g.rpt : tile / g.nseg;
+          const int nrows = min(g.rpt, g.R - row0);
+          mbar_wait(sm.t_empty, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(sm.t_full, (uint32_t)nrows * CC * 16);
+          bulk_g2s(sm.Tsm, T4 + (size_t)row0 * CC, (uint32_t)nrows * CC * 16, sm.t_full);
+        }
         for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           const uint8_t* src = (c2 < NCH ? w1img + (size_t)c2 * CF::NSPLIT * W_IMG
@@ -358,6 +373,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           for (int sp = 0; sp < CF::NSPLIT; ++sp)
             bulk_g2s(sm.w_img(s) + sp * W_IMG, src + (size_t)sp * W_IMG, W_IMG, sm.full_w + s);
         }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -455,8 +471,10 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         m = mask ? mask[prx] : 1.0f;
         d0 = r0 * inv * m; d1 = r1 * inv * m; d2 = r2 * inv * m;
         Trow = T4 + (size_t)row * CC;
+        if (use_tsm) Trow = sm.Tsm + (size_t)(row - (g.nseg == 1 ? tile * g.rpt : row)) * CC;
       }
       // ---------------- epilogue 1: dZ chunks for GEMM2 (this half owns ring slots of parity hh)
+      if (use_tsm) mbar_wait(sm.t_full, it & 1);
       mbar_wait(d1_full, it & 1);
       tc_fence_after();
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -476,7 +494,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
             const int cpi = kc2 * CF::KCH + part * 32 + k;
             const float co = ftanh_(v[k]);
             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) t4 = __ldg(Trow + cpi);
+            if (valid) t4 = use_tsm ? Trow[cpi] : __ldg(Trow + cpi);
             const float gco = d0 * t4.x + d1 * t4.y + d2 * t4.z;
             g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
             dz[part * 32 + k] = gco * (1.0f - co * co);
@@ -494,6 +512,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         tc_fence_before();
         mbar_arrive(sm.full_e + s);
       }
+      if (use_tsm) mbar_arrive(sm.t_empty);          // T rows of this tile are consumed
       sm.gdS[hh * TILE + p] = make_float4(g0, g1, g2, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (hh == 0 && valid) {
