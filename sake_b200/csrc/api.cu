@@ -205,19 +205,26 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
   if ((rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st)))
     return rc;
-  if (sc.nbuf && (rc = tc_node_dw(d, *grads, sc, engine, st))) return rc;
+  XtgList xl;
+  if (sc.nbuf && (rc = tc_node_dw(d, *grads, sc, xl, st))) return rc;
   float* gWx = grads ? grads->x_mixing_kernel : nullptr;
   if (engine == SAKE_ENGINE_FP32 || !d.spatial) {
     if ((rc = gen_mix_bwd(d, *params, x, mask, sv, sc, gWx, st))) return rc;
   } else {
-    if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, st))) return rc;
+    if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, xl, st))) return rc;
   }
   if ((rc = gen_attn_bwd(d, *params, sv, sc, st))) return rc;
   if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d))
-    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, b + SL.edgew, b + SL.edgeb, engine, st);
+    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, b + SL.edgew, b + SL.edgeb, xl, st);
   else
     rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);
   if (rc) return rc;
+  if (xl.n > 0) {
+    // every weight-gradient contraction of this layer in one batched tensor-core launch
+    if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, st))) return rc;
+    tc_edge_finish(xl, st);
+    tc_node_finish(xl, st);
+  }
   return gen_node_pre_bwd(d, *params, h, dh, grads, sc, st);
 }
 

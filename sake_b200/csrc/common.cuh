@@ -125,6 +125,36 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_end_launch(st); }
 };
 
+// D[MX x NG] += sum_p X[p][:]^T G[p][:]  (tc_xtg.cu) — every weight-gradient contraction (K = pairs or nodes)
+struct XtgArgs {
+  const float* X; int ldx; int xw;     // X source [P, xw] row-major fp32 (ignored when e != nullptr)
+  const float* e; const float* att;    // X = e (x) att  (xw = 256, feature c = f*4 + head) when e != nullptr
+  int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
+  const float* G; int ldg; int gw;     // G source [P, gw]
+  int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
+  long long P, pairs_per_cta;
+  float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
+  float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
+  float* partial;                            // scratch for per-CTA partial sums (tc_xtg_partial_bytes()); NULL = atomics
+  int gx;                                    // CTAs assigned to this problem (set by the launcher)
+};
+// All weight-gradient contractions of one layer backward are collected and run as ONE batched launch
+// (+ one reduction launch): blockIdx.y selects the problem.
+struct XtgList {
+  static constexpr int MAXP = 12;
+  XtgArgs a[MAXP];
+  int n = 0;
+  // small follow-up kernels that consume `extra` rows of some problems
+  float *post_tmp = nullptr, *g_post2_bias = nullptr, *g_post0_bias = nullptr;
+  float *mb_extra = nullptr, *g_mu = nullptr, *g_beta = nullptr;
+  const float *mu = nullptr, *beta = nullptr;
+  int K = 0;
+  int push(const XtgArgs& q) { if (n >= MAXP) return -1; a[n++] = q; return 0; }
+};
+int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st);
+int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
+size_t tc_xtg_partial_bytes();
+
 // ---- generic fp32 engine ------------------------------------------------------------------
 int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st);
 int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
@@ -141,7 +171,7 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
                       const BwdScratch& sc, cudaStream_t st);
 size_t tc_node_dw_scratch_bytes(const Dims& d);
-int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, int engine, cudaStream_t st);
+int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
 int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
@@ -156,24 +186,11 @@ int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const fl
                const Saved& sv, void* tc_scratch, int engine, cudaStream_t st);
 // mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
-               const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine,
+               const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L,
                cudaStream_t st);
 size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads);
 
-// D[MX x NG] += sum_p X[p][:]^T G[p][:]  (tc_xtg.cu) — every weight-gradient contraction (K = pairs or nodes)
-struct XtgArgs {
-  const float* X; int ldx; int xw;     // X source [P, xw] row-major fp32 (ignored when e != nullptr)
-  const float* e; const float* att;    // X = e (x) att  (xw = 256, feature c = f*4 + head) when e != nullptr
-  int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
-  const float* G; int ldg; int gw;     // G source [P, gw]
-  int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
-  long long P, pairs_per_cta;
-  float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
-  float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
-  float* partial;                            // scratch for per-CTA partial sums (tc_xtg_partial_bytes()); NULL = atomics
-};
-int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
-size_t tc_xtg_partial_bytes();
+
 bool tc_supported(const Dims& d);
 
 // ---- tcgen05 engine (edge model), tc_edge.cu ---------------------------------------------------
@@ -183,7 +200,9 @@ size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads);
 int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 void* wscratch, cudaStream_t st);
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
-                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, int engine,
+                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
                 cudaStream_t st);
+void tc_edge_finish(const XtgList& L, cudaStream_t st);
+void tc_node_finish(const XtgList& L, cudaStream_t st);
 
 }  // namespace sake

@@ -934,39 +934,44 @@ __global__ void k_post_bias_finish(const float* __restrict__ tmp, float* __restr
 }
 size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) * (size_t)d.R * NB_LD) + 1024; }
 
-int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, int engine, cudaStream_t st) {
+int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st) {
   const float* nb = sc.nbuf;
   float* tmp = sc.nbuf + (size_t)d.R * NB_LD;          // [128] bias scratch
-  int rc;
   auto call = [&](const float* X, int xw, int ones, int mxpad, const float* G, int gw, int ng, float* out, int ldo,
                   int out_rows, int out_cols, float* extra, int extra_ld) {
     XtgArgs q;
     memset(&q, 0, sizeof(q));
     q.X = X; q.ldx = NB_LD; q.xw = xw; q.ones_col = ones; q.G = G; q.ldg = NB_LD; q.gw = gw; q.MXpad = mxpad; q.NG = ng;
     q.P = d.R; q.out = out; q.ldo = ldo; q.out_rows = out_rows; q.out_cols = out_cols;
-    q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld; q.partial = sc.xtg_partial;
-    return tc_xtg(q, engine, 0, st);
+    q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld;
+    return L.push(q);
   };
+  int rc = 0;
   // node_mlp (layers.py:58-66)
-  if ((rc = call(nb + NB_N1, 64, 64, 128, nb + NB_GT2, 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64))) return rc;
-  if ((rc = call(nb + NB_CAT, 256, -1, 256, nb + NB_GT1, 64, 64, g.node0_kernel, 64, 256, 64, nullptr, 64))) return rc;
-  if ((rc = call(nb + NB_CAT + 256, 128, 128, 256, nb + NB_GT1, 64, 64, g.node0_kernel + 256 * 64, 64, 128, 64,
-                 g.node0_bias, 64))) return rc;
+  rc |= call(nb + NB_N1, 64, 64, 128, nb + NB_GT2, 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
+  rc |= call(nb + NB_CAT, 256, -1, 256, nb + NB_GT1, 64, 64, g.node0_kernel, 64, 256, 64, nullptr, 64);
+  rc |= call(nb + NB_CAT + 256, 128, 128, 256, nb + NB_GT1, 64, 64, g.node0_kernel + 256 * 64, 64, 128, 64, g.node0_bias, 64);
   if (d.spatial) {
     // post_norm_mlp (layers.py:85-92); the ones-row of the first call carries both bias gradients
     SAKE_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 128, st));
-    if ((rc = call(nb + NB_HP1, 64, 64, 128, nb + NB_GTP2, 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128))) return rc;
-    k_post_bias_finish<<<1, 128, 0, st>>>(tmp, g.post2_bias, g.post0_bias);
-    if ((rc = call(nb + NB_NRM, 256, -1, 256, nb + NB_GTP1, 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64))) return rc;
+    rc |= call(nb + NB_HP1, 64, 64, 128, nb + NB_GTP2, 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128);
+    L.post_tmp = tmp; L.g_post2_bias = g.post2_bias; L.g_post0_bias = g.post0_bias;
+    rc |= call(nb + NB_NRM, 256, -1, 256, nb + NB_GTP1, 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64);
   }
   if (d.update && d.has_v) {
     // velocity_mlp (layers.py:69-76)
-    if ((rc = call(nb + NB_HOUT, 64, 64, 128, nb + NB_GTV, 64, 64, g.vel0_kernel, 64, 64, 64, g.vel0_bias, 64))) return rc;
-    if ((rc = call(nb + NB_AV, 64, -1, 128, nb + NB_GY, 1, 16, g.vel2_kernel, 1, 64, 1, nullptr, 16))) return rc;
+    rc |= call(nb + NB_HOUT, 64, 64, 128, nb + NB_GTV, 64, 64, g.vel0_kernel, 64, 64, 64, g.vel0_bias, 64);
+    rc |= call(nb + NB_AV, 64, -1, 128, nb + NB_GY, 1, 16, g.vel2_kernel, 1, 64, 1, nullptr, 16);
   }
-  note_launches(1);
-  SAKE_CUDA_CHECK(cudaGetLastError());
+  if (rc) { set_error("xtg list full"); return SAKE_EINVAL; }
   return 0;
+}
+
+void tc_node_finish(const XtgList& L, cudaStream_t st) {
+  if (L.post_tmp) {
+    k_post_bias_finish<<<1, 128, 0, st>>>(L.post_tmp, L.g_post2_bias, L.g_post0_bias);
+    note_launches(1);
+  }
 }
 
 int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st) {

@@ -543,7 +543,7 @@ size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads) {
 }
 
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
-                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, int engine,
+                const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
                 cudaStream_t st) {
   EdgeW w = carve_edge_w(wscratch);
   edge_prep(d, p, w, st);
@@ -566,32 +566,36 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   if (g) {
-    int rc;
     XtgArgs q;
     // dW2, db2 (layers.py:24):  a1^T g_e
     memset(&q, 0, sizeof(q));
     q.X = a1buf; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.ge; q.ldg = 64; q.gw = 64; q.MXpad = 128; q.NG = 64;
     q.P = d.P; q.out = g->mlp_out2_kernel; q.ldo = 64; q.out_rows = 64; q.out_cols = 64;
-    q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64; q.partial = sc.xtg_partial;
-    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
+    q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64;
+    L.push(q);
     // dW1[2H : 2H+K+1] (RBF channels + distance row, layers.py:22) and the RBF mean / width sums
     SAKE_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(float) * 2 * PB_LD, st));
     memset(&q, 0, sizeof(q));
     q.X = gbuf; q.ldx = 64; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
     q.P = d.P; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
-    q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD; q.partial = sc.xtg_partial;
-    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
-    k_mubeta_finish<<<1, 64, 0, st>>>(d.K, p.rbf_means, p.rbf_betas, extra, g->rbf_means, g->rbf_betas);
+    q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD;
+    L.push(q);
+    L.mb_extra = extra; L.mu = p.rbf_means; L.beta = p.rbf_betas; L.g_mu = g->rbf_means; L.g_beta = g->rbf_betas; L.K = d.K;
     // dWs, dbs (layers.py:80):  e^T g_q
     memset(&q, 0, sizeof(q));
     q.X = sv.e; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.gw = 4; q.MXpad = 128; q.NG = 16;
     q.P = d.P; q.out = g->sem_kernel; q.ldo = 4; q.out_rows = 64; q.out_cols = 4;
-    q.extra = g->sem_bias; q.extra_rows = 1; q.extra_ld = 4; q.partial = sc.xtg_partial;
-    if ((rc = tc_xtg(q, engine, 0, st))) return rc;
-    note_launches(1);
-    SAKE_CUDA_CHECK(cudaGetLastError());
+    q.extra = g->sem_bias; q.extra_rows = 1; q.extra_ld = 4;
+    if (L.push(q)) { set_error("xtg list full"); return SAKE_EINVAL; }
   }
   return 0;
+}
+
+void tc_edge_finish(const XtgList& L, cudaStream_t st) {
+  if (L.mb_extra) {
+    k_mubeta_finish<<<1, 64, 0, st>>>(L.K, L.mu, L.beta, L.mb_extra, L.g_mu, L.g_beta);
+    note_launches(1);
+  }
 }
 
 }  // namespace sake

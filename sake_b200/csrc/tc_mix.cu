@@ -695,7 +695,7 @@ int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* g
 
 template <int ENGINE>
 static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
-                       const BwdScratch& sc, float* gWx, void* scratch, cudaStream_t st) {
+                       const BwdScratch& sc, float* gWx, void* scratch, XtgList& L, cudaStream_t st) {
   using CF = Cfg<ENGINE>;
   uint8_t* w1 = (uint8_t*)scratch;
   uint8_t* w2 = w1 + wimg_bytes<CF>();
@@ -725,8 +725,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     a.G = sc.gZ; a.ldg = CC; a.gw = CC;
     a.MXpad = CC; a.NG = CC; a.P = d.P;
     a.out = gWx; a.ldo = CC; a.out_rows = CC; a.out_cols = CC;
-    a.partial = sc.xtg_partial;
-    return tc_xtg(a, ENGINE, 3, st);
+    if (L.push(a)) { set_error("xtg list full"); return SAKE_EINVAL; }
   }
   return 0;
 }
@@ -738,9 +737,9 @@ int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const fl
 }
 
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
-               const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, cudaStream_t st) {
-  if (engine == SAKE_ENGINE_BF16) return tc_bwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, sc, gWx, tc_scratch, st);
-  return tc_bwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, sc, gWx, tc_scratch, st);
+               const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L, cudaStream_t st) {
+  if (engine == SAKE_ENGINE_BF16) return tc_bwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, sc, gWx, tc_scratch, L, st);
+  return tc_bwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, sc, gWx, tc_scratch, L, st);
 }
 
 // ---- self-test ------------------------------------------------------------------------------------

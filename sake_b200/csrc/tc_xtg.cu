@@ -68,9 +68,13 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
   }
 }
 
+struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
+
 template <int ENGINE>
-__global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
+__global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant__ XtgBatch batch) {
   using CF = XCfg<ENGINE>;
+  const XtgArgs& a = batch.a[blockIdx.y];
+  if ((int)blockIdx.x >= a.gx) return;                        // CTA beyond this problem's range
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int xblocks = a.MXpad / XBLK;
@@ -242,8 +246,11 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(XtgArgs a) {
 }
 
 // out[row][col] += sum_cta partial[cta][col][row]   (deterministic second stage of the flush)
-__global__ void __launch_bounds__(128) k_xtg_reduce(XtgArgs a, int ncta) {
+__global__ void __launch_bounds__(128) k_xtg_reduce(const __grid_constant__ XtgBatch batch) {
+  const XtgArgs& a = batch.a[blockIdx.y];
   const int col = blockIdx.x;
+  const int ncta = a.gx;
+  if (col >= a.NG || a.partial == nullptr) return;
   for (int row = threadIdx.x; row < a.out_rows + a.extra_rows; row += blockDim.x) {
     const float* pp = a.partial + (size_t)col * a.MXpad + row;
     float s = 0.f;
@@ -256,49 +263,85 @@ __global__ void __launch_bounds__(128) k_xtg_reduce(XtgArgs a, int ncta) {
   }
 }
 
-size_t tc_xtg_partial_bytes() { return (size_t)160 * 256 * 256 * sizeof(float); }
+size_t tc_xtg_partial_bytes() { return (size_t)128 << 20; }
 
-int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
-  XtgArgs a = a0;
-  if (a.P <= 0) return 0;
+static int xtg_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// Launch every collected contraction as one grid (blockIdx.y = problem) + one reduction grid.
+int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st) {
+  if (L.n == 0) return 0;
   const bool bf = engine == SAKE_ENGINE_BF16;
   const int nsplit = bf ? 1 : 3;
-  if (a.extra_ld == 0) a.extra_ld = a.NG;
-  if (a.MXpad % 128 != 0 || a.MXpad > 256 || a.NG % 16 != 0 || a.NG > 256 || (a.MXpad / 128) * a.NG > 512) {
-    set_error("tc_xtg: unsupported shape MXpad=%d NG=%d", a.MXpad, a.NG);
-    return SAKE_EUNSUPPORTED;
+  const int sms = xtg_num_sms();
+  XtgBatch batch;
+  memset(&batch, 0, sizeof(batch));
+  size_t smem_max = 0, poff = 0;
+  int gx_max = 0, ng_max = 0, nb = 0;
+  long long prof_pairs = 0;
+  for (int i = 0; i < L.n; ++i) {
+    XtgArgs a = L.a[i];
+    if (a.P <= 0) continue;
+    if (a.extra_ld == 0) a.extra_ld = a.NG;
+    if (a.MXpad % 128 != 0 || a.MXpad > 256 || a.NG % 16 != 0 || a.NG > 256 || (a.MXpad / 128) * a.NG > 512) {
+      set_error("tc_xtg: unsupported shape MXpad=%d NG=%d", a.MXpad, a.NG);
+      return SAKE_EUNSUPPORTED;
+    }
+    const size_t lbo = (size_t)XKP * 128;
+    const size_t stage = nsplit * ((size_t)(a.MXpad / XBLK) * lbo + (size_t)((a.NG + XBLK - 1) / XBLK) * lbo);
+    const size_t smem = XTG_NSTAGE * stage + 256 + 1024;
+    if (smem > smem_max) smem_max = smem;
+    long long stages_total = (a.P + XKP - 1) / XKP;
+    long long per = (stages_total + sms - 1) / sms;
+    if (per < 4) per = 4;                                  // keep the flush amortised
+    a.pairs_per_cta = per * XKP;
+    a.gx = (int)((a.P + a.pairs_per_cta - 1) / a.pairs_per_cta);
+    const size_t need = (size_t)a.gx * a.MXpad * a.NG;
+    if (partial != nullptr && (poff + need) * sizeof(float) <= tc_xtg_partial_bytes()) {
+      a.partial = partial + poff;
+      poff += need;
+    } else {
+      a.partial = nullptr;                                 // falls back to atomics
+    }
+    if (a.gx > gx_max) gx_max = a.gx;
+    if (a.NG > ng_max) ng_max = a.NG;
+    if (a.P > prof_pairs) prof_pairs = a.P;
+    batch.a[nb++] = a;
   }
-  const size_t lbo = (size_t)XKP * 128;
-  const size_t stage = nsplit * ((size_t)(a.MXpad / XBLK) * lbo + (size_t)((a.NG + XBLK - 1) / XBLK) * lbo);
-  const size_t smem = XTG_NSTAGE * stage + 256 + 1024;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long stages_total = (a.P + XKP - 1) / XKP;
-  long long per = (stages_total + sms - 1) / sms;
-  if (per < 4) per = 4;                                  // keep the atomic flush amortised
-  a.pairs_per_cta = per * XKP;
-  const int gx = (int)((a.P + a.pairs_per_cta - 1) / a.pairs_per_cta);
-  if (gx > 160) a.partial = nullptr;                   // partial buffer is sized for <= 160 CTAs
+  L.n = 0;
+  if (nb == 0) return 0;
+  if (smem_max > 200 * 1024) { set_error("tc_xtg: smem %zu", smem_max); return SAKE_EUNSUPPORTED; }
   static bool attr_tf = false, attr_bf = false;
   if (bf) {
     if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
   } else {
     if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
   }
-  if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
   {
-    ProfScope prof(prof_kind, a.P, st);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16><<<gx, XTG_THREADS, smem, st>>>(a);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3><<<gx, XTG_THREADS, smem, st>>>(a);
-    if (a.partial != nullptr) {
-      k_xtg_reduce<<<a.NG, 128, 0, st>>>(a, gx);
-      note_launches(1);
-    }
+    ProfScope prof(prof_kind, prof_pairs, st);
+    dim3 grid(gx_max, nb);
+    if (bf) k_tc_xtg<SAKE_ENGINE_BF16><<<grid, XTG_THREADS, smem_max, st>>>(batch);
+    else k_tc_xtg<SAKE_ENGINE_TF32X3><<<grid, XTG_THREADS, smem_max, st>>>(batch);
+    dim3 rgrid(ng_max, nb);
+    k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
   }
-  note_launches(1);
+  note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
+  XtgList L;
+  L.push(a0);
+  return tc_xtg_flush(L, a0.partial, engine, prof_kind, st);
 }
 
 }  // namespace sake
