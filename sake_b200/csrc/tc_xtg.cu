@@ -34,24 +34,36 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// 8 consecutive features of one pair -> one 16-byte unit in each split image
+// upper halves of two fp32 words -> one bf16x2 word (truncation), one PRMT
+__device__ __forceinline__ uint32_t pack_hi16(float a, float b) {
+  return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+__device__ __forceinline__ float trunc_bf16(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFF0000u); }
+// 8 consecutive features of one pair -> one 16-byte unit in each split image.
+// 3-way split by truncation: x = hi + mid + lo exactly up to 2^-24 |x| (each term keeps 8 mantissa bits),
+// two integer ops + one FSUB per term instead of round-to-nearest conversions.
 template <class CF>
 __device__ __forceinline__ void xtg_store_unit(uint8_t* img, size_t split_stride, uint32_t off, const float* v) {
-  uint32_t pk[4];
+  if constexpr (CF::NSPLIT == 1) {
+    uint32_t pk[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  if constexpr (CF::NSPLIT == 3) {
+    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  } else {
+    uint32_t pk[4];
     float r[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+    for (int i = 0; i < 4; ++i) pk[i] = pack_hi16(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+    for (int i = 0; i < 8; ++i) r[i] = v[i] - trunc_bf16(v[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack_hi16(r[2 * i], r[2 * i + 1]);
     *reinterpret_cast<uint4*>(img + split_stride + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = r[i] - __bfloat162float(__float2bfloat16_rn(r[i]));
+    for (int i = 0; i < 8; ++i) r[i] = r[i] - trunc_bf16(r[i]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) pk[i] = pack_hi16(r[2 * i], r[2 * i + 1]);
     *reinterpret_cast<uint4*>(img + 2 * split_stride + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
@@ -131,6 +143,24 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
     const int gu = gblocks * (XBLK / XEPU);          // G side
     const bool xvec = a.X != nullptr && (a.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0);
     const bool gvec = (a.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
+    // Per-thread work items are loop invariant: up to 4 X units and 4 G units (pair row r, features c0..c0+7).
+    // Everything that needs an integer division is computed once; per stage only pointers advance.
+    int xr[4], xc[4], gr[4], gc[4];
+    uint32_t xo[4], go[4];
+    bool xok[4], gok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = bt + 256 * k;
+      xok[k] = idx < XKP * xu;
+      gok[k] = idx < XKP * gu;
+      xr[k] = xok[k] ? idx / xu : 0;
+      xc[k] = xok[k] ? (idx - xr[k] * xu) * XEPU : 0;
+      gr[k] = gok[k] ? idx / gu : 0;
+      gc[k] = gok[k] ? (idx - gr[k] * gu) * XEPU : 0;
+      xo[k] = (uint32_t)(xc[k] / XBLK) * LBO + sw128_offset((uint32_t)xr[k], (uint32_t)((xc[k] % XBLK) / XEPU));
+      go[k] = (uint32_t)(gc[k] / XBLK) * LBO + sw128_offset((uint32_t)gr[k], (uint32_t)((gc[k] % XBLK) / XEPU));
+    }
+    const bool emode = a.e != nullptr;
     // Software pipeline: the global loads of stage it+1 are issued right after the stores of stage it, so
     // their latency overlaps the wait for the next free slot instead of sitting in front of every store.
     float xv[4][8], gv[4][8];
@@ -138,30 +168,19 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
       const long long p0 = p_beg + (long long)it * XKP;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int idx = bt + 256 * k;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { xv[k][i] = 0.f; gv[k][i] = 0.f; }
-        if (idx < XKP * xu) {
-          const int r = idx / xu, ug = idx - r * xu;
-          const long long p = p0 + r;
-          const int c0 = ug * XEPU;
-          if (p < p_end) {
-            if (a.e != nullptr) {           // raw operands of E = e (x) att; the product is formed at store time
-              if (c0 < 256) {
-                const float4 at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
-                const float2 ef = __ldg(reinterpret_cast<const float2*>(a.e + p * 64 + c0 / 4));
-                xv[k][0] = at.x; xv[k][1] = at.y; xv[k][2] = at.z; xv[k][3] = at.w; xv[k][4] = ef.x; xv[k][5] = ef.y;
-              }
-            } else {
-              load8(a.X + p * a.ldx, c0, a.xw, xvec, xv[k]);
-            }
+        if (xok[k] && p0 + xr[k] < p_end) {
+          const long long p = p0 + xr[k];
+          if (emode) {                      // raw operands of E = e (x) att; the product is formed at store time
+            const float4 at = __ldg(reinterpret_cast<const float4*>(a.att + p * 4));
+            const float2 ef = __ldg(reinterpret_cast<const float2*>(a.e + p * 64 + (xc[k] >> 2)));
+            xv[k][0] = at.x; xv[k][1] = at.y; xv[k][2] = at.z; xv[k][3] = at.w; xv[k][4] = ef.x; xv[k][5] = ef.y;
+          } else {
+            load8(a.X + p * a.ldx, xc[k], a.xw, xvec, xv[k]);
           }
         }
-        if (idx < XKP * gu) {
-          const int r = idx / gu, ug = idx - r * gu;
-          const long long p = p0 + r;
-          if (p < p_end) load8(a.G + p * a.ldg, ug * XEPU, a.gw, gvec, gv[k]);
-        }
+        if (gok[k] && p0 + gr[k] < p_end) load8(a.G + (p0 + gr[k]) * a.ldg, gc[k], a.gw, gvec, gv[k]);
       }
     };
     if (nst > 0) load_stage(0);
@@ -173,32 +192,23 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
       const long long p0 = p_beg + (long long)it * XKP;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int idx = bt + 256 * k;
-        if (idx < XKP * xu) {
-          const int r = idx / xu, ug = idx - r * xu;
-          const int c0 = ug * XEPU;
+        if (xok[k]) {
           float vals[8];
-          if (a.e != nullptr) {             // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
+          if (emode) {                      // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
             vals[0] = xv[k][4] * xv[k][0]; vals[1] = xv[k][4] * xv[k][1]; vals[2] = xv[k][4] * xv[k][2]; vals[3] = xv[k][4] * xv[k][3];
             vals[4] = xv[k][5] * xv[k][0]; vals[5] = xv[k][5] * xv[k][1]; vals[6] = xv[k][5] * xv[k][2]; vals[7] = xv[k][5] * xv[k][3];
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) vals[i] = xv[k][i];
           }
-          if (p0 + r < p_end) {
+          if (a.ones_col >= xc[k] && a.ones_col < xc[k] + 8 && p0 + xr[k] < p_end) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (c0 + i == a.ones_col) vals[i] = 1.0f;
+              if (xc[k] + i == a.ones_col) vals[i] = 1.0f;
           }
-          const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
-          xtg_store_unit<CF>(ximgp, ximg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), vals);
+          xtg_store_unit<CF>(ximgp, ximg, xo[k], vals);
         }
-        if (idx < XKP * gu) {
-          const int r = idx / gu, ug = idx - r * gu;
-          const int c0 = ug * XEPU;
-          const int mb = c0 / XBLK, u = (c0 % XBLK) / XEPU;
-          xtg_store_unit<CF>(gimgp, gimg, (uint32_t)mb * LBO + sw128_offset((uint32_t)r, (uint32_t)u), gv[k]);
-        }
+        if (gok[k]) xtg_store_unit<CF>(gimgp, gimg, go[k], gv[k]);
       }
       fence_proxy_async();
       mbar_arrive(full + s);
