@@ -173,12 +173,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        val, dt, Bs = cpu_arm(args.workload, args.depth, steps, max(1, min(args.warmup, 1)), args.cpu_sample)
+        # honour K / W but keep the whole run within a few minutes (the sample batch bounds each step)
+        steps = max(1, min(args.steps, 30))
+        warm = max(1, min(args.warmup, 5))
+        val, dt, Bs = cpu_arm(args.workload, args.depth, steps, warm, args.cpu_sample)
         sample = f"{Bs} of {B} molecules of the same workload per step, {steps} timed steps"
         print(json.dumps({
             "impl": "reference", "metric": "molecules_per_sec", "value": val, "unit": "molecules/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": sample + " (torch-eager fp32 restatement of the reference; JAX not installable)"},
@@ -206,9 +208,8 @@ def main():
 
     allreduce = None
     if world > 1 and mode == "train":
-        def allreduce(flat):
-            dist.all_reduce(flat)          # NCCL sum over NVLink; 1/world folded into the Adam kernel
-            return 1.0 / world
+        from sake_b200.parallel import GradAllReducer
+        allreduce = GradAllReducer()       # NCCL sum of the flat grad bucket; 1/world folded into the Adam kernel
 
     def step():
         if mode == "train":
