@@ -74,8 +74,8 @@ __device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, in
     float a1 = accumulate ? y[(n0 + 1) * out + o] : (bias ? bias[o] : 0.f);
     const float* x0 = x + n0 * ldx;
     const float* x1 = x0 + ldx;
-#pragma unroll 4
-    for (int i = 0; i < in; ++i) {
+#pragma unroll 16
+    for (int i = 0; i < in; ++i) {      // 16 independent weight loads in flight (L2-latency bound otherwise)
       const float w = W[(size_t)i * out + o];
       a0 = fmaf(x0[i], w, a0);
       a1 = fmaf(x1[i], w, a1);

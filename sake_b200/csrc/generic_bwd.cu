@@ -5,7 +5,7 @@
 
 namespace sake {
 
-static constexpr int NODES = 8;
+static constexpr int NODES = SAKE_NODES;    // nodes per CTA in the per-node kernels
 static constexpr int PJ = 16;
 static constexpr int MJ = 8;
 
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
       float a0 = 0.f, a1 = 0.f;
       const float* g0p = gt1 + n0 * H;
       const float* g1p = g0p + H;
-#pragma unroll 4
+#pragma unroll 16
       for (int f = 0; f < H; ++f) {
         const float w = wt.node0T[(size_t)f * NC + o];
         a0 = fmaf(g0p[f], w, a0);

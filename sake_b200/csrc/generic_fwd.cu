@@ -5,7 +5,7 @@
 
 namespace sake {
 
-static constexpr int NODES = 8;    // nodes per CTA in the per-node kernels
+static constexpr int NODES = SAKE_NODES;    // nodes per CTA in the per-node kernels
 static constexpr int PJ = 16;      // pairs per chunk in the edge kernel
 static constexpr int MJ = 8;       // pairs per chunk in the mix kernel
 

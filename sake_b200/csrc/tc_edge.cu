@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  mbar_wait(wbar, 0);
+  mbar_wait_warp(wbar, 0);
   const uint32_t tmem_base = *tptr;
   const uint32_t tcol = tmem_base + grp * 256;                         // this group's TMEM columns
   const uint32_t lane_addr = tcol + ((uint32_t)((warp & 3) * 32) << 16);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       edge_gemm(tcol + 0, img_u32, smem_u32(sWA), 64, idesc64);          // Z1 -> cols [0,64)
       umma_commit(mbar + grp);
     }
-    mbar_wait(mbar + grp, ph); ph ^= 1;
+    mbar_wait_warp(mbar + grp, ph); ph ^= 1;
     tc_fence_after();
 
     if (!BWD) {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 80, idesc80);       // E' -> cols [64,144)
         umma_commit(mbar + grp);
       }
-      mbar_wait(mbar + grp, ph); ph ^= 1;
+      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
       tc_fence_after();
       // ---------------- (e) e = E' + b2 ; logits = celu(q) - 1e5*diag - 1e5*(1-m)  (layers.py:24,155-165)
 #pragma unroll 1
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 64, idesc64);       // GA1 = GE W2^T -> cols [64,128)
         umma_commit(mbar + grp);
       }
-      mbar_wait(mbar + grp, ph); ph ^= 1;
+      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
       tc_fence_after();
       // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record
 #pragma unroll 1
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         edge_gemm(tcol + 128, img_u32, smem_u32(sWD), 64, idesc64);      // GG = GZ1 W1[2H:]^T -> cols [128,192)
         umma_commit(mbar + grp);
       }
-      mbar_wait(mbar + grp, ph); ph ^= 1;
+      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
       tc_fence_after();
       // ---------------- (g) RBF / geometry backward (utils.py:61-65, functional.py:7-19, layers.py:115)
       float gt = 0.f, gn = 0.f;

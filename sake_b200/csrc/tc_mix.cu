@@ -159,6 +159,11 @@ struct Smem {
   __device__ uint8_t* w_img(int s) const { return stages + (size_t)s * stage_bytes<CF>() + CF::NSPLIT * P_IMG; }
 };
 
+__device__ __noinline__ void emit_ssum(float* o, float s0, float s1, float s2, bool accumulate) {
+  if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
+  else { o[0] = s0; o[1] = s1; o[2] = s2; }
+}
+
 // =================================================================================================
 // forward:  D^T[c' (lane), pair (column)] = sum_c Wx[c][c'] * E[pair][c]
 //   A = weight image (M = 128 of the 256 c' per MMA, two halves), B = E image (N = 128 pairs)
@@ -267,12 +272,12 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
-      mbar_wait(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
+      mbar_wait_warp(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
       sm.dirm[buf * TILE + p] = dm;
 #pragma unroll
       for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
-        mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        mbar_wait_warp(sm.empty + s, (n & 1) ^ 1);
         build_E_chunk<CF>(sm.p_img(s), p, kc, ev, at);
         fence_proxy_async();
         mbar_arrive(sm.full_e + s);
@@ -285,7 +290,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     const bool accumulate = g.nseg > 1;
     for (int it = 0; it < ntl; ++it) {
       const int buf = it & 1, use = it >> 1;
-      mbar_wait(sm.acc_full + buf, use & 1);
+      mbar_wait_warp(sm.acc_full + buf, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + mh * 128;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -300,10 +305,8 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           const float co = ftanh_(v[k]);
           s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
           const int flag = __float_as_int(dm.w);
-          if (flag != 0) {
-            float* o = ssum + ((size_t)(flag - 1) * CC + cp) * 3;
-            if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
-            else { o[0] = s0; o[1] = s1; o[2] = s2; }
+          if (flag != 0) {                      // rare (once per receiver row) and warp-uniform: a real call,
+            emit_ssum(ssum + ((size_t)(flag - 1) * CC + cp) * 3, s0, s1, s2, accumulate);   // not 3 predicated STG per column
             s0 = 0.f; s1 = 0.f; s2 = 0.f;
           }
         }

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
     if (nst > 0) load_stage(0);
     for (int it = 0; it < nst; ++it) {
       const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
-      mbar_wait(empty + s, (n & 1) ^ 1);
+      mbar_wait_warp(empty + s, (n & 1) ^ 1);
       uint8_t* ximgp = base + s * stage;
       uint8_t* gimgp = ximgp + CF::NSPLIT * ximg;
       const long long p0 = p_beg + (long long)it * XKP;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
     }
     // ------------------------------------------------------------ epilogue: flush the accumulator
     if (nst > 0) {
-      mbar_wait(done, 0);
+      mbar_wait_warp(done, 0);
       tc_fence_after();
       const int q = warp & 3, half = (warp - 1) >> 2;      // two warps per lane quarter
       const int nchunks = (a.NG + 31) / 32;
