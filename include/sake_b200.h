@@ -203,6 +203,11 @@ int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capac
 int sake_selftest_xtg(int32_t engine, int64_t P, int32_t xw, int32_t gw, const float* X, const float* G,
                       float* out, sake_stream_t stream);
 
+/* Diagnostic: wait-cycle counters of the forward mix kernel's MMA issuer (armed with the environment
+ * variable SAKE_DEBUG_WSPLITS=7): [0] accumulator, [1] weight chunk, [2] pair chunk, [3] total, [4] tiles.
+ * Reads and clears 8 counters (host memory). */
+int sake_debug_counters(unsigned long long* out8);
+
 /* Number of CUDA kernels this library has launched in this process (diagnostic). */
 unsigned long long sake_launch_count(void);
 

@@ -21,6 +21,7 @@ int dense_fwd(long long rows, int in, int out, int act, const float* x, const fl
 int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
               const float* dy, float* dx, float* dw, float* db, cudaStream_t st);
 int tc_selftest(float* max_abs_err, cudaStream_t st);
+int tc_debug_counters(unsigned long long* out8);
 
 static int make_dims(const SakeDims* s, Dims* d) {
   if (!s) { set_error("dims is NULL"); return SAKE_EINVAL; }
@@ -242,6 +243,8 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
   note_launches(1);
   return dense_bwd(rows, in_features, out_features, act, x, kernel, bias, dy, dx, dkernel, dbias, (cudaStream_t)stream);
 }
+
+int sake_debug_counters(unsigned long long* out8) { return tc_debug_counters(out8); }
 
 unsigned long long sake_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 

@@ -159,6 +159,10 @@ struct Smem {
   __device__ uint8_t* w_img(int s) const { return stages + (size_t)s * stage_bytes<CF>() + CF::NSPLIT * P_IMG; }
 };
 
+// optional wait-time accounting of the MMA issuer (SAKE_DEBUG_WSPLITS=7): cycles spent waiting for
+// [0] accumulator free, [1] weight chunk (TMA), [2] pair-side chunk (builders / epilogue), [3] total loop
+__device__ unsigned long long g_mma_wait[8];
+
 __device__ __noinline__ void emit_ssum(float* o, float s0, float s1, float s2, bool accumulate) {
   if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
   else { o[0] = s0; o[1] = s1; o[2] = s2; }
@@ -198,7 +202,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           mbar_wait(sm.empty + s, (n & 1) ^ 1);
-          const int nsp = dbg_wsplits > 0 ? dbg_wsplits : CF::NSPLIT;
+          const int nsp = dbg_wsplits == 1 ? 1 : CF::NSPLIT;   // 1: timing experiment (half the weight bytes)
           mbar_arrive_expect_tx(sm.full_w + s, nsp * W_IMG);
           for (int sp = 0; sp < nsp; ++sp)
             bulk_g2s(sm.w_img(s) + sp * W_IMG, w1img + ((size_t)kc * CF::NSPLIT + sp) * W_IMG, W_IMG, sm.full_w + s);
@@ -209,14 +213,22 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(CF::FMT, 128, TILE);
       int pos = 0;
+      long long w_acc = 0, w_w = 0, w_e = 0;
+      const long long t_begin = clock64();
       for (int it = 0; it < ntl; ++it) {
         const int buf = it & 1, use = it >> 1;
+        long long t0 = clock64();
         mbar_wait(sm.acc_empty + buf, (use & 1) ^ 1);
+        w_acc += clock64() - t0;
         tc_fence_after();
         for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          t0 = clock64();
           mbar_wait(sm.full_w + s, n & 1);
+          long long t1 = clock64();
           mbar_wait(sm.full_e + s, n & 1);
+          w_w += t1 - t0;
+          w_e += clock64() - t1;
           tc_fence_after();
           const uint32_t wbase = smem_u32(sm.w_img(s)), pbase = smem_u32(sm.p_img(s));
 #pragma unroll
@@ -236,6 +248,13 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           umma_commit(sm.empty + s);
         }
         umma_commit(sm.acc_full + buf);
+      }
+      if (dbg_wsplits == 7) {
+        atomicAdd(&g_mma_wait[0], (unsigned long long)w_acc);
+        atomicAdd(&g_mma_wait[1], (unsigned long long)w_w);
+        atomicAdd(&g_mma_wait[2], (unsigned long long)w_e);
+        atomicAdd(&g_mma_wait[3], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&g_mma_wait[4], (unsigned long long)ntl);
       }
     }
   } else if (warp < 6) {
@@ -646,6 +665,13 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
 // host side
 // =================================================================================================
 bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
+
+int tc_debug_counters(unsigned long long* out8) {
+  SAKE_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_mma_wait, sizeof(unsigned long long) * 8));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  SAKE_CUDA_CHECK(cudaMemcpyToSymbol(g_mma_wait, z, sizeof(z)));
+  return 0;
+}
 
 template <class CF> static size_t wimg_bytes() { return (size_t)CF::NCHUNK * CF::NSPLIT * W_IMG; }
 
