@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
-    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32x3", "bf16"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32x3", "bf16", "f16x2"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--depth", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=16, help="molecules in the CPU-baseline sample batch")
@@ -319,7 +319,8 @@ def main():
     line = {
         "metric": "molecules_per_sec", "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-parity split)", "bf16": "bf16"}[run.engine],
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-parity split)", "bf16": "bf16",
+                  "f16x2": "f16x2 (fp32-parity split, fp16 hi/lo)"}[run.engine],
         "data": "synthetic", "config": config,
         "atom_pairs_per_sec": world * B * N * N * args.depth / (ms_step * 1e-3),
         "real_atom_pairs_per_sec": world * float((n_real.astype(np.float64) ** 2).sum()) * args.depth / (ms_step * 1e-3),

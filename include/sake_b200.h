@@ -50,7 +50,10 @@ enum {
   SAKE_ENGINE_AUTO = 0,   /* tcgen05 3xTF32 when the shape allows, else the generic fp32 path   */
   SAKE_ENGINE_FP32 = 1,   /* generic CUDA-core fp32 kernels, any H / A / K                      */
   SAKE_ENGINE_TF32X3 = 2, /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs) — fp32-parity mode     */
-  SAKE_ENGINE_BF16 = 3    /* tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate) — fast mode  */
+  SAKE_ENGINE_BF16 = 3,   /* tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate) — fast mode  */
+  SAKE_ENGINE_F16X2 = 4   /* tcgen05.mma kind::f16, fp16 hi/lo split with per-row power-of-two scaling
+                             (3 MMAs at the 16-bit rate, 22 mantissa bits) — fp32-parity mode at half
+                             the tensor and shared-memory cost of TF32X3                                */
 };
 
 typedef struct SakeDims {

@@ -47,7 +47,7 @@ static int resolve_engine(const SakeDims* s, const Dims& d) {
   int e = s->engine;
   if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_TF32X3 : SAKE_ENGINE_FP32;
   if (e == SAKE_ENGINE_FP32) return e;
-  if (e == SAKE_ENGINE_TF32X3 || e == SAKE_ENGINE_BF16) {
+  if (e == SAKE_ENGINE_TF32X3 || e == SAKE_ENGINE_BF16 || e == SAKE_ENGINE_F16X2) {
     if (!tc_supported(d)) {
       set_error("tcgen05 engine needs H=64, A=4 (C=256); got H=%d A=%d", d.H, d.A);
       return SAKE_EUNSUPPORTED;
@@ -79,13 +79,14 @@ static Saved carve_saved(const Dims& d, void* base) {
   return s;
 }
 
-struct ScratchLayout { size_t T, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
+struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
   size_t o = 0;
   if (for_backward) {
     L.T = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 4);
+    L.tmax = o; o += align_up(sizeof(float) * (size_t)d.R);
     L.ghe = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
     L.ge = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
     L.gatt = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
@@ -199,7 +200,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   Saved sv = carve_saved(d, const_cast<void*>(saved));
   char* b = (char*)scratch;
   BwdScratch sc;
-  sc.T = (float*)(b + SL.T); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
+  sc.T = (float*)(b + SL.T); sc.tmax = (float*)(b + SL.tmax); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;

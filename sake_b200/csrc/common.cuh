@@ -37,6 +37,7 @@ struct Saved {
 // `scratch` buffer for the backward pass
 struct BwdScratch {
   float* T;         // [R,C,4] cotangent of ssum (float4 per coefficient, w unused)
+  float* tmax;      // [R]     max |T| per receiver (row scale of the fp16-split backward operand)
   float* ghe;       // [R,C]   cotangent of he
   float* ge;        // [P,H]   cotangent of e
   float* gatt;      // [P,A]   cotangent of att, then of the pre-celu logits q
@@ -102,6 +103,16 @@ __device__ __forceinline__ float ftanh_(float x) {
   const float ax = fabsf(x);
   const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * ax) + 1.0f);
   return copysignf(t, x);
+}
+
+// tanh and its derivative sech^2 = 4t/(t+1)^2 (t = e^{2|x|}) from ONE exponential; computing the
+// derivative directly avoids the 1 - tanh^2 cancellation in saturated coefficients.
+__device__ __forceinline__ void ftanh_sech2_(float x, float& th, float& s2) {
+  const float ax = fminf(fabsf(x), 40.0f);
+  const float t = __expf(2.0f * ax);
+  const float r = __fdividef(1.0f, t + 1.0f);
+  th = copysignf(1.0f - 2.0f * r, x);
+  s2 = 4.0f * t * r * r;
 }
 
 void set_error(const char* fmt, ...);

@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     const float* __restrict__ mask, const float* __restrict__ ssum, const float* __restrict__ he_in,
     const float* __restrict__ dh_out, const float* __restrict__ dx_out, const float* __restrict__ dv_out,
     float* __restrict__ dh, float* __restrict__ dx, float* __restrict__ dv, float* __restrict__ T,
-    float* __restrict__ ghe, SakeLayerGrads g, int want_grads, float* __restrict__ nbuf) {
+    float* __restrict__ ghe, SakeLayerGrads g, int want_grads, float* __restrict__ nbuf, float* __restrict__ tmax) {
   extern __shared__ float sm[];
+  __shared__ int tmx[NODES];
+  if (threadIdx.x < NODES) tmx[threadIdx.x] = 0;
   const int H = d.H, C = d.C, N = d.N, NH = NODES * d.H;
   // nbuf != NULL (tcgen05 engines, H = 64): the per-node operands of the weight-gradient contractions are
   // written out (NB_LD floats per node) and the contractions run on the tensor cores (tc_node_dw).
@@ -332,9 +334,12 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
         }
       }
       *reinterpret_cast<float4*>(T + (row * C + c) * 4) = make_float4(t0, t1v, t2v, 0.f);   // [R][C] float4
+      atomicMax(&tmx[n], __float_as_int(fmaxf(fabsf(t0), fmaxf(fabsf(t1v), fabsf(t2v)))));      // non-negative floats order as ints
     }
     if (want_grads && spatial && upd) atomicAdd(g.v_mixing_kernel + c, gwv);
   }
+  __syncthreads();
+  if (threadIdx.x < nn) tmax[r0 + threadIdx.x] = __int_as_float(tmx[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -920,7 +925,7 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
   if ((rc = ensure_smem(k_node_post_bwd, smem))) return rc;
   k_node_post_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, carve_node_wt(d, sc.nodeWT), h, v, mask, sv.ssum,
                                                                 sv.he, dh_out, dx_out, dv_out, dh, dx, dv, sc.T, sc.ghe,
-                                                                g ? *g : null_grads(), g != nullptr, sc.nbuf);
+                                                                g ? *g : null_grads(), g != nullptr, sc.nbuf, sc.tmax);
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -11,6 +11,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte-aligned start of the dynamic shared-memory window.  The pad is added to the ORIGINAL pointer
+// (no integer round trip), so the compiler keeps the shared address space and emits LDS/STS instead of
+// generic LD/ST for everything carved out of it.
+__device__ __forceinline__ uint8_t* align1024_shared(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -134,7 +134,7 @@ __device__ __forceinline__ void edge_gemm(uint32_t d_tmem, uint32_t a_img, uint3
 template <bool BWD>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = align1024_shared(smem_raw);
   constexpr int W_BYTES = BWD ? (WA_BYTES + WC_BYTES + WD_BYTES) : (WA_BYTES + WB_BYTES);
   uint8_t* sWA = base;
   uint8_t* sW2 = base + WA_BYTES;                          // fwd: WB ; bwd: WC

@@ -8,6 +8,7 @@
 // Precision: SAKE_ENGINE_TF32X3 = kind::tf32 with an exact hi/lo split of both operands (3 MMAs:
 // hi*hi + lo*hi + hi*lo) -> fp32-class accuracy; SAKE_ENGINE_BF16 = kind::f16, bf16 operands.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -25,15 +26,23 @@ constexpr int NTHREADS = 448;        // 14 warps: 0 TMA producer, 1 MMA issuer, 
 
 template <int ENGINE> struct Cfg;
 template <> struct Cfg<SAKE_ENGINE_TF32X3> {
-  static constexpr bool TF32 = true;
+  static constexpr bool TF32 = true, F16 = false;
   static constexpr int KCH = 32, NSPLIT = 2, NPROD = 3, NCHUNK = 8, FMT = 2, NSTAGE = 2, EPU = 4;
 };
 template <> struct Cfg<SAKE_ENGINE_BF16> {
-  static constexpr bool TF32 = false;
+  static constexpr bool TF32 = false, F16 = false;
   static constexpr int KCH = 64, NSPLIT = 1, NPROD = 1, NCHUNK = 4, FMT = 1, NSTAGE = 4, EPU = 8;
 };
+// fp16 hi/lo split (x = hi + lo, 22 mantissa bits), 3 MMAs at the 16-bit rate: half the tensor cycles
+// and half the operand bytes of 3xTF32.  fp16's narrow exponent range is handled by exact per-row
+// power-of-two scaling of the pair-side operand (E rows by max|e|, dZ rows by max|T|).
+template <> struct Cfg<SAKE_ENGINE_F16X2> {
+  static constexpr bool TF32 = false, F16 = true;
+  static constexpr int KCH = 64, NSPLIT = 2, NPROD = 3, NCHUNK = 4, FMT = 0, NSTAGE = 2, EPU = 8;
+};
 constexpr int TSM_ROWS = 6;                       // receiver rows whose T = d(loss)/d(ssum) fits the staging buffer
-constexpr int AUX_BYTES = 2 * TILE * 16 /*gdS (fwd: dirm)*/ + 2 * TILE * 16 /*gaS*/ + TSM_ROWS * CC * 16 /*T rows*/;
+constexpr int AUX_BYTES = 2 * TILE * 16 /*gdS (fwd: dirm)*/ + 2 * TILE * 16 /*gaS*/ + TSM_ROWS * CC * 16 /*T rows*/ +
+                          2 * TILE * 4 /*escale*/;
 template <class CF> __host__ __device__ constexpr int stage_bytes() { return CF::NSPLIT * (P_IMG + W_IMG); }
 template <class CF> __host__ __device__ constexpr size_t smem_bytes() {
   return (size_t)CF::NSTAGE * stage_bytes<CF>() + AUX_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
@@ -53,6 +62,18 @@ __device__ __forceinline__ void store_unit(uint8_t* img, int row, int u, const f
     split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
     *reinterpret_cast<float4*>(img + off) = hi;
     *reinterpret_cast<float4*>(img + P_IMG + off) = lo;
+  } else if constexpr (CF::F16) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h2 = __floats2half2_rn(vals[2 * i], vals[2 * i + 1]);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(vals[2 * i] - hf.x, vals[2 * i + 1] - hf.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + P_IMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   } else {
     __nv_bfloat162 b0 = __floats2bfloat162_rn(vals[0], vals[1]);
     __nv_bfloat162 b1 = __floats2bfloat162_rn(vals[2], vals[3]);
@@ -118,6 +139,18 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
     split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
     *reinterpret_cast<float4*>(base + off) = hi;
     *reinterpret_cast<float4*>(base + W_IMG + off) = lo;
+  } else if constexpr (CF::F16) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h2 = __floats2half2_rn(vals[2 * i], vals[2 * i + 1]);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(vals[2 * i] - hf.x, vals[2 * i + 1] - hf.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + W_IMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   } else {
     uint32_t pk[4];
 #pragma unroll
@@ -129,6 +162,15 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
   }
 }
 
+// power-of-two scale that brings a row with max magnitude `mx` to <= ~2^13 (fp16 overflows at 65504)
+__device__ __forceinline__ float row_scale_down(float mx) {
+  return mx > 8192.f ? exp2f(-ceilf(log2f(mx * (1.0f / 8192.f)))) : 1.0f;
+}
+// power-of-two scale that brings a row bounded by `bound` to ~1 (gradients can be arbitrarily small)
+__device__ __forceinline__ float row_scale_unit(float bound) {
+  return (bound > 0.f && bound < 3.0e38f) ? exp2f(-ceilf(log2f(bound))) : 1.0f;
+}
+
 // ---- shared-memory carve-up -----------------------------------------------------------------
 template <class CF>
 struct Smem {
@@ -137,16 +179,18 @@ struct Smem {
   float4* gdS;    // [2][TILE]  partial g_dir of the two column halves     backward
   float4* gaS;    // [2][TILE]  partial g_att of the two column halves     backward
   float4* Tsm;    // [TSM_ROWS][CC] cotangent rows of the tile's receivers   backward (TMA-staged)
+  float* escale;  // [2][TILE] 1/scale of the E rows (fp16-split engine)
   uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty, *t_full, *t_empty;
   uint32_t* tmem_ptr;
   __device__ Smem(uint8_t* raw) {
-    uint8_t* b = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b = align1024_shared(raw);
     stages = b;
     dirm = reinterpret_cast<float4*>(b + (size_t)CF::NSTAGE * stage_bytes<CF>());
     gdS = dirm;
     gaS = gdS + 2 * TILE;
     Tsm = gaS + 2 * TILE;
-    full_w = reinterpret_cast<uint64_t*>(Tsm + TSM_ROWS * CC);
+    escale = reinterpret_cast<float*>(Tsm + TSM_ROWS * CC);
+    full_w = reinterpret_cast<uint64_t*>(escale + 2 * TILE);
     full_e = full_w + CF::NSTAGE;
     empty = full_e + CF::NSTAGE;
     acc_full = empty + CF::NSTAGE;      // [2]
@@ -291,8 +335,21 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
+      float inv_s = 1.0f;
+      if constexpr (CF::F16) {                      // keep |E| = |e*att| <= |e| inside the fp16 range (exact 2^k scale)
+        float mx = 0.f;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) mx = fmaxf(mx, fabsf(ev[q]));
+        const float sc = row_scale_down(mx);
+        if (sc != 1.0f) {
+#pragma unroll
+          for (int q = 0; q < 64; ++q) ev[q] *= sc;
+          inv_s = 1.0f / sc;
+        }
+      }
       mbar_wait_warp(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
       sm.dirm[buf * TILE + p] = dm;
+      if constexpr (CF::F16) sm.escale[buf * TILE + p] = inv_s;
 #pragma unroll
       for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
@@ -318,14 +375,22 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         float v[32];
         tmem_ld32(taddr + cc * 32, v);
         tmem_ld_wait();
+        // phase 1: 32 independent tanh chains (full ILP; no control flow in between)
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float z = v[k];
+          if constexpr (CF::F16) z *= sm.escale[buf * TILE + cc * 32 + k];
+          v[k] = ftanh_(z);
+        }
+        // phase 2: weighted sum over senders; the (rare, warp-uniform) row flush is the only branch
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const float4 dm = sm.dirm[buf * TILE + cc * 32 + k];
-          const float co = ftanh_(v[k]);
+          const float co = v[k];
           s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
           const int flag = __float_as_int(dm.w);
-          if (flag != 0) {                      // rare (once per receiver row) and warp-uniform: a real call,
-            emit_ssum(ssum + ((size_t)(flag - 1) * CC + cp) * 3, s0, s1, s2, accumulate);   // not 3 predicated STG per column
+          if (flag != 0) {                      // once per receiver row: a real call, not 3 predicated STG per column
+            emit_ssum(ssum + ((size_t)(flag - 1) * CC + cp) * 3, s0, s1, s2, accumulate);
             s0 = 0.f; s1 = 0.f; s2 = 0.f;
           }
         }
@@ -350,8 +415,8 @@ template <int ENGINE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
              const float* __restrict__ att, const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
-             const float4* __restrict__ T4, const float* __restrict__ ghe, float* __restrict__ ge,
-             float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out) {
+             const float4* __restrict__ T4, const float* __restrict__ tmax, const float* __restrict__ ghe,
+             float* __restrict__ ge, float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out) {
   using CF = Cfg<ENGINE>;
   constexpr int NCH = CF::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
@@ -452,6 +517,17 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
+      if constexpr (CF::F16) {                      // exact 2^k row scale, undone in epilogue 1
+        float mx = 0.f;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) mx = fmaxf(mx, fabsf(ev[q]));
+        const float sc = row_scale_down(mx);
+        if (sc != 1.0f) {
+#pragma unroll
+          for (int q = 0; q < 64; ++q) ev[q] *= sc;
+        }
+        sm.escale[(it & 1) * TILE + p] = 1.0f / sc;   // rewritten two tiles later, after epilogue 1 of tile it+1
+      }
       int pos = it * 2 * NCH;
 #pragma unroll
       for (int kc = 0; kc < NCH; ++kc, ++pos) {
@@ -499,6 +575,11 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       if (use_tsm) mbar_wait(sm.t_full, it & 1);
       mbar_wait(d1_full, it & 1);
       tc_fence_after();
+      float zs = 1.0f, dzs = 1.0f;                  // fp16-split engine: 1/scale of the E row, scale of the dZ row
+      if constexpr (CF::F16) {
+        zs = sm.escale[(it & 1) * TILE + p];
+        if (valid) dzs = row_scale_unit(2.0f * tmax[row]);      // |dZ| <= |dir|_1 * max|T| < 2 max|T|
+      }
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
       for (int qq = 0; qq < NCH / 2; ++qq) {
@@ -511,15 +592,18 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           float v[32];
           tmem_ld32(lane_addr + kc2 * CF::KCH + part * 32, v);
           tmem_ld_wait();
+          float s2v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) ftanh_sech2_(CF::F16 ? v[k] * zs : v[k], v[k], s2v[k]);   // independent chains first
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int cpi = kc2 * CF::KCH + part * 32 + k;
-            const float co = ftanh_(v[k]);
+            const float co = v[k];
             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) t4 = use_tsm ? Trow[cpi] : __ldg(Trow + cpi);
             const float gco = d0 * t4.x + d1 * t4.y + d2 * t4.z;
             g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
-            dz[part * 32 + k] = gco * (1.0f - co * co);
+            dz[part * 32 + k] = gco * s2v[k];
           }
         }
         if (gZ_out != nullptr && valid) {
@@ -528,6 +612,10 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           for (int k = 0; k < CF::KCH / 4; ++k) o[k] = make_float4(dz[4 * k], dz[4 * k + 1], dz[4 * k + 2], dz[4 * k + 3]);
         }
         mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        if constexpr (CF::F16) {
+#pragma unroll
+          for (int k = 0; k < CF::KCH; ++k) dz[k] *= dzs;
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) store_unit<CF>(sm.p_img(s), p, u, dz + u * CF::EPU);
         fence_proxy_async();
@@ -548,6 +636,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) at = *reinterpret_cast<const float4*>(att + prx * 4);
       float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, ga3 = 0.f;
+      const float idz = CF::F16 ? 1.0f / dzs : 1.0f;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         float v[32];
@@ -563,8 +652,8 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
           for (int k8 = 0; k8 < 8; ++k8) {
             const float4 gh = __ldg(gh4 + k8);
-            const float x0 = fmaf(m, gh.x, v[4 * k8]), x1 = fmaf(m, gh.y, v[4 * k8 + 1]),
-                        x2 = fmaf(m, gh.z, v[4 * k8 + 2]), x3 = fmaf(m, gh.w, v[4 * k8 + 3]);
+            const float x0 = fmaf(m, gh.x, v[4 * k8] * idz), x1 = fmaf(m, gh.y, v[4 * k8 + 1] * idz),
+                        x2 = fmaf(m, gh.z, v[4 * k8 + 2] * idz), x3 = fmaf(m, gh.w, v[4 * k8 + 3] * idz);
             gev[k8] = x0 * at.x + x1 * at.y + x2 * at.z + x3 * at.w;
             ga0 = fmaf(x0, ef[k8], ga0); ga1 = fmaf(x1, ef[k8], ga1);
             ga2 = fmaf(x2, ef[k8], ga2); ga3 = fmaf(x3, ef[k8], ga3);
@@ -597,7 +686,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
                                                         float* __restrict__ D, int nchunk) {
   using CF = Cfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = align1024_shared(smem_raw);
   uint8_t* pimg = base;                                  // [nchunk][NSPLIT][P_IMG]
   uint8_t* wimg = base + (size_t)nchunk * CF::NSPLIT * P_IMG;    // [nchunk][NSPLIT][W_IMG]
   uint64_t* bar = reinterpret_cast<uint64_t*>(wimg + (size_t)nchunk * CF::NSPLIT * W_IMG);
@@ -622,6 +711,17 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
           split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
           *reinterpret_cast<float4*>(wb + off) = hi;
           *reinterpret_cast<float4*>(wb + W_IMG + off) = lo;
+        } else if constexpr (CF::F16) {
+          uint32_t hi[4], lo[4];
+          for (int i = 0; i < 4; ++i) {
+            const __half2 h2 = __floats2half2_rn(vals[2 * i], vals[2 * i + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(vals[2 * i] - hf.x, vals[2 * i + 1] - hf.y);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          *reinterpret_cast<uint4*>(wb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(wb + W_IMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         } else {
           uint32_t pk[4];
           for (int i = 0; i < 4; ++i) {
@@ -677,7 +777,8 @@ template <class CF> static size_t wimg_bytes() { return (size_t)CF::NCHUNK * CF:
 
 size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads) {
   (void)d; (void)for_backward; (void)with_param_grads;
-  size_t w = engine == SAKE_ENGINE_BF16 ? wimg_bytes<Cfg<SAKE_ENGINE_BF16>>() : wimg_bytes<Cfg<SAKE_ENGINE_TF32X3>>();
+  size_t w = engine == SAKE_ENGINE_BF16 ? wimg_bytes<Cfg<SAKE_ENGINE_BF16>>()
+             : engine == SAKE_ENGINE_F16X2 ? wimg_bytes<Cfg<SAKE_ENGINE_F16X2>>() : wimg_bytes<Cfg<SAKE_ENGINE_TF32X3>>();
   return 2 * w + 1024;
 }
 
@@ -741,8 +842,8 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   {
     ProfScope prof(2, d.P, st);
     k_tc_mix_bwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
-                                                                  reinterpret_cast<const float4*>(sc.T), sc.ghe, sc.ge,
-                                                                  sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+                                                                  reinterpret_cast<const float4*>(sc.T), sc.tmax, sc.ghe,
+                                                                  sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
@@ -762,12 +863,14 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
 int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                void* tc_scratch, int engine, cudaStream_t st) {
   if (engine == SAKE_ENGINE_BF16) return tc_fwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, tc_scratch, st);
+  if (engine == SAKE_ENGINE_F16X2) return tc_fwd_impl<SAKE_ENGINE_F16X2>(d, p, x, mask, sv, tc_scratch, st);
   return tc_fwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, tc_scratch, st);
 }
 
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L, cudaStream_t st) {
   if (engine == SAKE_ENGINE_BF16) return tc_bwd_impl<SAKE_ENGINE_BF16>(d, p, x, mask, sv, sc, gWx, tc_scratch, L, st);
+  if (engine == SAKE_ENGINE_F16X2) return tc_bwd_impl<SAKE_ENGINE_F16X2>(d, p, x, mask, sv, sc, gWx, tc_scratch, L, st);
   return tc_bwd_impl<SAKE_ENGINE_TF32X3>(d, p, x, mask, sv, sc, gWx, tc_scratch, L, st);
 }
 
@@ -807,12 +910,15 @@ static int selftest_one(float* max_err, cudaStream_t st) {
 }
 
 int tc_selftest(float* max_abs_err, cudaStream_t st) {
-  float e1 = 0.f, e2 = 0.f;
+  float e1 = 0.f, e2 = 0.f, e3 = 0.f;
   int rc = selftest_one<SAKE_ENGINE_TF32X3>(&e1, st);
   if (rc) return rc;
   rc = selftest_one<SAKE_ENGINE_BF16>(&e2, st);
   if (rc) return rc;
+  rc = selftest_one<SAKE_ENGINE_F16X2>(&e3, st);
+  if (rc) return rc;
   if (max_abs_err) { max_abs_err[0] = e1; max_abs_err[1] = e2; }
+  if (!(e3 < 1e-5f)) { set_error("tcgen05 selftest: f16x2 max abs err %g", e3); return SAKE_ECUDA; }
   if (!(e1 < 1e-5f)) { set_error("tcgen05 selftest: tf32x3 max abs err %g", e1); return SAKE_ECUDA; }
   if (!(e2 < 5e-2f)) { set_error("tcgen05 selftest: bf16 max abs err %g", e2); return SAKE_ECUDA; }
   return 0;

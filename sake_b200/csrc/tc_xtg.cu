@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
   const XtgArgs& a = batch.a[blockIdx.y];
   if ((int)blockIdx.x >= a.gx) return;                        // CTA beyond this problem's range
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = align1024_shared(smem_raw);
   const int xblocks = a.MXpad / XBLK;
   const int gblocks = (a.NG + XBLK - 1) / XBLK;
   constexpr uint32_t LBO = XKP * 128;                         // bytes between 64-feature MN blocks

@@ -7,7 +7,7 @@ import bench
 import sake_b200
 from sake_b200 import runner as R, _lib
 B, N, S, padded, n_min, mode, desc = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"]
-model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=4, engine="tf32x3")
+model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=4, engine=(sys.argv[2] if len(sys.argv) > 2 else "tf32x3"))
 run = R.ModelRunner(model, bench.init_params_cpu(4, S, 0), B, N, S, masked=padded, train=False)
 h, x, mask, am, y, n_real = bench.synth(2666, B, N, S, padded, n_min)
 T = lambda a: None if a is None else torch.tensor(a, device="cuda")

@@ -32,9 +32,11 @@ def _setup(H, depth, B, N, S, seed, engine, padded=False, n_min=2, update=True):
         (None if am is None else torch.tensor(am, device=dev))
 
 
-@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("engine", ["fp32", "auto", "f16x2"])
 @pytest.mark.parametrize("H,depth,B,N", [(64, 2, 4, 21), (16, 3, 3, 9), (64, 1, 2, 70)])
 def test_energy_forces_vs_oracle(engine, H, depth, B, N):
+    if engine == "f16x2" and H != 64:
+        pytest.skip("tcgen05 engines need H = 64")
     model, p, h, x, _, _ = _setup(H, depth, B, N, 8, 2666 + N, engine)
     e, f = model.energy_and_forces(p, h, x)
     po = _oracle_params(p)
@@ -45,7 +47,7 @@ def test_energy_forces_vs_oracle(engine, H, depth, B, N):
     assert ferr < 1e-4, f"force abs err {ferr:.3e} (max |F| {f0.abs().max().item():.3e})"
 
 
-@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("engine", ["fp32", "auto", "f16x2"])
 def test_param_grads_vs_oracle(engine):
     import sake_b200.layers as L
     H, depth, B, N = 64, 2, 3, 12
@@ -75,7 +77,7 @@ def test_param_grads_vs_oracle(engine):
         assert err < 2e-3 * scale + 1e-6, f"{k}: err {err:.3e} scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("engine", ["fp32", "auto", "f16x2"])
 def test_padded_batch_matches_unpadded_oracle(engine):
     """QM9-style padding (scripts/qm9/run.py:23-24,35): real atoms of every padded molecule match the
     oracle run on that molecule alone, unpadded and unmasked (sake/tests/test_mask.py:202-240)."""
@@ -166,7 +168,7 @@ def test_tcgen05_selftest():
     assert err[0] < 1e-5 and err[1] < 5e-2
 
 
-@pytest.mark.parametrize("engine", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("engine", ["tf32x3", "f16x2", "bf16"])
 @pytest.mark.parametrize("B,N,padded", [(64, 29, True), (40, 21, False), (3, 200, False)])
 def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
     """More 128-pair tiles than SMs (persistent multi-tile pipeline, every ring/phase wrap) and rows
@@ -192,10 +194,44 @@ def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
         outs[eng] = (e, f, loss, run.flat_grads.clone(), {k: v.clone() for k, v in run.g.items()})
     e0, f0, l0, g0, gd0 = outs["fp32"]
     e1, f1, l1, g1, gd1 = outs[engine]
-    etol, ftol, gtol = (1e-5, 1e-4, 2e-3) if engine == "tf32x3" else (2e-2, 5e-2, 1e-1)
+    etol, ftol, gtol = (1e-5, 1e-4, 2e-3) if engine in ("tf32x3", "f16x2") else (2e-2, 5e-2, 1e-1)
     assert torch.isfinite(e1).all() and torch.isfinite(f1).all() and torch.isfinite(g1).all()
     assert ((e1 - e0).abs() / e0.abs().clamp_min(1e-3)).max().item() < etol
     assert (f1 - f0).abs().max().item() < ftol * max(1.0, f0.abs().max().item() if engine == "bf16" else 1.0)
     for k in gd0:
         scale = max(float(gd0[k].abs().max()), 1e-6)
         assert float((gd1[k] - gd0[k]).abs().max()) < gtol * scale + 1e-7, k
+
+
+@pytest.mark.parametrize("engine", ["tf32x3", "f16x2"])
+def test_small_gradient_scale_and_large_features(engine):
+    """Range robustness of the split-precision engines: edge features blown up to ~1e3 (the fp16-split
+    engine must take its exact power-of-two down-scaling path) and cotangents scaled by 1e-6 (up-scaling
+    path).  Saturated tanh makes this an ill-conditioned regime even for plain fp32 arithmetic, so the
+    yardstick is the generic fp32 CUDA-core engine: against the fp64 oracle a split engine may be at
+    most 4x worse than it (plus the stated 1e-5 / 1e-4 floors)."""
+    import sake_b200
+    B, N, S, depth = 8, 21, 6, 2
+    h, x, mask, am = synth.molecules(123, B, N, S, False, 0)
+    dev = "cuda"
+    T = lambda a: None if a is None else torch.tensor(a, device=dev)
+    errs = {}
+    for eng in ("fp32", engine):
+        model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=depth, engine=eng)
+        params = model.init(3, T(h), T(x))["params"]
+        params["d0"]["edge_model"]["mlp_out"]["layers_2"]["kernel"].mul_(3000.0)
+        po = _oracle_params(params)
+        e0, f0 = O.energy_and_forces(po, T(h).cpu().double(), T(x).cpu().double())
+        fmax = max(1.0, f0.abs().max().item())
+        for scale in (1.0, 1e-6):
+            xx = T(x).requires_grad_(True)
+            e = model.energy(params, T(h), xx)
+            (g,) = torch.autograd.grad((e * scale).sum(), xx)
+            assert torch.isfinite(g).all() and torch.isfinite(e).all()
+            erel = ((e.cpu().double() - e0).abs() / e0.abs().clamp_min(1e-3)).max().item()
+            ferr = (-g.cpu().double() / scale - f0).abs().max().item() / fmax
+            errs[(eng, scale)] = (erel, ferr)
+    for scale in (1.0, 1e-6):
+        (er0, fr0), (er1, fr1) = errs[("fp32", scale)], errs[(engine, scale)]
+        assert er1 < 4 * er0 + 1e-5, f"energy: {engine} {er1:.3e} vs fp32 engine {er0:.3e} (scale {scale})"
+        assert fr1 < 4 * fr0 + 1e-4, f"forces: {engine} {fr1:.3e} vs fp32 engine {fr0:.3e} (scale {scale})"
