@@ -212,6 +212,25 @@ __device__ __noinline__ void emit_ssum(float* o, float s0, float s1, float s2, b
   else { o[0] = s0; o[1] = s1; o[2] = s2; }
 }
 
+// 32 TMEM columns (= 32 pairs) of one coefficient: coef = tanh(z), s += dir*m*coef.  Straight-line code:
+// 32 independent MUFU chains, two partial sums per component.  dm.w = 1/scale of the pair's E row.
+template <class CF, bool MASKED>
+__device__ __forceinline__ void epi_fwd_chunk(const float (&v)[32], const float4* __restrict__ dmp, uint32_t mask,
+                                              float& s0, float& s1, float& s2) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float4 dm = dmp[k];
+    float z = v[k];
+    if constexpr (CF::F16) z *= dm.w;
+    float co = CF::TF32 || CF::F16 ? ftanh_(z) : ftanh_mufu_(z);
+    if constexpr (MASKED) co = ((mask >> k) & 1u) ? co : 0.f;
+    if (k & 1) { b0 = fmaf(dm.x, co, b0); b1 = fmaf(dm.y, co, b1); b2 = fmaf(dm.z, co, b2); }
+    else { a0 = fmaf(dm.x, co, a0); a1 = fmaf(dm.y, co, a1); a2 = fmaf(dm.z, co, a2); }
+  }
+  s0 += a0 + b0; s1 += a1 + b1; s2 += a2 + b2;
+}
+
 // =================================================================================================
 // forward:  D^T[c' (lane), pair (column)] = sum_c Wx[c][c'] * E[pair][c]
 //   A = weight image (M = 128 of the 256 c' per MMA, two halves), B = E image (N = 128 pairs)
@@ -330,7 +349,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);   // functional.py:14-17
         const float inv = 1.0f / (nrm + 1e-5f);                                      // layers.py:115
         const float m = mask ? mask[prx] : 1.0f;
-        dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, __int_as_float(seg_end ? row + 1 : 0));
+        dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, 1.0f);
       } else {
 #pragma unroll
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
@@ -348,8 +367,8 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         }
       }
       mbar_wait_warp(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
+      dm.w = inv_s;                                          // fp16-split engine: undoes the E row scale
       sm.dirm[buf * TILE + p] = dm;
-      if constexpr (CF::F16) sm.escale[buf * TILE + p] = inv_s;
 #pragma unroll
       for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
@@ -361,39 +380,38 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     }
   } else {
     // ------------------------------------------------------------ epilogue: tanh + sum over senders
+    // Thread = coefficient c'.  The tile's receiver rows are walked as segments of TMEM columns; every
+    // 32-column load is one branch-free block of 32 independent tanh chains (the segment boundaries are
+    // handled by a warp-uniform bit mask on a clamped, possibly overlapping load), and the row sums are
+    // written once per segment.
     const int q = warp & 3, mh = (warp - 6) >> 2;
     const int cp = mh * 128 + q * 32 + lane;
     const bool accumulate = g.nseg > 1;
     for (int it = 0; it < ntl; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       const int buf = it & 1, use = it >> 1;
+      int row0, nsegs, seglen;
+      if (g.nseg == 1) { row0 = tile * g.rpt; nsegs = min(g.rpt, g.R - row0); seglen = g.N; }
+      else { row0 = tile / g.nseg; const int seg = tile - row0 * g.nseg; nsegs = 1; seglen = min(g.js, g.N - seg * g.js); }
       mbar_wait_warp(sm.acc_full + buf, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + mh * 128;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      const float4* dmt = sm.dirm + buf * TILE;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        float v[32];
-        tmem_ld32(taddr + cc * 32, v);
-        tmem_ld_wait();
-        // phase 1: 32 independent tanh chains (full ILP; no control flow in between)
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float z = v[k];
-          if constexpr (CF::F16) z *= sm.escale[buf * TILE + cc * 32 + k];
-          v[k] = ftanh_(z);
+      for (int sg = 0; sg < nsegs; ++sg) {
+        const int c0 = sg * seglen, c1 = c0 + seglen;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c = c0; c < c1; c += 32) {
+          const int ls = min(c, TILE - 32);            // clamped load start: never reads past the tile's 128 columns
+          const int n = min(32, c1 - c);
+          float v[32];
+          tmem_ld32(taddr + ls, v);
+          tmem_ld_wait();
+          if (n == 32 && ls == c) epi_fwd_chunk<CF, false>(v, dmt + ls, 0u, s0, s1, s2);
+          else epi_fwd_chunk<CF, true>(v, dmt + ls, (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (c - ls), s0, s1, s2);
         }
-        // phase 2: weighted sum over senders; the (rare, warp-uniform) row flush is the only branch
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float4 dm = sm.dirm[buf * TILE + cc * 32 + k];
-          const float co = v[k];
-          s0 = fmaf(dm.x, co, s0); s1 = fmaf(dm.y, co, s1); s2 = fmaf(dm.z, co, s2);
-          const int flag = __float_as_int(dm.w);
-          if (flag != 0) {                      // once per receiver row: a real call, not 3 predicated STG per column
-            emit_ssum(ssum + ((size_t)(flag - 1) * CC + cp) * 3, s0, s1, s2, accumulate);
-            s0 = 0.f; s1 = 0.f; s2 = 0.f;
-          }
-        }
+        emit_ssum(ssum + ((size_t)(row0 + sg) * CC + cp) * 3, s0, s1, s2, accumulate);
       }
       tc_fence_before();
       mbar_arrive(sm.acc_empty + buf);
@@ -402,6 +420,23 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// backward epilogue 1 on 32 TMEM columns (= 32 coefficients c') of one pair: coef = tanh z,
+// dZ = (dir*m . T[c']) sech^2 z, g_dir += coef * T[c'].  Straight-line: the loads of T carry no predicate
+// (idle lanes read a valid row with dir = 0), so the 32 chains interleave freely.
+template <class CF>
+__device__ __forceinline__ void epi1_part(const float (&v)[32], const float4* __restrict__ Tp, float zs, float d0,
+                                          float d1, float d2, float& g0, float& g1, float& g2, float* dz) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float4 t4 = Tp[k];
+    float co, s2;
+    ftanh_sech2_(CF::F16 ? v[k] * zs : v[k], co, s2);
+    const float gco = fmaf(d2, t4.z, fmaf(d1, t4.y, d0 * t4.x));
+    g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
+    dz[k] = gco * s2;
+  }
 }
 
 // =================================================================================================
@@ -557,7 +592,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       tile_pair(g, tile, p, valid, row, j, seg_end);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, m = 0.f;
       size_t prx = 0;
-      const float4* Trow = T4;
+      int trow = 0;                                   // row of the T operand (any valid row for idle lanes: d = 0)
       if (valid) {
         prx = (size_t)row * g.N + j;
         const int b = row / g.N;
@@ -568,9 +603,10 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         const float inv = 1.0f / (nrm + 1e-5f);
         m = mask ? mask[prx] : 1.0f;
         d0 = r0 * inv * m; d1 = r1 * inv * m; d2 = r2 * inv * m;
-        Trow = T4 + (size_t)row * CC;
-        if (use_tsm) Trow = sm.Tsm + (size_t)(row - (g.nseg == 1 ? tile * g.rpt : row)) * CC;
+        trow = use_tsm ? row - (g.nseg == 1 ? tile * g.rpt : row) : row;
       }
+      const float4* Tg = T4 + (size_t)trow * CC;      // global copy of the row
+      const float4* Ts = sm.Tsm + trow * CC;          // TMA-staged copy (use_tsm)
       // ---------------- epilogue 1: dZ chunks for GEMM2 (this half owns ring slots of parity hh)
       if (use_tsm) mbar_wait(sm.t_full, it & 1);
       mbar_wait(d1_full, it & 1);
@@ -590,21 +626,11 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int part = 0; part < CF::KCH / 32; ++part) {
           float v[32];
-          tmem_ld32(lane_addr + kc2 * CF::KCH + part * 32, v);
+          const int cb = kc2 * CF::KCH + part * 32;
+          tmem_ld32(lane_addr + cb, v);
           tmem_ld_wait();
-          float s2v[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) ftanh_sech2_(CF::F16 ? v[k] * zs : v[k], v[k], s2v[k]);   // independent chains first
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const int cpi = kc2 * CF::KCH + part * 32 + k;
-            const float co = v[k];
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) t4 = use_tsm ? Trow[cpi] : __ldg(Trow + cpi);
-            const float gco = d0 * t4.x + d1 * t4.y + d2 * t4.z;
-            g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
-            dz[part * 32 + k] = gco * s2v[k];
-          }
+          if (use_tsm) epi1_part<CF>(v, Ts + cb, zs, d0, d1, d2, g0, g1, g2, dz + part * 32);
+          else epi1_part<CF>(v, Tg + cb, zs, d0, d1, d2, g0, g1, g2, dz + part * 32);
         }
         if (gZ_out != nullptr && valid) {
           float4* o = reinterpret_cast<float4*>(gZ_out + prx * CC + kc2 * CF::KCH);
