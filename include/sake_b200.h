@@ -210,6 +210,8 @@ int sake_selftest_xtg(int32_t engine, int64_t P, int32_t xw, int32_t gw, const f
  * variable SAKE_DEBUG_WSPLITS=7): [0] accumulator, [1] weight chunk, [2] pair chunk, [3] total, [4] tiles.
  * Reads and clears 8 counters (host memory). */
 int sake_debug_counters(unsigned long long* out8);
+/* Same switch, backward mix kernel: 16 counters (MMA issuer waits, epilogue phases, builder waits; see tc_mix.cu). */
+int sake_debug_counters_bwd(unsigned long long* out16);
 
 /* Number of CUDA kernels this library has launched in this process (diagnostic). */
 unsigned long long sake_launch_count(void);

@@ -73,6 +73,8 @@ lib.sake_selftest_xtg.argtypes = [_i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]
 lib.sake_selftest_xtg.restype = C.c_int
 lib.sake_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
 lib.sake_debug_counters.restype = C.c_int
+lib.sake_debug_counters_bwd.argtypes = [C.POINTER(C.c_ulonglong)]
+lib.sake_debug_counters_bwd.restype = C.c_int
 lib.sake_launch_count.restype = C.c_ulonglong
 lib.sake_selftest_tcgen05.argtypes = [C.POINTER(C.c_float), _vp]
 lib.sake_selftest_tcgen05.restype = C.c_int
@@ -80,7 +82,7 @@ lib.sake_selftest_tcgen05.restype = C.c_int
 EXPORTS = ("sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
            "sake_layer_scratch_bytes", "sake_layer_fwd", "sake_layer_bwd", "sake_dense_fwd",
            "sake_dense_bwd", "sake_selftest_tcgen05", "sake_energy_head", "sake_adam_step",
-           "sake_profile_begin", "sake_profile_collect", "sake_launch_count", "sake_selftest_xtg", "sake_debug_counters")
+           "sake_profile_begin", "sake_profile_collect", "sake_launch_count", "sake_selftest_xtg", "sake_debug_counters", "sake_debug_counters_bwd")
 
 
 class SakeError(RuntimeError):

@@ -22,6 +22,7 @@ int dense_bwd(long long rows, int in, int out, int act, const float* x, const fl
               const float* dy, float* dx, float* dw, float* db, cudaStream_t st);
 int tc_selftest(float* max_abs_err, cudaStream_t st);
 int tc_debug_counters(unsigned long long* out8);
+int tc_debug_counters_bwd(unsigned long long* out16);
 
 static int make_dims(const SakeDims* s, Dims* d) {
   if (!s) { set_error("dims is NULL"); return SAKE_EINVAL; }
@@ -246,6 +247,7 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
 }
 
 int sake_debug_counters(unsigned long long* out8) { return tc_debug_counters(out8); }
+int sake_debug_counters_bwd(unsigned long long* out16) { return tc_debug_counters_bwd(out16); }
 
 unsigned long long sake_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 

@@ -41,12 +41,15 @@ template <> struct Cfg<SAKE_ENGINE_F16X2> {
   static constexpr int KCH = 64, NSPLIT = 2, NPROD = 3, NCHUNK = 4, FMT = 0, NSTAGE = 2, EPU = 8;
 };
 constexpr int TSM_ROWS = 6;                       // receiver rows whose T = d(loss)/d(ssum) fits the staging buffer
-constexpr int AUX_BYTES = 2 * TILE * 16 /*gdS (fwd: dirm)*/ + 2 * TILE * 16 /*gaS*/ + TSM_ROWS * CC * 16 /*T rows*/ +
-                          2 * TILE * 4 /*escale*/;
+// auxiliary shared memory behind the stage ring.  There is no alignment slack: the dynamic window must
+// start 1024-byte aligned (it does: it follows the 1 KB the runtime reserves); the kernels trap otherwise.
+constexpr int AUX_BYTES = 2 * TILE * 16 /*fwd: dirm[2][TILE]; bwd: g_dir / g_att exchange*/ + TSM_ROWS * CC * 16 /*T rows*/ +
+                          TSM_ROWS * CC * 4 /*ghe rows*/ + TILE * 4 /*escale*/;
 template <class CF> __host__ __device__ constexpr int stage_bytes() { return CF::NSPLIT * (P_IMG + W_IMG); }
 template <class CF> __host__ __device__ constexpr size_t smem_bytes() {
-  return (size_t)CF::NSTAGE * stage_bytes<CF>() + AUX_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  return (size_t)CF::NSTAGE * stage_bytes<CF>() + AUX_BYTES + 256 /*barriers*/;
 }
+static_assert(2 * 2 * (P_IMG + W_IMG) + AUX_BYTES + 256 <= 232448, "shared-memory budget (227 KB per CTA)");
 // products (pair-side split, weight-side split), small terms last
 __device__ __constant__ int c_prod_p[3] = {0, 1, 0};
 __device__ __constant__ int c_prod_w[3] = {0, 0, 1};
@@ -175,29 +178,34 @@ __device__ __forceinline__ float row_scale_unit(float bound) {
 template <class CF>
 struct Smem {
   uint8_t* stages;
-  float4* dirm;   // [2][TILE]  (dir*m xyz, segment-end flag)            forward (aliases gdS)
-  float4* gdS;    // [2][TILE]  partial g_dir of the two column halves     backward
-  float4* gaS;    // [2][TILE]  partial g_att of the two column halves     backward
+  float4* dirm;   // [2][TILE]  (dir*m xyz, 1/scale of the E row)           forward
+  float4* gdX;    // [TILE]  g_dir partial of column half 1 -> half 0        backward (aliases dirm)
+  float4* gaX;    // [TILE]  g_att partial of column half 1 -> half 0        backward
   float4* Tsm;    // [TSM_ROWS][CC] cotangent rows of the tile's receivers   backward (TMA-staged)
-  float* escale;  // [2][TILE] 1/scale of the E rows (fp16-split engine)
-  uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty, *t_full, *t_empty;
+  float* ghS;     // [TSM_ROWS][CC] cotangent of the aggregate h_e           backward (TMA-staged)
+  float* escale;  // [TILE] 1/scale of the E rows (fp16-split engine)        backward
+  uint64_t *full_w, *full_e, *empty, *acc_full, *acc_empty, *t_full, *t_empty, *g_full, *g_empty;
   uint32_t* tmem_ptr;
   __device__ Smem(uint8_t* raw) {
     uint8_t* b = align1024_shared(raw);
+    if (b != raw) __trap();                            // no slack is budgeted (see AUX_BYTES)
     stages = b;
     dirm = reinterpret_cast<float4*>(b + (size_t)CF::NSTAGE * stage_bytes<CF>());
-    gdS = dirm;
-    gaS = gdS + 2 * TILE;
-    Tsm = gaS + 2 * TILE;
-    escale = reinterpret_cast<float*>(Tsm + TSM_ROWS * CC);
-    full_w = reinterpret_cast<uint64_t*>(escale + 2 * TILE);
+    gdX = dirm;
+    gaX = gdX + TILE;
+    Tsm = dirm + 2 * TILE;
+    ghS = reinterpret_cast<float*>(Tsm + TSM_ROWS * CC);
+    escale = ghS + TSM_ROWS * CC;
+    full_w = reinterpret_cast<uint64_t*>(escale + TILE);
     full_e = full_w + CF::NSTAGE;
     empty = full_e + CF::NSTAGE;
     acc_full = empty + CF::NSTAGE;      // [2]
     acc_empty = acc_full + 2;           // [2]
     t_full = acc_empty + 2;
     t_empty = t_full + 1;
-    tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 1);
+    g_full = t_empty + 1;
+    g_empty = g_full + 1;
+    tmem_ptr = reinterpret_cast<uint32_t*>(g_empty + 1);
   }
   __device__ uint8_t* p_img(int s) const { return stages + (size_t)s * stage_bytes<CF>(); }
   __device__ uint8_t* w_img(int s) const { return stages + (size_t)s * stage_bytes<CF>() + CF::NSPLIT * P_IMG; }
@@ -206,6 +214,10 @@ struct Smem {
 // optional wait-time accounting of the MMA issuer (SAKE_DEBUG_WSPLITS=7): cycles spent waiting for
 // [0] accumulator free, [1] weight chunk (TMA), [2] pair-side chunk (builders / epilogue), [3] total loop
 __device__ unsigned long long g_mma_wait[8];
+// backward kernel (same switch): MMA issuer [0] d2_empty [1] G1 weights [2] G1 pair chunks [3] G2 weights [4] G2 dZ chunks
+// [5] total [6] tiles; epilogue warp 6 lane 0: [7] d1_full wait [8] ring-slot wait [9] bar1 [10] d2_full wait [11] E1 total
+// [12] E2 total; builder warp 2 lane 0: [13] ring waits [14] load+build
+__device__ unsigned long long g_bwd_wait[16];
 
 __device__ __noinline__ void emit_ssum(float* o, float s0, float s1, float s2, bool accumulate) {
   if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
@@ -426,16 +438,39 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 // dZ = (dir*m . T[c']) sech^2 z, g_dir += coef * T[c'].  Straight-line: the loads of T carry no predicate
 // (idle lanes read a valid row with dir = 0), so the 32 chains interleave freely.
 template <class CF>
-__device__ __forceinline__ void epi1_part(const float (&v)[32], const float4* __restrict__ Tp, float zs, float d0,
-                                          float d1, float d2, float& g0, float& g1, float& g2, float* dz) {
+__device__ __forceinline__ void epi1_part(const float (&v)[32], const float4* __restrict__ Tp, float zs, float d0q,
+                                          float d1q, float d2q, float& g0, float& g1, float& g2, float* dz) {
+  // d?q = 4 * dir * m: the derivative is computed as sech^2 z / 4 = r - r^2 with r = 1/(e^{2|z|}+1), which has no
+  // cancellation in saturated coefficients and needs no clamp (e^{2|z|} = inf -> r = 0 -> coef = +-1, dZ = 0)
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const float4 t4 = Tp[k];
-    float co, s2;
-    ftanh_sech2_(CF::F16 ? v[k] * zs : v[k], co, s2);
-    const float gco = fmaf(d2, t4.z, fmaf(d1, t4.y, d0 * t4.x));
+    const float z = CF::F16 ? v[k] * zs : v[k];
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    const float co = copysignf(fmaf(-2.0f, r, 1.0f), z);
+    const float s2q = fmaf(-r, r, r);
+    const float gco = fmaf(d2q, t4.z, fmaf(d1q, t4.y, d0q * t4.x));
     g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
-    dz[k] = gco * s2;
+    dz[k] = gco * s2q;
+  }
+}
+
+// backward epilogue 2 on 32 TMEM columns (= 8 features f x 4 heads) of one pair:
+// dE += m*ghe;  g_e[f] = sum_a dE att[a];  g_att[a] += sum_f dE e[f]
+__device__ __forceinline__ void epi2_part(const float (&v)[32], const float4* __restrict__ gh4, const float4& ea,
+                                          const float4& eb, const float4& at, float m, float idz, float* gev,
+                                          float& ga0, float& ga1, float& ga2, float& ga3) {
+  const float ef[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+  for (int k8 = 0; k8 < 8; ++k8) {
+    const float4 gh = gh4[k8];
+    const float x0 = fmaf(m, gh.x, v[4 * k8] * idz), x1 = fmaf(m, gh.y, v[4 * k8 + 1] * idz),
+                x2 = fmaf(m, gh.z, v[4 * k8 + 2] * idz), x3 = fmaf(m, gh.w, v[4 * k8 + 3] * idz);
+    gev[k8] = x0 * at.x + x1 * at.y + x2 * at.z + x3 * at.w;
+    ga0 = fmaf(x0, ef[k8], ga0); ga1 = fmaf(x1, ef[k8], ga1);
+    ga2 = fmaf(x2, ef[k8], ga2); ga3 = fmaf(x3, ef[k8], ga3);
   }
 }
 
@@ -451,7 +486,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
              const float* __restrict__ att, const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
              const float4* __restrict__ T4, const float* __restrict__ tmax, const float* __restrict__ ghe,
-             float* __restrict__ ge, float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out) {
+             float* __restrict__ ge, float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out, int dbg) {
   using CF = Cfg<ENGINE>;
   constexpr int NCH = CF::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
@@ -463,7 +498,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 128); mbar_init(sm.empty + s, 1); }
     mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d2_empty, 256); mbar_init(sm.acc_empty + 1, 1);
-    mbar_init(sm.t_full, 1); mbar_init(sm.t_empty, 256);
+    mbar_init(sm.t_full, 1); mbar_init(sm.t_empty, 256); mbar_init(sm.g_full, 1); mbar_init(sm.g_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(sm.tmem_ptr);
@@ -487,6 +522,16 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           bulk_g2s(sm.Tsm, T4 + (size_t)row0 * CC, (uint32_t)nrows * CC * 16, sm.t_full);
         }
         for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
+          if (c2 == NCH && use_tsm) {
+            // ghe rows for epilogue 2: requested only now, so that waiting for epilogue 2 of the previous tile
+            // (g_empty) cannot hold back the GEMM1 weight stream; GEMM2 needs that epilogue finished anyway
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int row0 = g.nseg == 1 ? tile * g.rpt : tile / g.nseg;
+            const int nrows = min(g.rpt, g.R - row0);
+            mbar_wait(sm.g_empty, (it & 1) ^ 1);
+            mbar_arrive_expect_tx(sm.g_full, (uint32_t)nrows * CC * 4);
+            bulk_g2s(sm.ghS, ghe + (size_t)row0 * CC, (uint32_t)nrows * CC * 4, sm.g_full);
+          }
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           const uint8_t* src = (c2 < NCH ? w1img + (size_t)c2 * CF::NSPLIT * W_IMG
                                          : w2img + (size_t)(c2 - NCH) * CF::NSPLIT * W_IMG);
@@ -501,15 +546,22 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(CF::FMT, TILE, CC);
       int pos = 0;
+      long long w[5] = {0, 0, 0, 0, 0};
+      const long long t_begin = clock64();
       for (int it = 0; it < ntl; ++it) {
         for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+          long long t0 = clock64();
           if (c2 == NCH) {                              // before GEMM2 overwrites D2: previous tile drained
             mbar_wait(d2_empty, (it & 1) ^ 1);
             tc_fence_after();
           }
+          long long t1 = clock64();
           mbar_wait(sm.full_w + s, n & 1);
+          long long t2 = clock64();
           mbar_wait(sm.full_e + s, n & 1);
+          long long t3 = clock64();
+          w[0] += t1 - t0; w[c2 < NCH ? 1 : 3] += t2 - t1; w[c2 < NCH ? 2 : 4] += t3 - t2;
           tc_fence_after();
           const uint32_t wbase = smem_u32(sm.w_img(s)), pbase = smem_u32(sm.p_img(s));
           const uint32_t d = tmem_base + (c2 < NCH ? 0 : 256);
@@ -528,10 +580,17 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           if (c2 == 2 * NCH - 1) umma_commit(d2_full);
         }
       }
+      if (dbg == 7) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&g_bwd_wait[i], (unsigned long long)w[i]);
+        atomicAdd(&g_bwd_wait[5], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&g_bwd_wait[6], (unsigned long long)ntl);
+      }
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------ builders: E image for GEMM1
     const int p = (warp - 2) * 32 + lane;
+    long long bw_ring = 0;
+    const long long bw_begin = clock64();
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       bool valid, seg_end;
@@ -561,13 +620,15 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
           for (int q = 0; q < 64; ++q) ev[q] *= sc;
         }
-        sm.escale[(it & 1) * TILE + p] = 1.0f / sc;   // rewritten two tiles later, after epilogue 1 of tile it+1
+        sm.escale[p] = 1.0f / sc;   // single buffer: the builders only get here after epilogue 1 of the previous tile started
       }
       int pos = it * 2 * NCH;
 #pragma unroll
       for (int kc = 0; kc < NCH; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
+        const long long t0 = dbg == 7 ? clock64() : 0;
         mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        if (dbg == 7) bw_ring += clock64() - t0;
         build_E_chunk<CF>(sm.p_img(s), p, kc, ev, at);
         fence_proxy_async();
         mbar_arrive(sm.full_e + s);
@@ -575,16 +636,23 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       // The GEMM2 ring slots of this tile are filled by the epilogue warps.  A parity wait can only tell
       // adjacent phases apart, so walk through those slots too (no work) to stay phase-synchronised with
       // the `empty` barriers before building the next tile's chunks.
+      const long long t1 = dbg == 7 ? clock64() : 0;
       for (int kc = 0; kc < NCH; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
         mbar_wait(sm.empty + s, (n & 1) ^ 1);
       }
+      if (dbg == 7) bw_ring += clock64() - t1;
+    }
+    if (dbg == 7 && threadIdx.x == 64) {
+      atomicAdd(&g_bwd_wait[13], (unsigned long long)bw_ring);
+      atomicAdd(&g_bwd_wait[14], (unsigned long long)(clock64() - bw_begin - bw_ring));
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (thread = pair)
     const int q = warp & 3, hh = (warp - 6) >> 2;
     const int p = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    long long ew[6] = {0, 0, 0, 0, 0, 0};
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       bool valid, seg_end;
@@ -608,12 +676,15 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       const float4* Tg = T4 + (size_t)trow * CC;      // global copy of the row
       const float4* Ts = sm.Tsm + trow * CC;          // TMA-staged copy (use_tsm)
       // ---------------- epilogue 1: dZ chunks for GEMM2 (this half owns ring slots of parity hh)
+      const long long e_t0 = dbg == 7 ? clock64() : 0;
       if (use_tsm) mbar_wait(sm.t_full, it & 1);
       mbar_wait(d1_full, it & 1);
       tc_fence_after();
+      const long long e_t1 = dbg == 7 ? clock64() : 0;
+      ew[0] += e_t1 - e_t0;
       float zs = 1.0f, dzs = 1.0f;                  // fp16-split engine: 1/scale of the E row, scale of the dZ row
       if constexpr (CF::F16) {
-        zs = sm.escale[(it & 1) * TILE + p];
+        zs = sm.escale[p];
         if (valid) dzs = row_scale_unit(2.0f * tmax[row]);      // |dZ| <= |dir|_1 * max|T| < 2 max|T|
       }
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -629,15 +700,17 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           const int cb = kc2 * CF::KCH + part * 32;
           tmem_ld32(lane_addr + cb, v);
           tmem_ld_wait();
-          if (use_tsm) epi1_part<CF>(v, Ts + cb, zs, d0, d1, d2, g0, g1, g2, dz + part * 32);
-          else epi1_part<CF>(v, Tg + cb, zs, d0, d1, d2, g0, g1, g2, dz + part * 32);
+          if (use_tsm) epi1_part<CF>(v, Ts + cb, zs, 4.0f * d0, 4.0f * d1, 4.0f * d2, g0, g1, g2, dz + part * 32);
+          else epi1_part<CF>(v, Tg + cb, zs, 4.0f * d0, 4.0f * d1, 4.0f * d2, g0, g1, g2, dz + part * 32);
         }
         if (gZ_out != nullptr && valid) {
           float4* o = reinterpret_cast<float4*>(gZ_out + prx * CC + kc2 * CF::KCH);
 #pragma unroll
           for (int k = 0; k < CF::KCH / 4; ++k) o[k] = make_float4(dz[4 * k], dz[4 * k + 1], dz[4 * k + 2], dz[4 * k + 3]);
         }
+        const long long e_s0 = dbg == 7 ? clock64() : 0;
         mbar_wait(sm.empty + s, (n & 1) ^ 1);
+        if (dbg == 7) ew[1] += clock64() - e_s0;
         if constexpr (CF::F16) {
 #pragma unroll
           for (int k = 0; k < CF::KCH; ++k) dz[k] *= dzs;
@@ -649,54 +722,67 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         mbar_arrive(sm.full_e + s);
       }
       if (use_tsm) mbar_arrive(sm.t_empty);          // T rows of this tile are consumed
-      sm.gdS[hh * TILE + p] = make_float4(g0, g1, g2, 0.f);
+      // operands of epilogue 2 that do not depend on GEMM2: fetched now, their latency hides behind the hand-off
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 ef4[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ef4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        at = *reinterpret_cast<const float4*>(att + prx * 4);
+        const float4* e4 = reinterpret_cast<const float4*>(e + prx * 64 + hh * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ef4[k] = __ldg(e4 + k);
+      }
+      if (hh == 1) sm.gdX[p] = make_float4(g0, g1, g2, 0.f);
+      const long long e_t2 = dbg == 7 ? clock64() : 0;
+      ew[4] += e_t2 - e_t1;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (dbg == 7) ew[2] += clock64() - e_t2;
       if (hh == 0 && valid) {
-        const float4 a = sm.gdS[p], bq = sm.gdS[TILE + p];
+        const float4 bq = sm.gdX[p];
         float* o = gdir + prx * 3;
-        o[0] = (a.x + bq.x) * m; o[1] = (a.y + bq.y) * m; o[2] = (a.z + bq.z) * m;
+        o[0] = (g0 + bq.x) * m; o[1] = (g1 + bq.y) * m; o[2] = (g2 + bq.z) * m;
       }
       // ---------------- epilogue 2: dE -> g_e, g_att   (this half owns f in [32 hh, 32 hh + 32))
+      const long long e_t3 = dbg == 7 ? clock64() : 0;
+      if (use_tsm) mbar_wait(sm.g_full, it & 1);
       mbar_wait(d2_full, it & 1);
       tc_fence_after();
-      float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) at = *reinterpret_cast<const float4*>(att + prx * 4);
+      const long long e_t4 = dbg == 7 ? clock64() : 0;
+      ew[3] += e_t4 - e_t3;
       float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, ga3 = 0.f;
       const float idz = CF::F16 ? 1.0f / dzs : 1.0f;
-#pragma unroll 1
+      const float4* ghs4 = reinterpret_cast<const float4*>(sm.ghS + trow * CC) + hh * 32;      // staged row (use_tsm)
+      const float4* ghg4 = reinterpret_cast<const float4*>(ghe + (size_t)trow * CC) + hh * 32;  // global row
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         float v[32];
         tmem_ld32(lane_addr + 256 + hh * 128 + cc * 32, v);
         tmem_ld_wait();
+        float gev[8];
+        if (use_tsm) epi2_part(v, ghs4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
+        else epi2_part(v, ghg4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
         if (valid) {
-          const int f0 = hh * 32 + cc * 8;
-          const float4* gh4 = reinterpret_cast<const float4*>(ghe + (size_t)row * CC) + f0;
-          const float4* e4 = reinterpret_cast<const float4*>(e + prx * 64 + f0);
-          const float4 ea = __ldg(e4), eb = __ldg(e4 + 1);
-          const float ef[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
-          float gev[8];
-#pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const float4 gh = __ldg(gh4 + k8);
-            const float x0 = fmaf(m, gh.x, v[4 * k8] * idz), x1 = fmaf(m, gh.y, v[4 * k8 + 1] * idz),
-                        x2 = fmaf(m, gh.z, v[4 * k8 + 2] * idz), x3 = fmaf(m, gh.w, v[4 * k8 + 3] * idz);
-            gev[k8] = x0 * at.x + x1 * at.y + x2 * at.z + x3 * at.w;
-            ga0 = fmaf(x0, ef[k8], ga0); ga1 = fmaf(x1, ef[k8], ga1);
-            ga2 = fmaf(x2, ef[k8], ga2); ga3 = fmaf(x3, ef[k8], ga3);
-          }
-          float4* o = reinterpret_cast<float4*>(ge + prx * 64 + f0);
+          float4* o = reinterpret_cast<float4*>(ge + prx * 64 + hh * 32 + cc * 8);
           o[0] = make_float4(gev[0], gev[1], gev[2], gev[3]);
           o[1] = make_float4(gev[4], gev[5], gev[6], gev[7]);
         }
       }
       tc_fence_before();
       mbar_arrive(d2_empty);
-      sm.gaS[hh * TILE + p] = make_float4(ga0, ga1, ga2, ga3);
+      if (use_tsm) mbar_arrive(sm.g_empty);          // ghe rows of this tile are consumed
+      if (hh == 1) sm.gaX[p] = make_float4(ga0, ga1, ga2, ga3);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (hh == 0 && valid) {
-        const float4 a = sm.gaS[p], bq = sm.gaS[TILE + p];
-        *reinterpret_cast<float4*>(gatt + prx * 4) = make_float4(a.x + bq.x, a.y + bq.y, a.z + bq.z, a.w + bq.w);
+        const float4 bq = sm.gaX[p];
+        *reinterpret_cast<float4*>(gatt + prx * 4) = make_float4(ga0 + bq.x, ga1 + bq.y, ga2 + bq.z, ga3 + bq.w);
       }
+      if (dbg == 7) ew[5] += clock64() - e_t4;
+    }
+    if (dbg == 7 && threadIdx.x == 192) {
+      atomicAdd(&g_bwd_wait[7], (unsigned long long)ew[0]); atomicAdd(&g_bwd_wait[8], (unsigned long long)ew[1]);
+      atomicAdd(&g_bwd_wait[9], (unsigned long long)ew[2]); atomicAdd(&g_bwd_wait[10], (unsigned long long)ew[3]);
+      atomicAdd(&g_bwd_wait[11], (unsigned long long)ew[4]); atomicAdd(&g_bwd_wait[12], (unsigned long long)ew[5]);
     }
   }
   tc_fence_before();
@@ -798,6 +884,13 @@ int tc_debug_counters(unsigned long long* out8) {
   SAKE_CUDA_CHECK(cudaMemcpyToSymbol(g_mma_wait, z, sizeof(z)));
   return 0;
 }
+int tc_debug_counters_bwd(unsigned long long* out16) {
+  SAKE_CUDA_CHECK(cudaMemcpyFromSymbol(out16, g_bwd_wait, sizeof(unsigned long long) * 16));
+  unsigned long long z[16];
+  memset(z, 0, sizeof(z));
+  SAKE_CUDA_CHECK(cudaMemcpyToSymbol(g_bwd_wait, z, sizeof(z)));
+  return 0;
+}
 
 template <class CF> static size_t wimg_bytes() { return (size_t)CF::NCHUNK * CF::NSPLIT * W_IMG; }
 
@@ -867,9 +960,11 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
   {
     ProfScope prof(2, d.P, st);
+    static int dbg = -1;
+    if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
     k_tc_mix_bwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
                                                                   reinterpret_cast<const float4*>(sc.T), sc.tmax, sc.ghe,
-                                                                  sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr);
+                                                                  sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr, dbg);
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
