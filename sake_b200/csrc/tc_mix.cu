@@ -22,7 +22,8 @@ using namespace tc;
 constexpr int CC = 256;              // C = A*H (the engine is specialised to H=64, A=4)
 constexpr int P_IMG = TILE * 128;    // bytes of one pair-side chunk image   (128 rows x 128 B)
 constexpr int W_IMG = CC * 128;      // bytes of one weight-side chunk image (256 rows x 128 B)
-constexpr int NTHREADS = 448;        // 14 warps: 0 TMA producer, 1 MMA issuer, 2-5 builders, 6-13 epilogue
+constexpr int NTHREADS = 448;        // forward: 14 warps: 0 TMA producer, 1 MMA issuer, 2-5 builders, 6-13 epilogue
+constexpr int BWD_THREADS = 512;     // backward: 4 warpgroups: {TMA, MMA, 2 idle}, builders, 2 x epilogue (setmaxnreg needs whole groups)
 
 template <int ENGINE> struct Cfg;
 template <> struct Cfg<SAKE_ENGINE_TF32X3> {
@@ -436,24 +437,41 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 
 // backward epilogue 1 on 32 TMEM columns (= 32 coefficients c') of one pair: coef = tanh z,
 // dZ = (dir*m . T[c']) sech^2 z, g_dir += coef * T[c'].  Straight-line: the loads of T carry no predicate
-// (idle lanes read a valid row with dir = 0), so the 32 chains interleave freely.
+// (idle lanes read a valid row with dir = 0), so the 32 chains interleave freely.  dZ goes straight into
+// the GEMM2 operand image, EPU values at a time (unit0 = first 16-byte unit of this block in the row).
+//   q? = 4 * dzs * dir * m: the derivative is computed as sech^2 z / 4 = r - r^2 with r = 1/(e^{2|z|}+1),
+//   which has no cancellation in saturated coefficients and needs no clamp (e^{2|z|} = inf -> r = 0 ->
+//   coef = +-1, dZ = 0); dzs is the fp16-split engine's power-of-two row scale (1 otherwise), undone
+//   (idz) for the fp32 copy of dZ that the weight-gradient contraction reads.
 template <class CF>
-__device__ __forceinline__ void epi1_part(const float (&v)[32], const float4* __restrict__ Tp, float zs, float d0q,
-                                          float d1q, float d2q, float& g0, float& g1, float& g2, float* dz) {
-  // d?q = 4 * dir * m: the derivative is computed as sech^2 z / 4 = r - r^2 with r = 1/(e^{2|z|}+1), which has no
-  // cancellation in saturated coefficients and needs no clamp (e^{2|z|} = inf -> r = 0 -> coef = +-1, dZ = 0)
+__device__ __forceinline__ void epi1_block(const float (&v)[32], const float4* __restrict__ Tp, float zs, float q0,
+                                           float q1, float q2, float& g0, float& g1, float& g2, uint8_t* img, int p,
+                                           int unit0, float* __restrict__ gz, float idz) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float4 t4 = Tp[k];
-    const float z = CF::F16 ? v[k] * zs : v[k];
-    float t, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.885390081777927f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
-    const float co = copysignf(fmaf(-2.0f, r, 1.0f), z);
-    const float s2q = fmaf(-r, r, r);
-    const float gco = fmaf(d2q, t4.z, fmaf(d1q, t4.y, d0q * t4.x));
-    g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
-    dz[k] = gco * s2q;
+  for (int u = 0; u < 32 / CF::EPU; ++u) {
+    float dz[CF::EPU];
+#pragma unroll
+    for (int i = 0; i < CF::EPU; ++i) {
+      const int k = u * CF::EPU + i;
+      const float4 t4 = Tp[k];
+      const float z = CF::F16 ? v[k] * zs : v[k];
+      float t, r;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.885390081777927f));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+      const float co = copysignf(fmaf(-2.0f, r, 1.0f), z);
+      const float s2q = fmaf(-r, r, r);
+      const float gco = fmaf(q2, t4.z, fmaf(q1, t4.y, q0 * t4.x));
+      g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
+      dz[i] = gco * s2q;
+    }
+    if (gz != nullptr) {
+#pragma unroll
+      for (int i = 0; i < CF::EPU; i += 4)
+        *reinterpret_cast<float4*>(gz + u * CF::EPU + i) =
+            CF::F16 ? make_float4(dz[i] * idz, dz[i + 1] * idz, dz[i + 2] * idz, dz[i + 3] * idz)
+                    : make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
+    }
+    store_unit<CF>(img, p, unit0 + u, dz);
   }
 }
 
@@ -482,7 +500,7 @@ __device__ __forceinline__ void epi2_part(const float (&v)[32], const float4* __
 //   every epilogue thread owns one pair (TMEM lane), so all reductions over c / c' are thread-local.
 // =================================================================================================
 template <int ENGINE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
              const float* __restrict__ att, const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
              const float4* __restrict__ T4, const float* __restrict__ tmax, const float* __restrict__ ghe,
@@ -509,7 +527,12 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   const bool use_tsm = g.rpt <= TSM_ROWS;          // T rows of the tile are staged in smem by TMA
-  if (warp == 0) {
+  // register re-balancing between the warpgroups (the kernel starts with 128 per thread): the TMA / MMA
+  // group keeps 40, the epilogue groups grow to 168 so that a 32-column block keeps all its chains in flight
+  // (each setmaxnreg sits inside its role's branch: ptxas budgets registers per branch only then)
+  if (warp < 4) {
+   setmaxnreg_dec<40>();
+   if (warp == 0) {
     if (lane == 0) {
       int pos = 0;
       for (int it = 0; it < ntl; ++it) {
@@ -542,7 +565,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(CF::FMT, TILE, CC);
       int pos = 0;
@@ -586,9 +609,10 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         atomicAdd(&g_bwd_wait[6], (unsigned long long)ntl);
       }
     }
-  } else if (warp < 6) {
+   }   // warps 2, 3: idle, they only lend their registers
+  } else if (warp < 8) {
     // ------------------------------------------------------------ builders: E image for GEMM1
-    const int p = (warp - 2) * 32 + lane;
+    const int p = (warp - 4) * 32 + lane;
     long long bw_ring = 0;
     const long long bw_begin = clock64();
     for (int it = 0; it < ntl; ++it) {
@@ -643,15 +667,19 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       }
       if (dbg == 7) bw_ring += clock64() - t1;
     }
-    if (dbg == 7 && threadIdx.x == 64) {
+    if (dbg == 7 && threadIdx.x == 128) {
       atomicAdd(&g_bwd_wait[13], (unsigned long long)bw_ring);
       atomicAdd(&g_bwd_wait[14], (unsigned long long)(clock64() - bw_begin - bw_ring));
     }
   } else {
+    setmaxnreg_inc<168>();
     // ------------------------------------------------------------ epilogue warps (thread = pair)
-    const int q = warp & 3, hh = (warp - 6) >> 2;
+    // Every thread walks 4 blocks of 32 TMEM columns in each epilogue; the load of the next block is in
+    // flight while the current one is processed (two register buffers).
+    const int q = warp & 3, hh = (warp - 8) >> 2;
     const int p = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int PPC = CF::KCH / 32;                   // 32-column blocks per ring chunk (1: tf32, 2: 16-bit formats)
     long long ew[6] = {0, 0, 0, 0, 0, 0};
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -687,39 +715,42 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         zs = sm.escale[p];
         if (valid) dzs = row_scale_unit(2.0f * tmax[row]);      // |dZ| <= |dir|_1 * max|T| < 2 max|T|
       }
+      const float idz = 1.0f / dzs;
+      const float q0 = 4.0f * dzs * d0, q1 = 4.0f * dzs * d1, q2 = 4.0f * dzs * d2;    // see epi1_block
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-#pragma unroll 1
-      for (int qq = 0; qq < NCH / 2; ++qq) {
-        const int kc2 = hh * (NCH / 2) + qq;
-        const int pos = it * 2 * NCH + NCH + 2 * qq + hh;
+      float* gzrow = (gZ_out != nullptr && valid) ? gZ_out + prx * CC : nullptr;
+      // block jb (0..3) of this thread: ring chunk kc2, first column cb, ring position pos
+      auto blk_col = [&](int jb) { return (hh * (NCH / 2) + jb / PPC) * CF::KCH + (jb % PPC) * 32; };
+      auto run_block1 = [&](int jb, const float (&v)[32]) {
+        const int cb = blk_col(jb);
+        const int pos = it * 2 * NCH + NCH + 2 * (jb / PPC) + hh;
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
-        float dz[CF::KCH];
-#pragma unroll
-        for (int part = 0; part < CF::KCH / 32; ++part) {
-          float v[32];
-          const int cb = kc2 * CF::KCH + part * 32;
-          tmem_ld32(lane_addr + cb, v);
-          tmem_ld_wait();
-          if (use_tsm) epi1_part<CF>(v, Ts + cb, zs, 4.0f * d0, 4.0f * d1, 4.0f * d2, g0, g1, g2, dz + part * 32);
-          else epi1_part<CF>(v, Tg + cb, zs, 4.0f * d0, 4.0f * d1, 4.0f * d2, g0, g1, g2, dz + part * 32);
+        if (jb % PPC == 0) {
+          const long long e_s0 = dbg == 7 ? clock64() : 0;
+          mbar_wait(sm.empty + s, (n & 1) ^ 1);
+          if (dbg == 7) ew[1] += clock64() - e_s0;
         }
-        if (gZ_out != nullptr && valid) {
-          float4* o = reinterpret_cast<float4*>(gZ_out + prx * CC + kc2 * CF::KCH);
-#pragma unroll
-          for (int k = 0; k < CF::KCH / 4; ++k) o[k] = make_float4(dz[4 * k], dz[4 * k + 1], dz[4 * k + 2], dz[4 * k + 3]);
+        float* gz = gzrow ? gzrow + cb : nullptr;
+        if (use_tsm) epi1_block<CF>(v, Ts + cb, zs, q0, q1, q2, g0, g1, g2, sm.p_img(s), p, (jb % PPC) * (32 / CF::EPU), gz, idz);
+        else epi1_block<CF>(v, Tg + cb, zs, q0, q1, q2, g0, g1, g2, sm.p_img(s), p, (jb % PPC) * (32 / CF::EPU), gz, idz);
+        if (jb % PPC == PPC - 1) {
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(sm.full_e + s);
         }
-        const long long e_s0 = dbg == 7 ? clock64() : 0;
-        mbar_wait(sm.empty + s, (n & 1) ^ 1);
-        if (dbg == 7) ew[1] += clock64() - e_s0;
-        if constexpr (CF::F16) {
+      };
+      {
+        float va[32], vb[32];
+        tmem_ld32(lane_addr + blk_col(0), va);
 #pragma unroll
-          for (int k = 0; k < CF::KCH; ++k) dz[k] *= dzs;
+        for (int jj = 0; jj < 2; ++jj) {
+          tmem_ld_wait_dep(va);
+          tmem_ld32(lane_addr + blk_col(2 * jj + 1), vb);
+          run_block1(2 * jj, va);
+          tmem_ld_wait_dep(vb);
+          if (jj == 0) tmem_ld32(lane_addr + blk_col(2), va);
+          run_block1(2 * jj + 1, vb);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) store_unit<CF>(sm.p_img(s), p, u, dz + u * CF::EPU);
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(sm.full_e + s);
       }
       if (use_tsm) mbar_arrive(sm.t_empty);          // T rows of this tile are consumed
       // operands of epilogue 2 that do not depend on GEMM2: fetched now, their latency hides behind the hand-off
@@ -733,32 +764,18 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) ef4[k] = __ldg(e4 + k);
       }
-      if (hh == 1) sm.gdX[p] = make_float4(g0, g1, g2, 0.f);
-      const long long e_t2 = dbg == 7 ? clock64() : 0;
-      ew[4] += e_t2 - e_t1;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (dbg == 7) ew[2] += clock64() - e_t2;
-      if (hh == 0 && valid) {
-        const float4 bq = sm.gdX[p];
-        float* o = gdir + prx * 3;
-        o[0] = (g0 + bq.x) * m; o[1] = (g1 + bq.y) * m; o[2] = (g2 + bq.z) * m;
-      }
       // ---------------- epilogue 2: dE -> g_e, g_att   (this half owns f in [32 hh, 32 hh + 32))
       const long long e_t3 = dbg == 7 ? clock64() : 0;
+      ew[4] += e_t3 - e_t1;
       if (use_tsm) mbar_wait(sm.g_full, it & 1);
       mbar_wait(d2_full, it & 1);
       tc_fence_after();
       const long long e_t4 = dbg == 7 ? clock64() : 0;
       ew[3] += e_t4 - e_t3;
       float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, ga3 = 0.f;
-      const float idz = CF::F16 ? 1.0f / dzs : 1.0f;
       const float4* ghs4 = reinterpret_cast<const float4*>(sm.ghS + trow * CC) + hh * 32;      // staged row (use_tsm)
       const float4* ghg4 = reinterpret_cast<const float4*>(ghe + (size_t)trow * CC) + hh * 32;  // global row
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float v[32];
-        tmem_ld32(lane_addr + 256 + hh * 128 + cc * 32, v);
-        tmem_ld_wait();
+      auto run_block2 = [&](int cc, const float (&v)[32]) {
         float gev[8];
         if (use_tsm) epi2_part(v, ghs4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
         else epi2_part(v, ghg4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
@@ -767,19 +784,38 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           o[0] = make_float4(gev[0], gev[1], gev[2], gev[3]);
           o[1] = make_float4(gev[4], gev[5], gev[6], gev[7]);
         }
+      };
+      {
+        const uint32_t a2 = lane_addr + 256 + hh * 128;
+        float va[32], vb[32];
+        tmem_ld32(a2, va);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          tmem_ld_wait_dep(va);
+          tmem_ld32(a2 + (2 * jj + 1) * 32, vb);
+          run_block2(2 * jj, va);
+          tmem_ld_wait_dep(vb);
+          if (jj == 0) tmem_ld32(a2 + 64, va);
+          run_block2(2 * jj + 1, vb);
+        }
       }
       tc_fence_before();
       mbar_arrive(d2_empty);
       if (use_tsm) mbar_arrive(sm.g_empty);          // ghe rows of this tile are consumed
-      if (hh == 1) sm.gaX[p] = make_float4(ga0, ga1, ga2, ga3);
+      // the two column halves of a pair meet once per tile: half 1 hands its partial g_dir / g_att to half 0
+      if (hh == 1) { sm.gdX[p] = make_float4(g0, g1, g2, 0.f); sm.gaX[p] = make_float4(ga0, ga1, ga2, ga3); }
+      const long long e_t5 = dbg == 7 ? clock64() : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (dbg == 7) ew[2] += clock64() - e_t5;
       if (hh == 0 && valid) {
-        const float4 bq = sm.gaX[p];
-        *reinterpret_cast<float4*>(gatt + prx * 4) = make_float4(ga0 + bq.x, ga1 + bq.y, ga2 + bq.z, ga3 + bq.w);
+        const float4 bd = sm.gdX[p], ba = sm.gaX[p];
+        float* o = gdir + prx * 3;
+        o[0] = (g0 + bd.x) * m; o[1] = (g1 + bd.y) * m; o[2] = (g2 + bd.z) * m;
+        *reinterpret_cast<float4*>(gatt + prx * 4) = make_float4(ga0 + ba.x, ga1 + ba.y, ga2 + ba.z, ga3 + ba.w);
       }
       if (dbg == 7) ew[5] += clock64() - e_t4;
     }
-    if (dbg == 7 && threadIdx.x == 192) {
+    if (dbg == 7 && threadIdx.x == 256) {
       atomicAdd(&g_bwd_wait[7], (unsigned long long)ew[0]); atomicAdd(&g_bwd_wait[8], (unsigned long long)ew[1]);
       atomicAdd(&g_bwd_wait[9], (unsigned long long)ew[2]); atomicAdd(&g_bwd_wait[10], (unsigned long long)ew[3]);
       atomicAdd(&g_bwd_wait[11], (unsigned long long)ew[4]); atomicAdd(&g_bwd_wait[12], (unsigned long long)ew[5]);
@@ -962,7 +998,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     ProfScope prof(2, d.P, st);
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
-    k_tc_mix_bwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
+    k_tc_mix_bwd<ENGINE><<<grid, BWD_THREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
                                                                   reinterpret_cast<const float4*>(sc.T), sc.tmax, sc.ghe,
                                                                   sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr, dbg);
   }
