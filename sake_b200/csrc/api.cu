@@ -59,23 +59,25 @@ static int resolve_engine(const SakeDims* s, const Dims& d) {
   return SAKE_EINVAL;
 }
 
-struct SavedLayout { size_t e, att, ssum, he, nodeproj, total; };
+struct SavedLayout { size_t e, att, logit, ssum, he, nodeproj, total; };
 static SavedLayout saved_layout(const Dims& d) {
   SavedLayout L;
   size_t o = 0;
   L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
   L.att = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
+  L.logit = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
   L.ssum = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
   L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
   L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
   L.total = o;
   return L;
 }
-static Saved carve_saved(const Dims& d, void* base) {
+static Saved carve_saved(const Dims& d, void* base, bool tc_edge) {
   SavedLayout L = saved_layout(d);
   char* b = (char*)base;
   Saved s;
   s.e = (float*)(b + L.e); s.att = (float*)(b + L.att); s.ssum = (float*)(b + L.ssum);
+  s.logit = tc_edge ? (float*)(b + L.logit) : s.att;   // tcgen05 edge path keeps the logits for the backward pass
   s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj);
   return s;
 }
@@ -163,8 +165,8 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (SL.total > 256 && (!scratch || scratch_bytes < SL.total)) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  Saved sv = carve_saved(d, saved);
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
+  Saved sv = carve_saved(d, saved, tc_edge);
   if ((rc = gen_node_pre(d, *params, h, sv, st))) return rc;
   if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, (char*)scratch + SL.edgew, st);
   else rc = gen_edge_fwd(d, *params, x, mask, sv, st);
@@ -198,7 +200,8 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  Saved sv = carve_saved(d, const_cast<void*>(saved));
+  const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
+  Saved sv = carve_saved(d, const_cast<void*>(saved), tc_edge);
   char* b = (char*)scratch;
   BwdScratch sc;
   sc.T = (float*)(b + SL.T); sc.tmax = (float*)(b + SL.tmax); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
@@ -216,8 +219,10 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, xl, st))) return rc;
   }
-  if ((rc = gen_attn_bwd(d, *params, sv, sc, st))) return rc;
-  if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d))
+  // tcgen05 edge path: softmax backward only (celu' comes from the saved logits, the W_s g_q term of g_e is
+  // added inside the edge kernel); generic path: the original kernel that recomputes q and updates g_e
+  if ((rc = tc_edge ? tc_attn_bwd(d, sv, sc, st) : gen_attn_bwd(d, *params, sv, sc, st))) return rc;
+  if (tc_edge)
     rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, b + SL.edgew, b + SL.edgeb, xl, st);
   else
     rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);

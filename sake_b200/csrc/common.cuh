@@ -28,7 +28,8 @@ struct Dims {
 // `saved` buffer (fwd -> bwd), all fp32:
 struct Saved {
   float* e;         // [P,H]   edge features h_e_mtx (layers.py:204)
-  float* att;       // [P,A]   combined attention (layers.py:205); holds logits between kernels
+  float* att;       // [P,A]   combined attention (layers.py:205)
+  float* logit;     // [P,A]   attention logits s (layers.py:155-165); aliases att on the generic engine (normalised in place)
   float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
   float* he;        // [R,C]   aggregate (layers.py:135-140)
   float* nodeproj;  // [R,NP]
@@ -179,6 +180,7 @@ int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const 
 int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                  cudaStream_t st);
 int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
+int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
 int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 cudaStream_t st);
 int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
 // (layers.py:135-140).  One warp per receiving atom, several rows per CTA; att is normalised in place.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restrict__ mask,
-                                                  const float* __restrict__ e, float* __restrict__ att,
+                                                  const float* __restrict__ e, const float* lg, float* att,
                                                   float* __restrict__ he) {
   extern __shared__ float sm[];
   const int N = d.N, A = d.A, H = d.H, C = d.C;
@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   float* as = sm + (size_t)warp * N * A;  // [N][A]
   float* arow = att + (size_t)row * N * A;
   const float* mrow = mask ? mask + (size_t)row * N : nullptr;
-  for (int t = lane; t < N * A; t += 32) as[t] = arow[t];
+  const float* lrow = lg + (size_t)row * N * A;        // logits (may alias att: read completely before any write)
+  for (int t = lane; t < N * A; t += 32) as[t] = lrow[t];
   __syncwarp();
   for (int a = 0; a < A; ++a) {
     float mx = -INFINITY;
@@ -169,12 +170,20 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
     // lane owns f = 2*lane, 2*lane+1 (coalesced float2 loads of e) and all four heads
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float* ep = e + (size_t)row * N * 64 + 2 * lane;
-    for (int j = 0; j < N; ++j) {
-      const float2 ev = *reinterpret_cast<const float2*>(ep + (size_t)j * 64);
-      float4 w = *reinterpret_cast<const float4*>(as + j * 4);
-      if (mrow) { const float m = mrow[j]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
-      acc[0] = fmaf(ev.x, w.x, acc[0]); acc[1] = fmaf(ev.x, w.y, acc[1]); acc[2] = fmaf(ev.x, w.z, acc[2]); acc[3] = fmaf(ev.x, w.w, acc[3]);
-      acc[4] = fmaf(ev.y, w.x, acc[4]); acc[5] = fmaf(ev.y, w.y, acc[5]); acc[6] = fmaf(ev.y, w.z, acc[6]); acc[7] = fmaf(ev.y, w.w, acc[7]);
+    for (int j0 = 0; j0 < N; j0 += 8) {
+      float2 ev[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)                        // 8 independent 256-byte row loads in flight per warp
+        ev[u] = j0 + u < N ? __ldg(reinterpret_cast<const float2*>(ep + (size_t)(j0 + u) * 64)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j0 + u < N) {
+          float4 w = *reinterpret_cast<const float4*>(as + (j0 + u) * 4);
+          if (mrow) { const float m = mrow[j0 + u]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+          acc[0] = fmaf(ev[u].x, w.x, acc[0]); acc[1] = fmaf(ev[u].x, w.y, acc[1]); acc[2] = fmaf(ev[u].x, w.z, acc[2]); acc[3] = fmaf(ev[u].x, w.w, acc[3]);
+          acc[4] = fmaf(ev[u].y, w.x, acc[4]); acc[5] = fmaf(ev[u].y, w.y, acc[5]); acc[6] = fmaf(ev[u].y, w.z, acc[6]); acc[7] = fmaf(ev[u].y, w.w, acc[7]);
+        }
+      }
     }
     float4* o = reinterpret_cast<float4*>(he + (size_t)row * 256 + 8 * lane);
     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -443,7 +452,7 @@ int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t
   while (nw > 1 && sizeof(float) * d.N * d.A * nw > 160 * 1024) nw >>= 1;
   size_t smem = sizeof(float) * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
-  k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, mask, sv.e, sv.att, sv.he);
+  k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, mask, sv.e, sv.logit, sv.att, sv.he);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -23,7 +23,7 @@ constexpr int WA_BYTES = 2 * 2 * 64 * 128;  // rows f  (64), K = k
 constexpr int WB_BYTES = 2 * 2 * 80 * 128;  // rows [e(64) | q(4) | 0(12)], K = f'
 constexpr int WC_BYTES = 2 * 2 * 64 * 128;  // rows f' (64), K = f
 constexpr int WD_BYTES = 2 * 2 * 64 * 128;  // rows k  (64), K = f
-constexpr int EVEC = 256;                   // floats: mu[64] beta[64] b2[64] bq[4] ...
+constexpr int EVEC = 512;                   // floats: mu[64] beta[64] b2[64] bq[4] ... | Ws[64][4] at 256
 constexpr int PB_LD = 192;                  // per-pair backward record: gz1[64] | gu[<=60] | g_r[124..126] | w[128..]
 constexpr int EDGE_THREADS = 256;
 
@@ -91,6 +91,9 @@ __global__ void k_edge_prep(int H, int K, int A, const float* __restrict__ W1, c
       float s = bs[a];
       for (int f = 0; f < H; ++f) s = fmaf(b2[f], Ws[(size_t)f * A + a], s);
       v = s;
+    } else if (t >= 256) {
+      const int f = (t - 256) / 4, a = (t - 256) % 4;
+      if (f < H && a < A) v = Ws[(size_t)f * A + a];
     }
     w.vec[t] = v;
   }
@@ -102,7 +105,9 @@ struct EdgeArgs {
   const float *x, *mask, *proj;
   EdgeW w;
   float *e_out, *logit_out;            // forward outputs  [P,64], [P,4]
-  const float *ge, *gdir;              // backward inputs  [P,64], [P,3]
+  float* ge;                           // backward input   [P,64] cotangent of e through x_mixing / aggregate; the
+                                       // attention-logit term W_s g_q is added here (written back when training)
+  const float *gdir, *gq;              // backward inputs  [P,3], [P,4] (cotangent of the pre-celu logits)
   float *PB, *a1buf, *gbuf;            // backward outputs [P,192], [P,64], [P,64] (a1buf/gbuf: training only)
   int train;
 };
@@ -135,6 +140,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024_shared(smem_raw);
+  if (base != smem_raw) __trap();                          // the budget has no alignment slack
   constexpr int W_BYTES = BWD ? (WA_BYTES + WC_BYTES + WD_BYTES) : (WA_BYTES + WB_BYTES);
   uint8_t* sWA = base;
   uint8_t* sW2 = base + WA_BYTES;                          // fwd: WB ; bwd: WC
@@ -336,13 +342,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         }
       }
       {
+        // g_e = (cotangent through x_mixing / aggregate) + W_s g_q   (layers.py:155: logits = e W_s + b_s)
         float4 g4[16];
+        float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) gq = __ldg(reinterpret_cast<const float4*>(a.gq + prx * 4));
 #pragma unroll
         for (int u = 0; u < 16; ++u)
-          g4[u] = valid ? __ldg(reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          g4[u] = valid ? *reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* s_ws = reinterpret_cast<const float4*>(svec + 256);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+          float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 ws = s_ws[4 * u + i];
+            vals[i] += ws.x * gq.x + ws.y * gq.y + ws.z * gq.z + ws.w * gq.w;
+          }
+          if (a.train && valid) *reinterpret_cast<float4*>(a.ge + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
           store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
         }
       }
@@ -462,6 +478,52 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- attention backward (tcgen05 edge path) --------------------------------------------------------
+// One warp per receiving atom: g_s = att * (g_att - sum_j g_att att) (the renormalisation of layers.py:180
+// is the identity on the gradient), g_q = g_s * celu_2'(q) with celu_2'(q) = 1 (q > 0) or e^{q/2} =
+// celu_2(q)/2 + 1 read off the saved logits (the -1e5 offsets of self / masked pairs meet att = 0).
+// Lane l owns the elements t = l, l+32, ... of the [N,4] row, i.e. always head a = l & 3.
+__global__ void __launch_bounds__(256) k_attn_bwd_tc(int R, int N, const float* __restrict__ att,
+                                                     const float* __restrict__ logit, float* __restrict__ gatt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= R) return;
+  const size_t base = (size_t)row * N * 4;
+  const int n4 = N * 4;
+  constexpr int MAXI = 8;                                  // register-resident up to N = 64; longer rows re-read
+  float av[MAXI], gv[MAXI];
+  float s = 0.f;
+  for (int i = 0; i * 32 + lane < n4; ++i) {
+    const int t = i * 32 + lane;
+    const float a_ = att[base + t], g_ = gatt[base + t];
+    if (i < MAXI) { av[i] = a_; gv[i] = g_; }
+    s = fmaf(g_, a_, s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int t = i * 32 + lane;
+    if (t < n4) {
+      const float lgv = logit[base + t];
+      gatt[base + t] = av[i] * (gv[i] - s) * (lgv > 0.f ? 1.0f : fmaf(0.5f, lgv, 1.0f));
+    }
+  }
+  for (int i = MAXI; i * 32 + lane < n4; ++i) {
+    const int t = i * 32 + lane;
+    const float lgv = logit[base + t];
+    gatt[base + t] = att[base + t] * (gatt[base + t] - s) * (lgv > 0.f ? 1.0f : fmaf(0.5f, lgv, 1.0f));
+  }
+}
+
+int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
+  k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d.R, d.N, sv.att, sv.logit, sc.gatt);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ---- reductions of the per-pair record over senders / receivers -----------------------------------
 // gproj[n] = [ sum_i gu[(i,n)] | sum_j gu[(n,j)] | sum_i gz1[(i,n)] | sum_j gz1[(n,j)] ],  dx[n] += sum_i g_r[(i,n)] - sum_j g_r[(n,j)]
 __global__ void __launch_bounds__(128) k_pair_reduce(int N, int K, int Kp, int NP, const float* __restrict__ PB,
@@ -525,8 +587,8 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.g = make_geom(d);
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
-  a.e_out = sv.e; a.logit_out = sv.att;
-  const size_t smem = WA_BYTES + WB_BYTES + 2 * EG_IMG + EVEC * 4 + 64 + 1024;
+  a.e_out = sv.e; a.logit_out = sv.logit;
+  const size_t smem = WA_BYTES + WB_BYTES + 2 * EG_IMG + EVEC * 4 + 64;
   static bool attr = false;
   if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
@@ -557,8 +619,8 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.g = make_geom(d);
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
-  a.ge = sc.ge; a.gdir = sc.gdir; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
-  const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + 2 * EG_IMG + EVEC * 4 + 64 + 1024;
+  a.ge = sc.ge; a.gdir = sc.gdir; a.gq = sc.gatt; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
+  const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + 2 * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
   static bool attr = false;
   if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
