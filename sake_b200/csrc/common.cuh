@@ -64,12 +64,81 @@ __device__ __forceinline__ float dsiluf_(float x) {
 __device__ __forceinline__ float celu2f_(float x) { return x > 0.f ? x : 2.0f * expm1f(0.5f * x); }
 __device__ __forceinline__ float dcelu2f_(float x) { return x > 0.f ? 1.0f : expf(0.5f * x); }
 
-constexpr int SAKE_NODES = 8;   // nodes per CTA in the per-node kernels
+constexpr int SAKE_NODES = 16;  // nodes per CTA in the per-node kernels
 
-// y[n][o] = bias[o] + sum_i x[n][i] * W[i][o]      (W row-major [in][out]; coalesced over o)
-// work item = (output o, pair of nodes): every thread of the CTA is busy for out = H = 64
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// acc[n][o] = sum_i x[n][i] * W[i][o] for SAKE_NODES nodes and ONE 64-column block of W (row stride ldw):
+// the weight rows go through shared memory in chunks of `wrows` rows (cp.async, double-buffered), so every
+// CTA reads a weight matrix from L2 once instead of once per warp (the node kernels were L2-bound on that).
+// 256 threads: warp = node pair, lane = (4 output columns og, K half ks); the halves meet by one shuffle.
+// epi(node, first column within the block, acc[4]) runs on the ks = 0 lanes.  Ends with __syncthreads().
+template <class Epi>
+__device__ __forceinline__ void node_gemm64(const float* x, int ldx, int in, const float* __restrict__ W, int ldw,
+                                            float* wbuf, int wrows, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int og = lane & 15, ks = lane >> 4;
+  const float* x0 = x + (2 * warp) * ldx;
+  const float* x1 = x0 + ldx;
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nchunk = (in + wrows - 1) / wrows, half = wrows / 2;
+  auto prefetch = [&](int c) {
+    float* dst = wbuf + (c & 1) * wrows * 64;
+    const int r0 = c * wrows;
+    for (int t = threadIdx.x; t < wrows * 16; t += blockDim.x) {
+      const int r = t >> 4, q = t & 15;
+      if (r0 + r < in) cp_async16(dst + r * 64 + q * 4, W + (size_t)(r0 + r) * ldw + q * 4);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  for (int c = 0; c < nchunk; ++c) {
+    cp_async_wait_all();
+    __syncthreads();                       // chunk c landed; everyone is done with the buffer chunk c+1 goes into
+    if (c + 1 < nchunk) prefetch(c + 1);
+    const float* wb = wbuf + (c & 1) * wrows * 64 + 4 * og;
+    const int rows = min(wrows, in - c * wrows);
+    const int kb = ks * half, ke = min(rows, kb + half);
+    const float* xa = x0 + c * wrows;
+    const float* xb = x1 + c * wrows;
+#pragma unroll 8
+    for (int k = kb; k < ke; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(wb + k * 64);
+      const float v0 = xa[k], v1 = xb[k];
+      a0[0] = fmaf(v0, w.x, a0[0]); a0[1] = fmaf(v0, w.y, a0[1]); a0[2] = fmaf(v0, w.z, a0[2]); a0[3] = fmaf(v0, w.w, a0[3]);
+      a1[0] = fmaf(v1, w.x, a1[0]); a1[1] = fmaf(v1, w.y, a1[1]); a1[2] = fmaf(v1, w.z, a1[2]); a1[3] = fmaf(v1, w.w, a1[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], 16);
+    a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], 16);
+  }
+  if (ks == 0) { epi(2 * warp, 4 * og, a0); epi(2 * warp + 1, 4 * og, a1); }
+  __syncthreads();                         // the weight buffers are free again
+}
+
+// y[n][o] = bias[o] + sum_i x[n][i] * W[i][o]      (W row-major [in][out])
+// Fast path (wbuf != NULL, 256 threads, out a multiple of 64, W 16-byte aligned): node_gemm64 per 64-column block.
+// Generic path: work item = (output o, pair of nodes), weights read from global (coalesced over o).
 __device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, int in, const float* __restrict__ W,
-                                           const float* __restrict__ bias, int out, bool accumulate) {
+                                           const float* __restrict__ bias, int out, bool accumulate,
+                                           float* wbuf = nullptr, int wrows = 0) {
+  if (wbuf != nullptr && blockDim.x == 256 && (out & 63) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    for (int ob = 0; ob < out; ob += 64)
+      node_gemm64(x, ldx, in, W + ob, out, wbuf, wrows, [&](int n, int o4, const float* a) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = ob + o4 + i;
+          y[n * out + o] = a[i] + (accumulate ? y[n * out + o] : (bias ? bias[o] : 0.f));
+        }
+      });
+    return;
+  }
   for (int idx = threadIdx.x; idx < out * (SAKE_NODES / 2); idx += blockDim.x) {
     const int o = idx % out, n0 = (idx / out) * 2;
     float a0 = accumulate ? y[n0 * out + o] : (bias ? bias[o] : 0.f);
@@ -85,6 +154,7 @@ __device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, in
     y[n0 * out + o] = a0;
     y[(n0 + 1) * out + o] = a1;
   }
+  __syncthreads();
 }
 
 // ---- fast fp32-class transcendentals for the tensor-core kernels --------------------------------

@@ -86,8 +86,9 @@ __global__ void k_node_wt(Dims d, const SakeLayerParams p, float* __restrict__ b
   if (t < n6) { const int q = t / (2 * H), r = t % (2 * H); base[t] = p.mlp_out0_kernel[(size_t)r * H + q]; return; }
 }
 
+constexpr int BWD_WROWS = 16;     // weight rows per staged chunk (2 x 4 KB: two CTAs per SM still fit)
 size_t node_post_bwd_smem_bytes(const Dims& d) {
-  return sizeof(float) * (NODES * (2 * d.C + 17 * d.H) + 8 * NODES + 64);
+  return sizeof(float) * (NODES * (2 * d.C + 17 * d.H) + 8 * NODES + 64 + 2 * BWD_WROWS * 64);
 }
 
 __global__ void __launch_bounds__(256) k_node_post_bwd(
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
   float* gy = den2 + NODES;
   float* gate = gy + NODES;
   float* gdv = gate + NODES;         // [NODES][3] (+pad)
+  float* wbuf = gdv + 4 * NODES + 32;  // [2][BWD_WROWS][64] staged weight rows (16-byte aligned)
   const int r0 = blockIdx.x * NODES;
   const int nn = min(NODES, d.R - r0);
   const bool upd = d.update != 0, hv = d.has_v != 0, spatial = d.spatial != 0;
@@ -160,11 +162,11 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     ghout[t] = n < nn ? dh_out[(size_t)r0 * H + t] : 0.f;
   }
   __syncthreads();
-  node_dense(hp1, nrm, C, C, p.post0_kernel, p.post0_bias, H, false);
+  node_dense(hp1, nrm, C, C, p.post0_kernel, p.post0_bias, H, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = hp1[t]; hp1[t] = siluf_(z); dhp1[t] = dsiluf_(z); }
   __syncthreads();
-  node_dense(hcb, hp1, H, H, p.post2_kernel, p.post2_bias, H, false);
+  node_dense(hcb, hp1, H, H, p.post2_kernel, p.post2_bias, H, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) {
     const float z = hcb[t];
@@ -172,22 +174,22 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
     dhcb[t] = spatial ? dsiluf_(z) : 0.f;
   }
   __syncthreads();
-  node_dense(n1, hin, H, H, p.node0_kernel, p.node0_bias, H, false);
+  node_dense(n1, hin, H, H, p.node0_kernel, p.node0_bias, H, false, wbuf, BWD_WROWS);
   __syncthreads();
-  node_dense(n1, hes, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true);
+  node_dense(n1, hes, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true, wbuf, BWD_WROWS);
   __syncthreads();
-  node_dense(n1, hcb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true);
+  node_dense(n1, hcb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = n1[t]; n1[t] = siluf_(z); dn1[t] = dsiluf_(z); }
   __syncthreads();
-  node_dense(hout, n1, H, H, p.node2_kernel, p.node2_bias, H, false);
+  node_dense(hout, n1, H, H, p.node2_kernel, p.node2_bias, H, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = hout[t]; dn2[t] = dsiluf_(z); hout[t] = hin[t] + siluf_(z); }
   __syncthreads();
 
   // ---------------- velocity / position update backward (layers.py:226-232) ----------------
   if (upd && hv) {
-    node_dense(av, hout, H, H, p.vel0_kernel, p.vel0_bias, H, false);
+    node_dense(av, hout, H, H, p.vel0_kernel, p.vel0_bias, H, false, wbuf, BWD_WROWS);
     __syncthreads();
     for (int t = threadIdx.x; t < NH; t += blockDim.x) { const float z = av[t]; av[t] = siluf_(z); dav[t] = dsiluf_(z); }
   }
@@ -240,14 +242,14 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
       nb_store(nbuf, r0, nn, NB_AV, av, H, false);
       if (threadIdx.x < nn) nbuf[(size_t)(r0 + threadIdx.x) * NB_LD + NB_GY] = gy[threadIdx.x];
     }
-    node_dense(ghout, gtv, H, H, wt.vel0T, nullptr, H, true);      // g_h' += Wv1 g_tv
+    node_dense(ghout, gtv, H, H, wt.vel0T, nullptr, H, true, wbuf, BWD_WROWS);      // g_h' += Wv1 g_tv
     __syncthreads();
   }
 
   // ---------------- node_mlp backward (layers.py:142-151) ----------------
   for (int t = threadIdx.x; t < NH; t += blockDim.x) gt2[t] = ghout[t] * dn2[t];
   __syncthreads();
-  node_dense(gt1, gt2, H, H, wt.node2T, nullptr, H, false);
+  node_dense(gt1, gt2, H, H, wt.node2T, nullptr, H, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) gt1[t] *= dn1[t];
   __syncthreads();
@@ -270,33 +272,42 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
   // g_cat = Wn1 g_t1 : [dh | ghe | g_hcomb]   (coalesced through the transposed copy)
   {
     const int NC = 2 * H + C;
-    for (int idx = threadIdx.x; idx < NC * (NODES / 2); idx += blockDim.x) {
-      const int o = idx % NC, n0 = (idx / NC) * 2;
-      float a0 = 0.f, a1 = 0.f;
-      const float* g0p = gt1 + n0 * H;
-      const float* g1p = g0p + H;
-#pragma unroll 16
-      for (int f = 0; f < H; ++f) {
-        const float w = wt.node0T[(size_t)f * NC + o];
-        a0 = fmaf(g0p[f], w, a0);
-        a1 = fmaf(g1p[f], w, a1);
-      }
+    auto put = [&](int n, int o, float a) {
       if (o < H) {
-        if (n0 < nn) dh[(size_t)(r0 + n0) * H + o] = ghout[n0 * H + o] + a0;
-        if (n0 + 1 < nn) dh[(size_t)(r0 + n0 + 1) * H + o] = ghout[(n0 + 1) * H + o] + a1;
+        if (n < nn) dh[(size_t)(r0 + n) * H + o] = ghout[n * H + o] + a;
       } else if (o < H + C) {
-        if (n0 < nn) ghe[(size_t)(r0 + n0) * C + (o - H)] = a0;
-        if (n0 + 1 < nn) ghe[(size_t)(r0 + n0 + 1) * C + (o - H)] = a1;
+        if (n < nn) ghe[(size_t)(r0 + n) * C + (o - H)] = a;
       } else {
         const int q = o - H - C;
-        gtp2[n0 * H + q] = a0 * dhcb[n0 * H + q];
-        gtp2[(n0 + 1) * H + q] = a1 * dhcb[(n0 + 1) * H + q];
+        gtp2[n * H + q] = a * dhcb[n * H + q];
+      }
+    };
+    if (blockDim.x == 256 && (NC & 63) == 0 && (reinterpret_cast<uintptr_t>(wt.node0T) & 15) == 0) {
+      for (int ob = 0; ob < NC; ob += 64)
+        node_gemm64(gt1, H, H, wt.node0T + ob, NC, wbuf, BWD_WROWS, [&](int n, int o4, const float* a) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) put(n, ob + o4 + i, a[i]);
+        });
+    } else {
+      for (int idx = threadIdx.x; idx < NC * (NODES / 2); idx += blockDim.x) {
+        const int o = idx % NC, n0 = (idx / NC) * 2;
+        float a0 = 0.f, a1 = 0.f;
+        const float* g0p = gt1 + n0 * H;
+        const float* g1p = g0p + H;
+#pragma unroll 16
+        for (int f = 0; f < H; ++f) {
+          const float w = wt.node0T[(size_t)f * NC + o];
+          a0 = fmaf(g0p[f], w, a0);
+          a1 = fmaf(g1p[f], w, a1);
+        }
+        put(n0, o, a0);
+        put(n0 + 1, o, a1);
       }
     }
   }
   __syncthreads();
   // ---------------- post_norm_mlp backward (layers.py:85-92,129-131) ----------------
-  node_dense(gtp1, gtp2, H, H, wt.post2T, nullptr, H, false);
+  node_dense(gtp1, gtp2, H, H, wt.post2T, nullptr, H, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NH; t += blockDim.x) gtp1[t] *= dhp1[t];
   __syncthreads();
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(256) k_node_post_bwd(
   __syncthreads();
   // g_nrm = Wp1 g_tp1 (overwrites nrm), then
   // T[c][d] = 2*ssum[c][d]*g_nrm[c]/den^2 + Wv[c]*g_dv[d]/den2 ;  gWv[c] += sum_d ssum[c][d]*g_dv[d]/den2
-  if (spatial) node_dense(nrm, gtp1, H, H, wt.post0T, nullptr, C, false);
+  if (spatial) node_dense(nrm, gtp1, H, H, wt.post0T, nullptr, C, false, wbuf, BWD_WROWS);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float wv = (spatial && upd) ? p.v_mixing_kernel[c] : 0.f;

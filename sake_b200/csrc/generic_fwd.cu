@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(256) k_mix_fwd(Dims d, const float* __restrict
 // node_post: norms, post_norm_mlp, node_mlp + residual, velocity / position update
 // (layers.py:123-131,142-151,218-232).  NODES nodes per CTA.
 // ------------------------------------------------------------------------------------------
+constexpr int POST_WROWS = 32;    // weight rows per staged chunk (2 x 8 KB)
 struct NodePostSmem {
-  float *nrm, *he, *hin, *hp1, *hcomb, *n1, *hout, *den, *den2;
+  float *nrm, *he, *hin, *hp1, *hcomb, *n1, *hout, *den, *den2, *wbuf;
 };
 __device__ inline NodePostSmem node_post_carve(float* sm, const Dims& d) {
   NodePostSmem s;
@@ -293,9 +294,10 @@ __device__ inline NodePostSmem node_post_carve(float* sm, const Dims& d) {
   s.hout = s.n1 + NODES * d.H;
   s.den = s.hout + NODES * d.H;     // [NODES]
   s.den2 = s.den + NODES;           // [NODES]
+  s.wbuf = s.den2 + NODES + 32;     // [2][POST_WROWS][64] staged weight rows (16-byte aligned)
   return s;
 }
-size_t node_post_smem_bytes(const Dims& d) { return sizeof(float) * (NODES * (2 * d.C + 5 * d.H) + 2 * NODES + 64); }
+size_t node_post_smem_bytes(const Dims& d) { return sizeof(float) * (NODES * (2 * d.C + 5 * d.H) + 2 * NODES + 64 + 2 * POST_WROWS * 64); }
 
 __global__ void __launch_bounds__(256) k_node_post(Dims d, const SakeLayerParams p, const float* __restrict__ h,
                                                    const float* __restrict__ x, const float* __restrict__ v,
@@ -338,24 +340,24 @@ __global__ void __launch_bounds__(256) k_node_post(Dims d, const SakeLayerParams
   }
   __syncthreads();
   // post_norm_mlp (layers.py:85-92)
-  node_dense(s.hp1, s.nrm, C, C, p.post0_kernel, p.post0_bias, H, false);
+  node_dense(s.hp1, s.nrm, C, C, p.post0_kernel, p.post0_bias, H, false, s.wbuf, POST_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.hp1[t] = siluf_(s.hp1[t]);
   __syncthreads();
-  node_dense(s.hcomb, s.hp1, H, H, p.post2_kernel, p.post2_bias, H, false);
+  node_dense(s.hcomb, s.hp1, H, H, p.post2_kernel, p.post2_bias, H, false, s.wbuf, POST_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.hcomb[t] = d.spatial ? siluf_(s.hcomb[t]) : 0.f;
   __syncthreads();
   // node_mlp over [h | he | hcomb] + residual (layers.py:142-151)
-  node_dense(s.n1, s.hin, H, H, p.node0_kernel, p.node0_bias, H, false);
+  node_dense(s.n1, s.hin, H, H, p.node0_kernel, p.node0_bias, H, false, s.wbuf, POST_WROWS);
   __syncthreads();
-  node_dense(s.n1, s.he, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true);
+  node_dense(s.n1, s.he, C, C, p.node0_kernel + (size_t)H * H, nullptr, H, true, s.wbuf, POST_WROWS);
   __syncthreads();
-  node_dense(s.n1, s.hcomb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true);
+  node_dense(s.n1, s.hcomb, H, H, p.node0_kernel + (size_t)(H + C) * H, nullptr, H, true, s.wbuf, POST_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) s.n1[t] = siluf_(s.n1[t]);
   __syncthreads();
-  node_dense(s.hout, s.n1, H, H, p.node2_kernel, p.node2_bias, H, false);
+  node_dense(s.hout, s.n1, H, H, p.node2_kernel, p.node2_bias, H, false, s.wbuf, POST_WROWS);
   __syncthreads();
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) {
     const float ho = s.hin[t] + siluf_(s.hout[t]);

@@ -26,22 +26,26 @@ class ModelRunner:
         flat = flatten_tree(params)
         self.paths = list(flat.keys())
         sizes = [flat[k].numel() for k in self.paths]
-        self.n_params = sum(sizes)
-        self.flat_params = torch.empty(self.n_params, device=dev, dtype=f32)
-        self.p, off = {}, 0
-        for k, n in zip(self.paths, sizes):
+        # every tensor starts on a 16-byte boundary (vectorised / cp.async weight loads in the node kernels);
+        # the pad floats stay zero in the parameters, gradients and Adam moments
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4
+        self.n_params = off
+        self.n_params_real = sum(sizes)
+        self.flat_params = torch.zeros(self.n_params, device=dev, dtype=f32)
+        self.p = {}
+        for k, n, off in zip(self.paths, sizes, offs):
             self.p[k] = self.flat_params[off:off + n].view(flat[k].shape)
             self.p[k].copy_(flat[k])
-            off += n
         self.g = {}
         if train:
             self.flat_grads = torch.zeros(self.n_params, device=dev, dtype=f32)
             self.adam_m = torch.zeros_like(self.flat_grads)
             self.adam_v = torch.zeros_like(self.flat_grads)
-            off = 0
-            for k, n in zip(self.paths, sizes):
+            for k, n, off in zip(self.paths, sizes, offs):
                 self.g[k] = self.flat_grads[off:off + n].view(flat[k].shape)
-                off += n
         # ---- per-layer dims / param structs ---------------------------------------------------
         K = flat["d0/edge_model/kernel/means"].shape[0]
         self.dims, self.ps, self.gs, self._keep = [], [], [], []
