@@ -47,7 +47,7 @@ enum {
 
 /* precision / engine (SakeDims.engine) */
 enum {
-  SAKE_ENGINE_AUTO = 0,   /* tcgen05 3xTF32 when the shape allows, else the generic fp32 path   */
+  SAKE_ENGINE_AUTO = 0,   /* tcgen05 fp16-split (F16X2) when the shape allows, else the generic fp32 path */
   SAKE_ENGINE_FP32 = 1,   /* generic CUDA-core fp32 kernels, any H / A / K                      */
   SAKE_ENGINE_TF32X3 = 2, /* tcgen05.mma kind::tf32, hi/lo split (3 MMAs) — fp32-parity mode     */
   SAKE_ENGINE_BF16 = 3,   /* tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate) — fast mode  */

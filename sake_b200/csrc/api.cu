@@ -46,7 +46,7 @@ static int make_dims(const SakeDims* s, Dims* d) {
 
 static int resolve_engine(const SakeDims* s, const Dims& d) {
   int e = s->engine;
-  if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_TF32X3 : SAKE_ENGINE_FP32;
+  if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_F16X2 : SAKE_ENGINE_FP32;
   if (e == SAKE_ENGINE_FP32) return e;
   if (e == SAKE_ENGINE_TF32X3 || e == SAKE_ENGINE_BF16 || e == SAKE_ENGINE_F16X2) {
     if (!tc_supported(d)) {

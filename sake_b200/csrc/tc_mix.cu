@@ -114,8 +114,10 @@ __device__ __forceinline__ void build_E_chunk(uint8_t* img, int row, int kc, con
 // w1img[kc][split][row=c'][128B]: K index = c      (GEMM1: Z = E Wx)
 // w2img[q ][split][row=c ][128B]: K index = c', ring order q -> chunk (q%2)*(NCHUNK/2) + q/2 (GEMM2: dE = dZ Wx^T)
 template <int ENGINE>
-__global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1img, uint8_t* __restrict__ w2img) {
+__global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1img, uint8_t* __restrict__ w2img,
+                          const float* __restrict__ wscale) {
   using CF = Cfg<ENGINE>;
+  const float wsc = CF::F16 ? wscale[0] : 1.0f;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_img = CF::NCHUNK * CC * 8;
   if (t >= 2 * per_img) return;
@@ -129,10 +131,10 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
   for (int i = 0; i < CF::EPU; ++i) {
     const int k = u * CF::EPU + i;
     if (which == 0) {
-      vals[i] = Wx[(size_t)(chunk * CF::KCH + k) * CC + row];
+      vals[i] = wsc * Wx[(size_t)(chunk * CF::KCH + k) * CC + row];
     } else {
       const int kc2 = (chunk % 2) * (CF::NCHUNK / 2) + chunk / 2;
-      vals[i] = Wx[(size_t)row * CC + kc2 * CF::KCH + k];
+      vals[i] = wsc * Wx[(size_t)row * CC + kc2 * CF::KCH + k];
     }
   }
   uint8_t* base = (which == 0 ? w1img : w2img) + (size_t)chunk * CF::NSPLIT * W_IMG;
@@ -166,13 +168,37 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
   }
 }
 
-// power-of-two scale that brings a row with max magnitude `mx` to <= ~2^13 (fp16 overflows at 65504)
-__device__ __forceinline__ float row_scale_down(float mx) {
-  return mx > 8192.f ? exp2f(-ceilf(log2f(mx * (1.0f / 8192.f)))) : 1.0f;
+// fp16-split engine: exact power-of-two pair (sc, inv = 1/sc) that brings `bound` into [2^11, 2^12).
+// With the operand's largest magnitude there, hi = fp16(x) and lo = fp16(x - hi) together carry 22 bits of
+// the row / tensor maximum and nothing can overflow (fp16 max 65504) or drown in fp16 subnormals, however
+// large or small the fp32 values are.  Identity for 0, inf and nan.
+__device__ __forceinline__ void pow2_norm(float bound, float& sc, float& inv) {
+  const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);   // biased exponent: bound in [2^(e-127), 2^(e-126))
+  int k = 138 - e;
+  if (e == 0 || e == 255) k = 0;
+  k = max(-100, min(100, k));
+  sc = __uint_as_float((uint32_t)(k + 127) << 23);
+  inv = __uint_as_float((uint32_t)(127 - k) << 23);
 }
-// power-of-two scale that brings a row bounded by `bound` to ~1 (gradients can be arbitrarily small)
-__device__ __forceinline__ float row_scale_unit(float bound) {
-  return (bound > 0.f && bound < 3.0e38f) ? exp2f(-ceilf(log2f(bound))) : 1.0f;
+
+// max |Wx| -> {scale, 1/scale} of the weight images (fp16-split engine; {1, 1} otherwise)
+__global__ void __launch_bounds__(1024) k_tc_wscale(const float* __restrict__ Wx, float* __restrict__ ws, int f16) {
+  __shared__ float red[32];
+  float mx = 0.f;
+  if (f16)
+    for (int t = threadIdx.x; t < CC * CC; t += 1024) mx = fmaxf(mx, fabsf(Wx[t]));
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = red[threadIdx.x];
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) {
+      float sc = 1.0f, inv = 1.0f;
+      if (f16) pow2_norm(mx, sc, inv);
+      ws[0] = sc; ws[1] = inv;
+    }
+  }
 }
 
 // ---- shared-memory carve-up -----------------------------------------------------------------
@@ -253,7 +279,8 @@ __device__ __forceinline__ void epi_fwd_chunk(const float (&v)[32], const float4
 template <int ENGINE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
-             const float* __restrict__ att, const uint8_t* __restrict__ w1img, float* __restrict__ ssum, int dbg_wsplits) {
+             const float* __restrict__ att, const uint8_t* __restrict__ w1img, const float* __restrict__ wscale,
+             float* __restrict__ ssum, int dbg_wsplits) {
   using CF = Cfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
   Smem<CF> sm(smem_raw);
@@ -368,16 +395,14 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
       float inv_s = 1.0f;
-      if constexpr (CF::F16) {                      // keep |E| = |e*att| <= |e| inside the fp16 range (exact 2^k scale)
+      if constexpr (CF::F16) {                      // normalise the row E = e (x) att (exact 2^k, applied through att)
         float mx = 0.f;
 #pragma unroll
         for (int q = 0; q < 64; ++q) mx = fmaxf(mx, fabsf(ev[q]));
-        const float sc = row_scale_down(mx);
-        if (sc != 1.0f) {
-#pragma unroll
-          for (int q = 0; q < 64; ++q) ev[q] *= sc;
-          inv_s = 1.0f / sc;
-        }
+        float sc;
+        pow2_norm(mx * fmaxf(fmaxf(fabsf(at.x), fabsf(at.y)), fmaxf(fabsf(at.z), fabsf(at.w))), sc, inv_s);
+        at.x *= sc; at.y *= sc; at.z *= sc; at.w *= sc;
+        inv_s *= wscale[1];                         // ... and undo the weight-image scale with the same factor
       }
       mbar_wait_warp(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
       dm.w = inv_s;                                          // fp16-split engine: undoes the E row scale
@@ -503,7 +528,8 @@ template <int ENGINE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
              const float* __restrict__ att, const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
-             const float4* __restrict__ T4, const float* __restrict__ tmax, const float* __restrict__ ghe,
+             const float* __restrict__ wscale, const float4* __restrict__ T4, const float* __restrict__ tmax,
+             const float* __restrict__ ghe,
              float* __restrict__ ge, float* __restrict__ gatt, float* __restrict__ gdir, float* __restrict__ gZ_out, int dbg) {
   using CF = Cfg<ENGINE>;
   constexpr int NCH = CF::NCHUNK;
@@ -635,16 +661,14 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
-      if constexpr (CF::F16) {                      // exact 2^k row scale, undone in epilogue 1
+      if constexpr (CF::F16) {                      // normalise the row E = e (x) att (exact 2^k), undone in epilogue 1
         float mx = 0.f;
 #pragma unroll
         for (int q = 0; q < 64; ++q) mx = fmaxf(mx, fabsf(ev[q]));
-        const float sc = row_scale_down(mx);
-        if (sc != 1.0f) {
-#pragma unroll
-          for (int q = 0; q < 64; ++q) ev[q] *= sc;
-        }
-        sm.escale[p] = 1.0f / sc;   // single buffer: the builders only get here after epilogue 1 of the previous tile started
+        float sc, inv;
+        pow2_norm(mx * fmaxf(fmaxf(fabsf(at.x), fabsf(at.y)), fmaxf(fabsf(at.z), fabsf(at.w))), sc, inv);
+        at.x *= sc; at.y *= sc; at.z *= sc; at.w *= sc;
+        sm.escale[p] = inv * wscale[1];   // single buffer: the builders only get here after epilogue 1 of the previous tile started
       }
       int pos = it * 2 * NCH;
 #pragma unroll
@@ -710,12 +734,12 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       tc_fence_after();
       const long long e_t1 = dbg == 7 ? clock64() : 0;
       ew[0] += e_t1 - e_t0;
-      float zs = 1.0f, dzs = 1.0f;                  // fp16-split engine: 1/scale of the E row, scale of the dZ row
+      float zs = 1.0f, dzs = 1.0f, idz = 1.0f;      // fp16-split engine: 1/scale of the E row, scale of the dZ row
       if constexpr (CF::F16) {
         zs = sm.escale[p];
-        if (valid) dzs = row_scale_unit(2.0f * tmax[row]);      // |dZ| <= |dir|_1 * max|T| < 2 max|T|
+        if (valid) pow2_norm(2.0f * tmax[row], dzs, idz);       // |dZ| <= |dir|_1 * max|T| * max sech^2 < 2 max|T|
       }
-      const float idz = 1.0f / dzs;
+      const float idzw = CF::F16 ? idz * wscale[1] : 1.0f;      // GEMM2 output: undo the dZ row and weight-image scales
       const float q0 = 4.0f * dzs * d0, q1 = 4.0f * dzs * d1, q2 = 4.0f * dzs * d2;    // see epi1_block
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
       float* gzrow = (gZ_out != nullptr && valid) ? gZ_out + prx * CC : nullptr;
@@ -777,8 +801,8 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       const float4* ghg4 = reinterpret_cast<const float4*>(ghe + (size_t)trow * CC) + hh * 32;  // global row
       auto run_block2 = [&](int cc, const float (&v)[32]) {
         float gev[8];
-        if (use_tsm) epi2_part(v, ghs4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
-        else epi2_part(v, ghg4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idz, gev, ga0, ga1, ga2, ga3);
+        if (use_tsm) epi2_part(v, ghs4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idzw, gev, ga0, ga1, ga2, ga3);
+        else epi2_part(v, ghg4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idzw, gev, ga0, ga1, ga2, ga3);
         if (valid) {
           float4* o = reinterpret_cast<float4*>(ge + prx * 64 + hh * 32 + cc * 8);
           o[0] = make_float4(gev[0], gev[1], gev[2], gev[3]);
@@ -956,7 +980,9 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   uint8_t* w2 = w1 + wimg_bytes<CF>();
   TileGeom g = make_geom(d);
   const int prep_threads = 2 * CF::NCHUNK * CC * 8;
-  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2);
+  float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
+  k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
+  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
   if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
   static bool attr_set = false;
   if (!attr_set) {
@@ -969,9 +995,9 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     ProfScope prof(1, d.P, st);
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
-    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, sv.ssum, dbg);
+    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, wsc, sv.ssum, dbg);
   }
-  note_launches(2);
+  note_launches(3);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -986,7 +1012,9 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   uint8_t* w2 = w1 + wimg_bytes<CF>();
   TileGeom g = make_geom(d);
   const int prep_threads = 2 * CF::NCHUNK * CC * 8;
-  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2);
+  float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
+  k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
+  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
   static bool attr_set = false;
   if (!attr_set) {
     SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mix_bwd<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -998,7 +1026,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     ProfScope prof(2, d.P, st);
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
-    k_tc_mix_bwd<ENGINE><<<grid, BWD_THREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2,
+    k_tc_mix_bwd<ENGINE><<<grid, BWD_THREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, w2, wsc,
                                                                   reinterpret_cast<const float4*>(sc.T), sc.tmax, sc.ghe,
                                                                   sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr, dbg);
   }

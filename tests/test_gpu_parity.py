@@ -203,10 +203,11 @@ def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
         assert float((gd1[k] - gd0[k]).abs().max()) < gtol * scale + 1e-7, k
 
 
+@pytest.mark.parametrize("wscale", [3000.0, 1e-4])
 @pytest.mark.parametrize("engine", ["tf32x3", "f16x2"])
-def test_small_gradient_scale_and_large_features(engine):
-    """Range robustness of the split-precision engines: edge features blown up to ~1e3 (the fp16-split
-    engine must take its exact power-of-two down-scaling path) and cotangents scaled by 1e-6 (up-scaling
+def test_small_gradient_scale_and_large_features(engine, wscale):
+    """Range robustness of the split-precision engines: edge features blown up to ~1e3 or shrunk to ~1e-4
+    (the fp16-split engine normalises every operand row by an exact power of two) and cotangents scaled by 1e-6 (up-scaling
     path).  Saturated tanh makes this an ill-conditioned regime even for plain fp32 arithmetic, so the
     yardstick is the generic fp32 CUDA-core engine: against the fp64 oracle a split engine may be at
     most 10x worse than it (the split engines carry 21-22 mantissa bits per product against 24) (plus the stated 1e-5 / 1e-4 floors)."""
@@ -219,7 +220,8 @@ def test_small_gradient_scale_and_large_features(engine):
     for eng in ("fp32", engine):
         model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=depth, engine=eng)
         params = model.init(3, T(h), T(x))["params"]
-        params["d0"]["edge_model"]["mlp_out"]["layers_2"]["kernel"].mul_(3000.0)
+        params["d0"]["edge_model"]["mlp_out"]["layers_2"]["kernel"].mul_(wscale)
+        params["d0"]["edge_model"]["mlp_out"]["layers_2"]["bias"].mul_(wscale)
         po = _oracle_params(params)
         e0, f0 = O.energy_and_forces(po, T(h).cpu().double(), T(x).cpu().double())
         fmax = max(1.0, f0.abs().max().item())
