@@ -18,14 +18,15 @@ namespace sake {
 using namespace tc;
 
 constexpr int EP_IMG = TILE * 128;          // one chunk image, one split (16 KB)
-constexpr int EG_IMG = 4 * EP_IMG;          // pair-side image of one group: 2 K-chunks x {hi, lo}
+constexpr int EG_IMG = 2 * EP_IMG;          // pair-side image of one group: ONE K-chunk x {hi, lo}
 constexpr int WA_BYTES = 2 * 2 * 64 * 128;  // rows f  (64), K = k
 constexpr int WB_BYTES = 2 * 2 * 80 * 128;  // rows [e(64) | q(4) | 0(12)], K = f'
 constexpr int WC_BYTES = 2 * 2 * 64 * 128;  // rows f' (64), K = f
 constexpr int WD_BYTES = 2 * 2 * 64 * 128;  // rows k  (64), K = f
 constexpr int EVEC = 512;                   // floats: mu[64] beta[64] b2[64] bq[4] ... | Ws[64][4] at 256
 constexpr int PB_LD = 192;                  // per-pair backward record: gz1[64] | gu[<=60] | g_r[124..126] | w[128..]
-constexpr int EDGE_THREADS = 256;
+constexpr int EDGE_GROUPS = 4;              // independent 128-thread groups (tiles in flight) per CTA
+constexpr int EDGE_THREADS = 128 * EDGE_GROUPS;
 
 struct EdgeW {
   uint8_t *WA, *WB, *WC, *WD;
@@ -121,21 +122,27 @@ __device__ __forceinline__ void store_unit_tf32(uint8_t* chunk_img, int row, int
   *reinterpret_cast<float4*>(chunk_img + EP_IMG + off) = lo;
 }
 
-// one 3xTF32 GEMM: D[128 x N] = A[128 x 64] * B[N x 64]^T, K = 64 = 2 chunks of 32
-__device__ __forceinline__ void edge_gemm(uint32_t d_tmem, uint32_t a_img, uint32_t b_img, int b_rows, uint32_t idesc) {
+// one K-chunk (32 of the 64 K values) of a 3xTF32 GEMM: D[128 x N] (+)= A[128 x 32] * B[N x 32]^T
+//   a_img: {hi, lo} images of the chunk; b_img: weight image [2 chunks][{hi, lo}][b_rows x 128 B]
+__device__ __forceinline__ void edge_gemm_chunk(uint32_t d_tmem, uint32_t a_img, uint32_t b_img, int chunk, int b_rows,
+                                                uint32_t idesc) {
   const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
-    for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a0 = a_img + (c * 2 + pp[pr]) * EP_IMG + ks * 32;
-        const uint32_t b0 = b_img + (c * 2 + pw[pr]) * (b_rows * 128) + ks * 32;
-        umma<true>(d_tmem, umma_desc_k_sw128(a0), umma_desc_k_sw128(b0), idesc, (c | pr | ks) != 0);
-      }
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a0 = a_img + pp[pr] * EP_IMG + ks * 32;
+      const uint32_t b0 = b_img + (chunk * 2 + pw[pr]) * (b_rows * 128) + ks * 32;
+      umma<true>(d_tmem, umma_desc_k_sw128(a0), umma_desc_k_sw128(b0), idesc, (chunk | pr | ks) != 0);
+    }
 }
 
+// Four independent 128-thread groups per CTA (one tile each, round robin): the kernel is bound by the
+// latency of its per-pair chains (projection loads -> RBF / silu -> operand image -> MMA -> TMEM), so the
+// lever is the number of tiles in flight per SM.  To fit four groups, a group owns ONE 32 KB chunk image
+// ({hi, lo} of 32 K values) and 128 TMEM columns: every GEMM is issued as two K-chunks through the same
+// image, and accumulators are recycled (forward: E' overwrites Z1; backward: GG overwrites Z1) — the half
+// of Z1 that is still needed is pulled into registers before the overwriting MMA is issued.
 template <bool BWD>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -145,15 +152,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   uint8_t* sWA = base;
   uint8_t* sW2 = base + WA_BYTES;                          // fwd: WB ; bwd: WC
   uint8_t* sWD = base + WA_BYTES + WC_BYTES;               // bwd only
-  uint8_t* imgs = base + W_BYTES;                          // [2 groups][EG_IMG]
-  float* svec = reinterpret_cast<float*>(imgs + 2 * EG_IMG);
+  uint8_t* imgs = base + W_BYTES;                          // [EDGE_GROUPS][EG_IMG]
+  float* svec = reinterpret_cast<float*>(imgs + EDGE_GROUPS * EG_IMG);
   uint64_t* wbar = reinterpret_cast<uint64_t*>(svec + EVEC);
-  uint64_t* mbar = wbar + 1;                               // [2]
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(mbar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* mbar = wbar + 1;                               // [EDGE_GROUPS]
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(mbar + EDGE_GROUPS);
+  const int warp = threadIdx.x >> 5;
   const int grp = threadIdx.x >> 7, pl = threadIdx.x & 127;
   if (threadIdx.x == 0) {
-    mbar_init(wbar, 1); mbar_init(mbar, 1); mbar_init(mbar + 1, 1);
+    mbar_init(wbar, 1);
+    for (int g = 0; g < EDGE_GROUPS; ++g) mbar_init(mbar + g, 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(wbar, W_BYTES);
     bulk_g2s(sWA, a.w.WA, WA_BYTES, wbar);
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   tc_fence_after();
   mbar_wait_warp(wbar, 0);
   const uint32_t tmem_base = *tptr;
-  const uint32_t tcol = tmem_base + grp * 256;                         // this group's TMEM columns
+  const uint32_t tcol = tmem_base + grp * 128;                         // this group's 128 TMEM columns
   const uint32_t lane_addr = tcol + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* img = imgs + grp * EG_IMG;
   const uint32_t img_u32 = smem_u32(img);
@@ -181,8 +189,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   constexpr uint32_t idesc64 = umma_idesc(2, 128, 64);
   constexpr uint32_t idesc80 = umma_idesc(2, 128, 80);
   const int bar_id = 1 + grp;
+  // publish the chunk image, run one K-chunk of a GEMM on it, wait until the MMAs (and their reads of the
+  // image) are complete
+  auto run_chunk = [&](uint32_t dcol, const uint8_t* wimg, int chunk, int b_rows, uint32_t idesc) {
+    fence_proxy_async();
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    if (pl == 0) {
+      tc_fence_after();
+      edge_gemm_chunk(dcol, img_u32, smem_u32(wimg), chunk, b_rows, idesc);
+      umma_commit(mbar + grp);
+    }
+    mbar_wait_warp(mbar + grp, ph);
+    ph ^= 1;
+    tc_fence_after();
+  };
 
-  for (int it = grp; it < ntl; it += 2) {
+  for (int it = grp; it < ntl; it += EDGE_GROUPS) {
     const int tile = blockIdx.x + it * gridDim.x;
     bool valid, seg_end;
     int row, j;
@@ -205,10 +228,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       tt = fexp_(-nrm);                                                    // utils.py:62-64 (alpha = 1, lower = 0)
       if (a.mask) m = a.mask[prx];
     }
-    // ---------------- (a) G = [rho*u | n | 1 | t | 0...]  ->  A operand of GEMM A
-#pragma unroll
+    // ---------------- (a) G = [rho*u | n | 1 | t | 0...]  ->  A operand of GEMM A, one K-chunk at a time
+#pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
-      // issue the 16 projection loads of this half before any of the exp chains (latency overlap)
+      // issue the 16 projection loads of this chunk before any of the exp chains (latency overlap)
       float4 uj4[8], ui4[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -238,35 +261,29 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           }
           if (BWD && a.train) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         }
-        store_unit_tf32(img + hb * 2 * EP_IMG, pl, q, vals);
+        store_unit_tf32(img, pl, q, vals);
       }
+      run_chunk(tcol + 0, sWA, hb, 64, idesc64);                           // Z1 -> cols [0,64)
     }
-    fence_proxy_async();
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    if (pl == 0) {
-      tc_fence_after();
-      edge_gemm(tcol + 0, img_u32, smem_u32(sWA), 64, idesc64);          // Z1 -> cols [0,64)
-      umma_commit(mbar + grp);
-    }
-    mbar_wait_warp(mbar + grp, ph); ph ^= 1;
-    tc_fence_after();
 
     if (!BWD) {
-      // ---------------- (c) a1 = silu(Z1 + pj[j] + pi[i])  (layers.py:33-38, 23)
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      // ---------------- (c) a1 = silu(Z1 + pj[j] + pi[i])  (layers.py:33-38, 23) -> A operand of GEMM B.
+      // GEMM B writes E' over Z1, so the second half of Z1 is read before its first chunk is issued.
+      float z1b[32];
+      {
         float4 pj4[8], pi4[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           pi4[u] = pj4[u];
           if (valid) {
-            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
-            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
+            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 4 * u));
+            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 4 * u));
           }
         }
         float v[32];
-        tmem_ld32(lane_addr + half * 32, v);
+        tmem_ld32(lane_addr, v);
+        tmem_ld32(lane_addr + 32, z1b);
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -275,24 +292,36 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             vals[0] = fsilu_(v[4 * u] + pj4[u].x + pi4[u].x); vals[1] = fsilu_(v[4 * u + 1] + pj4[u].y + pi4[u].y);
             vals[2] = fsilu_(v[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = fsilu_(v[4 * u + 3] + pj4[u].w + pi4[u].w);
           }
-          store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
+          store_unit_tf32(img, pl, u, vals);
         }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (pl == 0) {
-        tc_fence_after();
-        edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 80, idesc80);       // E' -> cols [64,144)
-        umma_commit(mbar + grp);
+      // second-half projections: requested before the hand-off so that their latency hides behind the MMA
+      float4 pj4[8], pi4[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pi4[u] = pj4[u];
+        if (valid) {
+          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 32 + 4 * u));
+          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 32 + 4 * u));
+        }
       }
-      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
-      tc_fence_after();
+      run_chunk(tcol + 0, sW2, 0, 80, idesc80);                            // E' (chunk 0) -> cols [0,80)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float vals[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+          vals[0] = fsilu_(z1b[4 * u] + pj4[u].x + pi4[u].x); vals[1] = fsilu_(z1b[4 * u + 1] + pj4[u].y + pi4[u].y);
+          vals[2] = fsilu_(z1b[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = fsilu_(z1b[4 * u + 3] + pj4[u].w + pi4[u].w);
+        }
+        store_unit_tf32(img, pl, u, vals);
+      }
+      run_chunk(tcol + 0, sW2, 1, 80, idesc80);                            // E' (chunk 1)
       // ---------------- (e) e = E' + b2 ; logits = celu(q) - 1e5*diag - 1e5*(1-m)  (layers.py:24,155-165)
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float v[32];
-        tmem_ld32(lane_addr + 64 + half * 32, v);
+        tmem_ld32(lane_addr + half * 32, v);
         tmem_ld_wait();
         if (valid) {
           float4* o = reinterpret_cast<float4*>(a.e_out + prx * 64 + half * 32);
@@ -305,8 +334,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         }
       }
       {
-        float v[32];
-        tmem_ld32(lane_addr + 128, v);
+        float v[16];
+        tmem_ld16(lane_addr + 64, v);
         tmem_ld_wait();
         if (valid) {
           float s[4];
@@ -343,36 +372,32 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       }
       {
         // g_e = (cotangent through x_mixing / aggregate) + W_s g_q   (layers.py:155: logits = e W_s + b_s)
-        float4 g4[16];
         float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) gq = __ldg(reinterpret_cast<const float4*>(a.gq + prx * 4));
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-          g4[u] = valid ? *reinterpret_cast<const float4*>(a.ge + prx * 64 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* s_ws = reinterpret_cast<const float4*>(svec + 256);
+#pragma unroll 1
+        for (int hb = 0; hb < 2; ++hb) {
+          float4 g4[8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+          for (int u = 0; u < 8; ++u)
+            g4[u] = valid ? *reinterpret_cast<const float4*>(a.ge + prx * 64 + hb * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 ws = s_ws[4 * u + i];
-            vals[i] += ws.x * gq.x + ws.y * gq.y + ws.z * gq.z + ws.w * gq.w;
+          for (int u = 0; u < 8; ++u) {
+            float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 ws = s_ws[hb * 32 + 4 * u + i];
+              vals[i] += ws.x * gq.x + ws.y * gq.y + ws.z * gq.z + ws.w * gq.w;
+            }
+            if (a.train && valid) *reinterpret_cast<float4*>(a.ge + prx * 64 + hb * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            store_unit_tf32(img, pl, u, vals);
           }
-          if (a.train && valid) *reinterpret_cast<float4*>(a.ge + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-          store_unit_tf32(img + (u >> 3) * 2 * EP_IMG, pl, u & 7, vals);
+          run_chunk(tcol + 64, sW2, hb, 64, idesc64);                      // GA1 = GE W2^T -> cols [64,128)
         }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (pl == 0) {
-        tc_fence_after();
-        edge_gemm(tcol + 64, img_u32, smem_u32(sW2), 64, idesc64);       // GA1 = GE W2^T -> cols [64,128)
-        umma_commit(mbar + grp);
-      }
-      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
-      tc_fence_after();
-      // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record
+      // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record.
+      // GEMM D writes GG over Z1, so the second half of Z1 is read before its first chunk is issued.
+      float z1b[32];
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float4 pj4[8], pi4[8];
@@ -386,7 +411,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           }
         }
         float z[32], ga[32];
-        tmem_ld32(lane_addr + half * 32, z);
+        if (half == 0) {
+          tmem_ld32(lane_addr, z);
+          tmem_ld32(lane_addr + 32, z1b);
+        }
         tmem_ld32(lane_addr + 64 + half * 32, ga);
         tmem_ld_wait();
 #pragma unroll
@@ -396,25 +424,18 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             const int f0 = half * 32 + 4 * u;
             const float4 pj = pj4[u];
             const float4 pi = pi4[u];
-            vals[0] = ga[4 * u] * fdsilu_(z[4 * u] + pj.x + pi.x);
-            vals[1] = ga[4 * u + 1] * fdsilu_(z[4 * u + 1] + pj.y + pi.y);
-            vals[2] = ga[4 * u + 2] * fdsilu_(z[4 * u + 2] + pj.z + pi.z);
-            vals[3] = ga[4 * u + 3] * fdsilu_(z[4 * u + 3] + pj.w + pi.w);
+            const float zz0 = half == 0 ? z[4 * u] : z1b[4 * u], zz1 = half == 0 ? z[4 * u + 1] : z1b[4 * u + 1],
+                        zz2 = half == 0 ? z[4 * u + 2] : z1b[4 * u + 2], zz3 = half == 0 ? z[4 * u + 3] : z1b[4 * u + 3];
+            vals[0] = ga[4 * u] * fdsilu_(zz0 + pj.x + pi.x);
+            vals[1] = ga[4 * u + 1] * fdsilu_(zz1 + pj.y + pi.y);
+            vals[2] = ga[4 * u + 2] * fdsilu_(zz2 + pj.z + pi.z);
+            vals[3] = ga[4 * u + 3] * fdsilu_(zz3 + pj.w + pi.w);
             *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
           }
-          store_unit_tf32(img + half * 2 * EP_IMG, pl, u, vals);
+          store_unit_tf32(img, pl, u, vals);
         }
+        run_chunk(tcol + 0, sWD, half, 64, idesc64);                       // GG = GZ1 W1[2H:]^T -> cols [0,64)
       }
-      fence_proxy_async();
-      tc_fence_before();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (pl == 0) {
-        tc_fence_after();
-        edge_gemm(tcol + 128, img_u32, smem_u32(sWD), 64, idesc64);      // GG = GZ1 W1[2H:]^T -> cols [128,192)
-        umma_commit(mbar + grp);
-      }
-      mbar_wait_warp(mbar + grp, ph); ph ^= 1;
-      tc_fence_after();
       // ---------------- (g) RBF / geometry backward (utils.py:61-65, functional.py:7-19, layers.py:115)
       float gt = 0.f, gn = 0.f;
 #pragma unroll 1
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           }
         }
         float gg[32];
-        tmem_ld32(lane_addr + 128 + half * 32, gg);
+        tmem_ld32(lane_addr + half * 32, gg);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -574,7 +595,7 @@ static int edge_grid(const TileGeom& g) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int want = (g.num_tiles + 1) / 2;             // two groups per CTA
+  const int want = (g.num_tiles + EDGE_GROUPS - 1) / EDGE_GROUPS;
   return want < sms ? (want < 1 ? 1 : want) : sms;
 }
 
@@ -588,7 +609,7 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.e_out = sv.e; a.logit_out = sv.logit;
-  const size_t smem = WA_BYTES + WB_BYTES + 2 * EG_IMG + EVEC * 4 + 64;
+  const size_t smem = WA_BYTES + WB_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;
   static bool attr = false;
   if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
@@ -620,7 +641,7 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.ge = sc.ge; a.gdir = sc.gdir; a.gq = sc.gatt; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
-  const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + 2 * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
+  const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
   static bool attr = false;
   if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
