@@ -55,6 +55,9 @@ static_assert(2 * 2 * (P_IMG + W_IMG) + AUX_BYTES + 256 <= 232448, "shared-memor
 __device__ __constant__ int c_prod_p[3] = {0, 1, 0};
 __device__ __constant__ int c_prod_w[3] = {0, 0, 1};
 
+// L2 prefetch of the 128-byte line holding p (the next tile's rows: the demand loads then hit L2)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- operand image writers -------------------------------------------------------------------
 template <class CF>
 __device__ __forceinline__ void store_unit(uint8_t* img, int row, int u, const float* vals) {
@@ -370,6 +373,15 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       bool valid, seg_end;
       int row, j;
       tile_pair(g, tile, p, valid, row, j, seg_end);
+      if (it + 1 < ntl) {                           // pull the next tile's e / att rows into L2
+        bool v2, se2;
+        int row2, j2;
+        tile_pair(g, tile + gridDim.x, p, v2, row2, j2, se2);
+        if (v2) {
+          const size_t px2 = (size_t)row2 * g.N + j2;
+          prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4);
+        }
+      }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -646,6 +658,15 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       bool valid, seg_end;
       int row, j;
       tile_pair(g, tile, p, valid, row, j, seg_end);
+      if (it + 1 < ntl) {                           // pull the next tile's e / att rows into L2
+        bool v2, se2;
+        int row2, j2;
+        tile_pair(g, tile + gridDim.x, p, v2, row2, j2, se2);
+        if (v2) {
+          const size_t px2 = (size_t)row2 * g.N + j2;
+          prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4);
+        }
+      }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
