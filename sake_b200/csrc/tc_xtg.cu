@@ -78,8 +78,10 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
 
 struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
 
-template <int ENGINE>
-__global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant__ XtgBatch batch) {
+// TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
+// the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE)
+template <int ENGINE, int TCOLS>
+__global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
   using CF = XCfg<ENGINE>;
   const XtgArgs& a = batch.a[blockIdx.y];
   if ((int)blockIdx.x >= a.gx) return;                        // CTA beyond this problem's range
@@ -90,17 +92,17 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
   constexpr uint32_t LBO = XKP * 128;                         // bytes between 64-feature MN blocks
   const size_t ximg = (size_t)xblocks * LBO, gimg = (size_t)gblocks * LBO;
   const size_t stage = CF::NSPLIT * (ximg + gimg);
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + XTG_NSTAGE * stage);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + nstage * stage);
   uint64_t* empty = full + XTG_NSTAGE;
   uint64_t* done = empty + XTG_NSTAGE;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < XTG_NSTAGE; ++s) { mbar_init(full + s, 256); mbar_init(empty + s, 1); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 256); mbar_init(empty + s, 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(tptr);
+  if (warp == 0) tmem_alloc<TCOLS>(tptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
     if (lane == 0 && nst > 0) {
       const uint32_t idesc = umma_idesc(1 /*bf16*/, 128, a.NG, 1, 1);      // both operands MN-major
       for (int it = 0; it < nst; ++it) {
-        const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
+        const int s = it % nstage, n = it / nstage;
         mbar_wait(full + s, n & 1);
         tc_fence_after();
         const uint32_t xb = smem_u32(base + s * stage), gb = xb + (uint32_t)(CF::NSPLIT * ximg);
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
     };
     if (nst > 0) load_stage(0);
     for (int it = 0; it < nst; ++it) {
-      const int s = it % XTG_NSTAGE, n = it / XTG_NSTAGE;
+      const int s = it % nstage, n = it / nstage;
       mbar_wait_warp(empty + s, (n & 1) ^ 1);
       uint8_t* ximgp = base + s * stage;
       uint8_t* gimgp = ximgp + CF::NSPLIT * ximg;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) tmem_dealloc<TCOLS>(tmem_base);
 }
 
 // out[row][col] += sum_cta partial[cta][col][row]   (deterministic second stage of the flush)
@@ -282,17 +284,45 @@ static int xtg_num_sms() {
   return sms;
 }
 
-// Launch every collected contraction as one grid (blockIdx.y = problem) + one reduction grid.
+// Launch the collected contractions as two grids (blockIdx.y = problem): the 256 x 256 x_mixing gradient, which
+// needs the whole TMEM and a 192 KB operand ring (this launch is the one the profiler times as "mix_dw"), and
+// all the small ones (<= 256 TMEM columns, two-stage ring: two CTAs per SM) — each followed by its reduction grid.
+template <int TCOLS>
+static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, size_t smem, int nstage, bool bf,
+                      int prof_kind, long long prof_pairs, cudaStream_t st) {
+  if (nb == 0) return 0;
+  if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
+  static bool attr_tf = false, attr_bf = false;
+  if (bf) {
+    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
+  } else {
+    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
+  }
+  {
+    ProfScope prof(prof_kind, prof_pairs, st);
+    dim3 grid(gx_max, nb);
+    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    dim3 rgrid(ng_max, nb);
+    k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
+  }
+  note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st) {
   if (L.n == 0) return 0;
   const bool bf = engine == SAKE_ENGINE_BF16;
   const int nsplit = bf ? 1 : 2;
   const int sms = xtg_num_sms();
-  XtgBatch batch;
-  memset(&batch, 0, sizeof(batch));
-  size_t smem_max = 0, poff = 0;
-  int gx_max = 0, ng_max = 0, nb = 0;
+  XtgBatch big, small;
+  memset(&big, 0, sizeof(big));
+  memset(&small, 0, sizeof(small));
+  size_t smem_b = 0, smem_s = 0, poff = 0;
+  int gx_b = 0, gx_s = 0, ng_b = 0, ng_s = 0, nb_b = 0, nb_s = 0;
   long long prof_pairs = 0;
+  constexpr int NST_BIG = XTG_NSTAGE, NST_SMALL = 2;
   for (int i = 0; i < L.n; ++i) {
     XtgArgs a = L.a[i];
     if (a.P <= 0) continue;
@@ -301,10 +331,10 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
       set_error("tc_xtg: unsupported shape MXpad=%d NG=%d", a.MXpad, a.NG);
       return SAKE_EUNSUPPORTED;
     }
+    const bool is_big = (a.MXpad / 128) * a.NG > 256;
     const size_t lbo = (size_t)XKP * 128;
     const size_t stage = nsplit * ((size_t)(a.MXpad / XBLK) * lbo + (size_t)((a.NG + XBLK - 1) / XBLK) * lbo);
-    const size_t smem = XTG_NSTAGE * stage + 256 + 1024;
-    if (smem > smem_max) smem_max = smem;
+    const size_t smem = (is_big ? NST_BIG : NST_SMALL) * stage + 256 + 1024;
     long long stages_total = (a.P + XKP - 1) / XKP;
     long long per = (stages_total + sms - 1) / sms;
     if (per < 4) per = 4;                                  // keep the flush amortised
@@ -317,31 +347,23 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
     } else {
       a.partial = nullptr;                                 // falls back to atomics
     }
-    if (a.gx > gx_max) gx_max = a.gx;
-    if (a.NG > ng_max) ng_max = a.NG;
-    if (a.P > prof_pairs) prof_pairs = a.P;
-    batch.a[nb++] = a;
+    if (is_big) {
+      if (smem > smem_b) smem_b = smem;
+      if (a.gx > gx_b) gx_b = a.gx;
+      if (a.NG > ng_b) ng_b = a.NG;
+      if (a.P > prof_pairs) prof_pairs = a.P;
+      big.a[nb_b++] = a;
+    } else {
+      if (smem > smem_s) smem_s = smem;
+      if (a.gx > gx_s) gx_s = a.gx;
+      if (a.NG > ng_s) ng_s = a.NG;
+      small.a[nb_s++] = a;
+    }
   }
   L.n = 0;
-  if (nb == 0) return 0;
-  if (smem_max > 200 * 1024) { set_error("tc_xtg: smem %zu", smem_max); return SAKE_EUNSUPPORTED; }
-  static bool attr_tf = false, attr_bf = false;
-  if (bf) {
-    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
-  } else {
-    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
-  }
-  {
-    ProfScope prof(prof_kind, prof_pairs, st);
-    dim3 grid(gx_max, nb);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16><<<grid, XTG_THREADS, smem_max, st>>>(batch);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3><<<grid, XTG_THREADS, smem_max, st>>>(batch);
-    dim3 rgrid(ng_max, nb);
-    k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
-  }
-  note_launches(2);
-  SAKE_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  int rc = xtg_launch<512>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
+  if (rc) return rc;
+  return xtg_launch<256>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
 }
 
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
