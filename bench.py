@@ -161,6 +161,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="molecules in the CPU-baseline sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not
+    # get in the way: fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     B, N, S, padded, n_min, mode, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -178,13 +185,13 @@ def main():
         warm = max(1, min(args.warmup, 5))
         val, dt, Bs = cpu_arm(args.workload, args.depth, steps, warm, args.cpu_sample)
         sample = f"{Bs} of {B} molecules of the same workload per step, {steps} timed steps"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "molecules_per_sec", "value": val, "unit": "molecules/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": sample + " (torch-eager fp32 restatement of the reference; JAX not installable)"},
-            "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ---------------- our arm ----------------
@@ -331,7 +338,7 @@ def main():
                 "d2h_bytes_per_step": d2h},
         "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
