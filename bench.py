@@ -306,6 +306,10 @@ def main():
         d[0] += ms
         d[1] += 1
     kind_names = {1: "mix_fwd", 2: "mix_bwd", 3: "mix_dw"}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full`
+    # captures (profiles/r01e_ncu_cfg2_auto.txt, profiles/r01e_ncu_mix_bwd_cfg3_f16x2.txt); null where not captured
+    traffic_table = {("cfg2", "f16x2", "mix_bwd"): 98.501120e6 + 231.125248e6,
+                     ("cfg3", "f16x2", "mix_bwd"): 1.453833e9 + 1.117801e9}
     roofline = None
     if by_kind:
         dom = max(by_kind, key=lambda k: by_kind[k][0])
@@ -313,7 +317,8 @@ def main():
         avg_ms = tot / cnt
         achieved = FLOP_MIX * pairs / (avg_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": kind_names.get(dom, str(dom)), "achieved": achieved, "peak": sus,
-                    "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / sus,
+                    "traffic": traffic_table.get((args.workload, run.engine, kind_names.get(dom, str(dom)))),
                     "peak_source": f"bf16 dense sustained, {how} (MEASURED_PEAKS.json)",
                     "avg_launch_ms": avg_ms, "launches_timed": cnt, "algorithmic_flop_per_launch": FLOP_MIX * pairs,
                     "share_of_step": {kind_names.get(k, str(k)): by_kind[k][0] / (ms_step * args.steps) for k in by_kind}}
