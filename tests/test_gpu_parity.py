@@ -237,3 +237,36 @@ def test_small_gradient_scale_and_large_features(engine, wscale):
         (er0, fr0), (er1, fr1) = errs[("fp32", scale)], errs[(engine, scale)]
         assert er1 < 10 * er0 + 1e-5, f"energy: {engine} {er1:.3e} vs fp32 engine {er0:.3e} (scale {scale})"
         assert fr1 < 10 * fr0 + 1e-4, f"forces: {engine} {fr1:.3e} vs fp32 engine {fr0:.3e} (scale {scale})"
+
+
+@pytest.mark.parametrize("B,N,S,padded,n_min", [(256, 29, 10, True, 9), (1024, 63, 4, True, 20), (64, 200, 84, False, 0)])
+def test_full_size_properties(B, N, S, padded, n_min):
+    """BASELINE.json's full sizes (cfg2 / cfg3 / cfg4 shapes, depth 4, the default engine) through
+    size-independent properties of the energy/force path, plus an oracle spot check:
+      * forces of every molecule sum to zero (translation invariance of E);
+      * energies are invariant and forces co-rotate under a random rotation + translation
+        (sake/tests/test_equivariance.py, at batch scale);
+      * four molecules of the batch, cut out and run unpadded through the fp64 oracle, agree
+        (1e-5 relative energy, 1e-4 absolute force; sake/tests/test_mask.py:202-240 at full width)."""
+    model, p, h, x, mask, am = _setup(64, 4, B, N, S, 2666, "auto", padded=padded, n_min=n_min)
+    kw = {} if mask is None else {"mask": mask, "atom_mask": am}
+    e, f = model.energy_and_forces(p, h, x, **kw)
+    assert torch.isfinite(e).all() and torch.isfinite(f).all()
+    fs = f.sum(1).abs().max().item()
+    assert fs < 2e-3 * max(1.0, f.abs().max().item()), f"sum of forces {fs:.3e}"
+    rng = np.random.default_rng(7)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    Rm = torch.tensor(q.astype(np.float32), device="cuda")
+    t = torch.tensor(rng.standard_normal((1, 1, 3)).astype(np.float32), device="cuda")
+    x2 = x @ Rm + t
+    if am is not None:
+        x2 = x2 * am[..., None]                       # padded atoms stay at the origin (scripts/qm9/run.py:35)
+    e2, f2 = model.energy_and_forces(p, h, x2, **kw)
+    assert ((e2 - e).abs() / e.abs().clamp_min(1.0)).max().item() < 2e-5
+    assert (f2 - f @ Rm).abs().max().item() < 2e-4 * max(1.0, f.abs().max().item())
+    po = _oracle_params(p)
+    for b in (0, 1, B // 2, B - 1):
+        n = N if am is None else int(am[b].sum().item())
+        e0, f0 = O.energy_and_forces(po, h[b, :n].cpu().double(), x[b, :n].cpu().double())
+        assert abs(e[b].item() - e0.item()) < 1e-5 * max(1.0, abs(e0.item())), (b, e[b].item(), e0.item())
+        assert (f[b, :n].cpu().double() - f0).abs().max().item() < 1e-4, b
