@@ -161,9 +161,13 @@ __device__ __forceinline__ void node_dense(float* y, const float* x, int ldx, in
 // One MUFU each (ex2.approx / rcp.approx, <= 2 ulp) instead of the ~25-instruction libdevice paths.
 // Errors stay at the 1e-7 .. 1e-6 level (absolute for tanh/sigmoid, relative ~|x|*2^-24 for exp), well
 // inside the 1e-5 energy / 1e-4 force tolerance — and the epilogues are issue-bound, not MUFU-bound.
-__device__ __forceinline__ float fexp_(float x) { return __expf(x); }
+// (raw ex2.approx / rcp.approx with flush-to-zero: none of __expf's / __fdividef's range fix-ups; e^x -> 0 or
+// inf outside the fp32 range, 1/inf -> 0, which is what the callers need)
+__device__ __forceinline__ float fex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float frcpa_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fexp_(float x) { return fex2_(x * 1.4426950408889634f); }
 __device__ __forceinline__ float frcp_(float x) { return __frcp_rn(x); }
-__device__ __forceinline__ float fsigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fsigmoid_(float x) { return frcpa_(1.0f + fex2_(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float fsilu_(float x) { return x * fsigmoid_(x); }
 __device__ __forceinline__ float fdsilu_(float x) {
   const float s = fsigmoid_(x);
