@@ -25,7 +25,7 @@ constexpr int WC_BYTES = 2 * 2 * 64 * 128;  // rows f' (64), K = f
 constexpr int WD_BYTES = 2 * 2 * 64 * 128;  // rows k  (64), K = f
 constexpr int EVEC = 512;                   // floats: mu[64] beta[64] b2[64] bq[4] ... | Ws[64][4] at 256
 constexpr int PB_LD = 192;                  // per-pair backward record: gz1[64] | gu[<=60] | g_r[124..126] | w[128..]
-constexpr int EDGE_GROUPS = 4;              // independent 128-thread groups (tiles in flight) per CTA
+constexpr int EDGE_GROUPS = 3;              // independent 128-thread groups (tiles in flight) per CTA
 constexpr int EDGE_THREADS = 128 * EDGE_GROUPS;
 
 struct EdgeW {
@@ -137,9 +137,9 @@ __device__ __forceinline__ void edge_gemm_chunk(uint32_t d_tmem, uint32_t a_img,
     }
 }
 
-// Four independent 128-thread groups per CTA (one tile each, round robin): the kernel is bound by the
+// EDGE_GROUPS independent 128-thread groups per CTA (one tile each, round robin): the kernel is bound by the
 // latency of its per-pair chains (projection loads -> RBF / silu -> operand image -> MMA -> TMEM), so the
-// lever is the number of tiles in flight per SM.  To fit four groups, a group owns ONE 32 KB chunk image
+// lever is the number of tiles in flight per SM (3 groups of 168 registers measured best; 4 x 128 spills).  A group owns ONE 32 KB chunk image
 // ({hi, lo} of 32 K values) and 128 TMEM columns: every GEMM is issued as two K-chunks through the same
 // image, and accumulators are recycled (forward: E' overwrites Z1; backward: GG overwrites Z1) — the half
 // of Z1 that is still needed is pulled into registers before the overwriting MMA is issued.
