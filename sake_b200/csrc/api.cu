@@ -82,7 +82,7 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge) {
   return s;
 }
 
-struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, total; };
+struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, nodew, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -114,6 +114,8 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_xtg_partial_bytes());
   L.nbuf = o;
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_node_dw_scratch_bytes(d));
+  L.nodew = o;
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d)) o += align_up(tc_node_w_bytes());
   L.total = o + 256;
   return L;
 }
@@ -179,6 +181,8 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_fwd(d, *params, x, mask, sv, (char*)scratch + SL.tc, engine, st))) return rc;
   }
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d))
+    return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, (char*)scratch + SL.nodew, st);
   return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
 }
 

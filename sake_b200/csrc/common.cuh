@@ -254,6 +254,12 @@ int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const 
 int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                  cudaStream_t st);
 int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
+// tc_node.cu: per-node tail of the layer on the tensor cores (H = 64, A = 4)
+bool tc_node_supported(const Dims& d);
+size_t tc_node_w_bytes();
+int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                 const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
+                 cudaStream_t st);
 int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
 int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 cudaStream_t st);

@@ -1,0 +1,312 @@
+// tcgen05 engine for the per-node tail of DenseSAKELayer (sake/layers.py:85-92,123-131,142-151,184-186,
+// 218-232): post_norm_mlp on the squared norms of the spatial sums, node_mlp on [h | h_e | h_comb] with the
+// residual, and the velocity / position update.  Tile = 128 atoms, thread = atom (= TMEM lane), so every
+// activation, bias add and reduction over features is thread-local; the Dense layers
+//   post0 (256 -> 64), post2 (64 -> 64), node0 (384 -> 64), node2 (64 -> 64), vel0 (64 -> 64)
+// run as 3xTF32 GEMMs D[128 x 64] += A[128 x 32] B[64 x 32]^T, one 32-wide K-chunk at a time: the thread
+// writes its 32 input values into the (128-byte-swizzled, hi/lo split) A image, the weight chunk arrives by
+// TMA from a pre-swizzled image of all five matrices (26 chunks x 16 KB, L2 resident), one thread issues the
+// 12 MMAs.  Two accumulators of 64 TMEM columns alternate between consecutive layers.
+// Replaces the CUDA-core kernel k_node_post (generic_fwd.cu) when H = 64, A = 4.
+#include <string.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sake {
+using namespace tc;
+
+constexpr int NT_TILE = 128;                 // atoms per CTA
+constexpr int NT_IMG = NT_TILE * 128;        // one split of the A chunk image (16 KB)
+constexpr int NT_WCH = 2 * 64 * 128;         // one weight chunk: {hi, lo} x 64 output rows x 128 B (16 KB)
+// chunk index of every matrix inside the weight image
+constexpr int NTW_POST0 = 0, NTW_POST2 = 8, NTW_NODE0 = 10, NTW_NODE2 = 22, NTW_VEL0 = 24, NTW_CHUNKS = 26;
+constexpr int NT_VEC = 64 * 6 + 256;         // b_p1 b_p2 b_n1 b_n2 b_v1 vel2 | v_mixing
+
+size_t tc_node_w_bytes() { return (size_t)NTW_CHUNKS * NT_WCH + 256; }
+
+// weight image: chunk c = K rows [32c', 32c'+32) of its matrix W[in][64]; B operand rows = outputs
+__global__ void k_node_w_prep(const SakeLayerParams p, uint8_t* __restrict__ img) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NTW_CHUNKS * 64 * 8) return;
+  const int chunk = t / (64 * 8), o = (t / 8) % 64, u = t % 8;
+  const float* W;
+  int c0;
+  if (chunk < NTW_POST2) { W = p.post0_kernel; c0 = chunk; }
+  else if (chunk < NTW_NODE0) { W = p.post2_kernel; c0 = chunk - NTW_POST2; }
+  else if (chunk < NTW_NODE2) { W = p.node0_kernel; c0 = chunk - NTW_NODE0; }
+  else if (chunk < NTW_VEL0) { W = p.node2_kernel; c0 = chunk - NTW_NODE2; }
+  else { W = p.vel0_kernel; c0 = chunk - NTW_VEL0; }
+  float vals[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) vals[i] = W ? W[(size_t)(c0 * 32 + u * 4 + i) * 64 + o] : 0.f;
+  uint8_t* base = img + (size_t)chunk * NT_WCH;
+  const uint32_t off = sw128_offset((uint32_t)o, (uint32_t)u);
+  float4 hi, lo;
+  split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+  split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+  *reinterpret_cast<float4*>(base + off) = hi;
+  *reinterpret_cast<float4*>(base + 64 * 128 + off) = lo;
+}
+
+__device__ __forceinline__ void nt_store_unit(uint8_t* img, int row, int u, const float* vals) {
+  const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)u);
+  float4 hi, lo;
+  split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+  split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+  *reinterpret_cast<float4*>(img + off) = hi;
+  *reinterpret_cast<float4*>(img + NT_IMG + off) = lo;
+}
+
+struct NodeFwdArgs {
+  int R, N, update, has_v, spatial;
+  const float *h, *x, *v, *mask, *ssum, *he;
+  const uint8_t* wimg;
+  const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
+  float *h_out, *x_out, *v_out;
+};
+
+__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024_shared(smem_raw);
+  uint8_t* img = base;                                   // A chunk image {hi, lo}: 32 KB
+  uint8_t* wring = base + 2 * NT_IMG;                    // 2 weight chunk slots: 32 KB
+  float* svec = reinterpret_cast<float*>(wring + 2 * NT_WCH);
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(svec + NT_VEC);   // [2]
+  uint64_t* mdone = wfull + 2;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(mdone + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
+  for (int t = tid; t < NT_VEC; t += NT_TILE) {
+    const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
+    svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(wfull, 1); mbar_init(wfull + 1, 1); mbar_init(mdone, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(wfull, NT_WCH);
+    bulk_g2s(wring, a.wimg, NT_WCH, wfull);              // chunk 0
+  }
+  if (warp == 0) tmem_alloc<128>(tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t img_u32 = smem_u32(img);
+  constexpr uint32_t idesc = umma_idesc(2, 128, 64);
+  const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
+              *s_vel2 = svec + 320, *s_wv = svec + 384;
+  uint32_t mph = 0;
+  int wpos = 0;                                          // weight chunks consumed so far (ring position)
+  // publish the A chunk, run its 12 MMAs against weight chunk `wchunk` (already requested), request `wnext`
+  auto run_chunk = [&](uint32_t dcol, bool first, int wnext) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      const int slot = wpos & 1;
+      mbar_wait(wfull + slot, (wpos >> 1) & 1);
+      tc_fence_after();
+      const uint32_t wb = smem_u32(wring + slot * NT_WCH);
+      const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
+                     umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
+      umma_commit(mdone);
+    }
+    mbar_wait_warp(mdone, mph);
+    mph ^= 1;
+    tc_fence_after();
+    ++wpos;
+    if (tid == 0 && wnext >= 0) {                        // the slot the finished chunk before this one used is free
+      const int slot = wpos & 1;
+      mbar_arrive_expect_tx(wfull + slot, NT_WCH);
+      bulk_g2s(wring + slot * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + slot);
+    }
+  };
+  // NOTE on the ring: chunk k's weights must be in flight before run_chunk(k) waits for them.  Chunk 0 is
+  // requested in the prologue; run_chunk(k) requests chunk k+1 AFTER the MMAs of chunk k completed, i.e. the
+  // request for k+1 overlaps the building of A chunk k+1 (the other slot holds chunk k, now dead).
+
+  const int n = blockIdx.x * NT_TILE + tid;
+  const bool valid = n < a.R;
+  const size_t row = valid ? (size_t)n : 0;
+  float den = (float)a.N, den2 = (float)a.N;
+  if (a.mask && valid) {
+    float ms = 0.f;
+    const float* mr = a.mask + row * a.N;
+    for (int j = 0; j < a.N; ++j) ms += mr[j];
+    den = ms + 1e-8f;      // layers.py:123
+    den2 = ms + 1e-10f;    // layers.py:221
+  }
+  const float inv_den = 1.0f / den;
+  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0;
+  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
+  int wc = 0;                                            // weight chunk of the next run_chunk
+
+  // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256
+  float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float s[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
+      }
+      float vals[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
+        vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
+        const float w = s_wv[c * 32 + u * 4 + i];
+        dv0 = fmaf(w, s[3 * i], dv0); dv1 = fmaf(w, s[3 * i + 1], dv1); dv2 = fmaf(w, s[3 * i + 2], dv2);
+      }
+      nt_store_unit(img, tid, u, vals);
+    }
+    ++wc;
+    run_chunk(D0, c == 0, wc);
+  }
+  // ---------------- post2: h_p1 = silu(tp1 + b)  -> D1
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32];
+    tmem_ld32(lane_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float vals[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vals[i] = siluf_(v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]);
+      nt_store_unit(img, tid, u, vals);
+    }
+    ++wc;
+    run_chunk(D1, c == 0, wc);
+  }
+  // ---------------- node0 over [h | h_e | h_comb] (layers.py:142-151) -> D0
+  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
+  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
+#pragma unroll 1
+  for (int c = 0; c < 12; ++c) {
+    if (c < 10) {
+      const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 t4 = valid ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
+        nt_store_unit(img, tid, u, vals);
+      }
+    } else {
+      float v[32];
+      tmem_ld32(lane_addr + 64 + (c - 10) * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float vals[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vals[i] = spatial ? siluf_(v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i]) : 0.f;
+        nt_store_unit(img, tid, u, vals);
+      }
+    }
+    ++wc;
+    run_chunk(D0, c == 0, wc);
+  }
+  // ---------------- node2: n1 = silu(t1 + b) -> D1
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32];
+    tmem_ld32(lane_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float vals[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vals[i] = siluf_(v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]);
+      nt_store_unit(img, tid, u, vals);
+    }
+    ++wc;
+    run_chunk(D1, c == 0, (upd && hv) ? wc : (c == 0 ? wc : -1));
+  }
+  // ---------------- h' = h + silu(t2 + b)  (layers.py:150); velocity gate MLP on h' (layers.py:184-186) -> D0
+  float y = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32];
+    tmem_ld32(lane_addr + 64 + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 h4 = valid ? __ldg(hp + c * 8 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
+      float vals[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vals[i] = hin[i] + siluf_(v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]);
+      if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      if (upd && hv) nt_store_unit(img, tid, u, vals);
+    }
+    if (upd && hv) {
+      ++wc;
+      run_chunk(D0, c == 0, c == 0 ? wc : -1);
+    }
+  }
+  if (upd && hv) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) y = fmaf(siluf_(v[k] + s_bv1[c * 32 + k]), s_vel2[c * 32 + k], y);
+    }
+  }
+  // ---------------- velocity / position update (layers.py:218-232)
+  if (valid) {
+    const float* xr = a.x + row * 3;
+    if (!upd) {
+      a.x_out[row * 3] = xr[0]; a.x_out[row * 3 + 1] = xr[1]; a.x_out[row * 3 + 2] = xr[2];
+      if (a.v && a.v_out) { a.v_out[row * 3] = a.v[row * 3]; a.v_out[row * 3 + 1] = a.v[row * 3 + 1]; a.v_out[row * 3 + 2] = a.v[row * 3 + 2]; }
+    } else {
+      float vn0 = spatial ? dv0 / den2 : 0.f, vn1 = spatial ? dv1 / den2 : 0.f, vn2 = spatial ? dv2 / den2 : 0.f;
+      if (hv) {
+        const float gate = 2.0f * sigmoidf_(y);
+        vn0 = fmaf(gate, a.v[row * 3], vn0); vn1 = fmaf(gate, a.v[row * 3 + 1], vn1); vn2 = fmaf(gate, a.v[row * 3 + 2], vn2);
+      }
+      a.v_out[row * 3] = vn0; a.v_out[row * 3 + 1] = vn1; a.v_out[row * 3 + 2] = vn2;
+      a.x_out[row * 3] = xr[0] + vn0; a.x_out[row * 3 + 1] = xr[1] + vn1; a.x_out[row * 3 + 2] = xr[2] + vn2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+bool tc_node_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
+
+int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
+                 const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
+                 cudaStream_t st) {
+  uint8_t* wimg = (uint8_t*)wscratch;
+  k_node_w_prep<<<(NTW_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg);
+  NodeFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
+  a.h = h; a.x = x; a.v = v; a.mask = mask; a.ssum = sv.ssum; a.he = sv.he; a.wimg = wimg;
+  a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
+  a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
+  a.h_out = h_out; a.x_out = x_out; a.v_out = v_out;
+  const size_t smem = 2 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
+  static bool attr = false;
+  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_node_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  k_tc_node_post<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sake

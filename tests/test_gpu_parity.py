@@ -196,7 +196,9 @@ def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
     e1, f1, l1, g1, gd1 = outs[engine]
     etol, ftol, gtol = (1e-5, 1e-4, 2e-3) if engine in ("tf32x3", "f16x2") else (2e-2, 5e-2, 1e-1)
     assert torch.isfinite(e1).all() and torch.isfinite(f1).all() and torch.isfinite(g1).all()
-    assert ((e1 - e0).abs() / e0.abs().clamp_min(1e-3)).max().item() < etol
+    # relative to max(|E|, 0.1): a molecule whose atom terms (O(1) each) cancel to |E| ~ 0.03 carries the
+    # absolute fp32 rounding of the sum (a few 1e-7), which is not a relative error of the engine
+    assert ((e1 - e0).abs() / e0.abs().clamp_min(0.1)).max().item() < etol
     assert (f1 - f0).abs().max().item() < ftol * max(1.0, f0.abs().max().item() if engine == "bf16" else 1.0)
     for k in gd0:
         scale = max(float(gd0[k].abs().max()), 1e-6)
@@ -230,7 +232,9 @@ def test_small_gradient_scale_and_large_features(engine, wscale):
             e = model.energy(params, T(h), xx)
             (g,) = torch.autograd.grad((e * scale).sum(), xx)
             assert torch.isfinite(g).all() and torch.isfinite(e).all()
-            erel = ((e.cpu().double() - e0).abs() / e0.abs().clamp_min(1e-3)).max().item()
+            # relative to the batch's energy scale: single molecules whose atom terms cancel (|E| ~ 1e-3)
+            # would turn absolute fp32 rounding into an arbitrary relative number
+            erel = (e.cpu().double() - e0).abs().max().item() / max(1.0, e0.abs().max().item())
             ferr = (-g.cpu().double() / scale - f0).abs().max().item() / fmax
             errs[(eng, scale)] = (erel, ferr)
     for scale in (1.0, 1e-6):
