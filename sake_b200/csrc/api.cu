@@ -44,6 +44,13 @@ static int make_dims(const SakeDims* s, Dims* d) {
   return 0;
 }
 
+// SAKE_NODE_TC=0 keeps the CUDA-core per-node kernels under the tcgen05 engines (A/B diagnostics)
+static bool node_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SAKE_NODE_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 static int resolve_engine(const SakeDims* s, const Dims& d) {
   int e = s->engine;
   if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_F16X2 : SAKE_ENGINE_FP32;
@@ -82,7 +89,7 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge) {
   return s;
 }
 
-struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, nodew, total; };
+struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, nodew, noded, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -116,6 +123,8 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_node_dw_scratch_bytes(d));
   L.nodew = o;
   if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d)) o += align_up(tc_node_w_bytes());
+  L.noded = o;
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && for_backward) o += align_up(tc_node_bwd_scratch_bytes(d));
   L.total = o + 256;
   return L;
 }
@@ -181,7 +190,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_fwd(d, *params, x, mask, sv, (char*)scratch + SL.tc, engine, st))) return rc;
   }
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d))
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && node_tc_enabled())
     return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, (char*)scratch + SL.nodew, st);
   return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
 }
@@ -213,8 +222,14 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
-  if ((rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st)))
-    return rc;
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && node_tc_enabled()) {
+    if ((rc = gen_node_wt(d, *params, sc, st))) return rc;     // k_node_pre_bwd still reads the transposed copies
+    rc = tc_node_post_bwd(d, *params, h, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, b + SL.nodew,
+                          b + SL.noded, st);
+  }
+  else
+    rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st);
+  if (rc) return rc;
   XtgList xl;
   if (sc.nbuf && (rc = tc_node_dw(d, *grads, sc, xl, st))) return rc;
   float* gWx = grads ? grads->x_mixing_kernel : nullptr;

@@ -256,7 +256,13 @@ int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
 // tc_node.cu: per-node tail of the layer on the tensor cores (H = 64, A = 4)
 bool tc_node_supported(const Dims& d);
+int gen_node_wt(const Dims& d, const SakeLayerParams& p, const BwdScratch& sc, cudaStream_t st);
 size_t tc_node_w_bytes();
+size_t tc_node_bwd_scratch_bytes(const Dims& d);
+int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* v, const float* mask,
+                     const Saved& sv, const float* dh_out, const float* dx_out, const float* dv_out, float* dh, float* dx,
+                     float* dv, const SakeLayerGrads* g, const BwdScratch& sc, void* wscratch, void* nscratch,
+                     cudaStream_t st);
 int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st);

@@ -924,6 +924,15 @@ static SakeLayerGrads null_grads() {
   return g;
 }
 
+// transposed copies of the node-level weights (k_node_pre_bwd reads mlp_inT / w1hT from them)
+int gen_node_wt(const Dims& d, const SakeLayerParams& p, const BwdScratch& sc, cudaStream_t st) {
+  const size_t nwt = node_wt_floats(d);
+  k_node_wt<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(d, p, sc.nodeWT);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
                       const float* mask, const Saved& sv, const float* dh_out, const float* dx_out,
                       const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,

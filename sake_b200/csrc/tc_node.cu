@@ -20,25 +20,40 @@ constexpr int NT_IMG = NT_TILE * 128;        // one split of the A chunk image (
 constexpr int NT_WCH = 2 * 64 * 128;         // one weight chunk: {hi, lo} x 64 output rows x 128 B (16 KB)
 // chunk index of every matrix inside the weight image
 constexpr int NTW_POST0 = 0, NTW_POST2 = 8, NTW_NODE0 = 10, NTW_NODE2 = 22, NTW_VEL0 = 24, NTW_CHUNKS = 26;
+// backward (W^T g products): B rows = INPUT features of the layer, K = its outputs; 64-row blocks x 2 K-chunks
+constexpr int NTB_VEL0T = 26, NTB_NODE2T = 28, NTB_NODE0T = 30, NTB_POST2T = 42, NTB_POST0T = 44, NTB_CHUNKS = 52;
 constexpr int NT_VEC = 64 * 6 + 256;         // b_p1 b_p2 b_n1 b_n2 b_v1 vel2 | v_mixing
 
-size_t tc_node_w_bytes() { return (size_t)NTW_CHUNKS * NT_WCH + 256; }
+size_t tc_node_w_bytes() { return (size_t)NTB_CHUNKS * NT_WCH + 256; }
 
 // weight image: chunk c = K rows [32c', 32c'+32) of its matrix W[in][64]; B operand rows = outputs
-__global__ void k_node_w_prep(const SakeLayerParams p, uint8_t* __restrict__ img) {
+__global__ void k_node_w_prep(const SakeLayerParams p, uint8_t* __restrict__ img, int nchunks) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= NTW_CHUNKS * 64 * 8) return;
+  if (t >= nchunks * 64 * 8) return;
   const int chunk = t / (64 * 8), o = (t / 8) % 64, u = t % 8;
-  const float* W;
-  int c0;
-  if (chunk < NTW_POST2) { W = p.post0_kernel; c0 = chunk; }
-  else if (chunk < NTW_NODE0) { W = p.post2_kernel; c0 = chunk - NTW_POST2; }
-  else if (chunk < NTW_NODE2) { W = p.node0_kernel; c0 = chunk - NTW_NODE0; }
-  else if (chunk < NTW_VEL0) { W = p.node2_kernel; c0 = chunk - NTW_NODE2; }
-  else { W = p.vel0_kernel; c0 = chunk - NTW_VEL0; }
   float vals[4];
+  if (chunk < NTW_CHUNKS) {                                // forward: element (o, k) = W[k][o]
+    const float* W;
+    int c0;
+    if (chunk < NTW_POST2) { W = p.post0_kernel; c0 = chunk; }
+    else if (chunk < NTW_NODE0) { W = p.post2_kernel; c0 = chunk - NTW_POST2; }
+    else if (chunk < NTW_NODE2) { W = p.node0_kernel; c0 = chunk - NTW_NODE0; }
+    else if (chunk < NTW_VEL0) { W = p.node2_kernel; c0 = chunk - NTW_NODE2; }
+    else { W = p.vel0_kernel; c0 = chunk - NTW_VEL0; }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) vals[i] = W ? W[(size_t)(c0 * 32 + u * 4 + i) * 64 + o] : 0.f;
+    for (int i = 0; i < 4; ++i) vals[i] = W ? W[(size_t)(c0 * 32 + u * 4 + i) * 64 + o] : 0.f;
+  } else {                                                 // backward: row r = input feature, element (r, k) = W[r][k]
+    const float* W;
+    int c0;
+    if (chunk < NTB_NODE2T) { W = p.vel0_kernel; c0 = chunk - NTB_VEL0T; }
+    else if (chunk < NTB_NODE0T) { W = p.node2_kernel; c0 = chunk - NTB_NODE2T; }
+    else if (chunk < NTB_POST2T) { W = p.node0_kernel; c0 = chunk - NTB_NODE0T; }
+    else if (chunk < NTB_POST0T) { W = p.post2_kernel; c0 = chunk - NTB_POST2T; }
+    else { W = p.post0_kernel; c0 = chunk - NTB_POST0T; }
+    const int blk = c0 >> 1, kc = c0 & 1;                  // 64-row block, K chunk
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vals[i] = W ? W[(size_t)(blk * 64 + o) * 64 + kc * 32 + u * 4 + i] : 0.f;
+  }
   uint8_t* base = img + (size_t)chunk * NT_WCH;
   const uint32_t off = sw128_offset((uint32_t)o, (uint32_t)u);
   float4 hi, lo;
@@ -286,13 +301,490 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
   if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
+// =================================================================================================
+// backward of the per-node tail (VJP of everything k_tc_node_post computes; replaces k_node_post_bwd):
+//   recompute the forward (same chunk GEMMs), stash the four/five silu' vectors of the atom in a global
+//   scratch row, then walk the chain back: velocity gate -> node_mlp -> [dh | g_he | g_hcomb] -> post_norm_mlp
+//   -> g_nrm -> T = d(loss)/d(ssum) (+ the v_mixing path), row maximum of |T| for the fp16-split mix kernel.
+//   The W^T g products use the row-block images NTB_*: D[128 x 64] = G[128 x 64] * W[64-row block][64]^T.
+//   Training additionally writes the per-atom record (nbuf, layout NB_* of generic_bwd.cu) that the batched
+//   weight-gradient contractions read.
+// =================================================================================================
+enum { NB_N1 = 0, NB_GT2 = 64, NB_CAT = 128, NB_GT1 = 512, NB_HP1 = 576, NB_GTP2 = 640, NB_GTP1 = 704, NB_NRM = 768,
+       NB_HOUT = 1024, NB_GTV = 1088, NB_AV = 1152, NB_GY = 1216, NB_LD = 1232 };
+constexpr int ND_LD = 320;                   // stash row: silu'(tp1) silu'(tp2) silu'(t1) silu'(t2) silu'(tv)
+
+struct NodeBwdArgs {
+  int R, N, update, has_v, spatial;
+  const float *h, *v, *mask, *ssum, *he, *dh_out, *dx_out, *dv_out;
+  const uint8_t* wimg;
+  const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
+  float *dh, *dx, *dv, *T, *ghe, *tmax;
+  float *nder, *qv, *nbuf;                   // stash [R,320]; g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
+};
+
+__device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     // 32 floats of a row block
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<float4*>(dst + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
+}
+
+__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024_shared(smem_raw);
+  uint8_t* imgA = base;                                  // A image, K chunk 0 (or the serial chunk buffer): 32 KB
+  uint8_t* imgB = base + 2 * NT_IMG;                     // A image, K chunk 1: 32 KB
+  uint8_t* wring = imgB + 2 * NT_IMG;                    // 2 weight chunk slots: 32 KB
+  float* svec = reinterpret_cast<float*>(wring + 2 * NT_WCH);
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(svec + NT_VEC);   // [2]
+  uint64_t* mdone = wfull + 2;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(mdone + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
+  for (int t = tid; t < NT_VEC; t += NT_TILE) {
+    const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
+    svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(wfull, 1); mbar_init(wfull + 1, 1); mbar_init(mdone, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(wfull, NT_WCH);
+    bulk_g2s(wring, a.wimg, NT_WCH, wfull);              // chunk 0
+  }
+  if (warp == 0) tmem_alloc<128>(tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t imgA_u32 = smem_u32(imgA), imgB_u32 = smem_u32(imgB);
+  constexpr uint32_t idesc = umma_idesc(2, 128, 64);
+  const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
+              *s_vel2 = svec + 320, *s_wv = svec + 384;
+  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
+  // order in which the weight chunks are consumed (the image holds them in this order, with optional parts)
+  auto next_w = [&](int k) {
+    int nx = k + 1;
+    if (nx == NTW_VEL0 && !uv) nx = NTB_NODE2T;          // no velocity gate: skip vel0 and vel0^T
+    if (nx == NTB_POST2T && !spatial) nx = -1;
+    if (nx >= NTB_CHUNKS) nx = -1;
+    return nx;
+  };
+  uint32_t mph = 0;
+  int wpos = 0, wc = 0;                                  // ring position, current weight chunk
+  auto run_chunk = [&](uint32_t img_u32, uint32_t dcol, bool first) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      const int slot = wpos & 1;
+      mbar_wait(wfull + slot, (wpos >> 1) & 1);
+      tc_fence_after();
+      const uint32_t wb = smem_u32(wring + slot * NT_WCH);
+      const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
+                     umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
+      umma_commit(mdone);
+    }
+    mbar_wait_warp(mdone, mph);
+    mph ^= 1;
+    tc_fence_after();
+    ++wpos;
+    wc = next_w(wc);
+    if (tid == 0 && wc >= 0) {
+      const int slot = wpos & 1;
+      mbar_arrive_expect_tx(wfull + slot, NT_WCH);
+      bulk_g2s(wring + slot * NT_WCH, a.wimg + (size_t)wc * NT_WCH, NT_WCH, wfull + slot);
+    }
+  };
+  // NOTE: run_chunk(k) requests chunk next(k) AFTER the MMAs of k completed, into the slot chunk prev(k) used.
+  // The prologue requested chunk 0 only, so the request issued inside run_chunk(k) is for the chunk consumed by
+  // the NEXT run_chunk: wc always names the chunk the next run_chunk will consume.
+
+  const int n = blockIdx.x * NT_TILE + tid;
+  const bool valid = n < a.R;
+  const size_t row = valid ? (size_t)n : 0;
+  float den = (float)a.N, den2 = (float)a.N;
+  if (a.mask && valid) {
+    float ms = 0.f;
+    const float* mr = a.mask + row * a.N;
+    for (int j = 0; j < a.N; ++j) ms += mr[j];
+    den = ms + 1e-8f;
+    den2 = ms + 1e-10f;
+  }
+  const float inv_den = 1.0f / den;
+  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
+  float* nd = a.nder + row * ND_LD;
+  float* nb = a.nbuf ? a.nbuf + row * NB_LD : nullptr;
+  const bool rec = nb != nullptr && valid;
+  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
+  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
+
+  // =============================== forward recompute ===============================
+  // post0 (K = 256, serial chunks through imgA) -> D0 = tp1
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float s[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
+      }
+      float vals[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
+        vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
+      }
+      if (rec && spatial) *reinterpret_cast<float4*>(nb + NB_NRM + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      nt_store_unit(imgA, tid, u, vals);
+    }
+    run_chunk(imgA_u32, D0, c == 0);
+  }
+  // hp1 = silu(tp1 + b), stash silu'; post2 -> D1 = tp2
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32], dv_[32];
+    tmem_ld32(lane_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bp1[c * 32 + k]; v[k] = siluf_(z); dv_[k] = dsiluf_(z); }
+    if (valid) st64(nd, c, dv_);
+    if (rec && spatial) st64(nb + NB_HP1, c, v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+  }
+  run_chunk(imgA_u32, D1, true);
+  run_chunk(imgB_u32, D1, false);
+  // node0 over [h | h_e | h_comb] (serial chunks) -> D0 = t1
+#pragma unroll 1
+  for (int c = 0; c < 12; ++c) {
+    if (c < 10) {
+      const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 t4 = valid ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
+        if (rec) *reinterpret_cast<float4*>(nb + NB_CAT + c * 32 + 4 * u) = t4;
+        nt_store_unit(imgA, tid, u, vals);
+      }
+    } else {
+      float v[32], dv_[32];
+      tmem_ld32(lane_addr + 64 + (c - 10) * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float z = v[k] + s_bp2[(c - 10) * 32 + k];
+        v[k] = spatial ? siluf_(z) : 0.f;
+        dv_[k] = spatial ? dsiluf_(z) : 0.f;
+      }
+      if (valid) st64(nd + 64, c - 10, dv_);
+      if (rec) st64(nb + NB_CAT + 320, c - 10, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nt_store_unit(imgA, tid, u, v + 4 * u);
+    }
+    run_chunk(imgA_u32, D0, c == 0);
+  }
+  // n1 = silu(t1 + b), stash silu'; node2 -> D1 = t2
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32], dv_[32];
+    tmem_ld32(lane_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bn1[c * 32 + k]; v[k] = siluf_(z); dv_[k] = dsiluf_(z); }
+    if (valid) st64(nd + 128, c, dv_);
+    if (rec) st64(nb + NB_N1, c, v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+  }
+  run_chunk(imgA_u32, D1, true);
+  run_chunk(imgB_u32, D1, false);
+  // stash silu'(t2); h' = h + silu(t2 + b); velocity gate MLP on h' -> D0 = tv, y = av . vel2
+  float y = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32], dv_[32];
+    tmem_ld32(lane_addr + 64 + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 h4 = valid ? __ldg(hp + c * 8 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i];
+        dv_[4 * u + i] = dsiluf_(z);
+        v[4 * u + i] = hin[i] + siluf_(z);
+      }
+    }
+    if (valid) st64(nd + 192, c, dv_);
+    if (uv) {
+      if (rec) st64(nb + NB_HOUT, c, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+    }
+  }
+  if (uv) {
+    run_chunk(imgA_u32, D0, true);
+    run_chunk(imgB_u32, D0, false);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float v[32], dv_[32];
+      tmem_ld32(lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float z = v[k] + s_bv1[c * 32 + k];
+        v[k] = siluf_(z);
+        dv_[k] = dsiluf_(z);
+        y = fmaf(v[k], s_vel2[c * 32 + k], y);
+      }
+      if (valid) st64(nd + 256, c, dv_);
+      if (rec) st64(nb + NB_AV, c, v);
+    }
+  }
+  // =============================== velocity / position update backward (layers.py:226-232) ===============================
+  float gdv0 = 0.f, gdv1 = 0.f, gdv2 = 0.f, gy = 0.f;
+  if (valid) {
+    const float dxo0 = a.dx_out ? a.dx_out[row * 3] : 0.f, dxo1 = a.dx_out ? a.dx_out[row * 3 + 1] : 0.f,
+                dxo2 = a.dx_out ? a.dx_out[row * 3 + 2] : 0.f;
+    const float dvo0 = a.dv_out ? a.dv_out[row * 3] : 0.f, dvo1 = a.dv_out ? a.dv_out[row * 3 + 1] : 0.f,
+                dvo2 = a.dv_out ? a.dv_out[row * 3 + 2] : 0.f;
+    a.dx[row * 3] = dxo0; a.dx[row * 3 + 1] = dxo1; a.dx[row * 3 + 2] = dxo2;          // x' = x + v'
+    if (upd) {
+      gdv0 = dvo0 + dxo0; gdv1 = dvo1 + dxo1; gdv2 = dvo2 + dxo2;                        // cotangent of v'
+      if (hv) {
+        const float gt = 2.0f * sigmoidf_(y);
+        const float* vv = a.v + row * 3;
+        const float ggate = gdv0 * vv[0] + gdv1 * vv[1] + gdv2 * vv[2];
+        gy = ggate * gt * (1.0f - 0.5f * gt);
+        if (a.dv) { a.dv[row * 3] = gt * gdv0; a.dv[row * 3 + 1] = gt * gdv1; a.dv[row * 3 + 2] = gt * gdv2; }
+      }
+    } else if (a.dv && hv) {
+      a.dv[row * 3] = dvo0; a.dv[row * 3 + 1] = dvo1; a.dv[row * 3 + 2] = dvo2;          // v passes through
+    }
+    if (rec && uv) nb[NB_GY] = gy;
+    if (a.qv) *reinterpret_cast<float4*>(a.qv + row * 4) = make_float4(gdv0 / den2, gdv1 / den2, gdv2 / den2, 0.f);
+  }
+  // =============================== backward chain ===============================
+  float gho[64];                                         // cotangent of h' (dh_out + velocity-gate path)
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(a.dh_out + row * 64) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gho[4 * u] = t4.x; gho[4 * u + 1] = t4.y; gho[4 * u + 2] = t4.z; gho[4 * u + 3] = t4.w;
+  }
+  if (uv) {
+    // g_tv = vel2 * g_y * silu'(tv);  g_h' += g_tv W_v1^T
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float gtv[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 256 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gtv[4 * u] = s_vel2[c * 32 + 4 * u] * gy * d4.x; gtv[4 * u + 1] = s_vel2[c * 32 + 4 * u + 1] * gy * d4.y;
+        gtv[4 * u + 2] = s_vel2[c * 32 + 4 * u + 2] * gy * d4.z; gtv[4 * u + 3] = s_vel2[c * 32 + 4 * u + 3] * gy * d4.w;
+      }
+      if (rec) st64(nb + NB_GTV, c, gtv);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, gtv + 4 * u);
+    }
+    run_chunk(imgA_u32, D0, true);
+    run_chunk(imgB_u32, D0, false);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) gho[c * 32 + k] += v[k];
+    }
+  }
+  // g_t2 = g_h' * silu'(t2);  g_t1 = (g_t2 W_n2^T) * silu'(t1)
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float g2[32];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 192 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g2[4 * u] = gho[c * 32 + 4 * u] * d4.x; g2[4 * u + 1] = gho[c * 32 + 4 * u + 1] * d4.y;
+      g2[4 * u + 2] = gho[c * 32 + 4 * u + 2] * d4.z; g2[4 * u + 3] = gho[c * 32 + 4 * u + 3] * d4.w;
+    }
+    if (rec) st64(nb + NB_GT2, c, g2);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, g2 + 4 * u);
+  }
+  run_chunk(imgA_u32, D1, true);
+  run_chunk(imgB_u32, D1, false);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    float v[32];
+    tmem_ld32(lane_addr + 64 + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 128 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
+    }
+    if (rec) st64(nb + NB_GT1, c, v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+  }
+  // g_cat = g_t1 W_n1^T : six 64-row blocks [dh | g_he (4 blocks) | g_hcomb]; the g_t1 image stays in place
+  float gp2[64];                                         // g_tp2 = g_hcomb * silu'(tp2)
+#pragma unroll 1
+  for (int b = 0; b < 6; ++b) {
+    const uint32_t D = (b & 1) ? D1 : D0;
+    run_chunk(imgA_u32, D, true);
+    run_chunk(imgB_u32, D, false);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(lane_addr + (b & 1) * 64 + c * 32, v);
+      tmem_ld_wait();
+      if (b == 0) {
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] += c == 0 ? gho[k] : gho[32 + k];
+          st64(a.dh + row * 64, c, v);
+        }
+      } else if (b < 5) {
+        if (valid) st64(a.ghe + row * 256 + (b - 1) * 64, c, v);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 64 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float g0 = v[4 * u] * d4.x, g1 = v[4 * u + 1] * d4.y, g2 = v[4 * u + 2] * d4.z, g3 = v[4 * u + 3] * d4.w;
+          if (c == 0) { gp2[4 * u] = g0; gp2[4 * u + 1] = g1; gp2[4 * u + 2] = g2; gp2[4 * u + 3] = g3; }
+          else { gp2[32 + 4 * u] = g0; gp2[32 + 4 * u + 1] = g1; gp2[32 + 4 * u + 2] = g2; gp2[32 + 4 * u + 3] = g3; }
+        }
+      }
+    }
+  }
+  float tmx = 0.f;
+  float4* Trow = reinterpret_cast<float4*>(a.T) + row * 256;
+  if (spatial) {
+    // g_tp1 = (g_tp2 W_p2^T) * silu'(tp1)
+    if (rec) { st64(nb + NB_GTP2, 0, gp2); st64(nb + NB_GTP2, 1, gp2 + 32); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { nt_store_unit(imgA, tid, u, gp2 + 4 * u); nt_store_unit(imgB, tid, u, gp2 + 32 + 4 * u); }
+    run_chunk(imgA_u32, D0, true);
+    run_chunk(imgB_u32, D0, false);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
+      }
+      if (rec) st64(nb + NB_GTP1, c, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+    }
+    // g_nrm = g_tp1 W_p1^T (four 64-row blocks);  T[c][d] = 2 ssum[c][d] g_nrm[c] / den^2 + Wv[c] g_dv[d] / den2
+    const float k2 = 2.0f * inv_den * inv_den, q0 = gdv0 / den2, q1 = gdv1 / den2, q2 = gdv2 / den2;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t D = (b & 1) ? D1 : D0;
+      run_chunk(imgA_u32, D, true);
+      run_chunk(imgB_u32, D, false);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(lane_addr + (b & 1) * 64 + c * 32, v);
+        tmem_ld_wait();
+        const int c0 = b * 64 + c * 32;
+        const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0) * 3);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float s[12];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float gk = k2 * v[4 * u + i], w = upd ? s_wv[c0 + 4 * u + i] : 0.f;
+            const float t0 = fmaf(w, q0, gk * s[3 * i]), t1 = fmaf(w, q1, gk * s[3 * i + 1]), t2 = fmaf(w, q2, gk * s[3 * i + 2]);
+            tmx = fmaxf(tmx, fmaxf(fabsf(t0), fmaxf(fabsf(t1), fabsf(t2))));
+            if (valid) Trow[c0 + 4 * u + i] = make_float4(t0, t1, t2, 0.f);
+          }
+        }
+      }
+    }
+  } else if (valid) {
+    for (int c = 0; c < 256; ++c) Trow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (valid) a.tmax[row] = tmx;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+// gWv[c] += sum_n sum_d ssum[n][c][d] * g_dv[n][d] / den2[n]     (layers.py:94,220-223; training only)
+__global__ void __launch_bounds__(256) k_wv_grad(int R, const float* __restrict__ ssum, const float* __restrict__ qv,
+                                                 float* __restrict__ gWv) {
+  const int c = threadIdx.x;
+  const int n0 = blockIdx.x * 64, n1 = min(R, n0 + 64);
+  float acc = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float4 q = *reinterpret_cast<const float4*>(qv + (size_t)n * 4);
+    const float* sp = ssum + ((size_t)n * 256 + c) * 3;
+    acc += sp[0] * q.x + sp[1] * q.y + sp[2] * q.z;
+  }
+  atomicAdd(gWv + c, acc);
+}
+
+size_t tc_node_bwd_scratch_bytes(const Dims& d) {
+  return align_up(sizeof(float) * (size_t)d.R * ND_LD) + align_up(sizeof(float) * (size_t)d.R * 4);
+}
+
+int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* v, const float* mask,
+                     const Saved& sv, const float* dh_out, const float* dx_out, const float* dv_out, float* dh, float* dx,
+                     float* dv, const SakeLayerGrads* g, const BwdScratch& sc, void* wscratch, void* nscratch,
+                     cudaStream_t st) {
+  uint8_t* wimg = (uint8_t*)wscratch;
+  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTB_CHUNKS);
+  NodeBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
+  a.h = h; a.v = v; a.mask = mask; a.ssum = sv.ssum; a.he = sv.he;
+  a.dh_out = dh_out; a.dx_out = dx_out; a.dv_out = dv_out; a.wimg = wimg;
+  a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
+  a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
+  a.dh = dh; a.dx = dx; a.dv = dv; a.T = sc.T; a.ghe = sc.ghe; a.tmax = sc.tmax;
+  a.nder = (float*)nscratch;
+  const bool wvg = g != nullptr && d.update && d.spatial;
+  a.qv = wvg ? (float*)((char*)nscratch + align_up(sizeof(float) * (size_t)d.R * ND_LD)) : nullptr;
+  a.nbuf = g ? sc.nbuf : nullptr;
+  const size_t smem = 4 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
+  static bool attr = false;
+  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_node_post_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, sv.ssum, a.qv, g->v_mixing_kernel);
+  note_launches(wvg ? 3 : 2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 bool tc_node_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
 
 int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st) {
   uint8_t* wimg = (uint8_t*)wscratch;
-  k_node_w_prep<<<(NTW_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg);
+  k_node_w_prep<<<(NTW_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTW_CHUNKS);
   NodeFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
