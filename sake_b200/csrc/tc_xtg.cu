@@ -261,16 +261,8 @@ __global__ void __launch_bounds__(128) k_xtg_reduce(const __grid_constant__ XtgB
   if (col >= a.NG || a.partial == nullptr) return;
   for (int row = threadIdx.x; row < a.out_rows + a.extra_rows; row += blockDim.x) {
     const float* pp = a.partial + (size_t)col * a.MXpad + row;
-    const size_t cs = (size_t)a.MXpad * a.NG;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;        // fixed order: deterministic; 8 independent loads in flight
-    int c = 0;
-    for (; c + 8 <= ncta; c += 8) {
-      const float v0 = pp[(c + 0) * cs], v1 = pp[(c + 1) * cs], v2 = pp[(c + 2) * cs], v3 = pp[(c + 3) * cs];
-      const float v4 = pp[(c + 4) * cs], v5 = pp[(c + 5) * cs], v6 = pp[(c + 6) * cs], v7 = pp[(c + 7) * cs];
-      s0 += v0 + v4; s1 += v1 + v5; s2 += v2 + v6; s3 += v3 + v7;
-    }
-    for (; c < ncta; ++c) s0 += pp[c * cs];
-    const float s = (s0 + s1) + (s2 + s3);
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += pp[(size_t)c * a.MXpad * a.NG];
     if (row < a.out_rows) {
       if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += s;
     } else if (col < a.extra_ld) {
