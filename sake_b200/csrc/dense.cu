@@ -4,7 +4,7 @@
 
 namespace sake {
 
-static constexpr int DR = 8;  // rows per CTA
+static constexpr int DR = 16;  // rows per CTA
 
 __global__ void __launch_bounds__(256) k_dense_fwd(long long rows, int in, int out, int act,
                                                    const float* __restrict__ x, const float* __restrict__ w,
@@ -36,9 +36,12 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
   extern __shared__ float sm[];
   float* xs = sm;             // [DR][in]
   float* gs = xs + DR * in;   // [DR][out]  cotangent of the pre-activation
+  float* ws = gs + DR * out;  // [in][out + 1]  weights, row stride padded: both access patterns are conflict-free
+  const int ldw = out + 1;
   const long long r0 = (long long)blockIdx.x * DR;
   const int nn = (int)min((long long)DR, rows - r0);
   for (int t = threadIdx.x; t < DR * in; t += blockDim.x) xs[t] = (t / in) < nn ? x[r0 * in + t] : 0.f;
+  for (int t = threadIdx.x; t < in * out; t += blockDim.x) ws[(t / out) * ldw + (t % out)] = w[t];
   __syncthreads();
   for (int t = threadIdx.x; t < DR * out; t += blockDim.x) {
     const int n = t / out, o = t % out;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
       gv = dy[r0 * out + t];
       if (act == 1) {
         float z = b ? b[o] : 0.f;
-        for (int f = 0; f < in; ++f) z = fmaf(xs[n * in + f], w[(size_t)f * out + o], z);
+        for (int f = 0; f < in; ++f) z = fmaf(xs[n * in + f], ws[f * ldw + o], z);
         gv *= dsiluf_(z);
       }
     }
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
     for (int t = threadIdx.x; t < nn * in; t += blockDim.x) {
       const int n = t / in, f = t % in;
       float acc = 0.f;
-      const float* wr = w + (size_t)f * out;
+      const float* wr = ws + f * ldw;
       for (int o = 0; o < out; ++o) acc = fmaf(wr[o], gs[n * out + o], acc);
       dx[r0 * in + t] = acc;
     }
@@ -93,7 +96,7 @@ int dense_fwd(long long rows, int in, int out, int act, const float* x, const fl
 int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
               const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
   if (rows == 0) return 0;
-  size_t smem = sizeof(float) * DR * (in + out);
+  size_t smem = sizeof(float) * (DR * (in + out) + (size_t)in * (out + 1));
   if (smem > 48 * 1024) { set_error("dense: features %d/%d too large", in, out); return SAKE_EUNSUPPORTED; }
   k_dense_bwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db);
   SAKE_CUDA_CHECK(cudaGetLastError());

@@ -86,6 +86,7 @@ __global__ void k_node_wt(Dims d, const SakeLayerParams p, float* __restrict__ b
   if (t < n6) { const int q = t / (2 * H), r = t % (2 * H); base[t] = p.mlp_out0_kernel[(size_t)r * H + q]; return; }
 }
 
+constexpr int PRE_WROWS = 16;     // k_node_pre_bwd: weight rows per staged chunk
 constexpr int BWD_WROWS = 16;     // weight rows per staged chunk (2 x 4 KB: two CTAs per SM still fit)
 size_t node_post_bwd_smem_bytes(const Dims& d) {
   return sizeof(float) * (NODES * (2 * d.C + 17 * d.H) + 8 * NODES + 64 + 2 * BWD_WROWS * 64);
@@ -851,23 +852,42 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) hs[t] = (t / H) < nn ? h[(size_t)r0 * H + t] : 0.f;
   __syncthreads();
   // dh[n][f] += sum_k Win[f][k] g_uj[k] + Win[H+f][k] g_ui[k] + sum_q W1[f][q] g_pj[q] + W1[H+f][q] g_pi[q]
-  for (int idx = threadIdx.x; idx < H * (NODES / 2); idx += blockDim.x) {
-    const int f = idx % H, n0 = (idx / H) * 2;
-    const float* ga = gp + n0 * NP;
-    const float* gb = ga + NP;
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float wj = wt.mlp_inT[(size_t)k * 2 * H + f], wi = wt.mlp_inT[(size_t)k * 2 * H + H + f];
-      a0 = fmaf(wj, ga[k], fmaf(wi, ga[Kp + k], a0));
-      a1 = fmaf(wj, gb[k], fmaf(wi, gb[Kp + k], a1));
+  if (blockDim.x == 256 && H == 64 && (reinterpret_cast<uintptr_t>(wt.mlp_inT) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(wt.w1hT) & 15) == 0) {
+    // four staged GEMMs over the blocks of the projection cotangent (the transposed copies are [rows][2H]:
+    // sender half in columns [0,H), receiver half in [H,2H))
+    float* wbuf = hs + NODES * H;                       // [2][PRE_WROWS][64]
+    float* acc = wbuf + 2 * PRE_WROWS * 64;             // [NODES][H]
+    for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) acc[t] = 0.f;
+    __syncthreads();
+    auto add = [&](int n, int o4, const float* a) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[n * H + o4 + i] += a[i];
+    };
+    node_gemm64(gp, NP, K, wt.mlp_inT, 2 * H, wbuf, PRE_WROWS, add);
+    node_gemm64(gp + Kp, NP, K, wt.mlp_inT + H, 2 * H, wbuf, PRE_WROWS, add);
+    node_gemm64(gp + 2 * Kp, NP, H, wt.w1hT, 2 * H, wbuf, PRE_WROWS, add);
+    node_gemm64(gp + 2 * Kp + H, NP, H, wt.w1hT + H, 2 * H, wbuf, PRE_WROWS, add);
+    for (int t = threadIdx.x; t < nn * H; t += blockDim.x) dh[(size_t)r0 * H + t] += acc[t];
+  } else {
+    for (int idx = threadIdx.x; idx < H * (NODES / 2); idx += blockDim.x) {
+      const int f = idx % H, n0 = (idx / H) * 2;
+      const float* ga = gp + n0 * NP;
+      const float* gb = ga + NP;
+      float a0 = 0.f, a1 = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float wj = wt.mlp_inT[(size_t)k * 2 * H + f], wi = wt.mlp_inT[(size_t)k * 2 * H + H + f];
+        a0 = fmaf(wj, ga[k], fmaf(wi, ga[Kp + k], a0));
+        a1 = fmaf(wj, gb[k], fmaf(wi, gb[Kp + k], a1));
+      }
+      for (int q = 0; q < H; ++q) {
+        const float vj = wt.w1hT[(size_t)q * 2 * H + f], vi = wt.w1hT[(size_t)q * 2 * H + H + f];
+        a0 = fmaf(vj, ga[2 * Kp + q], fmaf(vi, ga[2 * Kp + H + q], a0));
+        a1 = fmaf(vj, gb[2 * Kp + q], fmaf(vi, gb[2 * Kp + H + q], a1));
+      }
+      if (n0 < nn) dh[(size_t)(r0 + n0) * H + f] += a0;
+      if (n0 + 1 < nn) dh[(size_t)(r0 + n0 + 1) * H + f] += a1;
     }
-    for (int q = 0; q < H; ++q) {
-      const float vj = wt.w1hT[(size_t)q * 2 * H + f], vi = wt.w1hT[(size_t)q * 2 * H + H + f];
-      a0 = fmaf(vj, ga[2 * Kp + q], fmaf(vi, ga[2 * Kp + H + q], a0));
-      a1 = fmaf(vj, gb[2 * Kp + q], fmaf(vi, gb[2 * Kp + H + q], a1));
-    }
-    if (n0 < nn) dh[(size_t)(r0 + n0) * H + f] += a0;
-    if (n0 + 1 < nn) dh[(size_t)(r0 + n0 + 1) * H + f] += a1;
   }
   if (want_grads) {
     for (int t = threadIdx.x; t < H * K; t += blockDim.x) {
@@ -1066,7 +1086,7 @@ int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,
                      const BwdScratch& sc, cudaStream_t st) {
   int rc;
-  size_t smem = sizeof(float) * NODES * (d.NP + d.H);
+  size_t smem = sizeof(float) * (NODES * (d.NP + 2 * d.H) + 2 * PRE_WROWS * 64 + 16);
   if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
   k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, carve_node_wt(d, sc.nodeWT), h, sc.gproj, dh,
                                                                g ? *g : null_grads(), g != nullptr);
