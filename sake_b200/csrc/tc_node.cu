@@ -113,13 +113,19 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
               *s_vel2 = svec + 320, *s_wv = svec + 384;
   uint32_t mph = 0;
   int wpos = 0;                                          // weight chunks consumed so far (ring position)
-  // publish the A chunk, run its 12 MMAs against weight chunk `wchunk` (already requested), request `wnext`
+  // publish the A chunk and run its 12 MMAs against the current weight chunk.  Two-deep weight ring: the chunk
+  // of the NEXT run (`wnext`, -1: none) is requested at the start of this run — its slot held the chunk of the
+  // previous run, whose MMAs have completed — so a weight chunk always has a full round of lead time.
   auto run_chunk = [&](uint32_t dcol, bool first, int wnext) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       const int slot = wpos & 1;
+      if (wnext >= 0) {
+        mbar_arrive_expect_tx(wfull + (slot ^ 1), NT_WCH);
+        bulk_g2s(wring + (slot ^ 1) * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + (slot ^ 1));
+      }
       mbar_wait(wfull + slot, (wpos >> 1) & 1);
       tc_fence_after();
       const uint32_t wb = smem_u32(wring + slot * NT_WCH);
@@ -136,15 +142,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     mph ^= 1;
     tc_fence_after();
     ++wpos;
-    if (tid == 0 && wnext >= 0) {                        // the slot the finished chunk before this one used is free
-      const int slot = wpos & 1;
-      mbar_arrive_expect_tx(wfull + slot, NT_WCH);
-      bulk_g2s(wring + slot * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + slot);
-    }
   };
-  // NOTE on the ring: chunk k's weights must be in flight before run_chunk(k) waits for them.  Chunk 0 is
-  // requested in the prologue; run_chunk(k) requests chunk k+1 AFTER the MMAs of chunk k completed, i.e. the
-  // request for k+1 overlaps the building of A chunk k+1 (the other slot holds chunk k, now dead).
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < a.R;
@@ -376,8 +374,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    const int wnext = next_w(wc);
     if (tid == 0) {
       const int slot = wpos & 1;
+      if (wnext >= 0) {                                  // two-deep ring: request the NEXT run's chunk now (its slot
+        mbar_arrive_expect_tx(wfull + (slot ^ 1), NT_WCH);   // held the previous run's chunk, whose MMAs are complete)
+        bulk_g2s(wring + (slot ^ 1) * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + (slot ^ 1));
+      }
       mbar_wait(wfull + slot, (wpos >> 1) & 1);
       tc_fence_after();
       const uint32_t wb = smem_u32(wring + slot * NT_WCH);
@@ -394,16 +397,9 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     mph ^= 1;
     tc_fence_after();
     ++wpos;
-    wc = next_w(wc);
-    if (tid == 0 && wc >= 0) {
-      const int slot = wpos & 1;
-      mbar_arrive_expect_tx(wfull + slot, NT_WCH);
-      bulk_g2s(wring + slot * NT_WCH, a.wimg + (size_t)wc * NT_WCH, NT_WCH, wfull + slot);
-    }
+    wc = wnext;
   };
-  // NOTE: run_chunk(k) requests chunk next(k) AFTER the MMAs of k completed, into the slot chunk prev(k) used.
-  // The prologue requested chunk 0 only, so the request issued inside run_chunk(k) is for the chunk consumed by
-  // the NEXT run_chunk: wc always names the chunk the next run_chunk will consume.
+  // wc always names the chunk the next run_chunk will consume (chunk 0 is requested in the prologue)
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < a.R;
