@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--depth", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=16, help="molecules in the CPU-baseline sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", action="store_true",
+                    help="replay the step as a CUDA graph (per-kernel roofline timings then come from a separate eager pass)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not
     # get in the way: fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
@@ -233,6 +235,23 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    graph_prof = None
+    if args.graphs:
+        # per-kernel durations for the roofline: a short eager, profiled pass of the same steps (a graph replay
+        # makes no host calls, so the library's per-launch events cannot be recorded inside it)
+        R.profile_begin(64 * 3)
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            step()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_prof = (R.profile_collect(64 * 3), g0.elapsed_time(g1) / 3)
+        run.capture()
+        config["cuda_graph"] = f"step body replayed as one CUDA graph ({run.graph_launches} library launches per replay)"
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
 
     # ---- device-resident timed region -------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -256,6 +275,8 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = lib.sake_launch_count() - launches0
     prof = R.profile_collect(64 * args.steps)
+    if args.graphs:
+        launches += args.steps * run.graph_launches      # kernels inside the replayed graphs
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     tmax = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -301,6 +322,9 @@ def main():
     # ---- roofline of the dominant kernel (x_mixing GEMM family) ---------------------------------------
     sus, burst, hbm, how = measured_peaks()
     by_kind = {}
+    prof_step_ms = ms_step * args.steps
+    if graph_prof is not None:
+        prof, prof_step_ms = graph_prof[0], graph_prof[1] * 3
     for ms, kind, pairs in prof:
         d = by_kind.setdefault(kind, [0.0, 0, pairs])
         d[0] += ms
@@ -321,7 +345,7 @@ def main():
                     "traffic": traffic_table.get((args.workload, run.engine, kind_names.get(dom, str(dom)))),
                     "peak_source": f"bf16 dense sustained, {how} (MEASURED_PEAKS.json)",
                     "avg_launch_ms": avg_ms, "launches_timed": cnt, "algorithmic_flop_per_launch": FLOP_MIX * pairs,
-                    "share_of_step": {kind_names.get(k, str(k)): by_kind[k][0] / (ms_step * args.steps) for k in by_kind}}
+                    "share_of_step": {kind_names.get(k, str(k)): by_kind[k][0] / prof_step_ms for k in by_kind}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         val, dt, Bs = cpu_arm(args.workload, args.depth, 2, 1, args.cpu_sample)

@@ -160,22 +160,55 @@ class ModelRunner:
         self._dx_final = dx_out
 
     # -- the two driver closures ---------------------------------------------------------------------
-    def energy_forces_step(self):
-        """E[b] and F = -dE/dx for the resident batch (scripts/md17/run.py:46-58)."""
+    def _ef_body(self):
         self.forward()
         self._head(0)
         self.backward(False)
         torch.neg(self._dx_final, out=self.forces)
-        return self.energy, self.forces
 
-    def train_step(self, allreduce=None):
-        """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
-        optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
+    def _train_body(self):
         self.flat_grads.zero_()
         self.loss.zero_()
         self.forward()
         self._head(1)
         self.backward(True)
+
+    def capture(self):
+        """Record the enqueue-only part of a step (everything the library launches between the input copy and
+        the optimiser / result read) into a CUDA graph; later steps replay it with one launch.  All buffers are
+        preallocated and the library never synchronises, so the capture is exact.  The gradient all-reduce and
+        the Adam kernel (its step counter is a host argument) stay outside the graph.  Returns the number of
+        library launches one replay stands for."""
+        body = self._train_body if self.train else self._ef_body
+        for _ in range(2):                       # first-use work (function attributes) must not happen inside a capture
+            body()
+        torch.cuda.synchronize(self.dev)
+        n0 = lib.sake_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        self.graph_launches = int(lib.sake_launch_count() - n0)
+        self.graph, self.graph_replays = g, 0
+        return self.graph_launches
+
+    def _run_body(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+            self.graph_replays += 1
+        elif self.train:
+            self._train_body()
+        else:
+            self._ef_body()
+
+    def energy_forces_step(self):
+        """E[b] and F = -dE/dx for the resident batch (scripts/md17/run.py:46-58)."""
+        self._run_body()
+        return self.energy, self.forces
+
+    def train_step(self, allreduce=None):
+        """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
+        optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
+        self._run_body()
         scale = 1.0
         if allreduce is not None:
             scale = allreduce(self.flat_grads)

@@ -274,3 +274,37 @@ def test_full_size_properties(B, N, S, padded, n_min):
         e0, f0 = O.energy_and_forces(po, h[b, :n].cpu().double(), x[b, :n].cpu().double())
         assert abs(e[b].item() - e0.item()) < 1e-5 * max(1.0, abs(e0.item())), (b, e[b].item(), e0.item())
         assert (f[b, :n].cpu().double() - f0).abs().max().item() < 1e-4, b
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_cuda_graph_replay_matches_eager(train):
+    """ModelRunner.capture(): replaying the recorded step gives bit-identical energies / forces / gradients
+    (the library is enqueue-only on the caller's stream, SURVEY 8b 'CUDA-graph capturable')."""
+    import sake_b200
+    from sake_b200 import runner as R
+    import bench
+    B, N, S = 16, 21, 6
+    h, x, mask, am = synth.molecules(11, B, N, S, True, 5)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=2, engine="auto")
+    T = lambda a: torch.tensor(a, device="cuda")
+    y = torch.randn(B, device="cuda")
+    outs = []
+    for use_graph in (False, True):
+        run = R.ModelRunner(model, bench.init_params_cpu(2, S, 0), B, N, S, masked=True, train=train)
+        run.load_inputs(T(h), T(x), T(mask), T(am), y)
+        if use_graph:
+            assert run.capture() > 10
+        if train:
+            run.train_step()
+            run.load_inputs(T(h), T(x), T(mask), T(am), y)
+            loss = run.train_step().clone()
+            outs.append((loss, run.flat_params.clone()))
+        else:
+            e, f = run.energy_forces_step()
+            outs.append((e.clone(), f.clone()))
+    if train:
+        # capture() runs two un-applied warm-up bodies, parameters only move in train_step: same two Adam steps
+        assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-7)
+    else:
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
