@@ -246,21 +246,28 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int u = hb * 8 + q;
-        float vals[4] = {0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-          const float us[4] = {uj4[q].x + ui4[q].x, uj4[q].y + ui4[q].y, uj4[q].z + ui4[q].z, uj4[q].w + ui4[q].w};
+        // branch-free over the 4 channels: mu / beta are zero-padded beyond K (rho = 1) and so are the
+        // projections (u = 0), hence rho*u = 0 there; the three extra columns n, 1, t are patched in by a
+        // warp-uniform test per unit, not per element (per-element branches serialise the exp chains)
+        float vals[4];
+        const float us[4] = {uj4[q].x + ui4[q].x, uj4[q].y + ui4[q].y, uj4[q].z + ui4[q].z, uj4[q].w + ui4[q].w};
+        const float4 mu4 = *reinterpret_cast<const float4*>(s_mu + 4 * u);
+        const float4 be4 = *reinterpret_cast<const float4*>(s_beta + 4 * u);
+        const float mus[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, bes[4] = {be4.x, be4.y, be4.z, be4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float dm = tt - mus[i];
+          vals[i] = fexp_(-bes[i] * dm * dm) * us[i];
+        }
+        if (4 * u + 3 >= K && 4 * u <= K + 2) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int k = 4 * u + i;
-            if (k < K) {
-              const float dm = tt - s_mu[k];
-              vals[i] = fexp_(-s_beta[k] * dm * dm) * us[i];
-            } else if (k == K) vals[i] = nrm;
-            else if (k == K + 1) vals[i] = 1.0f;        // column sums for free in the dW contraction
-            else if (k == K + 2) vals[i] = tt;
+            vals[i] = k == K ? nrm : (k == K + 1 ? 1.0f : (k == K + 2 ? tt : vals[i]));   // 1: column sums for free in the dW contraction
           }
-          if (BWD && a.train) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         }
+        if (!valid) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; vals[3] = 0.f; }
+        if (BWD && a.train && valid) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         store_unit_tf32(img, pl, q, vals);
       }
       run_chunk(tcol + 0, sWA, hb, 64, idesc64);                           // Z1 -> cols [0,64)
@@ -457,22 +464,27 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int k0 = half * 32 + 4 * u;
-            float gu[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
+            float gu[4], wv[4];
             const float uj[4] = {uj4[u].x, uj4[u].y, uj4[u].z, uj4[u].w};
             const float ui[4] = {ui4[u].x, ui4[u].y, ui4[u].z, ui4[u].w};
+            const float4 mu4 = *reinterpret_cast<const float4*>(s_mu + k0);
+            const float4 be4 = *reinterpret_cast<const float4*>(s_beta + k0);
+            const float mus[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, bes[4] = {be4.x, be4.y, be4.z, be4.w};
+            // branch-free (zero-padded mu / beta / projections beyond K: w = 0, beta = 0); the columns >= K of
+            // gu are never read (k_pair_reduce writes zeros there); the distance column is picked per unit
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int k = k0 + i;
-              if (k < K) {
-                const float dm = tt - s_mu[k];
-                const float rho = fexp_(-s_beta[k] * dm * dm);
-                gu[i] = gg[4 * u + i] * rho;                                   // d/du
-                const float w = dm * rho * gg[4 * u + i] * (uj[i] + ui[i]);   // dm * rho * d/drho
-                wv[i] = w;
-                gt = fmaf(-2.0f * s_beta[k], w, gt);
-              } else if (k == K) {
-                gn = gg[4 * u + i];                                            // through the distance input of mlp_out[0]
-              }
+              const float dm = tt - mus[i];
+              const float rho = fexp_(-bes[i] * dm * dm);
+              gu[i] = gg[4 * u + i] * rho;                                   // d/du
+              const float w = dm * rho * gg[4 * u + i] * (uj[i] + ui[i]);   // dm * rho * d/drho
+              wv[i] = w;
+              gt = fmaf(-2.0f * bes[i], w, gt);
+            }
+            if (K >= k0 && K < k0 + 4) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (k0 + i == K) gn = gg[4 * u + i];                         // through the distance input of mlp_out[0]
             }
             if (k0 < 60) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 64 + k0) = make_float4(gu[0], gu[1], gu[2], gu[3]);
             if (a.train) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 128 + k0) = make_float4(wv[0], wv[1], wv[2], wv[3]);

@@ -21,6 +21,7 @@ class ModelRunner:
         self.masked, self.train, self.dev = masked, train, torch.device(device)
         self.lr, self.wd, self.max_delta, self.mean, self.std = lr, weight_decay, max_delta, mean, std
         self.step_count = 0
+        self.graphs, self.graph_replays, self.graph_launches = {}, 0, 0
         dev, f32 = self.dev, torch.float32
         # ---- one flat fp32 parameter vector (+ grads, Adam moments): one all-reduce bucket --------
         flat = flatten_tree(params)
@@ -173,13 +174,15 @@ class ModelRunner:
         self._head(1)
         self.backward(True)
 
-    def capture(self):
+    def capture(self, train=None):
         """Record the enqueue-only part of a step (everything the library launches between the input copy and
-        the optimiser / result read) into a CUDA graph; later steps replay it with one launch.  All buffers are
-        preallocated and the library never synchronises, so the capture is exact.  The gradient all-reduce and
-        the Adam kernel (its step counter is a host argument) stay outside the graph.  Returns the number of
-        library launches one replay stands for."""
-        body = self._train_body if self.train else self._ef_body
+        the optimiser / result read) into a CUDA graph; later steps of that kind replay it with one launch.
+        All buffers are preallocated and the library never synchronises, so the capture is exact.  The gradient
+        all-reduce and the Adam kernel (its step counter is a host argument) stay outside the graph.
+        `train`: which step to record (default: the runner's own mode).  Returns the number of library launches
+        one replay stands for."""
+        train = self.train if train is None else bool(train)
+        body = self._train_body if train else self._ef_body
         for _ in range(2):                       # first-use work (function attributes) must not happen inside a capture
             body()
         torch.cuda.synchronize(self.dev)
@@ -188,27 +191,28 @@ class ModelRunner:
         with torch.cuda.graph(g):
             body()
         self.graph_launches = int(lib.sake_launch_count() - n0)
-        self.graph, self.graph_replays = g, 0
+        self.graphs[train] = g
         return self.graph_launches
 
-    def _run_body(self):
-        if getattr(self, "graph", None) is not None:
-            self.graph.replay()
+    def _run_body(self, train):
+        g = self.graphs.get(train)
+        if g is not None:
+            g.replay()
             self.graph_replays += 1
-        elif self.train:
+        elif train:
             self._train_body()
         else:
             self._ef_body()
 
     def energy_forces_step(self):
         """E[b] and F = -dE/dx for the resident batch (scripts/md17/run.py:46-58)."""
-        self._run_body()
+        self._run_body(False)
         return self.energy, self.forces
 
     def train_step(self, allreduce=None):
         """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
         optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
-        self._run_body()
+        self._run_body(True)
         scale = 1.0
         if allreduce is not None:
             scale = allreduce(self.flat_grads)
