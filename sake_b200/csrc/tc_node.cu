@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < a.R;
-  const size_t row = valid ? (size_t)n : 0;
+  const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
   if (a.mask && valid) {
     float ms = 0.f;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       float s[12];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t4 = __ldg(sp + u * 3 + q);
         s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
       }
       float vals[4];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     for (int u = 0; u < 8; ++u) {
       float vals[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = siluf_(v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) vals[i] = fsilu_(v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]);
       nt_store_unit(img, tid, u, vals);
     }
     ++wc;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 t4 = valid ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t4 = __ldg(src + u);
         const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
         nt_store_unit(img, tid, u, vals);
       }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       for (int u = 0; u < 8; ++u) {
         float vals[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) vals[i] = spatial ? siluf_(v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i]) : 0.f;
+        for (int i = 0; i < 4; ++i) vals[i] = spatial ? fsilu_(v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i]) : 0.f;
         nt_store_unit(img, tid, u, vals);
       }
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     for (int u = 0; u < 8; ++u) {
       float vals[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = siluf_(v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) vals[i] = fsilu_(v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]);
       nt_store_unit(img, tid, u, vals);
     }
     ++wc;
@@ -255,11 +255,11 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 h4 = valid ? __ldg(hp + c * 8 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 h4 = __ldg(hp + c * 8 + u);
       const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
       float vals[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = hin[i] + siluf_(v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) vals[i] = hin[i] + fsilu_(v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]);
       if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       if (upd && hv) nt_store_unit(img, tid, u, vals);
     }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       tmem_ld32(lane_addr + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) y = fmaf(siluf_(v[k] + s_bv1[c * 32 + k]), s_vel2[c * 32 + k], y);
+      for (int k = 0; k < 32; ++k) y = fmaf(fsilu_(v[k] + s_bv1[c * 32 + k]), s_vel2[c * 32 + k], y);
     }
   }
   // ---------------- velocity / position update (layers.py:218-232)
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     } else {
       float vn0 = spatial ? dv0 / den2 : 0.f, vn1 = spatial ? dv1 / den2 : 0.f, vn2 = spatial ? dv2 / den2 : 0.f;
       if (hv) {
-        const float gate = 2.0f * sigmoidf_(y);
+        const float gate = 2.0f * fsigmoid_(y);
         vn0 = fmaf(gate, a.v[row * 3], vn0); vn1 = fmaf(gate, a.v[row * 3 + 1], vn1); vn2 = fmaf(gate, a.v[row * 3 + 2], vn2);
       }
       a.v_out[row * 3] = vn0; a.v_out[row * 3 + 1] = vn1; a.v_out[row * 3 + 2] = vn2;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < a.R;
-  const size_t row = valid ? (size_t)n : 0;
+  const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
   if (a.mask && valid) {
     float ms = 0.f;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
       float s[12];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t4 = __ldg(sp + u * 3 + q);
         s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
       }
       float vals[4];
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     tmem_ld32(lane_addr + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bp1[c * 32 + k]; v[k] = siluf_(z); dv_[k] = dsiluf_(z); }
+    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bp1[c * 32 + k]; v[k] = fsilu_(z); dv_[k] = fdsilu_(z); }
     if (valid) st64(nd, c, dv_);
     if (rec && spatial) st64(nb + NB_HP1, c, v);
 #pragma unroll
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
       const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 t4 = valid ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t4 = __ldg(src + u);
         const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
         if (rec) *reinterpret_cast<float4*>(nb + NB_CAT + c * 32 + 4 * u) = t4;
         nt_store_unit(imgA, tid, u, vals);
@@ -478,8 +478,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const float z = v[k] + s_bp2[(c - 10) * 32 + k];
-        v[k] = spatial ? siluf_(z) : 0.f;
-        dv_[k] = spatial ? dsiluf_(z) : 0.f;
+        v[k] = spatial ? fsilu_(z) : 0.f;
+        dv_[k] = spatial ? fdsilu_(z) : 0.f;
       }
       if (valid) st64(nd + 64, c - 10, dv_);
       if (rec) st64(nb + NB_CAT + 320, c - 10, v);
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     tmem_ld32(lane_addr + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bn1[c * 32 + k]; v[k] = siluf_(z); dv_[k] = dsiluf_(z); }
+    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bn1[c * 32 + k]; v[k] = fsilu_(z); dv_[k] = fdsilu_(z); }
     if (valid) st64(nd + 128, c, dv_);
     if (rec) st64(nb + NB_N1, c, v);
 #pragma unroll
@@ -512,13 +512,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 h4 = valid ? __ldg(hp + c * 8 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 h4 = __ldg(hp + c * 8 + u);
       const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i];
-        dv_[4 * u + i] = dsiluf_(z);
-        v[4 * u + i] = hin[i] + siluf_(z);
+        dv_[4 * u + i] = fdsilu_(z);
+        v[4 * u + i] = hin[i] + fsilu_(z);
       }
     }
     if (valid) st64(nd + 192, c, dv_);
@@ -539,8 +539,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const float z = v[k] + s_bv1[c * 32 + k];
-        v[k] = siluf_(z);
-        dv_[k] = dsiluf_(z);
+        v[k] = fsilu_(z);
+        dv_[k] = fdsilu_(z);
         y = fmaf(v[k], s_vel2[c * 32 + k], y);
       }
       if (valid) st64(nd + 256, c, dv_);
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     if (upd) {
       gdv0 = dvo0 + dxo0; gdv1 = dvo1 + dxo1; gdv2 = dvo2 + dxo2;                        // cotangent of v'
       if (hv) {
-        const float gt = 2.0f * sigmoidf_(y);
+        const float gt = 2.0f * fsigmoid_(y);
         const float* vv = a.v + row * 3;
         const float ggate = gdv0 * vv[0] + gdv1 * vv[1] + gdv2 * vv[2];
         gy = ggate * gt * (1.0f - 0.5f * gt);
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   float gho[64];                                         // cotangent of h' (dh_out + velocity-gate path)
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
-    const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(a.dh_out + row * 64) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.dh_out + row * 64) + u);
     gho[4 * u] = t4.x; gho[4 * u + 1] = t4.y; gho[4 * u + 2] = t4.z; gho[4 * u + 3] = t4.w;
   }
   if (uv) {
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
       float gtv[32];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 256 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 d4 = *reinterpret_cast<const float4*>(nd + 256 + c * 32 + 4 * u);
         gtv[4 * u] = s_vel2[c * 32 + 4 * u] * gy * d4.x; gtv[4 * u + 1] = s_vel2[c * 32 + 4 * u + 1] * gy * d4.y;
         gtv[4 * u + 2] = s_vel2[c * 32 + 4 * u + 2] * gy * d4.z; gtv[4 * u + 3] = s_vel2[c * 32 + 4 * u + 3] * gy * d4.w;
       }
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     float g2[32];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 192 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 d4 = *reinterpret_cast<const float4*>(nd + 192 + c * 32 + 4 * u);
       g2[4 * u] = gho[c * 32 + 4 * u] * d4.x; g2[4 * u + 1] = gho[c * 32 + 4 * u + 1] * d4.y;
       g2[4 * u + 2] = gho[c * 32 + 4 * u + 2] * d4.z; g2[4 * u + 3] = gho[c * 32 + 4 * u + 3] * d4.w;
     }
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 128 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 d4 = *reinterpret_cast<const float4*>(nd + 128 + c * 32 + 4 * u);
       v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
     }
     if (rec) st64(nb + NB_GT1, c, v);
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
       } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + 64 + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 d4 = *reinterpret_cast<const float4*>(nd + 64 + c * 32 + 4 * u);
           const float g0 = v[4 * u] * d4.x, g1 = v[4 * u + 1] * d4.y, g2 = v[4 * u + 2] * d4.z, g3 = v[4 * u + 3] * d4.w;
           if (c == 0) { gp2[4 * u] = g0; gp2[4 * u + 1] = g1; gp2[4 * u + 2] = g2; gp2[4 * u + 3] = g3; }
           else { gp2[32 + 4 * u] = g0; gp2[32 + 4 * u + 1] = g1; gp2[32 + 4 * u + 2] = g2; gp2[32 + 4 * u + 3] = g3; }
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 d4 = valid ? *reinterpret_cast<const float4*>(nd + c * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 d4 = *reinterpret_cast<const float4*>(nd + c * 32 + 4 * u);
         v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
       }
       if (rec) st64(nb + NB_GTP1, c, v);
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
           float s[12];
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            const float4 t4 = valid ? __ldg(sp + u * 3 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 t4 = __ldg(sp + u * 3 + q);
             s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
           }
 #pragma unroll
