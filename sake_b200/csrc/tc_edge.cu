@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         const int u = hb * 8 + q;
         uj4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         ui4[q] = uj4[q];
-        if (valid && 4 * u < Kp) {
+        if (4 * u < Kp) {                      // idle lanes read node 0 (valid memory); their rows are never stored
           uj4[q] = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
           ui4[q] = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
         }
@@ -281,12 +281,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         float4 pj4[8], pi4[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          pi4[u] = pj4[u];
-          if (valid) {
-            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 4 * u));
-            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 4 * u));
-          }
+          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 4 * u));
+          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 4 * u));
         }
         float v[32];
         tmem_ld32(lane_addr, v);
@@ -294,11 +290,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float vals[4] = {0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            vals[0] = fsilu_(v[4 * u] + pj4[u].x + pi4[u].x); vals[1] = fsilu_(v[4 * u + 1] + pj4[u].y + pi4[u].y);
-            vals[2] = fsilu_(v[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = fsilu_(v[4 * u + 3] + pj4[u].w + pi4[u].w);
-          }
+          const float vals[4] = {fsilu_(v[4 * u] + pj4[u].x + pi4[u].x), fsilu_(v[4 * u + 1] + pj4[u].y + pi4[u].y),
+                                 fsilu_(v[4 * u + 2] + pj4[u].z + pi4[u].z), fsilu_(v[4 * u + 3] + pj4[u].w + pi4[u].w)};
           store_unit_tf32(img, pl, u, vals);
         }
       }
@@ -306,21 +299,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       float4 pj4[8], pi4[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pi4[u] = pj4[u];
-        if (valid) {
-          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 32 + 4 * u));
-          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 32 + 4 * u));
-        }
+        pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 32 + 4 * u));
+        pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 32 + 4 * u));
       }
       run_chunk(tcol + 0, sW2, 0, 80, idesc80);                            // E' (chunk 0) -> cols [0,80)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        float vals[4] = {0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-          vals[0] = fsilu_(z1b[4 * u] + pj4[u].x + pi4[u].x); vals[1] = fsilu_(z1b[4 * u + 1] + pj4[u].y + pi4[u].y);
-          vals[2] = fsilu_(z1b[4 * u + 2] + pj4[u].z + pi4[u].z); vals[3] = fsilu_(z1b[4 * u + 3] + pj4[u].w + pi4[u].w);
-        }
+        const float vals[4] = {fsilu_(z1b[4 * u] + pj4[u].x + pi4[u].x), fsilu_(z1b[4 * u + 1] + pj4[u].y + pi4[u].y),
+                               fsilu_(z1b[4 * u + 2] + pj4[u].z + pi4[u].z), fsilu_(z1b[4 * u + 3] + pj4[u].w + pi4[u].w)};
         store_unit_tf32(img, pl, u, vals);
       }
       run_chunk(tcol + 0, sW2, 1, 80, idesc80);                            // E' (chunk 1)
@@ -380,14 +366,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       {
         // g_e = (cotangent through x_mixing / aggregate) + W_s g_q   (layers.py:155: logits = e W_s + b_s)
         float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) gq = __ldg(reinterpret_cast<const float4*>(a.gq + prx * 4));
+        gq = __ldg(reinterpret_cast<const float4*>(a.gq + prx * 4));
         const float4* s_ws = reinterpret_cast<const float4*>(svec + 256);
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
           float4 g4[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            g4[u] = valid ? *reinterpret_cast<const float4*>(a.ge + prx * 64 + hb * 32 + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[u] = *reinterpret_cast<const float4*>(a.ge + prx * 64 + hb * 32 + 4 * u);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
@@ -410,12 +396,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         float4 pj4[8], pi4[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          pj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          pi4[u] = pj4[u];
-          if (valid) {
-            pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
-            pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
-          }
+          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
+          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
         }
         float z[32], ga[32];
         if (half == 0) {
@@ -426,8 +408,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float vals[4] = {0.f, 0.f, 0.f, 0.f};
-          if (valid) {
+          float vals[4];
+          {
             const int f0 = half * 32 + 4 * u;
             const float4 pj = pj4[u];
             const float4 pi = pi4[u];
@@ -437,7 +419,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             vals[1] = ga[4 * u + 1] * fdsilu_(zz1 + pj.y + pi.y);
             vals[2] = ga[4 * u + 2] * fdsilu_(zz2 + pj.z + pi.z);
             vals[3] = ga[4 * u + 3] * fdsilu_(zz3 + pj.w + pi.w);
-            *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            if (valid) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
           }
           store_unit_tf32(img, pl, u, vals);
         }
