@@ -243,13 +243,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           ui4[q] = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
         }
       }
+      // 32 independent exp chains, no control flow in between: mu / beta are zero-padded beyond K (rho = 1) and
+      // so are the projections (u = 0), hence rho*u = 0 there; the three extra columns n, 1, t are patched in
+      // afterwards under ONE warp-uniform test per chunk (per-element or per-unit branches serialise the chains)
+      float vals[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int u = hb * 8 + q;
-        // branch-free over the 4 channels: mu / beta are zero-padded beyond K (rho = 1) and so are the
-        // projections (u = 0), hence rho*u = 0 there; the three extra columns n, 1, t are patched in by a
-        // warp-uniform test per unit, not per element (per-element branches serialise the exp chains)
-        float vals[4];
         const float us[4] = {uj4[q].x + ui4[q].x, uj4[q].y + ui4[q].y, uj4[q].z + ui4[q].z, uj4[q].w + ui4[q].w};
         const float4 mu4 = *reinterpret_cast<const float4*>(s_mu + 4 * u);
         const float4 be4 = *reinterpret_cast<const float4*>(s_beta + 4 * u);
@@ -257,19 +257,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float dm = tt - mus[i];
-          vals[i] = fexp_(-bes[i] * dm * dm) * us[i];
+          vals[4 * q + i] = fexp_(-bes[i] * dm * dm) * us[i];
         }
-        if (4 * u + 3 >= K && 4 * u <= K + 2) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 4 * u + i;
-            vals[i] = k == K ? nrm : (k == K + 1 ? 1.0f : (k == K + 2 ? tt : vals[i]));   // 1: column sums for free in the dW contraction
-          }
-        }
-        if (!valid) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; vals[3] = 0.f; }
-        if (BWD && a.train && valid) *reinterpret_cast<float4*>(a.gbuf + prx * 64 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-        store_unit_tf32(img, pl, q, vals);
       }
+      if (hb * 32 + 31 >= K && hb * 32 <= K + 2) {
+#pragma unroll
+        for (int idx = 0; idx < 32; ++idx) {
+          const int k = hb * 32 + idx;
+          vals[idx] = k == K ? nrm : (k == K + 1 ? 1.0f : (k == K + 2 ? tt : vals[idx]));   // 1: column sums for free in the dW contraction
+        }
+      }
+      if (BWD && a.train && valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(a.gbuf + prx * 64 + hb * 32 + 4 * q) = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) store_unit_tf32(img, pl, q, vals + 4 * q);
       run_chunk(tcol + 0, sWA, hb, 64, idesc64);                           // Z1 -> cols [0,64)
     }
 
