@@ -484,32 +484,29 @@ template <class CF>
 __device__ __forceinline__ void epi1_block(const float (&v)[32], const float4* __restrict__ Tp, float zs, float q0,
                                            float q1, float q2, float& g0, float& g1, float& g2, uint8_t* img, int p,
                                            int unit0, float* __restrict__ gz, float idz) {
+  float dz[32];
 #pragma unroll
-  for (int u = 0; u < 32 / CF::EPU; ++u) {
-    float dz[CF::EPU];
-#pragma unroll
-    for (int i = 0; i < CF::EPU; ++i) {
-      const int k = u * CF::EPU + i;
-      const float4 t4 = Tp[k];
-      const float z = CF::F16 ? v[k] * zs : v[k];
-      float t, r;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.885390081777927f));
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
-      const float co = copysignf(fmaf(-2.0f, r, 1.0f), z);
-      const float s2q = fmaf(-r, r, r);
-      const float gco = fmaf(q2, t4.z, fmaf(q1, t4.y, q0 * t4.x));
-      g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
-      dz[i] = gco * s2q;
-    }
-    if (gz != nullptr) {
-#pragma unroll
-      for (int i = 0; i < CF::EPU; i += 4)
-        *reinterpret_cast<float4*>(gz + u * CF::EPU + i) =
-            CF::F16 ? make_float4(dz[i] * idz, dz[i + 1] * idz, dz[i + 2] * idz, dz[i + 3] * idz)
-                    : make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
-    }
-    store_unit<CF>(img, p, unit0 + u, dz);
+  for (int k = 0; k < 32; ++k) {                       // 32 independent chains, no control flow in between
+    const float4 t4 = Tp[k];
+    const float z = CF::F16 ? v[k] * zs : v[k];
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    const float co = copysignf(fmaf(-2.0f, r, 1.0f), z);
+    const float s2q = fmaf(-r, r, r);
+    const float gco = fmaf(q2, t4.z, fmaf(q1, t4.y, q0 * t4.x));
+    g0 = fmaf(co, t4.x, g0); g1 = fmaf(co, t4.y, g1); g2 = fmaf(co, t4.z, g2);
+    dz[k] = gco * s2q;
   }
+  if (gz != nullptr) {                                 // training: fp32 copy of dZ for the weight-gradient contraction
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      *reinterpret_cast<float4*>(gz + i) =
+          CF::F16 ? make_float4(dz[i] * idz, dz[i + 1] * idz, dz[i + 2] * idz, dz[i + 3] * idz)
+                  : make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
+  }
+#pragma unroll
+  for (int u = 0; u < 32 / CF::EPU; ++u) store_unit<CF>(img, p, unit0 + u, dz + u * CF::EPU);
 }
 
 // backward epilogue 2 on 32 TMEM columns (= 8 features f x 4 heads) of one pair:
