@@ -308,3 +308,41 @@ def test_cuda_graph_replay_matches_eager(train):
         assert (outs[0][1] - outs[1][1]).abs().max().item() < 1e-5 * gmax
     else:
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("update,with_v,spatial,masked", [(True, True, True, True), (True, False, True, False),
+                                                          (False, True, True, False), (True, True, False, True),
+                                                          (False, False, True, True)])
+def test_layer_variants_multi_tile_vs_generic(update, with_v, spatial, masked):
+    """Every branch of the per-node tail (velocity gate, update on/off, spatial attention off, mask) on more
+    than one 128-atom tile: the tcgen05 engine (tc_node.cu, tc_edge.cu, tc_mix.cu) against the generic fp32
+    CUDA-core engine, outputs and input gradients (sake/layers.py:188-235; the reference tests these flags only
+    for shapes, sake/tests/test_layers.py:27-36)."""
+    import sake_b200
+    B, N = 5, 31                                  # 155 atoms = 2 tiles, the second one partial
+    g = torch.Generator(device="cuda").manual_seed(17)
+    h = torch.randn(B, N, 64, device="cuda", generator=g)
+    x = torch.randn(B, N, 3, device="cuda", generator=g) * 2.0
+    v = torch.randn(B, N, 3, device="cuda", generator=g) if with_v else None
+    mask = None
+    if masked:
+        n_real = torch.tensor([31, 20, 9, 31, 2], device="cuda")
+        am = (torch.arange(N, device="cuda")[None, :] < n_real[:, None]).float()
+        mask = am[:, :, None] * am[:, None, :]
+        h, x = h * am[..., None], x * am[..., None]
+        v = v * am[..., None] if v is not None else None
+    outs = {}
+    for eng in ("fp32", "auto"):
+        layer = sake_b200.DenseSAKELayer(64, 64, update=update, use_spatial_attention=spatial, engine=eng)
+        p = layer.init(3, h, x, v, mask)
+        hh, xx = h.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        vv = v.clone().requires_grad_(True) if v is not None else None
+        ho, xo, vo = layer.apply(p, hh, xx, vv, mask)
+        s = (ho ** 2).sum() + (xo * 0.3).sum() + ((vo * vo).sum() if vo is not None else 0.0)
+        ins = [hh, xx] + ([vv] if vv is not None else [])
+        gr = torch.autograd.grad(s, ins, allow_unused=True)
+        outs[eng] = [ho, xo] + ([vo] if vo is not None else []) + [t for t in gr if t is not None]
+    for a, b in zip(outs["fp32"], outs["auto"]):
+        assert torch.isfinite(b).all()
+        scale = max(1.0, a.abs().max().item())
+        assert (a - b).abs().max().item() < 2e-4 * scale, ((a - b).abs().max().item(), scale)
