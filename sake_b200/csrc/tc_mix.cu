@@ -308,7 +308,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           mbar_wait(sm.empty + s, (n & 1) ^ 1);
-          const int nsp = dbg_wsplits == 1 ? 1 : CF::NSPLIT;   // 1: timing experiment (half the weight bytes)
+          constexpr int nsp = CF::NSPLIT;
           mbar_arrive_expect_tx(sm.full_w + s, nsp * W_IMG);
           for (int sp = 0; sp < nsp; ++sp)
             bulk_g2s(sm.w_img(s) + sp * W_IMG, w1img + ((size_t)kc * CF::NSPLIT + sp) * W_IMG, W_IMG, sm.full_w + s);
@@ -342,7 +342,6 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
             const uint32_t d = tmem_base + buf * 256 + mh * 128;
 #pragma unroll
             for (int pr = 0; pr < CF::NPROD; ++pr) {
-              if (dbg_wsplits < 0 && pr >= -dbg_wsplits) continue;     // timing experiment only
               const uint32_t a0 = wbase + c_prod_w[pr] * W_IMG + mh * (128 * 128);
               const uint32_t b0 = pbase + c_prod_p[pr] * P_IMG;
 #pragma unroll
