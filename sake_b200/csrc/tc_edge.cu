@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         for (int u = 0; u < 8; ++u) {
           uj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           ui4[u] = uj4[u];
-          if (valid && half * 32 + 4 * u < Kp) {
+          if (half * 32 + 4 * u < Kp) {               // warp-uniform; idle lanes read node 0
             uj4[u] = __ldg(reinterpret_cast<const float4*>(nj + half * 32 + 4 * u));
             ui4[u] = __ldg(reinterpret_cast<const float4*>(ni + Kp + half * 32 + 4 * u));
           }
@@ -446,34 +446,43 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         float gg[32];
         tmem_ld32(lane_addr + half * 32, gg);
         tmem_ld_wait();
+        // 32 straight-line chains (zero-padded mu / beta / projections beyond K: w = 0, beta = 0); the columns
+        // >= K of gu are never read (k_pair_reduce writes zeros there); stores and the distance column afterwards
+        float gu[32], wv[32];
+        float gta = 0.f, gtb = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k0 = half * 32 + 4 * u;
+          const float us[4] = {uj4[u].x + ui4[u].x, uj4[u].y + ui4[u].y, uj4[u].z + ui4[u].z, uj4[u].w + ui4[u].w};
+          const float4 mu4 = *reinterpret_cast<const float4*>(s_mu + k0);
+          const float4 be4 = *reinterpret_cast<const float4*>(s_beta + k0);
+          const float mus[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, bes[4] = {be4.x, be4.y, be4.z, be4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float dm = tt - mus[i];
+            const float rho = fexp_(-bes[i] * dm * dm);
+            gu[4 * u + i] = gg[4 * u + i] * rho;                         // d/du
+            const float w = dm * rho * gg[4 * u + i] * us[i];            // dm * rho * d/drho
+            wv[4 * u + i] = w;
+            if (u & 1) gtb = fmaf(-2.0f * bes[i], w, gtb); else gta = fmaf(-2.0f * bes[i], w, gta);
+          }
+        }
+        gt += gta + gtb;
+        if (K >= half * 32 && K < half * 32 + 32) {
+#pragma unroll
+          for (int idx = 0; idx < 32; ++idx)
+            if (half * 32 + idx == K) gn = gg[idx];                      // through the distance input of mlp_out[0]
+        }
         if (valid) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int k0 = half * 32 + 4 * u;
-            float gu[4], wv[4];
-            const float uj[4] = {uj4[u].x, uj4[u].y, uj4[u].z, uj4[u].w};
-            const float ui[4] = {ui4[u].x, ui4[u].y, ui4[u].z, ui4[u].w};
-            const float4 mu4 = *reinterpret_cast<const float4*>(s_mu + k0);
-            const float4 be4 = *reinterpret_cast<const float4*>(s_beta + k0);
-            const float mus[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, bes[4] = {be4.x, be4.y, be4.z, be4.w};
-            // branch-free (zero-padded mu / beta / projections beyond K: w = 0, beta = 0); the columns >= K of
-            // gu are never read (k_pair_reduce writes zeros there); the distance column is picked per unit
+            if (k0 < 60) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 64 + k0) = make_float4(gu[4 * u], gu[4 * u + 1], gu[4 * u + 2], gu[4 * u + 3]);
+          }
+          if (a.train) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float dm = tt - mus[i];
-              const float rho = fexp_(-bes[i] * dm * dm);
-              gu[i] = gg[4 * u + i] * rho;                                   // d/du
-              const float w = dm * rho * gg[4 * u + i] * (uj[i] + ui[i]);   // dm * rho * d/drho
-              wv[i] = w;
-              gt = fmaf(-2.0f * bes[i], w, gt);
-            }
-            if (K >= k0 && K < k0 + 4) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (k0 + i == K) gn = gg[4 * u + i];                         // through the distance input of mlp_out[0]
-            }
-            if (k0 < 60) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 64 + k0) = make_float4(gu[0], gu[1], gu[2], gu[3]);
-            if (a.train) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 128 + k0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 128 + half * 32 + 4 * u) = make_float4(wv[4 * u], wv[4 * u + 1], wv[4 * u + 2], wv[4 * u + 3]);
           }
         }
       }
