@@ -6,6 +6,9 @@
 // fp32 inputs are converted on the fly (exact 3-way bf16 split, 6 MMAs; or plain bf16).  The accumulator
 // lives in TMEM for the whole CTA and is flushed once with atomics.
 #include <cuda_bf16.h>
+#include <stdint.h>
+#include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -77,10 +80,15 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
 }
 
 struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
+__device__ __align__(16) float g_xtg_zeros[256];   // a source row of zeros (pair rows past the end of a contraction)
 
 // TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
 // the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE)
-template <int ENGINE, int TCOLS>
+// LEAN: every problem of the batch has the layer's regular shapes (xtg_is_lean): the builder then maps thread ->
+// (pair row, 16-byte unit position) once, so that a stage costs one pointer bump per operand, two LDG.128 and two
+// STS.128 per unit and nothing else — the generic builder (any width / alignment) executes ~5x the instructions,
+// and this kernel is bound by exactly that (measured: issue + fixed-latency stalls, not memory).
+template <int ENGINE, int TCOLS, bool LEAN>
 __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
   using CF = XCfg<ENGINE>;
   const XtgArgs& a = batch.a[blockIdx.y];
@@ -133,6 +141,98 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
         umma_commit(empty + s);
       }
       umma_commit(done);
+    }
+  } else if constexpr (LEAN) {
+    // ------------------------------------------------------------ lean builders: thread = (pair row r, unit position uu)
+    // of every 64-feature block.  Block j of X is either all data (j < nxf), the block whose first feature is the
+    // ones column (j == nxf when ones_col >= 0), or zero padding up to MXpad — written once, below.
+    // The 512-column instantiation is the x_mixing gradient (X = e (x) att, 4 + 4 blocks), the 256-column one the rest.
+    constexpr bool EMODE = TCOLS == 512;
+    const int bt = threadIdx.x - 32;                 // 0..255
+    const int r = bt >> 3, uu = bt & 7;
+    const uint32_t uoff = sw128_offset((uint32_t)r, (uint32_t)uu);
+    const int nxf = EMODE ? 4 : (a.xw >> 6);
+    const bool has_ones = !EMODE && a.ones_col >= 0;
+    const int ngf = EMODE ? 4 : (a.gw >> 6);
+    const bool gnarrow = !EMODE && (a.gw & 63) != 0; // gw < 64: one block, scalar loads
+    {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int s = 0; s < nstage; ++s)
+        for (int sp = 0; sp < CF::NSPLIT; ++sp) {
+          uint8_t* xs = base + s * stage + sp * ximg + uoff;
+          for (int j = nxf; j < xblocks; ++j) *reinterpret_cast<uint4*>(xs + j * LBO) = z;
+          uint8_t* gs = base + s * stage + CF::NSPLIT * ximg + sp * gimg + uoff;
+          for (int j = ngf + (gnarrow ? 1 : 0); j < gblocks; ++j) *reinterpret_cast<uint4*>(gs + j * LBO) = z;
+        }
+    }
+    float4 xa[4], xb[4], ga[4], gb[4];               // EMODE: xa[j].xy = the two e features of unit j
+    float gn[8];                                     // narrow G block
+    float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t onew_full = (has_ones && uu == 0) ? 0x00003F80u : 0u;   // ones unit: bf16(1.0) in element 0
+    uint32_t onew = 0u;
+    // One definition path for the loop-carried registers (no per-row branches, which cost a register shuffle at
+    // every merge): rows past the end (last stage of the grid only) read a page of zeros instead.
+    auto load_stage = [&](int it) {
+      const long long p = p_beg + (long long)it * XKP + r;
+      const bool rv = p < p_end;
+      onew = rv ? onew_full : 0u;
+      const float* gp = rv ? a.G + p * a.ldg + 8 * uu : g_xtg_zeros + 8 * uu;
+      if constexpr (EMODE) {                         // raw operands of E = e (x) att; the product is formed at store time
+        at = __ldg(reinterpret_cast<const float4*>(rv ? a.att + p * 4 : g_xtg_zeros));
+        const float2* ep = reinterpret_cast<const float2*>(rv ? a.e + p * 64 + 2 * uu : g_xtg_zeros + 2 * uu);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 8 * j); xa[j].x = ef.x; xa[j].y = ef.y; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j);
+          gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j + 1);
+        }
+      } else {
+        const float4* xp = reinterpret_cast<const float4*>(rv ? a.X + p * a.ldx + 8 * uu : g_xtg_zeros + 8 * uu);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nxf) { xa[j] = __ldg(xp + 16 * j); xb[j] = __ldg(xp + 16 * j + 1); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < ngf) {
+            ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j);
+            gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j + 1);
+          }
+        if (gnarrow) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + i) : 0.f;
+        }
+      }
+    };
+    if (nst > 0) load_stage(0);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % nstage, n = it / nstage;
+      mbar_wait_warp(empty + s, (n & 1) ^ 1);
+      uint8_t* xs = base + s * stage + uoff;
+      uint8_t* gs = xs + CF::NSPLIT * ximg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nxf) {
+          if constexpr (EMODE) {                     // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
+            const float vals[8] = {xa[j].x * at.x, xa[j].x * at.y, xa[j].x * at.z, xa[j].x * at.w,
+                                   xa[j].y * at.x, xa[j].y * at.y, xa[j].y * at.z, xa[j].y * at.w};
+            xtg_store_unit<CF>(xs + j * LBO, ximg, 0u, vals);
+          } else {
+            const float vals[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+            xtg_store_unit<CF>(xs + j * LBO, ximg, 0u, vals);
+          }
+        }
+      if (has_ones) *reinterpret_cast<uint4*>(xs + nxf * LBO) = make_uint4(onew, 0u, 0u, 0u);   // (the residual image stays zero)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < ngf) {
+          const float vals[8] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w, gb[j].x, gb[j].y, gb[j].z, gb[j].w};
+          xtg_store_unit<CF>(gs + j * LBO, gimg, 0u, vals);
+        }
+      if (gnarrow) xtg_store_unit<CF>(gs, gimg, 0u, gn);
+      fence_proxy_async();
+      mbar_arrive(full + s);
+      if (it + 1 < nst) load_stage(it + 1);
     }
   } else {
     // ------------------------------------------------------------ builders (thread = pair x 8-feature unit)
@@ -212,6 +312,8 @@ __global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant
       mbar_arrive(full + s);
       if (it + 1 < nst) load_stage(it + 1);
     }
+  }
+  if (warp != 0) {
     // ------------------------------------------------------------ epilogue: flush the accumulator
     if (nst > 0) {
       mbar_wait_warp(done, 0);
@@ -287,22 +389,40 @@ static int xtg_num_sms() {
 // Launch the collected contractions as two grids (blockIdx.y = problem): the 256 x 256 x_mixing gradient, which
 // needs the whole TMEM and a 192 KB operand ring (this launch is the one the profiler times as "mix_dw"), and
 // all the small ones (<= 256 TMEM columns, two-stage ring: two CTAs per SM) — each followed by its reduction grid.
-template <int TCOLS>
+// the regular shapes of the layer (see the LEAN builder): 64-multiples of 16-byte-aligned rows, the ones column
+// right behind the data, and G either whole 64-feature blocks or one narrow block
+static bool xtg_is_lean(const XtgArgs& a, bool is_big) {
+  if (is_big != (a.e != nullptr)) return false;        // the 512-column lean kernel is the E = e (x) att one
+  if (is_big && (a.gw != 256 || a.NG != 256)) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.e != nullptr) {
+    if (a.att == nullptr || !al16(a.e) || !al16(a.att) || a.xw != 256 || a.MXpad != 256 || a.ones_col >= 0) return false;
+  } else {
+    if (a.X == nullptr || !al16(a.X) || a.ldx % 4 != 0 || a.xw <= 0 || a.xw % 64 != 0) return false;
+    if (a.ones_col >= 0 && a.ones_col != a.xw) return false;
+    if (a.xw + (a.ones_col >= 0 ? 1 : 0) > a.MXpad) return false;
+  }
+  if (a.gw <= 0 || a.gw > a.NG) return false;
+  if (a.gw % 64 == 0) return al16(a.G) && a.ldg % 4 == 0;
+  return a.gw < 64;
+}
+
+template <int TCOLS, bool LEAN>
 static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, size_t smem, int nstage, bool bf,
                       int prof_kind, long long prof_pairs, cudaStream_t st) {
   if (nb == 0) return 0;
   if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
   static bool attr_tf = false, attr_bf = false;
   if (bf) {
-    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
+    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
   } else {
-    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
+    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
   }
   {
     ProfScope prof(prof_kind, prof_pairs, st);
     dim3 grid(gx_max, nb);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
     dim3 rgrid(ng_max, nb);
     k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
   }
@@ -322,6 +442,7 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   size_t smem_b = 0, smem_s = 0, poff = 0;
   int gx_b = 0, gx_s = 0, ng_b = 0, ng_s = 0, nb_b = 0, nb_s = 0;
   long long prof_pairs = 0;
+  bool lean_b = true, lean_s = true;
   constexpr int NST_BIG = XTG_NSTAGE, NST_SMALL = 2;
   for (int i = 0; i < L.n; ++i) {
     XtgArgs a = L.a[i];
@@ -352,18 +473,23 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
       if (a.gx > gx_b) gx_b = a.gx;
       if (a.NG > ng_b) ng_b = a.NG;
       if (a.P > prof_pairs) prof_pairs = a.P;
+      lean_b = lean_b && xtg_is_lean(a, true);
       big.a[nb_b++] = a;
     } else {
       if (smem > smem_s) smem_s = smem;
       if (a.gx > gx_s) gx_s = a.gx;
       if (a.NG > ng_s) ng_s = a.NG;
+      lean_s = lean_s && xtg_is_lean(a, false);
       small.a[nb_s++] = a;
     }
   }
   L.n = 0;
-  int rc = xtg_launch<512>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
+  static const bool no_lean = [] { const char* e = getenv("SAKE_XTG_GENERIC"); return e && atoi(e) != 0; }();   // A/B switch
+  int rc = lean_b && !no_lean ? xtg_launch<512, true>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
+                              : xtg_launch<512, false>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
   if (rc) return rc;
-  return xtg_launch<256>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
+  return lean_s && !no_lean ? xtg_launch<256, true>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st)
+                            : xtg_launch<256, false>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
 }
 
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
