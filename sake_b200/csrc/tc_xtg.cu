@@ -84,12 +84,12 @@ __device__ __align__(16) float g_xtg_zeros[256];   // a source row of zeros (pai
 
 // TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
 // the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE)
-// LEAN: every problem of the batch has the layer's regular shapes (xtg_is_lean): the builder then maps thread ->
+// MINB: CTAs per SM the register budget is cut for.  LEAN: every problem of the batch has the layer's regular shapes (xtg_is_lean): the builder then maps thread ->
 // (pair row, 16-byte unit position) once, so that a stage costs one pointer bump per operand, two LDG.128 and two
 // STS.128 per unit and nothing else — the generic builder (any width / alignment) executes ~5x the instructions,
 // and this kernel is bound by exactly that (measured: issue + fixed-latency stalls, not memory).
-template <int ENGINE, int TCOLS, bool LEAN>
-__global__ void __launch_bounds__(XTG_THREADS, 1) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
+template <int ENGINE, int TCOLS, bool LEAN, int MINB>
+__global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
   using CF = XCfg<ENGINE>;
   const XtgArgs& a = batch.a[blockIdx.y];
   if ((int)blockIdx.x >= a.gx) return;                        // CTA beyond this problem's range
@@ -407,22 +407,22 @@ static bool xtg_is_lean(const XtgArgs& a, bool is_big) {
   return a.gw < 64;
 }
 
-template <int TCOLS, bool LEAN>
+template <int TCOLS, bool LEAN, int MINB>
 static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, size_t smem, int nstage, bool bf,
                       int prof_kind, long long prof_pairs, cudaStream_t st) {
   if (nb == 0) return 0;
   if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
   static bool attr_tf = false, attr_bf = false;
   if (bf) {
-    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
+    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
   } else {
-    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
+    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
   }
   {
     ProfScope prof(prof_kind, prof_pairs, st);
     dim3 grid(gx_max, nb);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
     dim3 rgrid(ng_max, nb);
     k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
   }
@@ -485,11 +485,12 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   }
   L.n = 0;
   static const bool no_lean = [] { const char* e = getenv("SAKE_XTG_GENERIC"); return e && atoi(e) != 0; }();   // A/B switch
-  int rc = lean_b && !no_lean ? xtg_launch<512, true>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
-                              : xtg_launch<512, false>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
+  int rc = lean_b && !no_lean ? xtg_launch<512, true, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
+                              : xtg_launch<512, false, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
   if (rc) return rc;
-  return lean_s && !no_lean ? xtg_launch<256, true>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st)
-                            : xtg_launch<256, false>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
+  // the lean small kernel fits two CTAs per SM (96 registers, 256 TMEM columns, <= 82 KB): 4 builder warps per scheduler
+  return lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st)
+                            : xtg_launch<256, false, 1>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
 }
 
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
