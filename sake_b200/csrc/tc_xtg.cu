@@ -172,14 +172,19 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
     uint32_t onew = 0u;
     // One definition path for the loop-carried registers (no per-row branches, which cost a register shuffle at
     // every merge): rows past the end (last stage of the grid only) read a page of zeros instead.
-    auto load_stage = [&](int it) {
-      const long long p = p_beg + (long long)it * XKP + r;
-      const bool rv = p < p_end;
+    // this thread's source rows for the next load; every stage bumps them by XKP rows
+    long long pl = p_beg + r;
+    const float* xrow = EMODE ? a.e + pl * 64 + 2 * uu : a.X + pl * a.ldx + 8 * uu;
+    const float* grow = a.G + pl * a.ldg + 8 * uu;
+    const float* arow = EMODE ? a.att + pl * 4 : nullptr;
+    const long long xstep = EMODE ? (long long)XKP * 64 : (long long)XKP * a.ldx, gstep = (long long)XKP * a.ldg;
+    auto load_stage = [&]() {
+      const bool rv = pl < p_end;
       onew = rv ? onew_full : 0u;
-      const float* gp = rv ? a.G + p * a.ldg + 8 * uu : g_xtg_zeros + 8 * uu;
+      const float* gp = rv ? grow : g_xtg_zeros + 8 * uu;
       if constexpr (EMODE) {                         // raw operands of E = e (x) att; the product is formed at store time
-        at = __ldg(reinterpret_cast<const float4*>(rv ? a.att + p * 4 : g_xtg_zeros));
-        const float2* ep = reinterpret_cast<const float2*>(rv ? a.e + p * 64 + 2 * uu : g_xtg_zeros + 2 * uu);
+        at = __ldg(reinterpret_cast<const float4*>(rv ? arow : g_xtg_zeros));
+        const float2* ep = reinterpret_cast<const float2*>(rv ? xrow : g_xtg_zeros + 2 * uu);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 8 * j); xa[j].x = ef.x; xa[j].y = ef.y; }
 #pragma unroll
@@ -187,8 +192,9 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
           ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j);
           gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j + 1);
         }
+        arow += XKP * 4;
       } else {
-        const float4* xp = reinterpret_cast<const float4*>(rv ? a.X + p * a.ldx + 8 * uu : g_xtg_zeros + 8 * uu);
+        const float4* xp = reinterpret_cast<const float4*>(rv ? xrow : g_xtg_zeros + 8 * uu);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (j < nxf) { xa[j] = __ldg(xp + 16 * j); xb[j] = __ldg(xp + 16 * j + 1); }
@@ -203,8 +209,9 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
           for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + i) : 0.f;
         }
       }
+      pl += XKP; xrow += xstep; grow += gstep;
     };
-    if (nst > 0) load_stage(0);
+    if (nst > 0) load_stage();
     for (int it = 0; it < nst; ++it) {
       const int s = it % nstage, n = it / nstage;
       mbar_wait_warp(empty + s, (n & 1) ^ 1);
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
       if (gnarrow) xtg_store_unit<CF>(gs, gimg, 0u, gn);
       fence_proxy_async();
       mbar_arrive(full + s);
-      if (it + 1 < nst) load_stage(it + 1);
+      if (it + 1 < nst) load_stage();
     }
   } else {
     // ------------------------------------------------------------ builders (thread = pair x 8-feature unit)
@@ -356,20 +363,49 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
 }
 
 // out[row][col] += sum_cta partial[cta][col][row]   (deterministic second stage of the flush)
-__global__ void __launch_bounds__(128) k_xtg_reduce(const __grid_constant__ XtgBatch batch) {
+// Block = 128 rows x XRED_SLICES slices of the CTA range: each thread keeps 8 independent loads in flight (the
+// partials are L2-resident; one load per thread at a time left this kernel latency-bound at ~1 TB/s), the slices
+// are combined in a fixed order through shared memory.
+constexpr int XRED_SLICES = 4;
+__global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_constant__ XtgBatch batch) {
+  __shared__ float red[XRED_SLICES][128];
   const XtgArgs& a = batch.a[blockIdx.y];
   const int col = blockIdx.x;
   const int ncta = a.gx;
-  if (col >= a.NG || a.partial == nullptr) return;
-  for (int row = threadIdx.x; row < a.out_rows + a.extra_rows; row += blockDim.x) {
-    const float* pp = a.partial + (size_t)col * a.MXpad + row;
+  if (col >= a.NG || a.partial == nullptr) return;           // block-uniform
+  const int tx = threadIdx.x & 127, sl = threadIdx.x >> 7;
+  const int per = (ncta + XRED_SLICES - 1) / XRED_SLICES;
+  const int c0 = min(ncta, sl * per), c1 = min(ncta, c0 + per);
+  const size_t cstride = (size_t)a.MXpad * a.NG;
+  const int rows = a.out_rows + a.extra_rows;
+  for (int r0 = 0; r0 < rows; r0 += 128) {                    // block-uniform trip count (<= 2)
+    const int row = r0 + tx;
     float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += pp[(size_t)c * a.MXpad * a.NG];
-    if (row < a.out_rows) {
-      if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += s;
-    } else if (col < a.extra_ld) {
-      a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += s;
+    if (row < rows) {
+      const float* pp = a.partial + (size_t)col * a.MXpad + row + (size_t)c0 * cstride;
+      int c = c0;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      for (; c + 8 <= c1; c += 8, pp += 8 * cstride) {
+        const float v0 = pp[0], v1 = pp[cstride], v2 = pp[2 * cstride], v3 = pp[3 * cstride];
+        const float v4 = pp[4 * cstride], v5 = pp[5 * cstride], v6 = pp[6 * cstride], v7 = pp[7 * cstride];
+        t0 += v0; t1 += v1; t2 += v2; t3 += v3; t0 += v4; t1 += v5; t2 += v6; t3 += v7;
+      }
+      for (; c < c1; ++c, pp += cstride) t0 += pp[0];
+      s = (t0 + t1) + (t2 + t3);
     }
+    red[sl][tx] = s;
+    __syncthreads();
+    if (sl == 0 && row < rows) {
+      float tot = red[0][tx];
+#pragma unroll
+      for (int k = 1; k < XRED_SLICES; ++k) tot += red[k][tx];
+      if (row < a.out_rows) {
+        if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += tot;
+      } else if (col < a.extra_ld) {
+        a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += tot;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -424,7 +460,7 @@ static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, siz
     if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
     else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
     dim3 rgrid(ng_max, nb);
-    k_xtg_reduce<<<rgrid, 128, 0, st>>>(batch);
+    k_xtg_reduce<<<rgrid, 128 * XRED_SLICES, 0, st>>>(batch);
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
