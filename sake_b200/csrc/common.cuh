@@ -210,6 +210,21 @@ void note_launches(int n);
     }                                                                                \
   } while (0)
 
+// The > 48 KB dynamic shared-memory opt-in is a per-DEVICE function attribute: every launcher sets it once
+// per (kernel, device) — `done` is the launcher's own static bit mask, one bit per device ordinal.  A process
+// that drives several GPUs (one host thread per device, as XLA's pmap does) therefore opts in on each of them.
+template <typename Kern>
+static inline int smem_optin(Kern kern, size_t smem, unsigned long long& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if ((__atomic_load_n(&done, __ATOMIC_RELAXED) & bit) == 0) {
+    SAKE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    __atomic_fetch_or(&done, bit, __ATOMIC_RELAXED);
+  }
+  return 0;
+}
+
 // event profiler hooks around the dominant kernels (optim.cu)
 bool prof_begin_launch(int kind, long long pairs, cudaStream_t st);
 void prof_end_launch(cudaStream_t st);

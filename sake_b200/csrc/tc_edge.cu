@@ -617,8 +617,8 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.e_out = sv.e; a.logit_out = sv.logit;
   const size_t smem = WA_BYTES + WB_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;
-  static bool attr = false;
-  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_edge<false>, smem, optin); if (rc) return rc; }
   k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
@@ -649,8 +649,8 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.ge = sc.ge; a.gdir = sc.gdir; a.gq = sc.gatt; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
   const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
-  static bool attr = false;
-  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_edge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_edge<true>, smem, optin); if (rc) return rc; }
   k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
   k_pair_reduce<<<d.R, 128, 0, st>>>(d.N, d.K, d.Kp, d.NP, PB, sc.gproj, dx);
   note_launches(2);

@@ -1001,12 +1001,8 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
   k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
   if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mix_fwd<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes<CF>()));
-    attr_set = true;
-  }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_mix_fwd<ENGINE>, smem_bytes<CF>(), optin); if (rc) return rc; }
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
   {
     ProfScope prof(1, d.P, st);
@@ -1032,12 +1028,8 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
   k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
   k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mix_bwd<ENGINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes<CF>()));
-    attr_set = true;
-  }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_mix_bwd<ENGINE>, smem_bytes<CF>(), optin); if (rc) return rc; }
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
   {
     ProfScope prof(2, d.P, st);

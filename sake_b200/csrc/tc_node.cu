@@ -765,8 +765,8 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   a.qv = wvg ? (float*)((char*)nscratch + align_up(sizeof(float) * (size_t)d.R * ND_LD)) : nullptr;
   a.nbuf = g ? sc.nbuf : nullptr;
   const size_t smem = 4 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
-  static bool attr = false;
-  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_node_post_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_node_post_bwd, smem, optin); if (rc) return rc; }
   k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
   if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 3 : 2);
@@ -789,8 +789,8 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
   a.h_out = h_out; a.x_out = x_out; a.v_out = v_out;
   const size_t smem = 2 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
-  static bool attr = false;
-  if (!attr) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_node_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_node_post, smem, optin); if (rc) return rc; }
   k_tc_node_post<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());

@@ -448,12 +448,10 @@ static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, siz
                       int prof_kind, long long prof_pairs, cudaStream_t st) {
   if (nb == 0) return 0;
   if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
-  static bool attr_tf = false, attr_bf = false;
-  if (bf) {
-    if (!attr_bf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_bf = true; }
-  } else {
-    if (!attr_tf) { SAKE_CUDA_CHECK(cudaFuncSetAttribute(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_tf = true; }
-  }
+  static unsigned long long optin_tf = 0, optin_bf = 0;
+  const int orc = bf ? smem_optin(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB>, 200 * 1024, optin_bf)
+                     : smem_optin(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB>, 200 * 1024, optin_tf);
+  if (orc) return orc;
   {
     ProfScope prof(prof_kind, prof_pairs, st);
     dim3 grid(gx_max, nb);
