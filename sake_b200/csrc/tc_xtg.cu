@@ -83,11 +83,13 @@ struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
 __device__ __align__(16) float g_xtg_zeros[256];   // a source row of zeros (pair rows past the end of a contraction)
 
 // TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
-// the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE)
-// MINB: CTAs per SM the register budget is cut for.  LEAN: every problem of the batch has the layer's regular shapes (xtg_is_lean): the builder then maps thread ->
-// (pair row, 16-byte unit position) once, so that a stage costs one pointer bump per operand, two LDG.128 and two
-// STS.128 per unit and nothing else — the generic builder (any width / alignment) executes ~5x the instructions,
-// and this kernel is bound by exactly that (measured: issue + fixed-latency stalls, not memory).
+//        the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE).
+// MINB:  CTAs per SM the register budget is cut for (2 for the lean 256-column kernel: 96 registers).
+// LEAN:  every problem of the batch has one of the layer's regular shapes (xtg_is_lean).  The builder then maps
+//        thread -> (pair row, 16-byte unit position) once, so that a stage costs one pointer bump per operand plus
+//        two LDG.128, the bf16 split and two STS.128 per unit, and nothing else.  The generic builder (any width
+//        and alignment) executes ~2.5x the instructions per stage, and instruction issue is what bounds this kernel
+//        (DESIGN.md section 5).
 template <int ENGINE, int TCOLS, bool LEAN, int MINB>
 __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
   using CF = XCfg<ENGINE>;
