@@ -168,6 +168,25 @@ def test_tcgen05_selftest():
     assert err[0] < 1e-5 and err[1] < 5e-2
 
 
+@pytest.mark.parametrize("engine,tol", [(2, 1e-4), (3, 1e-2)])
+@pytest.mark.parametrize("P,xw,gw", [(64, 128, 64), (300, 256, 256), (1000, 64, 16), (5000, 256, 64), (777, 100, 128)])
+def test_xtg_contraction_shapes(engine, tol, P, xw, gw):
+    """out = X^T G (the weight-gradient contraction kernel) through sake_selftest_xtg: regular shapes (lean
+    builder: whole 64-feature blocks, one narrow block) and irregular ones (generic builder), with the
+    split-bf16 (engine 2) and the plain bf16 (engine 3) operand precision."""
+    from sake_b200 import _lib
+    gen = torch.Generator(device="cuda").manual_seed(P + xw)
+    X = torch.randn(P, xw, device="cuda", generator=gen)
+    G = torch.randn(P, gw, device="cuda", generator=gen)
+    out = torch.zeros(xw, gw, device="cuda")
+    rc = _lib.lib.sake_selftest_xtg(engine, P, xw, gw, X.data_ptr(), G.data_ptr(), out.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0, _lib.lib.sake_last_error().decode()
+    ref = X.double().T @ G.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err < tol * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("engine", ["tf32x3", "f16x2", "bf16"])
 @pytest.mark.parametrize("B,N,padded", [(64, 29, True), (40, 21, False), (3, 200, False)])
 def test_tc_engine_multi_tile_vs_generic(engine, B, N, padded):
