@@ -1,6 +1,7 @@
 // Blackwell (sm_100a) building blocks: mbarrier, bulk async copy (TMA), tcgen05 MMA / TMEM, and the
 // 128-byte-swizzled K-major operand image used by every tensor-core kernel in this library.
 #pragma once
+#include <stdio.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,17 +49,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Development builds (make WATCHDOG=1 -> -DSAKE_MBAR_WATCHDOG) turn a pipeline deadlock into a fast failure: a
+// wait that has spun for ~2 s of SM clock prints which barrier / parity / thread it was and traps, so a wrong
+// ring protocol costs seconds of GPU time instead of the whole test timeout.  The product build has no
+// watchdog: the polling loops are exactly the two instructions below.
+#ifdef SAKE_MBAR_WATCHDOG
+__device__ __noinline__ void mbar_watchdog_fire(uint64_t* bar, uint32_t parity) {
+  printf("sake mbarrier watchdog: block %d thread %d stuck on barrier smem+0x%x parity %u\n", (int)blockIdx.x,
+         (int)threadIdx.x, smem_u32(bar), parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) mbar_watchdog_fire(bar, parity);
+  }
+}
+#else
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_spin(bar, parity); }
 // Whole-warp wait with ONE polling lane: 32x fewer SYNCS/BRA issue slots and smem probes than every
 // lane spinning (the spin loops were a third of all issued instructions in the first profiles).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-  }
+  if ((threadIdx.x & 31) == 0) mbar_spin(bar, parity);
   __syncwarp();
 }
 
