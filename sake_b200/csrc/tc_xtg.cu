@@ -22,7 +22,14 @@ using namespace tc;
 // a relative error <= 2e-5 (they are sums over 10^5..10^6 pairs feeding Adam; energies and forces never
 // pass through this kernel).  The bf16 engine uses one bf16 image and one MMA.
 template <int ENGINE> struct XCfg;
+// Experimental (make XTG_RN3=1, not the product build): split by round-to-nearest (same instruction count) and
+// drop the mid*mid product.  CPU experiment scripts/xtg_split_error.py: 4.4e-6 rms error against 1.7e-5 of the
+// truncated four-product scheme, because unbiased rounding errors average out over K = pairs; 25 % fewer MMAs.
+#ifdef SAKE_XTG_RN3
+template <> struct XCfg<SAKE_ENGINE_TF32X3> { static constexpr int NSPLIT = 2, NPROD = 3; };
+#else
 template <> struct XCfg<SAKE_ENGINE_TF32X3> { static constexpr int NSPLIT = 2, NPROD = 4; };
+#endif
 template <> struct XCfg<SAKE_ENGINE_BF16> { static constexpr int NSPLIT = 1, NPROD = 1; };
 constexpr int XEPU = 8;      // features per 16-byte unit (bf16)
 constexpr int XBLK = 64;     // features per 128-byte MN block
@@ -56,6 +63,18 @@ __device__ __forceinline__ void xtg_store_unit(uint8_t* img, size_t split_stride
   } else {
     uint32_t pk[4];
     float r[8];
+#ifdef SAKE_XTG_RN3
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r[2 * i] = v[2 * i] - __uint_as_float(pk[i] << 16);
+      r[2 * i + 1] = v[2 * i + 1] - __uint_as_float(pk[i] & 0xFFFF0000u);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[i] = pack_hi16(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(img + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -63,6 +82,7 @@ __device__ __forceinline__ void xtg_store_unit(uint8_t* img, size_t split_stride
     for (int i = 0; i < 8; ++i) r[i] = v[i] - trunc_bf16(v[i]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[i] = pack_hi16(r[2 * i], r[2 * i + 1]);
+#endif
     *reinterpret_cast<uint4*>(img + split_stride + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
