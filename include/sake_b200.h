@@ -137,7 +137,31 @@ size_t sake_layer_saved_bytes(const SakeDims* dims);
  * for_backward != 0 sizes it for sake_layer_bwd (with_param_grads selects the training variant). */
 size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with_param_grads);
 
+/* ---- ragged batches: compute the real atoms of a padded batch only -------------------------------------
+ * The reference pads every molecule of a batch to N atoms and multiplies every O(N^2) tensor by
+ * mask = outer(m, m) (scripts/qm9/run.py:23-24,35; sake/layers.py:120-123,137-138,164-165,178-179,219-221).
+ * With `ragged` tables the layer instead works on a COMPACT layout that stores the n_real[b] real atoms of
+ * every molecule only (molecules ordered by n_real, R = sum n_real rows, P = sum n_real^2 pairs): same
+ * function on the real atoms (sake/tests/test_mask.py:202-240), no work on padding.
+ *   sake_ragged_bytes      size of the table buffer for a [B, N] batch (N <= 128)
+ *   sake_ragged_prepare    builds the tables on the device from n_real[B] (int32 DEVICE buffer, clamped to
+ *                          [0, N]; real atoms are the first n_real[b] of each molecule); no host sync
+ *   sake_ragged_gather     compact[r, :width] = padded[b, i, :width] for every real atom
+ *   sake_ragged_scatter    padded[b, i, :width] = alpha * compact[r, :width]; padding rows are left untouched
+ * Every entry point that takes `ragged` then expects compact tensors in buffers sized for the worst case
+ * (B*N rows), mask = NULL, and SakeDims {B, N} of the padded batch.  The real counts stay on the device:
+ * launch grids cover the worst case and kernels read their bounds from the tables. */
+size_t sake_ragged_bytes(int32_t B, int32_t N);
+int sake_ragged_prepare(int32_t B, int32_t N, const int32_t* n_real, void* ragged, size_t ragged_bytes,
+                        sake_stream_t stream);
+int sake_ragged_gather(const void* ragged, int32_t B, int32_t N, int32_t width, const float* padded,
+                       float* compact, sake_stream_t stream);
+int sake_ragged_scatter(const void* ragged, int32_t B, int32_t N, int32_t width, float alpha,
+                        const float* compact, float* padded, sake_stream_t stream);
+
 /* DenseSAKELayer.__call__ (sake/layers.py:188-235) with he=None, cutoff=None.
+ * `ragged`: NULL, or the tables of sake_ragged_prepare (then mask must be NULL and h / x / v and all
+ * outputs are compact; tcgen05 engines only).
  *   h [B,N,H], x [B,N,3], v [B,N,3] or NULL, mask [B,N,N] float or NULL
  *   -> h_out [B,N,H], x_out [B,N,3], v_out [B,N,3]
  * Coordinates are always 3 wide; 2-D systems (scripts/dw4) pad z = 0 on the host side.
@@ -145,7 +169,7 @@ size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with
  * Guarded masking: a row whose attention normaliser is 0 gets att = 0 (the reference yields
  * 0/0 = NaN there, layers.py:178-180); every other value follows the reference formulas. */
 int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
-                   const float* h, const float* x, const float* v, const float* mask,
+                   const float* h, const float* x, const float* v, const float* mask, const void* ragged,
                    float* h_out, float* x_out, float* v_out,
                    void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
                    sake_stream_t stream);
@@ -157,7 +181,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
  *   grads: NULL for the forces-only (inference) variant, else accumulated parameter gradients.
  * `saved` must be the buffer written by sake_layer_fwd for the same inputs. */
 int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params,
-                   const float* h, const float* x, const float* v, const float* mask,
+                   const float* h, const float* x, const float* v, const float* mask, const void* ragged,
                    const void* saved, size_t saved_bytes,
                    const float* dh_out, const float* dx_out, const float* dv_out,
                    float* dh, float* dx, float* dv, const SakeLayerGrads* grads,
@@ -165,14 +189,15 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params,
 
 /* nn.Dense (+ optional silu) over the last axis — embedding_in / embedding_out of
  * DenseSAKEModel (sake/models.py:24-31,57,60).  y[rows,out] = act(x[rows,in] @ kernel + bias).
- * act: 0 = identity, 1 = silu.  bias may be NULL. */
+ * act: 0 = identity, 1 = silu.  bias may be NULL.  `ragged` (nullable): x / y are compact, `rows` is the
+ * worst case B*N and the real row count is read from the tables on the device. */
 int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act,
                    const float* x, const float* kernel, const float* bias, float* y,
-                   sake_stream_t stream);
+                   const void* ragged, sake_stream_t stream);
 /* VJP of sake_dense_fwd: dx (may be NULL), and accumulated dkernel / dbias (may be NULL). */
 int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act,
                    const float* x, const float* kernel, const float* bias, const float* dy,
-                   float* dx, float* dkernel, float* dbias, sake_stream_t stream);
+                   float* dx, float* dkernel, float* dbias, const void* ragged, sake_stream_t stream);
 
 /* Energy head of the drivers: E[b] = sum_i sum_o y[b,i,o] * atom_mask[b,i]
  * (scripts/md17/run.py:46-52; masked sum of scripts/qm9/run.py:58-60), plus the cotangent dy that
@@ -181,10 +206,11 @@ int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int3
  *   mode 1 (L1 loss, scripts/qm9/run.py:79-82, coloring utils.py:7-8):
  *           loss += mean_b |std*E[b] + mean - target[b]| ;  dy = sign(.)*std/B * atom_mask
  * atom_mask [B,N] may be NULL (all ones); target NULL in mode 0; loss is a device scalar that is
- * accumulated (zero it first). */
+ * accumulated (zero it first).  `ragged` (nullable): y / dy are compact (atom_mask must be NULL), energies
+ * are still ordered by the molecule's index in the padded batch. */
 int sake_energy_head(int32_t B, int32_t N, int32_t out_features, int32_t mode, const float* y,
                      const float* atom_mask, const float* target, float mean, float std,
-                     float* energy, float* loss, float* dy, sake_stream_t stream);
+                     float* energy, float* loss, float* dy, const void* ragged, sake_stream_t stream);
 
 /* One optimiser step over a flat fp32 parameter vector, the chain every training driver uses
  * (scripts/qm9/run.py:134-138): additive_weight_decay(wd) -> clip(max_delta, element-wise)

@@ -51,17 +51,25 @@ lib.sake_layer_saved_bytes.argtypes = [_DP]
 lib.sake_layer_saved_bytes.restype = _sz
 lib.sake_layer_scratch_bytes.argtypes = [_DP, C.c_int, C.c_int]
 lib.sake_layer_scratch_bytes.restype = _sz
-lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+lib.sake_ragged_bytes.argtypes = [_i32, _i32]
+lib.sake_ragged_bytes.restype = _sz
+lib.sake_ragged_prepare.argtypes = [_i32, _i32, _vp, _vp, _sz, _vp]
+lib.sake_ragged_prepare.restype = C.c_int
+lib.sake_ragged_gather.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp, _vp]
+lib.sake_ragged_gather.restype = C.c_int
+lib.sake_ragged_scatter.argtypes = [_vp, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp]
+lib.sake_ragged_scatter.restype = C.c_int
+lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _sz, _vp, _sz, _vp]
 lib.sake_layer_fwd.restype = C.c_int
-lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _sz,
+lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SakeLayerGrads), _vp, _sz, _vp]
 lib.sake_layer_bwd.restype = C.c_int
-lib.sake_dense_fwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
+lib.sake_dense_fwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.sake_dense_fwd.restype = C.c_int
-lib.sake_dense_bwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.sake_dense_bwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.sake_dense_bwd.restype = C.c_int
-lib.sake_energy_head.argtypes = [_i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
+lib.sake_energy_head.argtypes = [_i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]
 lib.sake_energy_head.restype = C.c_int
 lib.sake_adam_step.argtypes = [_i64, _vp, _vp, _vp, _vp, _i32] + [C.c_float] * 7 + [_vp]
 lib.sake_adam_step.restype = C.c_int
@@ -79,7 +87,7 @@ lib.sake_launch_count.restype = C.c_ulonglong
 lib.sake_selftest_tcgen05.argtypes = [C.POINTER(C.c_float), _vp]
 lib.sake_selftest_tcgen05.restype = C.c_int
 
-EXPORTS = ("sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
+EXPORTS = ("sake_ragged_bytes", "sake_ragged_prepare", "sake_ragged_gather", "sake_ragged_scatter", "sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
            "sake_layer_scratch_bytes", "sake_layer_fwd", "sake_layer_bwd", "sake_dense_fwd",
            "sake_dense_bwd", "sake_selftest_tcgen05", "sake_energy_head", "sake_adam_step",
            "sake_profile_begin", "sake_profile_collect", "sake_launch_count", "sake_selftest_xtg", "sake_debug_counters", "sake_debug_counters_bwd")

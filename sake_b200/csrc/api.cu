@@ -17,9 +17,9 @@ void set_error(const char* fmt, ...) {
 }
 
 int dense_fwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b, float* y,
-              cudaStream_t st);
+              const RaggedHdr* hdr, cudaStream_t st);
 int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
-              const float* dy, float* dx, float* dw, float* db, cudaStream_t st);
+              const float* dy, float* dx, float* dw, float* db, const RaggedHdr* hdr, cudaStream_t st);
 int tc_selftest(float* max_abs_err, cudaStream_t st);
 int tc_debug_counters(unsigned long long* out8);
 int tc_debug_counters_bwd(unsigned long long* out16);
@@ -41,6 +41,38 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->has_v = (s->flags & SAKE_HAS_V) != 0;
   d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
   d->spatial = (s->flags & SAKE_NO_SPATIAL) == 0;
+  d->hdr = nullptr; d->rowinfo = nullptr; d->tileinfo = nullptr; d->molinfo = nullptr;
+  return 0;
+}
+// ragged batches (n_real-packed, see ragged.cu): compact tensors, no float mask, tcgen05 engines only
+static int attach_ragged(Dims* d, const void* ragged, const float* mask, int engine) {
+  if (!ragged) return 0;
+  if (mask || d->has_mask) { set_error("a ragged batch carries no float mask (padding atoms are not stored)"); return SAKE_EINVAL; }
+  if (d->N > 128) { set_error("ragged batches need N <= 128 (got %d)", d->N); return SAKE_EUNSUPPORTED; }
+  if (engine == SAKE_ENGINE_FP32) { set_error("ragged batches run on the tcgen05 engines only (H=64, A=4)"); return SAKE_EUNSUPPORTED; }
+  ragged_attach(*d, ragged);
+  return 0;
+}
+
+// Every leaf the configuration reads must be present: a flax tree initialised with v=None has no
+// velocity_mlp (layers.py:226-229), update=False has no v_mixing (layers.py:94,217) — applying such a tree
+// with v / update is a missing-parameter error in the reference, and an error (not a NULL dereference or a
+// silent zero weight) here.  `what` is "params" or "grads".
+template <class PS>
+static int check_leaves(const Dims& d, const PS& p, const char* what) {
+#define SAKE_NEED(field)                                                                                  \
+  if (!p.field) { set_error("%s: required leaf `%s` is NULL for this configuration (update=%d has_v=%d spatial=%d)", \
+                            what, #field, d.update, d.has_v, d.spatial); return SAKE_EINVAL; }
+  SAKE_NEED(rbf_means) SAKE_NEED(rbf_betas) SAKE_NEED(mlp_in_kernel) SAKE_NEED(mlp_in_bias)
+  SAKE_NEED(mlp_out0_kernel) SAKE_NEED(mlp_out0_bias) SAKE_NEED(mlp_out2_kernel) SAKE_NEED(mlp_out2_bias)
+  SAKE_NEED(sem_kernel) SAKE_NEED(sem_bias)
+  SAKE_NEED(node0_kernel) SAKE_NEED(node0_bias) SAKE_NEED(node2_kernel) SAKE_NEED(node2_bias)
+  // flax creates x_mixing / post_norm_mlp even with use_spatial_attention=False (layers.py:208-212 calls
+  // spatial_attention and then zeroes its outputs), and the per-node kernels read them unconditionally
+  SAKE_NEED(x_mixing_kernel) SAKE_NEED(post0_kernel) SAKE_NEED(post0_bias) SAKE_NEED(post2_kernel) SAKE_NEED(post2_bias)
+  if (d.update && d.spatial) { SAKE_NEED(v_mixing_kernel) }
+  if (d.update && d.has_v) { SAKE_NEED(vel0_kernel) SAKE_NEED(vel0_bias) SAKE_NEED(vel2_kernel) }
+#undef SAKE_NEED
   return 0;
 }
 
@@ -160,8 +192,8 @@ size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with
 }
 
 int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
-                   const float* v, const float* mask, float* h_out, float* x_out, float* v_out, void* saved,
-                   size_t saved_bytes, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
+                   const float* v, const float* mask, const void* ragged, float* h_out, float* x_out, float* v_out,
+                   void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
   Dims d;
   int rc = make_dims(dims, &d);
   if (rc) return rc;
@@ -169,12 +201,14 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (d.has_v != (v != nullptr)) { set_error("SAKE_HAS_V flag does not match v pointer"); return SAKE_EINVAL; }
   if (d.has_mask != (mask != nullptr)) { set_error("SAKE_HAS_MASK flag does not match mask pointer"); return SAKE_EINVAL; }
   if (d.update && !v_out) { set_error("update=True needs v_out"); return SAKE_EINVAL; }
+  if ((rc = check_leaves(d, *params, "params"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
   if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small: %zu < %zu", saved_bytes, saved_layout(d).total); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 0, 0);
   if (SL.total > 256 && (!scratch || scratch_bytes < SL.total)) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
+  if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
   Saved sv = carve_saved(d, saved, tc_edge);
@@ -190,13 +224,13 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_fwd(d, *params, x, mask, sv, (char*)scratch + SL.tc, engine, st))) return rc;
   }
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && node_tc_enabled())
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr))
     return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, (char*)scratch + SL.nodew, st);
   return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
 }
 
 int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
-                   const float* v, const float* mask, const void* saved, size_t saved_bytes, const float* dh_out,
+                   const float* v, const float* mask, const void* ragged, const void* saved, size_t saved_bytes, const float* dh_out,
                    const float* dx_out, const float* dv_out, float* dh, float* dx, float* dv,
                    const SakeLayerGrads* grads, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
   Dims d;
@@ -206,12 +240,15 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (d.has_v != (v != nullptr)) { set_error("SAKE_HAS_V flag does not match v pointer"); return SAKE_EINVAL; }
   if (d.has_mask != (mask != nullptr)) { set_error("SAKE_HAS_MASK flag does not match mask pointer"); return SAKE_EINVAL; }
   if (d.has_v && !dv) { set_error("v given but dv is NULL"); return SAKE_EINVAL; }
+  if ((rc = check_leaves(d, *params, "params"))) return rc;
+  if (grads && (rc = check_leaves(d, *grads, "grads"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
   if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 1, grads != nullptr);
   if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
+  if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
   Saved sv = carve_saved(d, const_cast<void*>(saved), tc_edge);
@@ -222,7 +259,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && node_tc_enabled()) {
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr)) {
     if ((rc = gen_node_wt(d, *params, sc, st))) return rc;     // k_node_pre_bwd still reads the transposed copies
     rc = tc_node_post_bwd(d, *params, h, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, b + SL.nodew,
                           b + SL.noded, st);
@@ -256,18 +293,19 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
 }
 
 int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,
-                   const float* kernel, const float* bias, float* y, sake_stream_t stream) {
+                   const float* kernel, const float* bias, float* y, const void* ragged, sake_stream_t stream) {
   if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !y) { set_error("sake_dense_fwd: bad argument"); return SAKE_EINVAL; }
   note_launches(1);
-  return dense_fwd(rows, in_features, out_features, act, x, kernel, bias, y, (cudaStream_t)stream);
+  return dense_fwd(rows, in_features, out_features, act, x, kernel, bias, y, (const RaggedHdr*)ragged, (cudaStream_t)stream);
 }
 
 int sake_dense_bwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,
                    const float* kernel, const float* bias, const float* dy, float* dx, float* dkernel,
-                   float* dbias, sake_stream_t stream) {
+                   float* dbias, const void* ragged, sake_stream_t stream) {
   if (rows < 0 || in_features <= 0 || out_features <= 0 || !x || !kernel || !dy) { set_error("sake_dense_bwd: bad argument"); return SAKE_EINVAL; }
   note_launches(1);
-  return dense_bwd(rows, in_features, out_features, act, x, kernel, bias, dy, dx, dkernel, dbias, (cudaStream_t)stream);
+  return dense_bwd(rows, in_features, out_features, act, x, kernel, bias, dy, dx, dkernel, dbias, (const RaggedHdr*)ragged,
+                   (cudaStream_t)stream);
 }
 
 int sake_debug_counters(unsigned long long* out8) { return tc_debug_counters(out8); }

@@ -7,15 +7,48 @@
 
 namespace sake {
 
+// ---- ragged batches (real atoms only) ---------------------------------------------------------------
+// A padded batch (QM9-style, scripts/qm9/run.py:23-24,35: molecule b has n_real[b] <= N real atoms stored
+// first, mask = outer(m, m)) is processed in a COMPACT layout that holds the real atoms only: molecules are
+// ordered by n_real (stable), molecule b owns n_b consecutive rows and row r owns n consecutive pair slots.
+// The tables below are built on the device from n_real (ragged.cu: sake_ragged_prepare) and every kernel
+// reads its loop bounds from the header, so the host never needs the counts (no sync, CUDA-graph replays
+// stay valid when the next batch has different n_real); grids are sized for the padded worst case.
+struct RaggedHdr {
+  int R;            // real rows (atoms)
+  int num_tiles;    // 128-pair tiles
+  int B;            // molecules
+  int reserved;
+  long long P;      // real pairs = sum n_b^2
+  long long R64;    // = R (64-bit copy: the K extent of the node-level weight-gradient contractions)
+};
+// rowinfo[r]  = {first row of r's molecule, n of that molecule, first pair slot of row r, padded row b*N+i}
+// tileinfo[t] = {first row, rows in the tile, n (uniform inside a tile), first pair slot}
+// molinfo[b]  = {first row of molecule b, n_b}   (b = index in the padded batch)
+
 // Resolved problem description handed to every kernel by value.
 struct Dims {
   int B, N, H, A, K, C;   // C = A*H
-  int R;                  // rows = B*N (one row per receiving atom i)
-  long long P;            // pairs = R*N
+  int R;                  // rows = B*N (one row per receiving atom i); ragged: the padded worst case
+  long long P;            // pairs = R*N                                  ; ragged: the padded worst case
   int Kp;                 // K rounded up to a multiple of 4 (16-byte aligned projection blocks)
   int NP;                 // per-node projection width = 2Kp + 2H
   int update, has_v, has_mask, spatial;
+  const RaggedHdr* hdr;   // NULL: uniform batch (every molecule has N atoms, optional float mask)
+  const int4* rowinfo;
+  const int4* tileinfo;
+  const int2* molinfo;
 };
+// rows / pairs actually present (device side)
+__device__ __forceinline__ int dims_rows(const Dims& d) { return d.hdr ? d.hdr->R : d.R; }
+__device__ __forceinline__ long long dims_pairs(const Dims& d) { return d.hdr ? d.hdr->P : d.P; }
+struct RowInfo { int mol0, n; long long pair0; };
+__device__ __forceinline__ RowInfo row_info(const Dims& d, int row) {
+  RowInfo r;
+  if (d.rowinfo) { const int4 q = __ldg(d.rowinfo + row); r.mol0 = q.x; r.n = q.y; r.pair0 = q.z; }
+  else { r.mol0 = (row / d.N) * d.N; r.n = d.N; r.pair0 = (long long)row * d.N; }
+  return r;
+}
 
 // Layout of the per-node projection buffer nodeproj[R][NP]:
 //   [0,K)            uj = h @ W_in[0:H]            (sender part of mlp_in,   layers.py:30)
@@ -200,6 +233,7 @@ __device__ __forceinline__ void ftanh_sech2_(float x, float& th, float& s2) {
 
 void set_error(const char* fmt, ...);
 void note_launches(int n);
+void ragged_attach(Dims& d, const void* blob);   // ragged.cu: point d.hdr / rowinfo / tileinfo / molinfo into a table blob
 
 #define SAKE_CUDA_CHECK(expr)                                                        \
   do {                                                                               \
@@ -241,7 +275,8 @@ struct XtgArgs {
   int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
   const float* G; int ldg; int gw;     // G source [P, gw]
   int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
-  long long P, pairs_per_cta;
+  long long P, pairs_per_cta;          // ragged batches: P is the padded worst case, the real extent is *Pdev
+  const long long* Pdev;               // device-resident K extent (RaggedHdr::P or ::R64), or NULL
   float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
   float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
   float* partial;                            // scratch for per-CTA partial sums (tc_xtg_partial_bytes()); NULL = atomics

@@ -8,9 +8,12 @@ static constexpr int DR = 16;  // rows per CTA
 
 __global__ void __launch_bounds__(256) k_dense_fwd(long long rows, int in, int out, int act,
                                                    const float* __restrict__ x, const float* __restrict__ w,
-                                                   const float* __restrict__ b, float* __restrict__ y) {
+                                                   const float* __restrict__ b, float* __restrict__ y,
+                                                   const RaggedHdr* hdr) {
   extern __shared__ float sm[];
+  if (hdr) rows = hdr->R;                       // ragged batches: real rows (the grid covers the worst case)
   const long long r0 = (long long)blockIdx.x * DR;
+  if (r0 >= rows) return;
   const int nn = (int)min((long long)DR, rows - r0);
   for (int t = threadIdx.x; t < DR * in; t += blockDim.x) sm[t] = (t / in) < nn ? x[r0 * in + t] : 0.f;
   __syncthreads();
@@ -32,8 +35,10 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
                                                    const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ b, const float* __restrict__ dy,
                                                    float* __restrict__ dx, float* __restrict__ dw,
-                                                   float* __restrict__ db) {
+                                                   float* __restrict__ db, const RaggedHdr* hdr) {
   extern __shared__ float sm[];
+  if (hdr) rows = hdr->R;
+  if ((long long)blockIdx.x * DR >= rows) return;
   float* xs = sm;             // [DR][in]
   float* gs = xs + DR * in;   // [DR][out]  cotangent of the pre-activation
   float* ws = gs + DR * out;  // [in][out + 1]  weights, row stride padded: both access patterns are conflict-free
@@ -84,21 +89,25 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
 }
 
 int dense_fwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b, float* y,
-              cudaStream_t st) {
+              const RaggedHdr* hdr, cudaStream_t st) {
   if (rows == 0) return 0;
   size_t smem = sizeof(float) * DR * in;
-  if (smem > 48 * 1024) { set_error("dense: in_features %d too large", in); return SAKE_EUNSUPPORTED; }
-  k_dense_fwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, y);
+  if (smem > 227 * 1024) { set_error("dense: in_features %d too large", in); return SAKE_EUNSUPPORTED; }
+  static unsigned long long optin = 0;
+  if (smem > 48 * 1024) { const int rc = smem_optin(k_dense_fwd, 227 * 1024, optin); if (rc) return rc; }
+  k_dense_fwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, y, hdr);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
-              const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
+              const float* dy, float* dx, float* dw, float* db, const RaggedHdr* hdr, cudaStream_t st) {
   if (rows == 0) return 0;
   size_t smem = sizeof(float) * (DR * (in + out) + (size_t)in * (out + 1));
-  if (smem > 48 * 1024) { set_error("dense: features %d/%d too large", in, out); return SAKE_EUNSUPPORTED; }
-  k_dense_bwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db);
+  if (smem > 227 * 1024) { set_error("dense: features %d/%d too large", in, out); return SAKE_EUNSUPPORTED; }
+  static unsigned long long optin = 0;   // H = 128 stages 66 KB of weights: opt in beyond the 48 KB default
+  if (smem > 48 * 1024) { const int rc = smem_optin(k_dense_bwd, 227 * 1024, optin); if (rc) return rc; }
+  k_dense_bwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db, hdr);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

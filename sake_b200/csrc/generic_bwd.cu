@@ -477,21 +477,25 @@ __global__ void __launch_bounds__(256) k_mix_bwd_nospatial(Dims d, const float* 
                                                            const float* __restrict__ e, const float* __restrict__ att,
                                                            const float* __restrict__ ghe, float* __restrict__ ge,
                                                            float* __restrict__ gatt, float* __restrict__ gdir) {
-  const int N = d.N, A = d.A, H = d.H, C = d.C;
-  const size_t pr = blockIdx.x;
-  const size_t row = pr / N;
-  const float m = mask ? mask[pr] : 1.0f;
-  for (int f = threadIdx.x; f < H; f += blockDim.x) {
-    float acc = 0.f;
-    for (int a = 0; a < A; ++a) acc = fmaf(m * ghe[row * C + f * A + a], att[pr * A + a], acc);
-    ge[pr * H + f] = acc;
+  const int A = d.A, H = d.H, C = d.C;
+  const size_t row = blockIdx.x;                       // one CTA per receiving atom, all its senders
+  if ((int)row >= dims_rows(d)) return;
+  const RowInfo ri = row_info(d, (int)row);
+  for (int j = 0; j < ri.n; ++j) {
+    const size_t pr = (size_t)ri.pair0 + j;
+    const float m = mask ? mask[pr] : 1.0f;
+    for (int f = threadIdx.x; f < H; f += blockDim.x) {
+      float acc = 0.f;
+      for (int a = 0; a < A; ++a) acc = fmaf(m * ghe[row * C + f * A + a], att[pr * A + a], acc);
+      ge[pr * H + f] = acc;
+    }
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+      float acc = 0.f;
+      for (int f = 0; f < H; ++f) acc = fmaf(m * ghe[row * C + f * A + a], e[pr * H + f], acc);
+      gatt[pr * A + a] = acc;
+    }
+    if (threadIdx.x < 3) gdir[pr * 3 + threadIdx.x] = 0.f;
   }
-  for (int a = threadIdx.x; a < A; a += blockDim.x) {
-    float acc = 0.f;
-    for (int f = 0; f < H; ++f) acc = fmaf(m * ghe[row * C + f * A + a], e[pr * H + f], acc);
-    gatt[pr * A + a] = acc;
-  }
-  if (threadIdx.x < 3) gdir[pr * 3 + threadIdx.x] = 0.f;
 }
 
 // dWx[c][c'] += sum_p E[p][c] * gZ[p][c']
@@ -847,7 +851,8 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
   float* gp = sm;               // [NODES][NP]
   float* hs = gp + NODES * NP;  // [NODES][H]
   const int r0 = blockIdx.x * NODES;
-  const int nn = min(NODES, d.R - r0);
+  if (r0 >= dims_rows(d)) return;                  // ragged: the grid covers the padded worst case
+  const int nn = min(NODES, dims_rows(d) - r0);
   for (int t = threadIdx.x; t < NODES * NP; t += blockDim.x) gp[t] = (t / NP) < nn ? gproj[(size_t)r0 * NP + t] : 0.f;
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) hs[t] = (t / H) < nn ? h[(size_t)r0 * H + t] : 0.f;
   __syncthreads();
@@ -987,7 +992,8 @@ int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, Xtg
     XtgArgs q;
     memset(&q, 0, sizeof(q));
     q.X = X; q.ldx = NB_LD; q.xw = xw; q.ones_col = ones; q.G = G; q.ldg = NB_LD; q.gw = gw; q.MXpad = mxpad; q.NG = ng;
-    q.P = d.R; q.out = out; q.ldo = ldo; q.out_rows = out_rows; q.out_cols = out_cols;
+    q.P = d.R; q.Pdev = d.hdr ? &d.hdr->R64 : nullptr;
+    q.out = out; q.ldo = ldo; q.out_rows = out_rows; q.out_cols = out_cols;
     q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld;
     return L.push(q);
   };
@@ -1036,7 +1042,7 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
                 const BwdScratch& sc, float* gWx, cudaStream_t st) {
   int rc;
   if (!d.spatial) {
-    k_mix_bwd_nospatial<<<(unsigned)d.P, 64, 0, st>>>(d, mask, sv.e, sv.att, sc.ghe, sc.ge, sc.gatt, sc.gdir);
+    k_mix_bwd_nospatial<<<(unsigned)d.R, 64, 0, st>>>(d, mask, sv.e, sv.att, sc.ghe, sc.ge, sc.gatt, sc.gdir);
     note_launches(1);
     SAKE_CUDA_CHECK(cudaGetLastError());
     return 0;

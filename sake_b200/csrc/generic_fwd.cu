@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restric
   extern __shared__ float sm[];
   float* hs = sm;  // [NODES][H]
   const int r0 = blockIdx.x * NODES;
-  const int nn = min(NODES, d.R - r0);
+  if (r0 >= dims_rows(d)) return;                  // ragged: the grid covers the padded worst case
+  const int nn = min(NODES, dims_rows(d) - r0);
   for (int t = threadIdx.x; t < nn * d.H; t += blockDim.x) hs[t] = h[(size_t)r0 * d.H + t];
   __syncthreads();
   const int H = d.H, K = d.K;
@@ -130,14 +131,16 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
                                                   const float* __restrict__ e, const float* lg, float* att,
                                                   float* __restrict__ he) {
   extern __shared__ float sm[];
-  const int N = d.N, A = d.A, H = d.H, C = d.C;
+  const int A = d.A, H = d.H, C = d.C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int row = blockIdx.x * nw + warp;
-  if (row >= d.R) return;
-  float* as = sm + (size_t)warp * N * A;  // [N][A]
-  float* arow = att + (size_t)row * N * A;
-  const float* mrow = mask ? mask + (size_t)row * N : nullptr;
-  const float* lrow = lg + (size_t)row * N * A;        // logits (may alias att: read completely before any write)
+  if (row >= dims_rows(d)) return;
+  const RowInfo ri = row_info(d, row);                 // ragged batches: n senders, pair slots from ri.pair0
+  const int N = ri.n;
+  float* as = sm + (size_t)warp * d.N * A;  // [N][A]
+  float* arow = att + (size_t)ri.pair0 * A;
+  const float* mrow = mask ? mask + (size_t)ri.pair0 : nullptr;
+  const float* lrow = lg + (size_t)ri.pair0 * A;       // logits (may alias att: read completely before any write)
   for (int t = lane; t < N * A; t += 32) as[t] = lrow[t];
   __syncwarp();
   for (int a = 0; a < A; ++a) {
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   if (A == 4 && H == 64) {
     // lane owns f = 2*lane, 2*lane+1 (coalesced float2 loads of e) and all four heads
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* ep = e + (size_t)row * N * 64 + 2 * lane;
+    const float* ep = e + (size_t)ri.pair0 * 64 + 2 * lane;
     for (int j0 = 0; j0 < N; j0 += 8) {
       float2 ev[8];
 #pragma unroll
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
       for (int j = 0; j < N; ++j) {
         float w = as[j * A + a];
         if (mrow) w *= mrow[j];
-        acc = fmaf(e[((size_t)row * N + j) * H + f], w, acc);
+        acc = fmaf(e[((size_t)ri.pair0 + j) * H + f], w, acc);
       }
       he[(size_t)row * C + c] = acc;
     }

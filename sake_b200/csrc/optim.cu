@@ -9,14 +9,18 @@ namespace sake {
 __global__ void __launch_bounds__(128) k_energy_head(int B, int N, int out, int mode, const float* __restrict__ y,
                                                      const float* __restrict__ am, const float* __restrict__ target,
                                                      float mean, float std, float* __restrict__ energy,
-                                                     float* __restrict__ loss, float* __restrict__ dy) {
+                                                     float* __restrict__ loss, float* __restrict__ dy,
+                                                     const int2* __restrict__ molinfo) {
   __shared__ float red[4];
   __shared__ float gsh;
   const int b = blockIdx.x;
+  // ragged batches: y / dy are compact, molecule b owns rows [molinfo[b].x, + molinfo[b].y) and there is no mask
+  const size_t base = molinfo ? (size_t)molinfo[b].x : (size_t)b * N;
+  if (molinfo) N = molinfo[b].y;
   float s = 0.f;
   for (int t = threadIdx.x; t < N * out; t += blockDim.x) {
     float m = am ? am[(size_t)b * N + t / out] : 1.0f;
-    s = fmaf(y[(size_t)b * N * out + t], m, s);
+    s = fmaf(y[base * out + t], m, s);
   }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(128) k_energy_head(int B, int N, int out, int 
     const float g = gsh;
     for (int t = threadIdx.x; t < N * out; t += blockDim.x) {
       float m = am ? am[(size_t)b * N + t / out] : 1.0f;
-      dy[(size_t)b * N * out + t] = g * m;
+      dy[base * out + t] = g * m;
     }
   }
 }
@@ -87,14 +91,22 @@ extern "C" {
 
 int sake_energy_head(int32_t B, int32_t N, int32_t out_features, int32_t mode, const float* y,
                      const float* atom_mask, const float* target, float mean, float std, float* energy,
-                     float* loss, float* dy, sake_stream_t stream) {
+                     float* loss, float* dy, const void* ragged, sake_stream_t stream) {
+  const int2* molinfo = nullptr;
+  if (ragged) {
+    if (atom_mask) { set_error("sake_energy_head: ragged batches carry no atom mask"); return SAKE_EINVAL; }
+    Dims d;
+    d.B = B; d.N = N;
+    ragged_attach(d, ragged);
+    molinfo = d.molinfo;
+  }
   if (B < 0 || N <= 0 || out_features <= 0 || !y || (mode == 1 && !target) || (mode != 0 && mode != 1)) {
     set_error("sake_energy_head: bad argument");
     return SAKE_EINVAL;
   }
   if (B == 0) return 0;
   k_energy_head<<<B, 128, 0, (cudaStream_t)stream>>>(B, N, out_features, mode, y, atom_mask, target, mean, std,
-                                                     energy, loss, dy);
+                                                     energy, loss, dy, molinfo);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
   const float* s_b2 = svec + 128;
   const float* s_bq = svec + 192;
   const int K = a.K, Kp = a.Kp, NP = a.NP;
-  const int ntl = (a.g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ntl = (geom_tiles(a.g) - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   uint32_t ph = 0;
   constexpr uint32_t idesc64 = umma_idesc(2, 128, 64);
   constexpr uint32_t idesc80 = umma_idesc(2, 128, 80);
@@ -207,22 +207,22 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 
   for (int it = grp; it < ntl; it += EDGE_GROUPS) {
     const int tile = blockIdx.x + it * gridDim.x;
-    bool valid, seg_end;
+    bool valid;
     int row, j;
-    tile_pair(a.g, tile, pl, valid, row, j, seg_end);
+    long long prx;
+    tile_pair(tile_desc(a.g, tile), pl, valid, row, j, prx);
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, nrm = 0.f, tt = 0.f, m = 1.0f;
-    size_t prx = 0;
     const float* nj = a.proj;
     const float* ni = a.proj;
     bool diag = false;
+    if (!valid) prx = 0;
     if (valid) {
-      prx = (size_t)row * a.g.N + j;
-      const int b = row / a.g.N;
-      diag = (row - b * a.g.N) == j;
-      nj = a.proj + (size_t)(b * a.g.N + j) * NP;
+      const int mol0 = geom_mol0(a.g, row);
+      diag = (row - mol0) == j;
+      nj = a.proj + (size_t)(mol0 + j) * NP;
       ni = a.proj + (size_t)row * NP;
       const float* xi = a.x + (size_t)row * 3;
-      const float* xj = a.x + (size_t)(b * a.g.N + j) * 3;
+      const float* xj = a.x + (size_t)(mol0 + j) * 3;
       r0 = xj[0] - xi[0]; r1 = xj[1] - xi[1]; r2 = xj[2] - xi[2];
       nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);     // functional.py:14-17
       tt = fexp_(-nrm);                                                    // utils.py:62-64 (alpha = 1, lower = 0)
@@ -511,13 +511,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 // is the identity on the gradient), g_q = g_s * celu_2'(q) with celu_2'(q) = 1 (q > 0) or e^{q/2} =
 // celu_2(q)/2 + 1 read off the saved logits (the -1e5 offsets of self / masked pairs meet att = 0).
 // Lane l owns the elements t = l, l+32, ... of the [N,4] row, i.e. always head a = l & 3.
-__global__ void __launch_bounds__(256) k_attn_bwd_tc(int R, int N, const float* __restrict__ att,
+__global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __restrict__ att,
                                                      const float* __restrict__ logit, float* __restrict__ gatt) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= R) return;
-  const size_t base = (size_t)row * N * 4;
-  const int n4 = N * 4;
+  if (row >= dims_rows(d)) return;
+  const RowInfo ri = row_info(d, row);
+  const size_t base = (size_t)ri.pair0 * 4;
+  const int n4 = ri.n * 4;
   constexpr int MAXI = 8;                                  // register-resident up to N = 64; longer rows re-read
   float av[MAXI], gv[MAXI];
   float s = 0.f;
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_tc(int R, int N, const float* 
 }
 
 int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
-  k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d.R, d.N, sv.att, sv.logit, sc.gatt);
+  k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d, sv.att, sv.logit, sc.gatt);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -554,13 +555,16 @@ int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream
 
 // ---- reductions of the per-pair record over senders / receivers -----------------------------------
 // gproj[n] = [ sum_i gu[(i,n)] | sum_j gu[(n,j)] | sum_i gz1[(i,n)] | sum_j gz1[(n,j)] ],  dx[n] += sum_i g_r[(i,n)] - sum_j g_r[(n,j)]
-__global__ void __launch_bounds__(128) k_pair_reduce(int N, int K, int Kp, int NP, const float* __restrict__ PB,
+__global__ void __launch_bounds__(128) k_pair_reduce(Dims d, const float* __restrict__ PB,
                                                      float* __restrict__ gproj, float* __restrict__ dx) {
   const int n = blockIdx.x;
-  const int b = n / N, a = n - b * N;
+  if (n >= dims_rows(d)) return;
+  const int K = d.K, Kp = d.Kp, NP = d.NP;
+  const RowInfo ri = row_info(d, n);
+  const int N = ri.n, a = n - ri.mol0;                     // atoms of this molecule, index of n inside it
   const int c = threadIdx.x;                               // column of the record [0,128)
-  const float* rowp = PB + ((size_t)n * N) * PB_LD + c;                    // (n, j) j = 0..N-1
-  const float* colp = PB + ((size_t)b * N * N + a) * PB_LD + c;            // (i, n) i = 0..N-1, stride N records
+  const float* rowp = PB + (size_t)ri.pair0 * PB_LD + c;                            // (n, j) j = 0..N-1
+  const float* colp = PB + (size_t)(ri.pair0 - (long long)a * N + a) * PB_LD + c;   // (i, n) i = 0..N-1, stride N records
   float si = 0.f, sj = 0.f;
   for (int q = 0; q < N; ++q) {
     si += rowp[(size_t)q * PB_LD];
@@ -652,7 +656,7 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_edge<true>, smem, optin); if (rc) return rc; }
   k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
-  k_pair_reduce<<<d.R, 128, 0, st>>>(d.N, d.K, d.Kp, d.NP, PB, sc.gproj, dx);
+  k_pair_reduce<<<d.R, 128, 0, st>>>(d, PB, sc.gproj, dx);
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   if (g) {
@@ -660,21 +664,21 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     // dW2, db2 (layers.py:24):  a1^T g_e
     memset(&q, 0, sizeof(q));
     q.X = a1buf; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.ge; q.ldg = 64; q.gw = 64; q.MXpad = 128; q.NG = 64;
-    q.P = d.P; q.out = g->mlp_out2_kernel; q.ldo = 64; q.out_rows = 64; q.out_cols = 64;
+    q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->mlp_out2_kernel; q.ldo = 64; q.out_rows = 64; q.out_cols = 64;
     q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64;
     L.push(q);
     // dW1[2H : 2H+K+1] (RBF channels + distance row, layers.py:22) and the RBF mean / width sums
     SAKE_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(float) * 2 * PB_LD, st));
     memset(&q, 0, sizeof(q));
     q.X = gbuf; q.ldx = 64; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
-    q.P = d.P; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
+    q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
     q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD;
     L.push(q);
     L.mb_extra = extra; L.mu = p.rbf_means; L.beta = p.rbf_betas; L.g_mu = g->rbf_means; L.g_beta = g->rbf_betas; L.K = d.K;
     // dWs, dbs (layers.py:80):  e^T g_q
     memset(&q, 0, sizeof(q));
     q.X = sv.e; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.gw = 4; q.MXpad = 128; q.NG = 16;
-    q.P = d.P; q.out = g->sem_kernel; q.ldo = 4; q.out_rows = 64; q.out_cols = 4;
+    q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->sem_kernel; q.ldo = 4; q.out_rows = 64; q.out_cols = 4;
     q.extra = g->sem_bias; q.extra_rows = 1; q.extra_ld = 4;
     if (L.push(q)) { set_error("xtg list full"); return SAKE_EINVAL; }
   }

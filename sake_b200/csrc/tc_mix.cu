@@ -298,7 +298,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_ptr;
-  const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  const int ntl = (geom_tiles(g) - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (TMA)
@@ -369,23 +369,21 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int buf = it & 1, use = it >> 1;
-      bool valid, seg_end;
+      bool valid;
       int row, j;
-      tile_pair(g, tile, p, valid, row, j, seg_end);
+      long long prx;
+      tile_pair(tile_desc(g, tile), p, valid, row, j, prx);
       if (it + 1 < ntl) {                           // pull the next tile's e / att rows into L2
-        bool v2, se2;
+        bool v2;
         int row2, j2;
-        tile_pair(g, tile + gridDim.x, p, v2, row2, j2, se2);
-        if (v2) {
-          const size_t px2 = (size_t)row2 * g.N + j2;
-          prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4);
-        }
+        long long px2;
+        tile_pair(tile_desc(g, tile + gridDim.x), p, v2, row2, j2, px2);
+        if (v2) { prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4); }
       }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
-        const size_t prx = (size_t)row * g.N + j;
         at = *reinterpret_cast<const float4*>(att + prx * 4);
         const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
 #pragma unroll
@@ -393,9 +391,8 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           float4 t4 = __ldg(ep + q);
           ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
         }
-        const int b = row / g.N;
         const float* xi = x + (size_t)row * 3;
-        const float* xj = x + (size_t)(b * g.N + j) * 3;
+        const float* xj = x + (size_t)(geom_mol0(g, row) + j) * 3;
         const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
         const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);   // functional.py:14-17
         const float inv = 1.0f / (nrm + 1e-5f);                                      // layers.py:115
@@ -439,9 +436,8 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int buf = it & 1, use = it >> 1;
-      int row0, nsegs, seglen;
-      if (g.nseg == 1) { row0 = tile * g.rpt; nsegs = min(g.rpt, g.R - row0); seglen = g.N; }
-      else { row0 = tile / g.nseg; const int seg = tile - row0 * g.nseg; nsegs = 1; seglen = min(g.js, g.N - seg * g.js); }
+      const TileDesc td = tile_desc(g, tile);
+      const int row0 = td.row0, nsegs = td.nrows, seglen = td.n;
       mbar_wait_warp(sm.acc_full + buf, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + mh * 128;
@@ -558,9 +554,10 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_ptr;
-  const int ntl = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ntl = (geom_tiles(g) - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  const bool use_tsm = g.rpt <= TSM_ROWS;          // T rows of the tile are staged in smem by TMA
+  // T / ghe rows of a tile are staged in smem by TMA when the tile has few enough receiver rows.  Ragged
+  // batches decide per tile, so every role counts the staged tiles itself (`tn`: phase of the t_* / g_* barriers).
   // register re-balancing between the warpgroups (the kernel starts with 128 per thread): the TMA / MMA
   // group keeps 40, the epilogue groups grow to 168 so that a 32-column block keeps all its chains in flight
   // (each setmaxnreg sits inside its role's branch: ptxas budgets registers per branch only then)
@@ -568,26 +565,22 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
    setmaxnreg_dec<40>();
    if (warp == 0) {
     if (lane == 0) {
-      int pos = 0;
+      int pos = 0, tn = 0;
       for (int it = 0; it < ntl; ++it) {
+        const TileDesc td = tile_desc(g, blockIdx.x + it * gridDim.x);
+        const bool use_tsm = td.nrows <= TSM_ROWS;
         if (use_tsm) {
-          const int tile = blockIdx.x + it * gridDim.x;
-          const int row0 = g.nseg == 1 ? tile * g.rpt : tile / g.nseg;
-          const int nrows = min(g.rpt, g.R - row0);
-          mbar_wait(sm.t_empty, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(sm.t_full, (uint32_t)nrows * CC * 16);
-          bulk_g2s(sm.Tsm, T4 + (size_t)row0 * CC, (uint32_t)nrows * CC * 16, sm.t_full);
+          mbar_wait(sm.t_empty, (tn & 1) ^ 1);
+          mbar_arrive_expect_tx(sm.t_full, (uint32_t)td.nrows * CC * 16);
+          bulk_g2s(sm.Tsm, T4 + (size_t)td.row0 * CC, (uint32_t)td.nrows * CC * 16, sm.t_full);
         }
         for (int c2 = 0; c2 < 2 * NCH; ++c2, ++pos) {
           if (c2 == NCH && use_tsm) {
             // ghe rows for epilogue 2: requested only now, so that waiting for epilogue 2 of the previous tile
             // (g_empty) cannot hold back the GEMM1 weight stream; GEMM2 needs that epilogue finished anyway
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int row0 = g.nseg == 1 ? tile * g.rpt : tile / g.nseg;
-            const int nrows = min(g.rpt, g.R - row0);
-            mbar_wait(sm.g_empty, (it & 1) ^ 1);
-            mbar_arrive_expect_tx(sm.g_full, (uint32_t)nrows * CC * 4);
-            bulk_g2s(sm.ghS, ghe + (size_t)row0 * CC, (uint32_t)nrows * CC * 4, sm.g_full);
+            mbar_wait(sm.g_empty, (tn & 1) ^ 1);
+            mbar_arrive_expect_tx(sm.g_full, (uint32_t)td.nrows * CC * 4);
+            bulk_g2s(sm.ghS, ghe + (size_t)td.row0 * CC, (uint32_t)td.nrows * CC * 4, sm.g_full);
           }
           const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
           const uint8_t* src = (c2 < NCH ? w1img + (size_t)c2 * CF::NSPLIT * W_IMG
@@ -597,6 +590,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           for (int sp = 0; sp < CF::NSPLIT; ++sp)
             bulk_g2s(sm.w_img(s) + sp * W_IMG, src + (size_t)sp * W_IMG, W_IMG, sm.full_w + s);
         }
+        tn += use_tsm ? 1 : 0;
       }
     }
    } else if (warp == 1) {
@@ -651,22 +645,20 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     const long long bw_begin = clock64();
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      bool valid, seg_end;
+      bool valid;
       int row, j;
-      tile_pair(g, tile, p, valid, row, j, seg_end);
+      long long prx;
+      tile_pair(tile_desc(g, tile), p, valid, row, j, prx);
       if (it + 1 < ntl) {                           // pull the next tile's e / att rows into L2
-        bool v2, se2;
+        bool v2;
         int row2, j2;
-        tile_pair(g, tile + gridDim.x, p, v2, row2, j2, se2);
-        if (v2) {
-          const size_t px2 = (size_t)row2 * g.N + j2;
-          prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4);
-        }
+        long long px2;
+        tile_pair(tile_desc(g, tile + gridDim.x), p, v2, row2, j2, px2);
+        if (v2) { prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4); }
       }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
-        const size_t prx = (size_t)row * g.N + j;
         at = *reinterpret_cast<const float4*>(att + prx * 4);
         const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
 #pragma unroll
@@ -722,31 +714,33 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int PPC = CF::KCH / 32;                   // 32-column blocks per ring chunk (1: tf32, 2: 16-bit formats)
     long long ew[6] = {0, 0, 0, 0, 0, 0};
+    int tn = 0;
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      bool valid, seg_end;
+      const TileDesc td = tile_desc(g, tile);
+      const bool use_tsm = td.nrows <= TSM_ROWS;
+      bool valid;
       int row, j;
-      tile_pair(g, tile, p, valid, row, j, seg_end);
+      long long prx;
+      tile_pair(td, p, valid, row, j, prx);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, m = 0.f;
-      size_t prx = 0;
       int trow = 0;                                   // row of the T operand (any valid row for idle lanes: d = 0)
+      if (!valid) prx = 0;
       if (valid) {
-        prx = (size_t)row * g.N + j;
-        const int b = row / g.N;
         const float* xi = x + (size_t)row * 3;
-        const float* xj = x + (size_t)(b * g.N + j) * 3;
+        const float* xj = x + (size_t)(geom_mol0(g, row) + j) * 3;
         const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
         const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
         const float inv = 1.0f / (nrm + 1e-5f);
         m = mask ? mask[prx] : 1.0f;
         d0 = r0 * inv * m; d1 = r1 * inv * m; d2 = r2 * inv * m;
-        trow = use_tsm ? row - (g.nseg == 1 ? tile * g.rpt : row) : row;
+        trow = use_tsm ? row - td.row0 : row;
       }
       const float4* Tg = T4 + (size_t)trow * CC;      // global copy of the row
       const float4* Ts = sm.Tsm + trow * CC;          // TMA-staged copy (use_tsm)
       // ---------------- epilogue 1: dZ chunks for GEMM2 (this half owns ring slots of parity hh)
       const long long e_t0 = dbg == 7 ? clock64() : 0;
-      if (use_tsm) mbar_wait(sm.t_full, it & 1);
+      if (use_tsm) mbar_wait(sm.t_full, tn & 1);
       mbar_wait(d1_full, it & 1);
       tc_fence_after();
       const long long e_t1 = dbg == 7 ? clock64() : 0;
@@ -808,7 +802,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       // ---------------- epilogue 2: dE -> g_e, g_att   (this half owns f in [32 hh, 32 hh + 32))
       const long long e_t3 = dbg == 7 ? clock64() : 0;
       ew[4] += e_t3 - e_t1;
-      if (use_tsm) mbar_wait(sm.g_full, it & 1);
+      if (use_tsm) mbar_wait(sm.g_full, tn & 1);
       mbar_wait(d2_full, it & 1);
       tc_fence_after();
       const long long e_t4 = dbg == 7 ? clock64() : 0;
@@ -842,7 +836,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       }
       tc_fence_before();
       mbar_arrive(d2_empty);
-      if (use_tsm) mbar_arrive(sm.g_empty);          // ghe rows of this tile are consumed
+      if (use_tsm) { mbar_arrive(sm.g_empty); ++tn; }   // ghe rows of this tile are consumed
       // the two column halves of a pair meet once per tile: half 1 hands its partial g_dir / g_att to half 0
       if (hh == 1) { sm.gdX[p] = make_float4(g0, g1, g2, 0.f); sm.gaX[p] = make_float4(ga0, ga1, ga2, ga3); }
       const long long e_t5 = dbg == 7 ? clock64() : 0;
@@ -1047,7 +1041,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     memset(&a, 0, sizeof(a));
     a.e = sv.e; a.att = sv.att; a.xw = CC; a.ones_col = -1;
     a.G = sc.gZ; a.ldg = CC; a.gw = CC;
-    a.MXpad = CC; a.NG = CC; a.P = d.P;
+    a.MXpad = CC; a.NG = CC; a.P = d.P; a.Pdev = d.hdr ? &d.hdr->P : nullptr;
     a.out = gWx; a.ldo = CC; a.out_rows = CC; a.out_cols = CC;
     if (L.push(a)) { set_error("xtg list full"); return SAKE_EINVAL; }
   }

@@ -74,6 +74,7 @@ __device__ __forceinline__ void nt_store_unit(uint8_t* img, int row, int u, cons
 
 struct NodeFwdArgs {
   int R, N, update, has_v, spatial;
+  const RaggedHdr* hdr; const int4* rowinfo;             // ragged batches (no mask): rows from hdr, n per row
   const float *h, *x, *v, *mask, *ssum, *he;
   const uint8_t* wimg;
   const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
@@ -81,6 +82,8 @@ struct NodeFwdArgs {
 };
 
 __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
+  const int nrows_real = a.hdr ? a.hdr->R : a.R;
+  if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024_shared(smem_raw);
   uint8_t* img = base;                                   // A chunk image {hi, lo}: 32 KB
@@ -145,9 +148,10 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
   };
 
   const int n = blockIdx.x * NT_TILE + tid;
-  const bool valid = n < a.R;
+  const bool valid = n < nrows_real;
   const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
+  if (a.rowinfo) den = den2 = (float)__ldg(a.rowinfo + row).y;   // unpadded molecule: mean over its own n atoms
   if (a.mask && valid) {
     float ms = 0.f;
     const float* mr = a.mask + row * a.N;
@@ -314,6 +318,7 @@ constexpr int ND_LD = 320;                   // stash row: silu'(tp1) silu'(tp2)
 
 struct NodeBwdArgs {
   int R, N, update, has_v, spatial;
+  const RaggedHdr* hdr; const int4* rowinfo;
   const float *h, *v, *mask, *ssum, *he, *dh_out, *dx_out, *dv_out;
   const uint8_t* wimg;
   const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
@@ -328,6 +333,8 @@ __device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     
 }
 
 __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+  const int nrows_real = a.hdr ? a.hdr->R : a.R;
+  if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024_shared(smem_raw);
   uint8_t* imgA = base;                                  // A image, K chunk 0 (or the serial chunk buffer): 32 KB
@@ -402,9 +409,10 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   // wc always names the chunk the next run_chunk will consume (chunk 0 is requested in the prologue)
 
   const int n = blockIdx.x * NT_TILE + tid;
-  const bool valid = n < a.R;
+  const bool valid = n < nrows_real;
   const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
+  if (a.rowinfo) den = den2 = (float)__ldg(a.rowinfo + row).y;   // unpadded molecule: mean over its own n atoms
   if (a.mask && valid) {
     float ms = 0.f;
     const float* mr = a.mask + row * a.N;
@@ -729,8 +737,10 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 }
 
 // gWv[c] += sum_n sum_d ssum[n][c][d] * g_dv[n][d] / den2[n]     (layers.py:94,220-223; training only)
-__global__ void __launch_bounds__(256) k_wv_grad(int R, const float* __restrict__ ssum, const float* __restrict__ qv,
-                                                 float* __restrict__ gWv) {
+__global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, const float* __restrict__ ssum,
+                                                 const float* __restrict__ qv, float* __restrict__ gWv) {
+  if (hdr) R = hdr->R;
+  if ((int)blockIdx.x * 64 >= R) return;
   const int c = threadIdx.x;
   const int n0 = blockIdx.x * 64, n1 = min(R, n0 + 64);
   float acc = 0.f;
@@ -755,6 +765,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   NodeBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
+  a.hdr = d.hdr; a.rowinfo = d.rowinfo;
   a.h = h; a.v = v; a.mask = mask; a.ssum = sv.ssum; a.he = sv.he;
   a.dh_out = dh_out; a.dx_out = dx_out; a.dv_out = dv_out; a.wimg = wimg;
   a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
@@ -768,7 +779,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_node_post_bwd, smem, optin); if (rc) return rc; }
   k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
-  if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, sv.ssum, a.qv, g->v_mixing_kernel);
+  if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 3 : 2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -784,6 +795,7 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   NodeFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
+  a.hdr = d.hdr; a.rowinfo = d.rowinfo;
   a.h = h; a.x = x; a.v = v; a.mask = mask; a.ssum = sv.ssum; a.he = sv.he; a.wimg = wimg;
   a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;

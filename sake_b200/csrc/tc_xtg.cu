@@ -100,6 +100,24 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
 }
 
 struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
+
+// K extent, slice per CTA and number of working CTAs of one problem.  Uniform batches: the host's values.
+// Ragged batches: the extent lives in device memory (a.Pdev), the host sized the grid and the partial-sum
+// buffer for a.gx CTAs, and the split is recomputed here so that the REAL pairs are spread over all of them.
+struct XtgSplit { long long P, per_cta; int gx; };
+__device__ __forceinline__ XtgSplit xtg_split(const XtgArgs& a) {
+  XtgSplit s;
+  s.P = a.P; s.per_cta = a.pairs_per_cta; s.gx = a.gx;
+  if (a.Pdev != nullptr) {
+    s.P = *a.Pdev;
+    const long long stages = (s.P + 31) / 32;             // XKP pairs per stage
+    long long per = (stages + a.gx - 1) / a.gx;
+    if (per < 4) per = 4;
+    s.per_cta = per * 32;
+    s.gx = (int)((s.P + s.per_cta - 1) / s.per_cta);
+  }
+  return s;
+}
 __device__ __align__(16) float g_xtg_zeros[256];   // a source row of zeros (pair rows past the end of a contraction)
 
 // TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
@@ -114,7 +132,8 @@ template <int ENGINE, int TCOLS, bool LEAN, int MINB>
 __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_constant__ XtgBatch batch, int nstage) {
   using CF = XCfg<ENGINE>;
   const XtgArgs& a = batch.a[blockIdx.y];
-  if ((int)blockIdx.x >= a.gx) return;                        // CTA beyond this problem's range
+  const XtgSplit split = xtg_split(a);
+  if ((int)blockIdx.x >= split.gx) return;                    // CTA beyond this problem's range
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024_shared(smem_raw);
   const int xblocks = a.MXpad / XBLK;
@@ -137,8 +156,8 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tptr;
-  const long long p_beg = (long long)blockIdx.x * a.pairs_per_cta;
-  const long long p_end = min(a.P, p_beg + a.pairs_per_cta);
+  const long long p_beg = (long long)blockIdx.x * split.per_cta;
+  const long long p_end = min(split.P, p_beg + split.per_cta);
   const int nst = p_end > p_beg ? (int)((p_end - p_beg + XKP - 1) / XKP) : 0;
   const int MH = a.MXpad / 128;
 
@@ -393,7 +412,7 @@ __global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_c
   __shared__ float red[XRED_SLICES][128];
   const XtgArgs& a = batch.a[blockIdx.y];
   const int col = blockIdx.x;
-  const int ncta = a.gx;
+  const int ncta = xtg_split(a).gx;
   if (col >= a.NG || a.partial == nullptr) return;           // block-uniform
   const int tx = threadIdx.x & 127, sl = threadIdx.x >> 7;
   const int per = (ncta + XRED_SLICES - 1) / XRED_SLICES;
@@ -517,6 +536,7 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
     if (per < 4) per = 4;                                  // keep the flush amortised
     a.pairs_per_cta = per * XKP;
     a.gx = (int)((a.P + a.pairs_per_cta - 1) / a.pairs_per_cta);
+    if (a.Pdev != nullptr) a.gx = sms;                     // ragged: the kernel splits the real extent over `gx` CTAs
     const size_t need = (size_t)a.gx * a.MXpad * a.NG;
     if (partial != nullptr && (poff + need) * sizeof(float) <= tc_xtg_partial_bytes()) {
       a.partial = partial + poff;

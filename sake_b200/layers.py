@@ -7,29 +7,8 @@ import math
 import torch
 
 from . import ops
-from .utils import exp_normal_smearing_init
-
-
-def _generator(key):
-    if isinstance(key, torch.Generator):
-        return key
-    g = torch.Generator()
-    g.manual_seed(int(key))
-    return g
-
-
-def lecun_normal(gen, shape):
-    """flax default kernel init: truncated normal (+-2 sigma), std = sqrt(1/fan_in)/0.8796."""
-    w = torch.empty(tuple(shape), dtype=torch.float64)
-    torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
-    return (w * (math.sqrt(1.0 / shape[0]) / 0.87962566103423978)).float()
-
-
-def dense_init(gen, fan_in, fan_out, use_bias=True):
-    p = {"kernel": lecun_normal(gen, (fan_in, fan_out))}
-    if use_bias:
-        p["bias"] = torch.zeros(fan_out)
-    return p
+from .init_params import (_generator, dense_init, init_layer_params, lecun_normal,  # noqa: F401
+                          init_model_params)
 
 
 def flatten_tree(t, prefix=""):
@@ -55,34 +34,6 @@ def unflatten_tree(flat):
 
 def tree_to(t, device):
     return {k: (tree_to(v, device) if isinstance(v, dict) else v.to(device)) for k, v in t.items()}
-
-
-def init_layer_params(gen, in_features, hidden_features, out_features, n_heads, update, has_v,
-                      log_gamma=True, kernel_features=50):
-    """Parameter tree of one layer, in flax creation semantics (velocity_mlp only when it is
-    actually called at init: layers.py:226-229)."""
-    F, H, A, K = in_features, hidden_features, n_heads, kernel_features
-    C = A * H
-    means, betas = exp_normal_smearing_init(K)
-    p = {
-        "edge_model": {
-            "kernel": {"means": means, "betas": betas},
-            "mlp_in": dense_init(gen, 2 * F, K),
-            "mlp_out": {"layers_0": dense_init(gen, 2 * F + K + 1, H), "layers_2": dense_init(gen, H, H)},
-        },
-    }
-    if log_gamma:
-        p["log_gamma"] = -torch.log(torch.linspace(1.0, 5.0, A))
-    p["semantic_attention_mlp"] = {"layers_0": dense_init(gen, H, A)}
-    p["x_mixing"] = {"layers_0": dense_init(gen, C, C, use_bias=False)}
-    p["post_norm_mlp"] = {"layers_0": dense_init(gen, C, H), "layers_2": dense_init(gen, H, H)}
-    p["node_mlp"] = {"layers_0": dense_init(gen, F + C + H, H), "layers_2": dense_init(gen, H, out_features)}
-    if update:
-        p["v_mixing"] = dense_init(gen, C, 1, use_bias=False)
-        if has_v:
-            p["velocity_mlp"] = {"layers_0": dense_init(gen, out_features, H),
-                                 "layers_2": dense_init(gen, H, 1, use_bias=False)}
-    return p
 
 
 def _pad3(t):

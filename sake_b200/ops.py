@@ -38,6 +38,14 @@ FIELD_OF = dict(LAYER_LEAVES)
 PATH_OF = {f: p for p, f in LAYER_LEAVES}
 
 
+def required_leaves(update, has_v, spatial=True):
+    """Leaves DenseSAKELayer.__call__ reads for this configuration (mirrors check_leaves in csrc/api.cu)."""
+    opt = {"v_mixing/kernel": update and spatial}
+    for q in ("velocity_mlp/layers_0/kernel", "velocity_mlp/layers_0/bias", "velocity_mlp/layers_2/kernel"):
+        opt[q] = update and has_v
+    return [p for p, _ in LAYER_LEAVES if opt.get(p, True)]
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -94,15 +102,16 @@ def _buf(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def layer_fwd_raw(dims, pstruct, h, x, v, mask, h_out, x_out, v_out, saved, scratch):
-    rc = lib.sake_layer_fwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask),
+def layer_fwd_raw(dims, pstruct, h, x, v, mask, h_out, x_out, v_out, saved, scratch, ragged=None):
+    rc = lib.sake_layer_fwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask), _ptr(ragged),
                             _ptr(h_out), _ptr(x_out), _ptr(v_out), _ptr(saved), saved.numel(),
                             _ptr(scratch), 0 if scratch is None else scratch.numel(), _stream())
     check(rc, "sake_layer_fwd")
 
 
-def layer_bwd_raw(dims, pstruct, h, x, v, mask, saved, dh_out, dx_out, dv_out, dh, dx, dv, gstruct, scratch):
-    rc = lib.sake_layer_bwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask),
+def layer_bwd_raw(dims, pstruct, h, x, v, mask, saved, dh_out, dx_out, dv_out, dh, dx, dv, gstruct, scratch,
+                  ragged=None):
+    rc = lib.sake_layer_bwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask), _ptr(ragged),
                             _ptr(saved), saved.numel(), _ptr(dh_out), _ptr(dx_out), _ptr(dv_out),
                             _ptr(dh), _ptr(dx), _ptr(dv),
                             None if gstruct is None else C.byref(gstruct),
@@ -110,17 +119,38 @@ def layer_bwd_raw(dims, pstruct, h, x, v, mask, saved, dh_out, dx_out, dv_out, d
     check(rc, "sake_layer_bwd")
 
 
-def dense_fwd_raw(x, kernel, bias, y, act):
+def dense_fwd_raw(x, kernel, bias, y, act, ragged=None):
     rows = x.numel() // kernel.shape[0]
     check(lib.sake_dense_fwd(rows, kernel.shape[0], kernel.shape[1], int(act), _ptr(x), _ptr(kernel),
-                             _ptr(bias), _ptr(y), _stream()), "sake_dense_fwd")
+                             _ptr(bias), _ptr(y), _ptr(ragged), _stream()), "sake_dense_fwd")
 
 
-def dense_bwd_raw(x, kernel, bias, dy, dx, dkernel, dbias, act):
+def dense_bwd_raw(x, kernel, bias, dy, dx, dkernel, dbias, act, ragged=None):
     rows = x.numel() // kernel.shape[0]
     check(lib.sake_dense_bwd(rows, kernel.shape[0], kernel.shape[1], int(act), _ptr(x), _ptr(kernel),
-                             _ptr(bias), _ptr(dy), _ptr(dx), _ptr(dkernel), _ptr(dbias), _stream()),
+                             _ptr(bias), _ptr(dy), _ptr(dx), _ptr(dkernel), _ptr(dbias), _ptr(ragged), _stream()),
           "sake_dense_bwd")
+
+
+# ---- ragged batches (include/sake_b200.h: sake_ragged_*) ----------------------------------------------------
+def ragged_bytes(B, N):
+    return int(lib.sake_ragged_bytes(int(B), int(N)))
+
+
+def ragged_prepare(B, N, n_real, blob):
+    """n_real: int32 CUDA tensor [B]; blob: uint8 CUDA tensor of ragged_bytes(B, N)."""
+    check(lib.sake_ragged_prepare(int(B), int(N), _ptr(n_real), _ptr(blob), blob.numel(), _stream()),
+          "sake_ragged_prepare")
+
+
+def ragged_gather(blob, B, N, width, padded, compact):
+    check(lib.sake_ragged_gather(_ptr(blob), int(B), int(N), int(width), _ptr(padded), _ptr(compact), _stream()),
+          "sake_ragged_gather")
+
+
+def ragged_scatter(blob, B, N, width, compact, padded, alpha=1.0):
+    check(lib.sake_ragged_scatter(_ptr(blob), int(B), int(N), int(width), float(alpha), _ptr(compact), _ptr(padded),
+                                  _stream()), "sake_ragged_scatter")
 
 
 class _DenseFn(torch.autograd.Function):
@@ -177,9 +207,10 @@ class _LayerFn(torch.autograd.Function):
         x_out = torch.empty_like(x)
         v_out = torch.empty_like(x) if (cfg["update"] or v is not None) else None
         layer_fwd_raw(dims, ps, h, x, v, mask, h_out, x_out, v_out, saved, scratch)
-        ctx.cfg, ctx.dims, ctx.flat = cfg, dims, flat
-        ctx.saved_buf = saved
-        ctx.save_for_backward(h, x, v, mask)
+        # leaves and the fwd->bwd buffer go through save_for_backward: autograd's version counters then catch an
+        # in-place parameter update between forward and backward, and the buffer is freed with the graph
+        ctx.cfg, ctx.dims = cfg, dims
+        ctx.save_for_backward(h, x, v, mask, saved, *[flat[p] for p in paths])
         ctx.n_leaves = len(leaves)
         if v_out is None:
             v_out = x.new_zeros(())      # placeholder (reference returns None)
@@ -188,8 +219,9 @@ class _LayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dh_out, dx_out, dv_out):
-        h, x, v, mask = ctx.saved_tensors
-        cfg, dims, flat = ctx.cfg, ctx.dims, ctx.flat
+        h, x, v, mask, saved_buf, *leaves = ctx.saved_tensors
+        cfg, dims = ctx.cfg, ctx.dims
+        flat = dict(zip(cfg["paths"], leaves))
         want_grads = any(ctx.needs_input_grad[5:])
         dev = h.device
         dh_out = _f32c(dh_out, "dh_out") if dh_out is not None else torch.zeros_like(h)
@@ -205,7 +237,7 @@ class _LayerFn(torch.autograd.Function):
             gs, _ = params_struct(gflat, _lib.SakeLayerGrads)
         ps, keep = params_struct(flat)
         scratch = _buf(scratch_bytes(dims, 1, want_grads), dev)
-        layer_bwd_raw(dims, ps, h, x, v, mask, ctx.saved_buf, dh_out, dx_out, dv_out, dh, dx, dv, gs, scratch)
+        layer_bwd_raw(dims, ps, h, x, v, mask, saved_buf, dh_out, dx_out, dv_out, dh, dx, dv, gs, scratch)
         grads = [gflat.get(p) if want_grads else None for p in cfg["paths"]]
         return (None, dh, dx, dv, None, *grads)
 
@@ -215,6 +247,11 @@ def sake_layer(flat_params, h, x, v=None, mask=None, *, n_heads=4, update=True, 
     """flat_params: {flax path -> tensor} of one DenseSAKELayer.  Returns (h, x, v) like
     sake/layers.py:188-235 (v is None when the reference would return None)."""
     paths = tuple(p for p, _ in LAYER_LEAVES if p in flat_params)
+    missing = [p for p in required_leaves(update, v is not None, use_spatial_attention) if p not in flat_params]
+    if missing:
+        # flax raises a missing-parameter error here (e.g. a tree initialised with v=None has no velocity_mlp,
+        # sake/layers.py:226-229); the C ABI returns SAKE_EINVAL for the same condition
+        raise _lib.SakeError("parameter tree lacks leaves this call needs: " + ", ".join(missing))
     K = flat_params["edge_model/kernel/means"].shape[0]
     cfg = {"paths": paths, "A": int(n_heads), "K": int(K), "update": bool(update),
            "spatial": bool(use_spatial_attention), "engine": engine}

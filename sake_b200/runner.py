@@ -13,8 +13,15 @@ from .layers import flatten_tree
 
 
 class ModelRunner:
-    def __init__(self, model, params, B, N, in_features, *, masked=False, train=False, device="cuda",
+    def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
                  lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0):
+        """masked: QM9-style padded batch with the reference's float mask = outer(m, m) (every kernel computes
+        all N^2 pairs of the padded width and multiplies by the mask, like the reference).
+        ragged: the same padded batch, but only the n_real[b] real atoms of every molecule are stored and
+        computed (compact layout, include/sake_b200.h `sake_ragged_*`); inputs / forces stay padded at the API."""
+        if ragged and masked:
+            raise _lib.SakeError("ragged batches carry no float mask: pass masked=False")
+        self.ragged = bool(ragged)
         self.model, self.B, self.N, self.F = model, int(B), int(N), int(in_features)
         self.H, self.L, self.A = model.hidden_features, model.depth, model.n_heads
         self.out = model.out_features
@@ -73,6 +80,14 @@ class ModelRunner:
         R = B * N
         self.h_in = torch.zeros(B, N, self.F, device=dev, dtype=f32)
         self.x_in = torch.zeros(B, N, 3, device=dev, dtype=f32)
+        self.rg = None
+        if self.ragged:
+            # padded copies of the inputs as the caller hands them over; h_in / x_in above hold the compact rows
+            self.h_pad = torch.zeros(B, N, self.F, device=dev, dtype=f32)
+            self.x_pad = torch.zeros(B, N, 3, device=dev, dtype=f32)
+            self.n_real = torch.full((B,), N, device=dev, dtype=torch.int32)
+            self.rg = ops._buf(ops.ragged_bytes(B, N), dev)
+            self.dx_pad = torch.zeros(B, N, 3, device=dev, dtype=f32)
         self.mask = torch.ones(B, N, N, device=dev, dtype=f32) if masked else None
         self.atom_mask = torch.ones(B, N, device=dev, dtype=f32) if masked else None
         self.target = torch.zeros(B, device=dev, dtype=f32)
@@ -96,10 +111,18 @@ class ModelRunner:
                              [self.flat_params, self.scratch, *self.saved, *self.hs, *self.xs[1:], *self.vs[1:]])
 
     # -- inputs ------------------------------------------------------------------------------------
-    def load_inputs(self, h, x, mask=None, atom_mask=None, target=None):
-        """Copy one batch into the resident input buffers (host pinned or device tensors)."""
-        self.h_in.copy_(h, non_blocking=True)
-        self.x_in.copy_(x, non_blocking=True)
+    def load_inputs(self, h, x, mask=None, atom_mask=None, target=None, n_real=None):
+        """Copy one batch into the resident input buffers (host pinned or device tensors).
+        ragged runners take the padded h [B,N,F], x [B,N,3] and n_real [B] (int32) instead of the masks."""
+        if self.ragged:
+            if n_real is None:
+                raise _lib.SakeError("a ragged runner needs n_real")
+            self.h_pad.copy_(h, non_blocking=True)
+            self.x_pad.copy_(x, non_blocking=True)
+            self.n_real.copy_(n_real, non_blocking=True)
+        else:
+            self.h_in.copy_(h, non_blocking=True)
+            self.x_in.copy_(x, non_blocking=True)
         if self.masked:
             self.mask.copy_(mask, non_blocking=True)
             self.atom_mask.copy_(atom_mask, non_blocking=True)
@@ -110,28 +133,40 @@ class ModelRunner:
         n = self.h_in.numel() + self.x_in.numel() + (self.target.numel() if self.train else 0)
         if self.masked:
             n += self.mask.numel() + self.atom_mask.numel()
+        if self.ragged:
+            n += self.n_real.numel()
         return 4 * n
+
+    def _ragged_inputs(self):
+        """Tables from n_real (device side) and the compact copies of the padded inputs: first launches of a step,
+        so a CUDA-graph replay picks up whatever batch load_inputs put into the resident buffers."""
+        ops.ragged_prepare(self.B, self.N, self.n_real, self.rg)
+        ops.ragged_gather(self.rg, self.B, self.N, self.F, self.h_pad, self.h_in)
+        ops.ragged_gather(self.rg, self.B, self.N, 3, self.x_pad, self.x_in)
 
     # -- forward (sake/models.py:56-61) -------------------------------------------------------------
     def forward(self):
         p = self.p
-        ops.dense_fwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.hs[0], 0)
+        rg = self.rg
+        if self.ragged:
+            self._ragged_inputs()
+        ops.dense_fwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.hs[0], 0, rg)
         for l in range(self.L):
             v_in = self.vs[l] if self.has_v[l] else None
             upd = self.model.update_list[l]
             v_out = self.vs[l + 1] if (upd or v_in is not None) else None
             ops.layer_fwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
-                              self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch)
+                              self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch, rg)
         ops.dense_fwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
-                          p.get("embedding_out/layers_0/bias"), self.y0, 1)
+                          p.get("embedding_out/layers_0/bias"), self.y0, 1, rg)
         ops.dense_fwd_raw(self.y0, p["embedding_out/layers_2/kernel"], p.get("embedding_out/layers_2/bias"),
-                          self.y, 0)
+                          self.y, 0, rg)
 
     def _head(self, mode):
         check(lib.sake_energy_head(self.B, self.N, self.out, mode, ops._ptr(self.y), ops._ptr(self.atom_mask),
                                    ops._ptr(self.target) if mode == 1 else None, self.mean, self.std,
                                    ops._ptr(self.energy), ops._ptr(self.loss) if mode == 1 else None,
-                                   ops._ptr(self.dy), ops._stream()), "sake_energy_head")
+                                   ops._ptr(self.dy), ops._ptr(self.rg), ops._stream()), "sake_energy_head")
 
     # -- backward ------------------------------------------------------------------------------------
     def backward(self, with_grads):
@@ -139,11 +174,11 @@ class ModelRunner:
         gk = (lambda k: g[k]) if with_grads else (lambda k: None)
         ops.dense_bwd_raw(self.y0, p["embedding_out/layers_2/kernel"], p.get("embedding_out/layers_2/bias"),
                           self.dy, self.dy0, gk("embedding_out/layers_2/kernel"),
-                          gk("embedding_out/layers_2/bias") if "embedding_out/layers_2/bias" in p else None, 0)
+                          gk("embedding_out/layers_2/bias") if "embedding_out/layers_2/bias" in p else None, 0, self.rg)
         cur = 0
         ops.dense_bwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
                           p.get("embedding_out/layers_0/bias"), self.dy0, self.dh[cur],
-                          gk("embedding_out/layers_0/kernel"), gk("embedding_out/layers_0/bias"), 1)
+                          gk("embedding_out/layers_0/kernel"), gk("embedding_out/layers_0/bias"), 1, self.rg)
         dx_out = dv_out = None
         for l in reversed(range(self.L)):
             nxt = 1 - cur
@@ -151,13 +186,13 @@ class ModelRunner:
             ops.layer_bwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask, self.saved[l],
                               self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
                               self.dv[nxt] if v_in is not None else None,
-                              self.gs[l] if with_grads else None, self.scratch)
+                              self.gs[l] if with_grads else None, self.scratch, self.rg)
             dx_out = self.dx[nxt]
             dv_out = self.dv[nxt] if v_in is not None else None
             cur = nxt
         if with_grads:
             ops.dense_bwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.dh[cur], None,
-                              g["embedding_in/kernel"], g.get("embedding_in/bias"), 0)
+                              g["embedding_in/kernel"], g.get("embedding_in/bias"), 0, self.rg)
         self._dx_final = dx_out
 
     # -- the two driver closures ---------------------------------------------------------------------
@@ -165,7 +200,11 @@ class ModelRunner:
         self.forward()
         self._head(0)
         self.backward(False)
-        torch.neg(self._dx_final, out=self.forces)
+        if self.ragged:                      # compact -dE/dx -> padded forces (padding atoms: exactly 0)
+            self.forces.zero_()
+            ops.ragged_scatter(self.rg, self.B, self.N, 3, self._dx_final, self.forces, alpha=-1.0)
+        else:
+            torch.neg(self._dx_final, out=self.forces)
 
     def _train_body(self):
         self.flat_grads.zero_()
