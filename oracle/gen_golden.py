@@ -168,7 +168,7 @@ def case_model(name, H, F_in, depth, N, batch, with_v, seed, out_features=1, upd
           "update": np.asarray(update, dtype=np.int64)})
 
 
-def case_flow(name, H, depth, mp_depth, N, D, B, seed):
+def case_flow(name, H, depth, mp_depth, N, D, B, seed, grad_keys=()):
     rng = np.random.default_rng(seed)
     jax.set_dtype(torch.float64)
     model = sake.flows.AugmentedFlowModel(depth=depth, mp_depth=mp_depth, hidden_features=H)
@@ -183,11 +183,36 @@ def case_flow(name, H, depth, mp_depth, N, D, B, seed):
     def fn(dt):
         p = as_params(flat, dt)
         xf, vf, ldf = model.apply(p, T(h, dt), T(x, dt), T(v, dt))
+        leaves = flatten(p["params"])
+        for k in grad_keys:
+            leaves[k].requires_grad_(True)
         xb, vb, ldb = model.apply(p, T(h, dt), T(x, dt), T(v, dt), method=model.f_backward)
-        return {"fwd_x": xf, "fwd_v": vf, "fwd_logdet": ldf, "bwd_x": xb, "bwd_v": vb, "bwd_logdet": ldb}
+        out = {"fwd_x": xf, "fwd_v": vf, "fwd_logdet": ldf, "bwd_x": xb, "bwd_v": vb, "bwd_logdet": ldb}
+        if grad_keys:
+            # the likelihood loss of scripts/lj13_aug/run.py:39-43 and its parameter gradient
+            prior = sake.flows.CenteredGaussian
+            loss = (-prior.log_prob(xb) - prior.log_prob(vb) + ldb).mean()
+            grads = torch.autograd.grad(loss, [leaves[k] for k in grad_keys])
+            out["loss"] = loss
+            for k, g in zip(grad_keys, grads):
+                out["grad:" + k] = g
+        return out
 
     save(name, flat, {"h": h, "x": x, "v": v}, run_both(fn),
          {"H": H, "N": N, "D": D, "depth": depth, "mp_depth": mp_depth, "kind": "flow"})
+
+
+def main_round2():
+    """Fixtures added in round 2 (the round-1 files are left byte-identical): hidden_features = 64 flows, i.e. the
+    shape the tcgen05 engine serves, LJ13-like (13 atoms, D = 3) and DW4-like (4 atoms, D = 2), with the
+    likelihood loss and its gradient for one leaf of every kind of sub-module."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    gk = ("xv_0/sake_model/d0/x_mixing/layers_0/kernel", "vx_0/sake_model/d1/edge_model/mlp_out/layers_2/kernel",
+          "xv_0/scale_mlp/layers_0/kernel", "vx_0/sake_model/d1/v_mixing/kernel",
+          "xv_0/sake_model/d1/node_mlp/layers_2/bias", "vx_0/sake_model/embedding_in/kernel")
+    case_flow("flow_h64_n13_d3", 64, 1, 2, 13, 3, 4, 13, grad_keys=gk)
+    case_flow("flow_h64_n4_d2", 64, 1, 2, 4, 2, 5, 14, grad_keys=gk)
 
 
 def main():
@@ -215,4 +240,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2()
+    else:
+        main()
+        main_round2()

@@ -94,12 +94,32 @@ def test_model_golden(name, engine):
 
 @pytest.mark.parametrize("name", G.names("flow"))
 def test_flow_golden(name):
+    """H = 16 fixtures run on the generic fp32 engine, the H = 64 ones (round 2: LJ13-like 13 atoms / D = 3 and
+    DW4-like 4 atoms / D = 2) on the tcgen05 engine (`auto`), including the likelihood loss of
+    scripts/lj13_aug/run.py:39-43 and its parameter gradient."""
     import sake_b200
+    import sake_b200.layers as L
     g = G.load(name)
     m = g["meta"]
     flow = sake_b200.flows.AugmentedFlowModel(depth=int(m["depth"]), mp_depth=int(m["mp_depth"]),
                                               hidden_features=int(m["H"]))
     p = _params(g)
+    gkeys = [k[len("f64/grad:"):] for k in g["out"] if k.startswith("f64/grad:")]
+    if gkeys:
+        flat = L.flatten_tree(p)
+        for k in gkeys:
+            flat[k].requires_grad_(True)
+        hh, xx, vv = (_dev(g["in"][k]) for k in ("h", "x", "v"))
+        xb, vb, ldb = flow.apply({"params": p}, hh, xx, vv, method="f_backward")
+        CG = sake_b200.flows.CenteredGaussian
+        loss = (-CG.log_prob(xb) - CG.log_prob(vb) + ldb).mean()
+        ref_loss = float(g["out"]["f64/loss"])
+        assert abs(loss.item() - ref_loss) < 1e-5 * max(1.0, abs(ref_loss)), (loss.item(), ref_loss)
+        grads = torch.autograd.grad(loss, [flat[k] for k in gkeys])
+        for k, gr in zip(gkeys, grads):
+            ref = g["out"]["f64/grad:" + k]
+            _close(gr, ref, 1e-3, 2e-3 * float(np.abs(ref).max()) + 1e-7, "grad " + k)
+        p = _params(g)
     h, x, v = (_dev(g["in"][k]) for k in ("h", "x", "v"))
     xf, vf, ld = flow.apply({"params": p}, h, x, v)
     _close(xf, g["out"]["f64/fwd_x"], 1e-4, 5e-5, "fwd_x")

@@ -301,7 +301,7 @@ def test_cuda_graph_replay_matches_eager(train):
     (the library is enqueue-only on the caller's stream, SURVEY 8b 'CUDA-graph capturable')."""
     import sake_b200
     from sake_b200 import runner as R
-    import bench
+    from sake_b200.init_params import _generator, init_model_params
     B, N, S = 16, 21, 6
     h, x, mask, am = synth.molecules(11, B, N, S, True, 5)
     model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=2, engine="auto")
@@ -309,7 +309,7 @@ def test_cuda_graph_replay_matches_eager(train):
     y = torch.randn(B, device="cuda")
     outs = []
     for use_graph in (False, True):
-        run = R.ModelRunner(model, bench.init_params_cpu(2, S, 0), B, N, S, masked=True, train=train)
+        run = R.ModelRunner(model, init_model_params(_generator(0), S, 64, 1, 2), B, N, S, masked=True, train=train)
         run.load_inputs(T(h), T(x), T(mask), T(am), y)
         if use_graph:
             assert run.capture() > 10

@@ -1,0 +1,331 @@
+"""GPU parity, round 2: ragged (n_real-packed) batches against the masked path and the oracle, the H = 64
+flows on the tcgen05 engine, parameter gradients against the fp64 oracle at a multi-tile size (parity and bf16
+engines, measured errors printed), the exact cfg1 shape, and the error paths the advisor asked for."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sake_oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _T(a, dtype=torch.float32):
+    return None if a is None else torch.tensor(a, device="cuda", dtype=dtype)
+
+
+def _oracle_params(p, dt=torch.float64):
+    return O.tree_map(lambda t: t.detach().cpu().to(dt), p)
+
+
+def _model_params(depth, S, seed, biases=True):
+    """Seeded flax-default init with non-zero biases (every bias path exercised)."""
+    import sake_b200.layers as L
+    from sake_b200.init_params import _generator, init_model_params
+    p = init_model_params(_generator(seed), S, 64, 1, depth)
+    flat = L.flatten_tree(p)
+    g = torch.Generator().manual_seed(seed + 1)
+    if biases:
+        for k, t in flat.items():
+            if k.endswith("bias"):
+                t.add_(0.1 * torch.randn(t.shape, generator=g))
+    return p
+
+
+def _n_real(am):
+    return am.sum(1).astype(np.int32)
+
+
+def _run_pair(B, N, S, depth, n_real, seed, engine="auto", train=True):
+    """Same padded batch through the masked runner (the reference's formulation: all N^2 pairs, float mask)
+    and the ragged runner (real atoms only)."""
+    import sake_b200
+    from sake_b200.runner import ModelRunner
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((B, N, 3)) * 0.62 * N ** (1.0 / 3.0)).astype(np.float32)
+    h = np.eye(S, dtype=np.float32)[rng.integers(0, S, (B, N))]
+    am = (np.arange(N)[None, :] < np.asarray(n_real)[:, None]).astype(np.float32)
+    h, x = h * am[..., None], x * am[..., None]
+    mask = am[:, :, None] * am[:, None, :]
+    y = rng.standard_normal(B).astype(np.float32)
+    params = _model_params(depth, S, seed)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=depth, engine=engine)
+    out = {}
+    for kind in ("masked", "ragged"):
+        run = ModelRunner(model, params, B, N, S, masked=(kind == "masked"), ragged=(kind == "ragged"), train=train)
+        if kind == "masked":
+            run.load_inputs(_T(h), _T(x), _T(mask), _T(am), _T(y))
+        else:
+            run.load_inputs(_T(h), _T(x), target=_T(y), n_real=_T(n_real, torch.int32))
+        e, f = run.energy_forces_step()
+        rec = {"e": e.clone(), "f": f.clone()}
+        if train:
+            rec["loss"] = run.train_step().clone()
+            rec["g"] = {k: v.clone() for k, v in run.g.items()}
+        torch.cuda.synchronize()
+        out[kind] = rec
+    return out, params, (h, x, am, y)
+
+
+@pytest.mark.parametrize("B,N,n_min,special", [(64, 29, 9, (1, 0, 29, 2)), (24, 63, 20, (63, 20)), (5, 128, 90, (128,))])
+def test_ragged_matches_masked_path(B, N, n_min, special):
+    """sum(n^2) real pairs instead of B*N^2: energies, forces, the L1 loss and every parameter gradient of the
+    ragged path equal the masked path's on the same padded batch (sake/tests/test_mask.py:202-240: padding does
+    not change real atoms).  n_real covers every tile shape: many rows per tile (n = 9: 14 rows, T rows read
+    from global), few (n >= 22: TMA-staged), n = 1 (a lone atom), n = 0 (an empty slot), n = N."""
+    rng = np.random.default_rng(B + N)
+    n_real = rng.integers(n_min, N + 1, B).astype(np.int32)
+    n_real[:len(special)] = special
+    out, _, _ = _run_pair(B, N, 6, 2, n_real, 11 + N)
+    m, r = out["masked"], out["ragged"]
+    assert torch.isfinite(r["e"]).all() and torch.isfinite(r["f"]).all()
+    escale = max(1.0, m["e"].abs().max().item())
+    assert (m["e"] - r["e"]).abs().max().item() < 2e-6 * escale
+    assert (m["f"] - r["f"]).abs().max().item() < 2e-6 * max(1.0, m["f"].abs().max().item())
+    am = (np.arange(N)[None, :] < n_real[:, None])
+    assert float(r["f"][_T(~am, torch.bool)].abs().max()) == 0.0 if (~am).any() else True
+    assert abs(m["loss"].item() - r["loss"].item()) < 2e-6 * max(1.0, abs(m["loss"].item()))
+    worst = 0.0
+    for k in m["g"]:
+        scale = max(float(m["g"][k].abs().max()), 1e-6)
+        err = float((m["g"][k] - r["g"][k]).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < 2e-4, (k, err)
+    print(f"ragged vs masked: worst parameter-gradient deviation {worst:.2e} of max|g|")
+
+
+def test_ragged_vs_oracle_unpadded():
+    """The ragged path against the fp64 oracle run on each molecule alone, unpadded and unmasked."""
+    B, N, S, depth = 12, 29, 6, 3
+    n_real = np.array([29, 9, 17, 1, 22, 29, 13, 10, 25, 5, 2, 19], dtype=np.int32)
+    out, params, (h, x, am, y) = _run_pair(B, N, S, depth, n_real, 5, train=False)
+    po = _oracle_params(params)
+    e, f = out["ragged"]["e"].cpu().double(), out["ragged"]["f"].cpu().double()
+    for b in range(B):
+        n = int(n_real[b])
+        e0, f0 = O.energy_and_forces(po, torch.tensor(h[b, :n]).double(), torch.tensor(x[b, :n]).double())
+        assert abs(e[b].item() - e0.item()) < 1e-5 * max(1.0, abs(e0.item())), (b, n, e[b].item(), e0.item())
+        assert (f[b, :n] - f0).abs().max().item() < 1e-4, (b, n)
+
+
+def test_ragged_graph_replay_with_new_batch():
+    """The tables are built on the device inside the step, so ONE captured graph serves batches with different
+    n_real (no host sync, CUDA-graph capturable)."""
+    import sake_b200
+    from sake_b200.runner import ModelRunner
+    B, N, S = 16, 21, 6
+    params = _model_params(2, S, 3)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=2)
+    rng = np.random.default_rng(0)
+
+    def batch(seed):
+        r = np.random.default_rng(seed)
+        n_real = r.integers(3, N + 1, B).astype(np.int32)
+        am = (np.arange(N)[None, :] < n_real[:, None]).astype(np.float32)
+        x = (r.standard_normal((B, N, 3)) * 1.7).astype(np.float32) * am[..., None]
+        h = np.eye(S, dtype=np.float32)[r.integers(0, S, (B, N))] * am[..., None]
+        return _T(h), _T(x), _T(n_real, torch.int32)
+
+    run_g = ModelRunner(model, params, B, N, S, ragged=True)
+    run_e = ModelRunner(model, params, B, N, S, ragged=True)
+    h, x, n = batch(1)
+    run_g.load_inputs(h, x, n_real=n)
+    assert run_g.capture() > 10
+    for seed in (2, 3):
+        h, x, n = batch(seed)
+        run_g.load_inputs(h, x, n_real=n)
+        run_e.load_inputs(h, x, n_real=n)
+        eg, fg = run_g.energy_forces_step()
+        ee, fe = run_e.energy_forces_step()
+        torch.cuda.synchronize()
+        assert run_g.graph_replays > 0
+        assert torch.equal(eg, ee) and torch.equal(fg, fe)
+
+
+@pytest.mark.parametrize("engine", ["auto", "bf16"])
+def test_param_grads_vs_oracle_multi_tile(engine):
+    """Every parameter gradient of an energy-L1 training step against the fp64 oracle at a multi-tile size
+    (QM9-shaped: N = 29, ragged, 32 molecules = ~100 pair tiles, depth 2), parity engine and bf16 engine;
+    the measured errors are printed (bf16: stated separately)."""
+    B, N, S, depth = 32, 29, 10, 2
+    rng = np.random.default_rng(77)
+    n_real = rng.integers(9, N + 1, B).astype(np.int32)
+    out, params, (h, x, am, y) = _run_pair(B, N, S, depth, n_real, 21, engine=engine)
+    r = out["ragged"]
+    po = _oracle_params(params)
+    fo = O.tree_flatten(po)
+    for t in fo.values():
+        t.requires_grad_(True)
+    es = []
+    for b in range(B):
+        n = int(n_real[b])
+        es.append(O.energy(po, torch.tensor(h[b, :n]).double(), torch.tensor(x[b, :n]).double()))
+    e0 = torch.stack(es)
+    loss0 = (e0 - torch.tensor(y).double()).abs().mean()
+    g0 = torch.autograd.grad(loss0, list(fo.values()), allow_unused=True)
+    erel = ((r["e"].cpu().double() - e0.detach()).abs() / e0.detach().abs().clamp_min(0.1)).max().item()
+    gtol, etol = (1e-3, 1e-5) if engine == "auto" else (1e-1, 2e-2)
+    worst, worst_k = 0.0, None
+    for (k, _), gb in zip(fo.items(), g0):
+        ga = r["g"][k].cpu().double()
+        if gb is None:
+            assert float(ga.abs().max()) == 0.0, k
+            continue
+        err = float((ga - gb).abs().max()) / max(float(gb.abs().max()), 1e-6)
+        if err > worst:
+            worst, worst_k = err, k
+    print(f"[{engine}] energy rel err {erel:.2e}; loss {r['loss'].item():.6f} vs {loss0.item():.6f}; "
+          f"worst parameter-gradient error {worst:.2e} of max|g| ({worst_k})")
+    assert erel < etol
+    assert abs(r["loss"].item() - loss0.item()) < etol * 10 * max(1.0, abs(loss0.item()))
+    assert worst < gtol, (worst, worst_k)
+
+
+@pytest.mark.parametrize("engine", ["auto", "bf16"])
+def test_cfg1_shape_vs_oracle(engine):
+    """BASELINE.json configs[0] exactly: MD17-aspirin-shaped, 21 atoms, batch 32, depth 4, energy + forces."""
+    import sake_b200
+    B, N, S = 32, 21, 8
+    h, x, _, _ = synth.molecules(2666, B, N, S)
+    params = _model_params(4, S, 0)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=4, engine=engine)
+    pc = O.tree_map(lambda t: t.cuda(), params)
+    e, f = model.energy_and_forces(pc, _T(h), _T(x))
+    e0, f0 = O.energy_and_forces(_oracle_params(params), torch.tensor(h).double(), torch.tensor(x).double())
+    erel = ((e.cpu().double() - e0).abs() / e0.abs().clamp_min(0.1)).max().item()
+    ferr = (f.cpu().double() - f0).abs().max().item()
+    print(f"[cfg1 {engine}] energy rel err {erel:.2e}, force abs err {ferr:.2e} (max |F| {f0.abs().max().item():.2e})")
+    if engine == "auto":
+        assert erel < 1e-5 and ferr < 1e-4
+    else:
+        assert erel < 2e-2 and ferr < 5e-2 * max(1.0, f0.abs().max().item())
+
+
+@pytest.mark.parametrize("N,D,B", [(13, 3, 64), (4, 2, 96)])
+def test_flow_h64_vs_oracle(N, D, B):
+    """AugmentedFlowModel(depth=2, mp_depth=2, hidden_features=64) on the tcgen05 engine (N+1 = 14 / 5 atoms:
+    9 / 25 receiver rows per tile): sampling, likelihood direction, invertibility and the gradient of the
+    likelihood loss (scripts/lj13_aug/run.py:39-43) against the fp64 oracle."""
+    import sake_b200
+    import sake_b200.layers as L
+    flow = sake_b200.flows.AugmentedFlowModel(depth=2, mp_depth=2, hidden_features=64)
+    assert flow.xv_layers[0].sake_model.engine == "auto"
+    g = torch.Generator().manual_seed(N)
+    h = torch.zeros(B, N, 2)
+    x = torch.randn(B, N, D, generator=g); x = x - x.mean(-2, keepdim=True)
+    v = torch.randn(B, N, D, generator=g); v = v - v.mean(-2, keepdim=True)
+    p = flow.init(7, h.cuda(), x.cuda(), v.cuda())["params"]
+    flat = L.flatten_tree(p)
+    for k, t in flat.items():
+        if k.endswith("bias"):
+            t.add_(0.1 * torch.randn(t.shape, generator=g).cuda())
+    po = _oracle_params(p)
+    hd, xd, vd = h.double(), x.double(), v.double()
+    xf, vf, ld = flow.apply({"params": p}, h.cuda(), x.cuda(), v.cuda())
+    xf0, vf0, ld0 = O.flow_forward(po, hd, xd, vd)
+    for a, b, w in ((xf, xf0, "fwd_x"), (vf, vf0, "fwd_v"), (ld, ld0, "fwd_logdet")):
+        err = (a.cpu().double() - b).abs().max().item()
+        assert err < 1e-4 * max(1.0, b.abs().max().item()), (w, err)
+    x2, v2, _ = flow.apply({"params": p}, h.cuda(), xf, vf, method="f_backward")
+    assert (x2.cpu() - x).abs().max().item() < 1e-4 and (v2.cpu() - v).abs().max().item() < 1e-4
+    for t in flat.values():
+        t.requires_grad_(True)
+    xb, vb, ldb = flow.apply({"params": p}, h.cuda(), x.cuda(), v.cuda(), method="f_backward")
+    CG = sake_b200.flows.CenteredGaussian
+    loss = (-CG.log_prob(xb) - CG.log_prob(vb) + ldb).mean()
+    grads = torch.autograd.grad(loss, list(flat.values()), allow_unused=True)
+    fo = O.tree_flatten(po)
+    for t in fo.values():
+        t.requires_grad_(True)
+    xb0, vb0, ldb0 = O.flow_backward(po, hd, xd, vd)
+    loss0 = (-O.centered_gaussian_log_prob(xb0) - O.centered_gaussian_log_prob(vb0) + ldb0).mean()
+    g0 = torch.autograd.grad(loss0, list(fo.values()), allow_unused=True)
+    assert abs(loss.item() - loss0.item()) < 1e-5 * max(1.0, abs(loss0.item()))
+    worst = 0.0
+    for (k, _), ga, gb in zip(flat.items(), grads, g0):
+        if gb is None:
+            assert ga is None or float(ga.abs().max()) == 0.0, k
+            continue
+        err = float((ga.cpu().double() - gb).abs().max()) / max(float(gb.abs().max()), 1e-6)
+        worst = max(worst, err)
+        assert err < 2e-3, (k, err)
+    print(f"flow N={N} D={D}: loss {loss.item():.6f}, worst parameter-gradient error {worst:.2e} of max|g|")
+
+
+def test_log_gamma_gradient_is_zero():
+    """log_gamma exists in the tree (checkpoint compatibility) but the dense layer never reads it
+    (sake/layers.py:97-105 vs :107-235): its gradient is exactly zero through both host paths."""
+    import sake_b200
+    import sake_b200.layers as L
+    from sake_b200.runner import ModelRunner
+    B, N, S = 4, 9, 5
+    h, x, _, _ = synth.molecules(3, B, N, S)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=2)
+    p = model.init(1, _T(h), _T(x))["params"]
+    assert "log_gamma" in p["d0"]
+    flat = L.flatten_tree(p)
+    for t in flat.values():
+        t.requires_grad_(True)
+    grads = torch.autograd.grad(model.energy(p, _T(h), _T(x)).sum(), list(flat.values()), allow_unused=True)
+    for k, g in zip(flat, grads):
+        if k.endswith("log_gamma"):
+            assert g is None or float(g.abs().max()) == 0.0
+    run = ModelRunner(model, O.tree_map(lambda t: t.detach(), p), B, N, S, train=True)
+    run.load_inputs(_T(h), _T(x), target=torch.zeros(B, device="cuda"))
+    run.train_step()
+    for k, g in run.g.items():
+        if k.endswith("log_gamma"):
+            assert float(g.abs().max()) == 0.0, k
+
+
+def test_missing_leaves_are_errors():
+    """A tree initialised with v=None has no velocity_mlp (flax creation semantics, sake/layers.py:226-229);
+    applying it with a velocity is a missing-parameter error — in Python before the launch and in the C ABI
+    (SAKE_EINVAL), never a NULL dereference or a silent zero weight."""
+    import ctypes as C
+    import sake_b200
+    from sake_b200 import _lib, ops
+    from sake_b200._lib import SakeError
+    B, N = 2, 7
+    g = torch.Generator(device="cuda").manual_seed(0)
+    h = torch.randn(B, N, 64, device="cuda", generator=g)
+    x = torch.randn(B, N, 3, device="cuda", generator=g)
+    v = torch.randn(B, N, 3, device="cuda", generator=g)
+    for engine in ("fp32", "auto"):
+        layer = sake_b200.DenseSAKELayer(64, 64, engine=engine)
+        p = layer.init(0, h, x)                          # v = None: no velocity_mlp
+        assert "velocity_mlp" not in p["params"]
+        with pytest.raises(SakeError, match="velocity_mlp"):
+            layer.apply(p, h, x, v)
+        # straight through the C ABI
+        import sake_b200.layers as L
+        flat = L.flatten_tree(p["params"])
+        ps, keep = ops.params_struct(flat)
+        dims = ops.make_dims(B, N, 64, 4, 50, True, True, False, True, engine)
+        saved = ops._buf(ops.saved_bytes(dims), h.device)
+        scratch = ops._buf(ops.scratch_bytes(dims, 0, 0), h.device)
+        ho, xo, vo = torch.empty_like(h), torch.empty_like(x), torch.empty_like(x)
+        rc = _lib.lib.sake_layer_fwd(C.byref(dims), C.byref(ps), ops._ptr(h), ops._ptr(x), ops._ptr(v), None, None,
+                                     ops._ptr(ho), ops._ptr(xo), ops._ptr(vo), ops._ptr(saved), saved.numel(),
+                                     ops._ptr(scratch), scratch.numel(), None)
+        assert rc == -1 and b"vel0_kernel" in _lib.lib.sake_last_error()
+    torch.cuda.synchronize()                             # the context is healthy: nothing was launched
+
+
+def test_dense_wide_features_backward():
+    """embedding_out backward with hidden_features = 128 (66 KB of staged weights: beyond the 48 KB default)."""
+    from sake_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(37, 128, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(128, 128, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    b = torch.randn(128, device="cuda", generator=g).requires_grad_(True)
+    y = ops.dense(x, w, b, act=1)
+    gy = torch.randn(37, 128, device="cuda", generator=g)
+    gx, gw, gb = torch.autograd.grad(y, [x, w, b], gy)
+    z = x.double() @ w.double() + b.double()
+    y0 = z * torch.sigmoid(z)
+    gx0, gw0, gb0 = torch.autograd.grad(y0, [x, w, b], gy.double())
+    assert (y.double() - y0).abs().max().item() < 1e-5
+    for a, c in ((gx, gx0), (gw, gw0), (gb, gb0)):
+        assert (a.double() - c.double()).abs().max().item() < 1e-4 * max(1.0, c.abs().max().item())

@@ -95,10 +95,23 @@ def test_flow(name):
     _close(xf, g["out"]["f64/fwd_x"], 1e-10, 1e-11, "fwd_x")
     _close(vf, g["out"]["f64/fwd_v"], 1e-10, 1e-11, "fwd_v")
     _close(ld, g["out"]["f64/fwd_logdet"], 1e-10, 1e-11, "fwd_logdet")
+    flat = O.tree_flatten(p)
+    gkeys = [k[len("f64/grad:"):] for k in g["out"] if k.startswith("f64/grad:")]
+    for k in gkeys:
+        flat[k].requires_grad_(True)
     xb, vb, ld = O.flow_backward(p, h, x, v)
-    _close(xb, g["out"]["f64/bwd_x"], 1e-10, 1e-11, "bwd_x")
-    _close(vb, g["out"]["f64/bwd_v"], 1e-10, 1e-11, "bwd_v")
-    _close(ld, g["out"]["f64/bwd_logdet"], 1e-10, 1e-11, "bwd_logdet")
+    _close(xb.detach(), g["out"]["f64/bwd_x"], 1e-10, 1e-11, "bwd_x")
+    _close(vb.detach(), g["out"]["f64/bwd_v"], 1e-10, 1e-11, "bwd_v")
+    _close(ld.detach(), g["out"]["f64/bwd_logdet"], 1e-10, 1e-11, "bwd_logdet")
+    if gkeys:
+        # likelihood loss of scripts/lj13_aug/run.py:39-43 and its parameter gradient (round-2 fixtures)
+        loss = (-O.centered_gaussian_log_prob(xb) - O.centered_gaussian_log_prob(vb) + ld).mean()
+        _close(loss.detach(), g["out"]["f64/loss"], 1e-10, 1e-11, "loss")
+        grads = torch.autograd.grad(loss, [flat[k] for k in gkeys])
+        for k, gr in zip(gkeys, grads):
+            ref = g["out"]["f64/grad:" + k]
+            _close(gr, ref, 1e-8, 1e-10 * max(1.0, float(abs(ref).max())), "grad " + k)
+        p = O.params_to(G.unflatten(g["params"]), dt)
     # invertibility, sake/tests/test_augmented_flow.py:47-63
     x2, v2, _ = O.flow_backward(p, h, xf, vf)
     _close(x2, x, 1e-9, 1e-9, "inv_x")
