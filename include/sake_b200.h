@@ -212,6 +212,25 @@ int sake_energy_head(int32_t B, int32_t N, int32_t out_features, int32_t mode, c
                      const float* atom_mask, const float* target, float mean, float std,
                      float* energy, float* loss, float* dy, const void* ragged, sake_stream_t stream);
 
+/* Coupling glue of the augmented flow (sake/flows.py:97-142; scripts/lj13_aug/run.py:32-43), one launch each:
+ *   sake_flow_pre      AugmentedFlowLayer.mp, flows.py:118-122: h_aug[B,N+1,F+1] = [h | sum pos^2] with a zero
+ *                      dummy atom appended, x_aug[B,N+1,3] = [pos ; 0]   (h may be NULL = zeros)
+ *   sake_flow_post     flows.py:123-142 after the DenseSAKEModel call: translation = (x_aug_out - pos0)[:N] minus
+ *                      its mean over atoms; scale = mean_i tanh(Dense(silu(Dense(y_i)))) with the scale_mlp leaves
+ *                      (y = the model's h output, out_features = 1; hidden width <= 64);
+ *                      direction +1 (f_forward):  other = exp(scale) * other + translation
+ *                      direction -1 (f_backward): other = exp(-scale) * (other - translation)
+ *                      logdet[b] += scale * N * D   (D = coordinate dimension of the system, 2 or 3)
+ *   sake_flow_logprob  out[b] = -log p(x) - log p(v) + logdet[b], p = CenteredGaussian (flows.py:13-21)
+ * All coordinate tensors are [B,N,3] (2-D systems carry z = 0). */
+int sake_flow_pre(int32_t B, int32_t N, int32_t h_features, const float* h, const float* pos, float* h_aug,
+                  float* x_aug, sake_stream_t stream);
+int sake_flow_post(int32_t B, int32_t N, int32_t D, int32_t scale_hidden, int32_t direction, const float* x_aug_out,
+                   const float* pos0, const float* y, const float* scale0_kernel, const float* scale0_bias,
+                   const float* scale2_kernel, float* other, float* logdet, sake_stream_t stream);
+int sake_flow_logprob(int32_t B, int32_t N, int32_t D, const float* x, const float* v, const float* logdet,
+                      float* out, sake_stream_t stream);
+
 /* One optimiser step over a flat fp32 parameter vector, the chain every training driver uses
  * (scripts/qm9/run.py:134-138): additive_weight_decay(wd) -> clip(max_delta, element-wise)
  * -> adam(lr, b1, b2, eps) with bias correction for `step` (1-based).  grad_scale multiplies the
@@ -222,8 +241,9 @@ int sake_adam_step(int64_t n, float* params, const float* grads, float* m, float
 
 /* Per-launch device timing of the dominant (x_mixing GEMM) kernels with CUDA events recorded on
  * the launch stream.  begin(capacity) arms it, collect() synchronises the recorded events and
- * returns how many records were written: ms[i] = duration, kind[i] = 1 mix-forward,
- * 2 mix-backward (dX), 3 mix-dW, pairs[i] = atom pairs processed by that launch. */
+ * returns how many records were written: ms[i] = duration, kind[i] = 1 mix-forward, 2 mix-backward (dX),
+ * 3 mix-dW, 4 edge-forward, 5 edge-backward, 6 node-tail forward, 7 node-tail backward, 8 small weight-gradient
+ * contractions; pairs[i] = atom pairs (kinds 6, 7: atoms) of the padded batch that launch covers. */
 int sake_profile_begin(int32_t capacity);
 int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capacity);
 

@@ -3,7 +3,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsake_b200.so")
+# SAKE_B200_LIB selects another build of the same library (e.g. the development build with the mbarrier
+# watchdog: make -C sake_b200/csrc WATCHDOG=1 -> libsake_b200_wd.so); the default is the product build.
+LIB_PATH = os.environ.get("SAKE_B200_LIB") or os.path.join(_HERE, "libsake_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -71,6 +73,12 @@ lib.sake_dense_bwd.argtypes = [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, 
 lib.sake_dense_bwd.restype = C.c_int
 lib.sake_energy_head.argtypes = [_i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]
 lib.sake_energy_head.restype = C.c_int
+lib.sake_flow_pre.argtypes = [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
+lib.sake_flow_pre.restype = C.c_int
+lib.sake_flow_post.argtypes = [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.sake_flow_post.restype = C.c_int
+lib.sake_flow_logprob.argtypes = [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
+lib.sake_flow_logprob.restype = C.c_int
 lib.sake_adam_step.argtypes = [_i64, _vp, _vp, _vp, _vp, _i32] + [C.c_float] * 7 + [_vp]
 lib.sake_adam_step.restype = C.c_int
 lib.sake_profile_begin.argtypes = [_i32]
@@ -87,7 +95,7 @@ lib.sake_launch_count.restype = C.c_ulonglong
 lib.sake_selftest_tcgen05.argtypes = [C.POINTER(C.c_float), _vp]
 lib.sake_selftest_tcgen05.restype = C.c_int
 
-EXPORTS = ("sake_ragged_bytes", "sake_ragged_prepare", "sake_ragged_gather", "sake_ragged_scatter", "sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
+EXPORTS = ("sake_flow_pre", "sake_flow_post", "sake_flow_logprob", "sake_ragged_bytes", "sake_ragged_prepare", "sake_ragged_gather", "sake_ragged_scatter", "sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
            "sake_layer_scratch_bytes", "sake_layer_fwd", "sake_layer_bwd", "sake_dense_fwd",
            "sake_dense_bwd", "sake_selftest_tcgen05", "sake_energy_head", "sake_adam_step",
            "sake_profile_begin", "sake_profile_collect", "sake_launch_count", "sake_selftest_xtg", "sake_debug_counters", "sake_debug_counters_bwd")

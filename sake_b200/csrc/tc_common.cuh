@@ -54,7 +54,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // ring protocol costs seconds of GPU time instead of the whole test timeout.  The product build has no
 // watchdog: the polling loops are exactly the two instructions below.
 #ifdef SAKE_MBAR_WATCHDOG
-__device__ __noinline__ void mbar_watchdog_fire(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_watchdog_fire(uint64_t* bar, uint32_t parity) {
   printf("sake mbarrier watchdog: block %d thread %d stuck on barrier smem+0x%x parity %u\n", (int)blockIdx.x,
          (int)threadIdx.x, smem_u32(bar), parity);
   __trap();

@@ -623,7 +623,10 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   const size_t smem = WA_BYTES + WB_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_edge<false>, smem, optin); if (rc) return rc; }
-  k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  {
+    ProfScope prof(4, d.P, st);
+    k_tc_edge<false><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -655,7 +658,10 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_edge<true>, smem, optin); if (rc) return rc; }
-  k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  {
+    ProfScope prof(5, d.P, st);
+    k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
+  }
   k_pair_reduce<<<d.R, 128, 0, st>>>(d, PB, sc.gproj, dx);
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());

@@ -778,7 +778,10 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   const size_t smem = 4 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_node_post_bwd, smem, optin); if (rc) return rc; }
-  k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  {
+    ProfScope prof(7, d.R, st);
+    k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  }
   if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 3 : 2);
   SAKE_CUDA_CHECK(cudaGetLastError());
@@ -803,7 +806,10 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   const size_t smem = 2 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_node_post, smem, optin); if (rc) return rc; }
-  k_tc_node_post<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  {
+    ProfScope prof(6, d.R, st);
+    k_tc_node_post<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+  }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

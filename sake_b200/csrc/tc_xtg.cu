@@ -565,8 +565,9 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
                               : xtg_launch<512, false, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
   if (rc) return rc;
   // the lean small kernel fits two CTAs per SM (96 registers, 256 TMEM columns, <= 82 KB): 4 builder warps per scheduler
-  return lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st)
-                            : xtg_launch<256, false, 1>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, 0, 0, st);
+  const int pk_small = prof_kind == 3 ? 8 : 0;   // profiler kind 8: the batched small contractions of a layer
+  return lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, pk_small, prof_pairs, st)
+                            : xtg_launch<256, false, 1>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, pk_small, prof_pairs, st);
 }
 
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {

@@ -12,6 +12,50 @@ from ._lib import lib, check
 from .layers import flatten_tree
 
 
+class ParamSet:
+    """The parameters of one DenseSAKEModel as ONE flat fp32 vector (+ gradient / Adam vectors when training: one
+    all-reduce bucket) with per-leaf views and the per-layer C structs (SakeLayerParams / SakeLayerGrads)."""
+
+    def __init__(self, model, params, device, train=False):
+        dev, f32 = torch.device(device), torch.float32
+        flat = flatten_tree(params)
+        self.paths = list(flat.keys())
+        sizes = [flat[k].numel() for k in self.paths]
+        # every tensor starts on a 16-byte boundary (vectorised / cp.async weight loads in the node kernels);
+        # the pad floats stay zero in the parameters, gradients and Adam moments
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4
+        self.n_params = off
+        self.n_params_real = sum(sizes)
+        self.flat_params = torch.zeros(self.n_params, device=dev, dtype=f32)
+        self.p = {}
+        for k, n, off in zip(self.paths, sizes, offs):
+            self.p[k] = self.flat_params[off:off + n].view(flat[k].shape)
+            self.p[k].copy_(flat[k])
+        self.g = {}
+        self.flat_grads = self.adam_m = self.adam_v = None
+        if train:
+            self.flat_grads = torch.zeros(self.n_params, device=dev, dtype=f32)
+            self.adam_m = torch.zeros_like(self.flat_grads)
+            self.adam_v = torch.zeros_like(self.flat_grads)
+            for k, n, off in zip(self.paths, sizes, offs):
+                self.g[k] = self.flat_grads[off:off + n].view(flat[k].shape)
+        self.K = flat["d0/edge_model/kernel/means"].shape[0]
+        self.ps, self.gs, self._keep = [], [], []
+        for l in range(model.depth):
+            sub = {k[len("d%d/" % l):]: t for k, t in self.p.items() if k.startswith("d%d/" % l)}
+            ps, keep = ops.params_struct(sub)
+            self.ps.append(ps)
+            self._keep.append(keep)
+            if train:
+                gsub = {k[len("d%d/" % l):]: t for k, t in self.g.items() if k.startswith("d%d/" % l)}
+                gs, keep = ops.params_struct(gsub, _lib.SakeLayerGrads)
+                self.gs.append(gs)
+                self._keep.append(keep)
+
+
 class ModelRunner:
     def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
                  lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0):
@@ -31,32 +75,14 @@ class ModelRunner:
         self.graphs, self.graph_replays, self.graph_launches = {}, 0, 0
         dev, f32 = self.dev, torch.float32
         # ---- one flat fp32 parameter vector (+ grads, Adam moments): one all-reduce bucket --------
-        flat = flatten_tree(params)
-        self.paths = list(flat.keys())
-        sizes = [flat[k].numel() for k in self.paths]
-        # every tensor starts on a 16-byte boundary (vectorised / cp.async weight loads in the node kernels);
-        # the pad floats stay zero in the parameters, gradients and Adam moments
-        offs, off = [], 0
-        for n in sizes:
-            offs.append(off)
-            off += (n + 3) // 4 * 4
-        self.n_params = off
-        self.n_params_real = sum(sizes)
-        self.flat_params = torch.zeros(self.n_params, device=dev, dtype=f32)
-        self.p = {}
-        for k, n, off in zip(self.paths, sizes, offs):
-            self.p[k] = self.flat_params[off:off + n].view(flat[k].shape)
-            self.p[k].copy_(flat[k])
-        self.g = {}
-        if train:
-            self.flat_grads = torch.zeros(self.n_params, device=dev, dtype=f32)
-            self.adam_m = torch.zeros_like(self.flat_grads)
-            self.adam_v = torch.zeros_like(self.flat_grads)
-            for k, n, off in zip(self.paths, sizes, offs):
-                self.g[k] = self.flat_grads[off:off + n].view(flat[k].shape)
-        # ---- per-layer dims / param structs ---------------------------------------------------
-        K = flat["d0/edge_model/kernel/means"].shape[0]
-        self.dims, self.ps, self.gs, self._keep = [], [], [], []
+        self.pset = ps_ = ParamSet(model, params, dev, train)
+        self.paths, self.n_params, self.n_params_real = ps_.paths, ps_.n_params, ps_.n_params_real
+        self.flat_params, self.p, self.g = ps_.flat_params, ps_.p, ps_.g
+        self.flat_grads, self.adam_m, self.adam_v = ps_.flat_grads, ps_.adam_m, ps_.adam_v
+        self.ps, self.gs = ps_.ps, ps_.gs
+        # ---- per-layer dims ---------------------------------------------------------------------
+        K = ps_.K
+        self.dims = []
         has_v = False
         self.has_v = []
         for l in range(self.L):
@@ -65,15 +91,6 @@ class ModelRunner:
                               model.engine)
             self.dims.append(d)
             self.has_v.append(has_v)
-            sub = {k[len("d%d/" % l):]: t for k, t in self.p.items() if k.startswith("d%d/" % l)}
-            ps, keep = ops.params_struct(sub)
-            self.ps.append(ps)
-            self._keep.append(keep)
-            if train:
-                gsub = {k[len("d%d/" % l):]: t for k, t in self.g.items() if k.startswith("d%d/" % l)}
-                gs, keep = ops.params_struct(gsub, _lib.SakeLayerGrads)
-                self.gs.append(gs)
-                self._keep.append(keep)
             has_v = has_v or upd
         self.engine = ops.resolve_engine(self.dims[0])
         # ---- activations -----------------------------------------------------------------------
@@ -145,8 +162,11 @@ class ModelRunner:
         ops.ragged_gather(self.rg, self.B, self.N, 3, self.x_pad, self.x_in)
 
     # -- forward (sake/models.py:56-61) -------------------------------------------------------------
-    def forward(self):
-        p = self.p
+    def forward(self, pset=None):
+        """pset: another ParamSet of the same architecture (the flow runs 2*depth models through one set of
+        activation buffers); default: the runner's own parameters."""
+        pset = self.pset if pset is None else pset
+        p = pset.p
         rg = self.rg
         if self.ragged:
             self._ragged_inputs()
@@ -155,7 +175,7 @@ class ModelRunner:
             v_in = self.vs[l] if self.has_v[l] else None
             upd = self.model.update_list[l]
             v_out = self.vs[l + 1] if (upd or v_in is not None) else None
-            ops.layer_fwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
+            ops.layer_fwd_raw(self.dims[l], pset.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
                               self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch, rg)
         ops.dense_fwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
                           p.get("embedding_out/layers_0/bias"), self.y0, 1, rg)

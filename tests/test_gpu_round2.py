@@ -253,6 +253,44 @@ def test_flow_h64_vs_oracle(N, D, B):
     print(f"flow N={N} D={D}: loss {loss.item():.6f}, worst parameter-gradient error {worst:.2e} of max|g|")
 
 
+@pytest.mark.parametrize("N,D", [(13, 3), (4, 2)])
+def test_flow_runner_matches_flow_module_and_oracle(N, D):
+    """FlowRunner (csrc/flow.cu glue kernels + ModelRunner.forward, optionally one CUDA graph per pass) against the
+    autograd-path module (sake_b200.flows) and the fp64 oracle: sampling, likelihood pass, per-molecule
+    -log p(x) - log p(v) + sum_log_det (scripts/lj13_aug/run.py:39-43)."""
+    import sake_b200
+    from sake_b200.flow_runner import FlowRunner
+    B = 48
+    g = torch.Generator().manual_seed(5 + N)
+    x = torch.randn(B, N, D, generator=g); x = x - x.mean(-2, keepdim=True)
+    v = torch.randn(B, N, D, generator=g); v = v - v.mean(-2, keepdim=True)
+    h = torch.zeros(B, N, 2)
+    flow = sake_b200.flows.AugmentedFlowModel(depth=2, mp_depth=2, hidden_features=64)
+    p = flow.init(3, h.cuda(), x.cuda(), v.cuda())["params"]
+    fr = FlowRunner(depth=2, mp_depth=2, B=B, N=N, D=D, params=p)
+    po = _oracle_params(p)
+    xb0, vb0, ld0 = O.flow_backward(po, h.double(), x.double(), v.double())
+    ll0 = -O.centered_gaussian_log_prob(xb0) - O.centered_gaussian_log_prob(vb0) + ld0
+    for use_graph in (False, True):
+        if use_graph:
+            assert fr.capture("loglik") > 20
+        fr.load_inputs(x.cuda(), v.cuda())
+        ll = fr.log_likelihood_step().clone()
+        xb, vb, ldb = flow.apply({"params": p}, h.cuda(), x.cuda(), v.cuda(), method="f_backward")
+        assert (fr.x[..., :D] - xb).abs().max().item() < 2e-5 and (fr.v[..., :D] - vb).abs().max().item() < 2e-5
+        assert (fr.logdet - ldb).abs().max().item() < 2e-5 * max(1.0, ldb.abs().max().item())
+        assert (ll.cpu().double() - ll0).abs().max().item() < 1e-4 * max(1.0, ll0.abs().max().item())
+    fr.graph = None
+    fr.load_inputs(x.cuda(), v.cuda())
+    fr.sample_step()
+    xf0, vf0, ldf0 = O.flow_forward(po, h.double(), x.double(), v.double())
+    assert (fr.x[..., :D].cpu().double() - xf0).abs().max().item() < 1e-4 * max(1.0, xf0.abs().max().item())
+    assert (fr.v[..., :D].cpu().double() - vf0).abs().max().item() < 1e-4 * max(1.0, vf0.abs().max().item())
+    assert (fr.logdet.cpu().double() - ldf0).abs().max().item() < 1e-4 * max(1.0, ldf0.abs().max().item())
+    if D == 2:
+        assert float(fr.x[..., 2].abs().max()) == 0.0 and float(fr.v[..., 2].abs().max()) == 0.0
+
+
 def test_log_gamma_gradient_is_zero():
     """log_gamma exists in the tree (checkpoint compatibility) but the dense layer never reads it
     (sake/layers.py:97-105 vs :107-235): its gradient is exactly zero through both host paths."""
