@@ -42,7 +42,13 @@ enum {
   SAKE_UPDATE = 1,       /* DenseSAKELayer.update (sake/layers.py:46,217)                      */
   SAKE_HAS_V = 2,        /* v argument is not None (sake/layers.py:226-229)                    */
   SAKE_HAS_MASK = 4,     /* mask argument is not None, float [B,N,N]                           */
-  SAKE_NO_SPATIAL = 8    /* use_spatial_attention=False (sake/layers.py:210-212)              */
+  SAKE_NO_SPATIAL = 8,   /* use_spatial_attention=False (sake/layers.py:210-212)              */
+  SAKE_DEFER_DW = 16     /* sake_layer_bwd only: enqueue the weight-gradient contractions (dW = X^T G over all
+                            pairs / atoms; nothing downstream of the layer reads them) on the library's side
+                            stream so that they overlap the next layer's backward.  SakeDims.reserved = scratch
+                            slot (0 or 1): the caller alternates two scratch buffers between consecutive layers,
+                            and a call first makes `stream` wait for the deferred work of the previous call that
+                            used the same slot.  Gradients are complete after sake_dw_sync(stream).           */
 };
 
 /* precision / engine (SakeDims.engine) */
@@ -186,6 +192,10 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params,
                    const float* dh_out, const float* dx_out, const float* dv_out,
                    float* dh, float* dx, float* dv, const SakeLayerGrads* grads,
                    void* scratch, size_t scratch_bytes, sake_stream_t stream);
+
+/* Joins the deferred weight-gradient work (SAKE_DEFER_DW) of this device into `stream`: everything enqueued after
+ * this call sees the complete parameter gradients, and the scratch / saved buffers may be reused.  Capturable. */
+int sake_dw_sync(sake_stream_t stream);
 
 /* nn.Dense (+ optional silu) over the last axis — embedding_in / embedding_out of
  * DenseSAKEModel (sake/models.py:24-31,57,60).  y[rows,out] = act(x[rows,in] @ kernel + bias).

@@ -76,6 +76,27 @@ static int check_leaves(const Dims& d, const PS& p, const char* what) {
   return 0;
 }
 
+// ---- deferred weight-gradient work (SAKE_DEFER_DW): one side stream per device -----------------------------
+struct SideCtx {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr}, all = nullptr;
+  bool pending[2] = {false, false}, any = false;
+};
+static SideCtx g_side[64];
+static SideCtx* side_ctx() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  SideCtx* c = &g_side[dev & 63];
+  if (!c->s) {
+    if (cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->done[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->all, cudaEventDisableTiming);
+  }
+  return c;
+}
+
 // SAKE_NODE_TC=0 keeps the CUDA-core per-node kernels under the tcgen05 engines (A/B diagnostics)
 static bool node_tc_enabled() {
   static int v = -1;
@@ -98,8 +119,8 @@ static int resolve_engine(const SakeDims* s, const Dims& d) {
   return SAKE_EINVAL;
 }
 
-struct SavedLayout { size_t e, att, logit, ssum, he, nodeproj, total; };
-static SavedLayout saved_layout(const Dims& d) {
+struct SavedLayout { size_t e, att, logit, ssum, he, nodeproj, nstash, wmix, wedge, wnode, nodeWT, total; };
+static SavedLayout saved_layout(const Dims& d, int engine) {
   SavedLayout L;
   size_t o = 0;
   L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
@@ -108,20 +129,31 @@ static SavedLayout saved_layout(const Dims& d) {
   L.ssum = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
   L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
   L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
+  L.nstash = o; o += align_up(sizeof(float) * (size_t)d.R * NS_LD);
+  L.wmix = L.wedge = L.wnode = L.nodeWT = o;
+  if (engine != SAKE_ENGINE_FP32) {
+    // 1024-byte aligned: the images are sources of bulk (TMA) copies
+    o = align_up(o, 1024);
+    L.wmix = o; o += align_up(tc_scratch_bytes(d, engine, 1, 1), 1024);
+    L.wedge = o; if (tc_edge_supported(d)) o += align_up(edge_w_bytes(), 1024);
+    L.wnode = o; if (tc_node_supported(d)) o += align_up(tc_node_w_bytes(), 1024);
+    L.nodeWT = o; o += align_up(node_wt_bytes(d));
+  }
   L.total = o;
   return L;
 }
-static Saved carve_saved(const Dims& d, void* base, bool tc_edge) {
-  SavedLayout L = saved_layout(d);
+static Saved carve_saved(const Dims& d, void* base, bool tc_edge, int engine) {
+  SavedLayout L = saved_layout(d, engine);
   char* b = (char*)base;
   Saved s;
   s.e = (float*)(b + L.e); s.att = (float*)(b + L.att); s.ssum = (float*)(b + L.ssum);
   s.logit = tc_edge ? (float*)(b + L.logit) : s.att;   // tcgen05 edge path keeps the logits for the backward pass
-  s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj);
+  s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj); s.nstash = (float*)(b + L.nstash);
+  s.wmix = b + L.wmix; s.wedge = b + L.wedge; s.wnode = b + L.wnode; s.nodeWT = (float*)(b + L.nodeWT);
   return s;
 }
 
-struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, tc, edgew, edgeb, xtgp, nbuf, nodew, noded, total; };
+struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, edgeb, xtgp, nbuf, noded, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -140,21 +172,12 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.gZ = o;
     if (with_grads) o += align_up(sizeof(float) * (size_t)d.P * d.C);
   }
-  L.tc = o;
-  if (engine != SAKE_ENGINE_FP32) o += align_up(tc_scratch_bytes(d, engine, for_backward, with_grads));
-  L.edgew = o;
   L.edgeb = o;
-  if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d)) {
-    o += align_up(edge_w_bytes());
-    L.edgeb = o;
-    if (for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
-  }
+  if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d) && for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
   L.xtgp = o;
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_xtg_partial_bytes());
   L.nbuf = o;
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_node_dw_scratch_bytes(d));
-  L.nodew = o;
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d)) o += align_up(tc_node_w_bytes());
   L.noded = o;
   if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && for_backward) o += align_up(tc_node_bwd_scratch_bytes(d));
   L.total = o + 256;
@@ -180,7 +203,9 @@ int sake_resolve_engine(const SakeDims* dims) {
 size_t sake_layer_saved_bytes(const SakeDims* dims) {
   Dims d;
   if (make_dims(dims, &d)) return 0;
-  return saved_layout(d).total;
+  int e = resolve_engine(dims, d);
+  if (e < 0) return 0;
+  return saved_layout(d, e).total;
 }
 
 size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with_param_grads) {
@@ -204,16 +229,17 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if ((rc = check_leaves(d, *params, "params"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
-  if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small: %zu < %zu", saved_bytes, saved_layout(d).total); return SAKE_EINVAL; }
+  if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small: %zu < %zu", saved_bytes, saved_layout(d, engine).total); return SAKE_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(saved) & 255) != 0) { set_error("saved buffer must be 256-byte aligned"); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 0, 0);
   if (SL.total > 256 && (!scratch || scratch_bytes < SL.total)) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
-  Saved sv = carve_saved(d, saved, tc_edge);
+  Saved sv = carve_saved(d, saved, tc_edge, engine);
   if ((rc = gen_node_pre(d, *params, h, sv, st))) return rc;
-  if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, (char*)scratch + SL.edgew, st);
+  if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, sv.wedge, st);
   else rc = gen_edge_fwd(d, *params, x, mask, sv, st);
   if (rc) return rc;
   if ((rc = gen_attn_fwd(d, mask, sv, st))) return rc;
@@ -222,10 +248,12 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else if (engine == SAKE_ENGINE_FP32) {
     if ((rc = gen_mix_fwd(d, *params, x, mask, sv, st))) return rc;
   } else {
-    if ((rc = tc_mix_fwd(d, *params, x, mask, sv, (char*)scratch + SL.tc, engine, st))) return rc;
+    if ((rc = tc_mix_fwd(d, *params, x, mask, sv, sv.wmix, engine, st))) return rc;
   }
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr))
-    return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, (char*)scratch + SL.nodew, st);
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr)) {
+    if ((rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;     // for the backward call's k_node_pre_bwd
+    return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, sv.wnode, st);
+  }
   return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
 }
 
@@ -244,26 +272,34 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (grads && (rc = check_leaves(d, *grads, "grads"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
-  if (saved_bytes < saved_layout(d).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
+  if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 1, grads != nullptr);
   if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // deferred weight gradients: wait for the previous user of this scratch slot before touching the scratch
+  SideCtx* side = nullptr;
+  const int slot = dims->reserved & 1;
+  if ((dims->flags & SAKE_DEFER_DW) && grads && engine != SAKE_ENGINE_FP32) {
+    side = side_ctx();
+    if (!side) { set_error("SAKE_DEFER_DW: cannot create the side stream"); return SAKE_ECUDA; }
+    if (side->pending[slot]) { SAKE_CUDA_CHECK(cudaStreamWaitEvent(st, side->done[slot], 0)); side->pending[slot] = false; }
+  }
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
-  Saved sv = carve_saved(d, const_cast<void*>(saved), tc_edge);
+  Saved sv = carve_saved(d, const_cast<void*>(saved), tc_edge, engine);
   char* b = (char*)scratch;
   BwdScratch sc;
   sc.T = (float*)(b + SL.T); sc.tmax = (float*)(b + SL.tmax); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
+  const bool tc_node = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr);
+  if (tc_node) sc.nodeWT = sv.nodeWT;                 // transposed copies left by the forward call
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr)) {
-    if ((rc = gen_node_wt(d, *params, sc, st))) return rc;     // k_node_pre_bwd still reads the transposed copies
-    rc = tc_node_post_bwd(d, *params, h, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, b + SL.nodew,
+  if (tc_node)
+    rc = tc_node_post_bwd(d, *params, h, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, sv.wnode,
                           b + SL.noded, st);
-  }
   else
     rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st);
   if (rc) return rc;
@@ -273,23 +309,47 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (engine == SAKE_ENGINE_FP32 || !d.spatial) {
     if ((rc = gen_mix_bwd(d, *params, x, mask, sv, sc, gWx, st))) return rc;
   } else {
-    if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, b + SL.tc, engine, xl, st))) return rc;
+    if ((rc = tc_mix_bwd(d, *params, x, mask, sv, sc, gWx, sv.wmix, engine, xl, st))) return rc;
   }
   // tcgen05 edge path: softmax backward only (celu' comes from the saved logits, the W_s g_q term of g_e is
   // added inside the edge kernel); generic path: the original kernel that recomputes q and updates g_e
   if ((rc = tc_edge ? tc_attn_bwd(d, sv, sc, st) : gen_attn_bwd(d, *params, sv, sc, st))) return rc;
   if (tc_edge)
-    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, b + SL.edgew, b + SL.edgeb, xl, st);
+    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, sv.wedge, b + SL.edgeb, xl, st);
   else
     rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);
   if (rc) return rc;
   if (xl.n > 0) {
-    // every weight-gradient contraction of this layer in one batched tensor-core launch
-    if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, st))) return rc;
-    tc_edge_finish(xl, st);
-    tc_node_finish(xl, st);
+    // every weight-gradient contraction of this layer in one batched tensor-core launch (+ its reductions);
+    // nothing downstream of the layer reads dW, so with SAKE_DEFER_DW it runs on the side stream, forked here
+    cudaStream_t ws = st;
+    if (side) {
+      SAKE_CUDA_CHECK(cudaEventRecord(side->fork, st));
+      SAKE_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
+      ws = side->s;
+    }
+    if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, ws))) return rc;
+    tc_edge_finish(xl, ws);
+    tc_node_finish(xl, ws);
+    if (side) {
+      SAKE_CUDA_CHECK(cudaEventRecord(side->done[slot], ws));
+      side->pending[slot] = true;
+      side->any = true;
+    }
   }
   return gen_node_pre_bwd(d, *params, h, dh, grads, sc, st);
+}
+
+int sake_dw_sync(sake_stream_t stream) {
+  SideCtx* side = side_ctx();
+  if (!side) { set_error("sake_dw_sync: cannot create the side stream"); return SAKE_ECUDA; }
+  if (side->any) {
+    SAKE_CUDA_CHECK(cudaEventRecord(side->all, side->s));
+    SAKE_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, side->all, 0));
+    side->any = false;
+    side->pending[0] = side->pending[1] = false;
+  }
+  return 0;
 }
 
 int sake_dense_fwd(int64_t rows, int32_t in_features, int32_t out_features, int32_t act, const float* x,

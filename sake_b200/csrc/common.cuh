@@ -66,7 +66,17 @@ struct Saved {
   float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
   float* he;        // [R,C]   aggregate (layers.py:135-140)
   float* nodeproj;  // [R,NP]
+  float* nstash;    // [R,NS_LD] per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
+  // tcgen05 engines: operand images of the layer's weights, built ONCE by the forward call and reused by the
+  // backward call of the same step (round 1 rebuilt them in both: 5 + 5 small launches per layer)
+  void* wmix;       // x_mixing images for GEMM1 / GEMM2 + {scale, 1/scale}   (tc_mix.cu)
+  void* wedge;      // edge-model images WA..WD + vectors                      (tc_edge.cu)
+  void* wnode;      // node-tail chunk images, forward and transposed blocks   (tc_node.cu)
+  float* nodeWT;    // transposed mlp_in / mlp_out[0] halves for k_node_pre_bwd (generic_bwd.cu)
 };
+// nstash row: silu' of the five hidden layers (tp1 tp2 t1 t2 tv: 5 x 64), then the activations the weight-gradient
+// record needs (hp1, hcomb, n1, av, h': 5 x 64) and the velocity-gate logit y
+enum { NS_D = 0, NS_HP1 = 320, NS_HCOMB = 384, NS_N1 = 448, NS_AV = 512, NS_HOUT = 576, NS_Y = 640, NS_LD = 648 };
 
 // `scratch` buffer for the backward pass
 struct BwdScratch {
@@ -306,7 +316,8 @@ int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
 // tc_node.cu: per-node tail of the layer on the tensor cores (H = 64, A = 4)
 bool tc_node_supported(const Dims& d);
-int gen_node_wt(const Dims& d, const SakeLayerParams& p, const BwdScratch& sc, cudaStream_t st);
+int gen_node_wt(const Dims& d, const SakeLayerParams& p, float* nodeWT, cudaStream_t st);
+size_t node_wt_bytes(const Dims& d);
 size_t tc_node_w_bytes();
 size_t tc_node_bwd_scratch_bytes(const Dims& d);
 int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* v, const float* mask,
@@ -344,7 +355,7 @@ int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const fl
 // mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
                const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L,
-               cudaStream_t st);
+               cudaStream_t st);      // tc_scratch: the images tc_mix_fwd built (saved.wmix)
 size_t tc_scratch_bytes(const Dims& d, int engine, int for_backward, int with_param_grads);
 
 

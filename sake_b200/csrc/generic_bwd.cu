@@ -950,9 +950,10 @@ static SakeLayerGrads null_grads() {
 }
 
 // transposed copies of the node-level weights (k_node_pre_bwd reads mlp_inT / w1hT from them)
-int gen_node_wt(const Dims& d, const SakeLayerParams& p, const BwdScratch& sc, cudaStream_t st) {
+size_t node_wt_bytes(const Dims& d) { return sizeof(float) * node_wt_floats(d); }
+int gen_node_wt(const Dims& d, const SakeLayerParams& p, float* nodeWT, cudaStream_t st) {
   const size_t nwt = node_wt_floats(d);
-  k_node_wt<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(d, p, sc.nodeWT);
+  k_node_wt<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(d, p, nodeWT);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

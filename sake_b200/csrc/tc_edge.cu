@@ -642,8 +642,7 @@ size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads) {
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
                 cudaStream_t st) {
-  EdgeW w = carve_edge_w(wscratch);
-  edge_prep(d, p, w, st);
+  EdgeW w = carve_edge_w(wscratch);                      // built by tc_edge_fwd of the same step (saved.wedge)
   char* eb = (char*)escratch;
   float* PB = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * PB_LD);
   float* extra = (float*)eb; eb += align_up(sizeof(float) * 2 * PB_LD);

@@ -1018,10 +1018,8 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   uint8_t* w1 = (uint8_t*)scratch;
   uint8_t* w2 = w1 + wimg_bytes<CF>();
   TileGeom g = make_geom(d);
-  const int prep_threads = 2 * CF::NCHUNK * CC * 8;
   float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
-  k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
-  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
+  (void)p;                                                            // the images were built by the forward call
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_mix_bwd<ENGINE>, smem_bytes<CF>(), optin); if (rc) return rc; }
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
@@ -1033,7 +1031,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
                                                                   reinterpret_cast<const float4*>(sc.T), sc.tmax, sc.ghe,
                                                                   sc.ge, sc.gatt, sc.gdir, gWx ? sc.gZ : nullptr, dbg);
   }
-  note_launches(2);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   if (gWx) {
     // dWx[c][c'] += sum_pairs E[pair][c] * dZ[pair][c']  (layers.py:95) on the tensor cores

@@ -79,6 +79,7 @@ struct NodeFwdArgs {
   const uint8_t* wimg;
   const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
   float *h_out, *x_out, *v_out;
+  float* stash;                                          // [R, NS_LD] activations kept for the backward kernel (or NULL)
 };
 
 __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
   const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0;
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   int wc = 0;                                            // weight chunk of the next run_chunk
+  float* ns = (a.stash && valid) ? a.stash + row * NS_LD : nullptr;   // this atom's row of the fwd -> bwd stash
 
   // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256
   float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
@@ -198,9 +200,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      float vals[4];
+      float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = fsilu_(v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
+      if (ns) {
+        *reinterpret_cast<float4*>(ns + NS_D + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        *reinterpret_cast<float4*>(ns + NS_HP1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      }
       nt_store_unit(img, tid, u, vals);
     }
     ++wc;
@@ -225,9 +231,17 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        float vals[4];
+        float vals[4], dvs[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) vals[i] = spatial ? fsilu_(v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i]) : 0.f;
+        for (int i = 0; i < 4; ++i) {
+          const float z = v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i];
+          vals[i] = spatial ? fsilu_(z) : 0.f;
+          dvs[i] = spatial ? fdsilu_(z) : 0.f;
+        }
+        if (ns) {
+          *reinterpret_cast<float4*>(ns + NS_D + 64 + (c - 10) * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          *reinterpret_cast<float4*>(ns + NS_HCOMB + (c - 10) * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        }
         nt_store_unit(img, tid, u, vals);
       }
     }
@@ -242,9 +256,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      float vals[4];
+      float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = fsilu_(v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
+      if (ns) {
+        *reinterpret_cast<float4*>(ns + NS_D + 128 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        *reinterpret_cast<float4*>(ns + NS_N1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      }
       nt_store_unit(img, tid, u, vals);
     }
     ++wc;
@@ -261,9 +279,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     for (int u = 0; u < 8; ++u) {
       const float4 h4 = __ldg(hp + c * 8 + u);
       const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
-      float vals[4];
+      float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vals[i] = hin[i] + fsilu_(v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]);
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]; vals[i] = hin[i] + fsilu_(z); dvs[i] = fdsilu_(z); }
+      if (ns) {
+        *reinterpret_cast<float4*>(ns + NS_D + 192 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        *reinterpret_cast<float4*>(ns + NS_HOUT + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      }
       if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       if (upd && hv) nt_store_unit(img, tid, u, vals);
     }
@@ -279,9 +301,23 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
       tmem_ld32(lane_addr + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) y = fmaf(fsilu_(v[k] + s_bv1[c * 32 + k]), s_vel2[c * 32 + k], y);
+      for (int u = 0; u < 8; ++u) {
+        float av[4], dvs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = 4 * u + i;
+          const float z = v[k] + s_bv1[c * 32 + k];
+          av[i] = fsilu_(z); dvs[i] = fdsilu_(z);
+          y = fmaf(av[i], s_vel2[c * 32 + k], y);
+        }
+        if (ns) {
+          *reinterpret_cast<float4*>(ns + NS_D + 256 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          *reinterpret_cast<float4*>(ns + NS_AV + c * 32 + 4 * u) = make_float4(av[0], av[1], av[2], av[3]);
+        }
+      }
     }
   }
+  if (ns) ns[NS_Y] = y;
   // ---------------- velocity / position update (layers.py:218-232)
   if (valid) {
     const float* xr = a.x + row * 3;
@@ -314,7 +350,6 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
 // =================================================================================================
 enum { NB_N1 = 0, NB_GT2 = 64, NB_CAT = 128, NB_GT1 = 512, NB_HP1 = 576, NB_GTP2 = 640, NB_GTP1 = 704, NB_NRM = 768,
        NB_HOUT = 1024, NB_GTV = 1088, NB_AV = 1152, NB_GY = 1216, NB_LD = 1232 };
-constexpr int ND_LD = 320;                   // stash row: silu'(tp1) silu'(tp2) silu'(t1) silu'(t2) silu'(tv)
 
 struct NodeBwdArgs {
   int R, N, update, has_v, spatial;
@@ -323,7 +358,8 @@ struct NodeBwdArgs {
   const uint8_t* wimg;
   const float *b_p1, *b_p2, *b_n1, *b_n2, *b_v1, *vel2, *wv;
   float *dh, *dx, *dv, *T, *ghe, *tmax;
-  float *nder, *qv, *nbuf;                   // stash [R,320]; g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
+  const float* stash;                        // saved.nstash [R, NS_LD] written by k_tc_node_post
+  float *qv, *nbuf;                          // g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
 };
 
 __device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     // 32 floats of a row block
@@ -354,7 +390,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     mbar_init(wfull, 1); mbar_init(wfull + 1, 1); mbar_init(mdone, 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(wfull, NT_WCH);
-    bulk_g2s(wring, a.wimg, NT_WCH, wfull);              // chunk 0
+    // first chunk the backward chain consumes: vel0^T with a velocity gate, node2^T otherwise
+    bulk_g2s(wring, a.wimg + (size_t)((a.update && a.has_v) ? NTB_VEL0T : NTB_NODE2T) * NT_WCH, NT_WCH, wfull);
   }
   if (warp == 0) tmem_alloc<128>(tptr);
   tc_fence_before();
@@ -376,7 +413,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     return nx;
   };
   uint32_t mph = 0;
-  int wpos = 0, wc = 0;                                  // ring position, current weight chunk
+  int wpos = 0, wc = uv ? NTB_VEL0T : NTB_NODE2T;        // ring position, current weight chunk
   auto run_chunk = [&](uint32_t img_u32, uint32_t dcol, bool first) {
     fence_proxy_async();
     tc_fence_before();
@@ -406,7 +443,7 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     ++wpos;
     wc = wnext;
   };
-  // wc always names the chunk the next run_chunk will consume (chunk 0 is requested in the prologue)
+  // wc always names the chunk the next run_chunk will consume (the first one is requested in the prologue)
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < nrows_real;
@@ -422,139 +459,53 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   }
   const float inv_den = 1.0f / den;
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
-  float* nd = a.nder + row * ND_LD;
   float* nb = a.nbuf ? a.nbuf + row * NB_LD : nullptr;
   const bool rec = nb != nullptr && valid;
   const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
   const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
 
-  // =============================== forward recompute ===============================
-  // post0 (K = 256, serial chunks through imgA) -> D0 = tp1
+  // =============================== forward activations: kept by k_tc_node_post ===============================
+  // (round 1 recomputed the forward here: 26 of the kernel's 52 serial chunk-GEMM rounds, on a kernel that is
+  // latency-bound at every size; the forward kernel now leaves silu' of the five hidden layers, the inputs of the
+  // Dense layers and the gate logit in saved.nstash, 2.6 KB per atom)
+  const float* nd = a.stash + row * NS_LD;
+  if (rec) {
+    // X operands of the batched weight-gradient contractions (record layout NB_*): the inputs of every Dense layer
+    if (spatial) {
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
-    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
+      for (int c = 0; c < 8; ++c) {                         // nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129)
+        const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float s[12];
+        for (int u = 0; u < 8; ++u) {
+          float s[12];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 t4 = __ldg(sp + u * 3 + q);
-        s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
-      }
-      float vals[4];
+          for (int q = 0; q < 3; ++q) {
+            const float4 t4 = __ldg(sp + u * 3 + q);
+            s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
+          }
+          float vals[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
-        vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
-      }
-      if (rec && spatial) *reinterpret_cast<float4*>(nb + NB_NRM + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-      nt_store_unit(imgA, tid, u, vals);
-    }
-    run_chunk(imgA_u32, D0, c == 0);
-  }
-  // hp1 = silu(tp1 + b), stash silu'; post2 -> D1 = tp2
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    float v[32], dv_[32];
-    tmem_ld32(lane_addr + c * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bp1[c * 32 + k]; v[k] = fsilu_(z); dv_[k] = fdsilu_(z); }
-    if (valid) st64(nd, c, dv_);
-    if (rec && spatial) st64(nb + NB_HP1, c, v);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
-  }
-  run_chunk(imgA_u32, D1, true);
-  run_chunk(imgB_u32, D1, false);
-  // node0 over [h | h_e | h_comb] (serial chunks) -> D0 = t1
-#pragma unroll 1
-  for (int c = 0; c < 12; ++c) {
-    if (c < 10) {
-      const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 t4 = __ldg(src + u);
-        const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
-        if (rec) *reinterpret_cast<float4*>(nb + NB_CAT + c * 32 + 4 * u) = t4;
-        nt_store_unit(imgA, tid, u, vals);
-      }
-    } else {
-      float v[32], dv_[32];
-      tmem_ld32(lane_addr + 64 + (c - 10) * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float z = v[k] + s_bp2[(c - 10) * 32 + k];
-        v[k] = spatial ? fsilu_(z) : 0.f;
-        dv_[k] = spatial ? fdsilu_(z) : 0.f;
-      }
-      if (valid) st64(nd + 64, c - 10, dv_);
-      if (rec) st64(nb + NB_CAT + 320, c - 10, v);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) nt_store_unit(imgA, tid, u, v + 4 * u);
-    }
-    run_chunk(imgA_u32, D0, c == 0);
-  }
-  // n1 = silu(t1 + b), stash silu'; node2 -> D1 = t2
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    float v[32], dv_[32];
-    tmem_ld32(lane_addr + c * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { const float z = v[k] + s_bn1[c * 32 + k]; v[k] = fsilu_(z); dv_[k] = fdsilu_(z); }
-    if (valid) st64(nd + 128, c, dv_);
-    if (rec) st64(nb + NB_N1, c, v);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
-  }
-  run_chunk(imgA_u32, D1, true);
-  run_chunk(imgB_u32, D1, false);
-  // stash silu'(t2); h' = h + silu(t2 + b); velocity gate MLP on h' -> D0 = tv, y = av . vel2
-  float y = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    float v[32], dv_[32];
-    tmem_ld32(lane_addr + 64 + c * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float4 h4 = __ldg(hp + c * 8 + u);
-      const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i];
-        dv_[4 * u + i] = fdsilu_(z);
-        v[4 * u + i] = hin[i] + fsilu_(z);
+          for (int i = 0; i < 4; ++i) {
+            const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
+            vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
+          }
+          *reinterpret_cast<float4*>(nb + NB_NRM + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        }
       }
     }
-    if (valid) st64(nd + 192, c, dv_);
-    if (uv) {
-      if (rec) st64(nb + NB_HOUT, c, v);
+    auto copy64 = [&](float* dst, const float* src) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
-    }
-  }
-  if (uv) {
-    run_chunk(imgA_u32, D0, true);
-    run_chunk(imgB_u32, D0, false);
+      for (int u = 0; u < 16; ++u) *reinterpret_cast<float4*>(dst + 4 * u) = __ldg(reinterpret_cast<const float4*>(src) + u);
+    };
+    if (spatial) copy64(nb + NB_HP1, nd + NS_HP1);
+    copy64(nb + NB_CAT, a.h + row * 64);
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      float v[32], dv_[32];
-      tmem_ld32(lane_addr + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float z = v[k] + s_bv1[c * 32 + k];
-        v[k] = fsilu_(z);
-        dv_[k] = fdsilu_(z);
-        y = fmaf(v[k], s_vel2[c * 32 + k], y);
-      }
-      if (valid) st64(nd + 256, c, dv_);
-      if (rec) st64(nb + NB_AV, c, v);
-    }
+    for (int q = 0; q < 4; ++q) copy64(nb + NB_CAT + 64 + 64 * q, a.he + row * 256 + 64 * q);
+    copy64(nb + NB_CAT + 320, nd + NS_HCOMB);
+    copy64(nb + NB_N1, nd + NS_N1);
+    if (uv) { copy64(nb + NB_HOUT, nd + NS_HOUT); copy64(nb + NB_AV, nd + NS_AV); }
   }
+  const float y = nd[NS_Y];
   // =============================== velocity / position update backward (layers.py:226-232) ===============================
   float gdv0 = 0.f, gdv1 = 0.f, gdv2 = 0.f, gy = 0.f;
   if (valid) {
@@ -753,15 +704,14 @@ __global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, co
 }
 
 size_t tc_node_bwd_scratch_bytes(const Dims& d) {
-  return align_up(sizeof(float) * (size_t)d.R * ND_LD) + align_up(sizeof(float) * (size_t)d.R * 4);
+  return align_up(sizeof(float) * (size_t)d.R * 4);
 }
 
 int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, const float* v, const float* mask,
                      const Saved& sv, const float* dh_out, const float* dx_out, const float* dv_out, float* dh, float* dx,
                      float* dv, const SakeLayerGrads* g, const BwdScratch& sc, void* wscratch, void* nscratch,
                      cudaStream_t st) {
-  uint8_t* wimg = (uint8_t*)wscratch;
-  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTB_CHUNKS);
+  uint8_t* wimg = (uint8_t*)wscratch;                     // built by tc_node_post of the same step (saved.wnode)
   NodeBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
@@ -771,9 +721,9 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
   a.dh = dh; a.dx = dx; a.dv = dv; a.T = sc.T; a.ghe = sc.ghe; a.tmax = sc.tmax;
-  a.nder = (float*)nscratch;
+  a.stash = sv.nstash;
   const bool wvg = g != nullptr && d.update && d.spatial;
-  a.qv = wvg ? (float*)((char*)nscratch + align_up(sizeof(float) * (size_t)d.R * ND_LD)) : nullptr;
+  a.qv = wvg ? (float*)nscratch : nullptr;
   a.nbuf = g ? sc.nbuf : nullptr;
   const size_t smem = 4 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
   static unsigned long long optin = 0;
@@ -783,7 +733,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
     k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
   }
   if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
-  note_launches(wvg ? 3 : 2);
+  note_launches(wvg ? 2 : 1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -794,7 +744,8 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st) {
   uint8_t* wimg = (uint8_t*)wscratch;
-  k_node_w_prep<<<(NTW_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTW_CHUNKS);
+  // all chunks, forward and transposed: the backward call of this step reuses the image
+  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTB_CHUNKS);
   NodeFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
@@ -802,7 +753,7 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.h = h; a.x = x; a.v = v; a.mask = mask; a.ssum = sv.ssum; a.he = sv.he; a.wimg = wimg;
   a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
-  a.h_out = h_out; a.x_out = x_out; a.v_out = v_out;
+  a.h_out = h_out; a.x_out = x_out; a.v_out = v_out; a.stash = sv.nstash;
   const size_t smem = 2 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_node_post, smem, optin); if (rc) return rc; }

@@ -58,7 +58,7 @@ class ParamSet:
 
 class ModelRunner:
     def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
-                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0):
+                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=True):
         """masked: QM9-style padded batch with the reference's float mask = outer(m, m) (every kernel computes
         all N^2 pairs of the padded width and multiplies by the mask, like the reference).
         ragged: the same padded batch, but only the n_real[b] real atoms of every molecule are stored and
@@ -114,6 +114,15 @@ class ModelRunner:
         self.saved = [ops._buf(ops.saved_bytes(d), dev) for d in self.dims]
         nscr = max(max(ops.scratch_bytes(d, 0, 0), ops.scratch_bytes(d, 1, int(train))) for d in self.dims)
         self.scratch = ops._buf(nscr, dev)
+        # training on a tcgen05 engine: the weight-gradient contractions of layer l run on the library's side stream
+        # under the backward of layer l-1 (SAKE_DEFER_DW), which needs a second scratch buffer to alternate with
+        self.defer_dw = bool(defer_dw and train and self.engine != "fp32" and self.L > 1)
+        self.scratches = [self.scratch, ops._buf(nscr, dev)] if self.defer_dw else [self.scratch, self.scratch]
+        self.dims_bwd = []
+        for l, d in enumerate(self.dims):
+            db = _lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags | (_lib.SAKE_DEFER_DW if self.defer_dw else 0),
+                               d.engine, l & 1)
+            self.dims_bwd.append(db)
         self.y0 = torch.empty(B, N, self.H, device=dev, dtype=f32)
         self.y = torch.empty(B, N, self.out, device=dev, dtype=f32)
         self.energy = torch.empty(B, device=dev, dtype=f32)
@@ -125,7 +134,7 @@ class ModelRunner:
         self.dv = [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(2)]
         self.forces = torch.empty(B, N, 3, device=dev, dtype=f32)
         self.hbm_bytes = sum(t.numel() * t.element_size() for t in
-                             [self.flat_params, self.scratch, *self.saved, *self.hs, *self.xs[1:], *self.vs[1:]])
+                             [self.flat_params, *set(self.scratches), *self.saved, *self.hs, *self.xs[1:], *self.vs[1:]])
 
     # -- inputs ------------------------------------------------------------------------------------
     def load_inputs(self, h, x, mask=None, atom_mask=None, target=None, n_real=None):
@@ -203,16 +212,19 @@ class ModelRunner:
         for l in reversed(range(self.L)):
             nxt = 1 - cur
             v_in = self.vs[l] if self.has_v[l] else None
-            ops.layer_bwd_raw(self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in, self.mask, self.saved[l],
-                              self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
+            ops.layer_bwd_raw(self.dims_bwd[l] if with_grads else self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in,
+                              self.mask, self.saved[l], self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
                               self.dv[nxt] if v_in is not None else None,
-                              self.gs[l] if with_grads else None, self.scratch, self.rg)
+                              self.gs[l] if with_grads else None, self.scratches[l & 1] if with_grads else self.scratch,
+                              self.rg)
             dx_out = self.dx[nxt]
             dv_out = self.dv[nxt] if v_in is not None else None
             cur = nxt
         if with_grads:
             ops.dense_bwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.dh[cur], None,
                               g["embedding_in/kernel"], g.get("embedding_in/bias"), 0, self.rg)
+            if self.defer_dw:                  # join the side stream: gradients complete from here on
+                check(lib.sake_dw_sync(ops._stream()), "sake_dw_sync")
         self._dx_final = dx_out
 
     # -- the two driver closures ---------------------------------------------------------------------
