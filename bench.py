@@ -246,7 +246,7 @@ class ModelJob:
         model = sake_b200.DenseSAKEModel(hidden_features=H, out_features=1, depth=args.depth, engine=args.engine)
         self.run = R.ModelRunner(model, init_params_cpu(args.depth, S, 0), B, N, S, masked=padded and not self.ragged,
                                  ragged=self.ragged, train=(mode == "train"), device=dev,
-                                 defer_dw=not args.no_defer_dw)
+                                 defer_dw=args.defer_dw)
         h, x, mask, am, y, n_real = synth(2666 + rank, B, N, S, padded, n_min)
         self.n_real = n_real
         pin = lambda a: None if a is None else torch.tensor(a).pin_memory()
@@ -388,7 +388,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="molecules in the CPU-baseline sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step as a CUDA graph")
-    ap.add_argument("--no-defer-dw", action="store_true", help="keep the weight-gradient contractions on the main stream")
+    ap.add_argument("--defer-dw", action="store_true",
+                    help="run the weight-gradient contractions on the library's side stream (measured: no gain, see DESIGN.md)")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total-size cfg3 / cfg4 records")
     ap.add_argument("--no-sustained", action="store_true", help="skip the extra timed rounds that extend the run to ~2.5 s")
     args = ap.parse_args()

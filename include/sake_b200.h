@@ -43,6 +43,10 @@ enum {
   SAKE_HAS_V = 2,        /* v argument is not None (sake/layers.py:226-229)                    */
   SAKE_HAS_MASK = 4,     /* mask argument is not None, float [B,N,N]                           */
   SAKE_NO_SPATIAL = 8,   /* use_spatial_attention=False (sake/layers.py:210-212)              */
+  SAKE_COSINE_CUTOFF = 32, /* DenseSAKELayer.cutoff = sake.utils.cosine_cutoff(lower, upper) (sake/utils.py:10-26,
+                            sake/layers.py:172-176): euclidean_attention = 0.5 (cos(pi (2 (d - lower) / (upper - lower) + 1)) + 1)
+                            with SakeDims.cutoff_lower / cutoff_upper; as in the reference the range masks are
+                            NOT applied (utils.py:24-25 discards them), so the factor is periodic in d       */
   SAKE_DEFER_DW = 16     /* sake_layer_bwd only: enqueue the weight-gradient contractions (dW = X^T G over all
                             pairs / atoms; nothing downstream of the layer reads them) on the library's side
                             stream so that they overlap the next layer's backward.  SakeDims.reserved = scratch
@@ -71,6 +75,8 @@ typedef struct SakeDims {
   int32_t flags;  /* SAKE_UPDATE | SAKE_HAS_V | SAKE_HAS_MASK | SAKE_NO_SPATIAL                  */
   int32_t engine; /* SAKE_ENGINE_*                                                               */
   int32_t reserved;
+  float cutoff_lower; /* only read with SAKE_COSINE_CUTOFF                                         */
+  float cutoff_upper;
 } SakeDims;
 
 /* Parameters of one DenseSAKELayer, flax layouts (kernel = [in, out]); SURVEY Appendix C.

@@ -100,10 +100,13 @@ def coords(rng, shape):
     return (rng.standard_normal(shape) * 0.62 * n ** (1.0 / 3.0)).astype(np.float32)
 
 
-def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True):
+def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True, cutoff=None):
+    """cutoff: None or (lower, upper) -> DenseSAKELayer(cutoff=partial(sake.utils.cosine_cutoff, lower=, upper=))"""
+    import functools
     rng = np.random.default_rng(seed)
     jax.set_dtype(torch.float64)
-    model = sake.layers.DenseSAKELayer(H, H, update=update)
+    cut = None if cutoff is None else functools.partial(sake.utils.cosine_cutoff, lower=cutoff[0], upper=cutoff[1])
+    model = sake.layers.DenseSAKELayer(H, H, update=update, cutoff=cut)
     shp = tuple(batch) + (N,)
     h = rng.uniform(size=shp + (H,)).astype(np.float32)
     x = coords(rng, shp + (3,))
@@ -131,8 +134,10 @@ def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True):
             out["v"] = vo
         return out
 
-    save(name, flat, {"h": h, "x": x, "v": v, "mask": mask}, run_both(fn),
-         {"H": H, "N": N, "n_real": n_real, "update": int(update), "kind": "layer"})
+    meta = {"H": H, "N": N, "n_real": n_real, "update": int(update), "kind": "layer"}
+    if cutoff is not None:
+        meta["cutoff"] = np.asarray(cutoff, dtype=np.float64)
+    save(name, flat, {"h": h, "x": x, "v": v, "mask": mask}, run_both(fn), meta)
 
 
 def case_model(name, H, F_in, depth, N, batch, with_v, seed, out_features=1, update=True, grad_keys=()):
@@ -213,6 +218,9 @@ def main_round2():
           "xv_0/sake_model/d1/node_mlp/layers_2/bias", "vx_0/sake_model/embedding_in/kernel")
     case_flow("flow_h64_n13_d3", 64, 1, 2, 13, 3, 4, 13, grad_keys=gk)
     case_flow("flow_h64_n4_d2", 64, 1, 2, 4, 2, 5, 14, grad_keys=gk)
+    # DenseSAKELayer(cutoff=cosine_cutoff) (sake/layers.py:172-176, sake/utils.py:10-26): tcgen05 shape and generic shape
+    case_layer("layer_h64_n9_b2_cutoff", 64, 9, (2,), True, False, 21, cutoff=(0.0, 5.0))
+    case_layer("layer_h16_n6_cutoff", 16, 6, (), False, False, 22, cutoff=(0.5, 4.0))
 
 
 def main():

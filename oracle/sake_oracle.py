@@ -104,10 +104,15 @@ def semantic_attention(p, h_e_mtx, mask=None):
     return torch.softmax(att, dim=-2)
 
 
-def combined_attention(p, x_norm, h_e_mtx, mask=None, guarded=True):
-    # sake/layers.py:170-182 (cutoff=None -> euclidean_attention = 1.0)
+def cosine_cutoff(x, lower=0.0, upper=5.0):
+    # sake/utils.py:10-26 (the range masks computed at :24-25 are discarded there: the cosine is the whole function)
+    return 0.5 * (torch.cos(math.pi * (2 * (x - lower) / (upper - lower) + 1.0)) + 1.0)
+
+
+def combined_attention(p, x_norm, h_e_mtx, mask=None, guarded=True, cutoff=None):
+    # sake/layers.py:170-182; cutoff: None (euclidean_attention = 1.0) or a callable of the pair distances
     sem = semantic_attention(p, h_e_mtx, mask=mask)
-    comb = 1.0 * sem
+    comb = (1.0 if cutoff is None else cutoff(x_norm)) * sem
     if mask is not None:
         comb = comb * mask.unsqueeze(-1)
     den = comb.sum(dim=-2, keepdim=True)
@@ -134,13 +139,13 @@ def spatial_attention(p, h_e_att, x_minus_xt, x_norm, mask=None):
 
 
 def layer_forward(p, h, x, v=None, mask=None, *, update=True, use_spatial_attention=True,
-                  guarded=True):
-    """DenseSAKELayer.__call__  (sake/layers.py:188-235).  he / cutoff are not supported."""
+                  guarded=True, cutoff=None):
+    """DenseSAKELayer.__call__  (sake/layers.py:188-235).  he is not supported."""
     x_minus_xt = get_x_minus_xt(x)
     x_norm = get_x_minus_xt_norm(x_minus_xt)
     h_cat_ht = get_h_cat_ht(h)
     h_e_mtx = edge_model(p["edge_model"], h_cat_ht, x_norm)
-    att = combined_attention(p, x_norm, h_e_mtx, mask=mask, guarded=guarded)
+    att = combined_attention(p, x_norm, h_e_mtx, mask=mask, guarded=guarded, cutoff=cutoff)
     h_e_att = h_e_mtx.unsqueeze(-1) * att.unsqueeze(-2)                    # [..., i, j, H, A]
     h_e_att = h_e_att.reshape(*h_e_att.shape[:-2], -1)                    # c = f*A + a
     h_comb, delta_v = spatial_attention(p, h_e_att, x_minus_xt, x_norm, mask=mask)
@@ -174,14 +179,14 @@ def layer_forward(p, h, x, v=None, mask=None, *, update=True, use_spatial_attent
 
 
 def model_forward(params, h, x, v=None, mask=None, *, update=True, use_spatial_attention=True,
-                  guarded=True):
+                  guarded=True, cutoff=None):
     """DenseSAKEModel.__call__ (sake/models.py:56-61).  depth = number of 'd<k>' entries."""
     depth = sum(1 for k in params if k.startswith("d") and k[1:].isdigit())
     upd = [update] * depth if isinstance(update, bool) else list(update)
     h = dense(params["embedding_in"], h)
     for k in range(depth):
         h, x, v = layer_forward(params["d%d" % k], h, x, v, mask, update=upd[k],
-                                use_spatial_attention=use_spatial_attention, guarded=guarded)
+                                use_spatial_attention=use_spatial_attention, guarded=guarded, cutoff=cutoff)
     h = silu(dense(params["embedding_out"]["layers_0"], h))
     h = dense(params["embedding_out"]["layers_2"], h)
     return h, x, v

@@ -15,7 +15,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 # enums (include/sake_b200.h)
-SAKE_UPDATE, SAKE_HAS_V, SAKE_HAS_MASK, SAKE_NO_SPATIAL, SAKE_DEFER_DW = 1, 2, 4, 8, 16
+SAKE_UPDATE, SAKE_HAS_V, SAKE_HAS_MASK, SAKE_NO_SPATIAL, SAKE_DEFER_DW, SAKE_COSINE_CUTOFF = 1, 2, 4, 8, 16, 32
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32X3, ENGINE_BF16, ENGINE_F16X2 = 0, 1, 2, 3, 4
 ENGINES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32x3": ENGINE_TF32X3, "bf16": ENGINE_BF16,
            "f16x2": ENGINE_F16X2}
@@ -23,7 +23,8 @@ ENGINE_NAMES = {v: k for k, v in ENGINES.items()}
 
 
 class SakeDims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "N", "H", "A", "K", "flags", "engine", "reserved")]
+    _fields_ = ([(n, C.c_int32) for n in ("B", "N", "H", "A", "K", "flags", "engine", "reserved")] +
+                [("cutoff_lower", C.c_float), ("cutoff_upper", C.c_float)])
 
 
 PARAM_FIELDS = (

@@ -41,6 +41,9 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->has_v = (s->flags & SAKE_HAS_V) != 0;
   d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
   d->spatial = (s->flags & SAKE_NO_SPATIAL) == 0;
+  d->cutoff = (s->flags & SAKE_COSINE_CUTOFF) != 0;
+  d->cut_lo = s->cutoff_lower; d->cut_hi = s->cutoff_upper;
+  if (d->cutoff && !(d->cut_hi > d->cut_lo)) { set_error("cosine cutoff needs upper > lower (got %g, %g)", d->cut_lo, d->cut_hi); return SAKE_EINVAL; }
   d->hdr = nullptr; d->rowinfo = nullptr; d->tileinfo = nullptr; d->molinfo = nullptr;
   return 0;
 }
@@ -153,7 +156,7 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge, int engine) {
   return s;
 }
 
-struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gproj, wxT, nodeWT, gZ, edgeb, xtgp, nbuf, noded, total; };
+struct ScratchLayout { size_t T, tmax, ghe, ge, gatt, gdir, gcut, gproj, wxT, nodeWT, gZ, edgeb, xtgp, nbuf, noded, total; };
 static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward, int with_grads) {
   ScratchLayout L;
   memset(&L, 0, sizeof(L));
@@ -165,6 +168,7 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.ge = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
     L.gatt = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
     L.gdir = o; o += align_up(sizeof(float) * (size_t)d.P * 3);
+    L.gcut = o; if (d.cutoff) o += align_up(sizeof(float) * (size_t)d.P);
     L.gproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
     L.wxT = o; o += align_up(sizeof(float) * (size_t)d.C * d.C);
     L.nodeWT = o; o += align_up(sizeof(float) * ((size_t)d.H * (2 * d.H + d.C) + 3 * (size_t)d.H * d.H + (size_t)d.H * d.C +
@@ -242,7 +246,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, sv.wedge, st);
   else rc = gen_edge_fwd(d, *params, x, mask, sv, st);
   if (rc) return rc;
-  if ((rc = gen_attn_fwd(d, mask, sv, st))) return rc;
+  if ((rc = gen_attn_fwd(d, x, mask, sv, st))) return rc;
   if (!d.spatial) {
     SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
   } else if (engine == SAKE_ENGINE_FP32) {
@@ -292,6 +296,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   BwdScratch sc;
   sc.T = (float*)(b + SL.T); sc.tmax = (float*)(b + SL.tmax); sc.ghe = (float*)(b + SL.ghe); sc.ge = (float*)(b + SL.ge);
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
+  sc.gcut = d.cutoff ? (float*)(b + SL.gcut) : nullptr;
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   const bool tc_node = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr);
   if (tc_node) sc.nodeWT = sv.nodeWT;                 // transposed copies left by the forward call
@@ -313,7 +318,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   }
   // tcgen05 edge path: softmax backward only (celu' comes from the saved logits, the W_s g_q term of g_e is
   // added inside the edge kernel); generic path: the original kernel that recomputes q and updates g_e
-  if ((rc = tc_edge ? tc_attn_bwd(d, sv, sc, st) : gen_attn_bwd(d, *params, sv, sc, st))) return rc;
+  if ((rc = tc_edge ? tc_attn_bwd(d, x, sv, sc, st) : gen_attn_bwd(d, *params, x, sv, sc, st))) return rc;
   if (tc_edge)
     rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, sv.wedge, b + SL.edgeb, xl, st);
   else

@@ -34,6 +34,8 @@ struct Dims {
   int Kp;                 // K rounded up to a multiple of 4 (16-byte aligned projection blocks)
   int NP;                 // per-node projection width = 2Kp + 2H
   int update, has_v, has_mask, spatial;
+  int cutoff;             // 1: cosine cutoff on the attention (layers.py:172-176), parameters below
+  float cut_lo, cut_hi;
   const RaggedHdr* hdr;   // NULL: uniform batch (every molecule has N atoms, optional float mask)
   const int4* rowinfo;
   const int4* tileinfo;
@@ -89,6 +91,7 @@ struct BwdScratch {
   float* gproj;     // [R,NP]  cotangent of nodeproj
   float* wxT;       // [C,C]   x_mixing kernel transposed
   float* gZ;        // [P,C]   cotangent of pre-tanh coefficients (training only, feeds the dW GEMM)
+  float* gcut;      // [P]     cotangent of the pair distance through the cosine cutoff (NULL without cutoff)
   float* nodeWT;       // transposed copies of the node-level weight matrices (k_node_wt)
   float* nbuf;         // per-node record for the node-level weight-gradient contractions (tcgen05 engines, training)
   float* xtg_partial;  // per-CTA partial sums of the weight-gradient contractions (tcgen05 engines, training)
@@ -102,6 +105,23 @@ __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float dsiluf_(float x) {
   float s = sigmoidf_(x);
   return s * (1.0f + x * (1.0f - s));
+}
+// sake.utils.cosine_cutoff (utils.py:10-26; the range masks computed there are discarded, so this is the whole
+// function): eps(d) = 0.5 (cos(pi (2 (d - lo) / (hi - lo) + 1)) + 1) = 0.5 (1 - cos(theta)), theta = 2 pi (d - lo) / (hi - lo)
+__device__ __forceinline__ float cosine_cutoff_(float d, float lo, float hi) {
+  return 0.5f * (cosf(3.14159265358979323846f * (2.0f * (d - lo) / (hi - lo) + 1.0f)) + 1.0f);
+}
+// d eps / dd divided by eps: (2 pi / (hi - lo)) * sin(theta) / (1 - cos(theta)); 0 where eps = 0
+__device__ __forceinline__ float cosine_cutoff_dlog_(float d, float lo, float hi) {
+  const float th = 6.28318530717958647692f * (d - lo) / (hi - lo);
+  const float den = 1.0f - cosf(th);
+  return den > 0.f ? (6.28318530717958647692f / (hi - lo)) * sinf(th) / den : 0.f;
+}
+// pair distance as the layer defines it (functional.py:14-17)
+__device__ __forceinline__ float pair_dist_(const float* __restrict__ x, int i, int j) {
+  const float r0 = x[(size_t)j * 3] - x[(size_t)i * 3], r1 = x[(size_t)j * 3 + 1] - x[(size_t)i * 3 + 1],
+              r2 = x[(size_t)j * 3 + 2] - x[(size_t)i * 3 + 2];
+  return sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);
 }
 // nn.celu(alpha=2): max(x,0) + 2*expm1(min(x,0)/2)   (layers.py:81)
 __device__ __forceinline__ float celu2f_(float x) { return x > 0.f ? x : 2.0f * expm1f(0.5f * x); }
@@ -313,7 +333,7 @@ size_t tc_xtg_partial_bytes();
 int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st);
 int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                  cudaStream_t st);
-int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st);
+int gen_attn_fwd(const Dims& d, const float* x, const float* mask, const Saved& sv, cudaStream_t st);
 // tc_node.cu: per-node tail of the layer on the tensor cores (H = 64, A = 4)
 bool tc_node_supported(const Dims& d);
 int gen_node_wt(const Dims& d, const SakeLayerParams& p, float* nodeWT, cudaStream_t st);
@@ -327,7 +347,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
 int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st);
-int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
+int tc_attn_bwd(const Dims& d, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
 int gen_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 cudaStream_t st);
 int gen_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
@@ -342,7 +362,7 @@ size_t tc_node_dw_scratch_bytes(const Dims& d);
 int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
-int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
+int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
 int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, float* dx,
                  const SakeLayerGrads* g, const BwdScratch& sc, cudaStream_t st);
 int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,

@@ -561,9 +561,10 @@ __global__ void k_transpose(int n, const float* __restrict__ in, float* __restri
 // One warp per receiving atom.  g_s = att*(g_att - sum_j g_att*att) (the renormalisation of
 // layers.py:180 is the identity on the gradient); g_q = g_s*celu'(q); g_e += Ws g_q.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_attn_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ e,
+__global__ void __launch_bounds__(256) k_attn_bwd(Dims d, const SakeLayerParams p, const float* __restrict__ x,
+                                                  const float* __restrict__ e,
                                                   const float* __restrict__ att, float* __restrict__ gatt,
-                                                  float* __restrict__ ge) {
+                                                  float* __restrict__ ge, float* __restrict__ gcut) {
   extern __shared__ float sm[];
   const int N = d.N, A = d.A, H = d.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -584,6 +585,15 @@ __global__ void __launch_bounds__(256) k_attn_bwd(Dims d, const SakeLayerParams 
     for (int j = lane; j < N; j += 32) gs[j * A + a] = as[j * A + a] * (gs[j * A + a] - s);    // g_s
   }
   __syncwarp();
+  if (gcut != nullptr) {
+    // cosine cutoff: cotangent of eps = sum over heads of g_s / eps (att is proportional to eps); see k_attn_bwd_tc
+    const int mol0 = (row / N) * N;
+    for (int j = lane; j < N; j += 32) {
+      float t = 0.f;
+      for (int a = 0; a < A; ++a) t += gs[j * A + a];
+      gcut[base + j] = t * cosine_cutoff_dlog_(pair_dist_(x, row, mol0 + j), d.cut_lo, d.cut_hi);
+    }
+  }
   if (A == 4 && H == 64) {
     // lane owns f = 2*lane, 2*lane+1: q via a warp reduction of the per-lane partial dot products
     // (parameter pointers are only guaranteed 4-byte aligned: scalar loads)
@@ -660,7 +670,8 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
                                                   const float* __restrict__ proj, const float* __restrict__ e,
                                                   const float* __restrict__ ge, const float* __restrict__ gq,
                                                   const float* __restrict__ gdir, float* __restrict__ gproj,
-                                                  float* __restrict__ dx, SakeLayerGrads g, int want_grads) {
+                                                  float* __restrict__ dx, SakeLayerGrads g, int want_grads,
+                                                  const float* __restrict__ gcut) {
   extern __shared__ float sm[];
   EdgeBwdSmem s = edge_bwd_carve(sm, d);
   const int H = d.H, K = d.K, A = d.A, N = d.N;
@@ -802,6 +813,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
         for (int k = 0; k < K; ++k) gt += s.gg[pj * K + k];
         float gn = -s.ts[pj] * gt;
         for (int f = 0; f < H; ++f) gn = fmaf(w1n[f], s.gz1[pj * H + f], gn);
+        if (gcut) gn += gcut[(size_t)row * N + j];               // euclidean attention eps(n) (layers.py:172-176)
         const float n = s.ns[pj];
         const float r0 = s.rs[pj * 3 + 0], r1 = s.rs[pj * 3 + 1], r2 = s.rs[pj * 3 + 2];
         const float* gd = gdir + ((size_t)row * N + j) * 3;
@@ -1064,13 +1076,13 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   return 0;
 }
 
-int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
+int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
   int rc;
   int nw = 8;
   while (nw > 1 && sizeof(float) * 2 * d.N * d.A * nw > 160 * 1024) nw >>= 1;
   size_t smem = sizeof(float) * 2 * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_bwd, smem))) return rc;
-  k_attn_bwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, p, sv.e, sv.att, sc.gatt, sc.ge);
+  k_attn_bwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, p, x, sv.e, sv.att, sc.gatt, sc.ge, d.cutoff ? sc.gcut : nullptr);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1084,7 +1096,7 @@ int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
   if ((rc = ensure_smem(k_edge_bwd, smem))) return rc;
   int grid = d.R < 148 * 2 ? d.R : 148 * 2;
   k_edge_bwd<<<grid, 256, smem, st>>>(d, x, p, sv.nodeproj, sv.e, sc.ge, sc.gatt, sc.gdir, sc.gproj, dx,
-                                      g ? *g : null_grads(), g != nullptr);
+                                      g ? *g : null_grads(), g != nullptr, d.cutoff ? sc.gcut : nullptr);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
 // attn_fwd: softmax over senders j, mask, renormalise (layers.py:167,172-180) + aggregate
 // (layers.py:135-140).  One warp per receiving atom, several rows per CTA; att is normalised in place.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restrict__ mask,
+__global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restrict__ x, const float* __restrict__ mask,
                                                   const float* __restrict__ e, const float* lg, float* att,
                                                   float* __restrict__ he) {
   extern __shared__ float sm[];
@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
     float csum = 0.f;
     for (int j = lane; j < N; j += 32) {
       float c = as[j * A + a] * inv;          // semantic attention (softmax)
-      if (mrow) c *= mrow[j];                 // combined = euclidean(1.0) * semantic * mask
+      if (d.cutoff) c *= cosine_cutoff_(pair_dist_(x, row, ri.mol0 + j), d.cut_lo, d.cut_hi);   // euclidean attention
+      if (mrow) c *= mrow[j];                 // combined = euclidean * semantic * mask
       as[j * A + a] = c;
       csum += c;
     }
@@ -451,13 +452,13 @@ int gen_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 }
 
 // softmax over senders + aggregate: normalises sv.att in place, fills sv.he
-int gen_attn_fwd(const Dims& d, const float* mask, const Saved& sv, cudaStream_t st) {
+int gen_attn_fwd(const Dims& d, const float* x, const float* mask, const Saved& sv, cudaStream_t st) {
   int rc;
   int nw = 8;
   while (nw > 1 && sizeof(float) * d.N * d.A * nw > 160 * 1024) nw >>= 1;
   size_t smem = sizeof(float) * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
-  k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, mask, sv.e, sv.logit, sv.att, sv.he);
+  k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, x, mask, sv.e, sv.logit, sv.att, sv.he);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -109,6 +109,7 @@ struct EdgeArgs {
   float* ge;                           // backward input   [P,64] cotangent of e through x_mixing / aggregate; the
                                        // attention-logit term W_s g_q is added here (written back when training)
   const float *gdir, *gq;              // backward inputs  [P,3], [P,4] (cotangent of the pre-celu logits)
+  const float* gcut;                   // backward input   [P] cotangent of the distance through the cutoff, or NULL
   float *PB, *a1buf, *gbuf;            // backward outputs [P,192], [P,64], [P,64] (a1buf/gbuf: training only)
   int train;
 };
@@ -488,6 +489,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       }
       if (valid) {
         gn = fmaf(-tt, gt, gn);                                  // t = exp(-n)
+        if (a.gcut) gn += a.gcut[prx];                           // euclidean attention eps(n) (layers.py:172-176)
         const float* gd = a.gdir + prx * 3;
         const float inv = 1.0f / (nrm + 1e-5f);
         float g0 = gd[0] * inv, g1 = gd[1] * inv, g2 = gd[2] * inv;
@@ -511,8 +513,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 // is the identity on the gradient), g_q = g_s * celu_2'(q) with celu_2'(q) = 1 (q > 0) or e^{q/2} =
 // celu_2(q)/2 + 1 read off the saved logits (the -1e5 offsets of self / masked pairs meet att = 0).
 // Lane l owns the elements t = l, l+32, ... of the [N,4] row, i.e. always head a = l & 3.
-__global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __restrict__ att,
-                                                     const float* __restrict__ logit, float* __restrict__ gatt) {
+__global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __restrict__ x, const float* __restrict__ att,
+                                                     const float* __restrict__ logit, float* __restrict__ gatt,
+                                                     float* __restrict__ gcut) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= dims_rows(d)) return;
@@ -531,6 +534,23 @@ __global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __rest
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   s += __shfl_xor_sync(0xffffffffu, s, 8);
   s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (gcut != nullptr) {
+    // cosine cutoff (layers.py:172-180): att = eps sigma m / sum_k(eps sigma m).  The cotangent of the softmax
+    // logits is still g_s = att (g_att - s); the one of eps is g_s / eps per head (att is proportional to eps),
+    // summed over the heads that share the pair's eps, times d eps / d d.  eps = 0 exactly: att = 0 and the
+    // term is dropped (a set of measure zero: d = lower + k (upper - lower)).
+    for (int t0 = 0; t0 < n4; t0 += 32) {                 // warp-uniform trip count: the shuffles need every lane
+      const int t = t0 + lane;
+      const bool on = t < n4;
+      float gs = on ? att[base + t] * (gatt[base + t] - s) : 0.f;
+      gs += __shfl_xor_sync(0xffffffffu, gs, 1);          // heads of one pair sit in 4 adjacent lanes (n4 % 4 == 0)
+      gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+      if (on && (t & 3) == 0) {
+        const int j = t >> 2;
+        gcut[(size_t)ri.pair0 + j] = gs * cosine_cutoff_dlog_(pair_dist_(x, row, ri.mol0 + j), d.cut_lo, d.cut_hi);
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < MAXI; ++i) {
     const int t = i * 32 + lane;
@@ -546,8 +566,8 @@ __global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __rest
   }
 }
 
-int tc_attn_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
-  k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d, sv.att, sv.logit, sc.gatt);
+int tc_attn_bwd(const Dims& d, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
+  k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d, x, sv.att, sv.logit, sc.gatt, d.cutoff ? sc.gcut : nullptr);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -653,6 +673,7 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.g = make_geom(d);
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
+  a.gcut = d.cutoff ? sc.gcut : nullptr;
   a.ge = sc.ge; a.gdir = sc.gdir; a.gq = sc.gatt; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
   const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
   static unsigned long long optin = 0;

@@ -82,56 +82,56 @@ struct NodeFwdArgs {
   float* stash;                                          // [R, NS_LD] activations kept for the backward kernel (or NULL)
 };
 
-__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
-  const int nrows_real = a.hdr ? a.hdr->R : a.R;
-  if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = align1024_shared(smem_raw);
-  uint8_t* img = base;                                   // A chunk image {hi, lo}: 32 KB
-  uint8_t* wring = base + 2 * NT_IMG;                    // 2 weight chunk slots: 32 KB
-  float* svec = reinterpret_cast<float*>(wring + 2 * NT_WCH);
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(svec + NT_VEC);   // [2]
-  uint64_t* mdone = wfull + 2;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(mdone + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
-  for (int t = tid; t < NT_VEC; t += NT_TILE) {
-    const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
-    svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
-  }
-  if (tid == 0) {
-    mbar_init(wfull, 1); mbar_init(wfull + 1, 1); mbar_init(mdone, 1);
+// ---- pipelined chunk-GEMM rounds ------------------------------------------------------------------------------
+// Both node kernels are chains of small GEMM rounds (one 32-wide K chunk: 12 MMAs), and at every size they are bound
+// by the LATENCY of a round, not by throughput (cfg2: 37 CTAs of 128 threads on 148 SMs).  Round 1 ran a round as
+// build image -> barrier -> MMA -> wait; here issue() does not wait: a round commits to a caller-chosen barrier and
+// the kernel waits only where a result or an image buffer is actually needed, so the image build and the global
+// loads of round c+1 run under the MMAs of round c (two image buffers, used alternately).  Weight chunks stream
+// through a four-slot ring two rounds ahead; a slot is re-filled once the MMAs that read it have completed
+// (tcgen05.commit on the slot's own barrier), which only the issuing thread waits for.
+// SLOTS = 4 (look-ahead 2: consecutive rounds' MMAs overlap; 130 KB of shared memory, one CTA per SM) is the
+// low-latency configuration for small batches; SLOTS = 2 (look-ahead 1; 99 KB) lets two CTAs share an SM and is
+// used when there are more than two tiles per SM, where throughput matters and the second CTA hides the latency.
+constexpr int NT_UBARS = 4;
+constexpr int NT_MAXSLOTS = 4;
+template <int SLOTS>
+struct NodePipe {
+  static constexpr int LA = SLOTS / 2;
+  uint8_t* wring;
+  uint64_t *wfull, *wfree, *ubar;
+  const uint8_t* wimg;
+  int wpos;                      // rounds issued so far
+  int c0, c1, c2;                // weight chunk of round wpos and wpos+1 (requested), wpos+2 (requested by the next issue); -1: none
+  uint32_t uph;                  // bit i: phase parity the next wait on user barrier i looks for
+
+  __device__ __forceinline__ void init_barriers() {      // one thread
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(wfull + i, 1); mbar_init(wfree + i, 1); }
+    for (int i = 0; i < NT_UBARS; ++i) mbar_init(ubar + i, 1);
     fence_barrier_init();
-    mbar_arrive_expect_tx(wfull, NT_WCH);
-    bulk_g2s(wring, a.wimg, NT_WCH, wfull);              // chunk 0
   }
-  if (warp == 0) tmem_alloc<128>(tptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tptr;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t img_u32 = smem_u32(img);
-  constexpr uint32_t idesc = umma_idesc(2, 128, 64);
-  const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
-              *s_vel2 = svec + 320, *s_wv = svec + 384;
-  uint32_t mph = 0;
-  int wpos = 0;                                          // weight chunks consumed so far (ring position)
-  // publish the A chunk and run its 12 MMAs against the current weight chunk.  Two-deep weight ring: the chunk
-  // of the NEXT run (`wnext`, -1: none) is requested at the start of this run — its slot held the chunk of the
-  // previous run, whose MMAs have completed — so a weight chunk always has a full round of lead time.
-  auto run_chunk = [&](uint32_t dcol, bool first, int wnext) {
+  __device__ __forceinline__ void request(int chunk, int slot) {   // one thread
+    mbar_arrive_expect_tx(wfull + slot, NT_WCH);
+    bulk_g2s(wring + slot * NT_WCH, wimg + (size_t)chunk * NT_WCH, NT_WCH, wfull + slot);
+  }
+  // publish the image (all threads), then one thread runs its 12 MMAs against the round's weight chunk.
+  // ub >= 0: the MMAs issued so far arrive on user barrier ub when complete (at most one un-waited commit per barrier).
+  template <class Next>
+  __device__ __forceinline__ void issue(uint32_t img_u32, uint32_t dcol, bool first, int ub, Next next) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      const int slot = wpos & 1;
-      if (wnext >= 0) {
-        mbar_arrive_expect_tx(wfull + (slot ^ 1), NT_WCH);
-        bulk_g2s(wring + (slot ^ 1) * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + (slot ^ 1));
+    if (threadIdx.x == 0) {
+      const int slot = wpos & (SLOTS - 1);
+      const int creq = LA == 2 ? c2 : c1;                // chunk of round wpos + LA
+      if (creq >= 0) {
+        const int s2 = (wpos + LA) & (SLOTS - 1);        // last read by round wpos + LA - SLOTS
+        if (wpos + LA >= SLOTS) mbar_wait(wfree + s2, ((wpos + LA - SLOTS) / SLOTS) & 1);
+        request(creq, s2);
       }
-      mbar_wait(wfull + slot, (wpos >> 1) & 1);
+      mbar_wait(wfull + slot, (wpos / SLOTS) & 1);
       tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc(2, 128, 64);
       const uint32_t wb = smem_u32(wring + slot * NT_WCH);
       const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
 #pragma unroll
@@ -140,13 +140,57 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
         for (int ks = 0; ks < 4; ++ks)
           umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
                      umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
-      umma_commit(mdone);
+      umma_commit(wfree + slot);
+      if (ub >= 0) umma_commit(ubar + ub);
     }
-    mbar_wait_warp(mdone, mph);
-    mph ^= 1;
-    tc_fence_after();
     ++wpos;
-  };
+    c0 = c1; c1 = c2; c2 = c2 >= 0 ? next(c2) : -1;
+  }
+  __device__ __forceinline__ void wait(int ub) {
+    mbar_wait_warp(ubar + ub, (uph >> ub) & 1u);
+    uph ^= 1u << ub;
+    tc_fence_after();
+  }
+};
+
+template <int SLOTS>
+__global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(NodeFwdArgs a) {
+  const int nrows_real = a.hdr ? a.hdr->R : a.R;
+  if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024_shared(smem_raw);
+  uint8_t* imgs = base;                                  // two A chunk images {hi, lo}: 2 x 32 KB
+  uint8_t* wring = base + 4 * NT_IMG;                    // SLOTS weight chunk slots of 16 KB
+  float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
+  const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
+  for (int t = tid; t < NT_VEC; t += NT_TILE) {
+    const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
+    svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
+  }
+  const int n_chunks = uv ? NTW_CHUNKS : NTW_VEL0;       // the forward consumes chunks 0 .. n_chunks-1 in order
+  auto next_w = [&](int k) { return k + 1 < n_chunks ? k + 1 : -1; };
+  NodePipe<SLOTS> pp;
+  pp.wring = wring; pp.wfull = bars; pp.wfree = bars + NT_MAXSLOTS; pp.ubar = bars + 2 * NT_MAXSLOTS; pp.wimg = a.wimg;
+  pp.wpos = 0; pp.c0 = 0; pp.c1 = 1; pp.c2 = 2; pp.uph = 0;
+  if (tid == 0) {
+    pp.init_barriers();
+    pp.request(0, 0);
+    if (SLOTS == 4) pp.request(1, 1);
+  }
+  if (warp == 0) tmem_alloc<128>(tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t img_u32[2] = {smem_u32(imgs), smem_u32(imgs + 2 * NT_IMG)};
+  uint8_t* const img_p[2] = {imgs, imgs + 2 * NT_IMG};
+  const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
+              *s_vel2 = svec + 320, *s_wv = svec + 384;
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < nrows_real;
@@ -161,22 +205,34 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
     den2 = ms + 1e-10f;    // layers.py:221
   }
   const float inv_den = 1.0f / den;
-  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0;
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
-  int wc = 0;                                            // weight chunk of the next run_chunk
   float* ns = (a.stash && valid) ? a.stash + row * NS_LD : nullptr;   // this atom's row of the fwd -> bwd stash
+  // Image buffer k = round parity; user barrier k tracks the last round that read image k.
+  // busy: bit k set while a round on image k is un-waited.
+  uint32_t busy = 0;
+  auto acquire = [&](int k) { if (busy & (1u << k)) { pp.wait(k); busy &= ~(1u << k); } };
+  auto launch = [&](int k, uint32_t dcol, bool first) { pp.issue(img_u32[k], dcol, first, k, next_w); busy |= 1u << k; };
+  auto drain = [&]() { acquire(0); acquire(1); };       // every MMA issued so far is complete (results readable)
 
-  // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256
+  // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256 -> D0
+  // the 24 row loads of chunk c+1 are issued before the hand-off of chunk c: their latency hides under its MMAs
   float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+  float4 sreg[24];
+  {
+    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256) * 3);
+#pragma unroll
+    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+  }
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {
-    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
+    const int k = c & 1;
+    acquire(k);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       float s[12];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const float4 t4 = __ldg(sp + u * 3 + q);
+        const float4 t4 = sreg[u * 3 + q];
         s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
       }
       float vals[4];
@@ -187,11 +243,22 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
         const float w = s_wv[c * 32 + u * 4 + i];
         dv0 = fmaf(w, s[3 * i], dv0); dv1 = fmaf(w, s[3 * i + 1], dv1); dv2 = fmaf(w, s[3 * i + 2], dv2);
       }
-      nt_store_unit(img, tid, u, vals);
+      nt_store_unit(img_p[k], tid, u, vals);
     }
-    ++wc;
-    run_chunk(D0, c == 0, wc);
+    if (c + 1 < 8) {
+      const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + (c + 1) * 32) * 3);
+#pragma unroll
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+    }
+    launch(k, D0, c == 0);
   }
+  // node0's first inputs (h, he: 10 chunks of 8 float4) start loading now
+  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
+  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
+  float4 creg[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) creg[u] = __ldg(hp + u);
+  drain();
   // ---------------- post2: h_p1 = silu(tp1 + b)  -> D1
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
@@ -207,23 +274,26 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
         *reinterpret_cast<float4*>(ns + NS_D + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
         *reinterpret_cast<float4*>(ns + NS_HP1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      nt_store_unit(img, tid, u, vals);
+      nt_store_unit(img_p[c], tid, u, vals);
     }
-    ++wc;
-    run_chunk(D1, c == 0, wc);
+    launch(c, D1, c == 0);
   }
-  // ---------------- node0 over [h | h_e | h_comb] (layers.py:142-151) -> D0
-  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
-  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
+  // ---------------- node0 over [h | h_e | h_comb] (layers.py:142-151) -> D0 (free: post2 only read it through registers)
 #pragma unroll 1
   for (int c = 0; c < 12; ++c) {
+    const int k = c & 1;
+    if (c == 10) drain();                                // h_comb needs the post2 result in D1
+    acquire(k);
     if (c < 10) {
-      const float4* src = c < 2 ? hp + c * 8 : hep + (c - 2) * 8;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 t4 = __ldg(src + u);
-        const float vals[4] = {t4.x, t4.y, t4.z, t4.w};
-        nt_store_unit(img, tid, u, vals);
+        const float vals[4] = {creg[u].x, creg[u].y, creg[u].z, creg[u].w};
+        nt_store_unit(img_p[k], tid, u, vals);
+      }
+      if (c + 1 < 10) {
+        const float4* src = c + 1 < 2 ? hp + (c + 1) * 8 : hep + (c + 1 - 2) * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) creg[u] = __ldg(src + u);
       }
     } else {
       float v[32];
@@ -242,12 +312,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
           *reinterpret_cast<float4*>(ns + NS_D + 64 + (c - 10) * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
           *reinterpret_cast<float4*>(ns + NS_HCOMB + (c - 10) * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         }
-        nt_store_unit(img, tid, u, vals);
+        nt_store_unit(img_p[k], tid, u, vals);
       }
     }
-    ++wc;
-    run_chunk(D0, c == 0, wc);
+    // D0 was last written by post0 and read (into registers) by post2: both long complete
+    launch(k, D0, c == 0);
   }
+  drain();
   // ---------------- node2: n1 = silu(t1 + b) -> D1
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
@@ -263,11 +334,11 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
         *reinterpret_cast<float4*>(ns + NS_D + 128 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
         *reinterpret_cast<float4*>(ns + NS_N1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      nt_store_unit(img, tid, u, vals);
+      nt_store_unit(img_p[c], tid, u, vals);
     }
-    ++wc;
-    run_chunk(D1, c == 0, (upd && hv) ? wc : (c == 0 ? wc : -1));
+    launch(c, D1, c == 0);
   }
+  drain();
   // ---------------- h' = h + silu(t2 + b)  (layers.py:150); velocity gate MLP on h' (layers.py:184-186) -> D0
   float y = 0.f;
 #pragma unroll 1
@@ -287,14 +358,12 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post(NodeFwdArgs a) {
         *reinterpret_cast<float4*>(ns + NS_HOUT + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
       if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-      if (upd && hv) nt_store_unit(img, tid, u, vals);
+      if (uv) nt_store_unit(img_p[c], tid, u, vals);
     }
-    if (upd && hv) {
-      ++wc;
-      run_chunk(D0, c == 0, c == 0 ? wc : -1);
-    }
+    if (uv) launch(c, D0, c == 0);
   }
-  if (upd && hv) {
+  if (uv) {
+    drain();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -368,30 +437,41 @@ __device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     
     *reinterpret_cast<float4*>(dst + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
 }
 
-__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+template <int SLOTS>
+__global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bwd(NodeBwdArgs a) {
   const int nrows_real = a.hdr ? a.hdr->R : a.R;
   if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024_shared(smem_raw);
-  uint8_t* imgA = base;                                  // A image, K chunk 0 (or the serial chunk buffer): 32 KB
+  uint8_t* imgA = base;                                  // A image, K chunk 0: 32 KB
   uint8_t* imgB = base + 2 * NT_IMG;                     // A image, K chunk 1: 32 KB
-  uint8_t* wring = imgB + 2 * NT_IMG;                    // 2 weight chunk slots: 32 KB
-  float* svec = reinterpret_cast<float*>(wring + 2 * NT_WCH);
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(svec + NT_VEC);   // [2]
-  uint64_t* mdone = wfull + 2;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(mdone + 1);
+  uint8_t* wring = imgB + 2 * NT_IMG;                    // SLOTS weight chunk slots of 16 KB
+  float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS);
   const int tid = threadIdx.x, warp = tid >> 5;
   const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
   for (int t = tid; t < NT_VEC; t += NT_TILE) {
     const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
     svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
   }
+  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
+  // order in which the weight chunks are consumed (the image holds them in this order, with optional parts):
+  // vel0^T (with a velocity gate), node2^T, node0^T, then post2^T and post0^T (with spatial attention)
+  auto next_w = [&](int k) {
+    int nx = k + 1;
+    if (nx == NTB_POST2T && !spatial) nx = -1;
+    if (nx >= NTB_CHUNKS) nx = -1;
+    return nx;
+  };
+  NodePipe<SLOTS> pp;
+  pp.wring = wring; pp.wfull = bars; pp.wfree = bars + NT_MAXSLOTS; pp.ubar = bars + 2 * NT_MAXSLOTS; pp.wimg = a.wimg;
+  pp.wpos = 0; pp.uph = 0;
+  pp.c0 = uv ? NTB_VEL0T : NTB_NODE2T; pp.c1 = next_w(pp.c0); pp.c2 = next_w(pp.c1);
   if (tid == 0) {
-    mbar_init(wfull, 1); mbar_init(wfull + 1, 1); mbar_init(mdone, 1);
-    fence_barrier_init();
-    mbar_arrive_expect_tx(wfull, NT_WCH);
-    // first chunk the backward chain consumes: vel0^T with a velocity gate, node2^T otherwise
-    bulk_g2s(wring, a.wimg + (size_t)((a.update && a.has_v) ? NTB_VEL0T : NTB_NODE2T) * NT_WCH, NT_WCH, wfull);
+    pp.init_barriers();
+    pp.request(pp.c0, 0);
+    if (SLOTS == 4) pp.request(pp.c1, 1);
   }
   if (warp == 0) tmem_alloc<128>(tptr);
   tc_fence_before();
@@ -400,50 +480,14 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   const uint32_t tmem_base = *tptr;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t imgA_u32 = smem_u32(imgA), imgB_u32 = smem_u32(imgB);
-  constexpr uint32_t idesc = umma_idesc(2, 128, 64);
   const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
               *s_vel2 = svec + 320, *s_wv = svec + 384;
-  const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
-  // order in which the weight chunks are consumed (the image holds them in this order, with optional parts)
-  auto next_w = [&](int k) {
-    int nx = k + 1;
-    if (nx == NTW_VEL0 && !uv) nx = NTB_NODE2T;          // no velocity gate: skip vel0 and vel0^T
-    if (nx == NTB_POST2T && !spatial) nx = -1;
-    if (nx >= NTB_CHUNKS) nx = -1;
-    return nx;
+  (void)s_bp1; (void)s_bp2; (void)s_bn1; (void)s_bn2; (void)s_bv1;
+  // One GEMM of the chain = the pair (imgA, imgB) = K 64 against two weight chunks; it commits to user barrier ub.
+  auto run_pair = [&](uint32_t dcol, int ub) {
+    pp.issue(imgA_u32, dcol, true, -1, next_w);
+    pp.issue(imgB_u32, dcol, false, ub, next_w);
   };
-  uint32_t mph = 0;
-  int wpos = 0, wc = uv ? NTB_VEL0T : NTB_NODE2T;        // ring position, current weight chunk
-  auto run_chunk = [&](uint32_t img_u32, uint32_t dcol, bool first) {
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    const int wnext = next_w(wc);
-    if (tid == 0) {
-      const int slot = wpos & 1;
-      if (wnext >= 0) {                                  // two-deep ring: request the NEXT run's chunk now (its slot
-        mbar_arrive_expect_tx(wfull + (slot ^ 1), NT_WCH);   // held the previous run's chunk, whose MMAs are complete)
-        bulk_g2s(wring + (slot ^ 1) * NT_WCH, a.wimg + (size_t)wnext * NT_WCH, NT_WCH, wfull + (slot ^ 1));
-      }
-      mbar_wait(wfull + slot, (wpos >> 1) & 1);
-      tc_fence_after();
-      const uint32_t wb = smem_u32(wring + slot * NT_WCH);
-      const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
-#pragma unroll
-      for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
-                     umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
-      umma_commit(mdone);
-    }
-    mbar_wait_warp(mdone, mph);
-    mph ^= 1;
-    tc_fence_after();
-    ++wpos;
-    wc = wnext;
-  };
-  // wc always names the chunk the next run_chunk will consume (the first one is requested in the prologue)
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < nrows_real;
@@ -461,8 +505,6 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   float* nb = a.nbuf ? a.nbuf + row * NB_LD : nullptr;
   const bool rec = nb != nullptr && valid;
-  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
-  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
 
   // =============================== forward activations: kept by k_tc_node_post ===============================
   // (round 1 recomputed the forward here: 26 of the kernel's 52 serial chunk-GEMM rounds, on a kernel that is
@@ -551,8 +593,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 #pragma unroll
       for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, gtv + 4 * u);
     }
-    run_chunk(imgA_u32, D0, true);
-    run_chunk(imgB_u32, D0, false);
+    run_pair(D0, 0);
+    pp.wait(0);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -576,8 +618,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
 #pragma unroll
     for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, g2 + 4 * u);
   }
-  run_chunk(imgA_u32, D1, true);
-  run_chunk(imgB_u32, D1, false);
+  run_pair(D1, 0);
+  pp.wait(0);
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
     float v[32];
@@ -594,11 +636,13 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
   }
   // g_cat = g_t1 W_n1^T : six 64-row blocks [dh | g_he (4 blocks) | g_hcomb]; the g_t1 image stays in place
   float gp2[64];                                         // g_tp2 = g_hcomb * silu'(tp2)
+  // block b+1 is issued before block b is read back: its MMAs run under the read-back (accumulators D0 / D1 and
+  // user barriers 0 / 1 alternate; the g_t1 images are read-only during the loop)
+  run_pair(D0, 0);
 #pragma unroll 1
   for (int b = 0; b < 6; ++b) {
-    const uint32_t D = (b & 1) ? D1 : D0;
-    run_chunk(imgA_u32, D, true);
-    run_chunk(imgB_u32, D, false);
+    if (b + 1 < 6) run_pair(((b + 1) & 1) ? D1 : D0, (b + 1) & 1);
+    pp.wait(b & 1);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -630,8 +674,8 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     if (rec) { st64(nb + NB_GTP2, 0, gp2); st64(nb + NB_GTP2, 1, gp2 + 32); }
 #pragma unroll
     for (int u = 0; u < 8; ++u) { nt_store_unit(imgA, tid, u, gp2 + 4 * u); nt_store_unit(imgB, tid, u, gp2 + 32 + 4 * u); }
-    run_chunk(imgA_u32, D0, true);
-    run_chunk(imgB_u32, D0, false);
+    run_pair(D0, 0);
+    pp.wait(0);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -648,24 +692,39 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_post_bwd(NodeBwdArgs a) 
     }
     // g_nrm = g_tp1 W_p1^T (four 64-row blocks);  T[c][d] = 2 ssum[c][d] g_nrm[c] / den^2 + Wv[c] g_dv[d] / den2
     const float k2 = 2.0f * inv_den * inv_den, q0 = gdv0 / den2, q1 = gdv1 / den2, q2 = gdv2 / den2;
+    // same look-ahead over the four blocks; the 24 row loads of ssum for the next 32 coefficients are issued
+    // before the current ones are consumed, so they are in flight during the barrier wait and the TMEM load
+    float4 sreg[24];
+    {
+      const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256) * 3);
+#pragma unroll
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+    }
+    run_pair(D0, 0);
 #pragma unroll 1
     for (int b = 0; b < 4; ++b) {
-      const uint32_t D = (b & 1) ? D1 : D0;
-      run_chunk(imgA_u32, D, true);
-      run_chunk(imgB_u32, D, false);
+      if (b + 1 < 4) run_pair(((b + 1) & 1) ? D1 : D0, (b + 1) & 1);
+      pp.wait(b & 1);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(lane_addr + (b & 1) * 64 + c * 32, v);
         tmem_ld_wait();
         const int c0 = b * 64 + c * 32;
-        const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0) * 3);
+        float4 scur[24];
+#pragma unroll
+        for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
+        if (c0 + 32 < 256) {
+          const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0 + 32) * 3);
+#pragma unroll
+          for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           float s[12];
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            const float4 t4 = __ldg(sp + u * 3 + q);
+            const float4 t4 = scur[u * 3 + q];
             s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
           }
 #pragma unroll
@@ -703,6 +762,17 @@ __global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, co
   atomicAdd(gWv + c, acc);
 }
 
+static int node_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
 size_t tc_node_bwd_scratch_bytes(const Dims& d) {
   return align_up(sizeof(float) * (size_t)d.R * 4);
 }
@@ -725,12 +795,15 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   const bool wvg = g != nullptr && d.update && d.spatial;
   a.qv = wvg ? (float*)nscratch : nullptr;
   a.nbuf = g ? sc.nbuf : nullptr;
-  const size_t smem = 4 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
-  static unsigned long long optin = 0;
-  { const int rc = smem_optin(k_tc_node_post_bwd, smem, optin); if (rc) return rc; }
+  const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
+  const bool deep = tiles <= 2 * node_num_sms();        // few tiles: latency configuration (see NodePipe)
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 128 + 1024;
+  static unsigned long long optin4 = 0, optin2 = 0;
+  { const int rc = deep ? smem_optin(k_tc_node_post_bwd<4>, smem, optin4) : smem_optin(k_tc_node_post_bwd<2>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(7, d.R, st);
-    k_tc_node_post_bwd<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+    if (deep) k_tc_node_post_bwd<4><<<tiles, NT_TILE, smem, st>>>(a);
+    else k_tc_node_post_bwd<2><<<tiles, NT_TILE, smem, st>>>(a);
   }
   if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 2 : 1);
@@ -754,12 +827,15 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.b_p1 = p.post0_bias; a.b_p2 = p.post2_bias; a.b_n1 = p.node0_bias; a.b_n2 = p.node2_bias;
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
   a.h_out = h_out; a.x_out = x_out; a.v_out = v_out; a.stash = sv.nstash;
-  const size_t smem = 2 * NT_IMG + 2 * NT_WCH + NT_VEC * sizeof(float) + 64 + 1024;
-  static unsigned long long optin = 0;
-  { const int rc = smem_optin(k_tc_node_post, smem, optin); if (rc) return rc; }
+  const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
+  const bool deep = tiles <= 2 * node_num_sms();
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 128 + 1024;
+  static unsigned long long optin4 = 0, optin2 = 0;
+  { const int rc = deep ? smem_optin(k_tc_node_post<4>, smem, optin4) : smem_optin(k_tc_node_post<2>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(6, d.R, st);
-    k_tc_node_post<<<(d.R + NT_TILE - 1) / NT_TILE, NT_TILE, smem, st>>>(a);
+    if (deep) k_tc_node_post<4><<<tiles, NT_TILE, smem, st>>>(a);
+    else k_tc_node_post<2><<<tiles, NT_TILE, smem, st>>>(a);
   }
   note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());

@@ -15,12 +15,14 @@
 
 namespace ffi = xla::ffi;
 
-static SakeDims make_dims(const ffi::AnyBuffer& h, int32_t heads, int32_t n_rbf, int32_t flags) {
+static SakeDims make_dims(const ffi::AnyBuffer& h, int32_t heads, int32_t n_rbf, int32_t flags, float cut_lo = 0.f,
+                          float cut_hi = 5.f) {
   auto dims = h.dimensions();            // [B, N, H] (leading dims flattened on the Python side)
   SakeDims d;
   std::memset(&d, 0, sizeof(d));
   d.B = (int32_t)dims[0]; d.N = (int32_t)dims[1]; d.H = (int32_t)dims[2];
   d.A = heads; d.K = n_rbf; d.flags = flags; d.engine = SAKE_ENGINE_AUTO;
+  d.cutoff_lower = cut_lo; d.cutoff_upper = cut_hi;      // read only with SAKE_COSINE_CUTOFF in flags
   return d;
 }
 static const float* opt(const ffi::AnyBuffer& b) { return b.element_count() ? (const float*)b.untyped_data() : nullptr; }

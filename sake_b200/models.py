@@ -46,8 +46,8 @@ class DenseSAKEModel:
         return {"params": tree_to(p, h.device)}
 
     def apply(self, variables, h, x, v=None, mask=None, he=None, method=None):
-        if method is not None:
-            raise ops._lib.SakeError("sub-method application is not exposed")
+        if method is not None and (method if isinstance(method, str) else method.__name__) != "__call__":
+            raise ops._lib.SakeError("DenseSAKEModel has no sub-methods (sake/models.py:11-61 defines __call__ only)")
         return self(variables["params"], h, x, v, mask, he)
 
     def __call__(self, params, h, x, v=None, mask=None, he=None):

@@ -64,11 +64,14 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-def make_dims(B, N, H, A, K, update, has_v, has_mask, spatial=True, engine="auto"):
+def make_dims(B, N, H, A, K, update, has_v, has_mask, spatial=True, engine="auto", cutoff=None):
+    """cutoff: None or (lower, upper) of sake.utils.cosine_cutoff (sake/utils.py:10-26)."""
     flags = ((_lib.SAKE_UPDATE if update else 0) | (_lib.SAKE_HAS_V if has_v else 0) |
-             (_lib.SAKE_HAS_MASK if has_mask else 0) | (0 if spatial else _lib.SAKE_NO_SPATIAL))
+             (_lib.SAKE_HAS_MASK if has_mask else 0) | (0 if spatial else _lib.SAKE_NO_SPATIAL) |
+             (_lib.SAKE_COSINE_CUTOFF if cutoff is not None else 0))
     eng = _lib.ENGINES[engine] if isinstance(engine, str) else int(engine)
-    return _lib.SakeDims(int(B), int(N), int(H), int(A), int(K), flags, eng, 0)
+    lo, hi = (0.0, 5.0) if cutoff is None else (float(cutoff[0]), float(cutoff[1]))
+    return _lib.SakeDims(int(B), int(N), int(H), int(A), int(K), flags, eng, 0, lo, hi)
 
 
 def resolve_engine(dims):
@@ -198,7 +201,7 @@ class _LayerFn(torch.autograd.Function):
         for s in lead:
             B *= s
         dims = make_dims(B, N, H, cfg["A"], cfg["K"], cfg["update"], v is not None, mask is not None,
-                         cfg["spatial"], cfg["engine"])
+                         cfg["spatial"], cfg["engine"], cfg.get("cutoff"))
         ps, keep = params_struct(flat)
         dev = h.device
         saved = _buf(saved_bytes(dims), dev)
@@ -243,7 +246,7 @@ class _LayerFn(torch.autograd.Function):
 
 
 def sake_layer(flat_params, h, x, v=None, mask=None, *, n_heads=4, update=True, use_spatial_attention=True,
-               engine="auto"):
+               engine="auto", cutoff=None):
     """flat_params: {flax path -> tensor} of one DenseSAKELayer.  Returns (h, x, v) like
     sake/layers.py:188-235 (v is None when the reference would return None)."""
     paths = tuple(p for p, _ in LAYER_LEAVES if p in flat_params)
@@ -254,7 +257,7 @@ def sake_layer(flat_params, h, x, v=None, mask=None, *, n_heads=4, update=True, 
         raise _lib.SakeError("parameter tree lacks leaves this call needs: " + ", ".join(missing))
     K = flat_params["edge_model/kernel/means"].shape[0]
     cfg = {"paths": paths, "A": int(n_heads), "K": int(K), "update": bool(update),
-           "spatial": bool(use_spatial_attention), "engine": engine}
+           "spatial": bool(use_spatial_attention), "engine": engine, "cutoff": cutoff}
     h_out, x_out, v_out = _LayerFn.apply(cfg, h, x, v, mask, *[flat_params[p] for p in paths])
     if not (update or v is not None):
         v_out = None

@@ -58,7 +58,7 @@ class ParamSet:
 
 class ModelRunner:
     def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
-                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=True):
+                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=False):
         """masked: QM9-style padded batch with the reference's float mask = outer(m, m) (every kernel computes
         all N^2 pairs of the padded width and multiplies by the mask, like the reference).
         ragged: the same padded batch, but only the n_real[b] real atoms of every molecule are stored and
@@ -88,7 +88,7 @@ class ModelRunner:
         for l in range(self.L):
             upd = model.update_list[l]
             d = ops.make_dims(B, N, self.H, self.A, K, upd, has_v, masked, model.use_spatial_attention,
-                              model.engine)
+                              model.engine, model.layers[l]._cutoff)
             self.dims.append(d)
             self.has_v.append(has_v)
             has_v = has_v or upd
@@ -114,14 +114,16 @@ class ModelRunner:
         self.saved = [ops._buf(ops.saved_bytes(d), dev) for d in self.dims]
         nscr = max(max(ops.scratch_bytes(d, 0, 0), ops.scratch_bytes(d, 1, int(train))) for d in self.dims)
         self.scratch = ops._buf(nscr, dev)
-        # training on a tcgen05 engine: the weight-gradient contractions of layer l run on the library's side stream
-        # under the backward of layer l-1 (SAKE_DEFER_DW), which needs a second scratch buffer to alternate with
+        # defer_dw (opt-in): the weight-gradient contractions of layer l run on the library's side stream under the
+        # backward of layer l-1 (SAKE_DEFER_DW), which needs a second scratch buffer to alternate with.  Measured on
+        # B200 (profiles/r02_*): no gain — every big kernel of the backward wants whole SMs (200+ KB of shared memory,
+        # 512 TMEM columns), so the two streams take turns on each SM instead of overlapping (cfg2 3.58 -> 3.83 ms).
         self.defer_dw = bool(defer_dw and train and self.engine != "fp32" and self.L > 1)
         self.scratches = [self.scratch, ops._buf(nscr, dev)] if self.defer_dw else [self.scratch, self.scratch]
         self.dims_bwd = []
         for l, d in enumerate(self.dims):
             db = _lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags | (_lib.SAKE_DEFER_DW if self.defer_dw else 0),
-                               d.engine, l & 1)
+                               d.engine, l & 1, d.cutoff_lower, d.cutoff_upper)
             self.dims_bwd.append(db)
         self.y0 = torch.empty(B, N, self.H, device=dev, dtype=f32)
         self.y = torch.empty(B, N, self.out, device=dev, dtype=f32)

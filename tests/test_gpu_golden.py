@@ -37,7 +37,12 @@ def test_layer_golden(name, engine):
     H = int(g["meta"]["H"])
     n_real = int(g["meta"]["n_real"])
     update = bool(int(g["meta"]["update"]))
-    layer = sake_b200.DenseSAKELayer(H, H, update=update, engine=engine)
+    cutoff = None
+    if "cutoff" in g["meta"]:                      # sake/layers.py:172-176 with sake.utils.cosine_cutoff
+        import functools
+        lo, hi = (float(c) for c in g["meta"]["cutoff"])
+        cutoff = functools.partial(sake_b200.utils.cosine_cutoff, lower=lo, upper=hi)
+    layer = sake_b200.DenseSAKELayer(H, H, update=update, engine=engine, cutoff=cutoff)
     p = _params(g)
     h = _dev(g["in"]["h"]).requires_grad_(True)
     x = _dev(g["in"]["x"]).requires_grad_(True)

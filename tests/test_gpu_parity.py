@@ -110,7 +110,7 @@ def test_equivariance():
 def test_error_paths():
     import sake_b200
     from sake_b200._lib import SakeError
-    with pytest.raises(SakeError):
+    with pytest.raises(SakeError):               # only the closed-form cosine cutoff runs inside the kernels
         sake_b200.DenseSAKELayer(16, 16, cutoff=lambda d: d)
     layer = sake_b200.DenseSAKELayer(16, 16)
     h = torch.zeros(3, 16)

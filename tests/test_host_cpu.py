@@ -70,3 +70,45 @@ def test_functional_shapes():
     assert r.shape == (5, 5, 3)
     assert sake_b200.functional.get_x_minus_xt_norm(r).shape == (5, 5, 1)
     assert sake_b200.functional.get_h_cat_ht(x).shape == (5, 5, 6)
+
+
+def test_layer_sub_methods_match_oracle():
+    """model.apply(params, ..., method=model.<sub-method>) as the reference's mask tests call it
+    (sake/tests/test_mask.py:80,107,155,189): the host-side mirrors against the oracle's restatement, on CPU
+    tensors (they are plain torch; the fused kernels never call them)."""
+    from oracle import sake_oracle as O
+    import sake_b200
+    import sake_b200.functional as F
+    torch.manual_seed(0)
+    layer = sake_b200.DenseSAKELayer(16, 16)
+    h = torch.rand(5, 16, dtype=torch.float64)
+    x = torch.randn(5, 3, dtype=torch.float64)
+    p = layer.init(3, h.float(), x.float(), v=torch.zeros(5, 3))
+    p = {"params": O.tree_map(lambda t: t.double(), p["params"])}
+    po = p["params"]
+    r = F.get_x_minus_xt(x)
+    n = F.get_x_minus_xt_norm(r)
+    hc = F.get_h_cat_ht(h)
+    e = layer.apply(p, hc, n, method=layer.edge_model)
+    assert torch.allclose(e, O.edge_model(po["edge_model"], hc, n), rtol=1e-12, atol=1e-12)
+    m = torch.cat([torch.ones(4), torch.zeros(1)]).double()
+    mask = m[None, :] * m[:, None]
+    for mk in (None, mask):
+        sem = layer.apply(p, e, mask=mk, method=layer.semantic_attention)
+        assert torch.allclose(sem, O.semantic_attention(po, e, mask=mk), rtol=1e-12, atol=1e-12)
+        euc, sem2, comb = layer.apply(p, n, e, mask=mk, method="combined_attention")
+        assert euc == 1.0 and torch.equal(sem2, sem)
+        assert torch.allclose(comb, O.combined_attention(po, n, e, mask=mk), rtol=1e-12, atol=1e-12)
+        hea = (e.unsqueeze(-1) * comb.unsqueeze(-2)).reshape(*e.shape[:-1], -1)
+        hcomb, combs = layer.apply(p, hea, r, n, mask=mk, method=layer.spatial_attention)
+        h0, c0 = O.spatial_attention(po, hea, r, n, mask=mk)
+        assert torch.allclose(hcomb, h0, rtol=1e-12, atol=1e-12) and torch.allclose(combs, c0, rtol=1e-12, atol=1e-12)
+        he = layer.apply(p, hea, mask=mk, method=layer.aggregate)
+        assert he.shape == (5, 64)
+        hn = layer.apply(p, h, he, hcomb, method=layer.node_model)
+        assert hn.shape == (5, 16)
+    v = layer.apply(p, torch.ones(5, 3).double(), h, method=layer.velocity_model)
+    assert v.shape == (5, 3)
+    from sake_b200._lib import SakeError
+    with pytest.raises(SakeError):        # stale in the reference too: DenseSAKELayer has no euclidean_attention
+        layer.apply(p, n, method="euclidean_attention")

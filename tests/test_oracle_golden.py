@@ -38,9 +38,13 @@ def test_layer(name, prec):
     v = _t(g["in"].get("v"), dt)
     mask = _t(g["in"].get("mask"), dt)
     update = bool(int(g["meta"]["update"]))
+    cutoff = None
+    if "cutoff" in g["meta"]:                      # DenseSAKELayer(cutoff=partial(cosine_cutoff, lower=, upper=))
+        lo, hi = (float(c) for c in g["meta"]["cutoff"])
+        cutoff = lambda d: O.cosine_cutoff(d, lo, hi)
     # guarded=False == the reference as written; real rows are identical in both modes
     for guarded in (False, True):
-        ho, xo, vo = O.layer_forward(p, h, x, v, mask, update=update, guarded=guarded)
+        ho, xo, vo = O.layer_forward(p, h, x, v, mask, update=update, guarded=guarded, cutoff=cutoff)
         ho, xo = ho[..., :n_real, :], xo[..., :n_real, :]
         rt, at = TOL[prec]
         _close(ho.detach(), g["out"][prec + "/h"], rt, at, "h")
