@@ -489,11 +489,11 @@ def main():
     launches = int(lib.sake_launch_count() - launches0) + (getattr(job.run, "graph_replays", 0) - replays0) * job.graph_launches()
     ms_step = dev_ms / args.steps
     value = world * B / (ms_step * 1e-3)
-    # sustained: more rounds of the same K steps until ~2.5 s of timed work have run, so that the clocks are sampled
+    # sustained: more rounds of the same K steps until ~4 s of timed work have run, so that the clocks are sampled
     # >= 20 times under load and the number is not a 0.1 s burst
     sustained = None
-    if not args.no_sustained and dev_ms < 2500.0:
-        rounds = int(min(200, math.ceil((2500.0 - dev_ms) / max(dev_ms, 1e-3))))
+    if not args.no_sustained and dev_ms < 4000.0:
+        rounds = int(min(400, math.ceil((4000.0 - dev_ms) / max(dev_ms, 1e-3))))
         tot = 0.0
         for _ in range(rounds):
             r_ms, _ = timed_region(job, args.steps, flush, dist, dev)

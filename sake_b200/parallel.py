@@ -43,6 +43,22 @@ class GradAllReducer:
             dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
         return 1.0 / self.world
 
+    # Bucketed form: start(bucket) as soon as one layer's gradients are final — the collective runs on the
+    # backend's own stream (NCCL: ordered after the work already enqueued on the current stream) while the backward
+    # of the next layer keeps the SMs busy — and finish() before the optimiser.  Buckets are views of the one flat
+    # gradient vector, so the result is the same all-reduce, cut at layer boundaries.
+    def start(self, bucket: torch.Tensor) -> None:
+        if self.world > 1 and bucket.numel() > 0:
+            if not hasattr(self, "_works"):
+                self._works = []
+            self._works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> float:
+        for w in getattr(self, "_works", []):
+            w.wait()                       # CUDA backends: makes the current stream wait, no host block
+        self._works = []
+        return 1.0 / self.world
+
 
 def max_over_ranks(value: float, device) -> float:
     """Device-side timing is reported as the max over ranks."""

@@ -31,6 +31,7 @@ class ParamSet:
         self.n_params_real = sum(sizes)
         self.flat_params = torch.zeros(self.n_params, device=dev, dtype=f32)
         self.p = {}
+        self.span = {k: (off, off + (n + 3) // 4 * 4) for k, n, off in zip(self.paths, sizes, offs)}
         for k, n, off in zip(self.paths, sizes, offs):
             self.p[k] = self.flat_params[off:off + n].view(flat[k].shape)
             self.p[k].copy_(flat[k])
@@ -54,6 +55,14 @@ class ParamSet:
                 gs, keep = ops.params_struct(gsub, _lib.SakeLayerGrads)
                 self.gs.append(gs)
                 self._keep.append(keep)
+
+
+    def bucket(self, prefix):
+        """(begin, end) of the contiguous slice of the flat vectors that holds every leaf under `prefix`."""
+        sp = [v for k, v in self.span.items() if k.startswith(prefix)]
+        b, e = min(a for a, _ in sp), max(c for _, c in sp)
+        assert sum(c - a for a, c in sp) == e - b, "leaves under one prefix are contiguous in the flat vector"
+        return b, e
 
 
 class ModelRunner:
@@ -200,34 +209,47 @@ class ModelRunner:
                                    ops._ptr(self.dy), ops._ptr(self.rg), ops._stream()), "sake_energy_head")
 
     # -- backward ------------------------------------------------------------------------------------
-    def backward(self, with_grads):
+    # The backward pass in segments (readout, one per layer from the last to the first, embedding): a training step
+    # on several GPUs starts the all-reduce of a layer's gradient bucket right after that layer's segment.
+    # The cotangent buffers ping-pong: layer l reads slot (L-1-l) & 1 and writes the other one.
+    def _bwd_readout(self, with_grads):
         p, g = self.p, self.g
         gk = (lambda k: g[k]) if with_grads else (lambda k: None)
         ops.dense_bwd_raw(self.y0, p["embedding_out/layers_2/kernel"], p.get("embedding_out/layers_2/bias"),
                           self.dy, self.dy0, gk("embedding_out/layers_2/kernel"),
                           gk("embedding_out/layers_2/bias") if "embedding_out/layers_2/bias" in p else None, 0, self.rg)
-        cur = 0
         ops.dense_bwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
-                          p.get("embedding_out/layers_0/bias"), self.dy0, self.dh[cur],
+                          p.get("embedding_out/layers_0/bias"), self.dy0, self.dh[0],
                           gk("embedding_out/layers_0/kernel"), gk("embedding_out/layers_0/bias"), 1, self.rg)
-        dx_out = dv_out = None
-        for l in reversed(range(self.L)):
-            nxt = 1 - cur
-            v_in = self.vs[l] if self.has_v[l] else None
-            ops.layer_bwd_raw(self.dims_bwd[l] if with_grads else self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in,
-                              self.mask, self.saved[l], self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
-                              self.dv[nxt] if v_in is not None else None,
-                              self.gs[l] if with_grads else None, self.scratches[l & 1] if with_grads else self.scratch,
-                              self.rg)
-            dx_out = self.dx[nxt]
-            dv_out = self.dv[nxt] if v_in is not None else None
-            cur = nxt
+
+    def _bwd_layer(self, l, with_grads):
+        cur = (self.L - 1 - l) & 1
+        nxt = 1 - cur
+        last = l == self.L - 1
+        v_in = self.vs[l] if self.has_v[l] else None
+        dx_out = None if last else self.dx[cur]
+        dv_out = None if (last or not self.has_v[l + 1]) else self.dv[cur]
+        ops.layer_bwd_raw(self.dims_bwd[l] if with_grads else self.dims[l], self.ps[l], self.hs[l], self.xs[l], v_in,
+                          self.mask, self.saved[l], self.dh[cur], dx_out, dv_out, self.dh[nxt], self.dx[nxt],
+                          self.dv[nxt] if v_in is not None else None,
+                          self.gs[l] if with_grads else None, self.scratches[l & 1] if with_grads else self.scratch,
+                          self.rg)
+
+    def _bwd_embed(self, with_grads):
+        cur = self.L & 1                       # slot the first layer wrote
         if with_grads:
+            p, g = self.p, self.g
             ops.dense_bwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.dh[cur], None,
                               g["embedding_in/kernel"], g.get("embedding_in/bias"), 0, self.rg)
             if self.defer_dw:                  # join the side stream: gradients complete from here on
                 check(lib.sake_dw_sync(ops._stream()), "sake_dw_sync")
-        self._dx_final = dx_out
+        self._dx_final = self.dx[cur]
+
+    def backward(self, with_grads):
+        self._bwd_readout(with_grads)
+        for l in reversed(range(self.L)):
+            self._bwd_layer(l, with_grads)
+        self._bwd_embed(with_grads)
 
     # -- the two driver closures ---------------------------------------------------------------------
     def _ef_body(self):
@@ -247,6 +269,20 @@ class ModelRunner:
         self._head(1)
         self.backward(True)
 
+    # the same step cut at the points where a gradient bucket becomes final (multi-GPU training)
+    def _train_segments(self):
+        def head():
+            self.flat_grads.zero_()
+            self.loss.zero_()
+            self.forward()
+            self._head(1)
+            self._bwd_readout(True)
+        segs = [("embedding_out/", head)]
+        for l in reversed(range(self.L)):
+            segs.append(("d%d/" % l, (lambda l=l: self._bwd_layer(l, True))))
+        segs.append(("embedding_in/", lambda: self._bwd_embed(True)))
+        return segs
+
     def capture(self, train=None):
         """Record the enqueue-only part of a step (everything the library launches between the input copy and
         the optimiser / result read) into a CUDA graph; later steps of that kind replay it with one launch.
@@ -265,6 +301,15 @@ class ModelRunner:
             body()
         self.graph_launches = int(lib.sake_launch_count() - n0)
         self.graphs[train] = g
+        if train:
+            # the segmented form of the same step (one graph per gradient bucket), used when an all-reduce runs
+            # between the segments; all graphs share one memory pool and the runner's static buffers
+            self.seg_graphs = []
+            for prefix, fn in self._train_segments():
+                sg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(sg, pool=g.pool()):
+                    fn()
+                self.seg_graphs.append((prefix, sg))
         return self.graph_launches
 
     def _run_body(self, train):
@@ -285,10 +330,25 @@ class ModelRunner:
     def train_step(self, allreduce=None):
         """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
         optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
-        self._run_body(True)
         scale = 1.0
-        if allreduce is not None:
-            scale = allreduce(self.flat_grads)
+        if allreduce is not None and getattr(allreduce, "world", 1) > 1 and hasattr(allreduce, "start"):
+            # per-layer buckets (lax.pmean over the same leaves, scripts/ani/run_gpu.py:130): the all-reduce of layer
+            # l's gradients runs on the NCCL stream under the backward of layer l-1
+            segs = getattr(self, "seg_graphs", None)
+            for prefix, fn in (segs if segs else self._train_segments()):
+                if segs:
+                    fn.replay()
+                else:
+                    fn()
+                b, e = self.pset.bucket(prefix)
+                allreduce.start(self.flat_grads[b:e])
+            if segs:
+                self.graph_replays += 1
+            scale = allreduce.finish()
+        else:
+            self._run_body(True)
+            if allreduce is not None:
+                scale = allreduce(self.flat_grads)
         self.step_count += 1
         check(lib.sake_adam_step(self.n_params, ops._ptr(self.flat_params), ops._ptr(self.flat_grads),
                                  ops._ptr(self.adam_m), ops._ptr(self.adam_v), self.step_count, self.lr, 0.9,

@@ -7,11 +7,11 @@ import bench
 import sake_b200
 from sake_b200 import runner as R, _lib
 B, N, S, padded, n_min, mode, desc = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"]
-model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=4, engine=(sys.argv[2] if len(sys.argv) > 2 else "tf32x3"))
-run = R.ModelRunner(model, bench.init_params_cpu(4, S, 0), B, N, S, masked=padded, train=False)
+model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=4, engine=(sys.argv[2] if len(sys.argv) > 2 else "f16x2"))
+run = R.ModelRunner(model, bench.init_params_cpu(4, S, 0), B, N, S, ragged=padded and N <= 128, train=False)
 h, x, mask, am, y, n_real = bench.synth(2666, B, N, S, padded, n_min)
 T = lambda a: None if a is None else torch.tensor(a, device="cuda")
-run.load_inputs(T(h), T(x), T(mask), T(am), T(y))
+run.load_inputs(T(h), T(x), target=T(y), n_real=(torch.tensor(n_real, device="cuda", dtype=torch.int32) if run.ragged else None))
 for _ in range(2):
     run.forward()
 torch.cuda.synchronize()

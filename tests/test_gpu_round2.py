@@ -350,6 +350,58 @@ def test_cosine_cutoff_model_vs_oracle(engine):
         assert (fr - f).abs().max().item() < 2e-6 * max(1.0, f.abs().max().item())
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_segmented_training_step_equals_whole_step(use_graph):
+    """The multi-GPU training step runs the backward in segments (readout, one per layer, embedding) and starts the
+    all-reduce of a gradient bucket after each one; cut or whole, eager or as CUDA graphs, it is the same step.
+    (The collective itself is covered on CPU with gloo, tests/test_parallel_cpu.py.)"""
+    import sake_b200
+    from sake_b200.runner import ModelRunner
+
+    class FakeReducer:                   # world 2 without a second process: records the buckets, reduces nothing
+        world = 2
+
+        def __init__(self):
+            self.spans = []
+
+        def start(self, bucket):
+            self.spans.append((bucket.data_ptr(), bucket.numel()))
+
+        def finish(self):
+            return 1.0
+
+    B, N, S = 24, 21, 6
+    rng = np.random.default_rng(3)
+    n_real = rng.integers(5, N + 1, B).astype(np.int32)
+    am = (np.arange(N)[None, :] < n_real[:, None]).astype(np.float32)
+    x = (rng.standard_normal((B, N, 3)) * 1.7).astype(np.float32) * am[..., None]
+    h = np.eye(S, dtype=np.float32)[rng.integers(0, S, (B, N))] * am[..., None]
+    y = rng.standard_normal(B).astype(np.float32)
+    params = _model_params(3, S, 8)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=3)
+    outs = []
+    for seg in (False, True):
+        run = ModelRunner(model, params, B, N, S, ragged=True, train=True)
+        run.load_inputs(_T(h), _T(x), target=_T(y), n_real=_T(n_real, torch.int32))
+        if use_graph:
+            run.capture()
+        red = FakeReducer() if seg else None
+        loss = run.train_step(red).clone()
+        torch.cuda.synchronize()
+        outs.append((loss, run.flat_grads.clone(), run.flat_params.clone()))
+        if seg:
+            # the buckets tile the whole flat gradient vector exactly once
+            base = run.flat_grads.data_ptr()
+            spans = sorted(((p - base) // 4, n) for p, n in red.spans)
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == run.n_params
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+            assert len(spans) == 3 + 2
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-7)
+    gmax = outs[0][1].abs().max().item()
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 1e-5 * gmax
+    assert (outs[0][2] - outs[1][2]).abs().max().item() < 1e-6
+
+
 def test_log_gamma_gradient_is_zero():
     """log_gamma exists in the tree (checkpoint compatibility) but the dense layer never reads it
     (sake/layers.py:97-105 vs :107-235): its gradient is exactly zero through both host paths."""

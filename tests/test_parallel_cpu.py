@@ -48,7 +48,15 @@ def _worker(rank, world, port, out):
     grads = torch.autograd.grad(loss, list(flat.values()), allow_unused=True)
     bucket = torch.cat([(gr if gr is not None else torch.zeros_like(t)).reshape(-1)
                         for gr, t in zip(grads, flat.values())])
+    # bucketed form (one all-reduce per layer, started as the layers finish): same result as the single call
+    pieces = bucket.clone()
+    red = par.GradAllReducer()
+    n3 = pieces.numel() // 3
+    for a, b in ((0, n3), (n3, 2 * n3), (2 * n3, pieces.numel())):
+        red.start(pieces[a:b])
+    s2 = red.finish()
     scale = par.GradAllReducer()(bucket)
+    assert s2 == scale and torch.equal(pieces, bucket)
     bucket = bucket * scale
     tmax = par.max_over_ranks(float(rank + 1), "cpu")
     if rank == 0:
