@@ -100,6 +100,8 @@ static SideCtx* side_ctx() {
   return c;
 }
 
+static inline bool H_is_64(const Dims& d) { return d.H == 64; }
+
 // SAKE_NODE_TC=0 keeps the CUDA-core per-node kernels under the tcgen05 engines (A/B diagnostics)
 static bool node_tc_enabled() {
   static int v = -1;
@@ -324,6 +326,8 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   else
     rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);
   if (rc) return rc;
+  const bool pre_dw_tc = tc_edge && grads && H_is_64(d);
+  if (pre_dw_tc && (rc = tc_node_pre_dw(d, h, *grads, sc, xl))) return rc;
   if (xl.n > 0) {
     // every weight-gradient contraction of this layer in one batched tensor-core launch (+ its reductions);
     // nothing downstream of the layer reads dW, so with SAKE_DEFER_DW it runs on the side stream, forked here
@@ -342,7 +346,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
       side->any = true;
     }
   }
-  return gen_node_pre_bwd(d, *params, h, dh, grads, sc, st);
+  return gen_node_pre_bwd(d, *params, h, dh, pre_dw_tc ? nullptr : grads, sc, st);
 }
 
 int sake_dw_sync(sake_stream_t stream) {

@@ -315,7 +315,7 @@ struct XtgArgs {
 // All weight-gradient contractions of one layer backward are collected and run as ONE batched launch
 // (+ one reduction launch): blockIdx.y selects the problem.
 struct XtgList {
-  static constexpr int MAXP = 12;
+  static constexpr int MAXP = 16;
   XtgArgs a[MAXP];
   int n = 0;
   // small follow-up kernels that consume `extra` rows of some problems
@@ -360,6 +360,7 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const BwdScratch& sc, cudaStream_t st);
 size_t tc_node_dw_scratch_bytes(const Dims& d);
 int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st);
+int tc_node_pre_dw(const Dims& d, const float* h, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
 int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st);

@@ -1031,6 +1031,31 @@ int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, Xtg
   return 0;
 }
 
+// Weight gradients of the separable per-node projections (mlp_in, rows [0, 2H) of mlp_out[0] and their biases:
+// layers.py:19,22,30,33-38) as four more problems of the layer's batched X^T G launch: X = h [R, H], G = a column
+// block of the projection cotangent gproj [R, NP] (layout: common.cuh).  k_node_pre_bwd used to accumulate them
+// with one atomicAdd per (CTA, weight): 4.3 M atomics per layer at cfg2, 70 % of that kernel's time.
+int tc_node_pre_dw(const Dims& d, const float* h, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L) {
+  const int H = d.H, K = d.K, Kp = d.Kp;
+  auto call = [&](int col0, int gw, float* out, int ldo, float* bias) {
+    XtgArgs q;
+    memset(&q, 0, sizeof(q));
+    q.X = h; q.ldx = H; q.xw = H; q.ones_col = bias ? H : -1; q.MXpad = 128;
+    q.G = sc.gproj + col0; q.ldg = d.NP; q.gw = gw; q.NG = 64;
+    q.P = d.R; q.Pdev = d.hdr ? &d.hdr->R64 : nullptr;
+    q.out = out; q.ldo = ldo; q.out_rows = H; q.out_cols = gw;
+    q.extra = bias; q.extra_rows = bias ? 1 : 0; q.extra_ld = gw;
+    return L.push(q);
+  };
+  int rc = 0;
+  rc |= call(0, K, g.mlp_in_kernel, K, nullptr);                               // sender half of mlp_in
+  rc |= call(Kp, K, g.mlp_in_kernel + (size_t)H * K, K, g.mlp_in_bias);        // receiver half + bias
+  rc |= call(2 * Kp, H, g.mlp_out0_kernel, H, nullptr);                        // sender half of mlp_out[0]
+  rc |= call(2 * Kp + H, H, g.mlp_out0_kernel + (size_t)H * H, H, g.mlp_out0_bias);
+  if (rc) { set_error("xtg list full"); return SAKE_EINVAL; }
+  return 0;
+}
+
 void tc_node_finish(const XtgList& L, cudaStream_t st) {
   if (L.post_tmp) {
     k_post_bias_finish<<<1, 128, 0, st>>>(L.post_tmp, L.g_post2_bias, L.g_post0_bias);
@@ -1102,6 +1127,7 @@ int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
   return 0;
 }
 
+// g == NULL: input cotangent dh only (the tcgen05 engines get the parameter gradients from tc_node_pre_dw)
 int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,
                      const BwdScratch& sc, cudaStream_t st) {
   int rc;

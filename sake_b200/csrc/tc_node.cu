@@ -750,9 +750,9 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
 __global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, const float* __restrict__ ssum,
                                                  const float* __restrict__ qv, float* __restrict__ gWv) {
   if (hdr) R = hdr->R;
-  if ((int)blockIdx.x * 64 >= R) return;
+  if ((int)blockIdx.x * 16 >= R) return;
   const int c = threadIdx.x;
-  const int n0 = blockIdx.x * 64, n1 = min(R, n0 + 64);
+  const int n0 = blockIdx.x * 16, n1 = min(R, n0 + 16);
   float acc = 0.f;
   for (int n = n0; n < n1; ++n) {
     const float4 q = *reinterpret_cast<const float4*>(qv + (size_t)n * 4);
@@ -805,7 +805,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
     if (deep) k_tc_node_post_bwd<4><<<tiles, NT_TILE, smem, st>>>(a);
     else k_tc_node_post_bwd<2><<<tiles, NT_TILE, smem, st>>>(a);
   }
-  if (wvg) k_wv_grad<<<(d.R + 63) / 64, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
+  if (wvg) k_wv_grad<<<(d.R + 15) / 16, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 2 : 1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

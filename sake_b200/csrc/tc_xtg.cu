@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_c
   }
 }
 
-size_t tc_xtg_partial_bytes() { return (size_t)128 << 20; }
+size_t tc_xtg_partial_bytes() { return (size_t)192 << 20; }
 
 static int xtg_num_sms() {
   static int sms = 0;
