@@ -239,21 +239,42 @@ class ModelJob:
         from sake_b200 import runner as R
         self.R = R
         B, N, S, padded, n_min, mode, desc = WORKLOADS[wl]
+        shard = None
         if B_override is not None:
-            B = B_override
+            # strong scaling: this rank's share of the ONE global batch (seed 2666), split by the dense pair cost
+            # sum(n_real^2) for padded batches and contiguously otherwise (scripts/ani/run_gpu.py:54-56)
+            from sake_b200.parallel import balanced_partition, shard_range
+            full = synth(2666, B, N, S, padded, n_min)
+            if padded and world > 1:
+                shard = balanced_partition(full[5], world)[rank]
+            else:
+                b0, b1 = shard_range(B, world, rank)
+                shard = np.arange(b0, b1)
+            B = len(shard)
         self.B, self.N, self.mode, self.padded = B, N, mode, padded
         self.ragged = padded and args.padding == "ragged" and N <= 128
         model = sake_b200.DenseSAKEModel(hidden_features=H, out_features=1, depth=args.depth, engine=args.engine)
         self.run = R.ModelRunner(model, init_params_cpu(args.depth, S, 0), B, N, S, masked=padded and not self.ragged,
                                  ragged=self.ragged, train=(mode == "train"), device=dev,
                                  defer_dw=args.defer_dw)
-        h, x, mask, am, y, n_real = synth(2666 + rank, B, N, S, padded, n_min)
+        if shard is not None:
+            h, x, mask, am, y, n_real = (None if t is None else t[shard] for t in full)
+        else:
+            # rank 0's batch is the N = 1 batch; every other rank draws its own molecules (species, coordinates,
+            # targets) with the SAME multiset of sizes in another order: weak scaling compares equal work per GPU
+            h, x, mask, am, y, n_real = synth(2666 + rank, B, N, S, padded, n_min)
+            if rank and padded:
+                n_real = np.random.default_rng(777 + rank).permutation(synth(2666, B, N, S, padded, n_min)[5]).astype(np.int32)
+                am = (np.arange(N)[None, :] < n_real[:, None]).astype(np.float32)
+                hz, xz = synth(2666 + rank, B, N, S, False, 0)[:2]
+                h, x, mask = hz * am[..., None], xz * am[..., None], am[:, :, None] * am[:, None, :]
         self.n_real = n_real
         pin = lambda a: None if a is None else torch.tensor(a).pin_memory()
         self.hp, self.xp, self.yp = pin(h), pin(x), pin(y)
         self.mp, self.ap, self.np_ = (None, None, pin(n_real)) if self.ragged else (pin(mask), pin(am), None)
         self.load()
         self.allreduce = None
+        self.bucketed = bool(getattr(args, "bucketed_allreduce", False))
         if world > 1 and mode == "train" and allreduce:
             from sake_b200.parallel import GradAllReducer
             self.allreduce = GradAllReducer()   # NCCL sum of the flat grad bucket; 1/world folded into the Adam kernel
@@ -272,7 +293,7 @@ class ModelJob:
 
     def step(self):
         if self.mode == "train":
-            return self.run.train_step(self.allreduce)
+            return self.run.train_step(self.allreduce, bucketed=self.bucketed)
         return self.run.energy_forces_step()
 
     def e2e_step(self):
@@ -390,6 +411,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step as a CUDA graph")
     ap.add_argument("--defer-dw", action="store_true",
                     help="run the weight-gradient contractions on the library's side stream (measured: no gain, see DESIGN.md)")
+    ap.add_argument("--bucketed-allreduce", action="store_true",
+                    help="training on several GPUs: all-reduce per-layer gradient buckets between backward segments instead of one all-reduce after the backward")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total-size cfg3 / cfg4 records")
     ap.add_argument("--no-sustained", action="store_true", help="skip the extra timed rounds that extend the run to ~2.5 s")
     args = ap.parse_args()
@@ -542,11 +565,9 @@ def main():
         strong = {}
         for swl in ("cfg3", "cfg4"):
             Bt = WORKLOADS[swl][0]
-            if Bt % world != 0:
-                continue
             job = None
             torch.cuda.empty_cache()
-            sj = ModelJob(swl, args, rank, world, dev, B_override=Bt // world)
+            sj = ModelJob(swl, args, rank, world, dev, B_override=Bt)
             for _ in range(3):
                 sj.step()
             if not args.no_graphs:
@@ -555,7 +576,9 @@ def main():
             torch.cuda.synchronize()
             ssteps = 10
             s_ms, _ = timed_region(sj, ssteps, flush, dist, dev)
-            strong[swl] = {"molecules_total": Bt, "molecules_per_gpu": Bt // world, "mode": sj.mode,
+            strong[swl] = {"molecules_total": Bt, "molecules_this_rank": sj.B, "mode": sj.mode,
+                           "split": "one global batch (seed 2666) split over the ranks: balanced by sum(n_real^2)" if sj.padded
+                                    else "one global batch (seed 2666) split contiguously",
                            "ms_per_step": s_ms / ssteps, "value": Bt / (s_ms / ssteps * 1e-3), "unit": "molecules/s",
                            "steps": ssteps, "collective": "ncclAllReduce of the flat gradient bucket" if sj.allreduce else "none",
                            "padding": "ragged" if sj.ragged else ("masked" if sj.padded else "none")}

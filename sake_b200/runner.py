@@ -327,13 +327,15 @@ class ModelRunner:
         self._run_body(False)
         return self.energy, self.forces
 
-    def train_step(self, allreduce=None):
+    def train_step(self, allreduce=None, bucketed=False):
         """One energy-L1 training step (scripts/qm9/run.py:79-89): fwd, bwd with parameter grads,
         optional gradient all-reduce (lax.pmean, scripts/ani/run_gpu.py:130), AdamW-style chain."""
         scale = 1.0
-        if allreduce is not None and getattr(allreduce, "world", 1) > 1 and hasattr(allreduce, "start"):
+        if bucketed and allreduce is not None and getattr(allreduce, "world", 1) > 1 and hasattr(allreduce, "start"):
             # per-layer buckets (lax.pmean over the same leaves, scripts/ani/run_gpu.py:130): the all-reduce of layer
-            # l's gradients runs on the NCCL stream under the backward of layer l-1
+            # l's gradients runs on the NCCL stream under the backward of layer l-1.  Opt-in: measured on 2 x B200 it
+            # is SLOWER than one all-reduce after the backward (3.61 vs 3.4 ms per cfg2 step) — the collective's CTAs
+            # take SMs away from persistent kernels that are sized one CTA per SM, which then need a second wave.
             segs = getattr(self, "seg_graphs", None)
             for prefix, fn in (segs if segs else self._train_segments()):
                 if segs:
