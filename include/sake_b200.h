@@ -47,6 +47,10 @@ enum {
                             sake/layers.py:172-176): euclidean_attention = 0.5 (cos(pi (2 (d - lower) / (upper - lower) + 1)) + 1)
                             with SakeDims.cutoff_lower / cutoff_upper; as in the reference the range masks are
                             NOT applied (utils.py:24-25 discards them), so the factor is periodic in d       */
+  SAKE_WEIGHTS_PREPARED = 64, /* sake_layer_fwd: the operand images of this layer's weights in `saved` are current
+                            (sake_layer_prepare ran on the same parameters since they last changed): skip
+                            rebuilding them.  Inference loops prepare once; a training step prepares after
+                            every optimiser step (or leaves the flag clear and lets the forward call do it).  */
   SAKE_DEFER_DW = 16     /* sake_layer_bwd only: enqueue the weight-gradient contractions (dW = X^T G over all
                             pairs / atoms; nothing downstream of the layer reads them) on the library's side
                             stream so that they overlap the next layer's backward.  SakeDims.reserved = scratch
@@ -185,6 +189,13 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
                    float* h_out, float* x_out, float* v_out,
                    void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
                    sake_stream_t stream);
+
+/* Builds the tcgen05 operand images of one layer's weights (swizzled, split-precision copies of x_mixing, the edge
+ * MLP, the node-tail MLPs and their transposes; ~1.7 MB) into `saved`, where sake_layer_fwd (with
+ * SAKE_WEIGHTS_PREPARED) and sake_layer_bwd read them.  No-op on the generic fp32 engine.  The images depend on the
+ * parameters only: the reference's XLA program has no counterpart (it re-reads the flax kernels every call). */
+int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void* saved, size_t saved_bytes,
+                       sake_stream_t stream);
 
 /* Vector-Jacobian product of sake_layer_fwd (what jax.grad / jax.vjp of the layer computes:
  * scripts/md17/run.py:58 forces, scripts/qm9/run.py:84-89 parameter gradients).

@@ -16,6 +16,7 @@ lib = C.CDLL(LIB_PATH)
 
 # enums (include/sake_b200.h)
 SAKE_UPDATE, SAKE_HAS_V, SAKE_HAS_MASK, SAKE_NO_SPATIAL, SAKE_DEFER_DW, SAKE_COSINE_CUTOFF = 1, 2, 4, 8, 16, 32
+SAKE_WEIGHTS_PREPARED = 64
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32X3, ENGINE_BF16, ENGINE_F16X2 = 0, 1, 2, 3, 4
 ENGINES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32x3": ENGINE_TF32X3, "bf16": ENGINE_BF16,
            "f16x2": ENGINE_F16X2}
@@ -65,6 +66,8 @@ lib.sake_ragged_scatter.restype = C.c_int
 lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _sz, _vp, _sz, _vp]
 lib.sake_layer_fwd.restype = C.c_int
+lib.sake_layer_prepare.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _sz, _vp]
+lib.sake_layer_prepare.restype = C.c_int
 lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SakeLayerGrads), _vp, _sz, _vp]
 lib.sake_layer_bwd.restype = C.c_int
@@ -98,7 +101,7 @@ lib.sake_launch_count.restype = C.c_ulonglong
 lib.sake_selftest_tcgen05.argtypes = [C.POINTER(C.c_float), _vp]
 lib.sake_selftest_tcgen05.restype = C.c_int
 
-EXPORTS = ("sake_dw_sync", "sake_flow_pre", "sake_flow_post", "sake_flow_logprob", "sake_ragged_bytes", "sake_ragged_prepare", "sake_ragged_gather", "sake_ragged_scatter", "sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
+EXPORTS = ("sake_layer_prepare", "sake_dw_sync", "sake_flow_pre", "sake_flow_post", "sake_flow_logprob", "sake_ragged_bytes", "sake_ragged_prepare", "sake_ragged_gather", "sake_ragged_scatter", "sake_version", "sake_last_error", "sake_resolve_engine", "sake_layer_saved_bytes",
            "sake_layer_scratch_bytes", "sake_layer_fwd", "sake_layer_bwd", "sake_dense_fwd",
            "sake_dense_bwd", "sake_selftest_tcgen05", "sake_energy_head", "sake_adam_step",
            "sake_profile_begin", "sake_profile_collect", "sake_launch_count", "sake_selftest_xtg", "sake_debug_counters", "sake_debug_counters_bwd")

@@ -41,6 +41,7 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->has_v = (s->flags & SAKE_HAS_V) != 0;
   d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
   d->spatial = (s->flags & SAKE_NO_SPATIAL) == 0;
+  d->prepared = (s->flags & SAKE_WEIGHTS_PREPARED) != 0;
   d->cutoff = (s->flags & SAKE_COSINE_CUTOFF) != 0;
   d->cut_lo = s->cutoff_lower; d->cut_hi = s->cutoff_upper;
   if (d->cutoff && !(d->cut_hi > d->cut_lo)) { set_error("cosine cutoff needs upper > lower (got %g, %g)", d->cut_lo, d->cut_hi); return SAKE_EINVAL; }
@@ -257,10 +258,32 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
     if ((rc = tc_mix_fwd(d, *params, x, mask, sv, sv.wmix, engine, st))) return rc;
   }
   if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr)) {
-    if ((rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;     // for the backward call's k_node_pre_bwd
+    if (!d.prepared && (rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;   // for the backward call's k_node_pre_bwd
     return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, sv.wnode, st);
   }
   return gen_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, st);
+}
+
+int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void* saved, size_t saved_bytes,
+                       sake_stream_t stream) {
+  Dims d;
+  int rc = make_dims(dims, &d);
+  if (rc) return rc;
+  if (!params || !saved) { set_error("sake_layer_prepare: NULL argument"); return SAKE_EINVAL; }
+  if ((rc = check_leaves(d, *params, "params"))) return rc;
+  int engine = resolve_engine(dims, d);
+  if (engine < 0) return engine;
+  if (engine == SAKE_ENGINE_FP32) return 0;
+  if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(d, saved, tc_edge_supported(d), engine);
+  if (d.spatial && (rc = tc_mix_prepare(*params, sv.wmix, engine, st))) return rc;
+  if (tc_edge_supported(d) && (rc = tc_edge_prepare(d, *params, sv.wedge, st))) return rc;
+  if (tc_node_supported(d)) {
+    if ((rc = tc_node_prepare(*params, sv.wnode, st))) return rc;
+    if ((rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;
+  }
+  return 0;
 }
 
 int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,

@@ -34,6 +34,7 @@ struct Dims {
   int Kp;                 // K rounded up to a multiple of 4 (16-byte aligned projection blocks)
   int NP;                 // per-node projection width = 2Kp + 2H
   int update, has_v, has_mask, spatial;
+  int prepared;           // 1: weight operand images in `saved` are current (SAKE_WEIGHTS_PREPARED)
   int cutoff;             // 1: cosine cutoff on the attention (layers.py:172-176), parameters below
   float cut_lo, cut_hi;
   const RaggedHdr* hdr;   // NULL: uniform batch (every molecule has N atoms, optional float mask)
@@ -373,6 +374,10 @@ int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, fl
 // mix forward: ssum[R,C,3] from e, att, x (replaces the generic k_mix_fwd)
 int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
                const Saved& sv, void* tc_scratch, int engine, cudaStream_t st);
+// weight operand images (built by sake_layer_prepare, or by the forward call when d.prepared == 0)
+int tc_mix_prepare(const SakeLayerParams& p, void* wmix, int engine, cudaStream_t st);
+int tc_edge_prepare(const Dims& d, const SakeLayerParams& p, void* wedge, cudaStream_t st);
+int tc_node_prepare(const SakeLayerParams& p, void* wnode, cudaStream_t st);
 // mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
                const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L,

@@ -630,10 +630,16 @@ static int edge_grid(const TileGeom& g) {
   return want < sms ? (want < 1 ? 1 : want) : sms;
 }
 
+int tc_edge_prepare(const Dims& d, const SakeLayerParams& p, void* wedge, cudaStream_t st) {
+  edge_prep(d, p, carve_edge_w(wedge), st);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 void* wscratch, cudaStream_t st) {
   EdgeW w = carve_edge_w(wscratch);
-  edge_prep(d, p, w, st);
+  if (!d.prepared) edge_prep(d, p, w, st);
   EdgeArgs a;
   memset(&a, 0, sizeof(a));
   a.g = make_geom(d);

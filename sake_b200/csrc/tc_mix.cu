@@ -113,14 +113,48 @@ __device__ __forceinline__ void build_E_chunk(uint8_t* img, int row, int kc, con
   }
 }
 
+// fp16-split engine: exact power-of-two pair (sc, inv = 1/sc) that brings `bound` into [2^11, 2^12).
+// With the operand's largest magnitude there, hi = fp16(x) and lo = fp16(x - hi) together carry 22 bits of
+// the row / tensor maximum and nothing can overflow (fp16 max 65504) or drown in fp16 subnormals, however
+// large or small the fp32 values are.  Identity for 0, inf and nan.
+__device__ __forceinline__ void pow2_norm(float bound, float& sc, float& inv) {
+  const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);   // biased exponent: bound in [2^(e-127), 2^(e-126))
+  int k = 138 - e;
+  if (e == 0 || e == 255) k = 0;
+  k = max(-100, min(100, k));
+  sc = __uint_as_float((uint32_t)(k + 127) << 23);
+  inv = __uint_as_float((uint32_t)(127 - k) << 23);
+}
+
 // ---- weight image preparation ------------------------------------------------------------------
 // w1img[kc][split][row=c'][128B]: K index = c      (GEMM1: Z = E Wx)
 // w2img[q ][split][row=c ][128B]: K index = c', ring order q -> chunk (q%2)*(NCHUNK/2) + q/2 (GEMM2: dE = dZ Wx^T)
+// (fp16-split engine: every CTA first reduces max |Wx| itself — 256 coalesced loads per thread from L2 — instead of
+// waiting for a separate one-CTA launch; block 0 publishes {scale, 1/scale} for the mix kernels)
 template <int ENGINE>
-__global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1img, uint8_t* __restrict__ w2img,
-                          const float* __restrict__ wscale) {
+__global__ void __launch_bounds__(256) k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1img,
+                                                 uint8_t* __restrict__ w2img, float* __restrict__ wscale) {
   using CF = Cfg<ENGINE>;
-  const float wsc = CF::F16 ? wscale[0] : 1.0f;
+  float wsc = 1.0f;
+  if constexpr (CF::F16) {
+    __shared__ float red[8];
+    float mx = 0.f;
+    for (int q = threadIdx.x; q < CC * CC / 4; q += 256) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wx) + q);
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(w4.x), fabsf(w4.y))), fmaxf(fabsf(w4.z), fabsf(w4.w)));
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) mx = fmaxf(mx, red[q]);
+    float inv;
+    pow2_norm(mx, wsc, inv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wscale[0] = wsc; wscale[1] = inv; }
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wscale[0] = 1.0f; wscale[1] = 1.0f; }
+  }
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_img = CF::NCHUNK * CC * 8;
   if (t >= 2 * per_img) return;
@@ -169,19 +203,6 @@ __global__ void k_tc_prep(const float* __restrict__ Wx, uint8_t* __restrict__ w1
     }
     *reinterpret_cast<uint4*>(base + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-}
-
-// fp16-split engine: exact power-of-two pair (sc, inv = 1/sc) that brings `bound` into [2^11, 2^12).
-// With the operand's largest magnitude there, hi = fp16(x) and lo = fp16(x - hi) together carry 22 bits of
-// the row / tensor maximum and nothing can overflow (fp16 max 65504) or drown in fp16 subnormals, however
-// large or small the fp32 values are.  Identity for 0, inf and nan.
-__device__ __forceinline__ void pow2_norm(float bound, float& sc, float& inv) {
-  const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu);   // biased exponent: bound in [2^(e-127), 2^(e-126))
-  int k = 138 - e;
-  if (e == 0 || e == 255) k = 0;
-  k = max(-100, min(100, k));
-  sc = __uint_as_float((uint32_t)(k + 127) << 23);
-  inv = __uint_as_float((uint32_t)(127 - k) << 23);
 }
 
 // max |Wx| -> {scale, 1/scale} of the weight images (fp16-split engine; {1, 1} otherwise)
@@ -990,10 +1011,8 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   uint8_t* w1 = (uint8_t*)scratch;
   uint8_t* w2 = w1 + wimg_bytes<CF>();
   TileGeom g = make_geom(d);
-  const int prep_threads = 2 * CF::NCHUNK * CC * 8;
   float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
-  k_tc_wscale<<<1, 1024, 0, st>>>(p.x_mixing_kernel, wsc, CF::F16 ? 1 : 0);
-  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
+  if (!d.prepared) { const int rc = tc_mix_prepare(p, scratch, ENGINE, st); if (rc) return rc; }
   if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_mix_fwd<ENGINE>, smem_bytes<CF>(), optin); if (rc) return rc; }
@@ -1004,9 +1023,28 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
     k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, wsc, sv.ssum, dbg);
   }
-  note_launches(3);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+template <int ENGINE>
+static int tc_prepare_impl(const SakeLayerParams& p, void* wmix, cudaStream_t st) {
+  using CF = Cfg<ENGINE>;
+  uint8_t* w1 = (uint8_t*)wmix;
+  uint8_t* w2 = w1 + wimg_bytes<CF>();
+  float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());
+  const int prep_threads = 2 * CF::NCHUNK * CC * 8;
+  if ((reinterpret_cast<uintptr_t>(p.x_mixing_kernel) & 15) != 0) { set_error("x_mixing kernel must be 16-byte aligned"); return SAKE_EINVAL; }
+  k_tc_prep<ENGINE><<<(prep_threads + 255) / 256, 256, 0, st>>>(p.x_mixing_kernel, w1, w2, wsc);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int tc_mix_prepare(const SakeLayerParams& p, void* wmix, int engine, cudaStream_t st) {
+  if (engine == SAKE_ENGINE_BF16) return tc_prepare_impl<SAKE_ENGINE_BF16>(p, wmix, st);
+  if (engine == SAKE_ENGINE_F16X2) return tc_prepare_impl<SAKE_ENGINE_F16X2>(p, wmix, st);
+  return tc_prepare_impl<SAKE_ENGINE_TF32X3>(p, wmix, st);
 }
 
 int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st);

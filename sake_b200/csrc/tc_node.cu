@@ -813,12 +813,19 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
 
 bool tc_node_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
 
+// all chunks, forward and transposed: the backward call of the step reuses the image
+int tc_node_prepare(const SakeLayerParams& p, void* wnode, cudaStream_t st) {
+  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, (uint8_t*)wnode, NTB_CHUNKS);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const float* x, const float* v,
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st) {
   uint8_t* wimg = (uint8_t*)wscratch;
-  // all chunks, forward and transposed: the backward call of this step reuses the image
-  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, wimg, NTB_CHUNKS);
+  if (!d.prepared) { const int rc = tc_node_prepare(p, wscratch, st); if (rc) return rc; }
   NodeFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
@@ -837,7 +844,7 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
     if (deep) k_tc_node_post<4><<<tiles, NT_TILE, smem, st>>>(a);
     else k_tc_node_post<2><<<tiles, NT_TILE, smem, st>>>(a);
   }
-  note_launches(2);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

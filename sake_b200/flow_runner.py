@@ -30,7 +30,9 @@ class FlowRunner:
         self.psets, self.scale = {}, {}
         for i in range(depth):
             for nm in ("xv_%d" % i, "vx_%d" % i):
-                self.psets[nm] = self.run.pset if nm == "xv_0" else ParamSet(model, params[nm]["sake_model"], dev)
+                # every coupling model gets its own ParamSet (also xv_0: the runner's built-in set would count as
+                # "own" and skip the weight-image rebuild that sharing one set of `saved` buffers makes necessary)
+                self.psets[nm] = ParamSet(model, params[nm]["sake_model"], dev)
                 sm = params[nm]["scale_mlp"]
                 self.scale[nm] = tuple(t.detach().to(dev).float().contiguous() for t in
                                        (sm["layers_0"]["kernel"], sm["layers_0"]["bias"], sm["layers_2"]["kernel"]))

@@ -121,6 +121,16 @@ class ModelRunner:
         self.xs = [self.x_in] + [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(self.L)]
         self.vs = [None] + [torch.empty(B, N, 3, device=dev, dtype=f32) for _ in range(self.L)]
         self.saved = [ops._buf(ops.saved_bytes(d), dev) for d in self.dims]
+        # inference: the weights do not change between steps, so their tcgen05 operand images are built ONCE
+        # (sake_layer_prepare) and every forward call skips the five small preparation launches per layer;
+        # call refresh_weights() after changing self.p in place.  Training rebuilds them in every forward call.
+        self.weights_prepared = False
+        self.dims_unprepared = [_lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags, d.engine, d.reserved, d.cutoff_lower,
+                                              d.cutoff_upper) for d in self.dims]
+        if not train:
+            for d in self.dims:
+                d.flags |= _lib.SAKE_WEIGHTS_PREPARED
+            self.refresh_weights()
         nscr = max(max(ops.scratch_bytes(d, 0, 0), ops.scratch_bytes(d, 1, int(train))) for d in self.dims)
         self.scratch = ops._buf(nscr, dev)
         # defer_dw (opt-in): the weight-gradient contractions of layer l run on the library's side stream under the
@@ -146,6 +156,14 @@ class ModelRunner:
         self.forces = torch.empty(B, N, 3, device=dev, dtype=f32)
         self.hbm_bytes = sum(t.numel() * t.element_size() for t in
                              [self.flat_params, *set(self.scratches), *self.saved, *self.hs, *self.xs[1:], *self.vs[1:]])
+
+    def refresh_weights(self, pset=None):
+        """(Re)build the weight operand images of every layer from the current parameters (inference runners)."""
+        pset = self.pset if pset is None else pset
+        for l in range(self.L):
+            check(lib.sake_layer_prepare(C.byref(self.dims[l]), C.byref(pset.ps[l]), ops._ptr(self.saved[l]),
+                                         self.saved[l].numel(), ops._stream()), "sake_layer_prepare")
+        self.weights_prepared = True
 
     # -- inputs ------------------------------------------------------------------------------------
     def load_inputs(self, h, x, mask=None, atom_mask=None, target=None, n_real=None):
@@ -185,9 +203,12 @@ class ModelRunner:
     def forward(self, pset=None):
         """pset: another ParamSet of the same architecture (the flow runs 2*depth models through one set of
         activation buffers); default: the runner's own parameters."""
+        foreign = pset is not None and pset is not self.pset
         pset = self.pset if pset is None else pset
         p = pset.p
         rg = self.rg
+        # another model's parameters through this runner's buffers (flows): the images in `saved` are not theirs
+        dims = self.dims_unprepared if foreign else self.dims
         if self.ragged:
             self._ragged_inputs()
         ops.dense_fwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.hs[0], 0, rg)
@@ -195,7 +216,7 @@ class ModelRunner:
             v_in = self.vs[l] if self.has_v[l] else None
             upd = self.model.update_list[l]
             v_out = self.vs[l + 1] if (upd or v_in is not None) else None
-            ops.layer_fwd_raw(self.dims[l], pset.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
+            ops.layer_fwd_raw(dims[l], pset.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
                               self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch, rg)
         ops.dense_fwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
                           p.get("embedding_out/layers_0/bias"), self.y0, 1, rg)
