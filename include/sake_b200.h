@@ -83,6 +83,22 @@ typedef struct SakeDims {
   float cutoff_upper;
 } SakeDims;
 
+/* Edge features `he` (DenseSAKELayer.__call__(..., he), sake/layers.py:201-202: h_cat_ht = concat(h_cat_ht, he)).
+ * The concatenated block only ever meets two Dense layers — rows [2F, 2F+E) of edge_model/mlp_in and of
+ * edge_model/mlp_out/layers_0 (sake/layers.py:30,33-38) — so it enters the layer as two per-pair additive terms
+ * that the caller computes with two small GEMMs over he [B,N,N,E]:
+ *     u = he @ mlp_in_kernel[2F:2F+E]        [B,N,N,Kp]  (K columns, zero-padded to Kp = K rounded up to 4)
+ *     p = he @ mlp_out0_kernel[2F:2F+E]      [B,N,N,H]
+ * and the kernels are handed the two kernels WITHOUT those rows ([2F, K] and [2F+K+1, H]).  The backward call
+ * returns the cotangents g_u / g_p of the two terms (same shapes), from which the caller's autodiff obtains d he and
+ * the gradients of the two row blocks.  Not available for ragged batches. */
+typedef struct SakePairTerms {
+  const float* u;
+  const float* p;
+  float* g_u; /* backward only; may be NULL */
+  float* g_p;
+} SakePairTerms;
+
 /* Parameters of one DenseSAKELayer, flax layouts (kernel = [in, out]); SURVEY Appendix C.
  * C = A*H.  Pointers that a configuration does not use may be NULL. */
 typedef struct SakeLayerParams {
@@ -186,6 +202,7 @@ int sake_ragged_scatter(const void* ragged, int32_t B, int32_t N, int32_t width,
  * 0/0 = NaN there, layers.py:178-180); every other value follows the reference formulas. */
 int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
                    const float* h, const float* x, const float* v, const float* mask, const void* ragged,
+                   const SakePairTerms* pair /* he terms, or NULL */,
                    float* h_out, float* x_out, float* v_out,
                    void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
                    sake_stream_t stream);
@@ -205,6 +222,7 @@ int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void
  * `saved` must be the buffer written by sake_layer_fwd for the same inputs. */
 int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params,
                    const float* h, const float* x, const float* v, const float* mask, const void* ragged,
+                   const SakePairTerms* pair /* he terms, or NULL */,
                    const void* saved, size_t saved_bytes,
                    const float* dh_out, const float* dx_out, const float* dv_out,
                    float* dh, float* dx, float* dv, const SakeLayerGrads* grads,

@@ -100,7 +100,7 @@ def coords(rng, shape):
     return (rng.standard_normal(shape) * 0.62 * n ** (1.0 / 3.0)).astype(np.float32)
 
 
-def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True, cutoff=None):
+def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True, cutoff=None, he_features=0):
     """cutoff: None or (lower, upper) -> DenseSAKELayer(cutoff=partial(sake.utils.cosine_cutoff, lower=, upper=))"""
     import functools
     rng = np.random.default_rng(seed)
@@ -116,20 +116,27 @@ def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True, cutoff=N
     if with_mask:
         m = np.concatenate([np.ones(n_real), np.zeros(N - n_real)]).astype(np.float32)
         mask = np.broadcast_to(m[None, :] * m[:, None], shp + (N,)).copy()
+    he = rng.standard_normal(shp + (N, he_features)).astype(np.float32) if he_features else None
     init = model.init(jax.random.PRNGKey(seed), T(h, torch.float64), T(x, torch.float64),
-                      T(v, torch.float64), T(mask, torch.float64))
+                      T(v, torch.float64), T(mask, torch.float64), T(he, torch.float64))
     flat = perturb(init["params"], rng)
 
     def fn(dt):
         p = as_params(flat, dt)
         xx = T(x, dt).requires_grad_(True)
         hh = T(h, dt).requires_grad_(True)
-        ho, xo, vo = model.apply(p, hh, xx, T(v, dt), T(mask, dt))
+        hee = T(he, dt).requires_grad_(True) if he is not None else None
+        ho, xo, vo = model.apply(p, hh, xx, T(v, dt), T(mask, dt), hee)
         ho, xo, vo = ho[..., :n_real, :], xo[..., :n_real, :], (vo[..., :n_real, :] if vo is not None else None)
         # a scalar that touches every output, for gradient pinning
         s = (ho ** 2).sum() + (xo * 0.3).sum() + ((vo * vo).sum() if (vo is not None and update) else 0.0)
-        gx, gh = torch.autograd.grad(s, [xx, hh])
+        if hee is not None:
+            gx, gh, ghe = torch.autograd.grad(s, [xx, hh, hee])
+        else:
+            gx, gh = torch.autograd.grad(s, [xx, hh])
         out = {"h": ho, "x": xo, "scalar": s, "grad_x": gx[..., :n_real, :], "grad_h": gh[..., :n_real, :]}
+        if hee is not None:
+            out["grad_he"] = ghe
         if vo is not None:
             out["v"] = vo
         return out
@@ -137,7 +144,7 @@ def case_layer(name, H, N, batch, with_v, with_mask, seed, update=True, cutoff=N
     meta = {"H": H, "N": N, "n_real": n_real, "update": int(update), "kind": "layer"}
     if cutoff is not None:
         meta["cutoff"] = np.asarray(cutoff, dtype=np.float64)
-    save(name, flat, {"h": h, "x": x, "v": v, "mask": mask}, run_both(fn), meta)
+    save(name, flat, {"h": h, "x": x, "v": v, "mask": mask, "he": he}, run_both(fn), meta)
 
 
 def case_model(name, H, F_in, depth, N, batch, with_v, seed, out_features=1, update=True, grad_keys=()):
@@ -221,6 +228,9 @@ def main_round2():
     # DenseSAKELayer(cutoff=cosine_cutoff) (sake/layers.py:172-176, sake/utils.py:10-26): tcgen05 shape and generic shape
     case_layer("layer_h64_n9_b2_cutoff", 64, 9, (2,), True, False, 21, cutoff=(0.0, 5.0))
     case_layer("layer_h16_n6_cutoff", 16, 6, (), False, False, 22, cutoff=(0.5, 4.0))
+    # edge features he (sake/layers.py:201-202), tcgen05 shape and generic shape
+    case_layer("layer_h64_n9_b2_he5", 64, 9, (2,), True, False, 23, he_features=5)
+    case_layer("layer_h16_n6_he3", 16, 6, (), False, False, 24, he_features=3)
 
 
 def main():

@@ -139,11 +139,13 @@ def spatial_attention(p, h_e_att, x_minus_xt, x_norm, mask=None):
 
 
 def layer_forward(p, h, x, v=None, mask=None, *, update=True, use_spatial_attention=True,
-                  guarded=True, cutoff=None):
-    """DenseSAKELayer.__call__  (sake/layers.py:188-235).  he is not supported."""
+                  guarded=True, cutoff=None, he=None):
+    """DenseSAKELayer.__call__  (sake/layers.py:188-235)."""
     x_minus_xt = get_x_minus_xt(x)
     x_norm = get_x_minus_xt_norm(x_minus_xt)
     h_cat_ht = get_h_cat_ht(h)
+    if he is not None:                                   # sake/layers.py:201-202
+        h_cat_ht = torch.cat([h_cat_ht, he], dim=-1)
     h_e_mtx = edge_model(p["edge_model"], h_cat_ht, x_norm)
     att = combined_attention(p, x_norm, h_e_mtx, mask=mask, guarded=guarded, cutoff=cutoff)
     h_e_att = h_e_mtx.unsqueeze(-1) * att.unsqueeze(-2)                    # [..., i, j, H, A]
@@ -179,14 +181,14 @@ def layer_forward(p, h, x, v=None, mask=None, *, update=True, use_spatial_attent
 
 
 def model_forward(params, h, x, v=None, mask=None, *, update=True, use_spatial_attention=True,
-                  guarded=True, cutoff=None):
+                  guarded=True, cutoff=None, he=None):
     """DenseSAKEModel.__call__ (sake/models.py:56-61).  depth = number of 'd<k>' entries."""
     depth = sum(1 for k in params if k.startswith("d") and k[1:].isdigit())
     upd = [update] * depth if isinstance(update, bool) else list(update)
     h = dense(params["embedding_in"], h)
     for k in range(depth):
         h, x, v = layer_forward(params["d%d" % k], h, x, v, mask, update=upd[k],
-                                use_spatial_attention=use_spatial_attention, guarded=guarded, cutoff=cutoff)
+                                use_spatial_attention=use_spatial_attention, guarded=guarded, cutoff=cutoff, he=he)
     h = silu(dense(params["embedding_out"]["layers_0"], h))
     h = dense(params["embedding_out"]["layers_2"], h)
     return h, x, v

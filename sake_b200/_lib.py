@@ -44,6 +44,11 @@ class SakeLayerGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
 
 
+class SakePairTerms(C.Structure):
+    """`he` edge features as per-pair additive terms (include/sake_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("u", "p", "g_u", "g_p")]
+
+
 _vp, _sz, _i32, _i64 = C.c_void_p, C.c_size_t, C.c_int32, C.c_int64
 _DP = C.POINTER(SakeDims)
 
@@ -63,12 +68,13 @@ lib.sake_ragged_gather.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp, _vp]
 lib.sake_ragged_gather.restype = C.c_int
 lib.sake_ragged_scatter.argtypes = [_vp, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp]
 lib.sake_ragged_scatter.restype = C.c_int
-lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                               _vp, _sz, _vp, _sz, _vp]
+lib.sake_layer_fwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, C.POINTER(SakePairTerms),
+                               _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]
 lib.sake_layer_fwd.restype = C.c_int
 lib.sake_layer_prepare.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _sz, _vp]
 lib.sake_layer_prepare.restype = C.c_int
-lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+lib.sake_layer_bwd.argtypes = [_DP, C.POINTER(SakeLayerParams), _vp, _vp, _vp, _vp, _vp, C.POINTER(SakePairTerms),
+                               _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SakeLayerGrads), _vp, _sz, _vp]
 lib.sake_layer_bwd.restype = C.c_int
 lib.sake_dw_sync.argtypes = [_vp]

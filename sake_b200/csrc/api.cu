@@ -46,9 +46,18 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->cut_lo = s->cutoff_lower; d->cut_hi = s->cutoff_upper;
   if (d->cutoff && !(d->cut_hi > d->cut_lo)) { set_error("cosine cutoff needs upper > lower (got %g, %g)", d->cut_lo, d->cut_hi); return SAKE_EINVAL; }
   d->hdr = nullptr; d->rowinfo = nullptr; d->tileinfo = nullptr; d->molinfo = nullptr;
+  d->pair_u = nullptr; d->pair_p = nullptr;
   return 0;
 }
 // ragged batches (n_real-packed, see ragged.cu): compact tensors, no float mask, tcgen05 engines only
+static int attach_pair(Dims* d, const SakePairTerms* pair, const void* ragged) {
+  if (!pair) return 0;
+  if (!pair->u || !pair->p) { set_error("SakePairTerms needs both u and p"); return SAKE_EINVAL; }
+  if (ragged) { set_error("edge features (SakePairTerms) are not available for ragged batches"); return SAKE_EUNSUPPORTED; }
+  if (((reinterpret_cast<uintptr_t>(pair->u) | reinterpret_cast<uintptr_t>(pair->p)) & 15) != 0) { set_error("SakePairTerms buffers must be 16-byte aligned"); return SAKE_EINVAL; }
+  d->pair_u = pair->u; d->pair_p = pair->p;
+  return 0;
+}
 static int attach_ragged(Dims* d, const void* ragged, const float* mask, int engine) {
   if (!ragged) return 0;
   if (mask || d->has_mask) { set_error("a ragged batch carries no float mask (padding atoms are not stored)"); return SAKE_EINVAL; }
@@ -224,7 +233,8 @@ size_t sake_layer_scratch_bytes(const SakeDims* dims, int for_backward, int with
 }
 
 int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
-                   const float* v, const float* mask, const void* ragged, float* h_out, float* x_out, float* v_out,
+                   const float* v, const float* mask, const void* ragged, const SakePairTerms* pair, float* h_out,
+                   float* x_out, float* v_out,
                    void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
   Dims d;
   int rc = make_dims(dims, &d);
@@ -242,6 +252,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (SL.total > 256 && (!scratch || scratch_bytes < SL.total)) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
+  if ((rc = attach_pair(&d, pair, ragged))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
   Saved sv = carve_saved(d, saved, tc_edge, engine);
@@ -287,7 +298,8 @@ int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void
 }
 
 int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const float* h, const float* x,
-                   const float* v, const float* mask, const void* ragged, const void* saved, size_t saved_bytes, const float* dh_out,
+                   const float* v, const float* mask, const void* ragged, const SakePairTerms* pair, const void* saved,
+                   size_t saved_bytes, const float* dh_out,
                    const float* dx_out, const float* dv_out, float* dh, float* dx, float* dv,
                    const SakeLayerGrads* grads, void* scratch, size_t scratch_bytes, sake_stream_t stream) {
   Dims d;
@@ -306,6 +318,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
   if (d.R == 0) return 0;
   if ((rc = attach_ragged(&d, ragged, mask, engine))) return rc;
+  if ((rc = attach_pair(&d, pair, ragged))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // deferred weight gradients: wait for the previous user of this scratch slot before touching the scratch
   SideCtx* side = nullptr;
@@ -344,10 +357,12 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   // tcgen05 edge path: softmax backward only (celu' comes from the saved logits, the W_s g_q term of g_e is
   // added inside the edge kernel); generic path: the original kernel that recomputes q and updates g_e
   if ((rc = tc_edge ? tc_attn_bwd(d, x, sv, sc, st) : gen_attn_bwd(d, *params, x, sv, sc, st))) return rc;
+  float* gpu_ = pair ? pair->g_u : nullptr;
+  float* gpp_ = pair ? pair->g_p : nullptr;
   if (tc_edge)
-    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, sv.wedge, b + SL.edgeb, xl, st);
+    rc = tc_edge_bwd(d, *params, x, mask, sv, sc, dx, grads, sv.wedge, b + SL.edgeb, xl, gpu_, gpp_, st);
   else
-    rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, st);
+    rc = gen_edge_bwd(d, *params, x, sv, dx, grads, sc, gpu_, gpp_, st);
   if (rc) return rc;
   const bool pre_dw_tc = tc_edge && grads && H_is_64(d);
   if (pre_dw_tc && (rc = tc_node_pre_dw(d, h, *grads, sc, xl))) return rc;

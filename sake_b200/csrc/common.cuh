@@ -37,6 +37,7 @@ struct Dims {
   int prepared;           // 1: weight operand images in `saved` are current (SAKE_WEIGHTS_PREPARED)
   int cutoff;             // 1: cosine cutoff on the attention (layers.py:172-176), parameters below
   float cut_lo, cut_hi;
+  const float *pair_u, *pair_p;   // `he` edge features as per-pair additive terms [P,Kp], [P,H] (SakePairTerms) or NULL
   const RaggedHdr* hdr;   // NULL: uniform batch (every molecule has N atoms, optional float mask)
   const int4* rowinfo;
   const int4* tileinfo;
@@ -366,7 +367,7 @@ int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
                 const BwdScratch& sc, float* gWx, cudaStream_t st);
 int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st);
 int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, float* dx,
-                 const SakeLayerGrads* g, const BwdScratch& sc, cudaStream_t st);
+                 const SakeLayerGrads* g, const BwdScratch& sc, float* g_pair_u, float* g_pair_p, cudaStream_t st);
 int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, float* dh, const SakeLayerGrads* g,
                      const BwdScratch& sc, cudaStream_t st);
 
@@ -395,7 +396,7 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
                 void* wscratch, cudaStream_t st);
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
-                cudaStream_t st);
+                float* g_pair_u, float* g_pair_p, cudaStream_t st);
 void tc_edge_finish(const XtgList& L, cudaStream_t st);
 void tc_node_finish(const XtgList& L, cudaStream_t st);
 

@@ -671,7 +671,8 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
                                                   const float* __restrict__ ge, const float* __restrict__ gq,
                                                   const float* __restrict__ gdir, float* __restrict__ gproj,
                                                   float* __restrict__ dx, SakeLayerGrads g, int want_grads,
-                                                  const float* __restrict__ gcut) {
+                                                  const float* __restrict__ gcut, float* __restrict__ g_pair_u,
+                                                  float* __restrict__ g_pair_p) {
   extern __shared__ float sm[];
   EdgeBwdSmem s = edge_bwd_carve(sm, d);
   const int H = d.H, K = d.K, A = d.A, N = d.N;
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
         float dm = s.ts[pj] - p.rbf_means[k];
         float rho = expf(-p.rbf_betas[k] * dm * dm);
         float u = proj[(size_t)(b * N + j) * d.NP + k] + s.pri[d.Kp + k];
+        if (d.pair_u) u += d.pair_u[((size_t)row * N + j) * d.Kp + k];     // edge features (SakePairTerms)
         s.rho[pj * K + k] = rho;
         s.u[pj * K + k] = u;
         s.g[pj * K + k] = rho * u;
@@ -713,6 +715,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
         const int pj = t / H, f = t % H;
         const int j = j0 + pj;
         float z = proj[(size_t)(b * N + j) * d.NP + 2 * d.Kp + f] + s.pri[2 * d.Kp + H + f];
+        if (d.pair_p) z += d.pair_p[((size_t)row * N + j) * H + f];
         z = fmaf(s.ns[pj], w1n[f], z);
         for (int k = 0; k < K; ++k) z = fmaf(s.g[pj * K + k], W1g[(size_t)k * H + f], z);
         s.z1[pj * H + f] = z;
@@ -786,6 +789,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
             const float grho = ggv * s.u[pj * K + k];
             const float dm = s.ts[pj] - mu;
             atomicAdd(gproj + (size_t)(b * N + j) * d.NP + k, gu);
+            if (g_pair_u) g_pair_u[((size_t)row * N + j) * d.Kp + k] = gu;
             gui += gu;
             const float w = dm * rho * grho;
             gmu = fmaf(2.0f * beta, w, gmu);
@@ -800,6 +804,7 @@ __global__ void __launch_bounds__(256) k_edge_bwd(Dims d, const float* __restric
           for (int pj = 0; pj < np; ++pj) {
             const int j = j0 + pj;
             const float gz = s.gz1[pj * H + f];
+            if (g_pair_p) g_pair_p[((size_t)row * N + j) * H + f] = gz;
             atomicAdd(gproj + (size_t)(b * N + j) * d.NP + 2 * d.Kp + f, gz);
             gpi += gz;
           }
@@ -1114,14 +1119,15 @@ int gen_attn_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const 
 }
 
 int gen_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const Saved& sv, float* dx,
-                 const SakeLayerGrads* g, const BwdScratch& sc, cudaStream_t st) {
+                 const SakeLayerGrads* g, const BwdScratch& sc, float* g_pair_u, float* g_pair_p, cudaStream_t st) {
   int rc;
   SAKE_CUDA_CHECK(cudaMemsetAsync(sc.gproj, 0, sizeof(float) * (size_t)d.R * d.NP, st));
+  if (g_pair_u) SAKE_CUDA_CHECK(cudaMemsetAsync(g_pair_u, 0, sizeof(float) * (size_t)d.P * d.Kp, st));   // padding columns
   size_t smem = sizeof(float) * edge_bwd_floats(d);
   if ((rc = ensure_smem(k_edge_bwd, smem))) return rc;
   int grid = d.R < 148 * 2 ? d.R : 148 * 2;
   k_edge_bwd<<<grid, 256, smem, st>>>(d, x, p, sv.nodeproj, sv.e, sc.ge, sc.gatt, sc.gdir, sc.gproj, dx,
-                                      g ? *g : null_grads(), g != nullptr, d.cutoff ? sc.gcut : nullptr);
+                                      g ? *g : null_grads(), g != nullptr, d.cutoff ? sc.gcut : nullptr, g_pair_u, g_pair_p);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

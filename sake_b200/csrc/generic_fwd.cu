@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
       float dm = tt - p.rbf_means[k];
       float rho = expf(-p.rbf_betas[k] * dm * dm);
       float u = proj[(size_t)(b * N + j) * d.NP + k] + pri[d.Kp + k];
+      if (d.pair_u) u += d.pair_u[((size_t)row * N + j) * d.Kp + k];       // edge features (SakePairTerms)
       gs[pj * K + k] = rho * u;
     }
     __syncthreads();
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) k_edge_fwd(Dims d, const float* __restric
       const int pj = t / H, f = t % H;
       const int j = j0 + pj;
       float z = proj[(size_t)(b * N + j) * d.NP + 2 * d.Kp + f] + pri[2 * d.Kp + H + f];
+      if (d.pair_p) z += d.pair_p[((size_t)row * N + j) * H + f];
       z = fmaf(ns[pj], w1n[f], z);
       for (int k = 0; k < K; ++k) z = fmaf(gs[pj * K + k], W1g[(size_t)k * H + f], z);
       a1[pj * H + f] = siluf_(z);

@@ -110,6 +110,7 @@ struct EdgeArgs {
                                        // attention-logit term W_s g_q is added here (written back when training)
   const float *gdir, *gq;              // backward inputs  [P,3], [P,4] (cotangent of the pre-celu logits)
   const float* gcut;                   // backward input   [P] cotangent of the distance through the cutoff, or NULL
+  const float *pair_u, *pair_p;        // `he` edge features as per-pair additive terms of u [P,Kp] and z1 [P,64], or NULL
   float *PB, *a1buf, *gbuf;            // backward outputs [P,192], [P,64], [P,64] (a1buf/gbuf: training only)
   int train;
 };
@@ -242,6 +243,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         if (4 * u < Kp) {                      // idle lanes read node 0 (valid memory); their rows are never stored
           uj4[q] = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
           ui4[q] = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
+          if (a.pair_u) {                      // edge features: + he @ W_in[2F:2F+E]  (SakePairTerms)
+            const float4 ue = __ldg(reinterpret_cast<const float4*>(a.pair_u + prx * Kp + 4 * u));
+            ui4[q].x += ue.x; ui4[q].y += ue.y; ui4[q].z += ue.z; ui4[q].w += ue.w;
+          }
         }
       }
       // 32 independent exp chains, no control flow in between: mu / beta are zero-padded beyond K (rho = 1) and
@@ -288,6 +293,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         for (int u = 0; u < 8; ++u) {
           pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 4 * u));
           pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 4 * u));
+          if (a.pair_p) {                      // edge features: + he @ W_1[2F:2F+E]
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + 4 * u));
+            pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
+          }
         }
         float v[32];
         tmem_ld32(lane_addr, v);
@@ -306,6 +315,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       for (int u = 0; u < 8; ++u) {
         pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 32 + 4 * u));
         pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 32 + 4 * u));
+        if (a.pair_p) {
+          const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + 32 + 4 * u));
+          pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
+        }
       }
       run_chunk(tcol + 0, sW2, 0, 80, idesc80);                            // E' (chunk 0) -> cols [0,80)
 #pragma unroll
@@ -361,7 +374,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             for (int u = 0; u < 8; ++u) {
               const int f0 = half * 32 + 4 * u;
               const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
-              const float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+              float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+              if (a.pair_p) {
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + f0));
+                pi.x += pe.x; pi.y += pe.y; pi.z += pe.z; pi.w += pe.w;
+              }
               o[u] = make_float4(fsilu_(v[4 * u] + pj.x + pi.x), fsilu_(v[4 * u + 1] + pj.y + pi.y),
                                  fsilu_(v[4 * u + 2] + pj.z + pi.z), fsilu_(v[4 * u + 3] + pj.w + pi.w));
             }
@@ -403,6 +420,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         for (int u = 0; u < 8; ++u) {
           pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
           pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
+          if (a.pair_p) {
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + half * 32 + 4 * u));
+            pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
+          }
         }
         float z[32], ga[32];
         if (half == 0) {
@@ -442,6 +463,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           if (half * 32 + 4 * u < Kp) {               // warp-uniform; idle lanes read node 0
             uj4[u] = __ldg(reinterpret_cast<const float4*>(nj + half * 32 + 4 * u));
             ui4[u] = __ldg(reinterpret_cast<const float4*>(ni + Kp + half * 32 + 4 * u));
+            if (a.pair_u) {
+              const float4 ue = __ldg(reinterpret_cast<const float4*>(a.pair_u + prx * Kp + half * 32 + 4 * u));
+              ui4[u].x += ue.x; ui4[u].y += ue.y; ui4[u].z += ue.z; ui4[u].w += ue.w;
+            }
           }
         }
         float gg[32];
@@ -601,6 +626,18 @@ __global__ void __launch_bounds__(128) k_pair_reduce(Dims d, const float* __rest
   }
 }
 
+// cotangents of SakePairTerms out of the per-pair record (columns >= K of g_u are zero)
+__global__ void k_pair_terms_out(long long P, int K, int Kp, const float* __restrict__ PB, float* __restrict__ g_u,
+                                 float* __restrict__ g_p) {
+  const int w = 64 + Kp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * w) return;
+  const long long pr = t / w;
+  const int c = (int)(t - pr * w);
+  if (c < 64) { if (g_p) g_p[pr * 64 + c] = PB[pr * PB_LD + c]; }
+  else if (g_u) { const int k = c - 64; g_u[pr * Kp + k] = k < K ? PB[pr * PB_LD + 64 + k] : 0.f; }
+}
+
 // dmu_k += 2 beta_k S1_k ;  dbeta_k += -(S2_k - mu_k S1_k)   with S1 = sum_p w_pk, S2 = sum_p t_p w_pk
 __global__ void k_mubeta_finish(int K, const float* __restrict__ mu, const float* __restrict__ beta,
                                 const float* __restrict__ extra, float* __restrict__ gmu, float* __restrict__ gbeta) {
@@ -645,6 +682,7 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.g = make_geom(d);
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
+  a.pair_u = d.pair_u; a.pair_p = d.pair_p;
   a.e_out = sv.e; a.logit_out = sv.logit;
   const size_t smem = WA_BYTES + WB_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;
   static unsigned long long optin = 0;
@@ -667,7 +705,7 @@ size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads) {
 
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
-                cudaStream_t st) {
+                float* g_pair_u, float* g_pair_p, cudaStream_t st) {
   EdgeW w = carve_edge_w(wscratch);                      // built by tc_edge_fwd of the same step (saved.wedge)
   char* eb = (char*)escratch;
   float* PB = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * PB_LD);
@@ -680,6 +718,7 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.gcut = d.cutoff ? sc.gcut : nullptr;
+  a.pair_u = d.pair_u; a.pair_p = d.pair_p;
   a.ge = sc.ge; a.gdir = sc.gdir; a.gq = sc.gatt; a.PB = PB; a.a1buf = a1buf; a.gbuf = gbuf; a.train = g != nullptr;
   const size_t smem = WA_BYTES + WC_BYTES + WD_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;   // 226.1 KB: no alignment slack
   static unsigned long long optin = 0;
@@ -690,6 +729,12 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   }
   k_pair_reduce<<<d.R, 128, 0, st>>>(d, PB, sc.gproj, dx);
   note_launches(2);
+  if (g_pair_u || g_pair_p) {
+    // cotangents of the `he` terms are columns of the per-pair record: g_z1 = PB[:, 0:64], g_u = PB[:, 64:64+Kp)
+    const long long total = d.P * (long long)(64 + d.Kp);
+    k_pair_terms_out<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d.P, d.K, d.Kp, PB, g_pair_u, g_pair_p);
+    note_launches(1);
+  }
   SAKE_CUDA_CHECK(cudaGetLastError());
   if (g) {
     XtgArgs q;

@@ -38,7 +38,7 @@ static ffi::Error FwdImpl(cudaStream_t stream, ffi::AnyBuffer h, ffi::AnyBuffer 
     auto b = leaves.get<ffi::AnyBuffer>(i);
     pp[i] = (b.has_value() && b->element_count()) ? (const float*)b->untyped_data() : nullptr;
   }
-  int rc = sake_layer_fwd(&d, &p, (const float*)h.untyped_data(), (const float*)x.untyped_data(), opt(v), opt(mask), /*ragged=*/nullptr,
+  int rc = sake_layer_fwd(&d, &p, (const float*)h.untyped_data(), (const float*)x.untyped_data(), opt(v), opt(mask), /*ragged=*/nullptr, /*pair=*/nullptr,
                           (float*)h2->untyped_data(), (float*)x2->untyped_data(), (float*)v2->untyped_data(),
                           saved->untyped_data(), saved->size_bytes(), scratch->untyped_data(), scratch->size_bytes(),
                           stream);
@@ -76,7 +76,7 @@ static ffi::Error BwdImpl(cudaStream_t stream, ffi::AnyBuffer h, ffi::AnyBuffer 
   auto dx = *rets.get<ffi::AnyBuffer>(1);
   auto dv = *rets.get<ffi::AnyBuffer>(2);
   auto scratch = *rets.get<ffi::AnyBuffer>(3 + NL);
-  int rc = sake_layer_bwd(&d, &p, (const float*)h.untyped_data(), (const float*)x.untyped_data(), opt(v), opt(mask), /*ragged=*/nullptr,
+  int rc = sake_layer_bwd(&d, &p, (const float*)h.untyped_data(), (const float*)x.untyped_data(), opt(v), opt(mask), /*ragged=*/nullptr, /*pair=*/nullptr,
                           saved.untyped_data(), saved.size_bytes(), (const float*)dh2.untyped_data(), opt(dx2), opt(dv2),
                           (float*)dh->untyped_data(), (float*)dx->untyped_data(),
                           dv->element_count() ? (float*)dv->untyped_data() : nullptr, &g, scratch->untyped_data(),

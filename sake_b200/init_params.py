@@ -38,17 +38,18 @@ def dense_init(gen, fan_in, fan_out, use_bias=True):
 
 
 def init_layer_params(gen, in_features, hidden_features, out_features, n_heads, update, has_v,
-                      log_gamma=True, kernel_features=50):
+                      log_gamma=True, kernel_features=50, edge_features=0):
     """Parameter tree of one layer, in flax creation semantics (velocity_mlp only when it is
     actually called at init: layers.py:226-229)."""
     F, H, A, K = in_features, hidden_features, n_heads, kernel_features
     C = A * H
+    E = edge_features          # width of `he` (sake/layers.py:201-202): h_cat_ht grows to 2F + E
     means, betas = exp_normal_smearing_init(K)
     p = {
         "edge_model": {
             "kernel": {"means": means, "betas": betas},
-            "mlp_in": dense_init(gen, 2 * F, K),
-            "mlp_out": {"layers_0": dense_init(gen, 2 * F + K + 1, H), "layers_2": dense_init(gen, H, H)},
+            "mlp_in": dense_init(gen, 2 * F + E, K),
+            "mlp_out": {"layers_0": dense_init(gen, 2 * F + E + K + 1, H), "layers_2": dense_init(gen, H, H)},
         },
     }
     if log_gamma:

@@ -70,14 +70,13 @@ class DenseSAKELayer:
 
     # -- flax-style API ---------------------------------------------------------------------
     def init(self, key, h, x, v=None, mask=None, he=None):
-        if he is not None:
-            raise ops._lib.SakeError("edge features `he` are not supported")
         if h.shape[-1] != self.out_features:
             raise ops._lib.SakeError("residual needs in_features == out_features (layers.py:150)")
         gen = _generator(key)
         p = init_layer_params(gen, h.shape[-1], self.hidden_features, self.out_features, self.n_heads,
                               self.update, v is not None,
-                              log_gamma=self.use_semantic_attention and self.use_euclidean_attention)
+                              log_gamma=self.use_semantic_attention and self.use_euclidean_attention,
+                              edge_features=0 if he is None else he.shape[-1])
         return {"params": tree_to(p, h.device)}
 
     def apply(self, variables, *args, method=None, **kwargs):
@@ -176,13 +175,27 @@ class DenseSAKELayer:
         return 2.0 * torch.sigmoid(g @ p["layers_2"]["kernel"]) * v
 
     def __call__(self, params, h, x, v=None, mask=None, he=None):
-        if he is not None:
-            raise ops._lib.SakeError("edge features `he` are not supported")
         flat = flatten_tree(params)
         D = x.shape[-1]
+        pair_u = pair_p = None
+        if he is not None:
+            # Edge features (sake/layers.py:201-202: h_cat_ht = concat(h_cat_ht, he)) only meet rows [2F, 2F+E) of
+            # mlp_in and mlp_out[0]: two small GEMMs here give the per-pair terms the kernels add (SakePairTerms,
+            # include/sake_b200.h), the kernels get the two kernels without those rows, and autograd carries the
+            # returned cotangents back to `he` and to the two row blocks.
+            F2, E = 2 * h.shape[-1], he.shape[-1]
+            w_in, w_1 = flat["edge_model/mlp_in/kernel"], flat["edge_model/mlp_out/layers_0/kernel"]
+            if w_in.shape[0] != F2 + E:
+                raise ops._lib.SakeError(f"mlp_in kernel has {w_in.shape[0]} rows, expected 2F + E = {F2 + E}")
+            K = w_in.shape[1]
+            pair_u = torch.nn.functional.pad(he.float() @ w_in[F2:F2 + E], (0, (-K) % 4))
+            pair_p = he.float() @ w_1[F2:F2 + E]
+            flat = dict(flat)
+            flat["edge_model/mlp_in/kernel"] = w_in[:F2]
+            flat["edge_model/mlp_out/layers_0/kernel"] = torch.cat([w_1[:F2], w_1[F2 + E:]], dim=0)
         ho, xo, vo = ops.sake_layer(flat, h, _pad3(x), _pad3(v), mask, n_heads=self.n_heads,
                                     update=self.update, use_spatial_attention=self.use_spatial_attention,
-                                    engine=self.engine, cutoff=self._cutoff)
+                                    engine=self.engine, cutoff=self._cutoff, pair_u=pair_u, pair_p=pair_p)
         if D != 3:
             xo = xo[..., :D]
             vo = None if vo is None else vo[..., :D]

@@ -41,7 +41,8 @@ class DenseSAKEModel:
         for i in range(self.depth):
             p["d%d" % i] = init_layer_params(
                 gen, H, H, H, self.n_heads, self.update_list[i], has_v,
-                log_gamma=self.use_semantic_attention and self.use_euclidean_attention)
+                log_gamma=self.use_semantic_attention and self.use_euclidean_attention,
+                edge_features=0 if he is None else he.shape[-1])
             has_v = has_v or self.update_list[i]
         return {"params": tree_to(p, h.device)}
 

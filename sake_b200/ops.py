@@ -105,17 +105,29 @@ def _buf(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def layer_fwd_raw(dims, pstruct, h, x, v, mask, h_out, x_out, v_out, saved, scratch, ragged=None):
+def _pair_struct(pair):
+    """pair: None or (u, p[, g_u, g_p]) CUDA tensors -> SakePairTerms (or None)"""
+    if pair is None:
+        return None
+    t = list(pair) + [None] * (4 - len(pair))
+    s = _lib.SakePairTerms()
+    for name, ten in zip(("u", "p", "g_u", "g_p"), t):
+        if ten is not None:
+            setattr(s, name, ten.data_ptr())
+    return C.byref(s)
+
+
+def layer_fwd_raw(dims, pstruct, h, x, v, mask, h_out, x_out, v_out, saved, scratch, ragged=None, pair=None):
     rc = lib.sake_layer_fwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask), _ptr(ragged),
-                            _ptr(h_out), _ptr(x_out), _ptr(v_out), _ptr(saved), saved.numel(),
+                            _pair_struct(pair), _ptr(h_out), _ptr(x_out), _ptr(v_out), _ptr(saved), saved.numel(),
                             _ptr(scratch), 0 if scratch is None else scratch.numel(), _stream())
     check(rc, "sake_layer_fwd")
 
 
 def layer_bwd_raw(dims, pstruct, h, x, v, mask, saved, dh_out, dx_out, dv_out, dh, dx, dv, gstruct, scratch,
-                  ragged=None):
+                  ragged=None, pair=None):
     rc = lib.sake_layer_bwd(C.byref(dims), C.byref(pstruct), _ptr(h), _ptr(x), _ptr(v), _ptr(mask), _ptr(ragged),
-                            _ptr(saved), saved.numel(), _ptr(dh_out), _ptr(dx_out), _ptr(dv_out),
+                            _pair_struct(pair), _ptr(saved), saved.numel(), _ptr(dh_out), _ptr(dx_out), _ptr(dv_out),
                             _ptr(dh), _ptr(dx), _ptr(dv),
                             None if gstruct is None else C.byref(gstruct),
                             _ptr(scratch), scratch.numel(), _stream())
@@ -188,13 +200,16 @@ class _LayerFn(torch.autograd.Function):
     """DenseSAKELayer.__call__ as one differentiable op (fwd / bwd = the two C-ABI entry points)."""
 
     @staticmethod
-    def forward(ctx, cfg, h, x, v, mask, *leaves):
+    def forward(ctx, cfg, h, x, v, mask, pair_u, pair_p, *leaves):
         paths = cfg["paths"]
         flat = {p: _f32c(t, p) for p, t in zip(paths, leaves)}
         h = _f32c(h, "h")
         x = _f32c(x, "x")
         v = _f32c(v, "v")
         mask = _f32c(mask, "mask")
+        pair_u = _f32c(pair_u, "pair_u")
+        pair_p = _f32c(pair_p, "pair_p")
+        pair = None if pair_u is None else (pair_u, pair_p)
         lead = h.shape[:-2]
         N, H = h.shape[-2], h.shape[-1]
         B = 1
@@ -209,11 +224,11 @@ class _LayerFn(torch.autograd.Function):
         h_out = torch.empty_like(h)
         x_out = torch.empty_like(x)
         v_out = torch.empty_like(x) if (cfg["update"] or v is not None) else None
-        layer_fwd_raw(dims, ps, h, x, v, mask, h_out, x_out, v_out, saved, scratch)
+        layer_fwd_raw(dims, ps, h, x, v, mask, h_out, x_out, v_out, saved, scratch, pair=pair)
         # leaves and the fwd->bwd buffer go through save_for_backward: autograd's version counters then catch an
         # in-place parameter update between forward and backward, and the buffer is freed with the graph
         ctx.cfg, ctx.dims = cfg, dims
-        ctx.save_for_backward(h, x, v, mask, saved, *[flat[p] for p in paths])
+        ctx.save_for_backward(h, x, v, mask, pair_u, pair_p, saved, *[flat[p] for p in paths])
         ctx.n_leaves = len(leaves)
         if v_out is None:
             v_out = x.new_zeros(())      # placeholder (reference returns None)
@@ -222,10 +237,10 @@ class _LayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dh_out, dx_out, dv_out):
-        h, x, v, mask, saved_buf, *leaves = ctx.saved_tensors
+        h, x, v, mask, pair_u, pair_p, saved_buf, *leaves = ctx.saved_tensors
         cfg, dims = ctx.cfg, ctx.dims
         flat = dict(zip(cfg["paths"], leaves))
-        want_grads = any(ctx.needs_input_grad[5:])
+        want_grads = any(ctx.needs_input_grad[7:])
         dev = h.device
         dh_out = _f32c(dh_out, "dh_out") if dh_out is not None else torch.zeros_like(h)
         dx_out = _f32c(dx_out, "dx_out") if dx_out is not None else None
@@ -240,13 +255,17 @@ class _LayerFn(torch.autograd.Function):
             gs, _ = params_struct(gflat, _lib.SakeLayerGrads)
         ps, keep = params_struct(flat)
         scratch = _buf(scratch_bytes(dims, 1, want_grads), dev)
-        layer_bwd_raw(dims, ps, h, x, v, mask, saved_buf, dh_out, dx_out, dv_out, dh, dx, dv, gs, scratch)
+        pair, g_u, g_p = None, None, None
+        if pair_u is not None:
+            g_u, g_p = torch.empty_like(pair_u), torch.empty_like(pair_p)
+            pair = (pair_u, pair_p, g_u, g_p)
+        layer_bwd_raw(dims, ps, h, x, v, mask, saved_buf, dh_out, dx_out, dv_out, dh, dx, dv, gs, scratch, pair=pair)
         grads = [gflat.get(p) if want_grads else None for p in cfg["paths"]]
-        return (None, dh, dx, dv, None, *grads)
+        return (None, dh, dx, dv, None, g_u, g_p, *grads)
 
 
 def sake_layer(flat_params, h, x, v=None, mask=None, *, n_heads=4, update=True, use_spatial_attention=True,
-               engine="auto", cutoff=None):
+               engine="auto", cutoff=None, pair_u=None, pair_p=None):
     """flat_params: {flax path -> tensor} of one DenseSAKELayer.  Returns (h, x, v) like
     sake/layers.py:188-235 (v is None when the reference would return None)."""
     paths = tuple(p for p, _ in LAYER_LEAVES if p in flat_params)
@@ -258,7 +277,7 @@ def sake_layer(flat_params, h, x, v=None, mask=None, *, n_heads=4, update=True, 
     K = flat_params["edge_model/kernel/means"].shape[0]
     cfg = {"paths": paths, "A": int(n_heads), "K": int(K), "update": bool(update),
            "spatial": bool(use_spatial_attention), "engine": engine, "cutoff": cutoff}
-    h_out, x_out, v_out = _LayerFn.apply(cfg, h, x, v, mask, *[flat_params[p] for p in paths])
+    h_out, x_out, v_out = _LayerFn.apply(cfg, h, x, v, mask, pair_u, pair_p, *[flat_params[p] for p in paths])
     if not (update or v is not None):
         v_out = None
     return h_out, x_out, v_out

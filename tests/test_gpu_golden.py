@@ -48,7 +48,10 @@ def test_layer_golden(name, engine):
     x = _dev(g["in"]["x"]).requires_grad_(True)
     v = _dev(g["in"].get("v"))
     mask = _dev(g["in"].get("mask"))
-    ho, xo, vo = layer.apply({"params": p}, h, x, v, mask)
+    he = _dev(g["in"].get("he"))                       # edge features (sake/layers.py:201-202), round-2 fixtures
+    if he is not None:
+        he.requires_grad_(True)
+    ho, xo, vo = layer.apply({"params": p}, h, x, v, mask, he)
     ho, xo = ho[..., :n_real, :], xo[..., :n_real, :]
     _close(ho, g["out"]["f32/h"], 1e-4, 2e-5, "h")
     _close(xo, g["out"]["f32/x"], 1e-4, 2e-5, "x")
@@ -60,7 +63,11 @@ def test_layer_golden(name, engine):
     if np.isnan(g["out"]["f32/grad_x"]).any():
         return     # the reference's own gradients are NaN for padded inputs (layers.py:178-180)
     s = (ho ** 2).sum() + (xo * 0.3).sum() + ((vo * vo).sum() if (vo is not None and update) else 0.0)
-    gx, gh = torch.autograd.grad(s, [x, h])
+    if he is not None:
+        gx, gh, ghe = torch.autograd.grad(s, [x, h, he])
+        _close(ghe, g["out"]["f64/grad_he"], 1e-3, 1e-4, "grad_he")
+    else:
+        gx, gh = torch.autograd.grad(s, [x, h])
     _close(gx[..., :n_real, :], g["out"]["f64/grad_x"], 1e-3, 1e-4, "grad_x")
     _close(gh[..., :n_real, :], g["out"]["f64/grad_h"], 1e-3, 1e-4, "grad_h")
 

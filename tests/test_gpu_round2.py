@@ -386,7 +386,7 @@ def test_segmented_training_step_equals_whole_step(use_graph):
         if use_graph:
             run.capture()
         red = FakeReducer() if seg else None
-        loss = run.train_step(red).clone()
+        loss = run.train_step(red, bucketed=True).clone()
         torch.cuda.synchronize()
         outs.append((loss, run.flat_grads.clone(), run.flat_params.clone()))
         if seg:
@@ -455,7 +455,7 @@ def test_missing_leaves_are_errors():
         saved = ops._buf(ops.saved_bytes(dims), h.device)
         scratch = ops._buf(ops.scratch_bytes(dims, 0, 0), h.device)
         ho, xo, vo = torch.empty_like(h), torch.empty_like(x), torch.empty_like(x)
-        rc = _lib.lib.sake_layer_fwd(C.byref(dims), C.byref(ps), ops._ptr(h), ops._ptr(x), ops._ptr(v), None, None,
+        rc = _lib.lib.sake_layer_fwd(C.byref(dims), C.byref(ps), ops._ptr(h), ops._ptr(x), ops._ptr(v), None, None, None,
                                      ops._ptr(ho), ops._ptr(xo), ops._ptr(vo), ops._ptr(saved), saved.numel(),
                                      ops._ptr(scratch), scratch.numel(), None)
         assert rc == -1 and b"vel0_kernel" in _lib.lib.sake_last_error()

@@ -33,8 +33,8 @@ def test_argument_validation_without_gpu():
     d = _lib.SakeDims(2, 5, 16, 4, 50, _lib.SAKE_UPDATE, _lib.ENGINE_AUTO, 0)
     assert _lib.lib.sake_resolve_engine(C.byref(d)) == _lib.ENGINE_FP32
     assert _lib.lib.sake_layer_saved_bytes(C.byref(d)) > 0
-    rc = _lib.lib.sake_layer_fwd(C.byref(d), None, None, None, None, None, None, None, None, None, None, 0, None, 0,
-                                 None)
+    rc = _lib.lib.sake_layer_fwd(C.byref(d), None, None, None, None, None, None, None, None, None, None, None, 0, None,
+                                 0, None)
     assert rc == -1
     # ragged tables: size query works without a GPU, bad arguments are refused before any launch
     assert _lib.lib.sake_ragged_bytes(256, 29) > 256 * 29 * 32

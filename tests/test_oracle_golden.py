@@ -37,6 +37,9 @@ def test_layer(name, prec):
     x = _t(g["in"]["x"], dt).requires_grad_(True)
     v = _t(g["in"].get("v"), dt)
     mask = _t(g["in"].get("mask"), dt)
+    he = _t(g["in"].get("he"), dt)
+    if he is not None:
+        he.requires_grad_(True)
     update = bool(int(g["meta"]["update"]))
     cutoff = None
     if "cutoff" in g["meta"]:                      # DenseSAKELayer(cutoff=partial(cosine_cutoff, lower=, upper=))
@@ -44,7 +47,7 @@ def test_layer(name, prec):
         cutoff = lambda d: O.cosine_cutoff(d, lo, hi)
     # guarded=False == the reference as written; real rows are identical in both modes
     for guarded in (False, True):
-        ho, xo, vo = O.layer_forward(p, h, x, v, mask, update=update, guarded=guarded, cutoff=cutoff)
+        ho, xo, vo = O.layer_forward(p, h, x, v, mask, update=update, guarded=guarded, cutoff=cutoff, he=he)
         ho, xo = ho[..., :n_real, :], xo[..., :n_real, :]
         rt, at = TOL[prec]
         _close(ho.detach(), g["out"][prec + "/h"], rt, at, "h")
@@ -53,7 +56,11 @@ def test_layer(name, prec):
             vo = vo[..., :n_real, :]
             _close(vo.detach(), g["out"][prec + "/v"], rt, at, "v")
         s = (ho ** 2).sum() + (xo * 0.3).sum() + ((vo * vo).sum() if (vo is not None and update) else 0.0)
-        gx, gh = torch.autograd.grad(s, [x, h])
+        if he is not None:                             # edge features: cotangent of he as well
+            gx, gh, ghe = torch.autograd.grad(s, [x, h, he])
+            _close(ghe, g["out"][prec + "/grad_he"], rt * 5, at * 5, "grad_he")
+        else:
+            gx, gh = torch.autograd.grad(s, [x, h])
         if np.isnan(g["out"][prec + "/grad_x"]).any():
             # reference as written: padded rows are 0/0, so its own gradients are NaN
             # (sake/layers.py:178-180); gradient parity for padded inputs is pinned by
