@@ -15,7 +15,8 @@
 namespace sake {
 using namespace tc;
 
-constexpr int NT_TILE = 128;                 // atoms per CTA
+constexpr int NT_TILE = 128;                 // atoms per CTA = builder threads (warps 0-3)
+constexpr int NT_THREADS = NT_TILE + 32;     // + warp 4: weight-chunk TMA and MMA issue
 constexpr int NT_IMG = NT_TILE * 128;        // one split of the A chunk image (16 KB)
 constexpr int NT_WCH = 2 * 64 * 128;         // one weight chunk: {hi, lo} x 64 output rows x 128 B (16 KB)
 // chunk index of every matrix inside the weight image
@@ -90,6 +91,10 @@ struct NodeFwdArgs {
 // loads of round c+1 run under the MMAs of round c (two image buffers, used alternately).  Weight chunks stream
 // through a four-slot ring two rounds ahead; a slot is re-filled once the MMAs that read it have completed
 // (tcgen05.commit on the slot's own barrier), which only the issuing thread waits for.
+// The issuing thread is lane 0 of a fifth warp: the 128 builder threads (one per atom) hand an image over with
+// a plain mbarrier arrive and go on to the next round — no block-wide barrier, and no builder thread spends its
+// time on descriptors and the weight ring.  The rounds of both kernels form a fixed sequence, which the issuing
+// warp walks on its own (mma_round), gated by the builders' arrives.
 // SLOTS = 4 (look-ahead 2: consecutive rounds' MMAs overlap; 130 KB of shared memory, one CTA per SM) is the
 // low-latency configuration for small batches; SLOTS = 2 (look-ahead 1; 99 KB) lets two CTAs share an SM and is
 // used when there are more than two tiles per SM, where throughput matters and the second CTA hides the latency.
@@ -99,7 +104,10 @@ template <int SLOTS>
 struct NodePipe {
   static constexpr int LA = SLOTS / 2;
   uint8_t* wring;
-  uint64_t *wfull, *wfree, *ubar;
+  uint64_t *wfull, *wfree, *ubar, *full;   // full[k]: image buffer k published (128 builder arrives)
+  uint64_t* taken;                         // taken[k]: the issuing thread has seen that publication
+  uint32_t npub;                           // builders: bit k = parity of the number of publications of buffer k so far
+  uint32_t anypub;                         // builders: bit k = buffer k has been published at least once
   const uint8_t* wimg;
   int wpos;                      // rounds issued so far
   int c0, c1, c2;                // weight chunk of round wpos and wpos+1 (requested), wpos+2 (requested by the next issue); -1: none
@@ -108,41 +116,52 @@ struct NodePipe {
   __device__ __forceinline__ void init_barriers() {      // one thread
     for (int i = 0; i < SLOTS; ++i) { mbar_init(wfull + i, 1); mbar_init(wfree + i, 1); }
     for (int i = 0; i < NT_UBARS; ++i) mbar_init(ubar + i, 1);
+    mbar_init(full, NT_TILE); mbar_init(full + 1, NT_TILE);
+    mbar_init(taken, 1); mbar_init(taken + 1, 1);
     fence_barrier_init();
   }
   __device__ __forceinline__ void request(int chunk, int slot) {   // one thread
     mbar_arrive_expect_tx(wfull + slot, NT_WCH);
     bulk_g2s(wring + slot * NT_WCH, wimg + (size_t)chunk * NT_WCH, NT_WCH, wfull + slot);
   }
-  // publish the image (all threads), then one thread runs its 12 MMAs against the round's weight chunk.
-  // ub >= 0: the MMAs issued so far arrive on user barrier ub when complete (at most one un-waited commit per barrier).
-  template <class Next>
-  __device__ __forceinline__ void issue(uint32_t img_u32, uint32_t dcol, bool first, int ub, Next next) {
+  // builders: publish image buffer k (this thread's rows are written).  Non-blocking, except that a buffer is not
+  // published a second time before the issuing thread has SEEN the first publication: an mbarrier wait can only
+  // tell adjacent phases apart, and the block loops of the backward kernel publish the same (read-only) images
+  // for consecutive GEMMs without waiting for MMA completion in between.
+  __device__ __forceinline__ void publish(int k) {
+    if ((anypub >> k) & 1u) mbar_wait_warp(taken + k, ((npub >> k) & 1u) ^ 1u);   // previous publication of k was taken
+    anypub |= 1u << k;
+    npub ^= 1u << k;
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int slot = wpos & (SLOTS - 1);
-      const int creq = LA == 2 ? c2 : c1;                // chunk of round wpos + LA
-      if (creq >= 0) {
-        const int s2 = (wpos + LA) & (SLOTS - 1);        // last read by round wpos + LA - SLOTS
-        if (wpos + LA >= SLOTS) mbar_wait(wfree + s2, ((wpos + LA - SLOTS) / SLOTS) & 1);
-        request(creq, s2);
-      }
-      mbar_wait(wfull + slot, (wpos / SLOTS) & 1);
-      tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc(2, 128, 64);
-      const uint32_t wb = smem_u32(wring + slot * NT_WCH);
-      const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
-#pragma unroll
-      for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
-                     umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
-      umma_commit(wfree + slot);
-      if (ub >= 0) umma_commit(ubar + ub);
+    mbar_arrive(full + k);
+  }
+  // issuing thread: round r = the r-th image handed over (buffer r & 1); 12 MMAs against the round's weight chunk.
+  // ub >= 0: the MMAs issued so far arrive on user barrier ub when complete (at most one un-waited commit per barrier).
+  template <class Next>
+  __device__ __forceinline__ void mma_round(uint32_t img_u32, uint32_t dcol, bool first, int ub, Next next) {
+    const int slot = wpos & (SLOTS - 1);
+    const int creq = LA == 2 ? c2 : c1;                // chunk of round wpos + LA
+    if (creq >= 0) {
+      const int s2 = (wpos + LA) & (SLOTS - 1);        // last read by round wpos + LA - SLOTS
+      if (wpos + LA >= SLOTS) mbar_wait(wfree + s2, ((wpos + LA - SLOTS) / SLOTS) & 1);
+      request(creq, s2);
     }
+    mbar_wait(wfull + slot, (wpos / SLOTS) & 1);
+    mbar_wait(full + (wpos & 1), (wpos >> 1) & 1);
+    mbar_arrive(taken + (wpos & 1));
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc(2, 128, 64);
+    const uint32_t wb = smem_u32(wring + slot * NT_WCH);
+    const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma<true>(dcol, umma_desc_k_sw128(img_u32 + pp[pr] * NT_IMG + ks * 32),
+                   umma_desc_k_sw128(wb + pw[pr] * (64 * 128) + ks * 32), idesc, !(first && pr == 0 && ks == 0));
+    umma_commit(wfree + slot);
+    if (ub >= 0) umma_commit(ubar + ub);
     ++wpos;
     c0 = c1; c1 = c2; c2 = c2 >= 0 ? next(c2) : -1;
   }
@@ -154,7 +173,7 @@ struct NodePipe {
 };
 
 template <int SLOTS>
-__global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(NodeFwdArgs a) {
+__global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post(NodeFwdArgs a) {
   const int nrows_real = a.hdr ? a.hdr->R : a.R;
   if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
@@ -163,11 +182,11 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(No
   uint8_t* wring = base + 4 * NT_IMG;                    // SLOTS weight chunk slots of 16 KB
   float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
   const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
-  for (int t = tid; t < NT_VEC; t += NT_TILE) {
+  for (int t = tid; t < NT_VEC; t += NT_THREADS) {
     const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
     svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
   }
@@ -175,8 +194,9 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(No
   auto next_w = [&](int k) { return k + 1 < n_chunks ? k + 1 : -1; };
   NodePipe<SLOTS> pp;
   pp.wring = wring; pp.wfull = bars; pp.wfree = bars + NT_MAXSLOTS; pp.ubar = bars + 2 * NT_MAXSLOTS; pp.wimg = a.wimg;
+  pp.full = bars + 2 * NT_MAXSLOTS + NT_UBARS; pp.taken = pp.full + 2; pp.npub = 0; pp.anypub = 0;
   pp.wpos = 0; pp.c0 = 0; pp.c1 = 1; pp.c2 = 2; pp.uph = 0;
-  if (tid == 0) {
+  if (tid == NT_TILE) {
     pp.init_barriers();
     pp.request(0, 0);
     if (SLOTS == 4) pp.request(1, 1);
@@ -191,7 +211,19 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(No
   uint8_t* const img_p[2] = {imgs, imgs + 2 * NT_IMG};
   const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
               *s_vel2 = svec + 320, *s_wv = svec + 384;
+  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
 
+  if (warp == 4) {
+    // ---------------- issuing warp: the fixed sequence of rounds — post0 (8, -> D0), post2 (2, -> D1), node0 (12, -> D0),
+    // node2 (2, -> D1), vel0 (2, -> D0, with a velocity gate); image buffer and user barrier = round parity
+    if ((tid & 31) == 0) {
+      for (int r = 0; r < n_chunks; ++r) {
+        const bool to_d1 = (r >= 8 && r < 10) || (r >= 22 && r < 24);
+        const bool first = r == 0 || r == 8 || r == 10 || r == 22 || r == 24;
+        pp.mma_round(img_u32[r & 1], to_d1 ? D1 : D0, first, r & 1, next_w);
+      }
+    }
+  } else {
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < nrows_real;
   const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
@@ -205,13 +237,12 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(No
     den2 = ms + 1e-10f;    // layers.py:221
   }
   const float inv_den = 1.0f / den;
-  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   float* ns = (a.stash && valid) ? a.stash + row * NS_LD : nullptr;   // this atom's row of the fwd -> bwd stash
   // Image buffer k = round parity; user barrier k tracks the last round that read image k.
   // busy: bit k set while a round on image k is un-waited.
   uint32_t busy = 0;
   auto acquire = [&](int k) { if (busy & (1u << k)) { pp.wait(k); busy &= ~(1u << k); } };
-  auto launch = [&](int k, uint32_t dcol, bool first) { pp.issue(img_u32[k], dcol, first, k, next_w); busy |= 1u << k; };
+  auto launch = [&](int k, uint32_t, bool) { pp.publish(k); busy |= 1u << k; };   // the issuing warp knows the rest
   auto drain = [&]() { acquire(0); acquire(1); };       // every MMA issued so far is complete (results readable)
 
   // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256 -> D0
@@ -403,6 +434,7 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post(No
       a.x_out[row * 3] = xr[0] + vn0; a.x_out[row * 3 + 1] = xr[1] + vn1; a.x_out[row * 3 + 2] = xr[2] + vn2;
     }
   }
+  }   // builders
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<128>(tmem_base);
@@ -438,7 +470,7 @@ __device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     
 }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+__global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post_bwd(NodeBwdArgs a) {
   const int nrows_real = a.hdr ? a.hdr->R : a.R;
   if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
@@ -448,10 +480,10 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
   uint8_t* wring = imgB + 2 * NT_IMG;                    // SLOTS weight chunk slots of 16 KB
   float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
-  for (int t = tid; t < NT_VEC; t += NT_TILE) {
+  for (int t = tid; t < NT_VEC; t += NT_THREADS) {
     const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
     svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
   }
@@ -466,9 +498,10 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
   };
   NodePipe<SLOTS> pp;
   pp.wring = wring; pp.wfull = bars; pp.wfree = bars + NT_MAXSLOTS; pp.ubar = bars + 2 * NT_MAXSLOTS; pp.wimg = a.wimg;
+  pp.full = bars + 2 * NT_MAXSLOTS + NT_UBARS; pp.taken = pp.full + 2; pp.npub = 0; pp.anypub = 0;
   pp.wpos = 0; pp.uph = 0;
   pp.c0 = uv ? NTB_VEL0T : NTB_NODE2T; pp.c1 = next_w(pp.c0); pp.c2 = next_w(pp.c1);
-  if (tid == 0) {
+  if (tid == NT_TILE) {
     pp.init_barriers();
     pp.request(pp.c0, 0);
     if (SLOTS == 4) pp.request(pp.c1, 1);
@@ -483,11 +516,26 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
   const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
               *s_vel2 = svec + 320, *s_wv = svec + 384;
   (void)s_bp1; (void)s_bp2; (void)s_bn1; (void)s_bn2; (void)s_bv1;
+  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   // One GEMM of the chain = the pair (imgA, imgB) = K 64 against two weight chunks; it commits to user barrier ub.
-  auto run_pair = [&](uint32_t dcol, int ub) {
-    pp.issue(imgA_u32, dcol, true, -1, next_w);
-    pp.issue(imgB_u32, dcol, false, ub, next_w);
-  };
+  if (warp == 4) {
+    // ---------------- issuing warp: vel0^T (with a gate), node2^T, six blocks of node0^T, then post2^T and four blocks
+    // of post0^T (with spatial attention); blocks alternate D0 / D1 and user barriers 0 / 1
+    if ((tid & 31) == 0) {
+      auto pair = [&](uint32_t dcol, int ub) {
+        pp.mma_round(imgA_u32, dcol, true, -1, next_w);
+        pp.mma_round(imgB_u32, dcol, false, ub, next_w);
+      };
+      if (uv) pair(D0, 0);
+      pair(D1, 0);
+      for (int b = 0; b < 6; ++b) pair((b & 1) ? D1 : D0, b & 1);
+      if (spatial) {
+        pair(D0, 0);
+        for (int b = 0; b < 4; ++b) pair((b & 1) ? D1 : D0, b & 1);
+      }
+    }
+  } else {
+  auto run_pair = [&](uint32_t, int) { pp.publish(0); pp.publish(1); };   // the issuing warp knows destination and barrier
 
   const int n = blockIdx.x * NT_TILE + tid;
   const bool valid = n < nrows_real;
@@ -502,7 +550,6 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
     den2 = ms + 1e-10f;
   }
   const float inv_den = 1.0f / den;
-  const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   float* nb = a.nbuf ? a.nbuf + row * NB_LD : nullptr;
   const bool rec = nb != nullptr && valid;
 
@@ -694,8 +741,9 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
     const float k2 = 2.0f * inv_den * inv_den, q0 = gdv0 / den2, q1 = gdv1 / den2, q2 = gdv2 / den2;
     // same look-ahead over the four blocks; the 24 row loads of ssum for the next 32 coefficients are issued
     // before the current ones are consumed, so they are in flight during the barrier wait and the TMEM load
+    // (SLOTS == 2, the two-CTAs-per-SM variant, has 200 registers per thread: it loads the rows where they are used)
     float4 sreg[24];
-    {
+    if constexpr (SLOTS == 4) {
       const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256) * 3);
 #pragma unroll
       for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
@@ -712,12 +760,18 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
         tmem_ld_wait();
         const int c0 = b * 64 + c * 32;
         float4 scur[24];
+        if constexpr (SLOTS == 4) {
 #pragma unroll
-        for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
-        if (c0 + 32 < 256) {
-          const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0 + 32) * 3);
+          for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
+          if (c0 + 32 < 256) {
+            const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0 + 32) * 3);
 #pragma unroll
-          for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+          }
+        } else {
+          const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0) * 3);
+#pragma unroll
+          for (int q = 0; q < 24; ++q) scur[q] = __ldg(sp + q);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -741,6 +795,7 @@ __global__ void __launch_bounds__(NT_TILE, SLOTS == 2 ? 2 : 1) k_tc_node_post_bw
     for (int c = 0; c < 256; ++c) Trow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (valid) a.tmax[row] = tmx;
+  }   // builders
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<128>(tmem_base);
@@ -797,13 +852,13 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   a.nbuf = g ? sc.nbuf : nullptr;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
   const bool deep = tiles <= 2 * node_num_sms();        // few tiles: latency configuration (see NodePipe)
-  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 128 + 1024;
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
   { const int rc = deep ? smem_optin(k_tc_node_post_bwd<4>, smem, optin4) : smem_optin(k_tc_node_post_bwd<2>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(7, d.R, st);
-    if (deep) k_tc_node_post_bwd<4><<<tiles, NT_TILE, smem, st>>>(a);
-    else k_tc_node_post_bwd<2><<<tiles, NT_TILE, smem, st>>>(a);
+    if (deep) k_tc_node_post_bwd<4><<<tiles, NT_THREADS, smem, st>>>(a);
+    else k_tc_node_post_bwd<2><<<tiles, NT_THREADS, smem, st>>>(a);
   }
   if (wvg) k_wv_grad<<<(d.R + 15) / 16, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 2 : 1);
@@ -836,13 +891,13 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.h_out = h_out; a.x_out = x_out; a.v_out = v_out; a.stash = sv.nstash;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
   const bool deep = tiles <= 2 * node_num_sms();
-  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 128 + 1024;
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
   { const int rc = deep ? smem_optin(k_tc_node_post<4>, smem, optin4) : smem_optin(k_tc_node_post<2>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(6, d.R, st);
-    if (deep) k_tc_node_post<4><<<tiles, NT_TILE, smem, st>>>(a);
-    else k_tc_node_post<2><<<tiles, NT_TILE, smem, st>>>(a);
+    if (deep) k_tc_node_post<4><<<tiles, NT_THREADS, smem, st>>>(a);
+    else k_tc_node_post<2><<<tiles, NT_THREADS, smem, st>>>(a);
   }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());

@@ -15,13 +15,13 @@
 
 namespace ffi = xla::ffi;
 
-static SakeDims make_dims(const ffi::AnyBuffer& h, int32_t heads, int32_t n_rbf, int32_t flags, float cut_lo = 0.f,
-                          float cut_hi = 5.f) {
+static SakeDims make_dims(const ffi::AnyBuffer& h, int32_t heads, int32_t n_rbf, int32_t flags, int32_t engine = SAKE_ENGINE_AUTO,
+                          float cut_lo = 0.f, float cut_hi = 5.f) {
   auto dims = h.dimensions();            // [B, N, H] (leading dims flattened on the Python side)
   SakeDims d;
   std::memset(&d, 0, sizeof(d));
   d.B = (int32_t)dims[0]; d.N = (int32_t)dims[1]; d.H = (int32_t)dims[2];
-  d.A = heads; d.K = n_rbf; d.flags = flags; d.engine = SAKE_ENGINE_AUTO;
+  d.A = heads; d.K = n_rbf; d.flags = flags; d.engine = engine;   // SAKE_ENGINE_* (AUTO = fp32-parity split when H = 64, A = 4)
   d.cutoff_lower = cut_lo; d.cutoff_upper = cut_hi;      // read only with SAKE_COSINE_CUTOFF in flags
   return d;
 }
@@ -30,8 +30,8 @@ static const float* opt(const ffi::AnyBuffer& b) { return b.element_count() ? (c
 static ffi::Error FwdImpl(cudaStream_t stream, ffi::AnyBuffer h, ffi::AnyBuffer x, ffi::AnyBuffer v, ffi::AnyBuffer mask,
                           ffi::RemainingArgs leaves, ffi::Result<ffi::AnyBuffer> h2, ffi::Result<ffi::AnyBuffer> x2,
                           ffi::Result<ffi::AnyBuffer> v2, ffi::Result<ffi::AnyBuffer> saved,
-                          ffi::Result<ffi::AnyBuffer> scratch, int32_t n_heads, int32_t n_rbf, int32_t flags) {
-  SakeDims d = make_dims(h, n_heads, n_rbf, flags);
+                          ffi::Result<ffi::AnyBuffer> scratch, int32_t n_heads, int32_t n_rbf, int32_t flags, int32_t engine) {
+  SakeDims d = make_dims(h, n_heads, n_rbf, flags, engine);
   SakeLayerParams p;
   const float** pp = reinterpret_cast<const float**>(&p);
   for (size_t i = 0; i < sizeof(p) / sizeof(float*); ++i) {
@@ -52,13 +52,13 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(SakeLayerFwd, FwdImpl,
                                   .RemainingArgs()
                                   .Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>()
                                   .Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>()
-                                  .Attr<int32_t>("n_heads").Attr<int32_t>("n_rbf").Attr<int32_t>("flags"));
+                                  .Attr<int32_t>("n_heads").Attr<int32_t>("n_rbf").Attr<int32_t>("flags").Attr<int32_t>("engine"));
 
 static ffi::Error BwdImpl(cudaStream_t stream, ffi::AnyBuffer h, ffi::AnyBuffer x, ffi::AnyBuffer v, ffi::AnyBuffer mask,
                           ffi::AnyBuffer saved, ffi::AnyBuffer dh2, ffi::AnyBuffer dx2, ffi::AnyBuffer dv2,
                           ffi::RemainingArgs leaves, ffi::RemainingRets rets, int32_t n_heads, int32_t n_rbf,
-                          int32_t flags) {
-  SakeDims d = make_dims(h, n_heads, n_rbf, flags);
+                          int32_t flags, int32_t engine) {
+  SakeDims d = make_dims(h, n_heads, n_rbf, flags, engine);
   constexpr size_t NL = sizeof(SakeLayerParams) / sizeof(float*);
   SakeLayerParams p;
   SakeLayerGrads g;
@@ -70,7 +70,8 @@ static ffi::Error BwdImpl(cudaStream_t stream, ffi::AnyBuffer h, ffi::AnyBuffer 
     auto r = rets.get<ffi::AnyBuffer>(3 + i);
     pp[i] = (b.has_value() && b->element_count()) ? (const float*)b->untyped_data() : nullptr;
     gp[i] = (r.has_value() && (*r)->element_count()) ? (float*)(*r)->untyped_data() : nullptr;
-    if (gp[i]) cudaMemsetAsync(gp[i], 0, (*r)->size_bytes(), stream);     // the C ABI accumulates
+    if (gp[i] && cudaMemsetAsync(gp[i], 0, (*r)->size_bytes(), stream) != cudaSuccess)      // the C ABI accumulates
+      return ffi::Error::Internal("cudaMemsetAsync of a gradient buffer failed");
   }
   auto dh = *rets.get<ffi::AnyBuffer>(0);
   auto dx = *rets.get<ffi::AnyBuffer>(1);
@@ -91,5 +92,5 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(SakeLayerBwd, BwdImpl,
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   .RemainingArgs()
                                   .RemainingRets()
-                                  .Attr<int32_t>("n_heads").Attr<int32_t>("n_rbf").Attr<int32_t>("flags"));
+                                  .Attr<int32_t>("n_heads").Attr<int32_t>("n_rbf").Attr<int32_t>("flags").Attr<int32_t>("engine"));
 #endif  // SAKE_HAVE_XLA_FFI

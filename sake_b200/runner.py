@@ -67,7 +67,7 @@ class ParamSet:
 
 class ModelRunner:
     def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
-                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=False):
+                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=False, async_prep=True):
         """masked: QM9-style padded batch with the reference's float mask = outer(m, m) (every kernel computes
         all N^2 pairs of the padded width and multiplies by the mask, like the reference).
         ragged: the same padded batch, but only the n_real[b] real atoms of every molecule are stored and
@@ -131,6 +131,14 @@ class ModelRunner:
             for d in self.dims:
                 d.flags |= _lib.SAKE_WEIGHTS_PREPARED
             self.refresh_weights()
+        # training: the parameters change every step, so the images are rebuilt every step — on a side stream, layer
+        # by layer, under the forward kernels of the earlier layers (layer l's forward waits for its own event)
+        self.async_prep = bool(async_prep and train and self.engine != "fp32")
+        if self.async_prep:
+            self.prep_stream = torch.cuda.Stream(device=dev)
+            self.prep_events = [torch.cuda.Event() for _ in range(self.L)]
+            self.dims_prepared = [_lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags | _lib.SAKE_WEIGHTS_PREPARED, d.engine,
+                                                d.reserved, d.cutoff_lower, d.cutoff_upper) for d in self.dims]
         nscr = max(max(ops.scratch_bytes(d, 0, 0), ops.scratch_bytes(d, 1, int(train))) for d in self.dims)
         self.scratch = ops._buf(nscr, dev)
         # defer_dw (opt-in): the weight-gradient contractions of layer l run on the library's side stream under the
@@ -209,6 +217,16 @@ class ModelRunner:
         rg = self.rg
         # another model's parameters through this runner's buffers (flows): the images in `saved` are not theirs
         dims = self.dims_unprepared if foreign else self.dims
+        async_prep = self.async_prep and not foreign
+        if async_prep:
+            main = torch.cuda.current_stream()
+            self.prep_stream.wait_stream(main)            # after the optimiser step that produced these parameters
+            with torch.cuda.stream(self.prep_stream):
+                for l in range(self.L):
+                    check(lib.sake_layer_prepare(C.byref(self.dims[l]), C.byref(pset.ps[l]), ops._ptr(self.saved[l]),
+                                                 self.saved[l].numel(), ops._stream()), "sake_layer_prepare")
+                    self.prep_events[l].record()
+            dims = self.dims_prepared
         if self.ragged:
             self._ragged_inputs()
         ops.dense_fwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.hs[0], 0, rg)
@@ -216,6 +234,8 @@ class ModelRunner:
             v_in = self.vs[l] if self.has_v[l] else None
             upd = self.model.update_list[l]
             v_out = self.vs[l + 1] if (upd or v_in is not None) else None
+            if async_prep:
+                torch.cuda.current_stream().wait_event(self.prep_events[l])
             ops.layer_fwd_raw(dims[l], pset.ps[l], self.hs[l], self.xs[l], v_in, self.mask,
                               self.hs[l + 1], self.xs[l + 1], v_out, self.saved[l], self.scratch, rg)
         ops.dense_fwd_raw(self.hs[self.L], p["embedding_out/layers_0/kernel"],
