@@ -134,14 +134,13 @@ static int resolve_engine(const SakeDims* s, const Dims& d) {
   return SAKE_EINVAL;
 }
 
-struct SavedLayout { size_t e, att, logit, emax, ssum, he, nodeproj, nstash, wmix, wedge, wnode, nodeWT, total; };
+struct SavedLayout { size_t e, att, logit, ssum, he, nodeproj, nstash, wmix, wedge, wnode, nodeWT, total; };
 static SavedLayout saved_layout(const Dims& d, int engine) {
   SavedLayout L;
   size_t o = 0;
   L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
   L.att = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
   L.logit = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
-  L.emax = o; if (engine != SAKE_ENGINE_FP32) o += align_up(sizeof(float) * (size_t)d.P);
   L.ssum = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
   L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
   L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
@@ -165,7 +164,6 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge, int engine) {
   s.e = (float*)(b + L.e); s.att = (float*)(b + L.att); s.ssum = (float*)(b + L.ssum);
   s.logit = tc_edge ? (float*)(b + L.logit) : s.att;   // tcgen05 edge path keeps the logits for the backward pass
   s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj); s.nstash = (float*)(b + L.nstash);
-  s.emax = (float*)(b + L.emax);
   s.wmix = b + L.wmix; s.wedge = b + L.wedge; s.wnode = b + L.wnode; s.nodeWT = (float*)(b + L.nodeWT);
   return s;
 }

@@ -70,7 +70,6 @@ struct Saved {
   float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
   float* he;        // [R,C]   aggregate (layers.py:135-140)
   float* nodeproj;  // [R,NP]
-  float* emax;      // [P]     max |e| of the pair's edge-feature row (tc_edge forward -> operand scale of the mix forward)
   float* nstash;    // [R,NS_LD] per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
   // tcgen05 engines: operand images of the layer's weights, built ONCE by the forward call and reused by the
   // backward call of the same step (round 1 rebuilt them in both: 5 + 5 small launches per layer)

@@ -106,7 +106,6 @@ struct EdgeArgs {
   const float *x, *mask, *proj;
   EdgeW w;
   float *e_out, *logit_out;            // forward outputs  [P,64], [P,4]
-  float* emax_out;                     // forward output   [P] max |e| of the row (scale of the mix kernel's fp16 operand)
   float* ge;                           // backward input   [P,64] cotangent of e through x_mixing / aggregate; the
                                        // attention-logit term W_s g_q is added here (written back when training)
   const float *gdir, *gq;              // backward inputs  [P,3], [P,4] (cotangent of the pre-celu logits)
@@ -330,7 +329,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       }
       run_chunk(tcol + 0, sW2, 1, 80, idesc80);                            // E' (chunk 1)
       // ---------------- (e) e = E' + b2 ; logits = celu(q) - 1e5*diag - 1e5*(1-m)  (layers.py:24,155-165)
-      float emx = 0.f;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float v[32];
@@ -341,14 +339,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int f0 = half * 32 + 4 * u;
-            const float4 ev = make_float4(v[4 * u] + s_b2[f0], v[4 * u + 1] + s_b2[f0 + 1], v[4 * u + 2] + s_b2[f0 + 2],
-                                          v[4 * u + 3] + s_b2[f0 + 3]);
-            o[u] = ev;
-            emx = fmaxf(fmaxf(emx, fmaxf(fabsf(ev.x), fabsf(ev.y))), fmaxf(fabsf(ev.z), fabsf(ev.w)));
+            o[u] = make_float4(v[4 * u] + s_b2[f0], v[4 * u + 1] + s_b2[f0 + 1], v[4 * u + 2] + s_b2[f0 + 2],
+                               v[4 * u + 3] + s_b2[f0 + 3]);
           }
         }
       }
-      if (valid) a.emax_out[prx] = emx;
       {
         float v[16];
         tmem_ld16(lane_addr + 64, v);
@@ -688,7 +683,7 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
   a.K = d.K; a.Kp = d.Kp; a.NP = d.NP;
   a.x = x; a.mask = mask; a.proj = sv.nodeproj; a.w = w;
   a.pair_u = d.pair_u; a.pair_p = d.pair_p;
-  a.e_out = sv.e; a.logit_out = sv.logit; a.emax_out = sv.emax;
+  a.e_out = sv.e; a.logit_out = sv.logit;
   const size_t smem = WA_BYTES + WB_BYTES + EDGE_GROUPS * EG_IMG + EVEC * 4 + 64;
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_edge<false>, smem, optin); if (rc) return rc; }

@@ -22,7 +22,7 @@ using namespace tc;
 constexpr int CC = 256;              // C = A*H (the engine is specialised to H=64, A=4)
 constexpr int P_IMG = TILE * 128;    // bytes of one pair-side chunk image   (128 rows x 128 B)
 constexpr int W_IMG = CC * 128;      // bytes of one weight-side chunk image (256 rows x 128 B)
-constexpr int NTHREADS = 576;        // forward: 18 warps: 0 TMA producer, 1 MMA issuer, 2-9 builders (two per pair row), 10-17 epilogue
+constexpr int NTHREADS = 448;        // forward: 14 warps: 0 TMA producer, 1 MMA issuer, 2-5 builders, 6-13 epilogue
 constexpr int BWD_THREADS = 512;     // backward: 4 warpgroups: {TMA, MMA, 2 idle}, builders, 2 x epilogue (setmaxnreg needs whole groups)
 
 template <int ENGINE> struct Cfg;
@@ -303,14 +303,14 @@ __device__ __forceinline__ void epi_fwd_chunk(const float (&v)[32], const float4
 template <int ENGINE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
-             const float* __restrict__ att, const float* __restrict__ emax, const uint8_t* __restrict__ w1img,
-             const float* __restrict__ wscale, float* __restrict__ ssum, int dbg_wsplits) {
+             const float* __restrict__ att, const uint8_t* __restrict__ w1img, const float* __restrict__ wscale,
+             float* __restrict__ ssum, int dbg_wsplits) {
   using CF = Cfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
   Smem<CF> sm(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 256); mbar_init(sm.empty + s, 1); }
+    for (int s = 0; s < CF::NSTAGE; ++s) { mbar_init(sm.full_w + s, 1); mbar_init(sm.full_e + s, 128); mbar_init(sm.empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(sm.acc_full + b, 1); mbar_init(sm.acc_empty + b, 256); }
     fence_barrier_init();
   }
@@ -383,16 +383,9 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         atomicAdd(&g_mma_wait[4], (unsigned long long)ntl);
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 6) {
     // ------------------------------------------------------------ builders: E image + pair geometry
-    // Two threads per pair row (warps 2-5: half 0, warps 6-9: half 1): each builds units [4 hf, 4 hf + 4) of every
-    // K-chunk from its 32 of the row's 64 edge features.  One warp per scheduler could not hide the latency of the
-    // split / pack chains (12.8 K cycles per tile against 6.1 K of MMA work, scripts/mma_wait.py); the row's
-    // power-of-two scale needs max |e| of the WHOLE row, which the edge kernel leaves in saved.emax.
-    const int bw = warp - 2, hf = bw >> 2;
-    const int p = (bw & 3) * 32 + lane;
-    constexpr int EPC = CF::KCH / 4;                // edge features per K-chunk (16: 16-bit formats, 8: tf32)
-    constexpr int EPH = EPC / 2;                    // ... per half
+    const int p = (warp - 2) * 32 + lane;
     int pos = 0;
     for (int it = 0; it < ntl; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -406,67 +399,48 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         int row2, j2;
         long long px2;
         tile_pair(tile_desc(g, tile + gridDim.x), p, v2, row2, j2, px2);
-        if (v2) { prefetch_l2(e + px2 * 64 + hf * 32); if (hf == 0) prefetch_l2(att + px2 * 4); }
+        if (v2) { prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4); }
       }
-      float ev[CF::NCHUNK * EPH];                   // this half's 32 features, chunk-major
+      float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
-      float mx = 0.f;
       if (valid) {
         at = *reinterpret_cast<const float4*>(att + prx * 4);
-        mx = __ldg(emax + prx);
+        const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
 #pragma unroll
-        for (int kc = 0; kc < CF::NCHUNK; ++kc) {
-          const float4* ep = reinterpret_cast<const float4*>(e + prx * 64 + kc * EPC + hf * EPH);
-#pragma unroll
-          for (int q = 0; q < EPH / 4; ++q) {
-            const float4 t4 = __ldg(ep + q);
-            ev[kc * EPH + 4 * q] = t4.x; ev[kc * EPH + 4 * q + 1] = t4.y; ev[kc * EPH + 4 * q + 2] = t4.z; ev[kc * EPH + 4 * q + 3] = t4.w;
-          }
+        for (int q = 0; q < 16; ++q) {
+          float4 t4 = __ldg(ep + q);
+          ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
         }
-        if (hf == 0) {
-          const float* xi = x + (size_t)row * 3;
-          const float* xj = x + (size_t)(geom_mol0(g, row) + j) * 3;
-          const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
-          const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);   // functional.py:14-17
-          const float inv = 1.0f / (nrm + 1e-5f);                                      // layers.py:115
-          const float m = mask ? mask[prx] : 1.0f;
-          dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, 1.0f);
-        }
+        const float* xi = x + (size_t)row * 3;
+        const float* xj = x + (size_t)(geom_mol0(g, row) + j) * 3;
+        const float r0 = xj[0] - xi[0], r1 = xj[1] - xi[1], r2 = xj[2] - xi[2];
+        const float nrm = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 0.f) + 1e-5f);   // functional.py:14-17
+        const float inv = 1.0f / (nrm + 1e-5f);                                      // layers.py:115
+        const float m = mask ? mask[prx] : 1.0f;
+        dm = make_float4(r0 * inv * m, r1 * inv * m, r2 * inv * m, 1.0f);
       } else {
 #pragma unroll
-        for (int q = 0; q < CF::NCHUNK * EPH; ++q) ev[q] = 0.f;
+        for (int q = 0; q < 64; ++q) ev[q] = 0.f;
       }
       float inv_s = 1.0f;
       if constexpr (CF::F16) {                      // normalise the row E = e (x) att (exact 2^k, applied through att)
+        float mx = 0.f;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) mx = fmaxf(mx, fabsf(ev[q]));
         float sc;
         pow2_norm(mx * fmaxf(fmaxf(fabsf(at.x), fabsf(at.y)), fmaxf(fabsf(at.z), fabsf(at.w))), sc, inv_s);
         at.x *= sc; at.y *= sc; at.z *= sc; at.w *= sc;
         inv_s *= wscale[1];                         // ... and undo the weight-image scale with the same factor
       }
       mbar_wait_warp(sm.acc_empty + buf, (use & 1) ^ 1);     // epilogue of the tile that last used dirm[buf] is done
-      if (hf == 0) {
-        dm.w = inv_s;                                        // fp16-split engine: undoes the E row scale
-        sm.dirm[buf * TILE + p] = dm;
-      }
+      dm.w = inv_s;                                          // fp16-split engine: undoes the E row scale
+      sm.dirm[buf * TILE + p] = dm;
 #pragma unroll
       for (int kc = 0; kc < CF::NCHUNK; ++kc, ++pos) {
         const int s = pos % CF::NSTAGE, n = pos / CF::NSTAGE;
         mbar_wait_warp(sm.empty + s, (n & 1) ^ 1);
-        uint8_t* img = sm.p_img(s);
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int u = 4 * hf + uu;
-          if constexpr (CF::TF32) {
-            const float ef = ev[kc * EPH + uu];
-            const float vals[4] = {ef * at.x, ef * at.y, ef * at.z, ef * at.w};
-            store_unit<CF>(img, p, u, vals);
-          } else {
-            const float e0 = ev[kc * EPH + 2 * uu], e1 = ev[kc * EPH + 2 * uu + 1];
-            const float vals[8] = {e0 * at.x, e0 * at.y, e0 * at.z, e0 * at.w, e1 * at.x, e1 * at.y, e1 * at.z, e1 * at.w};
-            store_unit<CF>(img, p, u, vals);
-          }
-        }
+        build_E_chunk<CF>(sm.p_img(s), p, kc, ev, at);
         fence_proxy_async();
         mbar_arrive(sm.full_e + s);
       }
@@ -477,7 +451,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
     // 32-column load is one branch-free block of 32 independent tanh chains (the segment boundaries are
     // handled by a warp-uniform bit mask on a clamped, possibly overlapping load), and the row sums are
     // written once per segment.
-    const int q = warp & 3, mh = (warp - 10) >> 2;
+    const int q = warp & 3, mh = (warp - 6) >> 2;
     const int cp = mh * 128 + q * 32 + lane;
     const bool accumulate = g.nseg > 1;
     for (int it = 0; it < ntl; ++it) {
@@ -994,9 +968,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
 // =================================================================================================
 // host side
 // =================================================================================================
-// (K <= 58: the tcgen05 edge kernel — whose row maxima the mix forward kernel reads — packs the RBF channels, the
-// distance and two bookkeeping columns into one 64-wide K block)
-bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4 && d.K <= 58; }
+bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
 
 int tc_debug_counters(unsigned long long* out8) {
   SAKE_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_mma_wait, sizeof(unsigned long long) * 8));
@@ -1049,7 +1021,7 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     ProfScope prof(1, d.P, st);
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
-    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, sv.emax, w1, wsc, sv.ssum, dbg);
+    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, wsc, sv.ssum, dbg);
   }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
