@@ -141,10 +141,10 @@ static SavedLayout saved_layout(const Dims& d, int engine) {
   L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
   L.att = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
   L.logit = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
-  L.ssum = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 3);
+  L.ssum = o; o += align_up(sizeof(float) * rows_pad128(d.R) * d.C * 3);
   L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
   L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
-  L.nstash = o; o += align_up(sizeof(float) * (size_t)d.R * NS_LD);
+  L.nstash = o; o += align_up(sizeof(float) * rows_pad128(d.R) * NS_LD);
   L.wmix = L.wedge = L.wnode = L.nodeWT = o;
   if (engine != SAKE_ENGINE_FP32) {
     // 1024-byte aligned: the images are sources of bulk (TMA) copies
@@ -165,6 +165,8 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge, int engine) {
   s.logit = tc_edge ? (float*)(b + L.logit) : s.att;   // tcgen05 edge path keeps the logits for the backward pass
   s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj); s.nstash = (float*)(b + L.nstash);
   s.wmix = b + L.wmix; s.wedge = b + L.wedge; s.wnode = b + L.wnode; s.nodeWT = (float*)(b + L.nodeWT);
+  // the tcgen05 node kernels read ssum tile-transposed; k_tc_mix_fwd writes it that way when they run
+  s.ssum_tt = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr);
   return s;
 }
 
@@ -262,7 +264,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (rc) return rc;
   if ((rc = gen_attn_fwd(d, x, mask, sv, st))) return rc;
   if (!d.spatial) {
-    SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
+    SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * rows_pad128(d.R) * d.C * 3, st));
   } else if (engine == SAKE_ENGINE_FP32) {
     if ((rc = gen_mix_fwd(d, *params, x, mask, sv, st))) return rc;
   } else {
@@ -347,7 +349,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
     rc = gen_node_post_bwd(d, *params, h, x, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, st);
   if (rc) return rc;
   XtgList xl;
-  if (sc.nbuf && (rc = tc_node_dw(d, *grads, sc, xl, st))) return rc;
+  if (sc.nbuf && (rc = tc_node_dw(d, h, sv, tc_node, *grads, sc, xl, st))) return rc;
   float* gWx = grads ? grads->x_mixing_kernel : nullptr;
   if (engine == SAKE_ENGINE_FP32 || !d.spatial) {
     if ((rc = gen_mix_bwd(d, *params, x, mask, sv, sc, gWx, st))) return rc;

@@ -68,9 +68,10 @@ struct Saved {
   float* att;       // [P,A]   combined attention (layers.py:205)
   float* logit;     // [P,A]   attention logits s (layers.py:155-165); aliases att on the generic engine (normalised in place)
   float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
+  int ssum_tt;      // ssum is tile-transposed [R/128][C/4][3][128][4] (tcgen05 mix + node kernels; tc_node.cu)
   float* he;        // [R,C]   aggregate (layers.py:135-140)
   float* nodeproj;  // [R,NP]
-  float* nstash;    // [R,NS_LD] per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
+  float* nstash;    // [R/128][NS_LD/4][128][4] (tile-transposed) per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
   // tcgen05 engines: operand images of the layer's weights, built ONCE by the forward call and reused by the
   // backward call of the same step (round 1 rebuilt them in both: 5 + 5 small launches per layer)
   void* wmix;       // x_mixing images for GEMM1 / GEMM2 + {scale, 1/scale}   (tc_mix.cu)
@@ -100,6 +101,7 @@ struct BwdScratch {
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline size_t rows_pad128(long long R) { return (size_t)((R + 127) / 128 * 128); }   // rows of a tile-transposed buffer
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
@@ -306,6 +308,7 @@ struct XtgArgs {
   const float* e; const float* att;    // X = e (x) att  (xw = 256, feature c = f*4 + head) when e != nullptr
   int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
   const float* G; int ldg; int gw;     // G source [P, gw]
+  int x_tt, g_tt;                      // > 0: the source is tile-transposed (tc_node.cu) with this many 16-byte units per row
   int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
   long long P, pairs_per_cta;          // ragged batches: P is the padded worst case, the real extent is *Pdev
   const long long* Pdev;               // device-resident K extent (RaggedHdr::P or ::R64), or NULL
@@ -317,7 +320,7 @@ struct XtgArgs {
 // All weight-gradient contractions of one layer backward are collected and run as ONE batched launch
 // (+ one reduction launch): blockIdx.y selects the problem.
 struct XtgList {
-  static constexpr int MAXP = 16;
+  static constexpr int MAXP = 20;
   XtgArgs a[MAXP];
   int n = 0;
   // small follow-up kernels that consume `extra` rows of some problems
@@ -361,7 +364,8 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
                       const float* dv_out, float* dh, float* dx, float* dv, const SakeLayerGrads* g,
                       const BwdScratch& sc, cudaStream_t st);
 size_t tc_node_dw_scratch_bytes(const Dims& d);
-int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st);
+int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, const SakeLayerGrads& g, const BwdScratch& sc,
+               XtgList& L, cudaStream_t st);
 int tc_node_pre_dw(const Dims& d, const float* h, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L);
 int gen_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* gWx, cudaStream_t st);

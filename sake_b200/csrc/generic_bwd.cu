@@ -1000,37 +1000,56 @@ __global__ void k_post_bias_finish(const float* __restrict__ tmp, float* __restr
   if (t < 64) gbp2[t] += tmp[t];
   else if (t < 128) gbp1[t - 64] += tmp[t];
 }
-size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) * (size_t)d.R * NB_LD) + 1024; }
+size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) * rows_pad128(d.R) * NB_LD) + 1024; }
 
-int tc_node_dw(const Dims& d, const SakeLayerGrads& g, const BwdScratch& sc, XtgList& L, cudaStream_t st) {
+// direct (the tcgen05 node kernels ran): the X operands are read where they live — h, saved.he and the forward
+// kernel's stash (saved.nstash, row stride NS_LD) — and the record holds the cotangents and nrm only; otherwise
+// (k_node_post_bwd, SAKE_NODE_TC=0) the record holds copies of everything.
+int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, const SakeLayerGrads& g, const BwdScratch& sc,
+               XtgList& L, cudaStream_t st) {
   const float* nb = sc.nbuf;
-  float* tmp = sc.nbuf + (size_t)d.R * NB_LD;          // [128] bias scratch
-  auto call = [&](const float* X, int xw, int ones, int mxpad, const float* G, int gw, int ng, float* out, int ldo,
+  float* tmp = sc.nbuf + rows_pad128(d.R) * NB_LD;     // [128] bias scratch
+  // a source: row-major (ld floats per row, tt = 0) or a field of a tile-transposed buffer (tt = units per row)
+  struct Src { const float* p; int ld, tt; };
+  auto rowmajor = [](const float* p, int ld) { return Src{p, ld, 0}; };
+  auto field = [](const float* buf, int col, int ld) { return Src{buf + (size_t)(col / 4) * 512, ld, ld / 4}; };
+  auto call = [&](Src X, int xw, int ones, int mxpad, Src G, int gw, int ng, float* out, int ldo,
                   int out_rows, int out_cols, float* extra, int extra_ld) {
     XtgArgs q;
     memset(&q, 0, sizeof(q));
-    q.X = X; q.ldx = NB_LD; q.xw = xw; q.ones_col = ones; q.G = G; q.ldg = NB_LD; q.gw = gw; q.MXpad = mxpad; q.NG = ng;
+    q.X = X.p; q.ldx = X.ld; q.x_tt = X.tt; q.xw = xw; q.ones_col = ones;
+    q.G = G.p; q.ldg = G.ld; q.g_tt = G.tt; q.gw = gw; q.MXpad = mxpad; q.NG = ng;
     q.P = d.R; q.Pdev = d.hdr ? &d.hdr->R64 : nullptr;
     q.out = out; q.ldo = ldo; q.out_rows = out_rows; q.out_cols = out_cols;
     q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld;
     return L.push(q);
   };
+  // record fields: tile-transposed when the tcgen05 node kernel wrote them, rows of NB_LD floats otherwise
+  auto rec = [&](int col) { return direct ? field(nb, col, NB_LD) : rowmajor(nb + col, NB_LD); };
+  auto stash = [&](int col) { return field(sv.nstash, col, NS_LD); };
   int rc = 0;
   // node_mlp (layers.py:58-66)
-  rc |= call(nb + NB_N1, 64, 64, 128, nb + NB_GT2, 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
-  rc |= call(nb + NB_CAT, 256, -1, 256, nb + NB_GT1, 64, 64, g.node0_kernel, 64, 256, 64, nullptr, 64);
-  rc |= call(nb + NB_CAT + 256, 128, 128, 256, nb + NB_GT1, 64, 64, g.node0_kernel + 256 * 64, 64, 128, 64, g.node0_bias, 64);
+  if (direct) {
+    rc |= call(stash(NS_N1), 64, 64, 128, rec(NB_GT2), 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
+    rc |= call(rowmajor(h, 64), 64, -1, 128, rec(NB_GT1), 64, 64, g.node0_kernel, 64, 64, 64, nullptr, 64);
+    rc |= call(rowmajor(sv.he, 256), 256, -1, 256, rec(NB_GT1), 64, 64, g.node0_kernel + 64 * 64, 64, 256, 64, nullptr, 64);
+    rc |= call(stash(NS_HCOMB), 64, 64, 128, rec(NB_GT1), 64, 64, g.node0_kernel + 320 * 64, 64, 64, 64, g.node0_bias, 64);
+  } else {
+    rc |= call(rec(NB_N1), 64, 64, 128, rec(NB_GT2), 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
+    rc |= call(rec(NB_CAT), 256, -1, 256, rec(NB_GT1), 64, 64, g.node0_kernel, 64, 256, 64, nullptr, 64);
+    rc |= call(rec(NB_CAT + 256), 128, 128, 256, rec(NB_GT1), 64, 64, g.node0_kernel + 256 * 64, 64, 128, 64, g.node0_bias, 64);
+  }
   if (d.spatial) {
     // post_norm_mlp (layers.py:85-92); the ones-row of the first call carries both bias gradients
     SAKE_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 128, st));
-    rc |= call(nb + NB_HP1, 64, 64, 128, nb + NB_GTP2, 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128);
+    rc |= call(direct ? stash(NS_HP1) : rec(NB_HP1), 64, 64, 128, rec(NB_GTP2), 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128);
     L.post_tmp = tmp; L.g_post2_bias = g.post2_bias; L.g_post0_bias = g.post0_bias;
-    rc |= call(nb + NB_NRM, 256, -1, 256, nb + NB_GTP1, 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64);
+    rc |= call(rec(NB_NRM), 256, -1, 256, rec(NB_GTP1), 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64);
   }
   if (d.update && d.has_v) {
     // velocity_mlp (layers.py:69-76)
-    rc |= call(nb + NB_HOUT, 64, 64, 128, nb + NB_GTV, 64, 64, g.vel0_kernel, 64, 64, 64, g.vel0_bias, 64);
-    rc |= call(nb + NB_AV, 64, -1, 128, nb + NB_GY, 1, 16, g.vel2_kernel, 1, 64, 1, nullptr, 16);
+    rc |= call(direct ? stash(NS_HOUT) : rec(NB_HOUT), 64, 64, 128, rec(NB_GTV), 64, 64, g.vel0_kernel, 64, 64, 64, g.vel0_bias, 64);
+    rc |= call(direct ? stash(NS_AV) : rec(NB_AV), 64, -1, 128, rec(NB_GY), 1, 16, g.vel2_kernel, 1, 64, 1, nullptr, 16);
   }
   if (rc) { set_error("xtg list full"); return SAKE_EINVAL; }
   return 0;

@@ -270,9 +270,9 @@ __device__ unsigned long long g_mma_wait[8];
 // [12] E2 total; builder warp 2 lane 0: [13] ring waits [14] load+build
 __device__ unsigned long long g_bwd_wait[16];
 
-__device__ __noinline__ void emit_ssum(float* o, float s0, float s1, float s2, bool accumulate) {
-  if (accumulate) { atomicAdd(o, s0); atomicAdd(o + 1, s1); atomicAdd(o + 2, s2); }
-  else { o[0] = s0; o[1] = s1; o[2] = s2; }
+__device__ __noinline__ void emit_ssum(float* o, int ds, float s0, float s1, float s2, bool accumulate) {
+  if (accumulate) { atomicAdd(o, s0); atomicAdd(o + ds, s1); atomicAdd(o + 2 * ds, s2); }
+  else { o[0] = s0; o[ds] = s1; o[2 * ds] = s2; }
 }
 
 // 32 TMEM columns (= 32 pairs) of one coefficient: coef = tanh(z), s += dir*m*coef.  Straight-line code:
@@ -304,7 +304,7 @@ template <int ENGINE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ e,
              const float* __restrict__ att, const uint8_t* __restrict__ w1img, const float* __restrict__ wscale,
-             float* __restrict__ ssum, int dbg_wsplits) {
+             float* __restrict__ ssum, int ssum_tt, int dbg_wsplits) {
   using CF = Cfg<ENGINE>;
   extern __shared__ uint8_t smem_raw[];
   Smem<CF> sm(smem_raw);
@@ -477,7 +477,11 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           if (n == 32 && ls == c) epi_fwd_chunk<CF, false>(v, dmt + ls, 0u, s0, s1, s2);
           else epi_fwd_chunk<CF, true>(v, dmt + ls, (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (c - ls), s0, s1, s2);
         }
-        emit_ssum(ssum + ((size_t)(row0 + sg) * CC + cp) * 3, s0, s1, s2, accumulate);
+        // ssum_tt: the tile-transposed layout the tcgen05 node kernels read (tc_node.cu): [128-row tile][c'/4][d][row][c'%4]
+        const size_t orow = (size_t)(row0 + sg);
+        float* o = ssum_tt ? ssum + ((((orow >> 7) * 64 + (cp >> 2)) * 3) * 128 + (orow & 127)) * 4 + (cp & 3)
+                           : ssum + (orow * CC + cp) * 3;
+        emit_ssum(o, ssum_tt ? 512 : 1, s0, s1, s2, accumulate);
       }
       tc_fence_before();
       mbar_arrive(sm.acc_empty + buf);
@@ -1013,7 +1017,7 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
   TileGeom g = make_geom(d);
   float* wsc = reinterpret_cast<float*>(w2 + wimg_bytes<CF>());       // {scale, 1/scale} of the weight images
   if (!d.prepared) { const int rc = tc_mix_prepare(p, scratch, ENGINE, st); if (rc) return rc; }
-  if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * (size_t)d.R * d.C * 3, st));
+  if (g.nseg > 1) SAKE_CUDA_CHECK(cudaMemsetAsync(sv.ssum, 0, sizeof(float) * rows_pad128(d.R) * d.C * 3, st));
   static unsigned long long optin = 0;
   { const int rc = smem_optin(k_tc_mix_fwd<ENGINE>, smem_bytes<CF>(), optin); if (rc) return rc; }
   const int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
@@ -1021,7 +1025,7 @@ static int tc_fwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     ProfScope prof(1, d.P, st);
     static int dbg = -1;
     if (dbg < 0) { const char* s = getenv("SAKE_DEBUG_WSPLITS"); dbg = s ? atoi(s) : 0; }
-    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, wsc, sv.ssum, dbg);
+    k_tc_mix_fwd<ENGINE><<<grid, NTHREADS, smem_bytes<CF>(), st>>>(g, x, mask, sv.e, sv.att, w1, wsc, sv.ssum, sv.ssum_tt, dbg);
   }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());

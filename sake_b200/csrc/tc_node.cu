@@ -73,6 +73,18 @@ __device__ __forceinline__ void nt_store_unit(uint8_t* img, int row, int u, cons
   *reinterpret_cast<float4*>(img + NT_IMG + off) = lo;
 }
 
+// Tile-transposed per-atom buffers (stash, record, ssum): thread = atom, and the 16-byte unit u of atom t of tile b
+// sits at float4 index (b * U + u) * 128 + t, so that a warp's access to unit u is 512 contiguous bytes (4 L1
+// wavefronts instead of the 32 of a thread-per-row walk over row-major rows: the node kernels were bound by exactly
+// those wavefronts).  tc_xtg.cu reads the same layout (XtgArgs::x_tt / g_tt).
+__device__ __forceinline__ float4* tt_base(float* buf, int units, int tile, int t) {
+  return reinterpret_cast<float4*>(buf) + (size_t)tile * units * 128 + t;
+}
+__device__ __forceinline__ const float4* tt_base(const float* buf, int units, int tile, int t) {
+  return reinterpret_cast<const float4*>(buf) + (size_t)tile * units * 128 + t;
+}
+#define TT(q, col) (q)[((col) >> 2) * 128]            /* the float4 holding columns col .. col+3 (col % 4 == 0) */
+
 struct NodeFwdArgs {
   int R, N, update, has_v, spatial;
   const RaggedHdr* hdr; const int4* rowinfo;             // ragged batches (no mask): rows from hdr, n per row
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     den2 = ms + 1e-10f;    // layers.py:221
   }
   const float inv_den = 1.0f / den;
-  float* ns = (a.stash && valid) ? a.stash + row * NS_LD : nullptr;   // this atom's row of the fwd -> bwd stash
+  float4* ns = (a.stash && valid) ? tt_base(a.stash, NS_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's fwd -> bwd stash
   // Image buffer k = round parity; user barrier k tracks the last round that read image k.
   // busy: bit k set while a round on image k is un-waited.
   uint32_t busy = 0;
@@ -248,11 +260,12 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256 -> D0
   // the 24 row loads of chunk c+1 are issued before the hand-off of chunk c: their latency hides under its MMAs
   float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+  // ssum is tile-transposed (written so by k_tc_mix_fwd): unit (c'/4)*3 + d holds component d of four coefficients
   float4 sreg[24];
+  const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);
   {
-    const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256) * 3);
 #pragma unroll
-    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * 128);
   }
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {
@@ -260,12 +273,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     acquire(k);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      float s[12];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 t4 = sreg[u * 3 + q];
-        s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
-      }
+      const float4 t0 = sreg[u * 3], t1 = sreg[u * 3 + 1], t2 = sreg[u * 3 + 2];
+      const float s[12] = {t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z, t0.w, t1.w, t2.w};
       float vals[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -277,9 +286,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       nt_store_unit(img_p[k], tid, u, vals);
     }
     if (c + 1 < 8) {
-      const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + (c + 1) * 32) * 3);
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c + 1) * 24 + q) * 128);
     }
     launch(k, D0, c == 0);
   }
@@ -302,8 +310,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        *reinterpret_cast<float4*>(ns + NS_D + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        *reinterpret_cast<float4*>(ns + NS_HP1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_HP1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
       nt_store_unit(img_p[c], tid, u, vals);
     }
@@ -340,8 +348,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
           dvs[i] = spatial ? fdsilu_(z) : 0.f;
         }
         if (ns) {
-          *reinterpret_cast<float4*>(ns + NS_D + 64 + (c - 10) * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-          *reinterpret_cast<float4*>(ns + NS_HCOMB + (c - 10) * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+          TT(ns, NS_D + 64 + (c - 10) * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          TT(ns, NS_HCOMB + (c - 10) * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         }
         nt_store_unit(img_p[k], tid, u, vals);
       }
@@ -362,8 +370,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        *reinterpret_cast<float4*>(ns + NS_D + 128 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        *reinterpret_cast<float4*>(ns + NS_N1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + 128 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_N1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
       nt_store_unit(img_p[c], tid, u, vals);
     }
@@ -385,8 +393,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]; vals[i] = hin[i] + fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        *reinterpret_cast<float4*>(ns + NS_D + 192 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        *reinterpret_cast<float4*>(ns + NS_HOUT + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + 192 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_HOUT + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
       if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       if (uv) nt_store_unit(img_p[c], tid, u, vals);
@@ -411,13 +419,13 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
           y = fmaf(av[i], s_vel2[c * 32 + k], y);
         }
         if (ns) {
-          *reinterpret_cast<float4*>(ns + NS_D + 256 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-          *reinterpret_cast<float4*>(ns + NS_AV + c * 32 + 4 * u) = make_float4(av[0], av[1], av[2], av[3]);
+          TT(ns, NS_D + 256 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          TT(ns, NS_AV + c * 32 + 4 * u) = make_float4(av[0], av[1], av[2], av[3]);
         }
       }
     }
   }
-  if (ns) ns[NS_Y] = y;
+  if (ns) reinterpret_cast<float*>(&TT(ns, NS_Y))[0] = y;
   // ---------------- velocity / position update (layers.py:218-232)
   if (valid) {
     const float* xr = a.x + row * 3;
@@ -463,6 +471,10 @@ struct NodeBwdArgs {
   float *qv, *nbuf;                          // g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
 };
 
+__device__ __forceinline__ void st64_tt(float4* q, int col0, int c, const float* v32) {   // 32 floats of a tile-transposed row
+#pragma unroll
+  for (int u = 0; u < 8; ++u) TT(q, col0 + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
+}
 __device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     // 32 floats of a row block
 #pragma unroll
   for (int u = 0; u < 8; ++u)
@@ -550,51 +562,19 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     den2 = ms + 1e-10f;
   }
   const float inv_den = 1.0f / den;
-  float* nb = a.nbuf ? a.nbuf + row * NB_LD : nullptr;
+  float4* nb = a.nbuf ? tt_base(a.nbuf, NB_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's record (tile-transposed)
   const bool rec = nb != nullptr && valid;
 
   // =============================== forward activations: kept by k_tc_node_post ===============================
   // (round 1 recomputed the forward here: 26 of the kernel's 52 serial chunk-GEMM rounds, on a kernel that is
   // latency-bound at every size; the forward kernel now leaves silu' of the five hidden layers, the inputs of the
   // Dense layers and the gate logit in saved.nstash, 2.6 KB per atom)
-  const float* nd = a.stash + row * NS_LD;
-  if (rec) {
-    // X operands of the batched weight-gradient contractions (record layout NB_*): the inputs of every Dense layer
-    if (spatial) {
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                         // nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129)
-        const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c * 32) * 3);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float s[12];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float4 t4 = __ldg(sp + u * 3 + q);
-            s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
-          }
-          float vals[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
-            vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
-          }
-          *reinterpret_cast<float4*>(nb + NB_NRM + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-        }
-      }
-    }
-    auto copy64 = [&](float* dst, const float* src) {
-#pragma unroll
-      for (int u = 0; u < 16; ++u) *reinterpret_cast<float4*>(dst + 4 * u) = __ldg(reinterpret_cast<const float4*>(src) + u);
-    };
-    if (spatial) copy64(nb + NB_HP1, nd + NS_HP1);
-    copy64(nb + NB_CAT, a.h + row * 64);
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) copy64(nb + NB_CAT + 64 + 64 * q, a.he + row * 256 + 64 * q);
-    copy64(nb + NB_CAT + 320, nd + NS_HCOMB);
-    copy64(nb + NB_N1, nd + NS_N1);
-    if (uv) { copy64(nb + NB_HOUT, nd + NS_HOUT); copy64(nb + NB_AV, nd + NS_AV); }
-  }
-  const float y = nd[NS_Y];
+  const float4* nd = tt_base(a.stash, NS_LD / 4, blockIdx.x, valid ? tid : 0);
+  // The X operands of the batched weight-gradient contractions (the inputs of every Dense layer) are read by
+  // tc_node_dw where they already live: h, saved.he and the stash fields.  Only the cotangents (and nrm, which
+  // falls out of the T loop below) are written to the record: 2.3 KB per atom instead of 4.9 KB + 5.3 KB of
+  // thread-per-row copies in front of the chain.
+  const float y = reinterpret_cast<const float*>(&TT(nd, NS_Y))[0];
   // =============================== velocity / position update backward (layers.py:226-232) ===============================
   float gdv0 = 0.f, gdv1 = 0.f, gdv2 = 0.f, gy = 0.f;
   if (valid) {
@@ -615,7 +595,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     } else if (a.dv && hv) {
       a.dv[row * 3] = dvo0; a.dv[row * 3 + 1] = dvo1; a.dv[row * 3 + 2] = dvo2;          // v passes through
     }
-    if (rec && uv) nb[NB_GY] = gy;
+    if (rec && uv) reinterpret_cast<float*>(&TT(nb, NB_GY))[0] = gy;
     if (a.qv) *reinterpret_cast<float4*>(a.qv + row * 4) = make_float4(gdv0 / den2, gdv1 / den2, gdv2 / den2, 0.f);
   }
   // =============================== backward chain ===============================
@@ -632,11 +612,11 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       float gtv[32];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 d4 = *reinterpret_cast<const float4*>(nd + 256 + c * 32 + 4 * u);
+        const float4 d4 = TT(nd, 256 + c * 32 + 4 * u);
         gtv[4 * u] = s_vel2[c * 32 + 4 * u] * gy * d4.x; gtv[4 * u + 1] = s_vel2[c * 32 + 4 * u + 1] * gy * d4.y;
         gtv[4 * u + 2] = s_vel2[c * 32 + 4 * u + 2] * gy * d4.z; gtv[4 * u + 3] = s_vel2[c * 32 + 4 * u + 3] * gy * d4.w;
       }
-      if (rec) st64(nb + NB_GTV, c, gtv);
+      if (rec) st64_tt(nb, NB_GTV, c, gtv);
 #pragma unroll
       for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, gtv + 4 * u);
     }
@@ -657,11 +637,11 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     float g2[32];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 d4 = *reinterpret_cast<const float4*>(nd + 192 + c * 32 + 4 * u);
+      const float4 d4 = TT(nd, 192 + c * 32 + 4 * u);
       g2[4 * u] = gho[c * 32 + 4 * u] * d4.x; g2[4 * u + 1] = gho[c * 32 + 4 * u + 1] * d4.y;
       g2[4 * u + 2] = gho[c * 32 + 4 * u + 2] * d4.z; g2[4 * u + 3] = gho[c * 32 + 4 * u + 3] * d4.w;
     }
-    if (rec) st64(nb + NB_GT2, c, g2);
+    if (rec) st64_tt(nb, NB_GT2, c, g2);
 #pragma unroll
     for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, g2 + 4 * u);
   }
@@ -674,10 +654,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 d4 = *reinterpret_cast<const float4*>(nd + 128 + c * 32 + 4 * u);
+      const float4 d4 = TT(nd, 128 + c * 32 + 4 * u);
       v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
     }
-    if (rec) st64(nb + NB_GT1, c, v);
+    if (rec) st64_tt(nb, NB_GT1, c, v);
 #pragma unroll
     for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
   }
@@ -706,7 +686,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const float4 d4 = *reinterpret_cast<const float4*>(nd + 64 + c * 32 + 4 * u);
+          const float4 d4 = TT(nd, 64 + c * 32 + 4 * u);
           const float g0 = v[4 * u] * d4.x, g1 = v[4 * u + 1] * d4.y, g2 = v[4 * u + 2] * d4.z, g3 = v[4 * u + 3] * d4.w;
           if (c == 0) { gp2[4 * u] = g0; gp2[4 * u + 1] = g1; gp2[4 * u + 2] = g2; gp2[4 * u + 3] = g3; }
           else { gp2[32 + 4 * u] = g0; gp2[32 + 4 * u + 1] = g1; gp2[32 + 4 * u + 2] = g2; gp2[32 + 4 * u + 3] = g3; }
@@ -718,7 +698,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   float4* Trow = reinterpret_cast<float4*>(a.T) + row * 256;
   if (spatial) {
     // g_tp1 = (g_tp2 W_p2^T) * silu'(tp1)
-    if (rec) { st64(nb + NB_GTP2, 0, gp2); st64(nb + NB_GTP2, 1, gp2 + 32); }
+    if (rec) { st64_tt(nb, NB_GTP2, 0, gp2); st64_tt(nb, NB_GTP2, 1, gp2 + 32); }
 #pragma unroll
     for (int u = 0; u < 8; ++u) { nt_store_unit(imgA, tid, u, gp2 + 4 * u); nt_store_unit(imgB, tid, u, gp2 + 32 + 4 * u); }
     run_pair(D0, 0);
@@ -730,10 +710,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 d4 = *reinterpret_cast<const float4*>(nd + c * 32 + 4 * u);
+        const float4 d4 = TT(nd, c * 32 + 4 * u);
         v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
       }
-      if (rec) st64(nb + NB_GTP1, c, v);
+      if (rec) st64_tt(nb, NB_GTP1, c, v);
 #pragma unroll
       for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
     }
@@ -743,10 +723,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     // before the current ones are consumed, so they are in flight during the barrier wait and the TMEM load
     // (SLOTS == 2, the two-CTAs-per-SM variant, has 200 registers per thread: it loads the rows where they are used)
     float4 sreg[24];
+    const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);     // tile-transposed, see the forward kernel
     if constexpr (SLOTS == 4) {
-      const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256) * 3);
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * 128);
     }
     run_pair(D0, 0);
 #pragma unroll 1
@@ -764,30 +744,29 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
 #pragma unroll
           for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
           if (c0 + 32 < 256) {
-            const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0 + 32) * 3);
 #pragma unroll
-            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(sp + q);
+            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c0 / 32 + 1) * 24 + q) * 128);
           }
         } else {
-          const float4* sp = reinterpret_cast<const float4*>(a.ssum + (row * 256 + c0) * 3);
 #pragma unroll
-          for (int q = 0; q < 24; ++q) scur[q] = __ldg(sp + q);
+          for (int q = 0; q < 24; ++q) scur[q] = __ldg(ssq + ((c0 / 32) * 24 + q) * 128);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float s[12];
+          const float4 t0 = scur[u * 3], t1 = scur[u * 3 + 1], t2 = scur[u * 3 + 2];
+          const float s[12] = {t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z, t0.w, t1.w, t2.w};
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float4 t4 = scur[u * 3 + q];
-            s[4 * q] = t4.x; s[4 * q + 1] = t4.y; s[4 * q + 2] = t4.z; s[4 * q + 3] = t4.w;
-          }
+          float nrm[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float gk = k2 * v[4 * u + i], w = upd ? s_wv[c0 + 4 * u + i] : 0.f;
             const float t0 = fmaf(w, q0, gk * s[3 * i]), t1 = fmaf(w, q1, gk * s[3 * i + 1]), t2 = fmaf(w, q2, gk * s[3 * i + 2]);
             tmx = fmaxf(tmx, fmaxf(fabsf(t0), fmaxf(fabsf(t1), fabsf(t2))));
             if (valid) Trow[c0 + 4 * u + i] = make_float4(t0, t1, t2, 0.f);
+            const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
+            nrm[i] = a0 * a0 + a1 * a1 + a2 * a2;            // layers.py:123-129: the X operand of post0's weight gradient
           }
+          if (rec) TT(nb, NB_NRM + c0 + 4 * u) = make_float4(nrm[0], nrm[1], nrm[2], nrm[3]);
         }
       }
     }
@@ -811,8 +790,8 @@ __global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, co
   float acc = 0.f;
   for (int n = n0; n < n1; ++n) {
     const float4 q = *reinterpret_cast<const float4*>(qv + (size_t)n * 4);
-    const float* sp = ssum + ((size_t)n * 256 + c) * 3;
-    acc += sp[0] * q.x + sp[1] * q.y + sp[2] * q.z;
+    const float* sp = ssum + ((((size_t)(n >> 7) * 64 + (c >> 2)) * 3) * 128 + (n & 127)) * 4 + (c & 3);   // tile-transposed
+    acc += sp[0] * q.x + sp[512] * q.y + sp[1024] * q.z;
   }
   atomicAdd(gWv + c, acc);
 }

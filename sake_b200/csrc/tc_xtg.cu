@@ -214,15 +214,26 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
     // One definition path for the loop-carried registers (no per-row branches, which cost a register shuffle at
     // every merge): rows past the end (last stage of the grid only) read a page of zeros instead.
     // this thread's source rows for the next load; every stage bumps them by XKP rows
+    // Tile-transposed sources (x_tt / g_tt = 16-byte units per row of the buffer; written by the thread-per-atom node
+    // kernels so that THEIR accesses coalesce): unit u of row p sits at float4 index ((p >> 7) * U + u) * 128 + (p & 127).
+    // The two float4 of a thread are then 128 float4 apart, consecutive 64-feature blocks 2048, and a stage step is
+    // 32 rows inside a 128-row tile or a jump to the next tile.  Four consecutive rows are 64 contiguous bytes, so a
+    // warp touches 8 lines per load either way.
+    const bool xtt = !EMODE && a.x_tt > 0, gtt = !EMODE && a.g_tt > 0;
     long long pl = p_beg + r;
-    const float* xrow = EMODE ? a.e + pl * 64 + 2 * uu : a.X + pl * a.ldx + 8 * uu;
-    const float* grow = a.G + pl * a.ldg + 8 * uu;
+    const float* xrow = EMODE ? a.e + pl * 64 + 2 * uu
+                        : xtt ? a.X + ((((pl >> 7) * a.x_tt + 2 * uu) << 7) + (pl & 127)) * 4
+                              : a.X + pl * a.ldx + 8 * uu;
+    const float* grow = gtt ? a.G + ((((pl >> 7) * a.g_tt + 2 * uu) << 7) + (pl & 127)) * 4 : a.G + pl * a.ldg + 8 * uu;
     const float* arow = EMODE ? a.att + pl * 4 : nullptr;
     const long long xstep = EMODE ? (long long)XKP * 64 : (long long)XKP * a.ldx, gstep = (long long)XKP * a.ldg;
+    const long long xjump = ((long long)a.x_tt * 128 - 96) * 4, gjump = ((long long)a.g_tt * 128 - 96) * 4;   // floats
     auto load_stage = [&]() {
       const bool rv = pl < p_end;
       onew = rv ? onew_full : 0u;
       const float* gp = rv ? grow : g_xtg_zeros + 8 * uu;
+      const int xs1 = (xtt && rv) ? 128 : 1, xs16 = (xtt && rv) ? 2048 : 16;     // float4 strides: unit pair / block
+      const int gs1 = (gtt && rv) ? 128 : 1, gs16 = (gtt && rv) ? 2048 : 16;
       if constexpr (EMODE) {                         // raw operands of E = e (x) att; the product is formed at store time
         at = __ldg(reinterpret_cast<const float4*>(rv ? arow : g_xtg_zeros));
         const float2* ep = reinterpret_cast<const float2*>(rv ? xrow : g_xtg_zeros + 2 * uu);
@@ -238,19 +249,22 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
         const float4* xp = reinterpret_cast<const float4*>(rv ? xrow : g_xtg_zeros + 8 * uu);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (j < nxf) { xa[j] = __ldg(xp + 16 * j); xb[j] = __ldg(xp + 16 * j + 1); }
+          if (j < nxf) { xa[j] = __ldg(xp + xs16 * j); xb[j] = __ldg(xp + xs16 * j + xs1); }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (j < ngf) {
-            ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j);
-            gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j + 1);
+            ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
+            gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
           }
         if (gnarrow) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + i) : 0.f;
+          for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + (i >> 2) * 4 * gs1 + (i & 3)) : 0.f;
         }
       }
-      pl += XKP; xrow += xstep; grow += gstep;
+      const bool cross = (pl & 127) >= 96;               // the next stage's row lies in the next 128-row tile
+      pl += XKP;
+      xrow += xtt ? (cross ? xjump : (long long)XKP * 4) : xstep;
+      grow += gtt ? (cross ? gjump : (long long)XKP * 4) : gstep;
     };
     if (nst > 0) load_stage();
     for (int it = 0; it < nst; ++it) {
@@ -475,13 +489,13 @@ static bool xtg_is_lean(const XtgArgs& a, bool is_big) {
   if (a.e != nullptr) {
     if (a.att == nullptr || !al16(a.e) || !al16(a.att) || a.xw != 256 || a.MXpad != 256 || a.ones_col >= 0) return false;
   } else {
-    if (a.X == nullptr || !al16(a.X) || a.ldx % 4 != 0 || a.xw <= 0 || a.xw % 64 != 0) return false;
+    if (a.X == nullptr || !al16(a.X) || (a.x_tt == 0 && a.ldx % 4 != 0) || a.xw <= 0 || a.xw % 64 != 0) return false;
     if (a.ones_col >= 0 && a.ones_col != a.xw) return false;
     if (a.xw + (a.ones_col >= 0 ? 1 : 0) > a.MXpad) return false;
   }
   if (a.gw <= 0 || a.gw > a.NG) return false;
-  if (a.gw % 64 == 0) return al16(a.G) && a.ldg % 4 == 0;
-  return a.gw < 64;
+  if (a.gw % 64 == 0) return al16(a.G) && (a.g_tt > 0 || a.ldg % 4 == 0);
+  return a.gw < 64 && (a.g_tt == 0 || al16(a.G));
 }
 
 template <int TCOLS, bool LEAN, int MINB>
@@ -561,6 +575,13 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   }
   L.n = 0;
   static const bool no_lean = [] { const char* e = getenv("SAKE_XTG_GENERIC"); return e && atoi(e) != 0; }();   // A/B switch
+  bool any_tt = false;
+  for (int i = 0; i < nb_s; ++i) any_tt = any_tt || small.a[i].x_tt > 0 || small.a[i].g_tt > 0;
+  for (int i = 0; i < nb_b; ++i) any_tt = any_tt || big.a[i].x_tt > 0 || big.a[i].g_tt > 0;
+  if (any_tt && (no_lean || !lean_s || !lean_b)) {
+    set_error("tc_xtg: tile-transposed sources need the lean builder (SAKE_XTG_GENERIC must be off)");
+    return SAKE_EUNSUPPORTED;
+  }
   int rc = lean_b && !no_lean ? xtg_launch<512, true, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
                               : xtg_launch<512, false, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
   if (rc) return rc;
