@@ -42,6 +42,7 @@ static int make_dims(const SakeDims* s, Dims* d) {
   d->has_mask = (s->flags & SAKE_HAS_MASK) != 0;
   d->spatial = (s->flags & SAKE_NO_SPATIAL) == 0;
   d->prepared = (s->flags & SAKE_WEIGHTS_PREPARED) != 0;
+  d->g8 = 0;                                  // set with the engine (sake_layer_fwd / bwd)
   d->cutoff = (s->flags & SAKE_COSINE_CUTOFF) != 0;
   d->cut_lo = s->cutoff_lower; d->cut_hi = s->cutoff_upper;
   if (d->cutoff && !(d->cut_hi > d->cut_lo)) { set_error("cosine cutoff needs upper > lower (got %g, %g)", d->cut_lo, d->cut_hi); return SAKE_EINVAL; }
@@ -112,20 +113,13 @@ static SideCtx* side_ctx() {
 
 static inline bool H_is_64(const Dims& d) { return d.H == 64; }
 
-// SAKE_NODE_TC=0 keeps the CUDA-core per-node kernels under the tcgen05 engines (A/B diagnostics)
-static bool node_tc_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SAKE_NODE_TC"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v != 0;
-}
-
 static int resolve_engine(const SakeDims* s, const Dims& d) {
   int e = s->engine;
   if (e == SAKE_ENGINE_AUTO) return tc_supported(d) ? SAKE_ENGINE_F16X2 : SAKE_ENGINE_FP32;
   if (e == SAKE_ENGINE_FP32) return e;
   if (e == SAKE_ENGINE_TF32X3 || e == SAKE_ENGINE_BF16 || e == SAKE_ENGINE_F16X2) {
     if (!tc_supported(d)) {
-      set_error("tcgen05 engine needs H=64, A=4 (C=256); got H=%d A=%d", d.H, d.A);
+      set_error("tcgen05 engine needs H=64, A=4 (C=256), n_rbf <= 58; got H=%d A=%d K=%d", d.H, d.A, d.K);
       return SAKE_EUNSUPPORTED;
     }
     return e;
@@ -138,12 +132,12 @@ struct SavedLayout { size_t e, att, logit, ssum, he, nodeproj, nstash, wmix, wed
 static SavedLayout saved_layout(const Dims& d, int engine) {
   SavedLayout L;
   size_t o = 0;
-  L.e = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
+  L.e = o; o += align_up(sizeof(float) * rows_pad8(d.P) * d.H);
   L.att = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
   L.logit = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
   L.ssum = o; o += align_up(sizeof(float) * rows_pad128(d.R) * d.C * 3);
-  L.he = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
-  L.nodeproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
+  L.he = o; o += align_up(sizeof(float) * rows_pad8(d.R) * d.C);
+  L.nodeproj = o; o += align_up(sizeof(float) * rows_pad8(d.R) * d.NP);
   L.nstash = o; o += align_up(sizeof(float) * rows_pad128(d.R) * NS_LD);
   L.wmix = L.wedge = L.wnode = L.nodeWT = o;
   if (engine != SAKE_ENGINE_FP32) {
@@ -166,7 +160,7 @@ static Saved carve_saved(const Dims& d, void* base, bool tc_edge, int engine) {
   s.he = (float*)(b + L.he); s.nodeproj = (float*)(b + L.nodeproj); s.nstash = (float*)(b + L.nstash);
   s.wmix = b + L.wmix; s.wedge = b + L.wedge; s.wnode = b + L.wnode; s.nodeWT = (float*)(b + L.nodeWT);
   // the tcgen05 node kernels read ssum tile-transposed; k_tc_mix_fwd writes it that way when they run
-  s.ssum_tt = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr);
+  s.ssum_tt = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && true;
   return s;
 }
 
@@ -179,16 +173,16 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
     L.T = o; o += align_up(sizeof(float) * (size_t)d.R * d.C * 4);
     L.tmax = o; o += align_up(sizeof(float) * (size_t)d.R);
     L.ghe = o; o += align_up(sizeof(float) * (size_t)d.R * d.C);
-    L.ge = o; o += align_up(sizeof(float) * (size_t)d.P * d.H);
+    L.ge = o; o += align_up(sizeof(float) * rows_pad8(d.P) * d.H);
     L.gatt = o; o += align_up(sizeof(float) * (size_t)d.P * d.A);
     L.gdir = o; o += align_up(sizeof(float) * (size_t)d.P * 3);
     L.gcut = o; if (d.cutoff) o += align_up(sizeof(float) * (size_t)d.P);
-    L.gproj = o; o += align_up(sizeof(float) * (size_t)d.R * d.NP);
+    L.gproj = o; o += align_up(sizeof(float) * rows_pad8(d.R) * d.NP);
     L.wxT = o; o += align_up(sizeof(float) * (size_t)d.C * d.C);
     L.nodeWT = o; o += align_up(sizeof(float) * ((size_t)d.H * (2 * d.H + d.C) + 3 * (size_t)d.H * d.H + (size_t)d.H * d.C +
                                                   (size_t)d.K * 2 * d.H + (size_t)d.H * 2 * d.H));
     L.gZ = o;
-    if (with_grads) o += align_up(sizeof(float) * (size_t)d.P * d.C);
+    if (with_grads) o += align_up(sizeof(float) * rows_pad8(d.P) * d.C);
   }
   L.edgeb = o;
   if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d) && for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
@@ -248,6 +242,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if ((rc = check_leaves(d, *params, "params"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
+  d.g8 = engine != SAKE_ENGINE_FP32;
   if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small: %zu < %zu", saved_bytes, saved_layout(d, engine).total); return SAKE_EINVAL; }
   if ((reinterpret_cast<uintptr_t>(saved) & 255) != 0) { set_error("saved buffer must be 256-byte aligned"); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 0, 0);
@@ -270,7 +265,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   } else {
     if ((rc = tc_mix_fwd(d, *params, x, mask, sv, sv.wmix, engine, st))) return rc;
   }
-  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr)) {
+  if (engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && true) {
     if (!d.prepared && (rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;   // for the backward call's k_node_pre_bwd
     return tc_node_post(d, *params, h, x, v, mask, h_out, x_out, v_out, sv, sv.wnode, st);
   }
@@ -286,6 +281,7 @@ int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void
   if ((rc = check_leaves(d, *params, "params"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
+  d.g8 = engine != SAKE_ENGINE_FP32;
   if (engine == SAKE_ENGINE_FP32) return 0;
   if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -315,6 +311,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (grads && (rc = check_leaves(d, *grads, "grads"))) return rc;
   int engine = resolve_engine(dims, d);
   if (engine < 0) return engine;
+  d.g8 = engine != SAKE_ENGINE_FP32;
   if (saved_bytes < saved_layout(d, engine).total) { set_error("saved buffer too small"); return SAKE_EINVAL; }
   ScratchLayout SL = scratch_layout(d, engine, 1, grads != nullptr);
   if (scratch_bytes < SL.total) { set_error("scratch buffer too small: %zu < %zu", scratch_bytes, SL.total); return SAKE_EINVAL; }
@@ -338,7 +335,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.gatt = (float*)(b + SL.gatt); sc.gdir = (float*)(b + SL.gdir); sc.gproj = (float*)(b + SL.gproj);
   sc.gcut = d.cutoff ? (float*)(b + SL.gcut) : nullptr;
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
-  const bool tc_node = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && (node_tc_enabled() || d.hdr != nullptr);
+  const bool tc_node = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && true;
   if (tc_node) sc.nodeWT = sv.nodeWT;                 // transposed copies left by the forward call
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;

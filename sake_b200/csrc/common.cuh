@@ -34,6 +34,8 @@ struct Dims {
   int Kp;                 // K rounded up to a multiple of 4 (16-byte aligned projection blocks)
   int NP;                 // per-node projection width = 2Kp + 2H
   int update, has_v, has_mask, spatial;
+  int g8;                 // 1 (tcgen05 engines): the internal per-pair / per-atom buffers e, he, nodeproj, ge, gproj, gZ and the
+                          // backward records use the G8 layout below; 0 (generic engine): row-major rows
   int prepared;           // 1: weight operand images in `saved` are current (SAKE_WEIGHTS_PREPARED)
   int cutoff;             // 1: cosine cutoff on the attention (layers.py:172-176), parameters below
   float cut_lo, cut_hi;
@@ -68,10 +70,10 @@ struct Saved {
   float* att;       // [P,A]   combined attention (layers.py:205)
   float* logit;     // [P,A]   attention logits s (layers.py:155-165); aliases att on the generic engine (normalised in place)
   float* ssum;      // [R,C,3] sum_j dir*coef*mask (numerator of combinations_sum, layers.py:123,127)
-  int ssum_tt;      // ssum is tile-transposed [R/128][C/4][3][128][4] (tcgen05 mix + node kernels; tc_node.cu)
+  int ssum_tt;      // ssum is in the G8 layout, unit (c/4)*3 + d = component d of four coefficients (tcgen05 engines)
   float* he;        // [R,C]   aggregate (layers.py:135-140)
   float* nodeproj;  // [R,NP]
-  float* nstash;    // [R/128][NS_LD/4][128][4] (tile-transposed) per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
+  float* nstash;    // [R, NS_LD] in the G8 layout per-atom activations of the node tail (tc_node.cu forward -> backward: no recompute)
   // tcgen05 engines: operand images of the layer's weights, built ONCE by the forward call and reused by the
   // backward call of the same step (round 1 rebuilt them in both: 5 + 5 small launches per layer)
   void* wmix;       // x_mixing images for GEMM1 / GEMM2 + {scale, 1/scale}   (tc_mix.cu)
@@ -101,7 +103,21 @@ struct BwdScratch {
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-inline size_t rows_pad128(long long R) { return (size_t)((R + 127) / 128 * 128); }   // rows of a tile-transposed buffer
+// ---- "G8" layout of per-row buffers (rows = atoms or atom pairs, U 16-byte units per row) ----------------------
+// The tcgen05 kernels are thread-per-row: a thread walks the units of ITS row, so with row-major rows the 32 lanes
+// of a load touch 32 different 128-byte lines (32 L1 wavefronts per instruction; ncu: the edge and node kernels sat
+// at the L1 wavefront ceiling).  G8 interleaves groups of 8 consecutive rows unit by unit:
+//     float4 index of (row r, unit u) = ((r >> 3) * U + u) * 8 + (r & 7)
+// so that 8 consecutive lanes read one full line (4 wavefronts per 128-bit load, the minimum), a whole 8-row group
+// is still one contiguous block (warp-per-row kernels read groups with fully coalesced loads), and the X^T G builder
+// (tc_xtg.cu: 8 lanes = the 8 units of a row) touches as many lines as with row-major rows.
+constexpr int G8S = 8;                                       // float4 stride between consecutive units of a row
+__host__ __device__ inline size_t g8_row(long long r, int U) { return (size_t)(r >> 3) * U * 8 + (size_t)(r & 7); }
+__host__ __device__ inline size_t g8_elem(long long r, int U, int col) {   // float index of column col of row r
+  return (g8_row(r, U) + (size_t)(col >> 2) * G8S) * 4 + (size_t)(col & 3);
+}
+inline size_t rows_pad8(long long R) { return (size_t)((R + 7) / 8 * 8); }
+inline size_t rows_pad128(long long R) { return (size_t)((R + 127) / 128 * 128); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
@@ -308,7 +324,7 @@ struct XtgArgs {
   const float* e; const float* att;    // X = e (x) att  (xw = 256, feature c = f*4 + head) when e != nullptr
   int ones_col;                        // X feature index forced to 1.0 (column sums of G for free), or -1
   const float* G; int ldg; int gw;     // G source [P, gw]
-  int x_tt, g_tt;                      // > 0: the source is tile-transposed (tc_node.cu) with this many 16-byte units per row
+  int x_tt, g_tt;                      // > 0: the source is in the G8 layout with this many 16-byte units per row
   int MXpad, NG;                       // operand image sizes: MXpad in {128,256}; NG multiple of 16, <= 256
   long long P, pairs_per_cta;          // ragged batches: P is the padded worst case, the real extent is *Pdev
   const long long* Pdev;               // device-resident K extent (RaggedHdr::P or ::R64), or NULL

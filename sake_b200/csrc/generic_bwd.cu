@@ -487,11 +487,11 @@ __global__ void __launch_bounds__(256) k_mix_bwd_nospatial(Dims d, const float* 
     for (int f = threadIdx.x; f < H; f += blockDim.x) {
       float acc = 0.f;
       for (int a = 0; a < A; ++a) acc = fmaf(m * ghe[row * C + f * A + a], att[pr * A + a], acc);
-      ge[pr * H + f] = acc;
+      ge[d.g8 ? g8_elem((long long)pr, H >> 2, f) : pr * H + f] = acc;
     }
     for (int a = threadIdx.x; a < A; a += blockDim.x) {
       float acc = 0.f;
-      for (int f = 0; f < H; ++f) acc = fmaf(m * ghe[row * C + f * A + a], e[pr * H + f], acc);
+      for (int f = 0; f < H; ++f) acc = fmaf(m * ghe[row * C + f * A + a], e[d.g8 ? g8_elem((long long)pr, H >> 2, f) : pr * H + f], acc);
       gatt[pr * A + a] = acc;
     }
     if (threadIdx.x < 3) gdir[pr * 3 + threadIdx.x] = 0.f;
@@ -870,7 +870,10 @@ __global__ void __launch_bounds__(256) k_node_pre_bwd(Dims d, const SakeLayerPar
   const int r0 = blockIdx.x * NODES;
   if (r0 >= dims_rows(d)) return;                  // ragged: the grid covers the padded worst case
   const int nn = min(NODES, dims_rows(d) - r0);
-  for (int t = threadIdx.x; t < NODES * NP; t += blockDim.x) gp[t] = (t / NP) < nn ? gproj[(size_t)r0 * NP + t] : 0.f;
+  for (int t = threadIdx.x; t < NODES * NP; t += blockDim.x) {
+    const int nl = t / NP, o = t - nl * NP;
+    gp[t] = nl < nn ? gproj[d.g8 ? g8_elem(r0 + nl, NP >> 2, o) : (size_t)r0 * NP + t] : 0.f;
+  }
   for (int t = threadIdx.x; t < NODES * H; t += blockDim.x) hs[t] = (t / H) < nn ? h[(size_t)r0 * H + t] : 0.f;
   __syncthreads();
   // dh[n][f] += sum_k Win[f][k] g_uj[k] + Win[H+f][k] g_ui[k] + sum_q W1[f][q] g_pj[q] + W1[H+f][q] g_pi[q]
@@ -1009,10 +1012,10 @@ int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, cons
                XtgList& L, cudaStream_t st) {
   const float* nb = sc.nbuf;
   float* tmp = sc.nbuf + rows_pad128(d.R) * NB_LD;     // [128] bias scratch
-  // a source: row-major (ld floats per row, tt = 0) or a field of a tile-transposed buffer (tt = units per row)
+  // a source: row-major (ld floats per row, tt = 0) or a field of a G8 buffer (tt = units per row; common.cuh)
   struct Src { const float* p; int ld, tt; };
   auto rowmajor = [](const float* p, int ld) { return Src{p, ld, 0}; };
-  auto field = [](const float* buf, int col, int ld) { return Src{buf + (size_t)(col / 4) * 512, ld, ld / 4}; };
+  auto field = [](const float* buf, int col, int ld) { return Src{buf + (size_t)(col / 4) * G8S * 4, ld, ld / 4}; };
   auto call = [&](Src X, int xw, int ones, int mxpad, Src G, int gw, int ng, float* out, int ldo,
                   int out_rows, int out_cols, float* extra, int extra_ld) {
     XtgArgs q;
@@ -1024,7 +1027,7 @@ int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, cons
     q.extra = extra; q.extra_rows = extra ? 1 : 0; q.extra_ld = extra_ld;
     return L.push(q);
   };
-  // record fields: tile-transposed when the tcgen05 node kernel wrote them, rows of NB_LD floats otherwise
+  // record fields: G8 when the tcgen05 node kernel wrote them, rows of NB_LD floats otherwise
   auto rec = [&](int col) { return direct ? field(nb, col, NB_LD) : rowmajor(nb + col, NB_LD); };
   auto stash = [&](int col) { return field(sv.nstash, col, NS_LD); };
   int rc = 0;
@@ -1032,7 +1035,7 @@ int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, cons
   if (direct) {
     rc |= call(stash(NS_N1), 64, 64, 128, rec(NB_GT2), 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
     rc |= call(rowmajor(h, 64), 64, -1, 128, rec(NB_GT1), 64, 64, g.node0_kernel, 64, 64, 64, nullptr, 64);
-    rc |= call(rowmajor(sv.he, 256), 256, -1, 256, rec(NB_GT1), 64, 64, g.node0_kernel + 64 * 64, 64, 256, 64, nullptr, 64);
+    rc |= call(field(sv.he, 0, 256), 256, -1, 256, rec(NB_GT1), 64, 64, g.node0_kernel + 64 * 64, 64, 256, 64, nullptr, 64);
     rc |= call(stash(NS_HCOMB), 64, 64, 128, rec(NB_GT1), 64, 64, g.node0_kernel + 320 * 64, 64, 64, 64, g.node0_bias, 64);
   } else {
     rc |= call(rec(NB_N1), 64, 64, 128, rec(NB_GT2), 64, 64, g.node2_kernel, 64, 64, 64, g.node2_bias, 64);
@@ -1065,7 +1068,7 @@ int tc_node_pre_dw(const Dims& d, const float* h, const SakeLayerGrads& g, const
     XtgArgs q;
     memset(&q, 0, sizeof(q));
     q.X = h; q.ldx = H; q.xw = H; q.ones_col = bias ? H : -1; q.MXpad = 128;
-    q.G = sc.gproj + col0; q.ldg = d.NP; q.gw = gw; q.NG = 64;
+    q.G = sc.gproj + (size_t)(col0 / 4) * G8S * 4; q.ldg = d.NP; q.g_tt = d.NP / 4; q.gw = gw; q.NG = 64;   // G8 field
     q.P = d.R; q.Pdev = d.hdr ? &d.hdr->R64 : nullptr;
     q.out = out; q.ldo = ldo; q.out_rows = H; q.out_cols = gw;
     q.extra = bias; q.extra_rows = bias ? 1 : 0; q.extra_ld = gw;

@@ -214,15 +214,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
     long long prx;
     tile_pair(tile_desc(a.g, tile), pl, valid, row, j, prx);
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, nrm = 0.f, tt = 0.f, m = 1.0f;
-    const float* nj = a.proj;
-    const float* ni = a.proj;
+    // per-node projections (G8 layout, NP / 4 units per atom): sender j varies with the lane -> full lines,
+    // receiver i is the same for all lanes of a row segment -> broadcast
+    const float4* nj4 = reinterpret_cast<const float4*>(a.proj);
+    const float4* ni4 = nj4;
     bool diag = false;
     if (!valid) prx = 0;
     if (valid) {
       const int mol0 = geom_mol0(a.g, row);
       diag = (row - mol0) == j;
-      nj = a.proj + (size_t)(mol0 + j) * NP;
-      ni = a.proj + (size_t)row * NP;
+      nj4 += g8_row(mol0 + j, NP >> 2);
+      ni4 += g8_row(row, NP >> 2);
       const float* xi = a.x + (size_t)row * 3;
       const float* xj = a.x + (size_t)(mol0 + j) * 3;
       r0 = xj[0] - xi[0]; r1 = xj[1] - xi[1]; r2 = xj[2] - xi[2];
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         uj4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         ui4[q] = uj4[q];
         if (4 * u < Kp) {                      // idle lanes read node 0 (valid memory); their rows are never stored
-          uj4[q] = __ldg(reinterpret_cast<const float4*>(nj + 4 * u));
-          ui4[q] = __ldg(reinterpret_cast<const float4*>(ni + Kp + 4 * u));
+          uj4[q] = __ldg(&nj4[((4 * u) >> 2) * G8S]);
+          ui4[q] = __ldg(&ni4[((Kp + 4 * u) >> 2) * G8S]);
           if (a.pair_u) {                      // edge features: + he @ W_in[2F:2F+E]  (SakePairTerms)
             const float4 ue = __ldg(reinterpret_cast<const float4*>(a.pair_u + prx * Kp + 4 * u));
             ui4[q].x += ue.x; ui4[q].y += ue.y; ui4[q].z += ue.z; ui4[q].w += ue.w;
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       if (BWD && a.train && valid) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(a.gbuf + prx * 64 + hb * 32 + 4 * q) = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+          reinterpret_cast<float4*>(a.gbuf)[g8_row(prx, 16) + (hb * 8 + q) * G8S] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) store_unit_tf32(img, pl, q, vals + 4 * q);
@@ -291,8 +293,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         float4 pj4[8], pi4[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 4 * u));
-          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 4 * u));
+          pj4[u] = __ldg(&nj4[((2 * Kp + 4 * u) >> 2) * G8S]);
+          pi4[u] = __ldg(&ni4[((2 * Kp + 64 + 4 * u) >> 2) * G8S]);
           if (a.pair_p) {                      // edge features: + he @ W_1[2F:2F+E]
             const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + 4 * u));
             pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
       float4 pj4[8], pi4[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + 32 + 4 * u));
-        pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + 32 + 4 * u));
+        pj4[u] = __ldg(&nj4[((2 * Kp + 32 + 4 * u) >> 2) * G8S]);
+        pi4[u] = __ldg(&ni4[((2 * Kp + 64 + 32 + 4 * u) >> 2) * G8S]);
         if (a.pair_p) {
           const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + 32 + 4 * u));
           pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
@@ -335,11 +337,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         tmem_ld32(lane_addr + half * 32, v);
         tmem_ld_wait();
         if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.e_out + prx * 64 + half * 32);
+          float4* o = reinterpret_cast<float4*>(a.e_out) + g8_row(prx, 16) + half * 8 * G8S;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int f0 = half * 32 + 4 * u;
-            o[u] = make_float4(v[4 * u] + s_b2[f0], v[4 * u + 1] + s_b2[f0 + 1], v[4 * u + 2] + s_b2[f0 + 2],
+            o[u * G8S] = make_float4(v[4 * u] + s_b2[f0], v[4 * u + 1] + s_b2[f0 + 1], v[4 * u + 2] + s_b2[f0 + 2],
                                v[4 * u + 3] + s_b2[f0 + 3]);
           }
         }
@@ -369,17 +371,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           tmem_ld32(lane_addr + half * 32, v);
           tmem_ld_wait();
           if (valid) {
-            float4* o = reinterpret_cast<float4*>(a.a1buf + prx * 64 + half * 32);
+            float4* o = reinterpret_cast<float4*>(a.a1buf) + g8_row(prx, 16) + half * 8 * G8S;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int f0 = half * 32 + 4 * u;
-              const float4 pj = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + f0));
-              float4 pi = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + f0));
+              const float4 pj = __ldg(&nj4[((2 * Kp + f0) >> 2) * G8S]);
+              float4 pi = __ldg(&ni4[((2 * Kp + 64 + f0) >> 2) * G8S]);
               if (a.pair_p) {
                 const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + f0));
                 pi.x += pe.x; pi.y += pe.y; pi.z += pe.z; pi.w += pe.w;
               }
-              o[u] = make_float4(fsilu_(v[4 * u] + pj.x + pi.x), fsilu_(v[4 * u + 1] + pj.y + pi.y),
+              o[u * G8S] = make_float4(fsilu_(v[4 * u] + pj.x + pi.x), fsilu_(v[4 * u + 1] + pj.y + pi.y),
                                  fsilu_(v[4 * u + 2] + pj.z + pi.z), fsilu_(v[4 * u + 3] + pj.w + pi.w));
             }
           }
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           float4 g4[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            g4[u] = *reinterpret_cast<const float4*>(a.ge + prx * 64 + hb * 32 + 4 * u);
+            g4[u] = reinterpret_cast<const float4*>(a.ge)[g8_row(prx, 16) + (hb * 8 + u) * G8S];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             float vals[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
@@ -404,12 +406,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
               const float4 ws = s_ws[hb * 32 + 4 * u + i];
               vals[i] += ws.x * gq.x + ws.y * gq.y + ws.z * gq.z + ws.w * gq.w;
             }
-            if (a.train && valid) *reinterpret_cast<float4*>(a.ge + prx * 64 + hb * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            if (a.train && valid) reinterpret_cast<float4*>(a.ge)[g8_row(prx, 16) + (hb * 8 + u) * G8S] = make_float4(vals[0], vals[1], vals[2], vals[3]);
             store_unit_tf32(img, pl, u, vals);
           }
           run_chunk(tcol + 64, sW2, hb, 64, idesc64);                      // GA1 = GE W2^T -> cols [64,128)
         }
       }
+      float4* const pb4 = reinterpret_cast<float4*>(a.PB) + g8_row(prx, PB_LD / 4);       // this pair's record (G8 layout)
       // ---------------- (e') g_z1 = GA1 * silu'(z1)  -> A operand of GEMM D, and the per-pair record.
       // GEMM D writes GG over Z1, so the second half of Z1 is read before its first chunk is issued.
       float z1b[32];
@@ -418,8 +421,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         float4 pj4[8], pi4[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          pj4[u] = __ldg(reinterpret_cast<const float4*>(nj + 2 * Kp + half * 32 + 4 * u));
-          pi4[u] = __ldg(reinterpret_cast<const float4*>(ni + 2 * Kp + 64 + half * 32 + 4 * u));
+          pj4[u] = __ldg(&nj4[((2 * Kp + half * 32 + 4 * u) >> 2) * G8S]);
+          pi4[u] = __ldg(&ni4[((2 * Kp + 64 + half * 32 + 4 * u) >> 2) * G8S]);
           if (a.pair_p) {
             const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pair_p + prx * 64 + half * 32 + 4 * u));
             pi4[u].x += pe.x; pi4[u].y += pe.y; pi4[u].z += pe.z; pi4[u].w += pe.w;
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
             vals[1] = ga[4 * u + 1] * fdsilu_(zz1 + pj.y + pi.y);
             vals[2] = ga[4 * u + 2] * fdsilu_(zz2 + pj.z + pi.z);
             vals[3] = ga[4 * u + 3] * fdsilu_(zz3 + pj.w + pi.w);
-            if (valid) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + f0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            if (valid) pb4[((f0) >> 2) * G8S] = make_float4(vals[0], vals[1], vals[2], vals[3]);
           }
           store_unit_tf32(img, pl, u, vals);
         }
@@ -461,8 +464,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
           uj4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           ui4[u] = uj4[u];
           if (half * 32 + 4 * u < Kp) {               // warp-uniform; idle lanes read node 0
-            uj4[u] = __ldg(reinterpret_cast<const float4*>(nj + half * 32 + 4 * u));
-            ui4[u] = __ldg(reinterpret_cast<const float4*>(ni + Kp + half * 32 + 4 * u));
+            uj4[u] = __ldg(&nj4[((half * 32 + 4 * u) >> 2) * G8S]);
+            ui4[u] = __ldg(&ni4[((Kp + half * 32 + 4 * u) >> 2) * G8S]);
             if (a.pair_u) {
               const float4 ue = __ldg(reinterpret_cast<const float4*>(a.pair_u + prx * Kp + half * 32 + 4 * u));
               ui4[u].x += ue.x; ui4[u].y += ue.y; ui4[u].z += ue.z; ui4[u].w += ue.w;
@@ -503,12 +506,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int k0 = half * 32 + 4 * u;
-            if (k0 < 60) *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 64 + k0) = make_float4(gu[4 * u], gu[4 * u + 1], gu[4 * u + 2], gu[4 * u + 3]);
+            if (k0 < 60) pb4[((64 + k0) >> 2) * G8S] = make_float4(gu[4 * u], gu[4 * u + 1], gu[4 * u + 2], gu[4 * u + 3]);
           }
           if (a.train) {
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 128 + half * 32 + 4 * u) = make_float4(wv[4 * u], wv[4 * u + 1], wv[4 * u + 2], wv[4 * u + 3]);
+              pb4[((128 + half * 32 + 4 * u) >> 2) * G8S] = make_float4(wv[4 * u], wv[4 * u + 1], wv[4 * u + 2], wv[4 * u + 3]);
           }
         }
       }
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(EdgeArgs a) {
         const float gn2 = n2 > 0.f ? gn / (2.0f * nrm) : 0.f;   // relu'(0) = 0 (functional.py:15)
         g0 = fmaf(2.0f * r0, gn2, g0); g1 = fmaf(2.0f * r1, gn2, g1); g2 = fmaf(2.0f * r2, gn2, g2);
         if (diag) { g0 = 0.f; g1 = 0.f; g2 = 0.f; }
-        *reinterpret_cast<float4*>(a.PB + prx * PB_LD + 124) = make_float4(g0, g1, g2, 0.f);
+        pb4[((124) >> 2) * G8S] = make_float4(g0, g1, g2, 0.f);
       }
       tc_fence_before();
     }
@@ -600,29 +603,62 @@ int tc_attn_bwd(const Dims& d, const float* x, const Saved& sv, const BwdScratch
 
 // ---- reductions of the per-pair record over senders / receivers -----------------------------------
 // gproj[n] = [ sum_i gu[(i,n)] | sum_j gu[(n,j)] | sum_i gz1[(i,n)] | sum_j gz1[(n,j)] ],  dx[n] += sum_i g_r[(i,n)] - sum_j g_r[(n,j)]
-__global__ void __launch_bounds__(128) k_pair_reduce(Dims d, const float* __restrict__ PB,
+// The record is in the G8 layout (8 pairs x one 16-byte unit = one line).  One CTA = 8 consecutive atoms, thread =
+// (atom a' = t & 7, unit u = t >> 3 of the first 128 record columns):
+//   column sums  sum_i rec[(i, n0 + a')]: the 8 threads of a unit read 8 consecutive pair slots of row i -> full lines
+//   row sums     sum_j rec[(n, j)]: for each of the 8 atoms in turn, the 8 threads of a unit read 8 consecutive j and
+//                the partial sums meet in three shuffles; thread a' keeps the sum of atom a'.
+// Every thread then owns both sums of (its atom, its unit) and writes the G8 rows of gproj itself.
+__global__ void __launch_bounds__(256) k_pair_reduce(Dims d, const float* __restrict__ PB,
                                                      float* __restrict__ gproj, float* __restrict__ dx) {
-  const int n = blockIdx.x;
-  if (n >= dims_rows(d)) return;
+  const int n0 = blockIdx.x * 8, R = dims_rows(d);
+  if (n0 >= R) return;
   const int K = d.K, Kp = d.Kp, NP = d.NP;
-  const RowInfo ri = row_info(d, n);
-  const int N = ri.n, a = n - ri.mol0;                     // atoms of this molecule, index of n inside it
-  const int c = threadIdx.x;                               // column of the record [0,128)
-  const float* rowp = PB + (size_t)ri.pair0 * PB_LD + c;                            // (n, j) j = 0..N-1
-  const float* colp = PB + (size_t)(ri.pair0 - (long long)a * N + a) * PB_LD + c;   // (i, n) i = 0..N-1, stride N records
-  float si = 0.f, sj = 0.f;
-  for (int q = 0; q < N; ++q) {
-    si += rowp[(size_t)q * PB_LD];
-    sj += colp[(size_t)q * N * PB_LD];
+  const int ap = threadIdx.x & 7, u = threadIdx.x >> 3;            // u = 0 .. 31
+  const float4* pb = reinterpret_cast<const float4*>(PB) + u * G8S;
+  constexpr int U = PB_LD / 4;
+  float4 sj = make_float4(0.f, 0.f, 0.f, 0.f), si = sj;
+  const int n = n0 + ap;
+  if (n < R) {
+    const RowInfo ri = row_info(d, n);
+    const long long c0 = ri.pair0 - (long long)(n - ri.mol0) * ri.n + (n - ri.mol0);   // pair (0, n) of the molecule
+    for (int i = 0; i < ri.n; ++i) {
+      const float4 v = __ldg(pb + g8_row(c0 + (long long)i * ri.n, U));
+      sj.x += v.x; sj.y += v.y; sj.z += v.z; sj.w += v.w;
+    }
   }
-  float* gp = gproj + (size_t)n * NP;
-  if (c < 64) { gp[2 * Kp + c] = sj; gp[2 * Kp + 64 + c] = si; }
-  else if (c < 64 + Kp) {
-    const int k = c - 64;
-    gp[k] = k < K ? sj : 0.f;
-    gp[Kp + k] = k < K ? si : 0.f;
-  } else if (c >= 124 && c < 127) {
-    dx[(size_t)n * 3 + (c - 124)] += sj - si;
+  for (int a2 = 0; a2 < 8; ++a2) {
+    const int m = n0 + a2;
+    if (m >= R) break;                                             // block-uniform
+    const RowInfo ri = row_info(d, m);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = ap; j < ri.n; j += 8) {
+      const float4 v = __ldg(pb + g8_row(ri.pair0 + j, U));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (ap == a2) si = acc;
+  }
+  if (n >= R) return;
+  float4* gp = reinterpret_cast<float4*>(gproj) + g8_row(n, NP >> 2);
+  if (u < 16) {                                                    // gz1: record columns [0, 64)
+    gp[((2 * Kp) / 4 + u) * G8S] = sj;
+    gp[((2 * Kp) / 4 + 16 + u) * G8S] = si;
+  } else if (u < 16 + Kp / 4) {                                    // gu: record columns [64, 64 + Kp), zero beyond K
+    const int k0 = 4 * (u - 16);
+    float4 a = sj, b = si;
+    if (k0 + 0 >= K) { a.x = 0.f; b.x = 0.f; }
+    if (k0 + 1 >= K) { a.y = 0.f; b.y = 0.f; }
+    if (k0 + 2 >= K) { a.z = 0.f; b.z = 0.f; }
+    if (k0 + 3 >= K) { a.w = 0.f; b.w = 0.f; }
+    gp[(u - 16) * G8S] = a;
+    gp[(Kp / 4 + u - 16) * G8S] = b;
+  } else if (u == 31) {                                            // g_r: record columns 124 .. 126
+    dx[(size_t)n * 3] += sj.x - si.x; dx[(size_t)n * 3 + 1] += sj.y - si.y; dx[(size_t)n * 3 + 2] += sj.z - si.z;
   }
 }
 
@@ -634,8 +670,9 @@ __global__ void k_pair_terms_out(long long P, int K, int Kp, const float* __rest
   if (t >= P * w) return;
   const long long pr = t / w;
   const int c = (int)(t - pr * w);
-  if (c < 64) { if (g_p) g_p[pr * 64 + c] = PB[pr * PB_LD + c]; }
-  else if (g_u) { const int k = c - 64; g_u[pr * Kp + k] = k < K ? PB[pr * PB_LD + 64 + k] : 0.f; }
+  const float v = PB[g8_elem(pr, PB_LD / 4, c)];
+  if (c < 64) { if (g_p) g_p[pr * 64 + c] = v; }
+  else if (g_u) { const int k = c - 64; g_u[pr * Kp + k] = k < K ? v : 0.f; }
 }
 
 // dmu_k += 2 beta_k S1_k ;  dbeta_k += -(S2_k - mu_k S1_k)   with S1 = sum_p w_pk, S2 = sum_p t_p w_pk
@@ -698,8 +735,8 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
 
 // PB [P,192] | a1buf [P,64] | gbuf [P,64] | extra [2,192]   (a1buf / gbuf only when training)
 size_t tc_edge_bwd_scratch_bytes(const Dims& d, int with_grads) {
-  size_t n = align_up(sizeof(float) * (size_t)d.P * PB_LD) + align_up(sizeof(float) * 2 * PB_LD);
-  if (with_grads) n += 2 * align_up(sizeof(float) * (size_t)d.P * 64);
+  size_t n = align_up(sizeof(float) * rows_pad8(d.P) * PB_LD) + align_up(sizeof(float) * 2 * PB_LD);
+  if (with_grads) n += 2 * align_up(sizeof(float) * rows_pad8(d.P) * 64);
   return n;
 }
 
@@ -708,10 +745,10 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
                 float* g_pair_u, float* g_pair_p, cudaStream_t st) {
   EdgeW w = carve_edge_w(wscratch);                      // built by tc_edge_fwd of the same step (saved.wedge)
   char* eb = (char*)escratch;
-  float* PB = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * PB_LD);
+  float* PB = (float*)eb; eb += align_up(sizeof(float) * rows_pad8(d.P) * PB_LD);
   float* extra = (float*)eb; eb += align_up(sizeof(float) * 2 * PB_LD);
   float* a1buf = nullptr; float* gbuf = nullptr;
-  if (g) { a1buf = (float*)eb; eb += align_up(sizeof(float) * (size_t)d.P * 64); gbuf = (float*)eb; }
+  if (g) { a1buf = (float*)eb; eb += align_up(sizeof(float) * rows_pad8(d.P) * 64); gbuf = (float*)eb; }
   EdgeArgs a;
   memset(&a, 0, sizeof(a));
   a.g = make_geom(d);
@@ -727,7 +764,7 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     ProfScope prof(5, d.P, st);
     k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
   }
-  k_pair_reduce<<<d.R, 128, 0, st>>>(d, PB, sc.gproj, dx);
+  k_pair_reduce<<<(d.R + 7) / 8, 256, 0, st>>>(d, PB, sc.gproj, dx);
   note_launches(2);
   if (g_pair_u || g_pair_p) {
     // cotangents of the `he` terms are columns of the per-pair record: g_z1 = PB[:, 0:64], g_u = PB[:, 64:64+Kp)
@@ -740,21 +777,21 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     XtgArgs q;
     // dW2, db2 (layers.py:24):  a1^T g_e
     memset(&q, 0, sizeof(q));
-    q.X = a1buf; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.ge; q.ldg = 64; q.gw = 64; q.MXpad = 128; q.NG = 64;
+    q.X = a1buf; q.ldx = 64; q.x_tt = 16; q.xw = 64; q.ones_col = 64; q.G = sc.ge; q.ldg = 64; q.g_tt = 16; q.gw = 64; q.MXpad = 128; q.NG = 64;
     q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->mlp_out2_kernel; q.ldo = 64; q.out_rows = 64; q.out_cols = 64;
     q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64;
     L.push(q);
     // dW1[2H : 2H+K+1] (RBF channels + distance row, layers.py:22) and the RBF mean / width sums
     SAKE_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(float) * 2 * PB_LD, st));
     memset(&q, 0, sizeof(q));
-    q.X = gbuf; q.ldx = 64; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
+    q.X = gbuf; q.ldx = 64; q.x_tt = 16; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.g_tt = PB_LD / 4; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
     q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
     q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD;
     L.push(q);
     L.mb_extra = extra; L.mu = p.rbf_means; L.beta = p.rbf_betas; L.g_mu = g->rbf_means; L.g_beta = g->rbf_betas; L.K = d.K;
     // dWs, dbs (layers.py:80):  e^T g_q
     memset(&q, 0, sizeof(q));
-    q.X = sv.e; q.ldx = 64; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.gw = 4; q.MXpad = 128; q.NG = 16;
+    q.X = sv.e; q.ldx = 64; q.x_tt = 16; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.g_tt = 1; q.gw = 4; q.MXpad = 128; q.NG = 16;   // [P,4] rows = G8 with one unit
     q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->sem_kernel; q.ldo = 4; q.out_rows = 64; q.out_cols = 4;
     q.extra = g->sem_bias; q.extra_rows = 1; q.extra_ld = 4;
     if (L.push(q)) { set_error("xtg list full"); return SAKE_EINVAL; }

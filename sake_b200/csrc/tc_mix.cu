@@ -399,17 +399,20 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         int row2, j2;
         long long px2;
         tile_pair(tile_desc(g, tile + gridDim.x), p, v2, row2, j2, px2);
-        if (v2) { prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4); }
+        if (v2) {                                   // G8: a line = one unit of 8 pairs; each pair of a group pulls two of the 16
+          const float4* e8 = reinterpret_cast<const float4*>(e) + g8_row(px2 & ~7LL, 16) + 2 * (px2 & 7) * G8S;
+          prefetch_l2(e8); prefetch_l2(e8 + G8S); prefetch_l2(att + px2 * 4);
+        }
       }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         at = *reinterpret_cast<const float4*>(att + prx * 4);
-        const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
+        const float4* ep = reinterpret_cast<const float4*>(e) + g8_row(prx, 16);     // G8 layout: unit q at ep[q * 8]
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          float4 t4 = __ldg(ep + q);
+          float4 t4 = __ldg(ep + q * G8S);
           ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
         }
         const float* xi = x + (size_t)row * 3;
@@ -477,11 +480,11 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           if (n == 32 && ls == c) epi_fwd_chunk<CF, false>(v, dmt + ls, 0u, s0, s1, s2);
           else epi_fwd_chunk<CF, true>(v, dmt + ls, (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << (c - ls), s0, s1, s2);
         }
-        // ssum_tt: the tile-transposed layout the tcgen05 node kernels read (tc_node.cu): [128-row tile][c'/4][d][row][c'%4]
+        // ssum_tt: the G8 layout the tcgen05 node kernels read (tc_node.cu), unit (c'/4)*3 + d = component d of 4 coefficients
         const size_t orow = (size_t)(row0 + sg);
-        float* o = ssum_tt ? ssum + ((((orow >> 7) * 64 + (cp >> 2)) * 3) * 128 + (orow & 127)) * 4 + (cp & 3)
+        float* o = ssum_tt ? ssum + (g8_row((long long)orow, 192) + (size_t)(cp >> 2) * 3 * G8S) * 4 + (cp & 3)
                            : ssum + (orow * CC + cp) * 3;
-        emit_ssum(o, ssum_tt ? 512 : 1, s0, s1, s2, accumulate);
+        emit_ssum(o, ssum_tt ? 4 * G8S : 1, s0, s1, s2, accumulate);
       }
       tc_fence_before();
       mbar_arrive(sm.acc_empty + buf);
@@ -503,7 +506,7 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
 template <class CF>
 __device__ __forceinline__ void epi1_block(const float (&v)[32], const float4* __restrict__ Tp, float zs, float q0,
                                            float q1, float q2, float& g0, float& g1, float& g2, uint8_t* img, int p,
-                                           int unit0, float* __restrict__ gz, float idz) {
+                                           int unit0, float4* __restrict__ gz, float idz) {
   float dz[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) {                       // 32 independent chains, no control flow in between
@@ -521,7 +524,7 @@ __device__ __forceinline__ void epi1_block(const float (&v)[32], const float4* _
   if (gz != nullptr) {                                 // training: fp32 copy of dZ for the weight-gradient contraction
 #pragma unroll
     for (int i = 0; i < 32; i += 4)
-      *reinterpret_cast<float4*>(gz + i) =
+      gz[(i / 4) * G8S] =
           CF::F16 ? make_float4(dz[i] * idz, dz[i + 1] * idz, dz[i + 2] * idz, dz[i + 3] * idz)
                   : make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
   }
@@ -679,16 +682,19 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         int row2, j2;
         long long px2;
         tile_pair(tile_desc(g, tile + gridDim.x), p, v2, row2, j2, px2);
-        if (v2) { prefetch_l2(e + px2 * 64); prefetch_l2(e + px2 * 64 + 32); prefetch_l2(att + px2 * 4); }
+        if (v2) {                                   // G8: a line = one unit of 8 pairs; each pair of a group pulls two of the 16
+          const float4* e8 = reinterpret_cast<const float4*>(e) + g8_row(px2 & ~7LL, 16) + 2 * (px2 & 7) * G8S;
+          prefetch_l2(e8); prefetch_l2(e8 + G8S); prefetch_l2(att + px2 * 4);
+        }
       }
       float ev[64];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         at = *reinterpret_cast<const float4*>(att + prx * 4);
-        const float4* ep = reinterpret_cast<const float4*>(e + prx * 64);
+        const float4* ep = reinterpret_cast<const float4*>(e) + g8_row(prx, 16);     // G8 layout: unit q at ep[q * 8]
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          float4 t4 = __ldg(ep + q);
+          float4 t4 = __ldg(ep + q * G8S);
           ev[4 * q] = t4.x; ev[4 * q + 1] = t4.y; ev[4 * q + 2] = t4.z; ev[4 * q + 3] = t4.w;
         }
       } else {
@@ -778,7 +784,8 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       const float idzw = CF::F16 ? idz * wscale[1] : 1.0f;      // GEMM2 output: undo the dZ row and weight-image scales
       const float q0 = 4.0f * dzs * d0, q1 = 4.0f * dzs * d1, q2 = 4.0f * dzs * d2;    // see epi1_block
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      float* gzrow = (gZ_out != nullptr && valid) ? gZ_out + prx * CC : nullptr;
+      // training: fp32 copy of dZ for the weight-gradient contraction, G8 layout (64 units per pair)
+      float4* gzrow = (gZ_out != nullptr && valid) ? reinterpret_cast<float4*>(gZ_out) + g8_row(prx, CC / 4) : nullptr;
       // block jb (0..3) of this thread: ring chunk kc2, first column cb, ring position pos
       auto blk_col = [&](int jb) { return (hh * (NCH / 2) + jb / PPC) * CF::KCH + (jb % PPC) * 32; };
       auto run_block1 = [&](int jb, const float (&v)[32]) {
@@ -790,7 +797,7 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
           mbar_wait(sm.empty + s, (n & 1) ^ 1);
           if (dbg == 7) ew[1] += clock64() - e_s0;
         }
-        float* gz = gzrow ? gzrow + cb : nullptr;
+        float4* gz = gzrow ? gzrow + (cb / 4) * G8S : nullptr;
         if (use_tsm) epi1_block<CF>(v, Ts + cb, zs, q0, q1, q2, g0, g1, g2, sm.p_img(s), p, (jb % PPC) * (32 / CF::EPU), gz, idz);
         else epi1_block<CF>(v, Tg + cb, zs, q0, q1, q2, g0, g1, g2, sm.p_img(s), p, (jb % PPC) * (32 / CF::EPU), gz, idz);
         if (jb % PPC == PPC - 1) {
@@ -820,9 +827,9 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       for (int k = 0; k < 8; ++k) ef4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         at = *reinterpret_cast<const float4*>(att + prx * 4);
-        const float4* e4 = reinterpret_cast<const float4*>(e + prx * 64 + hh * 32);
+        const float4* e4 = reinterpret_cast<const float4*>(e) + g8_row(prx, 16) + hh * 8 * G8S;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ef4[k] = __ldg(e4 + k);
+        for (int k = 0; k < 8; ++k) ef4[k] = __ldg(e4 + k * G8S);
       }
       // ---------------- epilogue 2: dE -> g_e, g_att   (this half owns f in [32 hh, 32 hh + 32))
       const long long e_t3 = dbg == 7 ? clock64() : 0;
@@ -840,9 +847,9 @@ k_tc_mix_bwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
         if (use_tsm) epi2_part(v, ghs4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idzw, gev, ga0, ga1, ga2, ga3);
         else epi2_part(v, ghg4 + cc * 8, ef4[2 * cc], ef4[2 * cc + 1], at, m, idzw, gev, ga0, ga1, ga2, ga3);
         if (valid) {
-          float4* o = reinterpret_cast<float4*>(ge + prx * 64 + hh * 32 + cc * 8);
+          float4* o = reinterpret_cast<float4*>(ge) + g8_row(prx, 16) + (hh * 8 + cc * 2) * G8S;   // G8 layout
           o[0] = make_float4(gev[0], gev[1], gev[2], gev[3]);
-          o[1] = make_float4(gev[4], gev[5], gev[6], gev[7]);
+          o[G8S] = make_float4(gev[4], gev[5], gev[6], gev[7]);
         }
       };
       {
@@ -972,7 +979,9 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
 // =================================================================================================
 // host side
 // =================================================================================================
-bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
+// K <= 58: the tcgen05 edge kernel's K = 64 operand holds the RBF channels plus three extra columns; the tcgen05
+// kernels share G8-layout buffers, so an engine is tcgen05 for all of them or for none
+bool tc_supported(const Dims& d) { return d.H == 64 && d.A == 4 && d.K <= 58; }
 
 int tc_debug_counters(unsigned long long* out8) {
   SAKE_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_mma_wait, sizeof(unsigned long long) * 8));
@@ -1080,7 +1089,7 @@ static int tc_bwd_impl(const Dims& d, const SakeLayerParams& p, const float* x, 
     XtgArgs a;
     memset(&a, 0, sizeof(a));
     a.e = sv.e; a.att = sv.att; a.xw = CC; a.ones_col = -1;
-    a.G = sc.gZ; a.ldg = CC; a.gw = CC;
+    a.G = sc.gZ; a.ldg = CC; a.g_tt = CC / 4; a.gw = CC;
     a.MXpad = CC; a.NG = CC; a.P = d.P; a.Pdev = d.hdr ? &d.hdr->P : nullptr;
     a.out = gWx; a.ldo = CC; a.out_rows = CC; a.out_cols = CC;
     if (L.push(a)) { set_error("xtg list full"); return SAKE_EINVAL; }

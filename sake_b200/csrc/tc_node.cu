@@ -73,17 +73,17 @@ __device__ __forceinline__ void nt_store_unit(uint8_t* img, int row, int u, cons
   *reinterpret_cast<float4*>(img + NT_IMG + off) = lo;
 }
 
-// Tile-transposed per-atom buffers (stash, record, ssum): thread = atom, and the 16-byte unit u of atom t of tile b
-// sits at float4 index (b * U + u) * 128 + t, so that a warp's access to unit u is 512 contiguous bytes (4 L1
-// wavefronts instead of the 32 of a thread-per-row walk over row-major rows: the node kernels were bound by exactly
-// those wavefronts).  tc_xtg.cu reads the same layout (XtgArgs::x_tt / g_tt).
+// Per-atom buffers of the node kernels (stash, record, ssum) use the G8 layout (common.cuh): thread = atom, and the
+// 16-byte unit u of row r sits at float4 index g8_row(r, U) + 8 u, so that a warp's access to one unit is four full
+// lines (4 L1 wavefronts instead of the 32 of a thread-per-row walk over row-major rows: the node kernels were bound
+// by exactly those wavefronts).  tc_xtg.cu reads the same layout (XtgArgs::x_tt / g_tt).
 __device__ __forceinline__ float4* tt_base(float* buf, int units, int tile, int t) {
-  return reinterpret_cast<float4*>(buf) + (size_t)tile * units * 128 + t;
+  return reinterpret_cast<float4*>(buf) + g8_row((long long)tile * 128 + t, units);
 }
 __device__ __forceinline__ const float4* tt_base(const float* buf, int units, int tile, int t) {
-  return reinterpret_cast<const float4*>(buf) + (size_t)tile * units * 128 + t;
+  return reinterpret_cast<const float4*>(buf) + g8_row((long long)tile * 128 + t, units);
 }
-#define TT(q, col) (q)[((col) >> 2) * 128]            /* the float4 holding columns col .. col+3 (col % 4 == 0) */
+#define TT(q, col) (q)[((col) >> 2) * G8S]            /* the float4 holding columns col .. col+3 (col % 4 == 0) */
 
 struct NodeFwdArgs {
   int R, N, update, has_v, spatial;
@@ -260,12 +260,12 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256 -> D0
   // the 24 row loads of chunk c+1 are issued before the hand-off of chunk c: their latency hides under its MMAs
   float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
-  // ssum is tile-transposed (written so by k_tc_mix_fwd): unit (c'/4)*3 + d holds component d of four coefficients
+  // ssum is in the G8 layout (written so by k_tc_mix_fwd): unit (c'/4)*3 + d holds component d of four coefficients
   float4 sreg[24];
   const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);
   {
 #pragma unroll
-    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * 128);
+    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * G8S);
   }
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {
@@ -287,13 +287,13 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     }
     if (c + 1 < 8) {
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c + 1) * 24 + q) * 128);
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c + 1) * 24 + q) * G8S);
     }
     launch(k, D0, c == 0);
   }
   // node0's first inputs (h, he: 10 chunks of 8 float4) start loading now
   const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
-  const float4* hep = reinterpret_cast<const float4*>(a.he + row * 256);
+  const float4* hep = reinterpret_cast<const float4*>(a.he) + g8_row((long long)row, 64);   // G8: unit q at hep[q * 8]
   float4 creg[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) creg[u] = __ldg(hp + u);
@@ -330,9 +330,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
         nt_store_unit(img_p[k], tid, u, vals);
       }
       if (c + 1 < 10) {
-        const float4* src = c + 1 < 2 ? hp + (c + 1) * 8 : hep + (c + 1 - 2) * 8;
+        const float4* src = c + 1 < 2 ? hp + (c + 1) * 8 : hep + (c + 1 - 2) * 8 * G8S;
+        const int us = c + 1 < 2 ? 1 : G8S;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) creg[u] = __ldg(src + u);
+        for (int u = 0; u < 8; ++u) creg[u] = __ldg(src + u * us);
       }
     } else {
       float v[32];
@@ -471,7 +472,7 @@ struct NodeBwdArgs {
   float *qv, *nbuf;                          // g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
 };
 
-__device__ __forceinline__ void st64_tt(float4* q, int col0, int c, const float* v32) {   // 32 floats of a tile-transposed row
+__device__ __forceinline__ void st64_tt(float4* q, int col0, int c, const float* v32) {   // 32 floats of a G8 row
 #pragma unroll
   for (int u = 0; u < 8; ++u) TT(q, col0 + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
 }
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     den2 = ms + 1e-10f;
   }
   const float inv_den = 1.0f / den;
-  float4* nb = a.nbuf ? tt_base(a.nbuf, NB_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's record (tile-transposed)
+  float4* nb = a.nbuf ? tt_base(a.nbuf, NB_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's record (G8 layout)
   const bool rec = nb != nullptr && valid;
 
   // =============================== forward activations: kept by k_tc_node_post ===============================
@@ -723,10 +724,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     // before the current ones are consumed, so they are in flight during the barrier wait and the TMEM load
     // (SLOTS == 2, the two-CTAs-per-SM variant, has 200 registers per thread: it loads the rows where they are used)
     float4 sreg[24];
-    const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);     // tile-transposed, see the forward kernel
+    const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);     // G8 layout, see the forward kernel
     if constexpr (SLOTS == 4) {
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * 128);
+      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * G8S);
     }
     run_pair(D0, 0);
 #pragma unroll 1
@@ -745,11 +746,11 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
           for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
           if (c0 + 32 < 256) {
 #pragma unroll
-            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c0 / 32 + 1) * 24 + q) * 128);
+            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c0 / 32 + 1) * 24 + q) * G8S);
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 24; ++q) scur[q] = __ldg(ssq + ((c0 / 32) * 24 + q) * 128);
+          for (int q = 0; q < 24; ++q) scur[q] = __ldg(ssq + ((c0 / 32) * 24 + q) * G8S);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -790,8 +791,8 @@ __global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, co
   float acc = 0.f;
   for (int n = n0; n < n1; ++n) {
     const float4 q = *reinterpret_cast<const float4*>(qv + (size_t)n * 4);
-    const float* sp = ssum + ((((size_t)(n >> 7) * 64 + (c >> 2)) * 3) * 128 + (n & 127)) * 4 + (c & 3);   // tile-transposed
-    acc += sp[0] * q.x + sp[512] * q.y + sp[1024] * q.z;
+    const float* sp = ssum + (g8_row(n, 192) + (size_t)(c >> 2) * 3 * G8S) * 4 + (c & 3);   // G8 layout, see the kernels above
+    acc += sp[0] * q.x + sp[4 * G8S] * q.y + sp[8 * G8S] * q.z;
   }
   atomicAdd(gWv + c, acc);
 }

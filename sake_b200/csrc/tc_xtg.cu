@@ -118,7 +118,8 @@ __device__ __forceinline__ XtgSplit xtg_split(const XtgArgs& a) {
   }
   return s;
 }
-__device__ __align__(16) float g_xtg_zeros[256];   // a source row of zeros (pair rows past the end of a contraction)
+__device__ __align__(16) float g_xtg_zeros[2304];  // a source row of zeros (pair rows past the end of a contraction), long
+                                                   // enough for the unit strides of a G8 source
 
 // TCOLS: TMEM columns of the CTA (512: the 256 x 256 x_mixing gradient; 256: everything else, so that two CTAs of
 //        the small contractions share an SM); nstage: operand ring depth (<= XTG_NSTAGE).
@@ -190,7 +191,9 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
     // The 512-column instantiation is the x_mixing gradient (X = e (x) att, 4 + 4 blocks), the 256-column one the rest.
     constexpr bool EMODE = TCOLS == 512;
     const int bt = threadIdx.x - 32;                 // 0..255
-    const int r = bt >> 3, uu = bt & 7;
+    // lanes: 8 rows x 4 unit positions, so that a warp's load covers whole lines of a G8 source (8 rows of one unit =
+    // 128 bytes) and, for row-major sources, 4 x 32 contiguous bytes of each of 8 rows — the same lines either way
+    const int r = (bt & 7) | ((bt >> 6) << 3), uu = (bt >> 3) & 7;
     const uint32_t uoff = sw128_offset((uint32_t)r, (uint32_t)uu);
     const int nxf = EMODE ? 4 : (a.xw >> 6);
     const bool has_ones = !EMODE && a.ones_col >= 0;
@@ -207,46 +210,47 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
         }
     }
     float4 xa[4], xb[4], ga[4], gb[4];               // EMODE: xa[j].xy = the two e features of unit j
-    float gn[8];                                     // narrow G block
+                                                     // a narrow G block (gw < 64, no full block) lives in ga[0], gb[0]
     float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t onew_full = (has_ones && uu == 0) ? 0x00003F80u : 0u;   // ones unit: bf16(1.0) in element 0
-    uint32_t onew = 0u;
+    const bool ones_here = has_ones && uu == 0;      // ones unit: bf16(1.0) in element 0 (valid rows only)
+    bool ones_on = false;
     // One definition path for the loop-carried registers (no per-row branches, which cost a register shuffle at
     // every merge): rows past the end (last stage of the grid only) read a page of zeros instead.
     // this thread's source rows for the next load; every stage bumps them by XKP rows
-    // Tile-transposed sources (x_tt / g_tt = 16-byte units per row of the buffer; written by the thread-per-atom node
-    // kernels so that THEIR accesses coalesce): unit u of row p sits at float4 index ((p >> 7) * U + u) * 128 + (p & 127).
-    // The two float4 of a thread are then 128 float4 apart, consecutive 64-feature blocks 2048, and a stage step is
-    // 32 rows inside a 128-row tile or a jump to the next tile.  Four consecutive rows are 64 contiguous bytes, so a
-    // warp touches 8 lines per load either way.
-    const bool xtt = !EMODE && a.x_tt > 0, gtt = !EMODE && a.g_tt > 0;
-    long long pl = p_beg + r;
-    const float* xrow = EMODE ? a.e + pl * 64 + 2 * uu
-                        : xtt ? a.X + ((((pl >> 7) * a.x_tt + 2 * uu) << 7) + (pl & 127)) * 4
+    // G8 sources (x_tt / g_tt = 16-byte units per row; common.cuh): unit u of row p sits at float4 index
+    // g8_row(p, U) + 8 u.  The two float4 of a thread are then 8 float4 apart and consecutive 64-feature blocks 128;
+    // a stage step (32 rows = 4 groups) is the same number of floats as with row-major rows.  Eight consecutive rows
+    // of one unit are one line, so a warp touches as many lines per load as with row-major rows.
+    const bool xtt = !EMODE && a.x_tt > 0, gtt = a.g_tt > 0;
+    const long long pl = p_beg + r;
+    int left = (int)min((long long)(1 << 30), p_end - pl);          // rows of this thread's slice still to load (<= 0: none)
+    const float* xrow = EMODE ? a.e + (g8_row(pl, 16) + (uu >> 1) * G8S) * 4 + 2 * (uu & 1)   // e features 16 j + 2 uu, +1 (G8)
+                        : xtt ? a.X + (g8_row(pl, a.x_tt) + 2 * uu * G8S) * 4
                               : a.X + pl * a.ldx + 8 * uu;
-    const float* grow = gtt ? a.G + ((((pl >> 7) * a.g_tt + 2 * uu) << 7) + (pl & 127)) * 4 : a.G + pl * a.ldg + 8 * uu;
+    const float* grow = gtt ? a.G + (g8_row(pl, a.g_tt) + 2 * uu * G8S) * 4 : a.G + pl * a.ldg + 8 * uu;
     const float* arow = EMODE ? a.att + pl * 4 : nullptr;
-    const long long xstep = EMODE ? (long long)XKP * 64 : (long long)XKP * a.ldx, gstep = (long long)XKP * a.ldg;
-    const long long xjump = ((long long)a.x_tt * 128 - 96) * 4, gjump = ((long long)a.g_tt * 128 - 96) * 4;   // floats
+    const int xstep = EMODE ? XKP * 64 : xtt ? XKP * a.x_tt * 4 : XKP * a.ldx;      // floats per stage
+    const int gstep = gtt ? XKP * a.g_tt * 4 : XKP * a.ldg;
+    const int xs1 = xtt ? G8S : 1, xs16 = xtt ? 16 * G8S : 16;     // float4 strides: unit pair / 64-feature block
+    const int gs1 = gtt ? G8S : 1, gs16 = gtt ? 16 * G8S : 16;
     auto load_stage = [&]() {
-      const bool rv = pl < p_end;
-      onew = rv ? onew_full : 0u;
-      const float* gp = rv ? grow : g_xtg_zeros + 8 * uu;
-      const int xs1 = (xtt && rv) ? 128 : 1, xs16 = (xtt && rv) ? 2048 : 16;     // float4 strides: unit pair / block
-      const int gs1 = (gtt && rv) ? 128 : 1, gs16 = (gtt && rv) ? 2048 : 16;
+      const bool rv = left > 0;
+      ones_on = rv && ones_here;
+      const float* zp = g_xtg_zeros + 2 * uu * G8S * 4;             // page of zeros: either set of strides stays inside
+      const float* gp = rv ? grow : zp;
       if constexpr (EMODE) {                         // raw operands of E = e (x) att; the product is formed at store time
         at = __ldg(reinterpret_cast<const float4*>(rv ? arow : g_xtg_zeros));
         const float2* ep = reinterpret_cast<const float2*>(rv ? xrow : g_xtg_zeros + 2 * uu);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 8 * j); xa[j].x = ef.x; xa[j].y = ef.y; }
+        for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 4 * G8S * 2 * j); xa[j].x = ef.x; xa[j].y = ef.y; }   // 4 units on
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j);
-          gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + 16 * j + 1);
+          ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
+          gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
         }
         arow += XKP * 4;
       } else {
-        const float4* xp = reinterpret_cast<const float4*>(rv ? xrow : g_xtg_zeros + 8 * uu);
+        const float4* xp = reinterpret_cast<const float4*>(rv ? xrow : zp);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (j < nxf) { xa[j] = __ldg(xp + xs16 * j); xb[j] = __ldg(xp + xs16 * j + xs1); }
@@ -257,14 +261,14 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
             gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
           }
         if (gnarrow) {
+          float gn[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + (i >> 2) * 4 * gs1 + (i & 3)) : 0.f;
+          ga[0] = make_float4(gn[0], gn[1], gn[2], gn[3]);
+          gb[0] = make_float4(gn[4], gn[5], gn[6], gn[7]);
         }
       }
-      const bool cross = (pl & 127) >= 96;               // the next stage's row lies in the next 128-row tile
-      pl += XKP;
-      xrow += xtt ? (cross ? xjump : (long long)XKP * 4) : xstep;
-      grow += gtt ? (cross ? gjump : (long long)XKP * 4) : gstep;
+      left -= XKP; xrow += xstep; grow += gstep;
     };
     if (nst > 0) load_stage();
     for (int it = 0; it < nst; ++it) {
@@ -284,14 +288,13 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
             xtg_store_unit<CF>(xs + j * LBO, ximg, 0u, vals);
           }
         }
-      if (has_ones) *reinterpret_cast<uint4*>(xs + nxf * LBO) = make_uint4(onew, 0u, 0u, 0u);   // (the residual image stays zero)
+      if (has_ones) *reinterpret_cast<uint4*>(xs + nxf * LBO) = make_uint4(ones_on ? 0x00003F80u : 0u, 0u, 0u, 0u);   // (the residual image stays zero)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (j < ngf) {
+        if (j < ngf || (j == 0 && gnarrow)) {
           const float vals[8] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w, gb[j].x, gb[j].y, gb[j].z, gb[j].w};
           xtg_store_unit<CF>(gs + j * LBO, gimg, 0u, vals);
         }
-      if (gnarrow) xtg_store_unit<CF>(gs, gimg, 0u, gn);
       fence_proxy_async();
       mbar_arrive(full + s);
       if (it + 1 < nst) load_stage();
@@ -579,7 +582,7 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   for (int i = 0; i < nb_s; ++i) any_tt = any_tt || small.a[i].x_tt > 0 || small.a[i].g_tt > 0;
   for (int i = 0; i < nb_b; ++i) any_tt = any_tt || big.a[i].x_tt > 0 || big.a[i].g_tt > 0;
   if (any_tt && (no_lean || !lean_s || !lean_b)) {
-    set_error("tc_xtg: tile-transposed sources need the lean builder (SAKE_XTG_GENERIC must be off)");
+    set_error("tc_xtg: G8 sources need the lean builder (SAKE_XTG_GENERIC must be off)");
     return SAKE_EUNSUPPORTED;
   }
   int rc = lean_b && !no_lean ? xtg_launch<512, true, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
