@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restric
                                                   float* __restrict__ proj) {
   extern __shared__ float sm[];
   float* hs = sm;  // [NODES][H]
+  float* ps = sm + NODES * d.H;   // [NODES][NP] output staging (G8 layout only)
   const int r0 = blockIdx.x * NODES;
   if (r0 >= dims_rows(d)) return;                  // ragged: the grid covers the padded worst case
   const int nn = min(NODES, dims_rows(d) - r0);
@@ -34,7 +35,10 @@ __global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restric
     else if (o < 2 * Kp + H) { w = W1 + (o - 2 * Kp); ld = H; }
     else { w = W1 + (size_t)H * H + (o - 2 * Kp - H); ld = H; bias = b1[o - 2 * Kp - H]; }
     if (w == nullptr) {      // padding slot
-      for (int n = 0; n < nn; ++n) proj[d.g8 ? g8_elem(r0 + n, d.NP >> 2, o) : (size_t)(r0 + n) * d.NP + o] = 0.f;
+      for (int n = 0; n < NODES; ++n) {
+        if (d.g8) ps[n * d.NP + o] = 0.f;
+        else if (n < nn) proj[(size_t)(r0 + n) * d.NP + o] = 0.f;
+      }
       continue;
     }
     float acc[NODES];
@@ -45,8 +49,22 @@ __global__ void __launch_bounds__(256) k_node_pre(Dims d, const float* __restric
 #pragma unroll
       for (int n = 0; n < NODES; ++n) acc[n] = fmaf(hs[n * H + f], wv, acc[n]);
     }
-    // G8 layout (tcgen05 engines): 4 consecutive columns of one row are one 16-byte unit, units of a row 128 bytes apart
-    for (int n = 0; n < nn; ++n) proj[d.g8 ? g8_elem(r0 + n, d.NP >> 2, o) : (size_t)(r0 + n) * d.NP + o] = acc[n];
+    if (d.g8) {
+#pragma unroll
+      for (int n = 0; n < NODES; ++n) ps[n * d.NP + o] = acc[n];
+    } else {
+      for (int n = 0; n < nn; ++n) proj[(size_t)(r0 + n) * d.NP + o] = acc[n];
+    }
+  }
+  if (d.g8) {
+    // G8 layout (tcgen05 engines): the CTA's rows are two groups of 8, each one contiguous block of NP/4 units x 8 rows
+    __syncthreads();
+    const int U = d.NP >> 2;
+    float4* p4 = reinterpret_cast<float4*>(proj) + g8_row(r0, U);           // r0 is a multiple of 8
+    for (int t = threadIdx.x; t < (NODES / 8) * U * 8; t += blockDim.x) {
+      const int grp = t / (U * 8), rem = t - grp * U * 8, u = rem >> 3, rr = rem & 7, n = grp * 8 + rr;
+      if (n < nn) p4[t] = *reinterpret_cast<const float4*>(ps + n * d.NP + 4 * u);
+    }
   }
 }
 
@@ -174,57 +192,28 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   for (int t = lane; t < N * A; t += 32) arow[t] = as[t];
   // aggregate: he[c = f*A+a] = sum_j e[j,f] * att[j,a] * m_j
   if (A == 4 && H == 64 && d.g8) {
-    // e in the G8 layout: a group of 8 consecutive pair slots x 16 units is one contiguous 2 KB block.  Lane l reads
-    // float4 l + 32 k of each group (pair l & 7, unit (l >> 3) + 4 k), multiplies by its pair's four attention
-    // weights and keeps 4 x 16 partial sums; the 8 lanes that share a unit meet in three shuffles at the end.
-    const int pl8 = lane & 7, ub = lane >> 3;
-    float acc[4][16];
+    // e and he in the G8 layout (common.cuh).  Lane owns f = 2*lane, 2*lane+1 (half a 16-byte unit) and all four heads;
+    // the 16 lines a pair's features live in are shared by the 8 pairs of its group, so consecutive j hit L1.
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* e0 = e + (size_t)(lane >> 1) * G8S * 4 + (lane & 1) * 2;
+    for (int j0 = 0; j0 < N; j0 += 8) {
+      float2 ev[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+      for (int u = 0; u < 8; ++u)                        // 8 independent loads in flight per lane
+        ev[u] = j0 + u < N ? __ldg(reinterpret_cast<const float2*>(e0 + g8_row(ri.pair0 + j0 + u, 16) * 4)) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
-    const long long q0 = ri.pair0, q1 = ri.pair0 + N;
-    for (long long grp = q0 >> 3; grp <= ((q1 - 1) >> 3); ++grp) {
-      const long long q = grp * 8 + pl8;
-      const bool on = q >= q0 && q < q1;
-      const float4* ep = reinterpret_cast<const float4*>(e) + grp * (16 * G8S) + lane;
-      float4 ev[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ev[k] = on ? __ldg(ep + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (on) {
-        const int j = (int)(q - q0);
-        w = *reinterpret_cast<const float4*>(as + j * 4);
-        if (mrow) { const float m = mrow[j]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float ef[4] = {ev[k].x, ev[k].y, ev[k].z, ev[k].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[k][4 * i] = fmaf(ef[i], w.x, acc[k][4 * i]); acc[k][4 * i + 1] = fmaf(ef[i], w.y, acc[k][4 * i + 1]);
-          acc[k][4 * i + 2] = fmaf(ef[i], w.z, acc[k][4 * i + 2]); acc[k][4 * i + 3] = fmaf(ef[i], w.w, acc[k][4 * i + 3]);
+      for (int u = 0; u < 8; ++u) {
+        if (j0 + u < N) {
+          float4 w = *reinterpret_cast<const float4*>(as + (j0 + u) * 4);
+          if (mrow) { const float m = mrow[j0 + u]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+          acc[0] = fmaf(ev[u].x, w.x, acc[0]); acc[1] = fmaf(ev[u].x, w.y, acc[1]); acc[2] = fmaf(ev[u].x, w.z, acc[2]); acc[3] = fmaf(ev[u].x, w.w, acc[3]);
+          acc[4] = fmaf(ev[u].y, w.x, acc[4]); acc[5] = fmaf(ev[u].y, w.y, acc[5]); acc[6] = fmaf(ev[u].y, w.z, acc[6]); acc[7] = fmaf(ev[u].y, w.w, acc[7]);
         }
       }
     }
-    // reduce-scatter over the 8 lanes of a unit group (56 shuffles): after the three steps lane (b2 b1 b0) holds the
-    // complete sums of values 8 b0 .. 8 b0 + 7 of k = 2 b2 + b1, i.e. two float4 of unit ub + 4 k
-    const bool b2 = (pl8 & 4) != 0, b1 = (pl8 & 2) != 0, b0 = (pl8 & 1) != 0;
-    float w[32], y[16], z[8];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float lo = acc[i >> 4][i & 15], hi = acc[2 + (i >> 4)][i & 15];
-      w[i] = (b2 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b2 ? lo : hi, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = (b1 ? w[16 + i] : w[i]) + __shfl_xor_sync(0xffffffffu, b1 ? w[i] : w[16 + i], 2);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = (b0 ? y[8 + i] : y[i]) + __shfl_xor_sync(0xffffffffu, b0 ? y[i] : y[8 + i], 1);
-    // unit u = ub + 4 k holds he columns 16 u .. 16 u + 15 (c = f*4 + a, f = 4 u + i); he is G8 too (64 units per atom)
-    const int k = (b2 ? 2 : 0) + (b1 ? 1 : 0);
-    float4* ho = reinterpret_cast<float4*>(he) + g8_row(row, 64) + ((ub + 4 * k) * 4 + (b0 ? 2 : 0)) * G8S;
-    ho[0] = make_float4(z[0], z[1], z[2], z[3]);
-    ho[G8S] = make_float4(z[4], z[5], z[6], z[7]);
+    float4* ho = reinterpret_cast<float4*>(he) + g8_row(row, 64) + 2 * lane * G8S;     // he columns 8*lane .. 8*lane+7
+    ho[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    ho[G8S] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   } else if (A == 4 && H == 64) {
     // lane owns f = 2*lane, 2*lane+1 (coalesced float2 loads of e) and all four heads
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -485,7 +474,7 @@ static int ensure_smem(Kern kern, size_t smem) {
 // per-node projections: fills sv.nodeproj
 int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st) {
   int rc;
-  size_t smem = sizeof(float) * NODES * d.H;
+  size_t smem = sizeof(float) * (NODES * d.H + (d.g8 ? NODES * d.NP : 0));
   if ((rc = ensure_smem(k_node_pre, smem))) return rc;
   k_node_pre<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, h, p.mlp_in_kernel, p.mlp_in_bias, p.mlp_out0_kernel,
                                                             p.mlp_out0_bias, sv.nodeproj);

@@ -209,11 +209,10 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
           for (int j = ngf + (gnarrow ? 1 : 0); j < gblocks; ++j) *reinterpret_cast<uint4*>(gs + j * LBO) = z;
         }
     }
-    float4 xa[4], xb[4], ga[4], gb[4];               // EMODE: xa[j].xy = the two e features of unit j
-                                                     // a narrow G block (gw < 64, no full block) lives in ga[0], gb[0]
-    float4 at = make_float4(0.f, 0.f, 0.f, 0.f);
+    // one stage of raw operands in registers.  EMODE: R.xa[j].xy = the two e features of unit j; a narrow G block
+    // (gw < 64, no full block) lives in R.ga[0], R.gb[0]
+    struct StageRegs { float4 xa[4], xb[4], ga[4], gb[4], at; bool ones_on; };
     const bool ones_here = has_ones && uu == 0;      // ones unit: bf16(1.0) in element 0 (valid rows only)
-    bool ones_on = false;
     // One definition path for the loop-carried registers (no per-row branches, which cost a register shuffle at
     // every merge): rows past the end (last stage of the grid only) read a page of zeros instead.
     // this thread's source rows for the next load; every stage bumps them by XKP rows
@@ -233,45 +232,44 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
     const int gstep = gtt ? XKP * a.g_tt * 4 : XKP * a.ldg;
     const int xs1 = xtt ? G8S : 1, xs16 = xtt ? 16 * G8S : 16;     // float4 strides: unit pair / 64-feature block
     const int gs1 = gtt ? G8S : 1, gs16 = gtt ? 16 * G8S : 16;
-    auto load_stage = [&]() {
+    auto load_stage = [&](StageRegs& R) {
       const bool rv = left > 0;
-      ones_on = rv && ones_here;
+      R.ones_on = rv && ones_here;
       const float* zp = g_xtg_zeros + 2 * uu * G8S * 4;             // page of zeros: either set of strides stays inside
       const float* gp = rv ? grow : zp;
       if constexpr (EMODE) {                         // raw operands of E = e (x) att; the product is formed at store time
-        at = __ldg(reinterpret_cast<const float4*>(rv ? arow : g_xtg_zeros));
+        R.at = __ldg(reinterpret_cast<const float4*>(rv ? arow : g_xtg_zeros));
         const float2* ep = reinterpret_cast<const float2*>(rv ? xrow : g_xtg_zeros + 2 * uu);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 4 * G8S * 2 * j); xa[j].x = ef.x; xa[j].y = ef.y; }   // 4 units on
+        for (int j = 0; j < 4; ++j) { const float2 ef = __ldg(ep + 4 * G8S * 2 * j); R.xa[j].x = ef.x; R.xa[j].y = ef.y; }   // 4 units on
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
-          gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
+          R.ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
+          R.gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
         }
         arow += XKP * 4;
       } else {
         const float4* xp = reinterpret_cast<const float4*>(rv ? xrow : zp);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (j < nxf) { xa[j] = __ldg(xp + xs16 * j); xb[j] = __ldg(xp + xs16 * j + xs1); }
+          if (j < nxf) { R.xa[j] = __ldg(xp + xs16 * j); R.xb[j] = __ldg(xp + xs16 * j + xs1); }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (j < ngf) {
-            ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
-            gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
+            R.ga[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j);
+            R.gb[j] = __ldg(reinterpret_cast<const float4*>(gp) + gs16 * j + gs1);
           }
         if (gnarrow) {
           float gn[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) gn[i] = (8 * uu + i < a.gw) ? __ldg(gp + (i >> 2) * 4 * gs1 + (i & 3)) : 0.f;
-          ga[0] = make_float4(gn[0], gn[1], gn[2], gn[3]);
-          gb[0] = make_float4(gn[4], gn[5], gn[6], gn[7]);
+          R.ga[0] = make_float4(gn[0], gn[1], gn[2], gn[3]);
+          R.gb[0] = make_float4(gn[4], gn[5], gn[6], gn[7]);
         }
       }
       left -= XKP; xrow += xstep; grow += gstep;
     };
-    if (nst > 0) load_stage();
-    for (int it = 0; it < nst; ++it) {
+    auto build_stage = [&](const StageRegs& R, int it) {
       const int s = it % nstage, n = it / nstage;
       mbar_wait_warp(empty + s, (n & 1) ^ 1);
       uint8_t* xs = base + s * stage + uoff;
@@ -280,24 +278,43 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
       for (int j = 0; j < 4; ++j)
         if (j < nxf) {
           if constexpr (EMODE) {                     // X = e (x) att, feature c = f*4 + head  (layers.py:206-207)
-            const float vals[8] = {xa[j].x * at.x, xa[j].x * at.y, xa[j].x * at.z, xa[j].x * at.w,
-                                   xa[j].y * at.x, xa[j].y * at.y, xa[j].y * at.z, xa[j].y * at.w};
+            const float vals[8] = {R.xa[j].x * R.at.x, R.xa[j].x * R.at.y, R.xa[j].x * R.at.z, R.xa[j].x * R.at.w,
+                                   R.xa[j].y * R.at.x, R.xa[j].y * R.at.y, R.xa[j].y * R.at.z, R.xa[j].y * R.at.w};
             xtg_store_unit<CF>(xs + j * LBO, ximg, 0u, vals);
           } else {
-            const float vals[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+            const float vals[8] = {R.xa[j].x, R.xa[j].y, R.xa[j].z, R.xa[j].w, R.xb[j].x, R.xb[j].y, R.xb[j].z, R.xb[j].w};
             xtg_store_unit<CF>(xs + j * LBO, ximg, 0u, vals);
           }
         }
-      if (has_ones) *reinterpret_cast<uint4*>(xs + nxf * LBO) = make_uint4(ones_on ? 0x00003F80u : 0u, 0u, 0u, 0u);   // (the residual image stays zero)
+      if (has_ones) *reinterpret_cast<uint4*>(xs + nxf * LBO) = make_uint4(R.ones_on ? 0x00003F80u : 0u, 0u, 0u, 0u);   // (the residual image stays zero)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < ngf || (j == 0 && gnarrow)) {
-          const float vals[8] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w, gb[j].x, gb[j].y, gb[j].z, gb[j].w};
+          const float vals[8] = {R.ga[j].x, R.ga[j].y, R.ga[j].z, R.ga[j].w, R.gb[j].x, R.gb[j].y, R.gb[j].z, R.gb[j].w};
           xtg_store_unit<CF>(gs + j * LBO, gimg, 0u, vals);
         }
       fence_proxy_async();
       mbar_arrive(full + s);
-      if (it + 1 < nst) load_stage();
+    };
+    if constexpr (EMODE) {
+      // the 256 x 256 contraction runs one CTA per SM with registers to spare: two stages of operands are kept in
+      // flight (set B is requested before set A is consumed and vice versa), so a load has a whole build + hand-off
+      // of lead time instead of only the wait for a free ring slot — the kernel was bound by that latency
+      StageRegs A, B;
+      if (nst > 0) load_stage(A);
+      for (int it = 0; it < nst; it += 2) {
+        if (it + 1 < nst) load_stage(B);
+        build_stage(A, it);
+        if (it + 2 < nst) load_stage(A);
+        if (it + 1 < nst) build_stage(B, it + 1);
+      }
+    } else {
+      StageRegs A;
+      if (nst > 0) load_stage(A);
+      for (int it = 0; it < nst; ++it) {
+        build_stage(A, it);
+        if (it + 1 < nst) load_stage(A);
+      }
     }
   } else {
     // ------------------------------------------------------------ builders (thread = pair x 8-feature unit)
