@@ -17,14 +17,17 @@ using namespace tc;
 
 // Operand precision.  kind::tf32 has no MN-major (transposing) operand path on sm_100a (measured: the
 // MMA is a silent no-op), and K-major images with K = pairs need a transposing builder that is L1-bound.
-// kind::f16 does support MN-major, so the fp32-parity engine splits every operand into two bf16 terms
-// (x = hi + mid + O(2^-16 |x|), by truncation) and issues 4 MMAs (hh, hm, mh, mm): weight gradients carry
-// a relative error <= 2e-5 (they are sums over 10^5..10^6 pairs feeding Adam; energies and forces never
-// pass through this kernel).  The bf16 engine uses one bf16 image and one MMA.
+// kind::f16 does support MN-major, so the fp32-parity engine splits every operand into two bf16 terms by
+// round-to-nearest (x = hi + mid + O(2^-17 |x|)) and issues 3 MMAs (hh, hm, mh; the mid*mid product is below the
+// split's own rounding error).  Unbiased rounding errors average out over K = pairs: CPU experiment
+// scripts/xtg_split_error.py 4.4e-6 rms; measured on B200 against the fp64 oracle: worst parameter-gradient error
+// 7.5e-5 of max|g| per tensor at the multi-tile test size (tests/test_gpu_round2.py), energies and forces never pass
+// through this kernel.  make XTG_TRUNC4=1 builds the round-1 scheme (split by truncation, 4 products: 8.7e-5, 10 %
+// slower).  The bf16 engine uses one bf16 image and one MMA.
+#ifndef SAKE_XTG_TRUNC4
+#define SAKE_XTG_RN3 1
+#endif
 template <int ENGINE> struct XCfg;
-// Experimental (make XTG_RN3=1, not the product build): split by round-to-nearest (same instruction count) and
-// drop the mid*mid product.  CPU experiment scripts/xtg_split_error.py: 4.4e-6 rms error against 1.7e-5 of the
-// truncated four-product scheme, because unbiased rounding errors average out over K = pairs; 25 % fewer MMAs.
 #ifdef SAKE_XTG_RN3
 template <> struct XCfg<SAKE_ENGINE_TF32X3> { static constexpr int NSPLIT = 2, NPROD = 3; };
 #else
@@ -99,7 +102,11 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, int c0, int
   }
 }
 
-struct XtgBatch { XtgArgs a[XtgList::MAXP]; };
+struct XtgBatch {
+  XtgArgs a[XtgList::MAXP];
+  int colbase[XtgList::MAXP + 1];   // reduction grid: first block of every problem (one block per output column)
+  int nprob;
+};
 
 // K extent, slice per CTA and number of working CTAs of one problem.  Uniform batches: the host's values.
 // Ragged batches: the extent lives in device memory (a.Pdev), the host sized the grid and the partial-sum
@@ -444,8 +451,10 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
 constexpr int XRED_SLICES = 4;
 __global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_constant__ XtgBatch batch) {
   __shared__ float red[XRED_SLICES][128];
-  const XtgArgs& a = batch.a[blockIdx.y];
-  const int col = blockIdx.x;
+  int pi = 0;
+  while (pi + 1 < batch.nprob && (int)blockIdx.x >= batch.colbase[pi + 1]) ++pi;   // <= 20 problems
+  const XtgArgs& a = batch.a[pi];
+  const int col = blockIdx.x - batch.colbase[pi];
   const int ncta = xtg_split(a).gx;
   if (col >= a.NG || a.partial == nullptr) return;           // block-uniform
   const int tx = threadIdx.x & 127, sl = threadIdx.x >> 7;
@@ -519,23 +528,26 @@ static bool xtg_is_lean(const XtgArgs& a, bool is_big) {
 }
 
 template <int TCOLS, bool LEAN, int MINB>
-static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, int ng_max, size_t smem, int nstage, bool bf,
-                      int prof_kind, long long prof_pairs, cudaStream_t st) {
+static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, size_t smem, int nstage, bool bf, cudaStream_t st) {
   if (nb == 0) return 0;
   if (smem > 200 * 1024) { set_error("tc_xtg: smem %zu", smem); return SAKE_EUNSUPPORTED; }
   static unsigned long long optin_tf = 0, optin_bf = 0;
   const int orc = bf ? smem_optin(k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB>, 200 * 1024, optin_bf)
                      : smem_optin(k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB>, 200 * 1024, optin_tf);
   if (orc) return orc;
-  {
-    ProfScope prof(prof_kind, prof_pairs, st);
-    dim3 grid(gx_max, nb);
-    if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
-    else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
-    dim3 rgrid(ng_max, nb);
-    k_xtg_reduce<<<rgrid, 128 * XRED_SLICES, 0, st>>>(batch);
-  }
-  note_launches(2);
+  dim3 grid(gx_max, nb);
+  if (bf) k_tc_xtg<SAKE_ENGINE_BF16, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+  else k_tc_xtg<SAKE_ENGINE_TF32X3, TCOLS, LEAN, MINB><<<grid, XTG_THREADS, smem, st>>>(batch, nstage);
+  note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+// ONE reduction grid for every problem of both launches: a block per output column, none for columns that do not exist
+static int xtg_reduce_all(const XtgBatch& all, cudaStream_t st) {
+  const int ncols = all.colbase[all.nprob];
+  if (ncols == 0) return 0;
+  k_xtg_reduce<<<ncols, 128 * XRED_SLICES, 0, st>>>(all);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -602,13 +614,36 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
     set_error("tc_xtg: G8 sources need the lean builder (SAKE_XTG_GENERIC must be off)");
     return SAKE_EUNSUPPORTED;
   }
-  int rc = lean_b && !no_lean ? xtg_launch<512, true, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st)
-                              : xtg_launch<512, false, 1>(big, nb_b, gx_b, ng_b, smem_b, NST_BIG, bf, prof_kind, prof_pairs, st);
-  if (rc) return rc;
+  // the small contractions: longest K first, so that the CTAs of the pair-level problems start in the first wave and the
+  // short node-level ones fill the tail
+  for (int i = 1; i < nb_s; ++i)
+    for (int j = i; j > 0 && small.a[j].P > small.a[j - 1].P; --j) { const XtgArgs t = small.a[j]; small.a[j] = small.a[j - 1]; small.a[j - 1] = t; }
+  XtgBatch all;
+  memset(&all, 0, sizeof(all));
+  int ncols = 0;
+  auto add_red = [&](const XtgArgs& a) {
+    if (a.partial == nullptr) return;
+    all.a[all.nprob] = a; all.colbase[all.nprob] = ncols; ncols += a.NG; ++all.nprob;
+  };
+  for (int i = 0; i < nb_b; ++i) add_red(big.a[i]);
+  for (int i = 0; i < nb_s; ++i) add_red(small.a[i]);
+  all.colbase[all.nprob] = ncols;
+  (void)ng_b; (void)ng_s;
+  int rc = 0;
+  {
+    ProfScope prof(prof_kind, prof_pairs, st);
+    rc = lean_b && !no_lean ? xtg_launch<512, true, 1>(big, nb_b, gx_b, smem_b, NST_BIG, bf, st)
+                            : xtg_launch<512, false, 1>(big, nb_b, gx_b, smem_b, NST_BIG, bf, st);
+    if (rc == 0 && nb_s == 0) rc = xtg_reduce_all(all, st);
+  }
+  if (rc || nb_s == 0) return rc;
   // the lean small kernel fits two CTAs per SM (96 registers, 256 TMEM columns, <= 82 KB): 4 builder warps per scheduler
-  const int pk_small = prof_kind == 3 ? 8 : 0;   // profiler kind 8: the batched small contractions of a layer
-  return lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, pk_small, prof_pairs, st)
-                            : xtg_launch<256, false, 1>(small, nb_s, gx_s, ng_s, smem_s, NST_SMALL, bf, pk_small, prof_pairs, st);
+  const int pk_small = prof_kind == 3 ? 8 : 0;   // profiler kind 8: the batched small contractions of a layer + the reduction
+  ProfScope prof(pk_small, prof_pairs, st);
+  rc = lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, smem_s, NST_SMALL, bf, st)
+                          : xtg_launch<256, false, 1>(small, nb_s, gx_s, smem_s, NST_SMALL, bf, st);
+  if (rc) return rc;
+  return xtg_reduce_all(all, st);
 }
 
 int tc_xtg(const XtgArgs& a0, int engine, int prof_kind, cudaStream_t st) {
