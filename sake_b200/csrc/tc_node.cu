@@ -16,7 +16,6 @@ namespace sake {
 using namespace tc;
 
 constexpr int NT_TILE = 128;                 // atoms per CTA = builder threads (warps 0-3)
-constexpr int NT_THREADS = NT_TILE + 32;     // + warp 4: weight-chunk TMA and MMA issue
 constexpr int NT_IMG = NT_TILE * 128;        // one split of the A chunk image (16 KB)
 constexpr int NT_WCH = 2 * 64 * 128;         // one weight chunk: {hi, lo} x 64 output rows x 128 B (16 KB)
 // chunk index of every matrix inside the weight image
@@ -125,10 +124,10 @@ struct NodePipe {
   int c0, c1, c2;                // weight chunk of round wpos and wpos+1 (requested), wpos+2 (requested by the next issue); -1: none
   uint32_t uph;                  // bit i: phase parity the next wait on user barrier i looks for
 
-  __device__ __forceinline__ void init_barriers() {      // one thread
+  __device__ __forceinline__ void init_barriers(int builders) {      // one thread
     for (int i = 0; i < SLOTS; ++i) { mbar_init(wfull + i, 1); mbar_init(wfree + i, 1); }
     for (int i = 0; i < NT_UBARS; ++i) mbar_init(ubar + i, 1);
-    mbar_init(full, NT_TILE); mbar_init(full + 1, NT_TILE);
+    mbar_init(full, builders); mbar_init(full + 1, builders);
     mbar_init(taken, 1); mbar_init(taken + 1, 1);
     fence_barrier_init();
   }
@@ -184,8 +183,17 @@ struct NodePipe {
   }
 };
 
-template <int SLOTS>
-__global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post(NodeFwdArgs a) {
+// HALVES = 2: two threads per atom.  Threads t and t + 128 share TMEM lane t (warps w and w + 4 address the same lane
+// quarter) and split every 32-wide chunk by 16-byte units: half hf owns units 4 hf .. 4 hf + 3, i.e. 16 of the 32
+// columns — of the images it writes, of the accumulator columns it reads back, of the global rows it loads and stores.
+// Everything in the chain is per column, so the halves never exchange data except the three reductions over features
+// (velocity gate logit, v_mixing sums), which meet in shared memory at the end.  A round is bound by the thread-side
+// work of building an image with one warp per scheduler; two threads per atom halve it.  HALVES = 1 (thread = atom)
+// is kept for the two-CTAs-per-SM configuration (SLOTS = 2), whose register budget has no room for 288 threads.
+template <int SLOTS, int HALVES>
+__global__ void __launch_bounds__(NT_TILE * HALVES + 32, SLOTS == 2 ? 2 : 1) k_tc_node_post(NodeFwdArgs a) {
+  constexpr int NTH = NT_TILE * HALVES + 32;             // builders + the issuing warp
+  constexpr int UH = 8 / HALVES, CH = 32 / HALVES;       // units / columns of a chunk owned by one thread
   const int nrows_real = a.hdr ? a.hdr->R : a.R;
   if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
@@ -195,10 +203,11 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS + 4);
+  float4* xch = reinterpret_cast<float4*>(tptr + 4);     // [NT_TILE] partial sums of half 1 -> half 0 (HALVES = 2)
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool upd = a.update != 0, hv = a.has_v != 0, spatial = a.spatial != 0, uv = upd && hv;
   const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
-  for (int t = tid; t < NT_VEC; t += NT_THREADS) {
+  for (int t = tid; t < NT_VEC; t += NTH) {
     const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
     svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
   }
@@ -208,8 +217,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   pp.wring = wring; pp.wfull = bars; pp.wfree = bars + NT_MAXSLOTS; pp.ubar = bars + 2 * NT_MAXSLOTS; pp.wimg = a.wimg;
   pp.full = bars + 2 * NT_MAXSLOTS + NT_UBARS; pp.taken = pp.full + 2; pp.npub = 0; pp.anypub = 0;
   pp.wpos = 0; pp.c0 = 0; pp.c1 = 1; pp.c2 = 2; pp.uph = 0;
-  if (tid == NT_TILE) {
-    pp.init_barriers();
+  if (tid == NT_TILE * HALVES) {
+    pp.init_barriers(NT_TILE * HALVES);
     pp.request(0, 0);
     if (SLOTS == 4) pp.request(1, 1);
   }
@@ -218,14 +227,14 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tptr;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t img_u32[2] = {smem_u32(imgs), smem_u32(imgs + 2 * NT_IMG)};
   uint8_t* const img_p[2] = {imgs, imgs + 2 * NT_IMG};
   const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
               *s_vel2 = svec + 320, *s_wv = svec + 384;
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
 
-  if (warp == 4) {
+  if (warp == 4 * HALVES) {
     // ---------------- issuing warp: the fixed sequence of rounds — post0 (8, -> D0), post2 (2, -> D1), node0 (12, -> D0),
     // node2 (2, -> D1), vel0 (2, -> D0, with a velocity gate); image buffer and user barrier = round parity
     if ((tid & 31) == 0) {
@@ -236,7 +245,9 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       }
     }
   } else {
-  const int n = blockIdx.x * NT_TILE + tid;
+  const int t = tid & (NT_TILE - 1), hf = HALVES == 2 ? tid >> 7 : 0;      // atom (= TMEM lane) and column half
+  const int u0 = hf * UH, c0h = hf * CH;                                   // first unit / column of a chunk owned here
+  const int n = blockIdx.x * NT_TILE + t;
   const bool valid = n < nrows_real;
   const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
@@ -249,30 +260,34 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     den2 = ms + 1e-10f;    // layers.py:221
   }
   const float inv_den = 1.0f / den;
-  float4* ns = (a.stash && valid) ? tt_base(a.stash, NS_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's fwd -> bwd stash
+  float4* ns = (a.stash && valid) ? tt_base(a.stash, NS_LD / 4, blockIdx.x, t) : nullptr;   // this atom's fwd -> bwd stash
   // Image buffer k = round parity; user barrier k tracks the last round that read image k.
   // busy: bit k set while a round on image k is un-waited.
   uint32_t busy = 0;
   auto acquire = [&](int k) { if (busy & (1u << k)) { pp.wait(k); busy &= ~(1u << k); } };
   auto launch = [&](int k, uint32_t, bool) { pp.publish(k); busy |= 1u << k; };   // the issuing warp knows the rest
   auto drain = [&]() { acquire(0); acquire(1); };       // every MMA issued so far is complete (results readable)
+  auto ld_chunk = [&](uint32_t col, float* v) {         // this thread's CH columns of a 32-column accumulator chunk
+    if constexpr (HALVES == 2) tmem_ld16(lane_addr + col + c0h, v); else tmem_ld32(lane_addr + col, v);
+    tmem_ld_wait();
+  };
 
   // ---------------- post0: nrm[c] = sum_d (ssum[c][d] / den)^2  (layers.py:123-129), K = 256 -> D0
-  // the 24 row loads of chunk c+1 are issued before the hand-off of chunk c: their latency hides under its MMAs
-  float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+  // the row loads of chunk c+1 are issued before the hand-off of chunk c: their latency hides under its MMAs
   // ssum is in the G8 layout (written so by k_tc_mix_fwd): unit (c'/4)*3 + d holds component d of four coefficients
-  float4 sreg[24];
-  const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);
+  float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f;
+  float4 sreg[3 * UH];
+  const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, t) + 3 * u0 * G8S;
   {
 #pragma unroll
-    for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * G8S);
+    for (int q = 0; q < 3 * UH; ++q) sreg[q] = __ldg(ssq + q * G8S);
   }
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {
     const int k = c & 1;
     acquire(k);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < UH; ++u) {
       const float4 t0 = sreg[u * 3], t1 = sreg[u * 3 + 1], t2 = sreg[u * 3 + 2];
       const float s[12] = {t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z, t0.w, t1.w, t2.w};
       float vals[4];
@@ -280,40 +295,39 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       for (int i = 0; i < 4; ++i) {
         const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
         vals[i] = a0 * a0 + a1 * a1 + a2 * a2;
-        const float w = s_wv[c * 32 + u * 4 + i];
+        const float w = s_wv[c * 32 + (u0 + u) * 4 + i];
         dv0 = fmaf(w, s[3 * i], dv0); dv1 = fmaf(w, s[3 * i + 1], dv1); dv2 = fmaf(w, s[3 * i + 2], dv2);
       }
-      nt_store_unit(img_p[k], tid, u, vals);
+      nt_store_unit(img_p[k], t, u0 + u, vals);
     }
     if (c + 1 < 8) {
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c + 1) * 24 + q) * G8S);
+      for (int q = 0; q < 3 * UH; ++q) sreg[q] = __ldg(ssq + ((c + 1) * 24 + q) * G8S);
     }
     launch(k, D0, c == 0);
   }
-  // node0's first inputs (h, he: 10 chunks of 8 float4) start loading now
-  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64);
-  const float4* hep = reinterpret_cast<const float4*>(a.he) + g8_row((long long)row, 64);   // G8: unit q at hep[q * 8]
-  float4 creg[8];
+  // node0's first inputs (h, he: 10 chunks) start loading now
+  const float4* hp = reinterpret_cast<const float4*>(a.h + row * 64) + u0;
+  const float4* hep = reinterpret_cast<const float4*>(a.he) + g8_row((long long)row, 64) + u0 * G8S;   // G8: unit q at hep[q * 8]
+  float4 creg[UH];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) creg[u] = __ldg(hp + u);
+  for (int u = 0; u < UH; ++u) creg[u] = __ldg(hp + u);
   drain();
   // ---------------- post2: h_p1 = silu(tp1 + b)  -> D1
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
-    float v[32];
-    tmem_ld32(lane_addr + c * 32, v);
-    tmem_ld_wait();
+    float v[CH];
+    ld_chunk(c * 32, v);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < UH; ++u) {
       float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bp1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bp1[c * 32 + c0h + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        TT(ns, NS_D + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        TT(ns, NS_HP1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + c * 32 + c0h + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_HP1 + c * 32 + c0h + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      nt_store_unit(img_p[c], tid, u, vals);
+      nt_store_unit(img_p[c], t, u0 + u, vals);
     }
     launch(c, D1, c == 0);
   }
@@ -325,34 +339,33 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     acquire(k);
     if (c < 10) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < UH; ++u) {
         const float vals[4] = {creg[u].x, creg[u].y, creg[u].z, creg[u].w};
-        nt_store_unit(img_p[k], tid, u, vals);
+        nt_store_unit(img_p[k], t, u0 + u, vals);
       }
       if (c + 1 < 10) {
         const float4* src = c + 1 < 2 ? hp + (c + 1) * 8 : hep + (c + 1 - 2) * 8 * G8S;
         const int us = c + 1 < 2 ? 1 : G8S;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) creg[u] = __ldg(src + u * us);
+        for (int u = 0; u < UH; ++u) creg[u] = __ldg(src + u * us);
       }
     } else {
-      float v[32];
-      tmem_ld32(lane_addr + 64 + (c - 10) * 32, v);
-      tmem_ld_wait();
+      float v[CH];
+      ld_chunk(64 + (c - 10) * 32, v);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < UH; ++u) {
         float vals[4], dvs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float z = v[4 * u + i] + s_bp2[(c - 10) * 32 + 4 * u + i];
+          const float z = v[4 * u + i] + s_bp2[(c - 10) * 32 + c0h + 4 * u + i];
           vals[i] = spatial ? fsilu_(z) : 0.f;
           dvs[i] = spatial ? fdsilu_(z) : 0.f;
         }
         if (ns) {
-          TT(ns, NS_D + 64 + (c - 10) * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-          TT(ns, NS_HCOMB + (c - 10) * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+          TT(ns, NS_D + 64 + (c - 10) * 32 + c0h + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          TT(ns, NS_HCOMB + (c - 10) * 32 + c0h + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
         }
-        nt_store_unit(img_p[k], tid, u, vals);
+        nt_store_unit(img_p[k], t, u0 + u, vals);
       }
     }
     // D0 was last written by post0 and read (into registers) by post2: both long complete
@@ -362,19 +375,18 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   // ---------------- node2: n1 = silu(t1 + b) -> D1
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
-    float v[32];
-    tmem_ld32(lane_addr + c * 32, v);
-    tmem_ld_wait();
+    float v[CH];
+    ld_chunk(c * 32, v);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < UH; ++u) {
       float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn1[c * 32 + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn1[c * 32 + c0h + 4 * u + i]; vals[i] = fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        TT(ns, NS_D + 128 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        TT(ns, NS_N1 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + 128 + c * 32 + c0h + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_N1 + c * 32 + c0h + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      nt_store_unit(img_p[c], tid, u, vals);
+      nt_store_unit(img_p[c], t, u0 + u, vals);
     }
     launch(c, D1, c == 0);
   }
@@ -383,22 +395,21 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   float y = 0.f;
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
-    float v[32];
-    tmem_ld32(lane_addr + 64 + c * 32, v);
-    tmem_ld_wait();
+    float v[CH];
+    ld_chunk(64 + c * 32, v);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < UH; ++u) {
       const float4 h4 = __ldg(hp + c * 8 + u);
       const float hin[4] = {h4.x, h4.y, h4.z, h4.w};
       float vals[4], dvs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn2[c * 32 + 4 * u + i]; vals[i] = hin[i] + fsilu_(z); dvs[i] = fdsilu_(z); }
+      for (int i = 0; i < 4; ++i) { const float z = v[4 * u + i] + s_bn2[c * 32 + c0h + 4 * u + i]; vals[i] = hin[i] + fsilu_(z); dvs[i] = fdsilu_(z); }
       if (ns) {
-        TT(ns, NS_D + 192 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-        TT(ns, NS_HOUT + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        TT(ns, NS_D + 192 + c * 32 + c0h + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+        TT(ns, NS_HOUT + c * 32 + c0h + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
       }
-      if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-      if (uv) nt_store_unit(img_p[c], tid, u, vals);
+      if (valid) *reinterpret_cast<float4*>(a.h_out + row * 64 + c * 32 + c0h + 4 * u) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+      if (uv) nt_store_unit(img_p[c], t, u0 + u, vals);
     }
     if (uv) launch(c, D0, c == 0);
   }
@@ -406,26 +417,31 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     drain();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(lane_addr + c * 32, v);
-      tmem_ld_wait();
+      float v[CH];
+      ld_chunk(c * 32, v);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < UH; ++u) {
         float av[4], dvs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = 4 * u + i;
-          const float z = v[k] + s_bv1[c * 32 + k];
+          const float z = v[k] + s_bv1[c * 32 + c0h + k];
           av[i] = fsilu_(z); dvs[i] = fdsilu_(z);
-          y = fmaf(av[i], s_vel2[c * 32 + k], y);
+          y = fmaf(av[i], s_vel2[c * 32 + c0h + k], y);
         }
         if (ns) {
-          TT(ns, NS_D + 256 + c * 32 + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
-          TT(ns, NS_AV + c * 32 + 4 * u) = make_float4(av[0], av[1], av[2], av[3]);
+          TT(ns, NS_D + 256 + c * 32 + c0h + 4 * u) = make_float4(dvs[0], dvs[1], dvs[2], dvs[3]);
+          TT(ns, NS_AV + c * 32 + c0h + 4 * u) = make_float4(av[0], av[1], av[2], av[3]);
         }
       }
     }
   }
+  if constexpr (HALVES == 2) {                           // the halves' sums over features meet: half 1 -> half 0
+    if (hf == 1) xch[t] = make_float4(dv0, dv1, dv2, y);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) { const float4 o = xch[t]; dv0 += o.x; dv1 += o.y; dv2 += o.z; y += o.w; }
+  }
+  if (hf == 0) {
   if (ns) reinterpret_cast<float*>(&TT(ns, NS_Y))[0] = y;
   // ---------------- velocity / position update (layers.py:218-232)
   if (valid) {
@@ -442,6 +458,7 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       a.v_out[row * 3] = vn0; a.v_out[row * 3 + 1] = vn1; a.v_out[row * 3 + 2] = vn2;
       a.x_out[row * 3] = xr[0] + vn0; a.x_out[row * 3 + 1] = xr[1] + vn1; a.x_out[row * 3 + 2] = xr[2] + vn2;
     }
+  }
   }
   }   // builders
   tc_fence_before();
@@ -472,18 +489,10 @@ struct NodeBwdArgs {
   float *qv, *nbuf;                          // g_dv / den2 [R,4] (training, v_mixing grad); record or NULL
 };
 
-__device__ __forceinline__ void st64_tt(float4* q, int col0, int c, const float* v32) {   // 32 floats of a G8 row
-#pragma unroll
-  for (int u = 0; u < 8; ++u) TT(q, col0 + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
-}
-__device__ __forceinline__ void st64(float* dst, int c, const float* v32) {     // 32 floats of a row block
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    *reinterpret_cast<float4*>(dst + c * 32 + 4 * u) = make_float4(v32[4 * u], v32[4 * u + 1], v32[4 * u + 2], v32[4 * u + 3]);
-}
-
-template <int SLOTS>
-__global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+template <int SLOTS, int HALVES>
+__global__ void __launch_bounds__(NT_TILE * HALVES + 32, SLOTS == 2 ? 2 : 1) k_tc_node_post_bwd(NodeBwdArgs a) {
+  constexpr int NTH = NT_TILE * HALVES + 32;
+  constexpr int UH = 8 / HALVES, CH = 32 / HALVES;       // units / columns of a 32-wide chunk owned by one thread (see the forward kernel)
   const int nrows_real = a.hdr ? a.hdr->R : a.R;
   if ((int)blockIdx.x * NT_TILE >= nrows_real) return;   // ragged: the grid covers the padded worst case
   extern __shared__ uint8_t smem_raw[];
@@ -494,9 +503,10 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   float* svec = reinterpret_cast<float*>(wring + SLOTS * NT_WCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(svec + NT_VEC);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2 * NT_MAXSLOTS + NT_UBARS + 4);
+  float* xch = reinterpret_cast<float*>(tptr + 4);       // [NT_TILE] row maximum of half 1 -> half 0 (HALVES = 2)
   const int tid = threadIdx.x, warp = tid >> 5;
   const float* vsrc[7] = {a.b_p1, a.b_p2, a.b_n1, a.b_n2, a.b_v1, a.vel2, a.wv};
-  for (int t = tid; t < NT_VEC; t += NT_THREADS) {
+  for (int t = tid; t < NT_VEC; t += NTH) {
     const int k = t < 384 ? t / 64 : 6, i = t < 384 ? t % 64 : t - 384;
     svec[t] = vsrc[k] ? vsrc[k][i] : 0.f;
   }
@@ -514,8 +524,8 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   pp.full = bars + 2 * NT_MAXSLOTS + NT_UBARS; pp.taken = pp.full + 2; pp.npub = 0; pp.anypub = 0;
   pp.wpos = 0; pp.uph = 0;
   pp.c0 = uv ? NTB_VEL0T : NTB_NODE2T; pp.c1 = next_w(pp.c0); pp.c2 = next_w(pp.c1);
-  if (tid == NT_TILE) {
-    pp.init_barriers();
+  if (tid == NT_TILE * HALVES) {
+    pp.init_barriers(NT_TILE * HALVES);
     pp.request(pp.c0, 0);
     if (SLOTS == 4) pp.request(pp.c1, 1);
   }
@@ -524,14 +534,12 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tptr;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t imgA_u32 = smem_u32(imgA), imgB_u32 = smem_u32(imgB);
-  const float *s_bp1 = svec, *s_bp2 = svec + 64, *s_bn1 = svec + 128, *s_bn2 = svec + 192, *s_bv1 = svec + 256,
-              *s_vel2 = svec + 320, *s_wv = svec + 384;
-  (void)s_bp1; (void)s_bp2; (void)s_bn1; (void)s_bn2; (void)s_bv1;
+  const float *s_vel2 = svec + 320, *s_wv = svec + 384;
   const uint32_t D0 = tmem_base, D1 = tmem_base + 64;
   // One GEMM of the chain = the pair (imgA, imgB) = K 64 against two weight chunks; it commits to user barrier ub.
-  if (warp == 4) {
+  if (warp == 4 * HALVES) {
     // ---------------- issuing warp: vel0^T (with a gate), node2^T, six blocks of node0^T, then post2^T and four blocks
     // of post0^T (with spatial attention); blocks alternate D0 / D1 and user barriers 0 / 1
     if ((tid & 31) == 0) {
@@ -550,7 +558,9 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   } else {
   auto run_pair = [&](uint32_t, int) { pp.publish(0); pp.publish(1); };   // the issuing warp knows destination and barrier
 
-  const int n = blockIdx.x * NT_TILE + tid;
+  const int t = tid & (NT_TILE - 1), hf = HALVES == 2 ? tid >> 7 : 0;      // atom (= TMEM lane) and column half
+  const int u0 = hf * UH, c0h = hf * CH;                                   // first unit / column of a chunk owned here
+  const int n = blockIdx.x * NT_TILE + t;
   const bool valid = n < nrows_real;
   const size_t row = valid ? (size_t)n : 0;        // idle lanes read atom 0 (valid memory) and never store
   float den = (float)a.N, den2 = (float)a.N;
@@ -563,27 +573,33 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
     den2 = ms + 1e-10f;
   }
   const float inv_den = 1.0f / den;
-  float4* nb = a.nbuf ? tt_base(a.nbuf, NB_LD / 4, blockIdx.x, tid) : nullptr;   // this atom's record (G8 layout)
+  float4* nb = a.nbuf ? tt_base(a.nbuf, NB_LD / 4, blockIdx.x, t) : nullptr;   // this atom's record (G8 layout)
   const bool rec = nb != nullptr && valid;
+  auto ld_chunk = [&](uint32_t col, float* v) {         // this thread's CH columns of a 32-column accumulator chunk
+    if constexpr (HALVES == 2) tmem_ld16(lane_addr + col + c0h, v); else tmem_ld32(lane_addr + col, v);
+    tmem_ld_wait();
+  };
+  uint8_t* const img_c[2] = {imgA, imgB};
 
   // =============================== forward activations: kept by k_tc_node_post ===============================
   // (round 1 recomputed the forward here: 26 of the kernel's 52 serial chunk-GEMM rounds, on a kernel that is
   // latency-bound at every size; the forward kernel now leaves silu' of the five hidden layers, the inputs of the
   // Dense layers and the gate logit in saved.nstash, 2.6 KB per atom)
-  const float4* nd = tt_base(a.stash, NS_LD / 4, blockIdx.x, valid ? tid : 0);
+  const float4* nd = tt_base(a.stash, NS_LD / 4, blockIdx.x, valid ? t : 0);
   // The X operands of the batched weight-gradient contractions (the inputs of every Dense layer) are read by
   // tc_node_dw where they already live: h, saved.he and the stash fields.  Only the cotangents (and nrm, which
   // falls out of the T loop below) are written to the record: 2.3 KB per atom instead of 4.9 KB + 5.3 KB of
   // thread-per-row copies in front of the chain.
   const float y = reinterpret_cast<const float*>(&TT(nd, NS_Y))[0];
   // =============================== velocity / position update backward (layers.py:226-232) ===============================
+  // (scalars: both halves compute them, half 0 stores)
   float gdv0 = 0.f, gdv1 = 0.f, gdv2 = 0.f, gy = 0.f;
   if (valid) {
     const float dxo0 = a.dx_out ? a.dx_out[row * 3] : 0.f, dxo1 = a.dx_out ? a.dx_out[row * 3 + 1] : 0.f,
                 dxo2 = a.dx_out ? a.dx_out[row * 3 + 2] : 0.f;
     const float dvo0 = a.dv_out ? a.dv_out[row * 3] : 0.f, dvo1 = a.dv_out ? a.dv_out[row * 3 + 1] : 0.f,
                 dvo2 = a.dv_out ? a.dv_out[row * 3 + 2] : 0.f;
-    a.dx[row * 3] = dxo0; a.dx[row * 3 + 1] = dxo1; a.dx[row * 3 + 2] = dxo2;          // x' = x + v'
+    if (hf == 0) { a.dx[row * 3] = dxo0; a.dx[row * 3 + 1] = dxo1; a.dx[row * 3 + 2] = dxo2; }          // x' = x + v'
     if (upd) {
       gdv0 = dvo0 + dxo0; gdv1 = dvo1 + dxo1; gdv2 = dvo2 + dxo2;                        // cotangent of v'
       if (hv) {
@@ -591,79 +607,92 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
         const float* vv = a.v + row * 3;
         const float ggate = gdv0 * vv[0] + gdv1 * vv[1] + gdv2 * vv[2];
         gy = ggate * gt * (1.0f - 0.5f * gt);
-        if (a.dv) { a.dv[row * 3] = gt * gdv0; a.dv[row * 3 + 1] = gt * gdv1; a.dv[row * 3 + 2] = gt * gdv2; }
+        if (a.dv && hf == 0) { a.dv[row * 3] = gt * gdv0; a.dv[row * 3 + 1] = gt * gdv1; a.dv[row * 3 + 2] = gt * gdv2; }
       }
-    } else if (a.dv && hv) {
+    } else if (a.dv && hv && hf == 0) {
       a.dv[row * 3] = dvo0; a.dv[row * 3 + 1] = dvo1; a.dv[row * 3 + 2] = dvo2;          // v passes through
     }
-    if (rec && uv) reinterpret_cast<float*>(&TT(nb, NB_GY))[0] = gy;
-    if (a.qv) *reinterpret_cast<float4*>(a.qv + row * 4) = make_float4(gdv0 / den2, gdv1 / den2, gdv2 / den2, 0.f);
+    if (rec && uv && hf == 0) reinterpret_cast<float*>(&TT(nb, NB_GY))[0] = gy;
+    if (a.qv && hf == 0) *reinterpret_cast<float4*>(a.qv + row * 4) = make_float4(gdv0 / den2, gdv1 / den2, gdv2 / den2, 0.f);
   }
   // =============================== backward chain ===============================
-  float gho[64];                                         // cotangent of h' (dh_out + velocity-gate path)
+  // every 64-wide vector lives as two chunks of 32 columns; this thread holds columns c*32 + c0h .. + CH - 1 of chunk c
+  float gho[2][CH];                                      // cotangent of h' (dh_out + velocity-gate path)
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.dh_out + row * 64) + u);
-    gho[4 * u] = t4.x; gho[4 * u + 1] = t4.y; gho[4 * u + 2] = t4.z; gho[4 * u + 3] = t4.w;
-  }
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int u = 0; u < UH; ++u) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.dh_out + row * 64) + c * 8 + u0 + u);
+      gho[c][4 * u] = t4.x; gho[c][4 * u + 1] = t4.y; gho[c][4 * u + 2] = t4.z; gho[c][4 * u + 3] = t4.w;
+    }
+  // write CH floats (this thread's part of chunk c) of a record field / a row-major row
+  auto rec_store = [&](int col0, int c, const float* v) {
+#pragma unroll
+    for (int u = 0; u < UH; ++u) TT(nb, col0 + c * 32 + c0h + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  };
+  auto row_store = [&](float* dst, int c, const float* v) {
+#pragma unroll
+    for (int u = 0; u < UH; ++u)
+      *reinterpret_cast<float4*>(dst + c * 32 + c0h + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  };
+  auto img_store = [&](int c, const float* v) {
+#pragma unroll
+    for (int u = 0; u < UH; ++u) nt_store_unit(img_c[c], t, u0 + u, v + 4 * u);
+  };
   if (uv) {
     // g_tv = vel2 * g_y * silu'(tv);  g_h' += g_tv W_v1^T
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      float gtv[32];
+      float gtv[CH];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 d4 = TT(nd, 256 + c * 32 + 4 * u);
-        gtv[4 * u] = s_vel2[c * 32 + 4 * u] * gy * d4.x; gtv[4 * u + 1] = s_vel2[c * 32 + 4 * u + 1] * gy * d4.y;
-        gtv[4 * u + 2] = s_vel2[c * 32 + 4 * u + 2] * gy * d4.z; gtv[4 * u + 3] = s_vel2[c * 32 + 4 * u + 3] * gy * d4.w;
+      for (int u = 0; u < UH; ++u) {
+        const float4 d4 = TT(nd, 256 + c * 32 + c0h + 4 * u);
+        const int k0 = c * 32 + c0h + 4 * u;
+        gtv[4 * u] = s_vel2[k0] * gy * d4.x; gtv[4 * u + 1] = s_vel2[k0 + 1] * gy * d4.y;
+        gtv[4 * u + 2] = s_vel2[k0 + 2] * gy * d4.z; gtv[4 * u + 3] = s_vel2[k0 + 3] * gy * d4.w;
       }
-      if (rec) st64_tt(nb, NB_GTV, c, gtv);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, gtv + 4 * u);
+      if (rec) rec_store(NB_GTV, c, gtv);
+      img_store(c, gtv);
     }
     run_pair(D0, 0);
     pp.wait(0);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(lane_addr + c * 32, v);
-      tmem_ld_wait();
+      float v[CH];
+      ld_chunk(c * 32, v);
 #pragma unroll
-      for (int k = 0; k < 32; ++k) gho[c * 32 + k] += v[k];
+      for (int k = 0; k < CH; ++k) gho[c][k] += v[k];
     }
   }
   // g_t2 = g_h' * silu'(t2);  g_t1 = (g_t2 W_n2^T) * silu'(t1)
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    float g2[32];
+    float g2[CH];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float4 d4 = TT(nd, 192 + c * 32 + 4 * u);
-      g2[4 * u] = gho[c * 32 + 4 * u] * d4.x; g2[4 * u + 1] = gho[c * 32 + 4 * u + 1] * d4.y;
-      g2[4 * u + 2] = gho[c * 32 + 4 * u + 2] * d4.z; g2[4 * u + 3] = gho[c * 32 + 4 * u + 3] * d4.w;
+    for (int u = 0; u < UH; ++u) {
+      const float4 d4 = TT(nd, 192 + c * 32 + c0h + 4 * u);
+      g2[4 * u] = gho[c][4 * u] * d4.x; g2[4 * u + 1] = gho[c][4 * u + 1] * d4.y;
+      g2[4 * u + 2] = gho[c][4 * u + 2] * d4.z; g2[4 * u + 3] = gho[c][4 * u + 3] * d4.w;
     }
-    if (rec) st64_tt(nb, NB_GT2, c, g2);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, g2 + 4 * u);
+    if (rec) rec_store(NB_GT2, c, g2);
+    img_store(c, g2);
   }
   run_pair(D1, 0);
   pp.wait(0);
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
-    float v[32];
-    tmem_ld32(lane_addr + 64 + c * 32, v);
-    tmem_ld_wait();
+    float v[CH];
+    ld_chunk(64 + c * 32, v);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float4 d4 = TT(nd, 128 + c * 32 + 4 * u);
+    for (int u = 0; u < UH; ++u) {
+      const float4 d4 = TT(nd, 128 + c * 32 + c0h + 4 * u);
       v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
     }
-    if (rec) st64_tt(nb, NB_GT1, c, v);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+    if (rec) rec_store(NB_GT1, c, v);
+    img_store(c, v);
   }
   // g_cat = g_t1 W_n1^T : six 64-row blocks [dh | g_he (4 blocks) | g_hcomb]; the g_t1 image stays in place
-  float gp2[64];                                         // g_tp2 = g_hcomb * silu'(tp2)
+  float gp2[2][CH];                                      // g_tp2 = g_hcomb * silu'(tp2)
   // block b+1 is issued before block b is read back: its MMAs run under the read-back (accumulators D0 / D1 and
   // user barriers 0 / 1 alternate; the g_t1 images are read-only during the loop)
   run_pair(D0, 0);
@@ -671,26 +700,24 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   for (int b = 0; b < 6; ++b) {
     if (b + 1 < 6) run_pair(((b + 1) & 1) ? D1 : D0, (b + 1) & 1);
     pp.wait(b & 1);
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(lane_addr + (b & 1) * 64 + c * 32, v);
-      tmem_ld_wait();
+      float v[CH];
+      ld_chunk((b & 1) * 64 + c * 32, v);
       if (b == 0) {
         if (valid) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] += c == 0 ? gho[k] : gho[32 + k];
-          st64(a.dh + row * 64, c, v);
+          for (int k = 0; k < CH; ++k) v[k] += gho[c][k];
+          row_store(a.dh + row * 64, c, v);
         }
       } else if (b < 5) {
-        if (valid) st64(a.ghe + row * 256 + (b - 1) * 64, c, v);
+        if (valid) row_store(a.ghe + row * 256 + (b - 1) * 64, c, v);
       } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 d4 = TT(nd, 64 + c * 32 + 4 * u);
-          const float g0 = v[4 * u] * d4.x, g1 = v[4 * u + 1] * d4.y, g2 = v[4 * u + 2] * d4.z, g3 = v[4 * u + 3] * d4.w;
-          if (c == 0) { gp2[4 * u] = g0; gp2[4 * u + 1] = g1; gp2[4 * u + 2] = g2; gp2[4 * u + 3] = g3; }
-          else { gp2[32 + 4 * u] = g0; gp2[32 + 4 * u + 1] = g1; gp2[32 + 4 * u + 2] = g2; gp2[32 + 4 * u + 3] = g3; }
+        for (int u = 0; u < UH; ++u) {
+          const float4 d4 = TT(nd, 64 + c * 32 + c0h + 4 * u);
+          gp2[c][4 * u] = v[4 * u] * d4.x; gp2[c][4 * u + 1] = v[4 * u + 1] * d4.y;
+          gp2[c][4 * u + 2] = v[4 * u + 2] * d4.z; gp2[c][4 * u + 3] = v[4 * u + 3] * d4.w;
         }
       }
     }
@@ -699,35 +726,32 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
   float4* Trow = reinterpret_cast<float4*>(a.T) + row * 256;
   if (spatial) {
     // g_tp1 = (g_tp2 W_p2^T) * silu'(tp1)
-    if (rec) { st64_tt(nb, NB_GTP2, 0, gp2); st64_tt(nb, NB_GTP2, 1, gp2 + 32); }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { nt_store_unit(imgA, tid, u, gp2 + 4 * u); nt_store_unit(imgB, tid, u, gp2 + 32 + 4 * u); }
+    if (rec) { rec_store(NB_GTP2, 0, gp2[0]); rec_store(NB_GTP2, 1, gp2[1]); }
+    img_store(0, gp2[0]); img_store(1, gp2[1]);
     run_pair(D0, 0);
     pp.wait(0);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(lane_addr + c * 32, v);
-      tmem_ld_wait();
+      float v[CH];
+      ld_chunk(c * 32, v);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 d4 = TT(nd, c * 32 + 4 * u);
+      for (int u = 0; u < UH; ++u) {
+        const float4 d4 = TT(nd, c * 32 + c0h + 4 * u);
         v[4 * u] *= d4.x; v[4 * u + 1] *= d4.y; v[4 * u + 2] *= d4.z; v[4 * u + 3] *= d4.w;
       }
-      if (rec) st64_tt(nb, NB_GTP1, c, v);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) nt_store_unit(c == 0 ? imgA : imgB, tid, u, v + 4 * u);
+      if (rec) rec_store(NB_GTP1, c, v);
+      img_store(c, v);
     }
     // g_nrm = g_tp1 W_p1^T (four 64-row blocks);  T[c][d] = 2 ssum[c][d] g_nrm[c] / den^2 + Wv[c] g_dv[d] / den2
     const float k2 = 2.0f * inv_den * inv_den, q0 = gdv0 / den2, q1 = gdv1 / den2, q2 = gdv2 / den2;
-    // same look-ahead over the four blocks; the 24 row loads of ssum for the next 32 coefficients are issued
+    // same look-ahead over the four blocks; the row loads of ssum for the next 32 coefficients are issued
     // before the current ones are consumed, so they are in flight during the barrier wait and the TMEM load
     // (SLOTS == 2, the two-CTAs-per-SM variant, has 200 registers per thread: it loads the rows where they are used)
-    float4 sreg[24];
-    const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, tid);     // G8 layout, see the forward kernel
+    float4 sreg[3 * UH];
+    const float4* ssq = tt_base(a.ssum, 192, blockIdx.x, t) + 3 * u0 * G8S;     // G8 layout, see the forward kernel
     if constexpr (SLOTS == 4) {
 #pragma unroll
-      for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + q * G8S);
+      for (int q = 0; q < 3 * UH; ++q) sreg[q] = __ldg(ssq + q * G8S);
     }
     run_pair(D0, 0);
 #pragma unroll 1
@@ -736,45 +760,49 @@ __global__ void __launch_bounds__(NT_THREADS, SLOTS == 2 ? 2 : 1) k_tc_node_post
       pp.wait(b & 1);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(lane_addr + (b & 1) * 64 + c * 32, v);
-        tmem_ld_wait();
-        const int c0 = b * 64 + c * 32;
-        float4 scur[24];
+        float v[CH];
+        ld_chunk((b & 1) * 64 + c * 32, v);
+        const int cb = b * 64 + c * 32;                  // first coefficient of the chunk; this thread: cb + c0h ..
+        float4 scur[3 * UH];
         if constexpr (SLOTS == 4) {
 #pragma unroll
-          for (int q = 0; q < 24; ++q) scur[q] = sreg[q];
-          if (c0 + 32 < 256) {
+          for (int q = 0; q < 3 * UH; ++q) scur[q] = sreg[q];
+          if (cb + 32 < 256) {
 #pragma unroll
-            for (int q = 0; q < 24; ++q) sreg[q] = __ldg(ssq + ((c0 / 32 + 1) * 24 + q) * G8S);
+            for (int q = 0; q < 3 * UH; ++q) sreg[q] = __ldg(ssq + ((cb / 32 + 1) * 24 + q) * G8S);
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 24; ++q) scur[q] = __ldg(ssq + ((c0 / 32) * 24 + q) * G8S);
+          for (int q = 0; q < 3 * UH; ++q) scur[q] = __ldg(ssq + ((cb / 32) * 24 + q) * G8S);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UH; ++u) {
           const float4 t0 = scur[u * 3], t1 = scur[u * 3 + 1], t2 = scur[u * 3 + 2];
           const float s[12] = {t0.x, t1.x, t2.x, t0.y, t1.y, t2.y, t0.z, t1.z, t2.z, t0.w, t1.w, t2.w};
-#pragma unroll
+          const int cc = cb + c0h + 4 * u;
           float nrm[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float gk = k2 * v[4 * u + i], w = upd ? s_wv[c0 + 4 * u + i] : 0.f;
-            const float t0 = fmaf(w, q0, gk * s[3 * i]), t1 = fmaf(w, q1, gk * s[3 * i + 1]), t2 = fmaf(w, q2, gk * s[3 * i + 2]);
-            tmx = fmaxf(tmx, fmaxf(fabsf(t0), fmaxf(fabsf(t1), fabsf(t2))));
-            if (valid) Trow[c0 + 4 * u + i] = make_float4(t0, t1, t2, 0.f);
+            const float gk = k2 * v[4 * u + i], w = upd ? s_wv[cc + i] : 0.f;
+            const float t0_ = fmaf(w, q0, gk * s[3 * i]), t1_ = fmaf(w, q1, gk * s[3 * i + 1]), t2_ = fmaf(w, q2, gk * s[3 * i + 2]);
+            tmx = fmaxf(tmx, fmaxf(fabsf(t0_), fmaxf(fabsf(t1_), fabsf(t2_))));
+            if (valid) Trow[cc + i] = make_float4(t0_, t1_, t2_, 0.f);
             const float a0 = s[3 * i] * inv_den, a1 = s[3 * i + 1] * inv_den, a2 = s[3 * i + 2] * inv_den;
             nrm[i] = a0 * a0 + a1 * a1 + a2 * a2;            // layers.py:123-129: the X operand of post0's weight gradient
           }
-          if (rec) TT(nb, NB_NRM + c0 + 4 * u) = make_float4(nrm[0], nrm[1], nrm[2], nrm[3]);
+          if (rec) TT(nb, NB_NRM + cc) = make_float4(nrm[0], nrm[1], nrm[2], nrm[3]);
         }
       }
     }
   } else if (valid) {
-    for (int c = 0; c < 256; ++c) Trow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = hf * (256 / HALVES); c < (hf + 1) * (256 / HALVES); ++c) Trow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (valid) a.tmax[row] = tmx;
+  if constexpr (HALVES == 2) {                           // the row maximum of |T| over both column halves
+    if (hf == 1) xch[t] = tmx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) tmx = fmaxf(tmx, xch[t]);
+  }
+  if (valid && hf == 0) a.tmax[row] = tmx;
   }   // builders
   tc_fence_before();
   __syncthreads();
@@ -832,13 +860,14 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   a.nbuf = g ? sc.nbuf : nullptr;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
   const bool deep = tiles <= 2 * node_num_sms();        // few tiles: latency configuration (see NodePipe)
-  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + 1024;
+  // deep: 4 weight slots, two threads per atom (288 threads, one CTA per SM); else 2 slots, thread = atom, two CTAs per SM
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + (deep ? 2048 : 0) + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
-  { const int rc = deep ? smem_optin(k_tc_node_post_bwd<4>, smem, optin4) : smem_optin(k_tc_node_post_bwd<2>, smem, optin2); if (rc) return rc; }
+  { const int rc = deep ? smem_optin(k_tc_node_post_bwd<4, 2>, smem, optin4) : smem_optin(k_tc_node_post_bwd<2, 1>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(7, d.R, st);
-    if (deep) k_tc_node_post_bwd<4><<<tiles, NT_THREADS, smem, st>>>(a);
-    else k_tc_node_post_bwd<2><<<tiles, NT_THREADS, smem, st>>>(a);
+    if (deep) k_tc_node_post_bwd<4, 2><<<tiles, 2 * NT_TILE + 32, smem, st>>>(a);
+    else k_tc_node_post_bwd<2, 1><<<tiles, NT_TILE + 32, smem, st>>>(a);
   }
   if (wvg) k_wv_grad<<<(d.R + 15) / 16, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
   note_launches(wvg ? 2 : 1);
@@ -871,13 +900,13 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.h_out = h_out; a.x_out = x_out; a.v_out = v_out; a.stash = sv.nstash;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
   const bool deep = tiles <= 2 * node_num_sms();
-  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + 1024;
+  const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + (deep ? 2048 : 0) + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
-  { const int rc = deep ? smem_optin(k_tc_node_post<4>, smem, optin4) : smem_optin(k_tc_node_post<2>, smem, optin2); if (rc) return rc; }
+  { const int rc = deep ? smem_optin(k_tc_node_post<4, 2>, smem, optin4) : smem_optin(k_tc_node_post<2, 1>, smem, optin2); if (rc) return rc; }
   {
     ProfScope prof(6, d.R, st);
-    if (deep) k_tc_node_post<4><<<tiles, NT_THREADS, smem, st>>>(a);
-    else k_tc_node_post<2><<<tiles, NT_THREADS, smem, st>>>(a);
+    if (deep) k_tc_node_post<4, 2><<<tiles, 2 * NT_TILE + 32, smem, st>>>(a);
+    else k_tc_node_post<2, 1><<<tiles, NT_TILE + 32, smem, st>>>(a);
   }
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
