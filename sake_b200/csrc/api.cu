@@ -375,8 +375,6 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
       ws = side->s;
     }
     if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, ws))) return rc;
-    tc_edge_finish(xl, ws);
-    tc_node_finish(xl, ws);
     if (side) {
       SAKE_CUDA_CHECK(cudaEventRecord(side->done[slot], ws));
       side->pending[slot] = true;

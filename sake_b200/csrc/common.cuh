@@ -330,6 +330,10 @@ struct XtgArgs {
   const long long* Pdev;               // device-resident K extent (RaggedHdr::P or ::R64), or NULL
   float* out; int ldo, out_rows, out_cols;   // out[r][c] += D[r][c], r < out_rows, c < out_cols
   float* extra; int extra_rows, extra_ld;    // extra[r - out_rows][c] += D[r][c] for the next extra_rows rows
+  float* extra2; int extra2_col0;            // single extra row split over two vectors: columns >= extra2_col0 go to extra2
+  // RBF mean / width gradients folded into the reduction (tc_edge.cu): the two rows behind out_rows hold, for column
+  // 128 + k, S1 = sum_p w_pk and S2 = sum_p t_p w_pk:  dmu_k += 2 beta_k S1,  dbeta_k -= S2 - mu_k S1
+  const float *mb_mu, *mb_beta; float *mb_gmu, *mb_gbeta; int mb_K;
   float* partial;                            // scratch for per-CTA partial sums (tc_xtg_partial_bytes()); NULL = atomics
   int gx;                                    // CTAs assigned to this problem (set by the launcher)
 };
@@ -339,11 +343,6 @@ struct XtgList {
   static constexpr int MAXP = 20;
   XtgArgs a[MAXP];
   int n = 0;
-  // small follow-up kernels that consume `extra` rows of some problems
-  float *post_tmp = nullptr, *g_post2_bias = nullptr, *g_post0_bias = nullptr;
-  float *mb_extra = nullptr, *g_mu = nullptr, *g_beta = nullptr;
-  const float *mu = nullptr, *beta = nullptr;
-  int K = 0;
   int push(const XtgArgs& q) { if (n >= MAXP) return -1; a[n++] = q; return 0; }
 };
 int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st);
@@ -417,7 +416,5 @@ int tc_edge_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
 int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask, const Saved& sv,
                 const BwdScratch& sc, float* dx, const SakeLayerGrads* g, void* wscratch, void* escratch, XtgList& L,
                 float* g_pair_u, float* g_pair_p, cudaStream_t st);
-void tc_edge_finish(const XtgList& L, cudaStream_t st);
-void tc_node_finish(const XtgList& L, cudaStream_t st);
 
 }  // namespace sake

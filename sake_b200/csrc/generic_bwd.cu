@@ -998,11 +998,6 @@ int gen_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, c
 }
 
 // weight gradients of node_mlp / post_norm_mlp / velocity_mlp from the per-node record (K = nodes)
-__global__ void k_post_bias_finish(const float* __restrict__ tmp, float* __restrict__ gbp2, float* __restrict__ gbp1) {
-  const int t = threadIdx.x;
-  if (t < 64) gbp2[t] += tmp[t];
-  else if (t < 128) gbp1[t - 64] += tmp[t];
-}
 size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) * rows_pad128(d.R) * NB_LD) + 1024; }
 
 // direct (the tcgen05 node kernels ran): the X operands are read where they live — h, saved.he and the forward
@@ -1011,7 +1006,6 @@ size_t tc_node_dw_scratch_bytes(const Dims& d) { return align_up(sizeof(float) *
 int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, const SakeLayerGrads& g, const BwdScratch& sc,
                XtgList& L, cudaStream_t st) {
   const float* nb = sc.nbuf;
-  float* tmp = sc.nbuf + rows_pad128(d.R) * NB_LD;     // [128] bias scratch
   // a source: row-major (ld floats per row, tt = 0) or a field of a G8 buffer (tt = units per row; common.cuh)
   struct Src { const float* p; int ld, tt; };
   auto rowmajor = [](const float* p, int ld) { return Src{p, ld, 0}; };
@@ -1044,9 +1038,8 @@ int tc_node_dw(const Dims& d, const float* h, const Saved& sv, bool direct, cons
   }
   if (d.spatial) {
     // post_norm_mlp (layers.py:85-92); the ones-row of the first call carries both bias gradients
-    SAKE_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 128, st));
-    rc |= call(direct ? stash(NS_HP1) : rec(NB_HP1), 64, 64, 128, rec(NB_GTP2), 128, 128, g.post2_kernel, 64, 64, 64, tmp, 128);
-    L.post_tmp = tmp; L.g_post2_bias = g.post2_bias; L.g_post0_bias = g.post0_bias;
+    rc |= call(direct ? stash(NS_HP1) : rec(NB_HP1), 64, 64, 128, rec(NB_GTP2), 128, 128, g.post2_kernel, 64, 64, 64, g.post2_bias, 128);
+    if (rc == 0) { L.a[L.n - 1].extra2 = g.post0_bias; L.a[L.n - 1].extra2_col0 = 64; }   // columns 64.. = sums of g_tp1
     rc |= call(rec(NB_NRM), 256, -1, 256, rec(NB_GTP1), 64, 64, g.post0_kernel, 64, 256, 64, nullptr, 64);
   }
   if (d.update && d.has_v) {
@@ -1081,13 +1074,6 @@ int tc_node_pre_dw(const Dims& d, const float* h, const SakeLayerGrads& g, const
   rc |= call(2 * Kp + H, H, g.mlp_out0_kernel + (size_t)H * H, H, g.mlp_out0_bias);
   if (rc) { set_error("xtg list full"); return SAKE_EINVAL; }
   return 0;
-}
-
-void tc_node_finish(const XtgList& L, cudaStream_t st) {
-  if (L.post_tmp) {
-    k_post_bias_finish<<<1, 128, 0, st>>>(L.post_tmp, L.g_post2_bias, L.g_post0_bias);
-    note_launches(1);
-  }
 }
 
 int gen_mix_dw_from_gz(const Dims& d, const Saved& sv, const float* gZ, float* gWx, cudaStream_t st) {

@@ -54,17 +54,33 @@ __global__ void __launch_bounds__(256) k_ragged_classes(int B, int N, const int*
   __syncthreads();
   for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&hist[clamp_n(n_real[b], N)], 1);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int m = 0, rw = 0, pr = 0, tl = 0;
-    for (int n = 0; n < RG_CLS; ++n) {
-      cmol[n] = m; crow[n] = rw; cpair[n] = pr; ctile[n] = tl;
+  // exclusive prefixes of molecules / rows / pairs / tiles over the classes: four Hillis-Steele scans side by side
+  // (a serial loop over the 129 classes in one thread was most of this kernel's 26 us)
+  __shared__ int4 scan[2][256];
+  {
+    const int n = threadIdx.x;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (n < RG_CLS) {
       const int rows = hist[n] * n;
-      m += hist[n]; rw += rows; pr += rows * n;
-      if (n > 0) { const int rpt = 128 / n; tl += (rows + rpt - 1) / rpt; }
+      v = make_int4(hist[n], rows, rows * n, n > 0 ? (rows + 128 / n - 1) / (128 / n) : 0);
     }
-    cmol[RG_CLS] = m; crow[RG_CLS] = rw; cpair[RG_CLS] = pr; ctile[RG_CLS] = tl;
-    r.hdr->R = rw; r.hdr->num_tiles = tl; r.hdr->B = B; r.hdr->reserved = 0;
-    r.hdr->P = pr; r.hdr->R64 = rw;
+    scan[0][n] = v;
+    __syncthreads();
+    int cur = 0;
+    for (int o = 1; o < 256; o <<= 1) {
+      int4 w = scan[cur][n];
+      if (n >= o) { const int4 q = scan[cur][n - o]; w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w; }
+      scan[cur ^ 1][n] = w;
+      cur ^= 1;
+      __syncthreads();
+    }
+    const int4 inc = scan[cur][n];                       // inclusive prefix; exclusive = inclusive - own
+    if (n < RG_CLS) { cmol[n] = inc.x - v.x; crow[n] = inc.y - v.y; cpair[n] = inc.z - v.z; ctile[n] = inc.w - v.w; }
+    if (n == RG_CLS - 1) {
+      cmol[RG_CLS] = inc.x; crow[RG_CLS] = inc.y; cpair[RG_CLS] = inc.z; ctile[RG_CLS] = inc.w;
+      r.hdr->R = inc.y; r.hdr->num_tiles = inc.w; r.hdr->B = B; r.hdr->reserved = 0;
+      r.hdr->P = inc.z; r.hdr->R64 = inc.y;
+    }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < RG_CLS; t += blockDim.x) {

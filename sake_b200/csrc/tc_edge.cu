@@ -675,16 +675,6 @@ __global__ void k_pair_terms_out(long long P, int K, int Kp, const float* __rest
   else if (g_u) { const int k = c - 64; g_u[pr * Kp + k] = k < K ? v : 0.f; }
 }
 
-// dmu_k += 2 beta_k S1_k ;  dbeta_k += -(S2_k - mu_k S1_k)   with S1 = sum_p w_pk, S2 = sum_p t_p w_pk
-__global__ void k_mubeta_finish(int K, const float* __restrict__ mu, const float* __restrict__ beta,
-                                const float* __restrict__ extra, float* __restrict__ gmu, float* __restrict__ gbeta) {
-  const int k = threadIdx.x;
-  if (k >= K) return;
-  const float s1 = extra[128 + k], s2 = extra[PB_LD + 128 + k];
-  gmu[k] += 2.0f * beta[k] * s1;
-  gbeta[k] += -(s2 - mu[k] * s1);
-}
-
 // ---- host ------------------------------------------------------------------------------------------
 bool tc_edge_supported(const Dims& d) { return d.H == 64 && d.A == 4 && d.K <= 58; }
 
@@ -782,13 +772,14 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     q.extra = g->mlp_out2_bias; q.extra_rows = 1; q.extra_ld = 64;
     L.push(q);
     // dW1[2H : 2H+K+1] (RBF channels + distance row, layers.py:22) and the RBF mean / width sums
-    SAKE_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(float) * 2 * PB_LD, st));
     memset(&q, 0, sizeof(q));
     q.X = gbuf; q.ldx = 64; q.x_tt = 16; q.xw = 64; q.ones_col = -1; q.G = PB; q.ldg = PB_LD; q.g_tt = PB_LD / 4; q.gw = PB_LD; q.MXpad = 128; q.NG = PB_LD;
     q.P = d.P; q.Pdev = d.hdr ? &d.hdr->P : nullptr; q.out = g->mlp_out0_kernel + (size_t)2 * d.H * d.H; q.ldo = 64; q.out_rows = d.K + 1; q.out_cols = 64;
-    q.extra = extra; q.extra_rows = 2; q.extra_ld = PB_LD;
+    // the two rows behind the K+1 outputs (the ones column and the t column of X) are the sums S1, S2 of the RBF mean /
+    // width gradients: finished inside the reduction (XtgArgs::mb_*), no scratch rows and no follow-up kernel
+    q.extra = nullptr; q.extra_rows = 2; q.extra_ld = PB_LD;
+    q.mb_mu = p.rbf_means; q.mb_beta = p.rbf_betas; q.mb_gmu = g->rbf_means; q.mb_gbeta = g->rbf_betas; q.mb_K = d.K;
     L.push(q);
-    L.mb_extra = extra; L.mu = p.rbf_means; L.beta = p.rbf_betas; L.g_mu = g->rbf_means; L.g_beta = g->rbf_betas; L.K = d.K;
     // dWs, dbs (layers.py:80):  e^T g_q
     memset(&q, 0, sizeof(q));
     q.X = sv.e; q.ldx = 64; q.x_tt = 16; q.xw = 64; q.ones_col = 64; q.G = sc.gatt; q.ldg = 4; q.g_tt = 1; q.gw = 4; q.MXpad = 128; q.NG = 16;   // [P,4] rows = G8 with one unit
@@ -797,13 +788,6 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     if (L.push(q)) { set_error("xtg list full"); return SAKE_EINVAL; }
   }
   return 0;
-}
-
-void tc_edge_finish(const XtgList& L, cudaStream_t st) {
-  if (L.mb_extra) {
-    k_mubeta_finish<<<1, 64, 0, st>>>(L.K, L.mu, L.beta, L.mb_extra, L.g_mu, L.g_beta);
-    note_launches(1);
-  }
 }
 
 }  // namespace sake

@@ -485,6 +485,19 @@ __global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_c
       for (int k = 1; k < XRED_SLICES; ++k) tot += red[k][tx];
       if (row < a.out_rows) {
         if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += tot;
+      } else if (a.mb_gmu != nullptr) {
+        // rows out_rows (S1) and out_rows + 1 (S2) of column 128 + k: the thread that owns S2 rebuilds S1 from the
+        // slices (same 128-row block) and finishes the RBF mean / width gradients (utils.py:61-65)
+        const int k = col - 128;
+        if (row == a.out_rows + 1 && k >= 0 && k < a.mb_K) {
+          float s1 = red[0][tx - 1];
+#pragma unroll
+          for (int q = 1; q < XRED_SLICES; ++q) s1 += red[q][tx - 1];
+          a.mb_gmu[k] += 2.0f * a.mb_beta[k] * s1;
+          a.mb_gbeta[k] += -(tot - a.mb_mu[k] * s1);
+        }
+      } else if (a.extra2 != nullptr && col >= a.extra2_col0) {
+        a.extra2[col - a.extra2_col0] += tot;
       } else if (col < a.extra_ld) {
         a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += tot;
       }
@@ -589,6 +602,10 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
       poff += need;
     } else {
       a.partial = nullptr;                                 // falls back to atomics
+    }
+    if (a.partial == nullptr && (a.extra2 != nullptr || a.mb_gmu != nullptr)) {
+      set_error("tc_xtg: split / folded extra rows need the partial-sum buffer");
+      return SAKE_EINVAL;
     }
     if (is_big) {
       if (smem > smem_b) smem_b = smem;
