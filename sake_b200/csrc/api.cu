@@ -339,6 +339,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   if (tc_node) sc.nodeWT = sv.nodeWT;                 // transposed copies left by the forward call
   sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
+  sc.qv = (tc_node && grads && d.update && d.spatial) ? (float*)(b + SL.noded) : nullptr;
   if (tc_node)
     rc = tc_node_post_bwd(d, *params, h, v, mask, sv, dh_out, dx_out, dv_out, dh, dx, dv, grads, sc, sv.wnode,
                           b + SL.noded, st);

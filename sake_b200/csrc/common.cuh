@@ -99,6 +99,7 @@ struct BwdScratch {
   float* gcut;      // [P]     cotangent of the pair distance through the cosine cutoff (NULL without cutoff)
   float* nodeWT;       // transposed copies of the node-level weight matrices (k_node_wt)
   float* nbuf;         // per-node record for the node-level weight-gradient contractions (tcgen05 engines, training)
+  float* qv;           // [R,4] g_dv / den2 per atom (tcgen05 node kernel -> v_mixing gradient in k_pair_reduce), or NULL
   float* xtg_partial;  // per-CTA partial sums of the weight-gradient contractions (tcgen05 engines, training)
 };
 

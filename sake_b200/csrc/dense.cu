@@ -4,7 +4,8 @@
 
 namespace sake {
 
-static constexpr int DR = 16;  // rows per CTA
+static constexpr int DR = 16;   // rows per CTA, forward
+static constexpr int DRB = 16;  // rows per CTA, backward (64 measured slower: the kernel is bound by the serial work of a CTA, not by its atomics)
 
 __global__ void __launch_bounds__(256) k_dense_fwd(long long rows, int in, int out, int act,
                                                    const float* __restrict__ x, const float* __restrict__ w,
@@ -38,17 +39,17 @@ __global__ void __launch_bounds__(256) k_dense_bwd(long long rows, int in, int o
                                                    float* __restrict__ db, const RaggedHdr* hdr) {
   extern __shared__ float sm[];
   if (hdr) rows = hdr->R;
-  if ((long long)blockIdx.x * DR >= rows) return;
-  float* xs = sm;             // [DR][in]
-  float* gs = xs + DR * in;   // [DR][out]  cotangent of the pre-activation
-  float* ws = gs + DR * out;  // [in][out + 1]  weights, row stride padded: both access patterns are conflict-free
+  if ((long long)blockIdx.x * DRB >= rows) return;
+  float* xs = sm;             // [DRB][in]
+  float* gs = xs + DRB * in;   // [DRB][out]  cotangent of the pre-activation
+  float* ws = gs + DRB * out;  // [in][out + 1]  weights, row stride padded: both access patterns are conflict-free
   const int ldw = out + 1;
-  const long long r0 = (long long)blockIdx.x * DR;
-  const int nn = (int)min((long long)DR, rows - r0);
-  for (int t = threadIdx.x; t < DR * in; t += blockDim.x) xs[t] = (t / in) < nn ? x[r0 * in + t] : 0.f;
+  const long long r0 = (long long)blockIdx.x * DRB;
+  const int nn = (int)min((long long)DRB, rows - r0);
+  for (int t = threadIdx.x; t < DRB * in; t += blockDim.x) xs[t] = (t / in) < nn ? x[r0 * in + t] : 0.f;
   for (int t = threadIdx.x; t < in * out; t += blockDim.x) ws[(t / out) * ldw + (t % out)] = w[t];
   __syncthreads();
-  for (int t = threadIdx.x; t < DR * out; t += blockDim.x) {
+  for (int t = threadIdx.x; t < DRB * out; t += blockDim.x) {
     const int n = t / out, o = t % out;
     float gv = 0.f;
     if (n < nn) {
@@ -103,11 +104,11 @@ int dense_fwd(long long rows, int in, int out, int act, const float* x, const fl
 int dense_bwd(long long rows, int in, int out, int act, const float* x, const float* w, const float* b,
               const float* dy, float* dx, float* dw, float* db, const RaggedHdr* hdr, cudaStream_t st) {
   if (rows == 0) return 0;
-  size_t smem = sizeof(float) * (DR * (in + out) + (size_t)in * (out + 1));
+  size_t smem = sizeof(float) * (DRB * (in + out) + (size_t)in * (out + 1));
   if (smem > 227 * 1024) { set_error("dense: features %d/%d too large", in, out); return SAKE_EUNSUPPORTED; }
   static unsigned long long optin = 0;   // H = 128 stages 66 KB of weights: opt in beyond the 48 KB default
   if (smem > 48 * 1024) { const int rc = smem_optin(k_dense_bwd, 227 * 1024, optin); if (rc) return rc; }
-  k_dense_bwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db, hdr);
+  k_dense_bwd<<<(unsigned)((rows + DRB - 1) / DRB), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db, hdr);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

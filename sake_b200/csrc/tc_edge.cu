@@ -609,10 +609,24 @@ int tc_attn_bwd(const Dims& d, const float* x, const Saved& sv, const BwdScratch
 //   row sums     sum_j rec[(n, j)]: for each of the 8 atoms in turn, the 8 threads of a unit read 8 consecutive j and
 //                the partial sums meet in three shuffles; thread a' keeps the sum of atom a'.
 // Every thread then owns both sums of (its atom, its unit) and writes the G8 rows of gproj itself.
+// Training with update = True also finishes the v_mixing gradient here (layers.py:94,220-223):
+//   gWv[c] += sum_n sum_d ssum[n][c][d] * qv[n][d],  qv = g_dv / den2 left by k_tc_node_post_bwd; thread = coefficient c.
 __global__ void __launch_bounds__(256) k_pair_reduce(Dims d, const float* __restrict__ PB,
-                                                     float* __restrict__ gproj, float* __restrict__ dx) {
+                                                     float* __restrict__ gproj, float* __restrict__ dx,
+                                                     const float* __restrict__ ssum, const float* __restrict__ qv,
+                                                     float* __restrict__ gWv) {
   const int n0 = blockIdx.x * 8, R = dims_rows(d);
   if (n0 >= R) return;
+  if (gWv != nullptr) {
+    const int c = threadIdx.x;
+    const float* sp = ssum + (g8_row(n0, 192) + (size_t)(c >> 2) * 3 * G8S) * 4 + (c & 3);   // G8: the 8 atoms of this CTA are one group
+    float acc = 0.f;
+    for (int a2 = 0; a2 < 8 && n0 + a2 < R; ++a2) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(qv) + n0 + a2);
+      acc += sp[4 * a2] * q.x + sp[4 * G8S + 4 * a2] * q.y + sp[8 * G8S + 4 * a2] * q.z;
+    }
+    atomicAdd(gWv + c, acc);
+  }
   const int K = d.K, Kp = d.Kp, NP = d.NP;
   const int ap = threadIdx.x & 7, u = threadIdx.x >> 3;            // u = 0 .. 31
   const float4* pb = reinterpret_cast<const float4*>(PB) + u * G8S;
@@ -754,7 +768,8 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     ProfScope prof(5, d.P, st);
     k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
   }
-  k_pair_reduce<<<(d.R + 7) / 8, 256, 0, st>>>(d, PB, sc.gproj, dx);
+  const bool wvg = g != nullptr && d.update && d.spatial && sc.qv != nullptr;
+  k_pair_reduce<<<(d.R + 7) / 8, 256, 0, st>>>(d, PB, sc.gproj, dx, sv.ssum, sc.qv, wvg ? g->v_mixing_kernel : nullptr);
   note_launches(2);
   if (g_pair_u || g_pair_p) {
     // cotangents of the `he` terms are columns of the per-pair record: g_z1 = PB[:, 0:64], g_u = PB[:, 64:64+Kp)

@@ -809,22 +809,6 @@ __global__ void __launch_bounds__(NT_TILE * HALVES + 32, SLOTS == 2 ? 2 : 1) k_t
   if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
-// gWv[c] += sum_n sum_d ssum[n][c][d] * g_dv[n][d] / den2[n]     (layers.py:94,220-223; training only)
-__global__ void __launch_bounds__(256) k_wv_grad(int R, const RaggedHdr* hdr, const float* __restrict__ ssum,
-                                                 const float* __restrict__ qv, float* __restrict__ gWv) {
-  if (hdr) R = hdr->R;
-  if ((int)blockIdx.x * 16 >= R) return;
-  const int c = threadIdx.x;
-  const int n0 = blockIdx.x * 16, n1 = min(R, n0 + 16);
-  float acc = 0.f;
-  for (int n = n0; n < n1; ++n) {
-    const float4 q = *reinterpret_cast<const float4*>(qv + (size_t)n * 4);
-    const float* sp = ssum + (g8_row(n, 192) + (size_t)(c >> 2) * 3 * G8S) * 4 + (c & 3);   // G8 layout, see the kernels above
-    acc += sp[0] * q.x + sp[4 * G8S] * q.y + sp[8 * G8S] * q.z;
-  }
-  atomicAdd(gWv + c, acc);
-}
-
 static int node_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -855,8 +839,8 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
   a.dh = dh; a.dx = dx; a.dv = dv; a.T = sc.T; a.ghe = sc.ghe; a.tmax = sc.tmax;
   a.stash = sv.nstash;
-  const bool wvg = g != nullptr && d.update && d.spatial;
-  a.qv = wvg ? (float*)nscratch : nullptr;
+  a.qv = sc.qv;                                           // v_mixing gradient: finished by k_pair_reduce (tc_edge.cu)
+  (void)nscratch;
   a.nbuf = g ? sc.nbuf : nullptr;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
   const bool deep = tiles <= 2 * node_num_sms();        // few tiles: latency configuration (see NodePipe)
@@ -869,8 +853,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
     if (deep) k_tc_node_post_bwd<4, 2><<<tiles, 2 * NT_TILE + 32, smem, st>>>(a);
     else k_tc_node_post_bwd<2, 1><<<tiles, NT_TILE + 32, smem, st>>>(a);
   }
-  if (wvg) k_wv_grad<<<(d.R + 15) / 16, 256, 0, st>>>(d.R, d.hdr, sv.ssum, a.qv, g->v_mixing_kernel);
-  note_launches(wvg ? 2 : 1);
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
