@@ -222,7 +222,8 @@ def traffic_lookup(workload, engine, kernel):
 
 
 KIND_NAMES = {1: "mix_fwd", 2: "mix_bwd", 3: "mix_dw", 4: "edge_fwd", 5: "edge_bwd", 6: "node_post", 7: "node_post_bwd",
-              8: "dw_small"}
+              8: "dw_small", 9: "node_pre", 10: "attn_fwd", 11: "pair_reduce", 12: "node_pre_bwd", 13: "attn_bwd",
+              14: "dense"}
 # algorithmic FLOPs per pair (kinds 1-5, 8) / per atom (6, 7) of one launch
 KIND_FLOP = {1: FLOP_MIX, 2: FLOP_MIX, 3: FLOP_MIX, 4: FLOP_EDGE, 5: 2 * FLOP_EDGE, 6: FLOP_NODE, 7: 2 * FLOP_NODE,
              8: FLOP_EDGE}
@@ -599,7 +600,7 @@ def main():
         d[1] += 1
     roofline = None
     if by_kind:
-        dom = max(by_kind, key=lambda k: by_kind[k][0])
+        dom = max((k for k in by_kind if k in KIND_FLOP), key=lambda k: by_kind[k][0])
         tot, cnt = by_kind[dom]
         avg_ms = tot / cnt
         units = head["units"][dom]

@@ -288,7 +288,9 @@ int sake_adam_step(int64_t n, float* params, const float* grads, float* m, float
  * the launch stream.  begin(capacity) arms it, collect() synchronises the recorded events and
  * returns how many records were written: ms[i] = duration, kind[i] = 1 mix-forward, 2 mix-backward (dX),
  * 3 mix-dW, 4 edge-forward, 5 edge-backward, 6 node-tail forward, 7 node-tail backward, 8 small weight-gradient
- * contractions; pairs[i] = atom pairs (kinds 6, 7: atoms) of the padded batch that launch covers. */
+ * contractions + the partial-sum reduction of the layer, 9 per-node projections, 10 softmax + aggregate, 11 pair-record
+ * reductions, 12 per-node projection backward, 13 softmax backward, 14 dense embedding / readout;
+ * pairs[i] = atom pairs (kinds 6, 7, 9, 12, 14: atoms / rows) of the padded batch that launch covers. */
 int sake_profile_begin(int32_t capacity);
 int sake_profile_collect(float* ms, int32_t* kind, int64_t* pairs, int32_t capacity);
 

@@ -253,7 +253,8 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
   Saved sv = carve_saved(d, saved, tc_edge, engine);
-  if ((rc = gen_node_pre(d, *params, h, sv, st))) return rc;
+  const bool tc_node_f = engine != SAKE_ENGINE_FP32 && tc_node_supported(d);
+  if ((rc = tc_node_f ? tc_node_pre(d, *params, h, sv, st) : gen_node_pre(d, *params, h, sv, st))) return rc;
   if (tc_edge) rc = tc_edge_fwd(d, *params, x, mask, sv, sv.wedge, st);
   else rc = gen_edge_fwd(d, *params, x, mask, sv, st);
   if (rc) return rc;
@@ -289,7 +290,7 @@ int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void
   if (d.spatial && (rc = tc_mix_prepare(*params, sv.wmix, engine, st))) return rc;
   if (tc_edge_supported(d) && (rc = tc_edge_prepare(d, *params, sv.wedge, st))) return rc;
   if (tc_node_supported(d)) {
-    if ((rc = tc_node_prepare(*params, sv.wnode, st))) return rc;
+    if ((rc = tc_node_prepare(d, *params, sv.wnode, st))) return rc;
     if ((rc = gen_node_wt(d, *params, sv.nodeWT, st))) return rc;
   }
   return 0;

@@ -398,7 +398,8 @@ int tc_mix_fwd(const Dims& d, const SakeLayerParams& p, const float* x, const fl
 // weight operand images (built by sake_layer_prepare, or by the forward call when d.prepared == 0)
 int tc_mix_prepare(const SakeLayerParams& p, void* wmix, int engine, cudaStream_t st);
 int tc_edge_prepare(const Dims& d, const SakeLayerParams& p, void* wedge, cudaStream_t st);
-int tc_node_prepare(const SakeLayerParams& p, void* wnode, cudaStream_t st);
+int tc_node_prepare(const Dims& d, const SakeLayerParams& p, void* wnode, cudaStream_t st);
+int tc_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st);
 // mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
                const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L,

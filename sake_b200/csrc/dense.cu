@@ -96,6 +96,7 @@ int dense_fwd(long long rows, int in, int out, int act, const float* x, const fl
   if (smem > 227 * 1024) { set_error("dense: in_features %d too large", in); return SAKE_EUNSUPPORTED; }
   static unsigned long long optin = 0;
   if (smem > 48 * 1024) { const int rc = smem_optin(k_dense_fwd, 227 * 1024, optin); if (rc) return rc; }
+  ProfScope prof(14, rows, st);
   k_dense_fwd<<<(unsigned)((rows + DR - 1) / DR), 256, smem, st>>>(rows, in, out, act, x, w, b, y, hdr);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -108,6 +109,7 @@ int dense_bwd(long long rows, int in, int out, int act, const float* x, const fl
   if (smem > 227 * 1024) { set_error("dense: features %d/%d too large", in, out); return SAKE_EUNSUPPORTED; }
   static unsigned long long optin = 0;   // H = 128 stages 66 KB of weights: opt in beyond the 48 KB default
   if (smem > 48 * 1024) { const int rc = smem_optin(k_dense_bwd, 227 * 1024, optin); if (rc) return rc; }
+  ProfScope prof(14, rows, st);
   k_dense_bwd<<<(unsigned)((rows + DRB - 1) / DRB), 256, smem, st>>>(rows, in, out, act, x, w, b, dy, dx, dw, db, hdr);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -1147,6 +1147,7 @@ int gen_node_pre_bwd(const Dims& d, const SakeLayerParams& p, const float* h, fl
   int rc;
   size_t smem = sizeof(float) * (NODES * (d.NP + 2 * d.H) + 2 * PRE_WROWS * 64 + 16);
   if ((rc = ensure_smem(k_node_pre_bwd, smem))) return rc;
+  ProfScope prof(12, d.R, st);
   k_node_pre_bwd<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, p, carve_node_wt(d, sc.nodeWT), h, sc.gproj, dh,
                                                                g ? *g : null_grads(), g != nullptr);
   note_launches(1);

@@ -476,6 +476,7 @@ int gen_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const 
   int rc;
   size_t smem = sizeof(float) * (NODES * d.H + (d.g8 ? NODES * d.NP : 0));
   if ((rc = ensure_smem(k_node_pre, smem))) return rc;
+  ProfScope prof(9, d.R, st);
   k_node_pre<<<(d.R + NODES - 1) / NODES, 256, smem, st>>>(d, h, p.mlp_in_kernel, p.mlp_in_bias, p.mlp_out0_kernel,
                                                             p.mlp_out0_bias, sv.nodeproj);
   note_launches(1);
@@ -502,6 +503,7 @@ int gen_attn_fwd(const Dims& d, const float* x, const float* mask, const Saved& 
   while (nw > 1 && sizeof(float) * d.N * d.A * nw > 160 * 1024) nw >>= 1;
   size_t smem = sizeof(float) * d.N * d.A * nw;
   if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
+  ProfScope prof(10, d.P, st);
   k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, x, mask, sv.e, sv.logit, sv.att, sv.he);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());

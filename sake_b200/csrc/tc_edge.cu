@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_tc(Dims d, const float* __rest
 }
 
 int tc_attn_bwd(const Dims& d, const float* x, const Saved& sv, const BwdScratch& sc, cudaStream_t st) {
+  ProfScope prof(13, d.P, st);
   k_attn_bwd_tc<<<(d.R + 7) / 8, 256, 0, st>>>(d, x, sv.att, sv.logit, sc.gatt, d.cutoff ? sc.gcut : nullptr);
   note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
@@ -769,7 +770,10 @@ int tc_edge_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const f
     k_tc_edge<true><<<edge_grid(a.g), EDGE_THREADS, smem, st>>>(a);
   }
   const bool wvg = g != nullptr && d.update && d.spatial && sc.qv != nullptr;
-  k_pair_reduce<<<(d.R + 7) / 8, 256, 0, st>>>(d, PB, sc.gproj, dx, sv.ssum, sc.qv, wvg ? g->v_mixing_kernel : nullptr);
+  {
+    ProfScope prof(11, d.P, st);
+    k_pair_reduce<<<(d.R + 7) / 8, 256, 0, st>>>(d, PB, sc.gproj, dx, sv.ssum, sc.qv, wvg ? g->v_mixing_kernel : nullptr);
+  }
   note_launches(2);
   if (g_pair_u || g_pair_p) {
     // cotangents of the `he` terms are columns of the per-pair record: g_z1 = PB[:, 0:64], g_u = PB[:, 64:64+Kp)

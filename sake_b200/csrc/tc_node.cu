@@ -24,7 +24,11 @@ constexpr int NTW_POST0 = 0, NTW_POST2 = 8, NTW_NODE0 = 10, NTW_NODE2 = 22, NTW_
 constexpr int NTB_VEL0T = 26, NTB_NODE2T = 28, NTB_NODE0T = 30, NTB_POST2T = 42, NTB_POST0T = 44, NTB_CHUNKS = 52;
 constexpr int NT_VEC = 64 * 6 + 256;         // b_p1 b_p2 b_n1 b_n2 b_v1 vel2 | v_mixing
 
-size_t tc_node_w_bytes() { return (size_t)NTB_CHUNKS * NT_WCH + 256; }
+// weight image of k_tc_node_pre behind the chunks of the node tail: [K chunk (2)][{hi, lo}][256 output rows x 128 B] + 256 biases
+constexpr size_t NTP_OFF = (size_t)NTB_CHUNKS * NT_WCH + 1024;
+constexpr int NTP_WSPLIT = 256 * 128;                    // one split of one K chunk (32 KB)
+constexpr int NTP_WBYTES = 4 * NTP_WSPLIT;               // 128 KB
+size_t tc_node_w_bytes() { return NTP_OFF + NTP_WBYTES + 1024; }
 
 // weight image: chunk c = K rows [32c', 32c'+32) of its matrix W[in][64]; B operand rows = outputs
 __global__ void k_node_w_prep(const SakeLayerParams p, uint8_t* __restrict__ img, int nchunks) {
@@ -83,6 +87,129 @@ __device__ __forceinline__ const float4* tt_base(const float* buf, int units, in
   return reinterpret_cast<const float4*>(buf) + g8_row((long long)tile * 128 + t, units);
 }
 #define TT(q, col) (q)[((col) >> 2) * G8S]            /* the float4 holding columns col .. col+3 (col % 4 == 0) */
+
+// ---- per-node projections on the tensor cores ---------------------------------------------------------------
+// proj[n] = h[n] @ [W_in[0:H] | W_in[H:2H] | W_1[0:H] | W_1[H:2H]] + [0 | b_in | 0 | b_1]   (layers.py:30,33-38; layout of
+// nodeproj in common.cuh): one 3xTF32 GEMM [128 atoms x 64] x [64 x 256] per tile, thread = atom = TMEM lane, G8 rows out.
+// Replaces the CUDA-core k_node_pre for the tcgen05 engines (cfg5: 109 -> ~20 us per layer call).
+__global__ void k_node_pre_w_prep(const SakeLayerParams p, int H, int K, int Kp, uint8_t* __restrict__ img,
+                                  float* __restrict__ bias) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 256) {
+    float b = 0.f;
+    if (t >= Kp && t < Kp + K) b = p.mlp_in_bias[t - Kp];
+    else if (t >= 2 * Kp + H && t < 2 * Kp + 2 * H) b = p.mlp_out0_bias[t - 2 * Kp - H];
+    bias[t] = b;
+  }
+  if (t >= 2 * 256 * 8) return;
+  const int chunk = t / (256 * 8), o = (t / 8) % 256, u = t % 8;
+  float vals[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = chunk * 32 + u * 4 + i;                // input feature
+    float v = 0.f;
+    if (o < Kp) { if (o < K) v = p.mlp_in_kernel[(size_t)k * K + o]; }
+    else if (o < 2 * Kp) { if (o - Kp < K) v = p.mlp_in_kernel[(size_t)(H + k) * K + (o - Kp)]; }
+    else if (o < 2 * Kp + H) v = p.mlp_out0_kernel[(size_t)k * H + (o - 2 * Kp)];
+    else if (o < 2 * Kp + 2 * H) v = p.mlp_out0_kernel[(size_t)(H + k) * H + (o - 2 * Kp - H)];
+    vals[i] = v;
+  }
+  uint8_t* base = img + (size_t)chunk * 2 * NTP_WSPLIT;
+  const uint32_t off = sw128_offset((uint32_t)o, (uint32_t)u);
+  float4 hi, lo;
+  split_tf32(vals[0], hi.x, lo.x); split_tf32(vals[1], hi.y, lo.y);
+  split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
+  *reinterpret_cast<float4*>(base + off) = hi;
+  *reinterpret_cast<float4*>(base + NTP_WSPLIT + off) = lo;
+}
+
+struct NodePreArgs { int R, NP; const RaggedHdr* hdr; const float* h; const uint8_t* wimg; const float* bias; float* proj; };
+
+__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_pre(NodePreArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024_shared(smem_raw);
+  uint8_t* sw = base;                                    // weight image, 128 KB
+  uint8_t* imgs = base + NTP_WBYTES;                     // two A chunk images {hi, lo}: 2 x 32 KB
+  float* sbias = reinterpret_cast<float*>(imgs + 4 * NT_IMG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 256);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int R = a.hdr ? a.hdr->R : a.R;
+  const int ntiles = (R + NT_TILE - 1) / NT_TILE;
+  if ((int)blockIdx.x >= ntiles) return;                 // ragged: the grid covers the padded worst case
+  if (tid == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 1, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bars, NTP_WBYTES);
+    bulk_g2s(sw, a.wimg, NTP_WBYTES / 2, bars);
+    bulk_g2s(sw + NTP_WBYTES / 2, a.wimg + NTP_WBYTES / 2, NTP_WBYTES / 2, bars);
+  }
+  if (warp == 0) tmem_alloc<256>(tptr);
+  for (int t = tid; t < 256; t += NT_TILE) sbias[t] = a.bias[t];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t img_u32 = smem_u32(imgs), sw_u32 = smem_u32(sw);
+  constexpr uint32_t idesc = umma_idesc(2, 128, 256);
+  const int units = a.NP >> 2;
+  uint32_t ph = 0;
+  bool w_ready = false;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile * NT_TILE + tid;
+    const bool valid = n < R;
+    const float4* hp = reinterpret_cast<const float4*>(a.h + (size_t)(valid ? n : 0) * 64);
+    float4 hv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) hv[u] = __ldg(hp + u);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float vals[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
+      nt_store_unit(imgs + (u >> 3) * 2 * NT_IMG, tid, u & 7, vals);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      if (!w_ready) mbar_wait(bars, 0);
+      tc_fence_after();
+      const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma<true>(tmem_base, umma_desc_k_sw128(img_u32 + (c * 2 + pp[pr]) * NT_IMG + ks * 32),
+                       umma_desc_k_sw128(sw_u32 + (c * 2 + pw[pr]) * NTP_WSPLIT + ks * 32), idesc, (c | pr | ks) != 0);
+      umma_commit(bars + 1);
+    }
+    w_ready = true;
+    mbar_wait_warp(bars + 1, ph);
+    ph ^= 1;
+    tc_fence_after();
+    float4* p4 = reinterpret_cast<float4*>(a.proj) + g8_row(valid ? n : 0, units);
+#pragma unroll 1
+    for (int cc = 0; cc * 8 < units; ++cc) {
+      float v[32];
+      tmem_ld32(lane_addr + cc * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int col = cc * 32 + 4 * u;
+          if (cc * 8 + u < units)
+            p4[(cc * 8 + u) * G8S] = make_float4(v[4 * u] + sbias[col], v[4 * u + 1] + sbias[col + 1],
+                                                 v[4 * u + 2] + sbias[col + 2], v[4 * u + 3] + sbias[col + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
 
 struct NodeFwdArgs {
   int R, N, update, has_v, spatial;
@@ -860,10 +987,35 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
 
 bool tc_node_supported(const Dims& d) { return d.H == 64 && d.A == 4; }
 
-// all chunks, forward and transposed: the backward call of the step reuses the image
-int tc_node_prepare(const SakeLayerParams& p, void* wnode, cudaStream_t st) {
-  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, (uint8_t*)wnode, NTB_CHUNKS);
+// per-node projections (fills sv.nodeproj, G8 layout); builds the node weight images first unless they are prepared
+int tc_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st) {
+  if (d.NP > 256) { set_error("tc_node_pre: projection width %d > 256", d.NP); return SAKE_EUNSUPPORTED; }
+  if (!d.prepared) { const int rc = tc_node_prepare(d, p, sv.wnode, st); if (rc) return rc; }
+  NodePreArgs a;
+  a.R = d.R; a.NP = d.NP; a.hdr = d.hdr; a.h = h;
+  a.wimg = (const uint8_t*)sv.wnode + NTP_OFF;
+  a.bias = reinterpret_cast<const float*>((const uint8_t*)sv.wnode + NTP_OFF + NTP_WBYTES);
+  a.proj = sv.nodeproj;
+  const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
+  const int sms = node_num_sms();
+  const size_t smem = NTP_WBYTES + 4 * NT_IMG + 256 * sizeof(float) + 64 + 1024;
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_node_pre, smem, optin); if (rc) return rc; }
+  {
+    ProfScope prof(9, d.R, st);
+    k_tc_node_pre<<<tiles < sms ? tiles : sms, NT_TILE, smem, st>>>(a);
+  }
   note_launches(1);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// all chunks, forward and transposed: the backward call of the step reuses the image
+int tc_node_prepare(const Dims& d, const SakeLayerParams& p, void* wnode, cudaStream_t st) {
+  k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, (uint8_t*)wnode, NTB_CHUNKS);
+  k_node_pre_w_prep<<<(2 * 256 * 8 + 255) / 256, 256, 0, st>>>(p, d.H, d.K, d.Kp, (uint8_t*)wnode + NTP_OFF,
+                                                              reinterpret_cast<float*>((uint8_t*)wnode + NTP_OFF + NTP_WBYTES));
+  note_launches(2);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -872,7 +1024,7 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
                  const float* mask, float* h_out, float* x_out, float* v_out, const Saved& sv, void* wscratch,
                  cudaStream_t st) {
   uint8_t* wimg = (uint8_t*)wscratch;
-  if (!d.prepared) { const int rc = tc_node_prepare(p, wscratch, st); if (rc) return rc; }
+  (void)p;                                                // the images were built by tc_node_pre of the same call
   NodeFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.R = d.R; a.N = d.N; a.update = d.update; a.has_v = d.has_v; a.spatial = d.spatial;
