@@ -162,6 +162,44 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   float* arow = att + (size_t)ri.pair0 * A;
   const float* mrow = mask ? mask + (size_t)ri.pair0 : nullptr;
   const float* lrow = lg + (size_t)ri.pair0 * A;       // logits (may alias att: read completely before any write)
+  if (A == 4 && N <= 32) {
+    // short rows (every ragged workload of the scripts): lane = sender, the four heads side by side in registers —
+    // three warp reductions of a float4 instead of twelve scalar ones with a shared-memory pass between them.
+    // Same operations in the same order as the general path below, so the results are bit-identical.
+    const bool on = lane < N;
+    float4 s = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (on) s = *reinterpret_cast<const float4*>(lrow + lane * 4);
+    float4 mx = s;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o));
+      mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o)); mx.w = fmaxf(mx.w, __shfl_xor_sync(0xffffffffu, mx.w, o));
+    }
+    float4 ex = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) ex = make_float4(expf(s.x - mx.x), expf(s.y - mx.y), expf(s.z - mx.z), expf(s.w - mx.w));
+    float4 sum = ex;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+      sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+    }
+    float4 c = make_float4(ex.x * (1.0f / sum.x), ex.y * (1.0f / sum.y), ex.z * (1.0f / sum.z), ex.w * (1.0f / sum.w));
+    if (on && d.cutoff) {
+      const float eps = cosine_cutoff_(pair_dist_(x, row, ri.mol0 + lane), d.cut_lo, d.cut_hi);   // euclidean attention
+      c.x *= eps; c.y *= eps; c.z *= eps; c.w *= eps;
+    }
+    if (on && mrow) { const float m = mrow[lane]; c.x *= m; c.y *= m; c.z *= m; c.w *= m; }
+    float4 cs = c;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    c.x *= cs.x > 0.f ? 1.0f / cs.x : 0.f; c.y *= cs.y > 0.f ? 1.0f / cs.y : 0.f;      // guarded: fully masked row -> att = 0
+    c.z *= cs.z > 0.f ? 1.0f / cs.z : 0.f; c.w *= cs.w > 0.f ? 1.0f / cs.w : 0.f;
+    if (on) { *reinterpret_cast<float4*>(as + lane * 4) = c; *reinterpret_cast<float4*>(arow + lane * 4) = c; }
+    __syncwarp();
+  } else {
   for (int t = lane; t < N * A; t += 32) as[t] = lrow[t];
   __syncwarp();
   for (int a = 0; a < A; ++a) {
@@ -190,6 +228,7 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   }
   __syncwarp();
   for (int t = lane; t < N * A; t += 32) arow[t] = as[t];
+  }
   // aggregate: he[c = f*A+a] = sum_j e[j,f] * att[j,a] * m_j
   if (A == 4 && H == 64 && d.g8) {
     // e and he in the G8 layout (common.cuh).  Lane owns f = 2*lane, 2*lane+1 (half a 16-byte unit) and all four heads;

@@ -637,20 +637,40 @@ __global__ void __launch_bounds__(256) k_pair_reduce(Dims d, const float* __rest
   if (n < R) {
     const RowInfo ri = row_info(d, n);
     const long long c0 = ri.pair0 - (long long)(n - ri.mol0) * ri.n + (n - ri.mol0);   // pair (0, n) of the molecule
-    for (int i = 0; i < ri.n; ++i) {
+    // four loads in flight per thread (the sums keep the order i = 0, 1, 2, ...: one accumulator)
+    int i = 0;
+    for (; i + 4 <= ri.n; i += 4) {
+      const float4 v0 = __ldg(pb + g8_row(c0 + (long long)i * ri.n, U));
+      const float4 v1 = __ldg(pb + g8_row(c0 + (long long)(i + 1) * ri.n, U));
+      const float4 v2 = __ldg(pb + g8_row(c0 + (long long)(i + 2) * ri.n, U));
+      const float4 v3 = __ldg(pb + g8_row(c0 + (long long)(i + 3) * ri.n, U));
+      sj.x += v0.x; sj.y += v0.y; sj.z += v0.z; sj.w += v0.w;
+      sj.x += v1.x; sj.y += v1.y; sj.z += v1.z; sj.w += v1.w;
+      sj.x += v2.x; sj.y += v2.y; sj.z += v2.z; sj.w += v2.w;
+      sj.x += v3.x; sj.y += v3.y; sj.z += v3.z; sj.w += v3.w;
+    }
+    for (; i < ri.n; ++i) {
       const float4 v = __ldg(pb + g8_row(c0 + (long long)i * ri.n, U));
       sj.x += v.x; sj.y += v.y; sj.z += v.z; sj.w += v.w;
     }
   }
+  // row sums: the loads of all eight atoms are issued before the first shuffle (they are independent)
+  float4 racc[8];
+#pragma unroll
   for (int a2 = 0; a2 < 8; ++a2) {
+    racc[a2] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int m = n0 + a2;
-    if (m >= R) break;                                             // block-uniform
-    const RowInfo ri = row_info(d, m);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = ap; j < ri.n; j += 8) {
-      const float4 v = __ldg(pb + g8_row(ri.pair0 + j, U));
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (m < R) {                                                   // block-uniform
+      const RowInfo ri = row_info(d, m);
+      for (int j = ap; j < ri.n; j += 8) {
+        const float4 v = __ldg(pb + g8_row(ri.pair0 + j, U));
+        racc[a2].x += v.x; racc[a2].y += v.y; racc[a2].z += v.z; racc[a2].w += v.w;
+      }
     }
+  }
+#pragma unroll
+  for (int a2 = 0; a2 < 8; ++a2) {
+    float4 acc = racc[a2];
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
