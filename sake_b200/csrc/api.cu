@@ -383,6 +383,7 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
       side->any = true;
     }
   }
+  if (tc_node && (pre_dw_tc || !grads) && d.NP <= 256) return tc_node_pre_bwd(d, sv, sc, dh, st);
   return gen_node_pre_bwd(d, *params, h, dh, pre_dw_tc ? nullptr : grads, sc, st);
 }
 

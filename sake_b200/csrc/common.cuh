@@ -400,6 +400,7 @@ int tc_mix_prepare(const SakeLayerParams& p, void* wmix, int engine, cudaStream_
 int tc_edge_prepare(const Dims& d, const SakeLayerParams& p, void* wedge, cudaStream_t st);
 int tc_node_prepare(const Dims& d, const SakeLayerParams& p, void* wnode, cudaStream_t st);
 int tc_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const Saved& sv, cudaStream_t st);
+int tc_node_pre_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, float* dh, cudaStream_t st);
 // mix backward: ge, gatt, gdir (and dWx when gWx != nullptr)
 int tc_mix_bwd(const Dims& d, const SakeLayerParams& p, const float* x, const float* mask,
                const Saved& sv, const BwdScratch& sc, float* gWx, void* tc_scratch, int engine, XtgList& L,

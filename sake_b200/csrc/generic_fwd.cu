@@ -231,24 +231,42 @@ __global__ void __launch_bounds__(256) k_attn_fwd(Dims d, const float* __restric
   }
   // aggregate: he[c = f*A+a] = sum_j e[j,f] * att[j,a] * m_j
   if (A == 4 && H == 64 && d.g8) {
-    // e and he in the G8 layout (common.cuh).  Lane owns f = 2*lane, 2*lane+1 (half a 16-byte unit) and all four heads;
-    // the 16 lines a pair's features live in are shared by the 8 pairs of its group, so consecutive j hit L1.
+    // e and he in the G8 layout (common.cuh): a group of 8 consecutive pair slots x 16 units is one contiguous 2 KB
+    // block.  The warp pulls two groups at a time with fully coalesced 128-bit loads (lane l: float4 l + 32 k of the
+    // group = pair l & 7, unit (l >> 3) + 4 k) into a padded [16 pairs][64 + 4] shared-memory tile, then every lane
+    // owns f = 2*lane, 2*lane+1 and all four heads as before.  (Reading e per pair straight from the G8 rows costs
+    // 16 L1 wavefronts per pair: it was half of this kernel's time at cfg5.)
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* e0 = e + (size_t)(lane >> 1) * G8S * 4 + (lane & 1) * 2;
-    for (int j0 = 0; j0 < N; j0 += 8) {
-      float2 ev[8];
+    float* es = sm + (size_t)nw * d.N * A + (size_t)warp * (16 * 68);
+    const float4* e4 = reinterpret_cast<const float4*>(e);
+    const long long q0 = ri.pair0, q1 = ri.pair0 + N;
+    const long long glast = (q1 - 1) >> 3;
+    for (long long g0 = q0 >> 3; g0 <= glast; g0 += 2) {
+      float4 ev[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)                        // 8 independent loads in flight per lane
-        ev[u] = j0 + u < N ? __ldg(reinterpret_cast<const float2*>(e0 + g8_row(ri.pair0 + j0 + u, 16) * 4)) : make_float2(0.f, 0.f);
+      for (int gg = 0; gg < 2; ++gg)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (j0 + u < N) {
-          float4 w = *reinterpret_cast<const float4*>(as + (j0 + u) * 4);
-          if (mrow) { const float m = mrow[j0 + u]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
-          acc[0] = fmaf(ev[u].x, w.x, acc[0]); acc[1] = fmaf(ev[u].x, w.y, acc[1]); acc[2] = fmaf(ev[u].x, w.z, acc[2]); acc[3] = fmaf(ev[u].x, w.w, acc[3]);
-          acc[4] = fmaf(ev[u].y, w.x, acc[4]); acc[5] = fmaf(ev[u].y, w.y, acc[5]); acc[6] = fmaf(ev[u].y, w.z, acc[6]); acc[7] = fmaf(ev[u].y, w.w, acc[7]);
+        for (int k = 0; k < 4; ++k)
+          ev[gg * 4 + k] = g0 + gg <= glast ? __ldg(e4 + (g0 + gg) * (16 * G8S) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(es + (gg * 8 + (lane & 7)) * 68 + ((lane >> 3) + 4 * k) * 4) = ev[gg * 4 + k];
+      __syncwarp();
+#pragma unroll 4
+      for (int pp = 0; pp < 16; ++pp) {
+        const long long q = g0 * 8 + pp;
+        if (q >= q0 && q < q1) {                          // warp-uniform
+          const int j = (int)(q - q0);
+          const float2 ef = *reinterpret_cast<const float2*>(es + pp * 68 + 2 * lane);
+          float4 w = *reinterpret_cast<const float4*>(as + j * 4);
+          if (mrow) { const float m = mrow[j]; w.x *= m; w.y *= m; w.z *= m; w.w *= m; }
+          acc[0] = fmaf(ef.x, w.x, acc[0]); acc[1] = fmaf(ef.x, w.y, acc[1]); acc[2] = fmaf(ef.x, w.z, acc[2]); acc[3] = fmaf(ef.x, w.w, acc[3]);
+          acc[4] = fmaf(ef.y, w.x, acc[4]); acc[5] = fmaf(ef.y, w.y, acc[5]); acc[6] = fmaf(ef.y, w.z, acc[6]); acc[7] = fmaf(ef.y, w.w, acc[7]);
         }
       }
+      __syncwarp();
     }
     float4* ho = reinterpret_cast<float4*>(he) + g8_row(row, 64) + 2 * lane * G8S;     // he columns 8*lane .. 8*lane+7
     ho[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -540,7 +558,7 @@ int gen_attn_fwd(const Dims& d, const float* x, const float* mask, const Saved& 
   int rc;
   int nw = 8;
   while (nw > 1 && sizeof(float) * d.N * d.A * nw > 160 * 1024) nw >>= 1;
-  size_t smem = sizeof(float) * d.N * d.A * nw;
+  size_t smem = sizeof(float) * (d.N * d.A * nw + (d.g8 ? nw * 16 * 68 : 0));
   if ((rc = ensure_smem(k_attn_fwd, smem))) return rc;
   ProfScope prof(10, d.P, st);
   k_attn_fwd<<<(d.R + nw - 1) / nw, nw * 32, smem, st>>>(d, x, mask, sv.e, sv.logit, sv.att, sv.he);

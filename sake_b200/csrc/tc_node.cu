@@ -28,7 +28,11 @@ constexpr int NT_VEC = 64 * 6 + 256;         // b_p1 b_p2 b_n1 b_n2 b_v1 vel2 | 
 constexpr size_t NTP_OFF = (size_t)NTB_CHUNKS * NT_WCH + 1024;
 constexpr int NTP_WSPLIT = 256 * 128;                    // one split of one K chunk (32 KB)
 constexpr int NTP_WBYTES = 4 * NTP_WSPLIT;               // 128 KB
-size_t tc_node_w_bytes() { return NTP_OFF + NTP_WBYTES + 1024; }
+// ... and of k_tc_node_pre_bwd: [K chunk of projection columns (8)][{hi, lo}][64 input-feature rows x 128 B]
+constexpr size_t NTQ_OFF = NTP_OFF + NTP_WBYTES + 1024;
+constexpr int NTQ_WSPLIT = 64 * 128;                     // one split of one K chunk (8 KB)
+constexpr int NTQ_WBYTES = 8 * 2 * NTQ_WSPLIT;           // 128 KB
+size_t tc_node_w_bytes() { return NTQ_OFF + NTQ_WBYTES; }
 
 // weight image: chunk c = K rows [32c', 32c'+32) of its matrix W[in][64]; B operand rows = outputs
 __global__ void k_node_w_prep(const SakeLayerParams p, uint8_t* __restrict__ img, int nchunks) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ const float4* tt_base(const float* buf, int units, in
 // nodeproj in common.cuh): one 3xTF32 GEMM [128 atoms x 64] x [64 x 256] per tile, thread = atom = TMEM lane, G8 rows out.
 // Replaces the CUDA-core k_node_pre for the tcgen05 engines (cfg5: 109 -> ~20 us per layer call).
 __global__ void k_node_pre_w_prep(const SakeLayerParams p, int H, int K, int Kp, uint8_t* __restrict__ img,
-                                  float* __restrict__ bias) {
+                                  float* __restrict__ bias, uint8_t* __restrict__ imgT) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < 256) {
     float b = 0.f;
@@ -121,6 +125,17 @@ __global__ void k_node_pre_w_prep(const SakeLayerParams p, int H, int K, int Kp,
   split_tf32(vals[2], hi.z, lo.z); split_tf32(vals[3], hi.w, lo.w);
   *reinterpret_cast<float4*>(base + off) = hi;
   *reinterpret_cast<float4*>(base + NTP_WSPLIT + off) = lo;
+  // the same numbers for the backward GEMM dh = gproj W^T: rows = input features, K = projection columns.
+  // This thread holds W[k = chunk*32 + 4u + i][o]; there they are element (row k, K index o), one scalar each.
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = chunk * 32 + u * 4 + i;
+    float h1, l1;
+    split_tf32(vals[i], h1, l1);
+    uint8_t* b2 = imgT + (size_t)(o >> 5) * 2 * NTQ_WSPLIT + sw128_offset((uint32_t)k, (uint32_t)((o & 31) >> 2)) + (o & 3) * 4;
+    *reinterpret_cast<float*>(b2) = h1;
+    *reinterpret_cast<float*>(b2 + NTQ_WSPLIT) = l1;
+  }
 }
 
 struct NodePreArgs { int R, NP; const RaggedHdr* hdr; const float* h; const uint8_t* wimg; const float* bias; float* proj; };
@@ -209,6 +224,97 @@ __global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_pre(NodePreArgs a) {
     __syncthreads();
   }
   if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+// dh[n] += gproj[n] @ W^T (cotangent of the per-node projections back to h; layers.py:30,33-38): [128 atoms x 256] x
+// [256 x 64] in 3xTF32, K = the projection columns in eight chunks of 32 through two image buffers.  Replaces the
+// CUDA-core k_node_pre_bwd for the tcgen05 engines (its weight gradients are X^T G problems: tc_node_pre_dw).
+struct NodePreBwdArgs { int R, NP; const RaggedHdr* hdr; const float* gproj; const uint8_t* wimg; float* dh; };
+
+__global__ void __launch_bounds__(NT_TILE, 1) k_tc_node_pre_bwd(NodePreBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024_shared(smem_raw);
+  uint8_t* sw = base;                                    // weight image, 128 KB
+  uint8_t* imgs = base + NTQ_WBYTES;                     // two A chunk images {hi, lo}: 2 x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(imgs + 4 * NT_IMG);   // [0] weights, [1], [2] image buffers
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int R = a.hdr ? a.hdr->R : a.R;
+  const int ntiles = (R + NT_TILE - 1) / NT_TILE;
+  if ((int)blockIdx.x >= ntiles) return;                 // ragged: the grid covers the padded worst case
+  if (tid == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bars, NTQ_WBYTES);
+    bulk_g2s(sw, a.wimg, NTQ_WBYTES / 2, bars);
+    bulk_g2s(sw + NTQ_WBYTES / 2, a.wimg + NTQ_WBYTES / 2, NTQ_WBYTES / 2, bars);
+  }
+  if (warp == 0) tmem_alloc<64>(tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t img_u32 = smem_u32(imgs), sw_u32 = smem_u32(sw);
+  constexpr uint32_t idesc = umma_idesc(2, 128, 64);
+  const int units = a.NP >> 2;
+  uint32_t ph = 0;                                       // bit b: parity the next wait on image barrier b looks for
+  bool w_ready = false;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile * NT_TILE + tid;
+    const bool valid = n < R;
+    const float4* gp = reinterpret_cast<const float4*>(a.gproj) + g8_row(valid ? n : 0, units);
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      const int b = c & 1;
+      float4 gv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) gv[u] = c * 8 + u < units ? __ldg(gp + (c * 8 + u) * G8S) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c >= 2) { mbar_wait_warp(bars + 1 + b, (ph >> b) & 1u); ph ^= 1u << b; }     // the MMAs of chunk c - 2 have read image b
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float vals[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+        nt_store_unit(imgs + b * 2 * NT_IMG, tid, u, vals);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        if (!w_ready) mbar_wait(bars, 0);
+        tc_fence_after();
+        const int pp[3] = {0, 1, 0}, pw[3] = {0, 0, 1};
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma<true>(tmem_base, umma_desc_k_sw128(img_u32 + (b * 2 + pp[pr]) * NT_IMG + ks * 32),
+                       umma_desc_k_sw128(sw_u32 + (c * 2 + pw[pr]) * NTQ_WSPLIT + ks * 32), idesc, (c | pr | ks) != 0);
+        umma_commit(bars + 1 + b);
+      }
+      w_ready = true;
+    }
+    mbar_wait_warp(bars + 1, ph & 1u); ph ^= 1u;         // chunks 6 and 7: every MMA of the tile is complete
+    mbar_wait_warp(bars + 2, (ph >> 1) & 1u); ph ^= 2u;
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      float v[32];
+      tmem_ld32(lane_addr + cc * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+        float4* o = reinterpret_cast<float4*>(a.dh + (size_t)n * 64 + cc * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 t4 = o[u];
+          t4.x += v[4 * u]; t4.y += v[4 * u + 1]; t4.z += v[4 * u + 2]; t4.w += v[4 * u + 3];
+          o[u] = t4;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
 
 struct NodeFwdArgs {
@@ -1014,8 +1120,27 @@ int tc_node_pre(const Dims& d, const SakeLayerParams& p, const float* h, const S
 int tc_node_prepare(const Dims& d, const SakeLayerParams& p, void* wnode, cudaStream_t st) {
   k_node_w_prep<<<(NTB_CHUNKS * 64 * 8 + 255) / 256, 256, 0, st>>>(p, (uint8_t*)wnode, NTB_CHUNKS);
   k_node_pre_w_prep<<<(2 * 256 * 8 + 255) / 256, 256, 0, st>>>(p, d.H, d.K, d.Kp, (uint8_t*)wnode + NTP_OFF,
-                                                              reinterpret_cast<float*>((uint8_t*)wnode + NTP_OFF + NTP_WBYTES));
+                                                              reinterpret_cast<float*>((uint8_t*)wnode + NTP_OFF + NTP_WBYTES),
+                                                              (uint8_t*)wnode + NTQ_OFF);
   note_launches(2);
+  SAKE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// dh += gproj W^T (the images were built by the forward call of the step)
+int tc_node_pre_bwd(const Dims& d, const Saved& sv, const BwdScratch& sc, float* dh, cudaStream_t st) {
+  NodePreBwdArgs a;
+  a.R = d.R; a.NP = d.NP; a.hdr = d.hdr; a.gproj = sc.gproj; a.wimg = (const uint8_t*)sv.wnode + NTQ_OFF; a.dh = dh;
+  const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
+  const int sms = node_num_sms();
+  const size_t smem = NTQ_WBYTES + 4 * NT_IMG + 64 + 1024;
+  static unsigned long long optin = 0;
+  { const int rc = smem_optin(k_tc_node_pre_bwd, smem, optin); if (rc) return rc; }
+  {
+    ProfScope prof(12, d.R, st);
+    k_tc_node_pre_bwd<<<tiles < sms ? tiles : sms, NT_TILE, smem, st>>>(a);
+  }
+  note_launches(1);
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
