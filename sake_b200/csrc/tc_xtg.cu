@@ -578,6 +578,15 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   long long prof_pairs = 0;
   bool lean_b = true, lean_s = true;
   constexpr int NST_BIG = XTG_NSTAGE, NST_SMALL = 2;
+  // Small problems with a long K (the pair-level ones) are split so that TOGETHER they fill the machine exactly once at
+  // two CTAs per SM: with every problem split over all SMs the long CTAs ran as one and a half waves, the second half
+  // on half the SMs.  The short (node-level) problems fill the slots as the long CTAs retire.
+  int n_long = 0;
+  for (int i = 0; i < L.n; ++i) {
+    const XtgArgs& a = L.a[i];
+    if (a.P > 0 && (a.MXpad / 128) * a.NG <= 256 && (a.P + XKP - 1) / XKP >= 8LL * sms) ++n_long;
+  }
+  const int gx_long = n_long > 0 ? (2 * sms / n_long > 2 * sms ? 2 * sms : (2 * sms / n_long < sms / 2 ? sms / 2 : 2 * sms / n_long)) : sms;
   for (int i = 0; i < L.n; ++i) {
     XtgArgs a = L.a[i];
     if (a.P <= 0) continue;
@@ -591,11 +600,12 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
     const size_t stage = nsplit * ((size_t)(a.MXpad / XBLK) * lbo + (size_t)((a.NG + XBLK - 1) / XBLK) * lbo);
     const size_t smem = (is_big ? NST_BIG : NST_SMALL) * stage + 256 + 1024;
     long long stages_total = (a.P + XKP - 1) / XKP;
-    long long per = (stages_total + sms - 1) / sms;
+    const int ctas = (!is_big && stages_total >= 8LL * sms) ? gx_long : sms;
+    long long per = (stages_total + ctas - 1) / ctas;
     if (per < 4) per = 4;                                  // keep the flush amortised
     a.pairs_per_cta = per * XKP;
     a.gx = (int)((a.P + a.pairs_per_cta - 1) / a.pairs_per_cta);
-    if (a.Pdev != nullptr) a.gx = sms;                     // ragged: the kernel splits the real extent over `gx` CTAs
+    if (a.Pdev != nullptr) a.gx = ctas;                    // ragged: the kernel splits the real extent over `gx` CTAs
     const size_t need = (size_t)a.gx * a.MXpad * a.NG;
     if (partial != nullptr && (poff + need) * sizeof(float) <= tc_xtg_partial_bytes()) {
       a.partial = partial + poff;
