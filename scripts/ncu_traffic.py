@@ -18,7 +18,8 @@ import sys
 
 KINDS = (("k_tc_mix_fwd", "mix_fwd"), ("k_tc_mix_bwd", "mix_bwd"), ("k_tc_edge<0>", "edge_fwd"), ("k_tc_edge<(bool)0>", "edge_fwd"),
          ("k_tc_edge<1>", "edge_bwd"), ("k_tc_edge<(bool)1>", "edge_bwd"), ("k_tc_node_post_bwd", "node_post_bwd"),
-         ("k_tc_node_post", "node_post"))
+         ("k_tc_node_post", "node_post"), ("k_tc_node_pre_bwd", "node_pre_bwd"), ("k_tc_node_pre", "node_pre"),
+         ("k_attn_fwd", "attn_fwd"), ("k_attn_bwd_tc", "attn_bwd"), ("k_pair_reduce", "pair_reduce"), ("k_xtg_reduce", "xtg_reduce"))
 METRICS = {
     "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write", "gpu__time_duration.sum": "ns",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
