@@ -163,7 +163,9 @@ const char* sake_last_error(void);
 int sake_resolve_engine(const SakeDims* dims);
 
 /* Bytes of the `saved` buffer: what sake_layer_fwd leaves for sake_layer_bwd (edge features
- * e[B,N,N,H], attention att[B,N,N,A], per-node projections and reductions).  Nothing O(N^2*C). */
+ * e[B,N,N,H], attention att[B,N,N,A], per-node projections and reductions, the weight operand images).
+ * Nothing O(N^2*C).  The buffer is OPAQUE: its internal layout depends on the engine (the tcgen05 engines interleave
+ * groups of 8 rows unit by unit) and may change between builds. */
 size_t sake_layer_saved_bytes(const SakeDims* dims);
 /* Bytes of the `scratch` buffer (temporaries; may be shared by all layers on one stream).
  * for_backward != 0 sizes it for sake_layer_bwd (with_param_grads selects the training variant). */
@@ -208,7 +210,7 @@ int sake_layer_fwd(const SakeDims* dims, const SakeLayerParams* params,
                    sake_stream_t stream);
 
 /* Builds the tcgen05 operand images of one layer's weights (swizzled, split-precision copies of x_mixing, the edge
- * MLP, the node-tail MLPs and their transposes; ~1.7 MB) into `saved`, where sake_layer_fwd (with
+ * MLP, the node-tail and per-node projection MLPs and their transposes; ~2.0 MB) into `saved`, where sake_layer_fwd (with
  * SAKE_WEIGHTS_PREPARED) and sake_layer_bwd read them.  No-op on the generic fp32 engine.  The images depend on the
  * parameters only: the reference's XLA program has no counterpart (it re-reads the flax kernels every call). */
 int sake_layer_prepare(const SakeDims* dims, const SakeLayerParams* params, void* saved, size_t saved_bytes,
