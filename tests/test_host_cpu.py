@@ -36,6 +36,17 @@ def test_argument_validation_without_gpu():
     rc = _lib.lib.sake_layer_fwd(C.byref(d), None, None, None, None, None, None, None, None, None, None, None, 0, None,
                                  0, None)
     assert rc == -1
+    # n_rbf: the tcgen05 edge kernel's K = 64 operand holds the RBF channels + 3 extra columns, and an engine is
+    # tcgen05 for all kernels of a layer or for none (they share G8-layout buffers): beyond 58 AUTO -> generic engine
+    d = _lib.SakeDims(2, 5, 64, 4, 58, 0, _lib.ENGINE_AUTO, 0)
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == _lib.ENGINES["f16x2"]
+    d = _lib.SakeDims(2, 5, 64, 4, 60, 0, _lib.ENGINE_AUTO, 0)
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == _lib.ENGINE_FP32
+    d = _lib.SakeDims(2, 5, 64, 4, 60, 0, _lib.ENGINES["f16x2"], 0)
+    assert _lib.lib.sake_resolve_engine(C.byref(d)) == -2 and b"n_rbf" in _lib.lib.sake_last_error()
+    # the saved buffer covers the G8 padding (rows rounded up to 8) and the weight images
+    d = _lib.SakeDims(1, 3, 64, 4, 50, 0, _lib.ENGINE_AUTO, 0)
+    assert _lib.lib.sake_layer_saved_bytes(C.byref(d)) > 2 * 1024 * 1024
     # ragged tables: size query works without a GPU, bad arguments are refused before any launch
     assert _lib.lib.sake_ragged_bytes(256, 29) > 256 * 29 * 32
     assert _lib.lib.sake_ragged_prepare(4, 200, None, None, 0, None) == -1
