@@ -294,6 +294,27 @@ __device__ __forceinline__ void epi_fwd_chunk(const float (&v)[32], const float4
   s0 += a0 + b0; s1 += a1 + b1; s2 += a2 + b2;
 }
 
+// The same block for TWO short rows at once (2 * seglen <= 32): every tanh of the 32-column window is evaluated once and
+// feeds the masked sums of both rows.  One window per row evaluated 32 tanh per row: 288 per tile for the 14-atom
+// molecules of the flows (9 rows of 14 columns) against 126 pair columns.
+template <class CF>
+__device__ __forceinline__ void epi_fwd_chunk2(const float (&v)[32], const float4* __restrict__ dmp, uint32_t maskA,
+                                               uint32_t maskB, float& sa0, float& sa1, float& sa2, float& sb0, float& sb1,
+                                               float& sb2) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float4 dm = dmp[k];
+    float z = v[k];
+    if constexpr (CF::F16) z *= dm.w;
+    const float co = CF::TF32 || CF::F16 ? ftanh_(z) : ftanh_mufu_(z);
+    const float ca = ((maskA >> k) & 1u) ? co : 0.f, cb = ((maskB >> k) & 1u) ? co : 0.f;
+    a0 = fmaf(dm.x, ca, a0); a1 = fmaf(dm.y, ca, a1); a2 = fmaf(dm.z, ca, a2);
+    b0 = fmaf(dm.x, cb, b0); b1 = fmaf(dm.y, cb, b1); b2 = fmaf(dm.z, cb, b2);
+  }
+  sa0 = a0; sa1 = a1; sa2 = a2; sb0 = b0; sb1 = b1; sb2 = b2;
+}
+
 // =================================================================================================
 // forward:  D^T[c' (lane), pair (column)] = sum_c Wx[c][c'] * E[pair][c]
 //   A = weight image (M = 128 of the 256 c' per MMA, two halves), B = E image (N = 128 pairs)
@@ -466,6 +487,28 @@ k_tc_mix_fwd(TileGeom g, const float* __restrict__ x, const float* __restrict__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + mh * 128;
       const float4* dmt = sm.dirm + buf * TILE;
+      if (!accumulate && 2 * seglen <= 32) {
+        // short rows: two per 32-column window (epi_fwd_chunk2)
+#pragma unroll 1
+        for (int sg = 0; sg < nsegs; sg += 2) {
+          const int c0 = sg * seglen;
+          const int ls = min(c0, TILE - 32);           // clamped window start; both rows end at or before column 128
+          const bool two = sg + 1 < nsegs;
+          const uint32_t m1 = ((1u << seglen) - 1u) << (c0 - ls);
+          const uint32_t m2 = two ? m1 << seglen : 0u;
+          float v[32];
+          tmem_ld32(taddr + ls, v);
+          tmem_ld_wait();
+          float sa0, sa1, sa2, sb0, sb1, sb2;
+          epi_fwd_chunk2<CF>(v, dmt + ls, m1, m2, sa0, sa1, sa2, sb0, sb1, sb2);
+          for (int h2 = 0; h2 < (two ? 2 : 1); ++h2) {
+            const size_t orow = (size_t)(row0 + sg + h2);
+            float* o = ssum_tt ? ssum + (g8_row((long long)orow, 192) + (size_t)(cp >> 2) * 3 * G8S) * 4 + (cp & 3)
+                               : ssum + (orow * CC + cp) * 3;
+            emit_ssum(o, ssum_tt ? 4 * G8S : 1, h2 ? sb0 : sa0, h2 ? sb1 : sa1, h2 ? sb2 : sa2, false);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int sg = 0; sg < nsegs; ++sg) {
         const int c0 = sg * seglen, c1 = c0 + seglen;
