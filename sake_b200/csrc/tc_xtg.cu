@@ -445,64 +445,78 @@ __global__ void __launch_bounds__(XTG_THREADS, MINB) k_tc_xtg(const __grid_const
 }
 
 // out[row][col] += sum_cta partial[cta][col][row]   (deterministic second stage of the flush)
-// Block = 128 rows x XRED_SLICES slices of the CTA range: each thread keeps 8 independent loads in flight (the
-// partials are L2-resident; one load per thread at a time left this kernel latency-bound at ~1 TB/s), the slices
-// are combined in a fixed order through shared memory.
+// Thread = four consecutive rows of one column (one float4 per partial: a warp reads 512 contiguous bytes), a block =
+// 128 / (MXpad / 4) columns x XRED_SLICES slices of the CTA range; each thread keeps 8 independent loads in flight (the
+// partials are L2-resident; one load per thread at a time left this kernel latency-bound at ~1 TB/s), the slices are
+// combined in a fixed order through shared memory.
 constexpr int XRED_SLICES = 4;
+__host__ __device__ inline int xred_cols_per_block(int MXpad) { return 128 / (MXpad / 4); }   // 4 (MXpad 128) or 2 (256)
 __global__ void __launch_bounds__(128 * XRED_SLICES) k_xtg_reduce(const __grid_constant__ XtgBatch batch) {
-  __shared__ float red[XRED_SLICES][128];
+  __shared__ float4 red[XRED_SLICES][128];
   int pi = 0;
   while (pi + 1 < batch.nprob && (int)blockIdx.x >= batch.colbase[pi + 1]) ++pi;   // <= 20 problems
   const XtgArgs& a = batch.a[pi];
-  const int col = blockIdx.x - batch.colbase[pi];
-  const int ncta = xtg_split(a).gx;
-  if (col >= a.NG || a.partial == nullptr) return;           // block-uniform
+  if (a.partial == nullptr) return;                          // block-uniform
   const int tx = threadIdx.x & 127, sl = threadIdx.x >> 7;
+  const int rq = a.MXpad >> 2;                               // threads per column
+  const int col = ((int)blockIdx.x - batch.colbase[pi]) * (128 / rq) + tx / rq;
+  const int r4 = tx % rq, row0 = 4 * r4;
+  const int ncta = xtg_split(a).gx;
   const int per = (ncta + XRED_SLICES - 1) / XRED_SLICES;
   const int c0 = min(ncta, sl * per), c1 = min(ncta, c0 + per);
-  const size_t cstride = (size_t)a.MXpad * a.NG;
+  const size_t cstride = ((size_t)a.MXpad * a.NG) >> 2;      // float4 per partial
   const int rows = a.out_rows + a.extra_rows;
-  for (int r0 = 0; r0 < rows; r0 += 128) {                    // block-uniform trip count (<= 2)
-    const int row = r0 + tx;
-    float s = 0.f;
-    if (row < rows) {
-      const float* pp = a.partial + (size_t)col * a.MXpad + row + (size_t)c0 * cstride;
-      int c = c0;
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-      for (; c + 8 <= c1; c += 8, pp += 8 * cstride) {
-        const float v0 = pp[0], v1 = pp[cstride], v2 = pp[2 * cstride], v3 = pp[3 * cstride];
-        const float v4 = pp[4 * cstride], v5 = pp[5 * cstride], v6 = pp[6 * cstride], v7 = pp[7 * cstride];
-        t0 += v0; t1 += v1; t2 += v2; t3 += v3; t0 += v4; t1 += v5; t2 += v6; t3 += v7;
-      }
-      for (; c < c1; ++c, pp += cstride) t0 += pp[0];
-      s = (t0 + t1) + (t2 + t3);
+  const bool on = col < a.NG && row0 < rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+    const float4* pp = reinterpret_cast<const float4*>(a.partial) + (((size_t)col * a.MXpad) >> 2) + r4 + (size_t)c0 * cstride;
+    int c = c0;
+    float4 t0 = s, t1 = s;
+    for (; c + 8 <= c1; c += 8, pp += 8 * cstride) {
+      const float4 v0 = pp[0], v1 = pp[cstride], v2 = pp[2 * cstride], v3 = pp[3 * cstride];
+      const float4 v4 = pp[4 * cstride], v5 = pp[5 * cstride], v6 = pp[6 * cstride], v7 = pp[7 * cstride];
+      t0.x += v0.x; t0.y += v0.y; t0.z += v0.z; t0.w += v0.w;   t1.x += v1.x; t1.y += v1.y; t1.z += v1.z; t1.w += v1.w;
+      t0.x += v2.x; t0.y += v2.y; t0.z += v2.z; t0.w += v2.w;   t1.x += v3.x; t1.y += v3.y; t1.z += v3.z; t1.w += v3.w;
+      t0.x += v4.x; t0.y += v4.y; t0.z += v4.z; t0.w += v4.w;   t1.x += v5.x; t1.y += v5.y; t1.z += v5.z; t1.w += v5.w;
+      t0.x += v6.x; t0.y += v6.y; t0.z += v6.z; t0.w += v6.w;   t1.x += v7.x; t1.y += v7.y; t1.z += v7.z; t1.w += v7.w;
     }
-    red[sl][tx] = s;
-    __syncthreads();
-    if (sl == 0 && row < rows) {
-      float tot = red[0][tx];
+    for (; c < c1; ++c, pp += cstride) { const float4 v = pp[0]; t0.x += v.x; t0.y += v.y; t0.z += v.z; t0.w += v.w; }
+    s = make_float4(t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w);
+  }
+  red[sl][tx] = s;
+  __syncthreads();
+  if (sl != 0 || !on) return;
+  auto total = [&](int t) {
+    float4 q = red[0][t];
 #pragma unroll
-      for (int k = 1; k < XRED_SLICES; ++k) tot += red[k][tx];
-      if (row < a.out_rows) {
-        if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += tot;
-      } else if (a.mb_gmu != nullptr) {
-        // rows out_rows (S1) and out_rows + 1 (S2) of column 128 + k: the thread that owns S2 rebuilds S1 from the
-        // slices (same 128-row block) and finishes the RBF mean / width gradients (utils.py:61-65)
-        const int k = col - 128;
-        if (row == a.out_rows + 1 && k >= 0 && k < a.mb_K) {
-          float s1 = red[0][tx - 1];
+    for (int k = 1; k < XRED_SLICES; ++k) { const float4 w = red[k][t]; q.x += w.x; q.y += w.y; q.z += w.z; q.w += w.w; }
+    return q;
+  };
+  const float4 tq = total(tx);
+  const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
 #pragma unroll
-          for (int q = 1; q < XRED_SLICES; ++q) s1 += red[q][tx - 1];
-          a.mb_gmu[k] += 2.0f * a.mb_beta[k] * s1;
-          a.mb_gbeta[k] += -(tot - a.mb_mu[k] * s1);
-        }
-      } else if (a.extra2 != nullptr && col >= a.extra2_col0) {
-        a.extra2[col - a.extra2_col0] += tot;
-      } else if (col < a.extra_ld) {
-        a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += tot;
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + i;
+    const float tot = tv[i];
+    if (row >= rows) break;
+    if (row < a.out_rows) {
+      if (col < a.out_cols) a.out[(size_t)row * a.ldo + col] += tot;
+    } else if (a.mb_gmu != nullptr) {
+      // rows out_rows (S1) and out_rows + 1 (S2) of column 128 + k: the thread that owns S2 fetches S1 (same column,
+      // possibly the neighbouring row quad) and finishes the RBF mean / width gradients (utils.py:61-65)
+      const int k = col - 128;
+      if (row == a.out_rows + 1 && k >= 0 && k < a.mb_K) {
+        const int r1 = a.out_rows;                           // row of S1
+        const float4 q1 = total(tx - r4 + (r1 >> 2));
+        const float s1 = (r1 & 3) == 0 ? q1.x : (r1 & 3) == 1 ? q1.y : (r1 & 3) == 2 ? q1.z : q1.w;
+        a.mb_gmu[k] += 2.0f * a.mb_beta[k] * s1;
+        a.mb_gbeta[k] += -(tot - a.mb_mu[k] * s1);
       }
+    } else if (a.extra2 != nullptr && col >= a.extra2_col0) {
+      a.extra2[col - a.extra2_col0] += tot;
+    } else if (col < a.extra_ld) {
+      a.extra[(size_t)(row - a.out_rows) * a.extra_ld + col] += tot;
     }
-    __syncthreads();
   }
 }
 
@@ -555,7 +569,7 @@ static int xtg_launch(const XtgBatch& batch, int nb, int gx_max, size_t smem, in
   SAKE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
-// ONE reduction grid for every problem of both launches: a block per output column, none for columns that do not exist
+// ONE reduction grid for every problem of both launches: a block per 4 (or 2) output columns, none for columns that do not exist
 static int xtg_reduce_all(const XtgBatch& all, cudaStream_t st) {
   const int ncols = all.colbase[all.nprob];
   if (ncols == 0) return 0;
@@ -650,7 +664,8 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   int ncols = 0;
   auto add_red = [&](const XtgArgs& a) {
     if (a.partial == nullptr) return;
-    all.a[all.nprob] = a; all.colbase[all.nprob] = ncols; ncols += a.NG; ++all.nprob;
+    const int cpb = xred_cols_per_block(a.MXpad);           // reduction blocks of this problem
+    all.a[all.nprob] = a; all.colbase[all.nprob] = ncols; ncols += (a.NG + cpb - 1) / cpb; ++all.nprob;
   };
   for (int i = 0; i < nb_b; ++i) add_red(big.a[i]);
   for (int i = 0; i < nb_s; ++i) add_red(small.a[i]);
