@@ -257,7 +257,7 @@ class ModelJob:
         model = sake_b200.DenseSAKEModel(hidden_features=H, out_features=1, depth=args.depth, engine=args.engine)
         self.run = R.ModelRunner(model, init_params_cpu(args.depth, S, 0), B, N, S, masked=padded and not self.ragged,
                                  ragged=self.ragged, train=(mode == "train"), device=dev,
-                                 defer_dw=args.defer_dw)
+                                 defer_dw=args.defer_dw, defer_reduce=args.defer_reduce)
         if shard is not None:
             h, x, mask, am, y, n_real = (None if t is None else t[shard] for t in full)
         else:
@@ -412,6 +412,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying the step as a CUDA graph")
     ap.add_argument("--defer-dw", action="store_true",
                     help="run the weight-gradient contractions on the library's side stream (measured: no gain, see DESIGN.md)")
+    ap.add_argument("--defer-reduce", action="store_true",
+                    help="run the weight-gradient partial-sum reduction on the library's side stream (measured: no gain)")
     ap.add_argument("--bucketed-allreduce", action="store_true",
                     help="training on several GPUs: all-reduce per-layer gradient buckets between backward segments instead of one all-reduce after the backward")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total-size cfg3 / cfg4 records")

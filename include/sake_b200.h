@@ -47,6 +47,10 @@ enum {
                             sake/layers.py:172-176): euclidean_attention = 0.5 (cos(pi (2 (d - lower) / (upper - lower) + 1)) + 1)
                             with SakeDims.cutoff_lower / cutoff_upper; as in the reference the range masks are
                             NOT applied (utils.py:24-25 discards them), so the factor is periodic in d       */
+  SAKE_DEFER_REDUCE = 128, /* sake_layer_bwd only (training, tcgen05 engines): the partial-sum reduction that finishes the
+                            layer's weight gradients runs on the library's side stream, under the per-node kernels of this
+                            layer and of the next one (which occupy a quarter of the SMs); SakeDims.reserved & 1 selects one
+                            of two partial-sum regions (alternate it between consecutive layers); sake_dw_sync() joins */
   SAKE_WEIGHTS_PREPARED = 64, /* sake_layer_fwd: the operand images of this layer's weights in `saved` are current
                             (sake_layer_prepare ran on the same parameters since they last changed): skip
                             rebuilding them.  Inference loops prepare once; a training step prepares after

@@ -16,6 +16,7 @@ lib = C.CDLL(LIB_PATH)
 
 # enums (include/sake_b200.h)
 SAKE_UPDATE, SAKE_HAS_V, SAKE_HAS_MASK, SAKE_NO_SPATIAL, SAKE_DEFER_DW, SAKE_COSINE_CUTOFF = 1, 2, 4, 8, 16, 32
+SAKE_DEFER_REDUCE = 128
 SAKE_WEIGHTS_PREPARED = 64
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32X3, ENGINE_BF16, ENGINE_F16X2 = 0, 1, 2, 3, 4
 ENGINES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32x3": ENGINE_TF32X3, "bf16": ENGINE_BF16,

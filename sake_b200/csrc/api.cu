@@ -187,7 +187,7 @@ static ScratchLayout scratch_layout(const Dims& d, int engine, int for_backward,
   L.edgeb = o;
   if (engine != SAKE_ENGINE_FP32 && tc_edge_supported(d) && for_backward) o += align_up(tc_edge_bwd_scratch_bytes(d, with_grads));
   L.xtgp = o;
-  if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_xtg_partial_bytes());
+  if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += 2 * align_up(tc_xtg_partial_bytes());   // two regions: SAKE_DEFER_REDUCE
   L.nbuf = o;
   if (engine != SAKE_ENGINE_FP32 && for_backward && with_grads) o += align_up(tc_node_dw_scratch_bytes(d));
   L.noded = o;
@@ -323,9 +323,10 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   // deferred weight gradients: wait for the previous user of this scratch slot before touching the scratch
   SideCtx* side = nullptr;
   const int slot = dims->reserved & 1;
-  if ((dims->flags & SAKE_DEFER_DW) && grads && engine != SAKE_ENGINE_FP32) {
+  const bool defer_all = (dims->flags & SAKE_DEFER_DW) != 0, defer_red = !defer_all && (dims->flags & SAKE_DEFER_REDUCE) != 0;
+  if ((defer_all || defer_red) && grads && engine != SAKE_ENGINE_FP32) {
     side = side_ctx();
-    if (!side) { set_error("SAKE_DEFER_DW: cannot create the side stream"); return SAKE_ECUDA; }
+    if (!side) { set_error("SAKE_DEFER_DW / SAKE_DEFER_REDUCE: cannot create the side stream"); return SAKE_ECUDA; }
     if (side->pending[slot]) { SAKE_CUDA_CHECK(cudaStreamWaitEvent(st, side->done[slot], 0)); side->pending[slot] = false; }
   }
   const bool tc_edge = engine != SAKE_ENGINE_FP32 && tc_edge_supported(d);
@@ -338,7 +339,9 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
   sc.wxT = (float*)(b + SL.wxT); sc.gZ = (float*)(b + SL.gZ); sc.nodeWT = (float*)(b + SL.nodeWT);
   const bool tc_node = engine != SAKE_ENGINE_FP32 && tc_node_supported(d) && true;
   if (tc_node) sc.nodeWT = sv.nodeWT;                 // transposed copies left by the forward call
-  sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.xtgp) : nullptr;
+  sc.xtg_partial = (engine != SAKE_ENGINE_FP32 && grads)
+                       ? (float*)(b + SL.xtgp + ((dims->flags & SAKE_DEFER_REDUCE) ? (size_t)slot * align_up(tc_xtg_partial_bytes()) : 0))
+                       : nullptr;
   sc.nbuf = (engine != SAKE_ENGINE_FP32 && grads) ? (float*)(b + SL.nbuf) : nullptr;
   sc.qv = (tc_node && grads && d.update && d.spatial) ? (float*)(b + SL.noded) : nullptr;
   if (tc_node)
@@ -371,14 +374,15 @@ int sake_layer_bwd(const SakeDims* dims, const SakeLayerParams* params, const fl
     // every weight-gradient contraction of this layer in one batched tensor-core launch (+ its reductions);
     // nothing downstream of the layer reads dW, so with SAKE_DEFER_DW it runs on the side stream, forked here
     cudaStream_t ws = st;
-    if (side) {
+    if (side && defer_all) {
       SAKE_CUDA_CHECK(cudaEventRecord(side->fork, st));
       SAKE_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
       ws = side->s;
     }
-    if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, ws))) return rc;
+    // SAKE_DEFER_REDUCE: the contractions stay on the caller's stream, only the partial-sum reduction is forked
+    if ((rc = tc_xtg_flush(xl, sc.xtg_partial, engine, 3, ws, side && defer_red ? side->s : nullptr, side ? side->fork : nullptr))) return rc;
     if (side) {
-      SAKE_CUDA_CHECK(cudaEventRecord(side->done[slot], ws));
+      SAKE_CUDA_CHECK(cudaEventRecord(side->done[slot], side->s));
       side->pending[slot] = true;
       side->any = true;
     }

@@ -346,7 +346,9 @@ struct XtgList {
   int n = 0;
   int push(const XtgArgs& q) { if (n >= MAXP) return -1; a[n++] = q; return 0; }
 };
-int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st);
+// red_st != st: the reduction runs on red_st, forked from st with `fork` (the caller joins red_st later)
+int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st, cudaStream_t red_st = nullptr,
+                 cudaEvent_t fork = nullptr);
 int tc_xtg(const XtgArgs& a, int engine, int prof_kind, cudaStream_t st);
 size_t tc_xtg_partial_bytes();
 

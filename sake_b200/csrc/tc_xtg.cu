@@ -579,7 +579,7 @@ static int xtg_reduce_all(const XtgBatch& all, cudaStream_t st) {
   return 0;
 }
 
-int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st) {
+int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStream_t st, cudaStream_t red_st, cudaEvent_t fork) {
   if (L.n == 0) return 0;
   const bool bf = engine == SAKE_ENGINE_BF16;
   const int nsplit = bf ? 1 : 2;
@@ -685,6 +685,11 @@ int tc_xtg_flush(XtgList& L, float* partial, int engine, int prof_kind, cudaStre
   rc = lean_s && !no_lean ? xtg_launch<256, true, 2>(small, nb_s, gx_s, smem_s, NST_SMALL, bf, st)
                           : xtg_launch<256, false, 1>(small, nb_s, gx_s, smem_s, NST_SMALL, bf, st);
   if (rc) return rc;
+  if (red_st != nullptr && red_st != st && fork != nullptr) {
+    SAKE_CUDA_CHECK(cudaEventRecord(fork, st));
+    SAKE_CUDA_CHECK(cudaStreamWaitEvent(red_st, fork, 0));
+    return xtg_reduce_all(all, red_st);
+  }
   return xtg_reduce_all(all, st);
 }
 

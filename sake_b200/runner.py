@@ -67,7 +67,8 @@ class ParamSet:
 
 class ModelRunner:
     def __init__(self, model, params, B, N, in_features, *, masked=False, ragged=False, train=False, device="cuda",
-                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=False, async_prep=True):
+                 lr=1e-3, weight_decay=1e-5, max_delta=1.0, mean=0.0, std=1.0, defer_dw=False, async_prep=True,
+                 defer_reduce=False):
         """masked: QM9-style padded batch with the reference's float mask = outer(m, m) (every kernel computes
         all N^2 pairs of the padded width and multiplies by the mask, like the reference).
         ragged: the same padded batch, but only the n_real[b] real atoms of every molecule are stored and
@@ -147,9 +148,15 @@ class ModelRunner:
         # 512 TMEM columns), so the two streams take turns on each SM instead of overlapping (cfg2 3.58 -> 3.83 ms).
         self.defer_dw = bool(defer_dw and train and self.engine != "fp32" and self.L > 1)
         self.scratches = [self.scratch, ops._buf(nscr, dev)] if self.defer_dw else [self.scratch, self.scratch]
+        # defer_reduce (opt-in): only the partial-sum reduction that finishes a layer's weight gradients goes to the
+        # side stream (SAKE_DEFER_REDUCE), under this layer's and the next layer's per-node kernels, which occupy a
+        # quarter of the SMs.  Measured on B200 (same box, cfg2): 2.547 vs 2.538 ms without — the reduction's CTAs
+        # delay the node kernels by as much as they save (k_tc_node_pre_bwd 17 -> 31 us).  Off by default.
+        self.defer_reduce = bool(defer_reduce and train and self.engine != "fp32" and not self.defer_dw)
         self.dims_bwd = []
         for l, d in enumerate(self.dims):
-            db = _lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags | (_lib.SAKE_DEFER_DW if self.defer_dw else 0),
+            db = _lib.SakeDims(d.B, d.N, d.H, d.A, d.K, d.flags | (_lib.SAKE_DEFER_DW if self.defer_dw else 0) |
+                               (_lib.SAKE_DEFER_REDUCE if self.defer_reduce else 0),
                                d.engine, l & 1, d.cutoff_lower, d.cutoff_upper)
             self.dims_bwd.append(db)
         self.y0 = torch.empty(B, N, self.H, device=dev, dtype=f32)
@@ -276,13 +283,19 @@ class ModelRunner:
                           self.gs[l] if with_grads else None, self.scratches[l & 1] if with_grads else self.scratch,
                           self.rg)
 
+    def _bwd_layer_joined(self, l):
+        """One layer's backward as a self-contained segment (its gradient bucket is complete when it returns)."""
+        self._bwd_layer(l, True)
+        if self.defer_dw or self.defer_reduce:
+            check(lib.sake_dw_sync(ops._stream()), "sake_dw_sync")
+
     def _bwd_embed(self, with_grads):
         cur = self.L & 1                       # slot the first layer wrote
         if with_grads:
             p, g = self.p, self.g
             ops.dense_bwd_raw(self.h_in, p["embedding_in/kernel"], p.get("embedding_in/bias"), self.dh[cur], None,
                               g["embedding_in/kernel"], g.get("embedding_in/bias"), 0, self.rg)
-            if self.defer_dw:                  # join the side stream: gradients complete from here on
+            if self.defer_dw or self.defer_reduce:       # join the side stream: gradients complete from here on
                 check(lib.sake_dw_sync(ops._stream()), "sake_dw_sync")
         self._dx_final = self.dx[cur]
 
@@ -320,7 +333,7 @@ class ModelRunner:
             self._bwd_readout(True)
         segs = [("embedding_out/", head)]
         for l in reversed(range(self.L)):
-            segs.append(("d%d/" % l, (lambda l=l: self._bwd_layer(l, True))))
+            segs.append(("d%d/" % l, (lambda l=l: self._bwd_layer_joined(l))))
         segs.append(("embedding_in/", lambda: self._bwd_embed(True)))
         return segs
 

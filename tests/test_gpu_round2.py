@@ -402,6 +402,39 @@ def test_segmented_training_step_equals_whole_step(use_graph):
     assert (outs[0][2] - outs[1][2]).abs().max().item() < 1e-6
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_side_stream_options_equal_default_step(use_graph):
+    """The two opt-in side-stream modes (SAKE_DEFER_DW: all weight-gradient contractions; SAKE_DEFER_REDUCE: only
+    their partial-sum reduction) change the schedule, not the step: same loss, gradients and updated parameters as
+    the default single-stream step, eager and as a CUDA graph."""
+    import sake_b200
+    from sake_b200.runner import ModelRunner
+    B, N, S = 24, 21, 6
+    rng = np.random.default_rng(5)
+    n_real = rng.integers(5, N + 1, B).astype(np.int32)
+    am = (np.arange(N)[None, :] < n_real[:, None]).astype(np.float32)
+    x = (rng.standard_normal((B, N, 3)) * 1.7).astype(np.float32) * am[..., None]
+    h = np.eye(S, dtype=np.float32)[rng.integers(0, S, (B, N))] * am[..., None]
+    y = rng.standard_normal(B).astype(np.float32)
+    params = _model_params(3, S, 9)
+    model = sake_b200.DenseSAKEModel(hidden_features=64, out_features=1, depth=3)
+    outs = []
+    for kw in ({}, {"defer_reduce": True}, {"defer_dw": True}):
+        run = ModelRunner(model, params, B, N, S, ragged=True, train=True, **kw)
+        run.load_inputs(_T(h), _T(x), target=_T(y), n_real=_T(n_real, torch.int32))
+        if use_graph:
+            run.capture()
+        for _ in range(2):                   # two steps: the slots of the side stream are reused
+            loss = run.train_step().clone()
+        torch.cuda.synchronize()
+        outs.append((loss, run.flat_grads.clone(), run.flat_params.clone()))
+    gmax = outs[0][1].abs().max().item()
+    for o in outs[1:]:
+        assert torch.allclose(outs[0][0], o[0], rtol=1e-6, atol=1e-7)
+        assert (outs[0][1] - o[1]).abs().max().item() < 1e-6 * gmax
+        assert (outs[0][2] - o[2]).abs().max().item() < 1e-6
+
+
 def test_log_gamma_gradient_is_zero():
     """log_gamma exists in the tree (checkpoint compatibility) but the dense layer never reads it
     (sake/layers.py:97-105 vs :107-235): its gradient is exactly zero through both host paths."""
