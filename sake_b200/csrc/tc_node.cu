@@ -8,6 +8,7 @@
 // TMA from a pre-swizzled image of all five matrices (26 chunks x 16 KB, L2 resident), one thread issues the
 // 12 MMAs.  Two accumulators of 64 TMEM columns alternate between consecutive layers.
 // Replaces the CUDA-core kernel k_node_post (generic_fwd.cu) when H = 64, A = 4.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -1042,6 +1043,14 @@ __global__ void __launch_bounds__(NT_TILE * HALVES + 32, SLOTS == 2 ? 2 : 1) k_t
   if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
+// tiles per SM up to which the one-CTA-per-SM configuration (4 weight slots, two threads per atom) is used: 2 for the
+// forward kernel, 4 for the backward kernel (measured: cfg3, 2.4 tiles per SM: backward 207 -> 182 us, forward 116 -> 119;
+// cfg5, 3 tiles per SM: forward 139 -> 150).  SAKE_NODE_DEEP overrides both (A/B switch).
+static int node_deep_factor(bool backward) {
+  static int f = -1;
+  if (f < 0) { const char* e = getenv("SAKE_NODE_DEEP"); f = e ? atoi(e) : 0; if (f < 0) f = 0; }
+  return f > 0 ? f : (backward ? 4 : 2);
+}
 static int node_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -1076,7 +1085,7 @@ int tc_node_post_bwd(const Dims& d, const SakeLayerParams& p, const float* h, co
   (void)nscratch;
   a.nbuf = g ? sc.nbuf : nullptr;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
-  const bool deep = tiles <= 2 * node_num_sms();        // few tiles: latency configuration (see NodePipe)
+  const bool deep = tiles <= node_deep_factor(true) * node_num_sms();        // few tiles: latency configuration (see NodePipe)
   // deep: 4 weight slots, two threads per atom (288 threads, one CTA per SM); else 2 slots, thread = atom, two CTAs per SM
   const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + (deep ? 2048 : 0) + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
@@ -1159,7 +1168,7 @@ int tc_node_post(const Dims& d, const SakeLayerParams& p, const float* h, const 
   a.b_v1 = p.vel0_bias; a.vel2 = p.vel2_kernel; a.wv = (d.update && d.spatial) ? p.v_mixing_kernel : nullptr;
   a.h_out = h_out; a.x_out = x_out; a.v_out = v_out; a.stash = sv.nstash;
   const int tiles = (d.R + NT_TILE - 1) / NT_TILE;
-  const bool deep = tiles <= 2 * node_num_sms();
+  const bool deep = tiles <= node_deep_factor(false) * node_num_sms();
   const size_t smem = 4 * NT_IMG + (deep ? 4 : 2) * NT_WCH + NT_VEC * sizeof(float) + 192 + (deep ? 2048 : 0) + 1024;
   static unsigned long long optin4 = 0, optin2 = 0;
   { const int rc = deep ? smem_optin(k_tc_node_post<4, 2>, smem, optin4) : smem_optin(k_tc_node_post<2, 1>, smem, optin2); if (rc) return rc; }
